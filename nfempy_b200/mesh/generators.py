@@ -1,0 +1,98 @@
+"""Synthetic simplex meshes laid out the way a gmsh file would be (boundary blocks first, domain last).
+
+gmsh is absent, so the benchmark workloads of SURVEY.md section 8(d) are built here: a unit cube cut into
+``n^3`` cubes x 6 Kuhn tetrahedra with interior vertices jittered, and a unit square cut into ``n^2 x 2``
+right triangles.  Physical tags follow the reference fixtures
+(R/examples/cosserat_elasticity/gmsh_files/ex_3/example_3_3d_l_0.msh: domain 1, sides 2..7).
+"""
+import itertools
+
+import numpy as np
+
+from .mesh import Mesh, TET_FACES, TRI_EDGES
+
+
+def box_tet_points_cells(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, lengths=(1.0, 1.0, 1.0), nz=None):
+    """Points ``[(n+1)^2 (nz+1), 3]`` and tets ``[6 n^2 nz, 4]`` of a Kuhn-subdivided box (``nz`` defaults to n)."""
+    nz = n if nz is None else nz
+    rng = np.random.default_rng(seed)
+    gx, gy, gz = np.meshgrid(np.arange(n + 1), np.arange(n + 1), np.arange(nz + 1), indexing="ij")
+    grid = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1)
+    dims = np.array([n, n, nz])
+    h = np.asarray(lengths, dtype=np.float64) / np.array([n, n, n])
+    points = grid * h
+    if jitter > 0.0:
+        interior = np.all((grid > 0) & (grid < dims), axis=1)
+        shift = rng.uniform(-jitter, jitter, size=points.shape) * h
+        points[interior] += shift[interior]
+
+    def nid(i, j, k):
+        return (i * (n + 1) + j) * (nz + 1) + k
+
+    ci, cj, ck = np.meshgrid(np.arange(n), np.arange(n), np.arange(nz), indexing="ij")
+    ci, cj, ck = ci.ravel(), cj.ravel(), ck.ravel()
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        corner = [np.stack([ci, cj, ck], axis=1)]
+        for axis in perm:
+            step = np.zeros(3, dtype=np.int64)
+            step[axis] = 1
+            corner.append(corner[-1] + step)
+        tets.append(np.stack([nid(c[:, 0], c[:, 1], c[:, 2]) for c in corner], axis=1))
+    # cube-major order: the 6 tets of a cube are consecutive
+    tets = np.stack(tets, axis=1).reshape(-1, 4)
+    if shuffle_local_nodes:
+        keys = rng.random(tets.shape)
+        tets = np.take_along_axis(tets, np.argsort(keys, axis=1), axis=1)
+    return points, tets.astype(np.int64), grid, dims
+
+
+def box_tet_mesh(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, nz=None, lengths=(1.0, 1.0, 1.0)):
+    """``Mesh`` of the Kuhn box: six boundary triangle blocks (tags 2..7), then the tets (tag 1)."""
+    points, tets, grid, dims = box_tet_points_cells(n, jitter, seed, shuffle_local_nodes, lengths, nz)
+    faces = tets[:, TET_FACES].reshape(-1, 3)
+    fg = grid[faces]  # [nf, 3 nodes, 3 coords]
+    blocks = []
+    # south y=0 (2), east x=n (3), north y=n (4), west x=0 (5), top z=nz (6), bottom z=0 (7)
+    sides = [(2, 1, 0), (3, 0, dims[0]), (4, 1, dims[1]), (5, 0, 0), (6, 2, dims[2]), (7, 2, 0)]
+    for tag, axis, value in sides:
+        on = np.all(fg[:, :, axis] == value, axis=1)
+        tri = faces[on]
+        blocks.append(("triangle", tri, np.full(len(tri), tag, dtype=np.int64)))
+    blocks.append(("tetra", tets, np.ones(len(tets), dtype=np.int64)))
+    mesh = Mesh.from_arrays(3, points, blocks)
+    mesh.build_conformal_mesh()
+    return mesh
+
+
+def square_tri_mesh(n, jitter=0.0, seed=1234):
+    """Unit square, ``n x n x 2`` right triangles; boundary line blocks tags 2..5, triangles tag 1."""
+    rng = np.random.default_rng(seed)
+    gx, gy = np.meshgrid(np.arange(n + 1), np.arange(n + 1), indexing="ij")
+    grid = np.stack([gx.ravel(), gy.ravel()], axis=1)
+    h = 1.0 / n
+    points = np.zeros((len(grid), 3))
+    points[:, :2] = grid * h
+    if jitter > 0.0:
+        interior = np.all((grid > 0) & (grid < n), axis=1)
+        shift = rng.uniform(-jitter, jitter, size=(len(grid), 2)) * h
+        points[interior, :2] += shift[interior]
+
+    def nid(i, j):
+        return i * (n + 1) + j
+
+    ci, cj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    ci, cj = ci.ravel(), cj.ravel()
+    lower = np.stack([nid(ci, cj), nid(ci + 1, cj), nid(ci + 1, cj + 1)], axis=1)
+    upper = np.stack([nid(ci, cj), nid(ci + 1, cj + 1), nid(ci, cj + 1)], axis=1)
+    tris = np.stack([lower, upper], axis=1).reshape(-1, 3).astype(np.int64)
+    edges = tris[:, TRI_EDGES].reshape(-1, 2)
+    eg = grid[edges]
+    blocks = []
+    for tag, axis, value in [(2, 1, 0), (3, 0, n), (4, 1, n), (5, 0, 0)]:
+        on = np.all(eg[:, :, axis] == value, axis=1)
+        blocks.append(("line", edges[on], np.full(int(on.sum()), tag, dtype=np.int64)))
+    blocks.append(("triangle", tris, np.ones(len(tris), dtype=np.int64)))
+    mesh = Mesh.from_arrays(2, points, blocks)
+    mesh.build_conformal_mesh()
+    return mesh

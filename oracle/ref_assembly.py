@@ -1,0 +1,81 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+Restates the reference scatter and the PETSc object it fills:
+
+* ``scatter_form`` / ``scatter_bc_form`` -- R/src/assembly/ScatterFormData.py:5-25, 36-56: residual added dof by dof,
+  Jacobian added entry by entry (all ``n_loc^2`` pairs, exact zeros included, row-major order);
+* ``DokMatrix``    -- ``PETSc.Mat().createAIJ([n, n])`` + ``setValue(..., addv=True)`` + ``assemble()`` +
+  ``getValuesCSR()`` as described in SURVEY.md A.6: additions happen in call order, columns come out sorted per
+  row, explicitly inserted zeros stay in the pattern, indices are 32-bit.  petsc4py is absent, so this is a
+  dictionary of keys.
+"""
+import numpy as np
+
+
+class DokMatrix:
+    def __init__(self, n):
+        self.n = n
+        self.data = {}
+
+    def setValue(self, row, col, value, addv=True):
+        key = (int(row), int(col))
+        if addv:
+            self.data[key] = self.data.get(key, 0.0) + float(value)
+        else:
+            self.data[key] = float(value)
+
+    def scale(self, a):
+        for k in self.data:
+            self.data[k] *= a
+
+    def getValuesCSR(self):
+        keys = sorted(self.data.keys())
+        indptr = np.zeros(self.n + 1, dtype=np.int32)
+        for r, _ in keys:
+            indptr[r + 1] += 1
+        indptr = np.cumsum(indptr, dtype=np.int32)
+        indices = np.array([c for _, c in keys], dtype=np.int32)
+        data = np.array([self.data[k] for k in keys], dtype=np.float64)
+        return indptr, indices, data
+
+
+def scatter_lhs(jac_g, jac_l, dest):
+    data = jac_l.ravel()
+    row = np.repeat(dest, len(dest))
+    col = np.tile(dest, len(dest))
+    for k in range(data.shape[0]):
+        jac_g.setValue(row=row[k], col=col[k], value=data[k], addv=True)
+
+
+def scatter_rhs(res_g, res_l, dest):
+    for k, s in enumerate(dest):
+        res_g[s] += res_l[k]
+
+
+def scatter_form(space, form, functions, idx, res_g, jac_g, alpha):
+    dest = space.destination_indexes(idx)
+    r_l, j_l = form(space, functions, idx, alpha[dest])
+    scatter_rhs(res_g, r_l, dest)
+    scatter_lhs(jac_g, j_l, dest)
+
+
+def scatter_bc_form(space, form, functions, idx, res_g, jac_g, alpha):
+    dest = space.bc_destination_indexes(idx)
+    r_l, j_l = form(space, functions, idx, alpha[dest])
+    scatter_rhs(res_g, r_l, dest)
+    scatter_lhs(jac_g, j_l, dest)
+
+
+def assemble(space, forms, alpha=None):
+    """``forms``: list of ``(kind, form_fn, functions, n_items)`` with kind in {"form", "bc_form"}.
+    Returns ``(indptr, indices, data, rhs)`` exactly as the reference + PETSc would hand them to a solver."""
+    n = space.n_dof
+    alpha = np.zeros(n) if alpha is None else alpha
+    res_g = np.zeros(n)
+    jac_g = DokMatrix(n)
+    for kind, form, functions, n_items in forms:
+        scatter = scatter_form if kind == "form" else scatter_bc_form
+        for i in range(n_items):
+            scatter(space, form, functions, i, res_g, jac_g, alpha)
+    indptr, indices, data = jac_g.getValuesCSR()
+    return indptr, indices, data, res_g

@@ -1,0 +1,246 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+Per-cell restatement of the reference weak forms, one quadrature point at a time, in the reference's own order of
+operations.  The reference differentiates its residual with ``auto_diff`` (third-party, absent); every library form
+is linear in ``alpha`` (SURVEY.md section 8a row AD), so the Jacobian is obtained here the way forward-mode AD
+would: the homogeneous part of the residual is pushed through the same code for the ``n_loc`` unit vectors
+(``_linearise``).  That is exact for linear forms and keeps the arithmetic of each column identical to the residual's.
+
+Forms restated:
+* ``le_primal``               -- R/src/weak_forms/le_primal_weak_form.py:13-129
+* ``le_primal_bc_dirichlet``  -- R/src/weak_forms/le_primal_weak_form.py:131-176
+* ``le_primal_bc_neumann``    -- R/src/weak_forms/le_primal_weak_form.py:179-221
+* ``laplace_primal``          -- R/src/weak_forms/laplace_primal_weak_form.py:10-74 (with ``quadrature[dim]``)
+* ``laplace_primal_bc_dirichlet`` -- R/src/weak_forms/laplace_primal_weak_form.py:77-157
+"""
+import numpy as np
+
+from . import ref_basis
+
+
+class RefElement:
+    """What ``space.elements[i]`` offers the forms: mapping + mapped basis of one cell."""
+
+    def __init__(self, space, cell_id, bc=False):
+        self.space = space
+        self.mesh = space.mesh
+        self.cell = space.mesh.cells[cell_id]
+        if bc:
+            self.family, self.k, self.disc = space.bc_family, space.bc_k_order, space.bc_discontinuous
+        else:
+            self.family, self.k, self.disc = space.family, space.k_order, space.discontinuous
+        if self.cell.dimension == 1 and space.generator_family in ("RT", "BDM", "N1E", "N2E"):
+            self.family = "Lagrange"
+
+    def evaluate_mapping(self, points):  # R/src/basis/finite_element.py:128-154
+        dim = self.cell.dimension
+        cell_points = self.mesh.points[self.cell.node_tags]
+        if dim == 0:
+            return ref_basis.evaluate_mapping(0, np.ones(1), cell_points)
+        phi = ref_basis.evaluate_linear_shapes(dim, points)
+        return ref_basis.evaluate_mapping(dim, phi, cell_points)
+
+    def evaluate_basis(self, points, jac, det_jac, inv_jac):  # R/src/basis/finite_element.py:156-186
+        dim = self.cell.dimension
+        if dim == 0:
+            return np.ones((1, 1, 1, 1))
+        tab = ref_basis.tabulate(self.family, dim, self.k, points, self.disc)
+        mapped = ref_basis.push_forward(self.family, tab[0], jac, det_jac, inv_jac)
+        if tab[0].shape == mapped.shape:
+            tab[0] = mapped
+        else:
+            tab = np.insert(tab, 2, 0, axis=3)
+            tab[0] = mapped
+        if self.family != "Lagrange" or self.k > 2:
+            from . import ref_hdiv
+
+            tab = ref_hdiv.permute_and_transform(tab, self)
+        return tab
+
+
+def _linearise(residual, alpha, n_dof):
+    """``r = residual(alpha, load=True)``; column ``j`` of the Jacobian = homogeneous residual of ``e_j``."""
+    r_el = residual(np.asarray(alpha, dtype=float), True)
+    j_el = np.zeros((n_dof, n_dof))
+    for j in range(n_dof):
+        e = np.zeros(n_dof)
+        e[j] = 1.0
+        j_el[:, j] = residual(e, False)
+    return r_el, j_el
+
+
+def _grad_phi(dim, inv_jac_i, tab, i):
+    rows = [inv_jac_i @ np.eye(3)[d] for d in range(dim)]
+    return (np.vstack(rows) @ tab[1 : tab.shape[0] + 1, i, :, 0]).T  # [nphi, dim]
+
+
+def le_primal(space, functions, iel, alpha):
+    u_space = space.discrete_spaces["u"]
+    nc = u_space.n_comp
+    el = RefElement(u_space, u_space.element_ids[iel])
+    dim = el.cell.dimension
+    points, weights = space.quadrature[dim]
+    x, jac, det_jac, inv_jac = el.evaluate_mapping(points)
+    tab = el.evaluate_basis(points, jac, det_jac, inv_jac)
+    n_phi = tab.shape[2]
+    n_dof = n_phi * nc
+    f_val = np.asarray(functions["rhs"](x[:, 0], x[:, 1], x[:, 2]))
+    lam = functions["lambda"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    mu = functions["mu"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    eye = np.identity(dim)
+
+    def residual(a, load):
+        el_form = np.zeros(n_dof)
+        if load:
+            for c in range(nc):
+                el_form[c : c + n_dof : nc] += det_jac * weights * tab[0, :, :, 0].T @ f_val[c]
+        for i, omega in enumerate(weights):
+            g = _grad_phi(dim, inv_jac[i], tab, i)
+            grad_uh = np.vstack([a[c : n_dof + c : nc] @ g for c in range(dim)])
+            eh = 0.5 * (grad_uh + grad_uh.T)
+            sh = 2.0 * mu[i] * eh + lam[i] * np.trace(eh) * eye
+            el_form = el_form + det_jac[i] * omega * (g @ sh.T).reshape((n_dof,))
+        return el_form
+
+    return _linearise(residual, alpha, n_dof)
+
+
+def _bc_setup(space, field, iel):
+    f_space = space.discrete_spaces[field]
+    el = RefElement(f_space, f_space.bc_element_ids[iel], bc=True)
+    dim = el.cell.dimension
+    points, weights = space.bc_quadrature[dim]
+    x, jac, det_jac, inv_jac = el.evaluate_mapping(points)
+    tab = el.evaluate_basis(points, jac, det_jac, inv_jac)
+    return f_space, el, weights, x, det_jac, tab
+
+
+def le_primal_bc_dirichlet(space, functions, iel, alpha):
+    u_space, el, weights, x, det_jac, tab = _bc_setup(space, "u", iel)
+    nc = u_space.n_comp
+    n_phi = tab.shape[2]
+    n_dof = n_phi * nc
+    j_el, r_el = np.zeros((n_dof, n_dof)), np.zeros(n_dof)
+    beta = 1.0e12
+    block = np.zeros((n_phi, n_phi))
+    for i, omega in enumerate(weights):
+        phi = tab[0, i, :, 0]
+        block += beta * det_jac[i] * omega * np.outer(phi, phi)
+    for c in range(nc):
+        res = np.zeros(n_phi)
+        for i, omega in enumerate(weights):
+            phi = tab[0, i, :, 0]
+            u_d = functions["u"](x[i, 0], x[i, 1], x[i, 2])
+            res -= beta * det_jac[i] * omega * u_d[c] * phi
+        r_el[c : c + n_dof : nc] += res
+        j_el[c : c + n_dof : nc, c : c + n_dof : nc] += block
+    return r_el, j_el
+
+
+def le_primal_bc_neumann(space, functions, iel, alpha):
+    u_space, el, weights, x, det_jac, tab = _bc_setup(space, "u", iel)
+    nc = u_space.n_comp
+    n_phi = tab.shape[2]
+    n_dof = n_phi * nc
+    j_el, r_el = np.zeros((n_dof, n_dof)), np.zeros(n_dof)
+    for c in range(nc):
+        res = np.zeros(n_phi)
+        for i, omega in enumerate(weights):
+            phi = tab[0, i, :, 0]
+            t_n = functions["t"](x[i, 0], x[i, 1], x[i, 2])
+            res += det_jac[i] * omega * t_n[c] * phi
+        r_el[c : c + n_dof : nc] += res
+    return r_el, j_el
+
+
+def laplace_primal(space, functions, iel, alpha):
+    p_space = space.discrete_spaces["p"]
+    nc = p_space.n_comp
+    el = RefElement(p_space, p_space.element_ids[iel])
+    dim = el.cell.dimension
+    points, weights = space.quadrature[dim]
+    x, jac, det_jac, inv_jac = el.evaluate_mapping(points)
+    tab = el.evaluate_basis(points, jac, det_jac, inv_jac)
+    n_dof = tab.shape[2] * nc
+    f_val = np.asarray(functions["rhs"](x[:, 0], x[:, 1], x[:, 2]))
+    phi_s_star = det_jac * weights * tab[0, :, :, 0].T
+
+    def residual(a, load):
+        el_form = np.zeros(n_dof)
+        if load:
+            for c in range(nc):
+                el_form[c : c + n_dof : nc] -= (phi_s_star @ f_val[c].T).ravel()
+        for i, omega in enumerate(weights):
+            xv = x[i]
+            g = _grad_phi(dim, inv_jac[i], tab, i)
+            grad_uh = (a @ g) * functions["kappa"](xv[0], xv[1], xv[2])
+            el_form = el_form + det_jac[i] * omega * (g @ grad_uh.T).reshape((n_dof,))
+        return el_form
+
+    return _linearise(residual, alpha, n_dof)
+
+
+def transform_lower_to_higher(points, cell, neigh_cell):  # R/src/basis/parametric_transformation.py:8-98
+    dim = cell.dimension
+    facet_index = neigh_cell.sub_cells_ids[dim].tolist().index(cell.id)
+    ref_vertices = np.concatenate([np.zeros((1, dim + 1)), np.eye(dim + 1)], axis=0)
+    facet = list(ref_basis.SUB[dim + 1][dim][facet_index])
+    sub = neigh_cell.node_tags[facet]
+    own = cell.node_tags
+    if tuple(own) != tuple(sub):
+        index_map = dict(zip(sub.tolist(), facet))
+        facet = [index_map[k] for k in own.tolist()]
+    if dim == 0:
+        return np.array([ref_vertices[facet[0]] * xi for xi in points])
+    if dim == 1:
+        return np.array([ref_vertices[facet[0]] * (1 - xi) + ref_vertices[facet[1]] * xi for xi in points[:, 0]])
+    return np.array(
+        [
+            ref_vertices[facet[0]] * (1 - xi - eta) + ref_vertices[facet[1]] * xi + ref_vertices[facet[2]] * eta
+            for xi, eta in points
+        ]
+    )
+
+
+def laplace_primal_bc_dirichlet(space, functions, iel, alpha):
+    p_space, el, weights, x, det_jac, _ = _bc_setup(space, "p", iel)
+    nc = p_space.n_comp
+    cell = el.cell
+    points, _ = space.bc_quadrature[cell.dimension]
+    neigh_id = p_space.first_neighbour(cell.id)
+    neigh = RefElement(p_space, neigh_id)
+    mapped = transform_lower_to_higher(points, cell, neigh.cell)
+    _, jac0, det0, inv0 = neigh.evaluate_mapping(mapped)
+    tr_tab = neigh.evaluate_basis(mapped, jac0, det0, inv0)
+    ned = ref_basis.num_entity_dofs(neigh.family, neigh.cell.dimension, neigh.k, neigh.disc)
+    # dof index of the first dof of each sub-entity of the neighbour (R/...laplace_primal_weak_form.py:119-131)
+    first_dof, run = [], 0
+    for d, per in enumerate(ned):
+        first_dof.append([])
+        for n in per:
+            first_dof[d].append(run if n > 0 else None)
+            run += n
+    dof_idx = []
+    for d in range(cell.dimension + 1):
+        for sid in cell.sub_cells_ids[d]:
+            idx = neigh.cell.sub_cells_ids[d].tolist().index(sid)
+            if first_dof[d][idx] is not None:
+                dof_idx.append(first_dof[d][idx])
+    dof_idx = np.array(dof_idx)
+    n_phi = len(dof_idx)
+    n_dof = n_phi * nc
+    j_el, r_el = np.zeros((n_dof, n_dof)), np.zeros(n_dof)
+    beta = 1.0e12
+    block = np.zeros((n_phi, n_phi))
+    for i, omega in enumerate(weights):
+        phi = tr_tab[0, i, dof_idx, 0]
+        block += beta * det_jac[i] * omega * np.outer(phi, phi)
+    for c in range(nc):
+        res = np.zeros(n_phi)
+        for i, omega in enumerate(weights):
+            phi = tr_tab[0, i, dof_idx, 0]
+            p_d = functions["p"](x[i, 0], x[i, 1], x[i, 2])
+            res -= beta * det_jac[i] * omega * p_d[c] * phi
+        r_el[c : c + n_dof : nc] += res
+        j_el[c : c + n_dof : nc, c : c + n_dof : nc] += block
+    return r_el, j_el
