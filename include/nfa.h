@@ -1,0 +1,142 @@
+/* nfa.h -- C ABI of the B200 finite-element assembly library (libnfa.so).
+ *
+ * Drop-in boundary for the assembly hot path of OmarDuran/nfempy (R = the reference tree).  The reference is
+ * pure Python; the interface each entry point replaces is cited as R/<file>:<lines>.  All pointers named
+ * d_* are DEVICE pointers owned by the caller (the Python host passes torch tensors' data_ptr()); the library
+ * allocates nothing the caller does not pass in except the opaque plan objects.  Every function returns 0 on
+ * success and a non-zero status otherwise, with the text available from nfa_last_error().  All work is
+ * stream-ordered on the caller's stream (a cudaStream_t passed as void*; NULL = default stream).
+ *
+ * Index types: int32 for dof and node indices (PETSc AIJ indices are 32-bit, R/.../md_primal_cosserat.py:415),
+ * int64 for counts.  All floating point is IEEE double.
+ */
+#ifndef NFA_H
+#define NFA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nfa_plan nfa_plan;   /* scalar sparsity plan: CSR pattern + deterministic gather lists */
+typedef struct nfa_bplan nfa_bplan; /* node-block plan for the fused H1 vector/scalar assembly */
+typedef void *nfa_stream;           /* cudaStream_t */
+
+int nfa_version(void);
+const char *nfa_last_error(void);
+/* number of kernels launched by this library since load (bench.py reports it as gpu_launches) */
+int64_t nfa_launch_count(void);
+/* when enabled, the fused assembly kernel is bracketed by CUDA events on its own stream; nfa_timing_read
+ * synchronises, returns the summed device time (ms) and the number of bracketed launches, and resets */
+void nfa_timing_enable(int on);
+int nfa_timing_read(double *total_ms, int64_t *count);
+
+/* ---- K1 geometry: replaces evaluate_mapping + _compute_det_and_pseudo_inverse, R/src/geometry/mapping.py:23-55.
+ * Simplex cells are affine, so J, |det| and J^+ are per cell (the reference recomputes them per quadrature
+ * point by QR).  dim = 1, 2, 3 (cell embedded in 3-space).  jac [n,3,dim], det [n] (always >= 0),
+ * inv [n,dim,3] = Moore-Penrose inverse.  Any output pointer may be NULL. */
+int nfa_geom_simplex(int dim, const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells,
+                     double *d_jac, double *d_det, double *d_inv, nfa_stream stream);
+
+/* x_q = sum_v phi_v(xi_q) X_v: physical quadrature points handed to the Python coefficient callables,
+ * R/src/geometry/mapping.py:46.  shape1 [n_q, dim+1] = P1 shape values at the reference points; x [n,n_q,3]. */
+int nfa_map_points(int dim, int n_q, const double *d_shape1, const double *d_coords,
+                   const int32_t *d_cell_nodes, int64_t n_cells, double *d_x, nfa_stream stream);
+
+/* ---- K2 H1 volume forms, general coefficients (quadrature loop as in the reference).
+ * tab [1+dim, n_q, n_phi]: reference values (slab 0) and reference gradients (slabs 1..dim) of the scalar
+ * Lagrange basis, weights [n_q].  Coefficients are addressed as c[cell*stride_cell + q*stride_q] so that a
+ * constant (0,0), a per-cell (1,0) and a per-point (n_q,1) array all fit.  d_f [n, n_q, n_comp] or NULL.
+ * d_alpha (global vector) + d_dest [n, n_loc] or NULL for alpha = 0.  Outputs: Ke [n, n_loc, n_loc] row-major,
+ * re [n, n_loc]; local dof = basis * n_comp + comp.
+ *
+ * nfa_local_h1_elasticity: LEPrimalWeakForm.evaluate_form, R/src/weak_forms/le_primal_weak_form.py:13-129
+ *   (r = +int phi.f + int sigma(u_h):grad phi, J = dr/dalpha), n_comp = dim.
+ * nfa_local_h1_laplace: LaplacePrimalWeakForm.evaluate_form, R/src/weak_forms/laplace_primal_weak_form.py:10-74
+ *   (r = -int phi f + int kappa grad u_h . grad phi), n_comp = 1. */
+int nfa_local_h1_elasticity(int dim, int n_phi, int n_q, const double *d_tab, const double *d_weights,
+                            const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells,
+                            const double *d_lambda, int64_t lambda_stride_cell, int64_t lambda_stride_q,
+                            const double *d_mu, int64_t mu_stride_cell, int64_t mu_stride_q,
+                            const double *d_f, const double *d_alpha, const int32_t *d_dest,
+                            double *d_Ke, double *d_re, nfa_stream stream);
+int nfa_local_h1_laplace(int dim, int n_phi, int n_q, const double *d_tab, const double *d_weights,
+                         const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells,
+                         const double *d_kappa, int64_t kappa_stride_cell, int64_t kappa_stride_q,
+                         const double *d_f, const double *d_alpha, const int32_t *d_dest,
+                         double *d_Ke, double *d_re, nfa_stream stream);
+
+/* load vector only: re [n, n_phi*n_comp] = sign * int phi_a f_i (the load term of the two forms above; used by
+ * the fused path, whose matrix kernel never forms local data).  tab0 [n_q, n_phi], f [n, n_q, n_comp]. */
+int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *d_tab0, const double *d_weights,
+                      const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_f,
+                      double sign, double *d_re, nfa_stream stream);
+
+/* ---- K5 H1 facet (boundary) forms on (dim-1)-simplices embedded in 3-space.
+ * J = beta * int phi phi^T per component, r = r_sign * beta * int g_c phi  (g [n, n_q, n_comp] host-evaluated).
+ * Dirichlet penalty (beta = 1e12, r_sign = -1): LEPrimalWeakFormBCDirichlet R/.../le_primal_weak_form.py:131-176,
+ * LaplacePrimalWeakFormBCDirichlet R/.../laplace_primal_weak_form.py:77-157.  Neumann load (with_matrix = 0,
+ * beta = 1, r_sign = +1): LEPrimalWeakFormBCNeumann R/.../le_primal_weak_form.py:179-221.
+ * facet_dim = dim-1 (0 = point facets of 1-D cells). */
+int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp, const double *d_tab0,
+                       const double *d_weights, const double *d_coords, const int32_t *d_facet_nodes,
+                       int64_t n_facets, const double *d_g, double beta, double r_sign, int with_matrix,
+                       double *d_Ke, double *d_re, nfa_stream stream);
+
+/* ---- K6 sparsity plan: replaces the implicit pattern growth of PETSc Mat.setValue(..., addv=True) without
+ * preallocation (R/src/assembly/ScatterFormData.py:5-11): the pattern is the union of
+ * dest x dest over all items of all segments ("full" policy: explicit zeros kept), columns sorted per row.
+ * A segment is one form's destination table d_dest[s] = int32 [n_items[s], n_loc[s]].
+ * base == NULL: the pattern is defined by these segments.  base != NULL: the segments are merged INTO the
+ * pattern of `base` (every pair must already be present, else an error) -- used to add boundary forms to a
+ * pattern produced by the fused path.  seg_flags[s] & 1: the segment contributes matrix entries (otherwise
+ * right-hand-side rows only, e.g. the volume load of the fused path); seg_flags == NULL means all do. */
+int nfa_plan_create(int64_t n_dof, int n_segments, const int32_t *const *d_dest, const int64_t *n_items,
+                    const int32_t *n_loc, const int32_t *seg_flags, const nfa_plan *base, nfa_plan **out,
+                    nfa_stream stream);
+/* adopt the pattern of a node-block plan (no gather lists) */
+int nfa_plan_from_bplan(const nfa_bplan *bp, nfa_plan **out, nfa_stream stream);
+void nfa_plan_destroy(nfa_plan *plan);
+int64_t nfa_plan_nnz(const nfa_plan *plan);
+int64_t nfa_plan_n_dof(const nfa_plan *plan);
+int64_t nfa_plan_bytes(const nfa_plan *plan);
+/* copy the pattern out: indptr int32 [n_dof+1], indices int32 [nnz] (device) -- A.getValuesCSR() index arrays */
+int nfa_plan_csr(const nfa_plan *plan, int32_t *d_indptr, int32_t *d_indices, nfa_stream stream);
+
+/* ---- K7 deterministic reduce: replaces the n_loc^2 setValue calls and res_g[dest[k]] += res_l[k]
+ * (R/src/assembly/ScatterFormData.py:5-25).  Every CSR value / rhs row sums its contributions in ascending
+ * (segment, item, local row, local col) order = the reference's call order; no atomics.
+ * d_Ke[s] [n_items[s], n_loc[s]^2], d_re[s] [n_items[s], n_loc[s]] (either array may be NULL to skip).
+ * accumulate != 0 adds to the existing d_vals / d_rhs (PETSc ADD_VALUES across scatter_forms calls). */
+int nfa_plan_reduce(const nfa_plan *plan, const double *const *d_Ke, const double *const *d_re,
+                    int accumulate_vals, double *d_vals, int accumulate_rhs, double *d_rhs,
+                    nfa_stream stream);
+
+/* y (+)= A x on the plan's pattern, one warp per row, fixed order (residual term J.alpha of the fused path) */
+int nfa_csr_spmv(const nfa_plan *plan, const double *d_vals, const double *d_x, int accumulate, double *d_y,
+                 nfa_stream stream);
+
+/* ---- fused H1 path (affine cells, cell-wise constant coefficients): local B^T D B contraction and the global
+ * reduce in ONE kernel, no local matrices in HBM.  The node-block plan groups the n_comp x n_comp blocks of the
+ * CSR by (row node, col node); d_node_dest int32 [n_cells, n_phi] = dest[:, ::n_comp] / n_comp. */
+int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const int32_t *d_node_dest, int64_t n_cells,
+                     nfa_bplan **out, nfa_stream stream);
+void nfa_bplan_destroy(nfa_bplan *bp);
+int64_t nfa_bplan_nnz(const nfa_bplan *bp);
+int64_t nfa_bplan_bytes(const nfa_bplan *bp);
+/* Mref [n_phi, n_phi, dim, dim] = int_ref d_k phi_a d_l phi_b (exact reference stiffness tensor).
+ * lambda, mu, kappa: per cell (stride 1) or constant (stride 0).  Writes ALL nnz values of the pattern. */
+int nfa_assemble_h1_elasticity_affine(const nfa_bplan *bp, int dim, const double *d_Mref,
+                                      const double *d_coords, const int32_t *d_cell_nodes,
+                                      const double *d_lambda, int64_t lambda_stride,
+                                      const double *d_mu, int64_t mu_stride,
+                                      double *d_vals, nfa_stream stream);
+int nfa_assemble_h1_laplace_affine(const nfa_bplan *bp, int dim, const double *d_Mref,
+                                   const double *d_coords, const int32_t *d_cell_nodes,
+                                   const double *d_kappa, int64_t kappa_stride,
+                                   double *d_vals, nfa_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFA_H */

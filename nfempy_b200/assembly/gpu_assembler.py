@@ -1,0 +1,279 @@
+"""``GPUAssembler``: drop-in for the reference's ``SequentialAssembler`` (R/src/assembly/SequentialAssembler.py:13-86).
+
+Same constructor ``(space, jacobian, residual)``, same ``form_to_input_list`` dictionary
+``{name: [form_type, sequence, weak_form, alpha]}`` and same ``scatter_forms(measure_time_q=False)``; the
+per-cell Python loop + ``Mat.setValue`` calls (R/src/assembly/ScatterFormData.py:5-56) are replaced by
+
+1. one sparsity plan per form list (built once, reused across Newton / time steps),
+2. one local-kernel launch per form (or the fused kernel for affine H1 forms with cell-wise coefficients),
+3. one deterministic reduce into the CSR values and the right-hand side.
+
+``residual`` stays a numpy vector mutated in place (``+=``), ``jacobian`` is a ``CSRMatrix`` (PETSc ``Mat``
+shim).  ``assemble()`` is the one-shot convenience returning ``(indptr, indices, data, rhs)``.
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..device import space_device
+from ..weak_forms.weak_form import BatchedWeakForm
+from .csr_matrix import CSRMatrix
+
+_SUPPORTED = ("form", "bc_form")
+_KNOWN = (
+    "form", "bc_form", "interface_form", "bc_interface_form", "time_dependent_form", "time_dependent_bc_form",
+)
+
+
+def _as_items(sequence, n_total):
+    """None when the sequence is exactly ``range(n_total)``, else an int64 index array."""
+    if isinstance(sequence, range) and sequence == range(n_total):
+        return None
+    items = np.asarray(list(sequence) if not isinstance(sequence, np.ndarray) else sequence, dtype=np.int64)
+    if items.ndim != 1:
+        raise ValueError("GPUAssembler: sequence must be a flat list of element indices")
+    if len(items) == n_total and np.array_equal(items, np.arange(n_total)):
+        return None
+    if len(items) and (items.min() < 0 or items.max() >= n_total):
+        raise IndexError("GPUAssembler: element index out of range")
+    return items
+
+
+class _Plan:
+    """Owns the native plan handles of one form list."""
+
+    def __init__(self):
+        self.plan = None  # nfa_plan* with gather lists
+        self.pattern = None  # nfa_plan* adopting the block plan's pattern (fused mode)
+        self.bplan = None
+        self.fused_index = None
+        self.n_dof = 0
+        self.nnz = 0
+        self.indptr = None
+        self.indices = None
+        self.build_seconds = 0.0
+        self.keep = []
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            if self.plan:
+                lib.nfa_plan_destroy(self.plan)
+            if self.pattern:
+                lib.nfa_plan_destroy(self.pattern)
+            if self.bplan:
+                lib.nfa_bplan_destroy(self.bplan)
+        except Exception:
+            pass
+
+
+class GPUAssembler:
+    def __init__(self, space, jacobian=None, residual=None, device=None, allow_fused=True):
+        self.space = space
+        self.jacobian = jacobian if jacobian is not None else CSRMatrix(getattr(space, "n_dof", None))
+        self.residual = residual
+        self.device = device
+        self.allow_fused = allow_fused
+        self._form_to_input_list = None
+        self._plans = {}
+        self.last_timings = {}
+
+    @property
+    def form_to_input_list(self):
+        return self._form_to_input_list
+
+    @form_to_input_list.setter
+    def form_to_input_list(self, value):
+        self._form_to_input_list = value
+
+    # ------------------------------------------------------------------------------------------
+    def _entries(self):
+        if not self._form_to_input_list:
+            raise ValueError("GPUAssembler: form_to_input_list is not set")
+        out = []
+        for name, input_list in self._form_to_input_list.items():
+            form_type = input_list[0]
+            if form_type not in _KNOWN:
+                raise KeyError(form_type)
+            if form_type not in _SUPPORTED:
+                raise NotImplementedError("GPUAssembler: form type %r has no CUDA kernel yet" % form_type)
+            _, sequence, form, alpha = input_list[:4]
+            if not isinstance(form, BatchedWeakForm):
+                raise NotImplementedError(
+                    "GPUAssembler: %s has no CUDA kernel (no CPU fallback is provided)" % type(form).__name__
+                )
+            if form.form_kind != form_type:
+                raise ValueError("GPUAssembler: %s is a %r, listed as %r" % (type(form).__name__, form.form_kind, form_type))
+            items = _as_items(sequence, form.n_items_total())
+            out.append((name, form_type, items, form, alpha))
+        return out
+
+    @staticmethod
+    def _dest_dev(dev, form, items):
+        full = dev.dest() if form.form_kind == "form" else dev.bc_dest()
+        if items is None:
+            return full
+        idx = torch.as_tensor(items).to(full.device)
+        return full.index_select(0, idx).contiguous()
+
+    def _plan_key(self, entries, fused_index):
+        key = [self.space.n_dof, self.space.dof_shift, fused_index]
+        for name, kind, items, form, _ in entries:
+            key.append((kind, id(form.space), type(form).__name__, None if items is None else items.tobytes()))
+        return tuple(key)
+
+    def _build_plan(self, dev, entries, dests, fused_index):
+        t0 = time.perf_counter()
+        lib = _lib.load()
+        p = _Plan()
+        p.n_dof = int(self.space.n_dof)
+        p.fused_index = fused_index
+        stream = _lib.stream_ptr()
+        nseg = len(entries)
+        dest_ptrs = (ctypes.c_void_p * nseg)(*[d.data_ptr() for d in dests])
+        n_items = (ctypes.c_int64 * nseg)(*[int(d.shape[0]) for d in dests])
+        n_loc = (ctypes.c_int32 * nseg)(*[int(d.shape[1]) for d in dests])
+        handle = ctypes.c_void_p()
+        if fused_index is None:
+            _lib.check(
+                lib.nfa_plan_create(p.n_dof, nseg, dest_ptrs, n_items, n_loc, None, None, ctypes.byref(handle), stream),
+                "nfa_plan_create",
+            )
+            p.plan = handle
+        else:
+            form = entries[fused_index][3]
+            s = form._field()
+            nc = s.n_comp
+            node_dest = (dests[fused_index][:, ::nc] // nc).contiguous()
+            if p.n_dof % nc != 0:
+                raise _lib.NfaError("fused path: n_dof is not a multiple of n_comp")
+            bh = ctypes.c_void_p()
+            _lib.check(
+                lib.nfa_bplan_create(
+                    p.n_dof // nc, int(node_dest.shape[1]), nc, _lib.ptr(node_dest), int(node_dest.shape[0]),
+                    ctypes.byref(bh), stream,
+                ),
+                "nfa_bplan_create",
+            )
+            p.bplan = bh
+            ph = ctypes.c_void_p()
+            _lib.check(lib.nfa_plan_from_bplan(bh, ctypes.byref(ph), stream), "nfa_plan_from_bplan")
+            p.pattern = ph
+            flags = (ctypes.c_int32 * nseg)(*[0 if i == fused_index else 1 for i in range(nseg)])
+            _lib.check(
+                lib.nfa_plan_create(p.n_dof, nseg, dest_ptrs, n_items, n_loc, flags, ph, ctypes.byref(handle), stream),
+                "nfa_plan_create",
+            )
+            p.plan = handle
+        p.nnz = int(lib.nfa_plan_nnz(p.plan))
+        p.indptr = torch.empty(p.n_dof + 1, dtype=torch.int32, device=dev.device)
+        p.indices = torch.empty(p.nnz, dtype=torch.int32, device=dev.device)
+        _lib.check(lib.nfa_plan_csr(p.plan, _lib.ptr(p.indptr), _lib.ptr(p.indices), stream), "nfa_plan_csr")
+        torch.cuda.synchronize(dev.device)
+        p.build_seconds = time.perf_counter() - t0
+        return p
+
+    # ------------------------------------------------------------------------------------------
+    def prepare(self):
+        """Evaluates the coefficient callables, uploads them and builds (or fetches) the sparsity plan.
+        Returns the state ``run`` consumes; split out so that repeated assemblies reuse it."""
+        dev = space_device(self.space, self.device)
+        entries = self._entries()
+        datas = [form.prepare(dev, items) for (_, _, items, form, _) in entries]
+        dests = [self._dest_dev(dev, form, items) for (_, _, items, form, _) in entries]
+        fused_index = None
+        if self.allow_fused:
+            for i, ((_, kind, _, form, _), data) in enumerate(zip(entries, datas)):
+                if kind == "form" and form.fused_spec(data) is not None and len(self.space.discrete_spaces) == 1:
+                    fused_index = i
+                    break
+        key = self._plan_key(entries, fused_index)
+        if key not in self._plans:
+            self._plans[key] = self._build_plan(dev, entries, dests, fused_index)
+        plan = self._plans[key]
+        return dev, entries, datas, dests, plan, key
+
+    def run(self, state, rhs_dev=None):
+        """Launches the kernels of one assembly.  Adds into ``self.jacobian`` and returns the device residual."""
+        dev, entries, datas, dests, plan, key = state
+        lib = _lib.load()
+        stream = _lib.stream_ptr()
+        jac = self.jacobian
+        if jac.plan_key != key:
+            if jac.plan_key is not None and not jac.is_zero:
+                raise _lib.NfaError("GPUAssembler: the jacobian holds values assembled on a different sparsity plan")
+            jac.bind_pattern(key, plan.n_dof, plan.indptr, plan.indices)
+        if rhs_dev is None:
+            rhs_dev = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
+        nseg = len(entries)
+        Ke_list, re_list, keep = [None] * nseg, [None] * nseg, []
+        for i, ((_, _, _, form, alpha), data, dest) in enumerate(zip(entries, datas, dests)):
+            alpha_dev = None
+            if alpha is not None and np.any(np.asarray(alpha) != 0.0):
+                alpha_dev = torch.as_tensor(np.ascontiguousarray(alpha, dtype=np.float64)).to(dev.device)
+            if i == plan.fused_index:
+                spec = form.fused_spec(data)
+                target = jac.values_dev if jac.is_zero else torch.empty_like(jac.values_dev)
+                args = [plan.bplan, data.dim, _lib.ptr(form.mref(dev)), _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes)]
+                for c in spec["coefs"]:
+                    args += [_lib.ptr(c[0]), c[1]]
+                args += [_lib.ptr(target), stream]
+                _lib.check(getattr(lib, spec["kernel"])(*args), spec["kernel"])
+                if alpha_dev is not None:
+                    _lib.check(
+                        lib.nfa_csr_spmv(plan.pattern, _lib.ptr(target), _lib.ptr(alpha_dev), 1, _lib.ptr(rhs_dev), stream),
+                        "nfa_csr_spmv",
+                    )
+                if target is not jac.values_dev:
+                    jac.values_dev.add_(target)
+                jac.is_zero = False
+                if data.f is not None:
+                    re = torch.empty((data.n_items, form.n_loc()), dtype=torch.float64, device=dev.device)
+                    form.launch_load(dev, data, re)
+                    re_list[i] = re
+                    keep.append(re)
+            else:
+                Ke, re = form.local_blocks(dev, data, alpha_dev, dest if alpha_dev is not None else None)
+                Ke_list[i], re_list[i] = Ke, re
+                keep += [Ke, re, alpha_dev]
+        ke_ptrs = (ctypes.c_void_p * nseg)(*[None if k is None else k.data_ptr() for k in Ke_list])
+        re_ptrs = (ctypes.c_void_p * nseg)(*[None if r is None else r.data_ptr() for r in re_list])
+        accumulate_vals = 0 if (jac.is_zero and plan.fused_index is None) else 1
+        _lib.check(
+            lib.nfa_plan_reduce(plan.plan, ke_ptrs, re_ptrs, accumulate_vals, _lib.ptr(jac.values_dev), 1, _lib.ptr(rhs_dev), stream),
+            "nfa_plan_reduce",
+        )
+        jac.is_zero = False
+        self._keep = keep  # buffers must outlive the stream-ordered kernels
+        return rhs_dev
+
+    def scatter_forms(self, measure_time_q=False):
+        t0 = time.perf_counter()
+        state = self.prepare()
+        t1 = time.perf_counter()
+        rhs_dev = self.run(state)
+        rhs = rhs_dev.cpu().numpy()
+        t2 = time.perf_counter()
+        if self.residual is None:
+            self.residual = np.zeros(len(rhs))
+        self.residual += rhs
+        self.last_timings = {"prepare_s": t1 - t0, "kernels_s": t2 - t1, "plan_build_s": state[4].build_seconds}
+        if measure_time_q:
+            print("GPUAssembler:: prepare (callables, upload, plan):", t1 - t0, "seconds")
+            print("GPUAssembler:: kernels + residual download:", t2 - t1, "seconds")
+
+    def assemble(self):
+        """One-shot: scatter all forms into a zeroed system and return ``(indptr, indices, data, rhs)``."""
+        self.jacobian.scale(0.0)
+        if self.residual is not None:
+            self.residual[:] = 0.0
+        self.scatter_forms()
+        indptr, indices, data = self.jacobian.getValuesCSR()
+        return indptr, indices, data, self.residual
+
+
+# the reference's name, so that `from assembly.SequentialAssembler import SequentialAssembler` ports by import path
+SequentialAssembler = GPUAssembler

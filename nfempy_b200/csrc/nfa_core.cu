@@ -1,0 +1,413 @@
+// libnfa: error state, geometry (K1) and the quadrature-loop H1 local kernels (K2, K5).  sm_100a.
+#include <atomic>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "nfa_common.cuh"
+
+namespace nfa {
+static std::mutex g_err_mutex;
+static std::string g_err = "";
+static std::atomic<int64_t> g_launches{0};
+void set_error(const std::string &msg) {
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    g_err = msg;
+}
+void count_launch(int64_t n) { g_launches += n; }
+}  // namespace nfa
+
+using namespace nfa;
+
+extern "C" int nfa_version(void) { return 100; }
+extern "C" const char *nfa_last_error(void) {
+    std::lock_guard<std::mutex> lock(g_err_mutex);
+    static thread_local std::string copy;
+    copy = g_err;
+    return copy.c_str();
+}
+extern "C" int64_t nfa_launch_count(void) { return g_launches.load(); }
+
+// ---- optional device timing of the dominant kernel (bench.py's roofline leg) -------------------------------
+namespace nfa {
+static bool g_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+bool timing_enabled() { return g_timing; }
+void timing_begin(cudaStream_t s) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, s);
+    g_events.push_back({a, b});
+}
+void timing_end(cudaStream_t s) { cudaEventRecord(g_events.back().second, s); }
+}  // namespace nfa
+
+extern "C" void nfa_timing_enable(int on) { g_timing = on != 0; }
+extern "C" int nfa_timing_read(double *total_ms, int64_t *count) {
+    double total = 0.0;
+    for (auto &ev : g_events) {
+        if (cudaEventSynchronize(ev.second) != cudaSuccess) return fail("nfa_timing_read: event sync failed");
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev.first, ev.second);
+        total += ms;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    if (total_ms) *total_ms = total;
+    if (count) *count = (int64_t)g_events.size();
+    g_events.clear();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 geometry
+template <int DIM>
+__global__ void geom_kernel(const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
+                            int64_t n_cells, double *__restrict__ jac, double *__restrict__ det,
+                            double *__restrict__ inv) {
+    int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    double X[DIM + 1][3];
+    load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+    Geom<DIM> g;
+    compute_geom<DIM>(X, g);
+    if (jac)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) jac[(cell * 3 + r) * DIM + c] = g.J[r][c];
+    if (det) det[cell] = g.det;
+    if (inv)
+#pragma unroll
+        for (int c = 0; c < DIM; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) inv[(cell * DIM + c) * 3 + r] = g.Jinv[c][r];
+}
+
+extern "C" int nfa_geom_simplex(int dim, const double *coords, const int32_t *cell_nodes, int64_t n_cells,
+                                double *jac, double *det, double *inv, nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int block = 128, grid = grid_for(n_cells, block);
+    if (dim == 3)
+        geom_kernel<3><<<grid, block, 0, s>>>(coords, cell_nodes, n_cells, jac, det, inv);
+    else if (dim == 2)
+        geom_kernel<2><<<grid, block, 0, s>>>(coords, cell_nodes, n_cells, jac, det, inv);
+    else if (dim == 1)
+        geom_kernel<1><<<grid, block, 0, s>>>(coords, cell_nodes, n_cells, jac, det, inv);
+    else
+        return fail("nfa_geom_simplex: dim must be 1, 2 or 3");
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void map_points_kernel(int nv, int n_q, const double *__restrict__ shape1,
+                                  const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
+                                  int64_t n_cells, double *__restrict__ x) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = n_cells * n_q * 3;
+    if (idx >= total) return;
+    int r = (int)(idx % 3);
+    int q = (int)((idx / 3) % n_q);
+    int64_t cell = idx / (3 * (int64_t)n_q);
+    double acc = 0.0;
+    for (int v = 0; v < nv; ++v) {
+        int64_t n = cell_nodes[cell * nv + v];
+        acc += shape1[q * nv + v] * __ldg(coords + 3 * n + r);
+    }
+    x[idx] = acc;
+}
+
+extern "C" int nfa_map_points(int dim, int n_q, const double *shape1, const double *coords,
+                              const int32_t *cell_nodes, int64_t n_cells, double *x, nfa_stream stream) {
+    if (dim < 0 || dim > 3) return fail("nfa_map_points: dim must be 0..3");
+    if (n_cells == 0) return 0;
+    int64_t total = n_cells * n_q * 3;
+    map_points_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(dim + 1, n_q, shape1, coords,
+                                                                               cell_nodes, n_cells, x);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: H1 volume forms with a quadrature loop (general coefficients).  One warp per cell.
+// FORM 0: elasticity (n_comp = DIM), FORM 1: Laplace (n_comp = 1).
+struct Coef {
+    const double *p;
+    int64_t sc, sq;
+};
+
+constexpr int WARPS_PER_CTA = 4;
+
+template <int DIM, int FORM>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+    local_h1_kernel(int n_phi, int n_q, const double *__restrict__ tab, const double *__restrict__ weights,
+                    const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes, int64_t n_cells,
+                    Coef c0, Coef c1, const double *__restrict__ f, const double *__restrict__ alpha,
+                    const int32_t *__restrict__ dest, double *__restrict__ Ke, double *__restrict__ re) {
+    constexpr int NC = (FORM == 0) ? DIM : 1;
+    extern __shared__ double smem[];
+    const int n_loc = n_phi * NC;
+    // CTA-shared: tab [1+DIM][n_q][n_phi], weights [n_q]
+    double *s_tab = smem;
+    double *s_w = s_tab + (1 + DIM) * n_q * n_phi;
+    double *s_warp = s_w + n_q;
+    const int per_warp = n_q * n_phi * DIM + 2 * n_q + n_loc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *s_g = s_warp + warp * per_warp;  // [n_q][n_phi][DIM] physical gradients
+    double *s_c0 = s_g + n_q * n_phi * DIM;  // [n_q] w det * coef0 (lambda | kappa)
+    double *s_c1 = s_c0 + n_q;               // [n_q] w det * coef1 (mu)
+    double *s_a = s_c1 + n_q;                // [n_loc] local alpha
+
+    for (int i = threadIdx.x; i < (1 + DIM) * n_q * n_phi; i += blockDim.x) s_tab[i] = tab[i];
+    for (int i = threadIdx.x; i < n_q; i += blockDim.x) s_w[i] = weights[i];
+    __syncthreads();
+
+    for (int64_t cell = (int64_t)blockIdx.x * WARPS_PER_CTA + warp; cell < n_cells;
+         cell += (int64_t)gridDim.x * WARPS_PER_CTA) {
+        double X[DIM + 1][3];
+        load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+        Geom<DIM> g;
+        compute_geom<DIM>(X, g);
+        __syncwarp();
+        for (int i = lane; i < n_q * n_phi; i += 32) {
+            int q = i / n_phi, a = i - q * n_phi;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) v += g.Jinv[k][d] * s_tab[((1 + k) * n_q + q) * n_phi + a];
+                s_g[(q * n_phi + a) * DIM + d] = v;
+            }
+        }
+        for (int q = lane; q < n_q; q += 32) {
+            double wd = s_w[q] * g.det;
+            s_c0[q] = wd * c0.p[cell * c0.sc + q * c0.sq];
+            if (FORM == 0) s_c1[q] = wd * c1.p[cell * c1.sc + q * c1.sq];
+        }
+        if (alpha)
+            for (int i = lane; i < n_loc; i += 32) s_a[i] = alpha[dest[cell * n_loc + i]];
+        __syncwarp();
+
+        double *K = Ke + cell * (int64_t)n_loc * n_loc;
+        for (int e = lane; e < n_loc * n_loc; e += 32) {
+            int ra = e / n_loc, rb = e - ra * n_loc;
+            int a = ra / NC, i = ra - a * NC, b = rb / NC, j = rb - b * NC;
+            double acc = 0.0;
+            if (FORM == 0) {
+                for (int q = 0; q < n_q; ++q) {
+                    const double *ga = s_g + (q * n_phi + a) * DIM;
+                    const double *gb = s_g + (q * n_phi + b) * DIM;
+                    double t = s_c0[q] * ga[i] * gb[j] + s_c1[q] * ga[j] * gb[i];
+                    if (i == j) {
+                        double dot = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) dot += ga[d] * gb[d];
+                        t += s_c1[q] * dot;
+                    }
+                    acc += t;
+                }
+            } else {
+                for (int q = 0; q < n_q; ++q) {
+                    const double *ga = s_g + (q * n_phi + a) * DIM;
+                    const double *gb = s_g + (q * n_phi + b) * DIM;
+                    double dot = 0.0;
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) dot += ga[d] * gb[d];
+                    acc += s_c0[q] * dot;
+                }
+            }
+            K[e] = acc;
+        }
+        __syncwarp();
+        // residual: load (+ for elasticity, - for Laplace) + K alpha
+        for (int ra = lane; ra < n_loc; ra += 32) {
+            int a = ra / NC, i = ra - a * NC;
+            double acc = 0.0;
+            if (f) {
+                for (int q = 0; q < n_q; ++q)
+                    acc += s_w[q] * g.det * s_tab[q * n_phi + a] * f[(cell * n_q + q) * NC + i];
+                if (FORM == 1) acc = -acc;
+            }
+            if (alpha) {
+                double ka = 0.0;
+                for (int rb = 0; rb < n_loc; ++rb) ka += K[ra * n_loc + rb] * s_a[rb];
+                acc += ka;
+            }
+            re[cell * n_loc + ra] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+template <int DIM, int FORM>
+static int launch_local_h1(int n_phi, int n_q, const double *tab, const double *weights, const double *coords,
+                           const int32_t *cell_nodes, int64_t n_cells, Coef c0, Coef c1, const double *f,
+                           const double *alpha, const int32_t *dest, double *Ke, double *re, cudaStream_t s) {
+    constexpr int NC = (FORM == 0) ? DIM : 1;
+    int n_loc = n_phi * NC;
+    size_t smem = sizeof(double) * ((size_t)(1 + DIM) * n_q * n_phi + n_q +
+                                    (size_t)WARPS_PER_CTA * (n_q * n_phi * DIM + 2 * n_q + n_loc));
+    if (smem > 200 * 1024) return fail("nfa_local_h1: element too large for the shared-memory staging");
+    auto kern = local_h1_kernel<DIM, FORM>;
+    NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t ctas = (n_cells + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
+    kern<<<grid, WARPS_PER_CTA * 32, smem, s>>>(n_phi, n_q, tab, weights, coords, cell_nodes, n_cells, c0, c1, f,
+                                                alpha, dest, Ke, re);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nfa_local_h1_elasticity(int dim, int n_phi, int n_q, const double *tab, const double *weights,
+                                       const double *coords, const int32_t *cell_nodes, int64_t n_cells,
+                                       const double *lam, int64_t lsc, int64_t lsq, const double *mu, int64_t msc,
+                                       int64_t msq, const double *f, const double *alpha, const int32_t *dest,
+                                       double *Ke, double *re, nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (alpha && !dest) return fail("nfa_local_h1_elasticity: alpha given without dest");
+    Coef c0{lam, lsc, lsq}, c1{mu, msc, msq};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dim == 3)
+        return launch_local_h1<3, 0>(n_phi, n_q, tab, weights, coords, cell_nodes, n_cells, c0, c1, f, alpha, dest,
+                                     Ke, re, s);
+    if (dim == 2)
+        return launch_local_h1<2, 0>(n_phi, n_q, tab, weights, coords, cell_nodes, n_cells, c0, c1, f, alpha, dest,
+                                     Ke, re, s);
+    return fail("nfa_local_h1_elasticity: dim must be 2 or 3");
+}
+
+extern "C" int nfa_local_h1_laplace(int dim, int n_phi, int n_q, const double *tab, const double *weights,
+                                    const double *coords, const int32_t *cell_nodes, int64_t n_cells,
+                                    const double *kappa, int64_t ksc, int64_t ksq, const double *f,
+                                    const double *alpha, const int32_t *dest, double *Ke, double *re,
+                                    nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (alpha && !dest) return fail("nfa_local_h1_laplace: alpha given without dest");
+    Coef c0{kappa, ksc, ksq}, c1{nullptr, 0, 0};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dim == 3)
+        return launch_local_h1<3, 1>(n_phi, n_q, tab, weights, coords, cell_nodes, n_cells, c0, c1, f, alpha, dest,
+                                     Ke, re, s);
+    if (dim == 2)
+        return launch_local_h1<2, 1>(n_phi, n_q, tab, weights, coords, cell_nodes, n_cells, c0, c1, f, alpha, dest,
+                                     Ke, re, s);
+    if (dim == 1)
+        return launch_local_h1<1, 1>(n_phi, n_q, tab, weights, coords, cell_nodes, n_cells, c0, c1, f, alpha, dest,
+                                     Ke, re, s);
+    return fail("nfa_local_h1_laplace: dim must be 1, 2 or 3");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: facet mass / load.  One warp per facet.
+template <int FDIM>
+__global__ void __launch_bounds__(128)
+    local_h1_facet_kernel(int n_phi, int n_q, int n_comp, const double *__restrict__ tab0,
+                          const double *__restrict__ weights, const double *__restrict__ coords,
+                          const int32_t *__restrict__ facet_nodes, int64_t n_facets,
+                          const double *__restrict__ gval, double beta, double r_sign, int with_matrix,
+                          double *__restrict__ Ke, double *__restrict__ re) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_loc = n_phi * n_comp;
+    for (int64_t fc = (int64_t)blockIdx.x * 4 + warp; fc < n_facets; fc += (int64_t)gridDim.x * 4) {
+        double det = 1.0;
+        if constexpr (FDIM > 0) {
+            double X[FDIM + 1][3];
+            load_cell_coords<FDIM>(coords, facet_nodes, fc, X);
+            Geom<FDIM> g;
+            compute_geom<FDIM>(X, g);
+            det = g.det;
+        }
+        if (Ke) {
+            double *K = Ke + fc * (int64_t)n_loc * n_loc;
+            for (int e = lane; e < n_loc * n_loc; e += 32) {
+                int ra = e / n_loc, rb = e - ra * n_loc;
+                int a = ra / n_comp, i = ra - a * n_comp, b = rb / n_comp, j = rb - b * n_comp;
+                double acc = 0.0;
+                if (with_matrix && i == j)
+                    for (int q = 0; q < n_q; ++q)
+                        acc += beta * det * weights[q] * (tab0[q * n_phi + a] * tab0[q * n_phi + b]);
+                K[e] = acc;
+            }
+        }
+        if (re) {
+            for (int ra = lane; ra < n_loc; ra += 32) {
+                int a = ra / n_comp, i = ra - a * n_comp;
+                double acc = 0.0;
+                if (gval)
+                    for (int q = 0; q < n_q; ++q)
+                        acc += beta * det * weights[q] * gval[(fc * n_q + q) * n_comp + i] * tab0[q * n_phi + a];
+                re[fc * n_loc + ra] = r_sign * acc;
+            }
+        }
+    }
+}
+
+extern "C" int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp, const double *tab0,
+                                  const double *weights, const double *coords, const int32_t *facet_nodes,
+                                  int64_t n_facets, const double *gval, double beta, double r_sign,
+                                  int with_matrix, double *Ke, double *re, nfa_stream stream) {
+    if (n_facets == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t ctas = (n_facets + 3) / 4;
+    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
+    if (facet_dim == 2)
+        local_h1_facet_kernel<2><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
+                                                      n_facets, gval, beta, r_sign, with_matrix, Ke, re);
+    else if (facet_dim == 1)
+        local_h1_facet_kernel<1><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
+                                                      n_facets, gval, beta, r_sign, with_matrix, Ke, re);
+    else if (facet_dim == 0)
+        local_h1_facet_kernel<0><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
+                                                      n_facets, gval, beta, r_sign, with_matrix, Ke, re);
+    else
+        return fail("nfa_local_h1_facet: facet_dim must be 0, 1 or 2");
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Load vector only (fused path): re[cell][a*nc + i] = sign * sum_q w_q det phi_a(q) f[cell][q][i].
+template <int DIM>
+__global__ void local_h1_load_kernel(int n_phi, int n_q, int n_comp, const double *__restrict__ tab0,
+                                     const double *__restrict__ weights, const double *__restrict__ coords,
+                                     const int32_t *__restrict__ cell_nodes, int64_t n_cells,
+                                     const double *__restrict__ f, double sign, double *__restrict__ re) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_cells * n_phi) return;
+    int64_t cell = idx / n_phi;
+    int a = (int)(idx - cell * n_phi);
+    double X[DIM + 1][3];
+    load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+    Geom<DIM> g;
+    compute_geom<DIM>(X, g);
+    for (int i = 0; i < n_comp; ++i) {
+        double acc = 0.0;
+        if (f)
+            for (int q = 0; q < n_q; ++q)
+                acc += weights[q] * g.det * tab0[q * n_phi + a] * f[(cell * n_q + q) * n_comp + i];
+        re[(cell * n_phi + a) * n_comp + i] = sign * acc;
+    }
+}
+
+extern "C" int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,
+                                 const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *f,
+                                 double sign, double *re, nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = grid_for(n_cells * n_phi, 128);
+    if (dim == 3)
+        local_h1_load_kernel<3><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
+                                                     sign, re);
+    else if (dim == 2)
+        local_h1_load_kernel<2><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
+                                                     sign, re);
+    else if (dim == 1)
+        local_h1_load_kernel<1><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
+                                                     sign, re);
+    else
+        return fail("nfa_local_h1_load: dim must be 1, 2 or 3");
+    NFA_LAUNCH_CHECK();
+    return 0;
+}

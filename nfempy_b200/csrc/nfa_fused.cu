@@ -1,0 +1,469 @@
+// libnfa: fused H1 assembly for affine simplices with cell-wise constant coefficients (sm_100a).
+//
+// One kernel does the local B^T D B contraction AND the global deterministic reduce: no local matrices are
+// written to HBM.  Work is organised by OUTPUT: a CTA owns a chunk of whole node-block rows of the CSR, lists
+// every (cell, a, b) contribution that lands in its rows, computes each 3x3 (or 1x1) block from the cell's
+// 96-byte geometry record and the exact reference tensor Mref held in shared memory, stages the blocks in
+// shared memory and sums them per CSR value in ascending cell order -- the order in which the reference's
+// Mat.setValue(..., addv=True) calls arrive (R/src/assembly/ScatterFormData.py:5-11).  No atomics.
+//
+// Per contribution the local entry is (elasticity, R/src/weak_forms/le_primal_weak_form.py:91-126 integrated
+// exactly):  T = Jinv^T Mref[a][b] Jinv,  K = (det lambda) T + (det mu) T^T + (det mu) tr(T) I.
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <vector>
+
+#include "nfa_plan.cuh"
+
+using namespace nfa;
+
+namespace {
+
+constexpr int FUSED_THREADS = 256;
+
+__global__ void fill_block_keys(const int32_t *__restrict__ node_dest, int64_t n_cells, int n_phi, int64_t n_nodes,
+                                uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int p2 = n_phi * n_phi;
+    if (e >= n_cells * p2) return;
+    int64_t cell = e / p2;
+    int r = (int)(e - cell * p2);
+    int a = r / n_phi, b = r - a * n_phi;
+    uint64_t na = (uint64_t)node_dest[cell * n_phi + a], nb = (uint64_t)node_dest[cell * n_phi + b];
+    keys[e] = na * (uint64_t)n_nodes + nb;
+    ids[e] = (uint32_t)e;
+}
+
+__global__ void block_cols(const uint64_t *__restrict__ ukeys, int64_t n, int64_t n_nodes, int32_t *__restrict__ bcols) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n) bcols[u] = (int32_t)(ukeys[u] % (uint64_t)n_nodes);
+}
+
+__global__ void block_ptr(const uint64_t *__restrict__ ukeys, int64_t n, int64_t n_nodes, int32_t *__restrict__ bptr) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_nodes) return;
+    uint64_t target = (uint64_t)r * (uint64_t)n_nodes;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (ukeys[mid] < target)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    bptr[r] = (int32_t)lo;
+}
+
+// per block row: number of contributions
+__global__ void row_contribs(const int32_t *__restrict__ bptr, const uint32_t *__restrict__ bseg, int64_t n_nodes,
+                             uint32_t *__restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_nodes) out[r] = bseg[bptr[r + 1]] - bseg[bptr[r]];
+}
+
+// key = (chunk << 32) | contribution id, value = staging slot within the chunk
+__global__ void chunk_keys(const uint32_t *__restrict__ ids_sorted, int64_t n_contrib,
+                           const uint32_t *__restrict__ chunk_cstart, int64_t n_chunks,
+                           uint64_t *__restrict__ keys, uint32_t *__restrict__ slots) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_contrib) return;
+    int64_t lo = 0, hi = n_chunks;  // last chunk with cstart <= k
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (chunk_cstart[mid] <= (uint32_t)k)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    keys[k] = ((uint64_t)lo << 32) | (uint64_t)ids_sorted[k];
+    slots[k] = (uint32_t)(k - chunk_cstart[lo]);
+}
+
+__global__ void unpack_chunk_sorted(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ slots, int64_t n,
+                                    uint32_t *__restrict__ contrib, uint16_t *__restrict__ contrib_slot) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    contrib[k] = (uint32_t)(keys[k] & 0xffffffffull);
+    contrib_slot[k] = (uint16_t)slots[k];
+}
+
+__global__ void scalar_pattern(const int32_t *__restrict__ bptr, const int32_t *__restrict__ bcols, int64_t n_nodes,
+                               int nc, int32_t *__restrict__ indptr, int32_t *__restrict__ indices) {
+    // one thread per (block row, block): writes its nc x nc column indices; first block of a row writes indptr
+    int64_t N = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (N > n_nodes) return;
+    if (N == n_nodes) {
+        indptr[(int64_t)nc * n_nodes] = nc * nc * bptr[n_nodes];
+        return;
+    }
+    int32_t b0 = bptr[N], nb = bptr[N + 1] - b0;
+    for (int i = 0; i < nc; ++i) {
+        int32_t start = nc * nc * b0 + i * nc * nb;
+        indptr[nc * N + i] = start;
+        for (int32_t k = 0; k < nb; ++k)
+            for (int j = 0; j < nc; ++j) indices[start + nc * k + j] = nc * bcols[b0 + k] + j;
+    }
+}
+
+}  // namespace
+
+extern "C" void nfa_bplan_destroy(nfa_bplan *bp) { delete bp; }
+extern "C" int64_t nfa_bplan_nnz(const nfa_bplan *bp) { return bp ? bp->n_bnz * bp->n_comp * bp->n_comp : -1; }
+extern "C" int64_t nfa_bplan_bytes(const nfa_bplan *bp) {
+    if (!bp) return -1;
+    return (int64_t)(bp->bptr.n + bp->bcols.n + bp->bseg.n + bp->chunk_row.n + bp->contrib.n + bp->contrib_slot.n +
+                     bp->indptr.n + bp->indices.n + bp->geo.n);
+}
+
+extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const int32_t *node_dest, int64_t n_cells,
+                                nfa_bplan **out, nfa_stream stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!out) return fail("nfa_bplan_create: out is NULL");
+    *out = nullptr;
+    if (n_comp < 1 || n_comp > 3) return fail("nfa_bplan_create: n_comp must be 1, 2 or 3");
+    if (n_phi < 1 || n_phi > 20) return fail("nfa_bplan_create: n_phi must be 1..20");
+    int64_t p2 = (int64_t)n_phi * n_phi;
+    int64_t E = n_cells * p2;
+    if (E <= 0 || E >= ((int64_t)1 << 31)) return fail("nfa_bplan_create: contribution count out of range");
+    if (n_nodes * n_comp > INT32_MAX) return fail("nfa_bplan_create: n_dof out of int32 range");
+    nfa_bplan *bp = new nfa_bplan();
+    auto bail = [&](int rc) {
+        delete bp;
+        return rc;
+    };
+    bp->n_nodes = n_nodes;
+    bp->n_cells = n_cells;
+    bp->n_phi = n_phi;
+    bp->n_comp = n_comp;
+    bp->n_contrib = E;
+
+    DevBuf keys, keys_alt, ids, ids_alt, tmp, ukeys, counts, nruns;
+    if (keys.alloc(8 * E) || keys_alt.alloc(8 * E) || ids.alloc(4 * E) || ids_alt.alloc(4 * E)) return bail(2);
+    fill_block_keys<<<grid_for(E, 256), 256, 0, s>>>(node_dest, n_cells, n_phi, n_nodes, (uint64_t *)keys.p,
+                                                     (uint32_t *)ids.p);
+    count_launch();
+    int end_bit = 1;
+    while (end_bit < 64 && (((uint64_t)n_nodes * (uint64_t)n_nodes) >> end_bit) != 0) ++end_bit;
+    cub::DoubleBuffer<uint64_t> dk((uint64_t *)keys.p, (uint64_t *)keys_alt.p);
+    cub::DoubleBuffer<uint32_t> dv((uint32_t *)ids.p, (uint32_t *)ids_alt.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, dk, dv, (int)E, 0, end_bit, s);
+    if (tmp.alloc(tb)) return bail(2);
+    if (cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk, dv, (int)E, 0, end_bit, s) != cudaSuccess)
+        return bail(fail("nfa_bplan_create: radix sort failed"));
+    count_launch(8);
+    if (ukeys.alloc(8 * E) || counts.alloc(4 * (E + 1)) || nruns.alloc(sizeof(int))) return bail(2);
+    cub::DeviceRunLengthEncode::Encode(nullptr, tb, dk.Current(), (uint64_t *)ukeys.p, (uint32_t *)counts.p,
+                                       (int *)nruns.p, (int)E, s);
+    if (tmp.alloc(tb)) return bail(2);
+    cub::DeviceRunLengthEncode::Encode(tmp.p, tb, dk.Current(), (uint64_t *)ukeys.p, (uint32_t *)counts.p,
+                                       (int *)nruns.p, (int)E, s);
+    count_launch(3);
+    int h_runs = 0;
+    cudaMemcpyAsync(&h_runs, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return bail(fail("nfa_bplan_create: run-length encode failed"));
+    bp->n_bnz = h_runs;
+    int64_t nb = h_runs;
+    if (nb * n_comp * n_comp > INT32_MAX) return bail(fail("nfa_bplan_create: nnz exceeds int32 (PETSc index type)"));
+    if (bp->bseg.alloc(4 * (nb + 1)) || bp->bcols.alloc(4 * nb) || bp->bptr.alloc(4 * (n_nodes + 1))) return bail(2);
+    cudaMemsetAsync((uint32_t *)counts.p + nb, 0, 4, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t *)counts.p, (uint32_t *)bp->bseg.p, (int)(nb + 1), s);
+    if (tmp.alloc(tb)) return bail(2);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, (uint32_t *)counts.p, (uint32_t *)bp->bseg.p, (int)(nb + 1), s);
+    block_cols<<<grid_for(nb, 256), 256, 0, s>>>((uint64_t *)ukeys.p, nb, n_nodes, (int32_t *)bp->bcols.p);
+    block_ptr<<<grid_for(n_nodes + 1, 256), 256, 0, s>>>((uint64_t *)ukeys.p, nb, n_nodes, (int32_t *)bp->bptr.p);
+    count_launch(4);
+    ukeys.release();
+    counts.release();
+    // keys (sorted) are no longer needed; dv.Current() holds contribution ids in output order
+    // ---- chunking on the host: whole block rows, bounded contributions and blocks per chunk
+    DevBuf rowc;
+    if (rowc.alloc(4 * n_nodes)) return bail(2);
+    row_contribs<<<grid_for(n_nodes, 256), 256, 0, s>>>((int32_t *)bp->bptr.p, (uint32_t *)bp->bseg.p, n_nodes,
+                                                        (uint32_t *)rowc.p);
+    count_launch();
+    std::vector<uint32_t> h_rowc(n_nodes);
+    std::vector<int32_t> h_bptr(n_nodes + 1);
+    cudaMemcpyAsync(h_rowc.data(), rowc.p, 4 * n_nodes, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(h_bptr.data(), bp->bptr.p, 4 * (n_nodes + 1), cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) return bail(fail("nfa_bplan_create: block pattern build failed"));
+    const int nc2 = n_comp * n_comp;
+    int cap_c = 1024, cap_b = 1024;
+    if (const char *e = getenv("NFA_FUSED_CAP")) cap_c = std::max(64, atoi(e));
+    // staging must fit: cap_c * nc2 doubles (+ Mref) within ~200 KB
+    std::vector<int32_t> chunk_row{0};
+    std::vector<uint32_t> chunk_cstart{0};
+    int64_t cur_c = 0, cur_b = 0;
+    uint32_t run = 0;
+    int max_c = 0, max_b = 0;
+    for (int64_t r = 0; r < n_nodes; ++r) {
+        int64_t rc = h_rowc[r], rb = h_bptr[r + 1] - h_bptr[r];
+        if (rc > 65535 || rc * nc2 * 8 > 180 * 1024)
+            return bail(fail("nfa_bplan_create: a node has too many adjacent cells for the fused staging"));
+        if (cur_c > 0 && (cur_c + rc > cap_c || cur_b + rb > cap_b)) {
+            chunk_row.push_back((int32_t)r);
+            chunk_cstart.push_back(run);
+            max_c = std::max<int>(max_c, (int)cur_c);
+            max_b = std::max<int>(max_b, (int)cur_b);
+            cur_c = cur_b = 0;
+        }
+        cur_c += rc;
+        cur_b += rb;
+        run += (uint32_t)rc;
+    }
+    max_c = std::max<int>(max_c, (int)cur_c);
+    max_b = std::max<int>(max_b, (int)cur_b);
+    chunk_row.push_back((int32_t)n_nodes);
+    bp->n_chunks = (int64_t)chunk_row.size() - 1;
+    bp->max_chunk_contrib = max_c;
+    bp->max_chunk_bnz = max_b;
+    DevBuf d_cstart;
+    if (bp->chunk_row.alloc(4 * chunk_row.size()) || d_cstart.alloc(4 * chunk_cstart.size())) return bail(2);
+    cudaMemcpyAsync(bp->chunk_row.p, chunk_row.data(), 4 * chunk_row.size(), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_cstart.p, chunk_cstart.data(), 4 * chunk_cstart.size(), cudaMemcpyHostToDevice, s);
+    // ---- reorder each chunk's contributions by (cell, a, b) = ascending id, remembering the staging slot
+    uint64_t *ck = (uint64_t *)dk.Alternate();  // reuse the sort buffers
+    uint32_t *cs = dv.Alternate();
+    chunk_keys<<<grid_for(E, 256), 256, 0, s>>>(dv.Current(), E, (uint32_t *)d_cstart.p, bp->n_chunks, ck, cs);
+    count_launch();
+    // sort (chunk, id) pairs; ping-pong buffers: keys -> dk.Current(), slots -> need one more u32 buffer
+    DevBuf slots_alt;
+    if (slots_alt.alloc(4 * E)) return bail(2);
+    cub::DoubleBuffer<uint64_t> dk2(ck, dk.Current());
+    cub::DoubleBuffer<uint32_t> dv2(cs, (uint32_t *)slots_alt.p);
+    int cbits = 1;
+    while (cbits < 32 && (((uint64_t)bp->n_chunks) >> cbits) != 0) ++cbits;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, dk2, dv2, (int)E, 0, 32 + cbits, s);
+    if (tmp.alloc(tb)) return bail(2);
+    if (cub::DeviceRadixSort::SortPairs(tmp.p, tb, dk2, dv2, (int)E, 0, 32 + cbits, s) != cudaSuccess)
+        return bail(fail("nfa_bplan_create: chunk sort failed"));
+    count_launch(8);
+    if (bp->contrib.alloc(4 * E) || bp->contrib_slot.alloc(2 * E)) return bail(2);
+    unpack_chunk_sorted<<<grid_for(E, 256), 256, 0, s>>>(dk2.Current(), dv2.Current(), E, (uint32_t *)bp->contrib.p,
+                                                         (uint16_t *)bp->contrib_slot.p);
+    count_launch();
+    // ---- scalar CSR pattern
+    int64_t n_dof = n_nodes * n_comp, nnz = nb * nc2;
+    if (bp->indptr.alloc(4 * (n_dof + 1)) || bp->indices.alloc(4 * nnz)) return bail(2);
+    if (bp->geo.alloc(sizeof(double) * 12 * n_cells)) return bail(2);  // per-assembly geometry records
+    scalar_pattern<<<grid_for(n_nodes + 1, 128), 128, 0, s>>>((int32_t *)bp->bptr.p, (int32_t *)bp->bcols.p, n_nodes,
+                                                              n_comp, (int32_t *)bp->indptr.p, (int32_t *)bp->indices.p);
+    count_launch();
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return bail(fail(std::string("nfa_bplan_create: ") + cudaGetErrorString(e)));
+    *out = bp;
+    return 0;
+}
+
+extern "C" int nfa_plan_from_bplan(const nfa_bplan *bp, nfa_plan **out, nfa_stream) {
+    if (!bp || !out) return fail("nfa_plan_from_bplan: NULL argument");
+    nfa_plan *plan = new nfa_plan();
+    plan->n_dof = bp->n_nodes * bp->n_comp;
+    plan->nnz = bp->n_bnz * bp->n_comp * bp->n_comp;
+    plan->ext_indptr = (const int32_t *)bp->indptr.p;
+    plan->ext_indices = (const int32_t *)bp->indices.p;
+    *out = plan;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// geometry records: [Jinv (DIM x DIM, the first DIM columns of the pseudo-inverse), det*c0, det*c1]
+template <int DIM, int FORM>
+struct GeoRec {
+    static constexpr int N = (FORM == 0) ? (DIM * DIM + 2) : (DIM * (DIM + 1) / 2);
+    static constexpr int STRIDE = (N + 1) & ~1;  // 16-byte aligned records
+};
+
+template <int DIM, int FORM>
+__global__ void geo_records_kernel(const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
+                                   int64_t n_cells, const double *__restrict__ c0, int64_t s0,
+                                   const double *__restrict__ c1, int64_t s1, double *__restrict__ geo) {
+    int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    double X[DIM + 1][3];
+    load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+    Geom<DIM> g;
+    compute_geom<DIM>(X, g);
+    double *rec = geo + cell * GeoRec<DIM, FORM>::STRIDE;
+    if (FORM == 0) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k)
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) rec[k * DIM + d] = g.Jinv[k][d];
+        rec[DIM * DIM] = g.det * c0[cell * s0];
+        rec[DIM * DIM + 1] = g.det * c1[cell * s1];
+    } else {
+        // G = det * kappa * Jinv Jinv^T (symmetric, upper triangle row-major); physical columns 0..DIM-1 only
+        double w = g.det * c0[cell * s0];
+        int t = 0;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k)
+#pragma unroll
+            for (int l = k; l < DIM; ++l) {
+                double v = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) v += g.Jinv[k][d] * g.Jinv[l][d];
+                rec[t++] = w * v;
+            }
+    }
+}
+
+template <int DIM, int FORM>
+__global__ void __launch_bounds__(FUSED_THREADS)
+    fused_h1_kernel(const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ bptr,
+                    const uint32_t *__restrict__ bseg, const uint32_t *__restrict__ contrib,
+                    const uint16_t *__restrict__ contrib_slot, const double *__restrict__ geo,
+                    const double *__restrict__ Mref, int n_phi, int stage_cap, double *__restrict__ vals) {
+    constexpr int NC = (FORM == 0) ? DIM : 1;
+    constexpr int NC2 = NC * NC;
+    constexpr int GS = GeoRec<DIM, FORM>::STRIDE;
+    extern __shared__ double smem[];
+    const int p2 = n_phi * n_phi;
+    double *s_M = smem;                              // [p2][DIM*DIM]
+    double *s_stage = s_M + p2 * DIM * DIM;          // [stage_cap][NC2]
+    int *s_rows = (int *)(s_stage + (size_t)stage_cap * NC2);  // [n_rows + 1] block offsets (relative to b0)
+
+    const int ch = blockIdx.x;
+    const int r0 = chunk_row[ch], r1 = chunk_row[ch + 1];
+    const int n_rows = r1 - r0;
+    const int b0 = bptr[r0], b1 = bptr[r1];
+    const uint32_t c0 = bseg[b0], c1 = bseg[b1];
+
+    for (int i = threadIdx.x; i < p2 * DIM * DIM; i += FUSED_THREADS) s_M[i] = Mref[i];
+    for (int i = threadIdx.x; i <= n_rows; i += FUSED_THREADS) s_rows[i] = bptr[r0 + i] - b0;
+    __syncthreads();
+
+    // ---- phase 1: one contribution per thread, cell-ordered
+    for (uint32_t k = c0 + threadIdx.x; k < c1; k += FUSED_THREADS) {
+        const uint32_t id = contrib[k];
+        const int slot = contrib_slot[k];
+        const uint32_t cell = id / (uint32_t)p2;
+        const int pair = (int)(id - cell * (uint32_t)p2);
+        const double *rec = geo + (int64_t)cell * GS;
+        const double *M = s_M + pair * DIM * DIM;
+        double *out = s_stage + (size_t)slot * NC2;
+        if constexpr (FORM == 0) {
+            double Ji[DIM][DIM];
+#pragma unroll
+            for (int q = 0; q < DIM * DIM; ++q) Ji[q / DIM][q % DIM] = __ldg(rec + q);
+            const double wl = __ldg(rec + DIM * DIM), wm = __ldg(rec + DIM * DIM + 1);
+            // P = Jinv^T M  (P[i][l] = sum_k Jinv[k][i] M[k][l]);  T = P Jinv (T[i][j] = sum_l P[i][l] Jinv[l][j])
+            double P[DIM][DIM], T[DIM][DIM];
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int l = 0; l < DIM; ++l) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < DIM; ++kk) v += Ji[kk][i] * M[kk * DIM + l];
+                    P[i][l] = v;
+                }
+            double tr = 0.0;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int l = 0; l < DIM; ++l) v += P[i][l] * Ji[l][j];
+                    T[i][j] = v;
+                }
+                tr += T[i][i];
+            }
+#pragma unroll
+            for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                for (int j = 0; j < DIM; ++j) {
+                    double v = wl * T[i][j] + wm * T[j][i];
+                    if (i == j) v += wm * tr;
+                    out[i * DIM + j] = v;
+                }
+        } else {
+            double v = 0.0;
+            int t = 0;
+#pragma unroll
+            for (int kk = 0; kk < DIM; ++kk)
+#pragma unroll
+                for (int l = kk; l < DIM; ++l) {
+                    double gkl = __ldg(rec + t);
+                    ++t;
+                    v += gkl * (kk == l ? M[kk * DIM + l] : (M[kk * DIM + l] + M[l * DIM + kk]));
+                }
+            out[0] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: one output scalar per thread, consecutive threads -> consecutive CSR values
+    const int n_blocks = b1 - b0;
+    const int64_t out_base = (int64_t)NC2 * b0;
+    for (int t = threadIdx.x; t < n_blocks * NC2; t += FUSED_THREADS) {
+        // locate block row: NC2 * s_rows[r] <= t < NC2 * s_rows[r + 1]
+        int lo = 0, hi = n_rows;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (NC2 * s_rows[mid] <= t)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int rb = s_rows[lo], nb = s_rows[lo + 1] - rb;
+        const int local = t - NC2 * rb;   // within the row's NC rows x (NC * nb) values
+        const int i = local / (NC * nb);
+        const int v = local - i * NC * nb;
+        const int blk = v / NC, j = v - blk * NC;
+        const int u = b0 + rb + blk;
+        const uint32_t s0 = bseg[u] - c0, s1 = bseg[u + 1] - c0;
+        double acc = 0.0;
+        for (uint32_t sidx = s0; sidx < s1; ++sidx) acc += s_stage[(size_t)sidx * NC2 + i * NC + j];
+        vals[out_base + t] = acc;
+    }
+}
+
+template <int DIM, int FORM>
+static int run_fused(const nfa_bplan *bp, const double *Mref, const double *coords, const int32_t *cell_nodes,
+                     const double *c0, int64_t s0, const double *c1, int64_t s1, double *vals, cudaStream_t s) {
+    constexpr int NC = (FORM == 0) ? DIM : 1;
+    if (bp->n_comp != NC) return fail("fused H1: plan n_comp does not match the form");
+    constexpr int GS = GeoRec<DIM, FORM>::STRIDE;
+    static_assert(GS <= 12, "geometry record exceeds the plan's scratch stride");
+    const DevBuf &geo = bp->geo;
+    geo_records_kernel<DIM, FORM><<<grid_for(bp->n_cells, 128), 128, 0, s>>>(coords, cell_nodes, bp->n_cells, c0, s0,
+                                                                             c1, s1, (double *)geo.p);
+    NFA_LAUNCH_CHECK();
+    int p2 = bp->n_phi * bp->n_phi;
+    int stage_cap = bp->max_chunk_contrib;
+    size_t smem = sizeof(double) * ((size_t)p2 * DIM * DIM + (size_t)stage_cap * NC * NC) + 4 * 1100;
+    auto kern = fused_h1_kernel<DIM, FORM>;
+    NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (timing_enabled()) timing_begin(s);
+    kern<<<(unsigned)bp->n_chunks, FUSED_THREADS, smem, s>>>(
+        (const int32_t *)bp->chunk_row.p, (const int32_t *)bp->bptr.p, (const uint32_t *)bp->bseg.p,
+        (const uint32_t *)bp->contrib.p, (const uint16_t *)bp->contrib_slot.p, (const double *)geo.p, Mref, bp->n_phi,
+        stage_cap, vals);
+    if (timing_enabled()) timing_end(s);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nfa_assemble_h1_elasticity_affine(const nfa_bplan *bp, int dim, const double *Mref,
+                                                 const double *coords, const int32_t *cell_nodes, const double *lam,
+                                                 int64_t ls, const double *mu, int64_t ms, double *vals,
+                                                 nfa_stream stream) {
+    if (!bp) return fail("nfa_assemble_h1_elasticity_affine: plan is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dim == 3) return run_fused<3, 0>(bp, Mref, coords, cell_nodes, lam, ls, mu, ms, vals, s);
+    if (dim == 2) return run_fused<2, 0>(bp, Mref, coords, cell_nodes, lam, ls, mu, ms, vals, s);
+    return fail("nfa_assemble_h1_elasticity_affine: dim must be 2 or 3");
+}
+
+extern "C" int nfa_assemble_h1_laplace_affine(const nfa_bplan *bp, int dim, const double *Mref, const double *coords,
+                                              const int32_t *cell_nodes, const double *kappa, int64_t ks, double *vals,
+                                              nfa_stream stream) {
+    if (!bp) return fail("nfa_assemble_h1_laplace_affine: plan is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dim == 3) return run_fused<3, 1>(bp, Mref, coords, cell_nodes, kappa, ks, nullptr, 0, vals, s);
+    if (dim == 2) return run_fused<2, 1>(bp, Mref, coords, cell_nodes, kappa, ks, nullptr, 0, vals, s);
+    if (dim == 1) return run_fused<1, 1>(bp, Mref, coords, cell_nodes, kappa, ks, nullptr, 0, vals, s);
+    return fail("nfa_assemble_h1_laplace_affine: dim must be 1, 2 or 3");
+}

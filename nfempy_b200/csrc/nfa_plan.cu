@@ -1,0 +1,396 @@
+// libnfa: K6 sparsity plan (sort/unique of (row, col) keys -> CSR + gather lists) and K7 deterministic reduce.
+// The one-off plan build leans on CUB device primitives (radix sort, run-length encode, scan) from the CUDA
+// toolkit; the per-assembly kernels (reduce, spmv) are hand-written.
+#include <cub/cub.cuh>
+#include <vector>
+
+#include "nfa_plan.cuh"
+
+using namespace nfa;
+
+namespace nfa {
+
+int DevBuf::alloc(size_t bytes) {
+    release();
+    if (bytes == 0) return 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+        return 2;
+    }
+    n = bytes;
+    return 0;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+}
+
+}  // namespace nfa
+
+// ---- key generation ------------------------------------------------------------------------------
+__global__ void fill_matrix_keys(const int32_t *__restrict__ dest, int64_t n_items, int n_loc, int64_t n_dof,
+                                 uint32_t entry_base, uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = (int64_t)n_loc * n_loc;
+    if (e >= n_items * per) return;
+    int64_t item = e / per;
+    int r = (int)(e - item * per);
+    int ra = r / n_loc, rb = r - ra * n_loc;
+    uint64_t row = (uint64_t)dest[item * n_loc + ra], col = (uint64_t)dest[item * n_loc + rb];
+    keys[entry_base + e] = row * (uint64_t)n_dof + col;
+    ids[entry_base + e] = entry_base + (uint32_t)e;
+}
+
+__global__ void fill_row_keys(const int32_t *__restrict__ dest, int64_t n_entries, uint32_t entry_base,
+                              uint32_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    keys[entry_base + e] = (uint32_t)dest[e];
+    ids[entry_base + e] = entry_base + (uint32_t)e;
+}
+
+__global__ void check_dest_range(const int32_t *__restrict__ dest, int64_t n, int64_t n_dof, int *flag) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    int32_t d = dest[e];
+    if (d < 0 || d >= n_dof) atomicExch(flag, 1);
+}
+
+__global__ void split_keys(const uint64_t *__restrict__ ukeys, int64_t nnz, int64_t n_dof,
+                           int32_t *__restrict__ indices) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nnz) return;
+    indices[u] = (int32_t)(ukeys[u] % (uint64_t)n_dof);
+}
+
+__global__ void build_indptr(const uint64_t *__restrict__ ukeys, int64_t nnz, int64_t n_dof,
+                             int32_t *__restrict__ indptr) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_dof) return;
+    uint64_t target = (uint64_t)r * (uint64_t)n_dof;
+    int64_t lo = 0, hi = nnz;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (ukeys[mid] < target)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    indptr[r] = (int32_t)lo;
+}
+
+__global__ void locate_in_base(const uint64_t *__restrict__ ukeys, int64_t n_unique, int64_t n_dof,
+                               const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                               int32_t *__restrict__ pos, int *flag) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_unique) return;
+    uint64_t key = ukeys[u];
+    int64_t row = (int64_t)(key / (uint64_t)n_dof);
+    int32_t col = (int32_t)(key % (uint64_t)n_dof);
+    int32_t lo = indptr[row], hi = indptr[row + 1];
+    while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+        if (indices[mid] < col)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (lo >= indptr[row + 1] || indices[lo] != col) {
+        atomicExch(flag, 1);
+        pos[u] = -1;
+    } else
+        pos[u] = lo;
+}
+
+__global__ void widen_u32(const uint32_t *__restrict__ in, int64_t n, int32_t *__restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)in[i];
+}
+
+// ---- gather-set construction -----------------------------------------------------------------------
+template <typename KeyT>
+static int sort_and_encode(KeyT *keys, KeyT *keys_alt, uint32_t *ids, uint32_t *ids_alt, int64_t n, int end_bit,
+                           DevBuf &ukeys, DevBuf &perm, DevBuf &seg_ptr, int64_t *n_unique, cudaStream_t s) {
+    if (n >= (int64_t)1 << 31) return fail("plan: more than 2^31 local entries in one gather set");
+    cub::DoubleBuffer<KeyT> dk(keys, keys_alt);
+    cub::DoubleBuffer<uint32_t> dv(ids, ids_alt);
+    size_t tmp_bytes = 0;
+    NFA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, end_bit, s));
+    DevBuf tmp;
+    if (tmp.alloc(tmp_bytes)) return 2;
+    NFA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, dk, dv, (int)n, 0, end_bit, s));
+    count_launch(8);
+    // run-length encode
+    DevBuf counts, nruns;
+    if (ukeys.alloc(sizeof(KeyT) * n) || counts.alloc(sizeof(uint32_t) * (n + 1)) || nruns.alloc(sizeof(int)))
+        return 2;
+    NFA_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, dk.Current(), (KeyT *)ukeys.p,
+                                                (uint32_t *)counts.p, (int *)nruns.p, (int)n, s));
+    if (tmp.alloc(tmp_bytes)) return 2;
+    NFA_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, tmp_bytes, dk.Current(), (KeyT *)ukeys.p,
+                                                (uint32_t *)counts.p, (int *)nruns.p, (int)n, s));
+    count_launch(3);
+    int h_runs = 0;
+    NFA_CUDA(cudaMemcpyAsync(&h_runs, nruns.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NFA_CUDA(cudaStreamSynchronize(s));
+    *n_unique = h_runs;
+    // seg_ptr = exclusive scan of counts over n_unique + 1 entries
+    if (seg_ptr.alloc(sizeof(uint32_t) * (h_runs + 1))) return 2;
+    NFA_CUDA(cudaMemsetAsync((uint32_t *)counts.p + h_runs, 0, sizeof(uint32_t), s));
+    NFA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, (uint32_t *)counts.p, (uint32_t *)seg_ptr.p,
+                                           h_runs + 1, s));
+    if (tmp.alloc(tmp_bytes)) return 2;
+    NFA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, (uint32_t *)counts.p, (uint32_t *)seg_ptr.p,
+                                           h_runs + 1, s));
+    count_launch(2);
+    if (perm.alloc(sizeof(uint32_t) * n)) return 2;
+    NFA_CUDA(cudaMemcpyAsync(perm.p, dv.Current(), sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int bits_for(uint64_t max_value) {
+    int b = 1;
+    while (b < 64 && (max_value >> b) != 0) ++b;
+    return b;
+}
+
+extern "C" int nfa_plan_create(int64_t n_dof, int n_segments, const int32_t *const *dest, const int64_t *n_items,
+                               const int32_t *n_loc, const int32_t *seg_flags, const nfa_plan *base, nfa_plan **out,
+                               nfa_stream stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!out) return fail("nfa_plan_create: out is NULL");
+    *out = nullptr;
+    if (n_segments < 0 || n_segments > NFA_MAX_SEGMENTS)
+        return fail("nfa_plan_create: at most " + std::to_string(NFA_MAX_SEGMENTS) + " segments");
+    if (n_dof <= 0 || n_dof > INT32_MAX) return fail("nfa_plan_create: n_dof out of int32 range");
+    if (base && base->n_dof != n_dof) return fail("nfa_plan_create: base plan has a different n_dof");
+    nfa_plan *plan = new nfa_plan();
+    plan->n_dof = n_dof;
+    plan->n_segments = n_segments;
+    int64_t E = 0, R = 0;
+    for (int k = 0; k < n_segments; ++k) {
+        plan->n_items[k] = n_items[k];
+        plan->n_loc[k] = n_loc[k];
+        plan->mat_off[k] = E;
+        plan->rhs_off[k] = R;
+        plan->with_matrix[k] = seg_flags ? (seg_flags[k] & 1) : 1;
+        if (plan->with_matrix[k]) E += n_items[k] * (int64_t)n_loc[k] * n_loc[k];
+        R += n_items[k] * (int64_t)n_loc[k];
+    }
+    plan->mat_off[n_segments] = E;
+    plan->rhs_off[n_segments] = R;
+    auto bail = [&](int rc) {
+        nfa_plan_destroy(plan);
+        return rc;
+    };
+    if (E >= (int64_t)1 << 31) return bail(fail("nfa_plan_create: more than 2^31 local matrix entries"));
+
+    // destination indices must be valid dofs
+    DevBuf flag;
+    if (flag.alloc(sizeof(int))) return bail(2);
+    cudaMemsetAsync(flag.p, 0, sizeof(int), s);
+    for (int k = 0; k < n_segments; ++k) {
+        int64_t n = n_items[k] * (int64_t)n_loc[k];
+        if (n == 0) continue;
+        check_dest_range<<<grid_for(n, 256), 256, 0, s>>>(dest[k], n, n_dof, (int *)flag.p);
+        count_launch();
+    }
+    int h_flag = 0;
+    cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    if (h_flag) return bail(fail("nfa_plan_create: destination index outside [0, n_dof)"));
+
+    // ---- matrix gather set
+    if (E > 0) {
+        DevBuf keys, keys_alt, ids, ids_alt, ukeys;
+        if (keys.alloc(8 * E) || keys_alt.alloc(8 * E) || ids.alloc(4 * E) || ids_alt.alloc(4 * E)) return bail(2);
+        for (int k = 0; k < n_segments; ++k) {
+            int64_t n = n_items[k] * (int64_t)n_loc[k] * n_loc[k];
+            if (n == 0 || !plan->with_matrix[k]) continue;
+            fill_matrix_keys<<<grid_for(n, 256), 256, 0, s>>>(dest[k], n_items[k], n_loc[k], n_dof,
+                                                              (uint32_t)plan->mat_off[k], (uint64_t *)keys.p,
+                                                              (uint32_t *)ids.p);
+            count_launch();
+        }
+        int end_bit = bits_for((uint64_t)n_dof * (uint64_t)n_dof);
+        int rc = sort_and_encode<uint64_t>((uint64_t *)keys.p, (uint64_t *)keys_alt.p, (uint32_t *)ids.p,
+                                           (uint32_t *)ids_alt.p, E, end_bit, ukeys, plan->mat.perm,
+                                           plan->mat.seg_ptr, &plan->mat.n_unique, s);
+        if (rc) return bail(rc);
+        keys.release();
+        keys_alt.release();
+        ids.release();
+        ids_alt.release();
+        int64_t nu = plan->mat.n_unique;
+        if (!base) {
+            plan->nnz = nu;
+            if (plan->indices.alloc(4 * nu) || plan->indptr.alloc(4 * (n_dof + 1))) return bail(2);
+            split_keys<<<grid_for(nu, 256), 256, 0, s>>>((uint64_t *)ukeys.p, nu, n_dof, (int32_t *)plan->indices.p);
+            build_indptr<<<grid_for(n_dof + 1, 256), 256, 0, s>>>((uint64_t *)ukeys.p, nu, n_dof,
+                                                                   (int32_t *)plan->indptr.p);
+            count_launch(2);
+        } else {
+            if (plan->mat.pos.alloc(4 * nu)) return bail(2);
+            cudaMemsetAsync(flag.p, 0, sizeof(int), s);
+            locate_in_base<<<grid_for(nu, 256), 256, 0, s>>>((uint64_t *)ukeys.p, nu, n_dof, base->d_indptr(),
+                                                              base->d_indices(), (int32_t *)plan->mat.pos.p,
+                                                              (int *)flag.p);
+            count_launch();
+            cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            if (h_flag)
+                return bail(fail("nfa_plan_create: a segment couples dofs that the base pattern does not contain"));
+        }
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return bail(fail(std::string("plan build: ") + cudaGetErrorString(e)));
+    } else if (!base) {
+        plan->nnz = 0;
+        if (plan->indptr.alloc(4 * (n_dof + 1))) return bail(2);
+        cudaMemsetAsync(plan->indptr.p, 0, 4 * (n_dof + 1), s);
+    }
+    if (base) {
+        plan->base = base;
+        plan->nnz = base->nnz;
+    }
+
+    // ---- rhs gather set (keys = destination rows)
+    if (R > 0) {
+        DevBuf keys, keys_alt, ids, ids_alt, ukeys;
+        if (keys.alloc(4 * R) || keys_alt.alloc(4 * R) || ids.alloc(4 * R) || ids_alt.alloc(4 * R)) return bail(2);
+        for (int k = 0; k < n_segments; ++k) {
+            int64_t n = n_items[k] * (int64_t)n_loc[k];
+            if (n == 0) continue;
+            fill_row_keys<<<grid_for(n, 256), 256, 0, s>>>(dest[k], n, (uint32_t)plan->rhs_off[k],
+                                                           (uint32_t *)keys.p, (uint32_t *)ids.p);
+            count_launch();
+        }
+        int rc = sort_and_encode<uint32_t>((uint32_t *)keys.p, (uint32_t *)keys_alt.p, (uint32_t *)ids.p,
+                                           (uint32_t *)ids_alt.p, R, bits_for((uint64_t)n_dof), ukeys,
+                                           plan->rhs.perm, plan->rhs.seg_ptr, &plan->rhs.n_unique, s);
+        if (rc) return bail(rc);
+        int64_t nu = plan->rhs.n_unique;
+        if (plan->rhs.pos.alloc(4 * nu)) return bail(2);
+        widen_u32<<<grid_for(nu, 256), 256, 0, s>>>((uint32_t *)ukeys.p, nu, (int32_t *)plan->rhs.pos.p);
+        count_launch();
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return bail(fail(std::string("plan build (rhs): ") + cudaGetErrorString(e)));
+    }
+    *out = plan;
+    return 0;
+}
+
+extern "C" void nfa_plan_destroy(nfa_plan *plan) { delete plan; }
+extern "C" int64_t nfa_plan_nnz(const nfa_plan *plan) { return plan ? plan->nnz : -1; }
+extern "C" int64_t nfa_plan_n_dof(const nfa_plan *plan) { return plan ? plan->n_dof : -1; }
+extern "C" int64_t nfa_plan_bytes(const nfa_plan *plan) {
+    if (!plan) return -1;
+    return (int64_t)(plan->indptr.n + plan->indices.n + plan->mat.perm.n + plan->mat.seg_ptr.n + plan->mat.pos.n +
+                     plan->rhs.perm.n + plan->rhs.seg_ptr.n + plan->rhs.pos.n);
+}
+
+extern "C" int nfa_plan_csr(const nfa_plan *plan, int32_t *indptr, int32_t *indices, nfa_stream stream) {
+    if (!plan) return fail("nfa_plan_csr: plan is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (indptr)
+        NFA_CUDA(cudaMemcpyAsync(indptr, plan->d_indptr(), 4 * (plan->n_dof + 1), cudaMemcpyDeviceToDevice, s));
+    if (indices && plan->nnz)
+        NFA_CUDA(cudaMemcpyAsync(indices, plan->d_indices(), 4 * plan->nnz, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// ---- K7 reduce ---------------------------------------------------------------------------------------
+struct SegPtrs {
+    const double *p[NFA_MAX_SEGMENTS];
+    int64_t off[NFA_MAX_SEGMENTS + 1];
+    int n;
+};
+
+__global__ void reduce_kernel(int64_t n_unique, const uint32_t *__restrict__ seg_ptr,
+                              const uint32_t *__restrict__ perm, const int32_t *__restrict__ pos, SegPtrs segs,
+                              int accumulate, double *__restrict__ out) {
+    int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_unique) return;
+    int64_t where = pos ? (int64_t)pos[u] : u;
+    double acc = accumulate ? out[where] : 0.0;
+    uint32_t b = seg_ptr[u], e = seg_ptr[u + 1];
+    for (uint32_t k = b; k < e; ++k) {
+        int64_t id = perm[k];
+        int sgm = 0;
+        while (sgm + 1 < segs.n && id >= segs.off[sgm + 1]) ++sgm;
+        const double *src = segs.p[sgm];
+        if (src) acc += src[id - segs.off[sgm]];
+    }
+    out[where] = acc;
+}
+
+__global__ void zero_kernel(double *p, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+
+extern "C" int nfa_plan_reduce(const nfa_plan *plan, const double *const *Ke, const double *const *re,
+                               int accumulate_vals, double *vals, int accumulate_rhs, double *rhs,
+                               nfa_stream stream) {
+    if (!plan) return fail("nfa_plan_reduce: plan is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (Ke && vals) {
+        // a plan merged into a base pattern only touches part of the values: never overwrite the rest
+        if (plan->base && !accumulate_vals)
+            return fail("nfa_plan_reduce: a plan merged into a base pattern must accumulate");
+        if (plan->mat.n_unique > 0) {
+            SegPtrs sp;
+            sp.n = plan->n_segments;
+            for (int k = 0; k < plan->n_segments; ++k) sp.p[k] = plan->with_matrix[k] ? Ke[k] : nullptr;
+            for (int k = 0; k <= plan->n_segments; ++k) sp.off[k] = plan->mat_off[k];
+            reduce_kernel<<<grid_for(plan->mat.n_unique, 256), 256, 0, s>>>(
+                plan->mat.n_unique, (const uint32_t *)plan->mat.seg_ptr.p, (const uint32_t *)plan->mat.perm.p,
+                (const int32_t *)plan->mat.pos.p, sp, accumulate_vals, vals);
+            NFA_LAUNCH_CHECK();
+        }
+    }
+    if (re && rhs) {
+        if (!accumulate_rhs) {
+            zero_kernel<<<grid_for(plan->n_dof, 256), 256, 0, s>>>(rhs, plan->n_dof);
+            NFA_LAUNCH_CHECK();
+        }
+        if (plan->rhs.n_unique > 0) {
+            SegPtrs sp;
+            sp.n = plan->n_segments;
+            for (int k = 0; k < plan->n_segments; ++k) sp.p[k] = re[k];
+            for (int k = 0; k <= plan->n_segments; ++k) sp.off[k] = plan->rhs_off[k];
+            reduce_kernel<<<grid_for(plan->rhs.n_unique, 256), 256, 0, s>>>(
+                plan->rhs.n_unique, (const uint32_t *)plan->rhs.seg_ptr.p, (const uint32_t *)plan->rhs.perm.p,
+                (const int32_t *)plan->rhs.pos.p, sp, 1, rhs);
+            NFA_LAUNCH_CHECK();
+        }
+    }
+    return 0;
+}
+
+// ---- SpMV: one warp per row, lanes stride the row, xor-shuffle tree (fixed order => deterministic) --------
+__global__ void spmv_kernel(int64_t n_rows, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                            const double *__restrict__ vals, const double *__restrict__ x, int accumulate,
+                            double *__restrict__ y) {
+    int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    double acc = 0.0;
+    for (int32_t k = indptr[row] + lane; k < indptr[row + 1]; k += 32) acc += vals[k] * x[indices[k]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = accumulate ? y[row] + acc : acc;
+}
+
+extern "C" int nfa_csr_spmv(const nfa_plan *plan, const double *vals, const double *x, int accumulate, double *y,
+                            nfa_stream stream) {
+    if (!plan) return fail("nfa_csr_spmv: plan is NULL");
+    int64_t threads = plan->n_dof * 32;
+    spmv_kernel<<<grid_for(threads, 256), 256, 0, (cudaStream_t)stream>>>(plan->n_dof, plan->d_indptr(),
+                                                                         plan->d_indices(), vals, x, accumulate, y);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,70 @@
+// Plan objects behind the opaque handles of include/nfa.h.
+#pragma once
+#include "nfa_common.cuh"
+
+#define NFA_MAX_SEGMENTS 16
+
+namespace nfa {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    int alloc(size_t bytes);
+    void release();
+};
+
+// Deterministic gather list: output u sums entries perm[seg_ptr[u] .. seg_ptr[u+1]) (ascending entry id =
+// reference call order) into position pos[u] (identity when pos is empty).
+struct GatherSet {
+    int64_t n_unique = 0;
+    DevBuf seg_ptr;  // uint32 [n_unique + 1]
+    DevBuf perm;     // uint32 [n_entries]
+    DevBuf pos;      // int32  [n_unique] or empty
+};
+
+}  // namespace nfa
+
+struct nfa_plan {
+    int64_t n_dof = 0, nnz = 0;
+    nfa::DevBuf indptr, indices;     // int32, owned unless base/bplan-backed
+    const nfa_plan *base = nullptr;  // pattern owner when merged into another plan
+    const int32_t *ext_indptr = nullptr, *ext_indices = nullptr;  // pattern owned by a block plan
+    int n_segments = 0;
+    int64_t n_items[NFA_MAX_SEGMENTS] = {0};
+    int32_t n_loc[NFA_MAX_SEGMENTS] = {0};
+    int with_matrix[NFA_MAX_SEGMENTS] = {0};
+    int64_t mat_off[NFA_MAX_SEGMENTS + 1] = {0}, rhs_off[NFA_MAX_SEGMENTS + 1] = {0};
+    nfa::GatherSet mat, rhs;
+
+    const int32_t *d_indptr() const {
+        if (base) return base->d_indptr();
+        return ext_indptr ? ext_indptr : (const int32_t *)indptr.p;
+    }
+    const int32_t *d_indices() const {
+        if (base) return base->d_indices();
+        return ext_indices ? ext_indices : (const int32_t *)indices.p;
+    }
+};
+
+// Node-block plan of the fused H1 path.  Block row N = node N; its columns (node ids, ascending) are
+// bcols[bptr[N] .. bptr[N+1]).  The scalar CSR follows: rows n_comp*N + i, columns n_comp*M + j.
+// Work is cut into CTA chunks of whole block rows; a chunk lists its contributions (cell, a, b) ordered by
+// cell so that geometry loads broadcast, each with the staging slot that orders the sum by ascending cell.
+struct nfa_bplan {
+    int64_t n_nodes = 0, n_cells = 0, n_bnz = 0, n_contrib = 0;
+    int n_phi = 0, n_comp = 0;
+    int64_t n_chunks = 0;
+    int max_chunk_contrib = 0, max_chunk_bnz = 0;
+    nfa::DevBuf bptr;         // int32 [n_nodes + 1]
+    nfa::DevBuf bcols;        // int32 [n_bnz]
+    nfa::DevBuf bseg;         // uint32 [n_bnz + 1]  contribution range of each block (output order)
+    nfa::DevBuf chunk_row;    // int32 [n_chunks + 1] first block row of each chunk
+    nfa::DevBuf contrib;      // uint32 [n_contrib]  (cell-ordered within chunk): cell * n_phi^2 + a * n_phi + b
+    nfa::DevBuf contrib_slot; // uint16 [n_contrib]  staging slot within the chunk (output order)
+    nfa::DevBuf indptr, indices;  // scalar CSR pattern int32
+    nfa::DevBuf geo;              // scratch: per-cell geometry records [n_cells][12], rewritten every assembly
+};

@@ -1,0 +1,147 @@
+"""Shared set-up of the parity tests: the same problem described once for the GPU path and once for the oracle."""
+import numpy as np
+
+from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
+from nfempy_b200.spaces import ProductSpace
+from oracle import ref_assembly, ref_forms
+from oracle.ref_mesh import RefMesh
+from oracle.ref_spaces import RefProductSpace
+
+
+def compare_csr(got, ref, rtol=1e-12, label=""):
+    """Pattern bit-exact; values within ``rtol`` of max(|ref|, largest |ref| of the row); rhs likewise vs its max."""
+    indptr_g, indices_g, data_g, rhs_g = got
+    indptr_r, indices_r, data_r, rhs_r = ref
+    assert indptr_g.dtype == np.int32 and indices_g.dtype == np.int32, "CSR index arrays must be int32"
+    assert np.array_equal(indptr_g, indptr_r), label + " indptr differs"
+    assert np.array_equal(indices_g, indices_r), label + " indices differ"
+    rows = np.repeat(np.arange(len(indptr_r) - 1), np.diff(indptr_r))
+    row_max = np.zeros(len(indptr_r) - 1)
+    np.maximum.at(row_max, rows, np.abs(data_r))
+    scale = np.maximum(np.abs(data_r), row_max[rows])
+    err = np.abs(data_g - data_r) / np.where(scale > 0, scale, 1.0)
+    assert err.max(initial=0.0) <= rtol, "%s matrix values: max scaled error %.3e" % (label, err.max())
+    rscale = max(np.abs(rhs_r).max(initial=0.0), 1e-300)
+    rerr = np.abs(rhs_g - rhs_r).max(initial=0.0) / rscale
+    assert rerr <= rtol, "%s rhs: max scaled error %.3e" % (label, rerr)
+    return err.max(initial=0.0), rerr
+
+
+def _f_rhs(x, y, z):
+    return np.array([np.sin(np.pi * x) * y, np.cos(np.pi * y) * z + 1.0, x * y * z - 0.5])
+
+
+def _u_exact(x, y, z):
+    return np.array([(1 - x) * x * y, np.sin(x) + z, 0.25 * z * z + y])
+
+
+class Case:
+    def __init__(self, mesh, data_fn, tags, btags, gpu_forms, ref_forms_fn, disc=None, alpha_fn=None):
+        self.mesh, self.data_fn, self.tags, self.btags = mesh, data_fn, tags, btags
+        self.gpu_forms, self.ref_forms_fn, self.disc, self.alpha_fn = gpu_forms, ref_forms_fn, disc or {}, alpha_fn
+
+    def space(self):
+        s = ProductSpace(self.data_fn(self.mesh))
+        s.make_subspaces_discontinuous(self.disc)
+        s.build_structures(self.tags, self.btags)
+        return s
+
+    def ref_space(self):
+        r = RefMesh(self.mesh.dimension, self.mesh.points, self.mesh._blocks)
+        r.build_conformal_mesh()
+        s = RefProductSpace(self.data_fn(r))
+        s.make_subspaces_discontinuous(self.disc)
+        s.build_structures(self.tags, self.btags)
+        return s
+
+    def run_gpu(self, allow_fused=True):
+        from nfempy_b200.assembly import GPUAssembler
+
+        space = self.space()
+        alpha = np.zeros(space.n_dof) if self.alpha_fn is None else self.alpha_fn(space.n_dof)
+        asm = GPUAssembler(space, None, np.zeros(space.n_dof), allow_fused=allow_fused)
+        asm.form_to_input_list = self.gpu_forms(space, alpha)
+        return asm.assemble()
+
+    def run_oracle(self):
+        space = self.ref_space()
+        alpha = np.zeros(space.n_dof) if self.alpha_fn is None else self.alpha_fn(space.n_dof)
+        return ref_assembly.assemble(space, self.ref_forms_fn(space), alpha)
+
+
+def elasticity_case(n=2, with_bc=True, varying=False, alpha=False, k=2, dim=3, mesh=None, neumann=False):
+    from nfempy_b200.weak_forms import LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet, LEPrimalWeakFormBCNeumann
+
+    if mesh is None:
+        mesh = box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(n, jitter=0.2)
+    btag_list = [2, 3, 4, 5, 6, 7] if dim == 3 else [2, 3, 4, 5]
+    if varying:
+        f_lam = lambda x, y, z: 1.0 + x + 2.0 * y * y
+        f_mu = lambda x, y, z: 2.0 + np.sin(z + x)
+    else:
+        f_lam = lambda x, y, z: 3.0 * np.ones_like(x)
+        f_mu = lambda x, y, z: 0.5 * np.ones_like(x)
+    rhs = _f_rhs if dim == 3 else (lambda x, y, z: _f_rhs(x, y, z)[:2])
+    uex = _u_exact if dim == 3 else (lambda x, y, z: _u_exact(x, y, z)[:2])
+    functions = {"rhs": rhs, "lambda": f_lam, "mu": f_mu}
+    bc_functions = {"u": uex}
+    t_functions = {"t": rhs}
+    dir_tags = btag_list[:-1] if neumann else btag_list
+
+    def gpu_forms(space, a):
+        wf = LEPrimalWeakForm(space)
+        wf.functions = functions
+        out = {"volume": ["form", range(len(space.discrete_spaces["u"].elements)), wf, a]}
+        if with_bc:
+            bf = LEPrimalWeakFormBCDirichlet(space)
+            bf.functions = bc_functions
+            out["bc"] = ["bc_form", range(len(space.discrete_spaces["u"].bc_elements)), bf, a]
+        return out
+
+    def ref_forms_fn(space):
+        out = [("form", ref_forms.le_primal, functions, len(space.discrete_spaces["u"].element_ids))]
+        if with_bc:
+            out.append(("bc_form", ref_forms.le_primal_bc_dirichlet, bc_functions, len(space.discrete_spaces["u"].bc_element_ids)))
+        return out
+
+    alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None
+    return Case(
+        mesh, lambda g: {"u": (dim, dim, "Lagrange", k, g)}, {"u": [1]}, {"u": dir_tags if with_bc else []},
+        gpu_forms, ref_forms_fn, alpha_fn=alpha_fn,
+    )
+
+
+def laplace_case(n=4, dim=2, k=1, with_bc=True, varying=False, alpha=False, mesh=None):
+    from nfempy_b200.weak_forms import LaplacePrimalWeakForm, LaplacePrimalWeakFormBCDirichlet
+
+    if mesh is None:
+        mesh = square_tri_mesh(n, jitter=0.2) if dim == 2 else box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True)
+    btag_list = [2, 3, 4, 5] if dim == 2 else [2, 3, 4, 5, 6, 7]
+    kappa = (lambda x, y, z: 1.0 + x * x + y) if varying else (lambda x, y, z: 2.0)
+    functions = {
+        "rhs": lambda x, y, z: np.array([2.0 * np.pi**2 * np.sin(np.pi * x) * np.sin(np.pi * y) + z]),
+        "kappa": kappa,
+    }
+    bc_functions = {"p": lambda x, y, z: np.array([np.sin(np.pi * x) + y])}
+
+    def gpu_forms(space, a):
+        wf = LaplacePrimalWeakForm(space)
+        wf.functions = functions
+        out = {"volume": ["form", range(len(space.discrete_spaces["p"].elements)), wf, a]}
+        if with_bc:
+            bf = LaplacePrimalWeakFormBCDirichlet(space)
+            bf.functions = bc_functions
+            out["bc"] = ["bc_form", range(len(space.discrete_spaces["p"].bc_elements)), bf, a]
+        return out
+
+    def ref_forms_fn(space):
+        out = [("form", ref_forms.laplace_primal, functions, len(space.discrete_spaces["p"].element_ids))]
+        if with_bc:
+            out.append(("bc_form", ref_forms.laplace_primal_bc_dirichlet, bc_functions, len(space.discrete_spaces["p"].bc_element_ids)))
+        return out
+
+    alpha_fn = (lambda nd: np.sin(np.arange(nd) * 0.61) + 0.3) if alpha else None
+    return Case(
+        mesh, lambda g: {"p": (dim, 1, "Lagrange", k, g)}, {"p": [1]}, {"p": btag_list if with_bc else []},
+        gpu_forms, ref_forms_fn, alpha_fn=alpha_fn,
+    )

@@ -1,0 +1,138 @@
+"""GPU parity tests (run on the B200 box with -m gpu): CUDA path through the C ABI vs the cell-by-cell oracle.
+
+Bar: CSR pattern bit-exact (int32 indptr/indices identical), FP64 values within 1e-12 of the oracle relative to
+max(|value|, largest |value| in its row); see tests/parity_helpers.compare_csr.
+"""
+import numpy as np
+import pytest
+
+from tests.parity_helpers import compare_csr, elasticity_case, laplace_case
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("with_bc", [False, True])
+def test_elasticity_p2_3d(fused, with_bc):
+    case = elasticity_case(n=2, with_bc=with_bc)
+    compare_csr(case.run_gpu(allow_fused=fused), case.run_oracle(), RTOL)
+
+
+def test_elasticity_p2_3d_varying_coefficients():
+    case = elasticity_case(n=2, with_bc=True, varying=True)
+    compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_elasticity_p2_3d_nonzero_alpha(fused):
+    case = elasticity_case(n=2, with_bc=True, alpha=True)
+    compare_csr(case.run_gpu(allow_fused=fused), case.run_oracle(), RTOL)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_elasticity_p1_3d(fused):
+    case = elasticity_case(n=2, with_bc=True, k=1)
+    compare_csr(case.run_gpu(allow_fused=fused), case.run_oracle(), RTOL)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("k", [1, 2])
+def test_elasticity_2d(fused, k):
+    case = elasticity_case(n=3, with_bc=True, k=k, dim=2)
+    compare_csr(case.run_gpu(allow_fused=fused), case.run_oracle(), RTOL)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("k", [1, 2])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_laplace(fused, k, dim):
+    case = laplace_case(n=4 if dim == 2 else 2, dim=dim, k=k, with_bc=True)
+    compare_csr(case.run_gpu(allow_fused=fused), case.run_oracle(), RTOL)
+
+
+def test_laplace_varying_kappa_and_alpha():
+    case = laplace_case(n=4, dim=2, k=2, with_bc=True, varying=True, alpha=True)
+    compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
+
+
+def test_evaluate_form_single_cell_matches_oracle():
+    from nfempy_b200.weak_forms import LEPrimalWeakForm
+    from oracle import ref_forms
+
+    case = elasticity_case(n=1, with_bc=False, varying=True)
+    space, rspace = case.space(), case.ref_space()
+    wf = LEPrimalWeakForm(space)
+    wf.functions = case.gpu_forms(space, None)["volume"][2].functions
+    rng = np.random.default_rng(0)
+    for iel in range(len(space.discrete_spaces["u"].elements)):
+        alpha_l = rng.standard_normal(30)
+        r, j = wf.evaluate_form(iel, alpha_l)
+        r0, j0 = ref_forms.le_primal(rspace, wf.functions, iel, alpha_l)
+        s = np.abs(j0).max()
+        assert np.abs(j - j0).max() <= RTOL * s
+        assert np.abs(r - r0).max() <= RTOL * max(np.abs(r0).max(), s)
+
+
+def test_bitwise_deterministic():
+    case = elasticity_case(n=3, with_bc=True, alpha=True)
+    a = case.run_gpu(allow_fused=True)
+    b = case.run_gpu(allow_fused=True)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    c = case.run_gpu(allow_fused=False)
+    d = case.run_gpu(allow_fused=False)
+    assert np.array_equal(c[2], d[2]) and np.array_equal(c[3], d[3])
+
+
+def test_fused_equals_two_stage_midsize():
+    """8 x 8 x 8 x 6 = 3072 tets: too slow for the oracle, so the two CUDA paths check each other + invariants."""
+    import scipy.sparse as sp
+
+    case = elasticity_case(n=8, with_bc=False)
+    f = case.run_gpu(allow_fused=True)
+    g = case.run_gpu(allow_fused=False)
+    compare_csr(f, g, RTOL)
+    A = sp.csr_matrix((f[2], f[1], f[0]))
+    n = A.shape[0] // 3
+    scale = np.abs(f[2]).max()
+    assert abs(A - A.T).max() <= 1e-13 * scale
+    for c in range(3):  # rigid translations are in the null space of the stiffness matrix
+        t = np.zeros(3 * n)
+        t[c::3] = 1.0
+        assert np.abs(A @ t).max() <= 1e-12 * scale
+
+
+def test_empty_sequence_and_reassembly_accumulates():
+    from nfempy_b200.assembly import GPUAssembler
+
+    case = elasticity_case(n=2, with_bc=True)
+    space = case.space()
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+    asm.form_to_input_list = case.gpu_forms(space, np.zeros(space.n_dof))
+    ip, ix, d1, r1 = asm.assemble()
+    d1, r1 = d1.copy(), r1.copy()
+    asm.scatter_forms()  # second scatter without zeroing: PETSc ADD_VALUES semantics
+    _, _, d2 = asm.jacobian.getValuesCSR()
+    # (v + b) + v + b differs from 2 (v + b) by round-off only
+    assert np.allclose(d2, 2.0 * d1, rtol=1e-14, atol=0.0)
+    assert np.allclose(asm.residual, 2.0 * r1, rtol=1e-13, atol=1e-13 * np.abs(r1).max())
+    asm.jacobian.scale(0.0)
+    asm.residual[:] = 0.0
+    asm.scatter_forms()
+    assert np.array_equal(asm.jacobian.getValuesCSR()[2], d1)
+
+
+def test_unknown_form_raises():
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.weak_forms import WeakForm
+
+    class HostOnly(WeakForm):
+        def evaluate_form(self, element_index, alpha):
+            return None
+
+    case = elasticity_case(n=1, with_bc=False)
+    space = case.space()
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+    asm.form_to_input_list = {"x": ["form", range(6), HostOnly(space), np.zeros(space.n_dof)]}
+    with pytest.raises(NotImplementedError):
+        asm.scatter_forms()
