@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""Headline benchmark: elements/s assembled, 3-D linear elasticity, vector H1 p=2 (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
+    python bench.py --impl reference ...                    # the reference algorithm on the host cores (oracle port)
+
+Workload: unit cube, 55^3 cubes x 6 Kuhn tets = 998 250 tets per GPU, interior vertices jittered
+(rng 1234), P2 x 3 displacement, lambda = mu = 1, smooth trigonometric load tabulated at the 27 quadrature points of
+every cell (the API-faithful general load), alpha = 0.  One step = one complete assembly of the CSR values and the
+right-hand side: geometry records -> fused local-contraction + deterministic global reduce -> load vector ->
+right-hand-side reduce.  The sparsity plan is built once, outside the timed region, and reported separately.
+
+At N > 1 every rank assembles its own z-slab of an N-times taller box (cells are partitioned, no data-path
+collective inside the timed step; weak scaling).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--n", type=int, default=55, help="cubes per box edge (55 -> 998250 tets)")
+    ap.add_argument("--cpu-cells", type=int, default=240, help="cells in the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def f_load(x, y, z):
+    return np.array(
+        [np.sin(np.pi * x) * np.cos(np.pi * y), np.cos(np.pi * y) * np.sin(np.pi * z), np.sin(np.pi * z) * np.cos(np.pi * x)]
+    )
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (reference algorithm, cell by cell) on a bounded sample of the same workload
+def _oracle_cells(args):
+    """Assemble ``cells`` tets (volume form + reference scatter) with the oracle; returns seconds."""
+    n_box, lo, hi = args
+    from nfempy_b200.mesh.generators import box_tet_points_cells
+    from oracle import ref_assembly, ref_forms
+    from oracle.ref_mesh import RefMesh
+    from oracle.ref_spaces import RefProductSpace
+
+    points, tets, _, _ = box_tet_points_cells(n_box, jitter=0.2, seed=1234)
+    sub = tets[lo:hi]
+    used, inv = np.unique(sub, return_inverse=True)
+    mesh = RefMesh(3, points[used], [("tetra", inv.reshape(sub.shape), np.ones(len(sub), dtype=np.int64))])
+    mesh.build_conformal_mesh()
+    space = RefProductSpace({"u": (3, 3, "Lagrange", 2, mesh)})
+    space.build_structures({"u": [1]}, {})
+    functions = {"rhs": f_load, "lambda": lambda x, y, z: np.ones_like(x), "mu": lambda x, y, z: np.ones_like(x)}
+    t0 = time.perf_counter()
+    ref_assembly.assemble(space, [("form", ref_forms.le_primal, functions, len(sub))])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(n_box, n_cells, workers):
+    """elements/s of the oracle port over ``workers`` processes, each assembling ``n_cells / workers`` tets."""
+    import multiprocessing as mp
+
+    per = max(1, n_cells // workers)
+    jobs = [(n_box, w * per, (w + 1) * per) for w in range(workers)]
+    t0 = time.perf_counter()
+    if workers == 1:
+        _oracle_cells(jobs[0])
+    else:
+        with mp.get_context("spawn").Pool(workers) as pool:
+            pool.map(_oracle_cells, jobs)
+    wall = time.perf_counter() - t0
+    return per * workers / wall, per * workers, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(cores, (args.cpu_cells // cores) * cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(min(args.n, 8), cores, cores)
+    times = []
+    for _ in range(args.steps):
+        v, cells, wall = cpu_baseline(min(args.n, 8), per_step, cores)
+        times.append(wall)
+    total = sum(times)
+    value = per_step * args.steps / total
+    sample = "%d tets per step (first tets of the jittered Kuhn box), oracle port of the reference algorithm" % per_step
+    line = {
+        "impl": "reference", "metric": "elements/s assembled (3D elasticity p=2)", "value": value, "unit": "elements/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D Cauchy elasticity, vector H1 p=2, Kuhn-tet unit cube (bounded CPU sample)",
+                   "cells_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the true reference (basix + auto_diff + PETSc) cannot be installed here; this times oracle/ on host cores",
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            tok = [t.strip() for t in ln.split(",")]
+            if len(tok) < 9:
+                continue
+            try:
+                sm.append(float(tok[1]))
+                mx.append(float(tok[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], tok[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_graft(args):
+    import torch
+    import torch.distributed as dist
+
+    from nfempy_b200 import _lib
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.mesh import box_tet_mesh
+    from nfempy_b200.spaces import ProductSpace
+    from nfempy_b200.weak_forms import LEPrimalWeakForm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the assembly path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load()
+
+    # ---- workload: rank r owns the z-slab [r, r+1) of an n x n x (n * world) box
+    t0 = time.perf_counter()
+    mesh = box_tet_mesh(args.n, jitter=0.2, seed=1234 + rank)
+    space = ProductSpace({"u": (3, 3, "Lagrange", 2, mesh)})
+    space.build_structures({"u": [1]}, {})
+    n_cells = len(space.discrete_spaces["u"].elements)
+    t_host = time.perf_counter() - t0
+    form = LEPrimalWeakForm(space)
+    form.functions = {"rhs": f_load, "lambda": lambda x, y, z: np.ones_like(x), "mu": lambda x, y, z: np.ones_like(x)}
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof), device=device)
+    asm.form_to_input_list = {"volume": ["form", range(n_cells), form, np.zeros(space.n_dof)]}
+    t0 = time.perf_counter()
+    state = asm.prepare()
+    torch.cuda.synchronize()
+    t_prepare = time.perf_counter() - t0
+    dev, entries, datas, dests, plan, key = state
+    nnz = plan.nnz
+    rhs_dev = torch.zeros(plan.n_dof, dtype=torch.float64, device=device)
+
+    def step():
+        asm.jacobian.is_zero = True  # fresh assembly: the fused kernel overwrites every value
+        rhs_dev.zero_()
+        asm.run(state, rhs_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    lib.nfa_timing_enable(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0 + args.steps  # + rhs_dev.zero_() per step (torch fill kernel)
+    k_ms, k_n = ctypes.c_double(), ctypes.c_int64()
+    _lib.check(lib.nfa_timing_read(ctypes.byref(k_ms), ctypes.byref(k_n)), "nfa_timing_read")
+    lib.nfa_timing_enable(0)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = n_cells * world / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant (fused) kernel; algorithmic bytes per tet, SURVEY.md 8(d)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    nnz_per_tet = nnz / n_cells
+    b_kernel = 112.0 + 40.0 + 16.0 + 8.0 * nnz_per_tet  # node ids + coords gather, dof table, lambda/mu, CSR values
+    b_step = b_kernel + 8.0 * plan.n_dof / n_cells + 27 * 3 * 8.0  # + rhs rows + tabulated load
+    kernel_ms = k_ms.value / max(k_n.value, 1)
+    achieved = b_kernel * n_cells / (kernel_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "kernel": "fused_h1_kernel<3,0>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_tet": b_kernel,
+        "peak_source": peak_src, "step_frac": b_step * n_cells / (ms_step * 1e-3) / 1e9 / peak,
+        "step_algorithmic_bytes_per_tet": b_step,
+    }
+
+    # ---- end to end through the host-buffer API: H2D of every input, kernels, D2H of CSR values + rhs
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, rhs_dev)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cells, wall = cpu_baseline(min(args.n, 8), args.cpu_cells, 1)
+        cpu = {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
+               "sample": "%d tets of the same jittered Kuhn box, oracle port (cell-by-cell numpy restatement of the "
+                         "reference, dict-of-keys scatter), %.1f s" % (cells, wall)}
+    if rank == 0:
+        line = {
+            "metric": "elements/s assembled (3D elasticity p=2)", "value": value, "unit": "elements/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "3D Cauchy linear elasticity, vector H1 p=2, %d tets per GPU (Kuhn box n=%d, jittered), "
+                            "lambda=mu=1, tabulated load, CSR values + rhs" % (n_cells, args.n),
+                "cells_per_gpu": n_cells, "n_dof_per_gpu": plan.n_dof, "nnz_per_gpu": nnz,
+                "nonzeros_per_s": nnz * world / (ms_step * 1e-3),
+                "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % ((b_step * n_cells + 6 * 100 * n_cells) / 1e9),
+                "plan_build_s": plan.build_seconds, "host_mesh_space_s": t_host, "prepare_s": t_prepare,
+                "path": "fused" if plan.fused_index is not None else "two-stage",
+            },
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, rhs_dev):
+    """Same step, host buffers in and out: pinned coords / connectivity / coefficient / load arrays are copied to
+    the device every step and the CSR values + rhs are copied back."""
+    from nfempy_b200 import _lib
+
+    dev, entries, datas, dests, plan, key = state
+    data = datas[0]
+    host_in = {
+        "coords": dev.coords.cpu().pin_memory(), "cell_nodes": data.cell_nodes.cpu().pin_memory(),
+        "f": data.f.cpu().pin_memory(), "lambda": data.coefs["lambda"][0].cpu().pin_memory(),
+        "mu": data.coefs["mu"][0].cpu().pin_memory(),
+    }
+    host_vals = torch.empty(plan.nnz, dtype=torch.float64).pin_memory()
+    host_rhs = torch.empty(plan.n_dof, dtype=torch.float64).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+    d2h = host_vals.numel() * 8 + host_rhs.numel() * 8
+
+    def step():
+        dev.coords.copy_(host_in["coords"], non_blocking=True)
+        data.cell_nodes.copy_(host_in["cell_nodes"], non_blocking=True)
+        data.f.copy_(host_in["f"], non_blocking=True)
+        data.coefs["lambda"][0].copy_(host_in["lambda"], non_blocking=True)
+        data.coefs["mu"][0].copy_(host_in["mu"], non_blocking=True)
+        asm.jacobian.is_zero = True
+        rhs_dev.zero_()
+        asm.run(state, rhs_dev)
+        host_vals.copy_(asm.jacobian.values_dev, non_blocking=True)
+        host_rhs.copy_(rhs_dev, non_blocking=True)
+
+    steps = max(3, min(args.steps, 5))
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"value": n_cells * world / (ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": ms, "steps": steps}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_graft(a)

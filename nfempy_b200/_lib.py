@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnfa.so")
+LIB_PATH = os.environ.get("NFA_LIB", os.path.join(_HERE, "csrc", "libnfa.so"))
 
 _c_i32p = ctypes.POINTER(ctypes.c_int32)
 _c_i64p = ctypes.POINTER(ctypes.c_int64)

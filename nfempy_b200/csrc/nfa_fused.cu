@@ -19,10 +19,16 @@ using namespace nfa;
 
 namespace {
 
-constexpr int FUSED_THREADS = 256;
+#ifndef NFA_FUSED_THREADS
+#define NFA_FUSED_THREADS 256
+#endif
+#ifndef NFA_FUSED_MINBLOCKS
+#define NFA_FUSED_MINBLOCKS 4
+#endif
+constexpr int FUSED_THREADS = NFA_FUSED_THREADS;
 
 __global__ void fill_block_keys(const int32_t *__restrict__ node_dest, int64_t n_cells, int n_phi, int64_t n_nodes,
-                                uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+                                int pair_bits, uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int p2 = n_phi * n_phi;
     if (e >= n_cells * p2) return;
@@ -31,7 +37,7 @@ __global__ void fill_block_keys(const int32_t *__restrict__ node_dest, int64_t n
     int a = r / n_phi, b = r - a * n_phi;
     uint64_t na = (uint64_t)node_dest[cell * n_phi + a], nb = (uint64_t)node_dest[cell * n_phi + b];
     keys[e] = na * (uint64_t)n_nodes + nb;
-    ids[e] = (uint32_t)e;
+    ids[e] = ((uint32_t)cell << pair_bits) | (uint32_t)r;  // ascending id == ascending (cell, a, b)
 }
 
 __global__ void block_cols(const uint64_t *__restrict__ ukeys, int64_t n, int64_t n_nodes, int32_t *__restrict__ bcols) {
@@ -79,12 +85,16 @@ __global__ void chunk_keys(const uint32_t *__restrict__ ids_sorted, int64_t n_co
     slots[k] = (uint32_t)(k - chunk_cstart[lo]);
 }
 
+// k = position in cell order; slots[k] = rank in output order (both relative to the chunk start):
+// contrib[k] = id, gather_pos[chunk start + output rank] = position in cell order
 __global__ void unpack_chunk_sorted(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ slots, int64_t n,
-                                    uint32_t *__restrict__ contrib, uint16_t *__restrict__ contrib_slot) {
+                                    const uint32_t *__restrict__ chunk_cstart, uint32_t *__restrict__ contrib,
+                                    uint16_t *__restrict__ gather_pos) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     contrib[k] = (uint32_t)(keys[k] & 0xffffffffull);
-    contrib_slot[k] = (uint16_t)slots[k];
+    uint32_t cs = chunk_cstart[keys[k] >> 32];
+    gather_pos[cs + slots[k]] = (uint16_t)(k - cs);
 }
 
 __global__ void scalar_pattern(const int32_t *__restrict__ bptr, const int32_t *__restrict__ bcols, int64_t n_nodes,
@@ -111,7 +121,7 @@ extern "C" void nfa_bplan_destroy(nfa_bplan *bp) { delete bp; }
 extern "C" int64_t nfa_bplan_nnz(const nfa_bplan *bp) { return bp ? bp->n_bnz * bp->n_comp * bp->n_comp : -1; }
 extern "C" int64_t nfa_bplan_bytes(const nfa_bplan *bp) {
     if (!bp) return -1;
-    return (int64_t)(bp->bptr.n + bp->bcols.n + bp->bseg.n + bp->chunk_row.n + bp->contrib.n + bp->contrib_slot.n +
+    return (int64_t)(bp->bptr.n + bp->bcols.n + bp->bseg.n + bp->chunk_row.n + bp->chunk_hdr.n + bp->contrib.n + bp->contrib_slot.n +
                      bp->indptr.n + bp->indices.n + bp->geo.n);
 }
 
@@ -139,8 +149,12 @@ extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const in
 
     DevBuf keys, keys_alt, ids, ids_alt, tmp, ukeys, counts, nruns;
     if (keys.alloc(8 * E) || keys_alt.alloc(8 * E) || ids.alloc(4 * E) || ids_alt.alloc(4 * E)) return bail(2);
-    fill_block_keys<<<grid_for(E, 256), 256, 0, s>>>(node_dest, n_cells, n_phi, n_nodes, (uint64_t *)keys.p,
-                                                     (uint32_t *)ids.p);
+    int pair_bits = 1;
+    while ((1 << pair_bits) < p2) ++pair_bits;
+    if ((n_cells << pair_bits) >= ((int64_t)1 << 32)) return bail(fail("nfa_bplan_create: too many cells for 32-bit contribution ids"));
+    bp->pair_bits = pair_bits;
+    fill_block_keys<<<grid_for(E, 256), 256, 0, s>>>(node_dest, n_cells, n_phi, n_nodes, pair_bits,
+                                                     (uint64_t *)keys.p, (uint32_t *)ids.p);
     count_launch();
     int end_bit = 1;
     while (end_bit < 64 && (((uint64_t)n_nodes * (uint64_t)n_nodes) >> end_bit) != 0) ++end_bit;
@@ -188,8 +202,8 @@ extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const in
     cudaMemcpyAsync(h_bptr.data(), bp->bptr.p, 4 * (n_nodes + 1), cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess) return bail(fail("nfa_bplan_create: block pattern build failed"));
     const int nc2 = n_comp * n_comp;
-    int cap_c = 1024, cap_b = 1024;
-    if (const char *e = getenv("NFA_FUSED_CAP")) cap_c = std::max(64, atoi(e));
+    int cap_c = 512, cap_b = 512;
+    if (const char *e = getenv("NFA_FUSED_CAP")) cap_c = cap_b = std::max(64, atoi(e));
     // staging must fit: cap_c * nc2 doubles (+ Mref) within ~200 KB
     std::vector<int32_t> chunk_row{0};
     std::vector<uint32_t> chunk_cstart{0};
@@ -218,7 +232,21 @@ extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const in
     bp->max_chunk_contrib = max_c;
     bp->max_chunk_bnz = max_b;
     DevBuf d_cstart;
-    if (bp->chunk_row.alloc(4 * chunk_row.size()) || d_cstart.alloc(4 * chunk_cstart.size())) return bail(2);
+    std::vector<int32_t> hdr(8 * (size_t)bp->n_chunks, 0);
+    for (int64_t c = 0; c < bp->n_chunks; ++c) {
+        int32_t ra = chunk_row[c], rz = chunk_row[c + 1];
+        uint32_t ca = chunk_cstart[c], cz = (c + 1 < bp->n_chunks) ? chunk_cstart[c + 1] : run;
+        hdr[8 * c + 0] = ra;
+        hdr[8 * c + 1] = rz - ra;
+        hdr[8 * c + 2] = h_bptr[ra];
+        hdr[8 * c + 3] = h_bptr[rz] - h_bptr[ra];
+        hdr[8 * c + 4] = (int32_t)ca;
+        hdr[8 * c + 5] = (int32_t)(cz - ca);
+    }
+    if (bp->chunk_row.alloc(4 * chunk_row.size()) || d_cstart.alloc(4 * chunk_cstart.size()) ||
+        bp->chunk_hdr.alloc(4 * hdr.size()))
+        return bail(2);
+    cudaMemcpyAsync(bp->chunk_hdr.p, hdr.data(), 4 * hdr.size(), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(bp->chunk_row.p, chunk_row.data(), 4 * chunk_row.size(), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(d_cstart.p, chunk_cstart.data(), 4 * chunk_cstart.size(), cudaMemcpyHostToDevice, s);
     // ---- reorder each chunk's contributions by (cell, a, b) = ascending id, remembering the staging slot
@@ -239,8 +267,8 @@ extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const in
         return bail(fail("nfa_bplan_create: chunk sort failed"));
     count_launch(8);
     if (bp->contrib.alloc(4 * E) || bp->contrib_slot.alloc(2 * E)) return bail(2);
-    unpack_chunk_sorted<<<grid_for(E, 256), 256, 0, s>>>(dk2.Current(), dv2.Current(), E, (uint32_t *)bp->contrib.p,
-                                                         (uint16_t *)bp->contrib_slot.p);
+    unpack_chunk_sorted<<<grid_for(E, 256), 256, 0, s>>>(dk2.Current(), dv2.Current(), E, (uint32_t *)d_cstart.p,
+                                                         (uint32_t *)bp->contrib.p, (uint16_t *)bp->contrib_slot.p);
     count_launch();
     // ---- scalar CSR pattern
     int64_t n_dof = n_nodes * n_comp, nnz = nb * nc2;
@@ -308,115 +336,191 @@ __global__ void geo_records_kernel(const double *__restrict__ coords, const int3
     }
 }
 
-template <int DIM, int FORM>
-__global__ void __launch_bounds__(FUSED_THREADS)
-    fused_h1_kernel(const int32_t *__restrict__ chunk_row, const int32_t *__restrict__ bptr,
+// Persistent CTAs stride over the chunks.  Per chunk:
+//   phase 1  one contribution per thread in cell order (geometry loads broadcast inside a warp); the block is staged
+//            at the thread's own position (consecutive 16-byte aligned records: no bank conflicts);
+//   phase 2a one CSR block per thread: gathers its contributions through gather_pos in ascending cell order into
+//            registers;
+//   phase 2b after a barrier the sums are written in CSR layout over the (now free) staging area;
+//   phase 2c linear, fully coalesced streaming copy of that tile to the CSR values in HBM.
+template <int DIM, int FORM, int MAXB>
+__global__ void __launch_bounds__(FUSED_THREADS, NFA_FUSED_MINBLOCKS)
+    fused_h1_kernel(int n_chunks, const int4 *__restrict__ chunk_hdr, const int32_t *__restrict__ bptr,
                     const uint32_t *__restrict__ bseg, const uint32_t *__restrict__ contrib,
-                    const uint16_t *__restrict__ contrib_slot, const double *__restrict__ geo,
-                    const double *__restrict__ Mref, int n_phi, int stage_cap, double *__restrict__ vals) {
+                    const uint16_t *__restrict__ gather_pos, const double *__restrict__ geo,
+                    const double *__restrict__ Mref, int n_phi, int pair_bits, int stage_cap, int block_cap,
+                    double *__restrict__ vals) {
     constexpr int NC = (FORM == 0) ? DIM : 1;
     constexpr int NC2 = NC * NC;
+    constexpr int SR = (NC2 + 1) & ~1;        // staging record stride (doubles), 16-byte aligned
+    constexpr int D2 = DIM * DIM;
+    constexpr int MR = (D2 + 1) & ~1;         // Mref record stride in shared memory
     constexpr int GS = GeoRec<DIM, FORM>::STRIDE;
     extern __shared__ double smem[];
     const int p2 = n_phi * n_phi;
-    double *s_M = smem;                              // [p2][DIM*DIM]
-    double *s_stage = s_M + p2 * DIM * DIM;          // [stage_cap][NC2]
-    int *s_rows = (int *)(s_stage + (size_t)stage_cap * NC2);  // [n_rows + 1] block offsets (relative to b0)
+    double *s_M = smem;                                        // [p2][MR]
+    double *s_stage = s_M + p2 * MR;                           // [stage_cap][SR]; reused as the output tile
+    int *s_bs = (int *)(s_stage + (size_t)stage_cap * SR);     // [n_blocks + 1] first contribution of each block
+    int *s_rows = s_bs + block_cap + 2;                        // [n_rows + 1] block offsets (relative to b0)
 
-    const int ch = blockIdx.x;
-    const int r0 = chunk_row[ch], r1 = chunk_row[ch + 1];
-    const int n_rows = r1 - r0;
-    const int b0 = bptr[r0], b1 = bptr[r1];
-    const uint32_t c0 = bseg[b0], c1 = bseg[b1];
+    for (int i = threadIdx.x; i < p2 * D2; i += FUSED_THREADS) s_M[(i / D2) * MR + (i % D2)] = __ldg(Mref + i);
+    const uint32_t pair_mask = (1u << pair_bits) - 1u;
 
-    for (int i = threadIdx.x; i < p2 * DIM * DIM; i += FUSED_THREADS) s_M[i] = Mref[i];
-    for (int i = threadIdx.x; i <= n_rows; i += FUSED_THREADS) s_rows[i] = bptr[r0 + i] - b0;
-    __syncthreads();
-
-    // ---- phase 1: one contribution per thread, cell-ordered
-    for (uint32_t k = c0 + threadIdx.x; k < c1; k += FUSED_THREADS) {
-        const uint32_t id = contrib[k];
-        const int slot = contrib_slot[k];
-        const uint32_t cell = id / (uint32_t)p2;
-        const int pair = (int)(id - cell * (uint32_t)p2);
-        const double *rec = geo + (int64_t)cell * GS;
-        const double *M = s_M + pair * DIM * DIM;
-        double *out = s_stage + (size_t)slot * NC2;
-        if constexpr (FORM == 0) {
-            double Ji[DIM][DIM];
-#pragma unroll
-            for (int q = 0; q < DIM * DIM; ++q) Ji[q / DIM][q % DIM] = __ldg(rec + q);
-            const double wl = __ldg(rec + DIM * DIM), wm = __ldg(rec + DIM * DIM + 1);
-            // P = Jinv^T M  (P[i][l] = sum_k Jinv[k][i] M[k][l]);  T = P Jinv (T[i][j] = sum_l P[i][l] Jinv[l][j])
-            double P[DIM][DIM], T[DIM][DIM];
-#pragma unroll
-            for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                for (int l = 0; l < DIM; ++l) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int kk = 0; kk < DIM; ++kk) v += Ji[kk][i] * M[kk * DIM + l];
-                    P[i][l] = v;
-                }
-            double tr = 0.0;
-#pragma unroll
-            for (int i = 0; i < DIM; ++i) {
-#pragma unroll
-                for (int j = 0; j < DIM; ++j) {
-                    double v = 0.0;
-#pragma unroll
-                    for (int l = 0; l < DIM; ++l) v += P[i][l] * Ji[l][j];
-                    T[i][j] = v;
-                }
-                tr += T[i][i];
-            }
-#pragma unroll
-            for (int i = 0; i < DIM; ++i)
-#pragma unroll
-                for (int j = 0; j < DIM; ++j) {
-                    double v = wl * T[i][j] + wm * T[j][i];
-                    if (i == j) v += wm * tr;
-                    out[i * DIM + j] = v;
-                }
-        } else {
-            double v = 0.0;
-            int t = 0;
-#pragma unroll
-            for (int kk = 0; kk < DIM; ++kk)
-#pragma unroll
-                for (int l = kk; l < DIM; ++l) {
-                    double gkl = __ldg(rec + t);
-                    ++t;
-                    v += gkl * (kk == l ? M[kk * DIM + l] : (M[kk * DIM + l] + M[l * DIM + kk]));
-                }
-            out[0] = v;
-        }
+    int ch = blockIdx.x;
+    int4 h0 = make_int4(0, 0, 0, 0), h1 = h0;
+    if (ch < n_chunks) {
+        h0 = __ldg(chunk_hdr + 2 * ch);
+        h1 = __ldg(chunk_hdr + 2 * ch + 1);
     }
     __syncthreads();
 
-    // ---- phase 2: one output scalar per thread, consecutive threads -> consecutive CSR values
-    const int n_blocks = b1 - b0;
-    const int64_t out_base = (int64_t)NC2 * b0;
-    for (int t = threadIdx.x; t < n_blocks * NC2; t += FUSED_THREADS) {
-        // locate block row: NC2 * s_rows[r] <= t < NC2 * s_rows[r + 1]
-        int lo = 0, hi = n_rows;
-        while (hi - lo > 1) {
-            int mid = (lo + hi) >> 1;
-            if (NC2 * s_rows[mid] <= t)
-                lo = mid;
-            else
-                hi = mid;
+    for (; ch < n_chunks; ch += gridDim.x) {
+        // chunk header: {r0, n_rows, b0, n_blocks}, {c0, n_contrib, -, -}
+        const int r0 = h0.x, n_rows = h0.y, b0 = h0.z, n_blocks = h0.w;
+        const uint32_t c0 = (uint32_t)h1.x, n_contrib = (uint32_t)h1.y;
+        const int next = ch + gridDim.x;
+        if (next < n_chunks) {  // prefetch the next header; consumed after this chunk's last barrier
+            h0 = __ldg(chunk_hdr + 2 * next);
+            h1 = __ldg(chunk_hdr + 2 * next + 1);
         }
-        const int rb = s_rows[lo], nb = s_rows[lo + 1] - rb;
-        const int local = t - NC2 * rb;   // within the row's NC rows x (NC * nb) values
-        const int i = local / (NC * nb);
-        const int v = local - i * NC * nb;
-        const int blk = v / NC, j = v - blk * NC;
-        const int u = b0 + rb + blk;
-        const uint32_t s0 = bseg[u] - c0, s1 = bseg[u + 1] - c0;
-        double acc = 0.0;
-        for (uint32_t sidx = s0; sidx < s1; ++sidx) acc += s_stage[(size_t)sidx * NC2 + i * NC + j];
-        vals[out_base + t] = acc;
+
+        uint32_t k = threadIdx.x;
+        uint32_t id = 0;
+        if (k < n_contrib) id = __ldg(contrib + c0 + k);
+        for (int i = threadIdx.x; i <= n_rows; i += FUSED_THREADS) s_rows[i] = __ldg(bptr + r0 + i) - b0;
+        for (int i = threadIdx.x; i <= n_blocks; i += FUSED_THREADS) s_bs[i] = (int)(__ldg(bseg + b0 + i) - c0);
+
+        // ---- phase 1
+        while (k < n_contrib) {
+            const uint32_t cell = id >> pair_bits;
+            const int pair = (int)(id & pair_mask);
+            const double2 *rec = reinterpret_cast<const double2 *>(geo + (int64_t)cell * GS);
+            double g[GS];
+#pragma unroll
+            for (int q = 0; q < GS / 2; ++q) {
+                double2 v = __ldg(rec + q);
+                g[2 * q] = v.x;
+                g[2 * q + 1] = v.y;
+            }
+            double2 *out = reinterpret_cast<double2 *>(s_stage + (size_t)k * SR);
+            k += FUSED_THREADS;
+            if (k < n_contrib) id = __ldg(contrib + c0 + k);  // prefetch while this one computes
+            const double2 *M2 = reinterpret_cast<const double2 *>(s_M + pair * MR);
+            double Mr[MR];
+#pragma unroll
+            for (int q = 0; q < MR / 2; ++q) {
+                double2 v = M2[q];
+                Mr[2 * q] = v.x;
+                Mr[2 * q + 1] = v.y;
+            }
+            double res[SR];
+            if constexpr (SR > NC2) res[SR - 1] = 0.0;
+            if constexpr (FORM == 0) {
+                const double wl = g[D2], wm = g[D2 + 1];
+                // P = Jinv^T M (P[i][l] = sum_k Jinv[k][i] M[k][l]);  T = P Jinv (T[i][j] = sum_l P[i][l] Jinv[l][j])
+                double P[DIM][DIM], T[DIM][DIM];
+#pragma unroll
+                for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                    for (int l = 0; l < DIM; ++l) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int kk = 0; kk < DIM; ++kk) v += g[kk * DIM + i] * Mr[kk * DIM + l];
+                        P[i][l] = v;
+                    }
+                double tr = 0.0;
+#pragma unroll
+                for (int i = 0; i < DIM; ++i) {
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int l = 0; l < DIM; ++l) v += P[i][l] * g[l * DIM + j];
+                        T[i][j] = v;
+                    }
+                    tr += T[i][i];
+                }
+#pragma unroll
+                for (int i = 0; i < DIM; ++i)
+#pragma unroll
+                    for (int j = 0; j < DIM; ++j) {
+                        double v = wl * T[i][j] + wm * T[j][i];
+                        if (i == j) v += wm * tr;
+                        res[i * DIM + j] = v;
+                    }
+            } else {
+                double v = 0.0;
+                int t = 0;
+#pragma unroll
+                for (int kk = 0; kk < DIM; ++kk)
+#pragma unroll
+                    for (int l = kk; l < DIM; ++l) {
+                        v += g[t] * (kk == l ? Mr[kk * DIM + l] : (Mr[kk * DIM + l] + Mr[l * DIM + kk]));
+                        ++t;
+                    }
+                res[0] = v;
+            }
+#pragma unroll
+            for (int q = 0; q < SR / 2; ++q) out[q] = make_double2(res[2 * q], res[2 * q + 1]);
+        }
+        __syncthreads();
+
+        // ---- phase 2a: one block per thread, contributions in ascending cell order
+        const uint16_t *gp = gather_pos + c0;
+        double acc[MAXB][NC2];
+        int where[MAXB], stride[MAXB];
+#pragma unroll
+        for (int m = 0; m < MAXB; ++m) {
+            const int blk = threadIdx.x + m * FUSED_THREADS;
+            where[m] = -1;
+            stride[m] = 0;
+#pragma unroll
+            for (int e = 0; e < NC2; ++e) acc[m][e] = 0.0;
+            if (blk < n_blocks) {
+                int lo = 0, hi = n_rows;  // block row: s_rows[lo] <= blk < s_rows[lo + 1]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_rows[mid] <= blk)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                const int rb = s_rows[lo], nb = s_rows[lo + 1] - rb;
+                where[m] = NC2 * rb + NC * (blk - rb);
+                stride[m] = NC * nb;
+                const int k0 = s_bs[blk], k1 = s_bs[blk + 1];
+                int pos = __ldg(gp + k0);
+                for (int kk = k0; kk < k1; ++kk) {
+                    const double2 *src = reinterpret_cast<const double2 *>(s_stage + (size_t)pos * SR);
+                    if (kk + 1 < k1) pos = __ldg(gp + kk + 1);
+                    double v[SR];
+#pragma unroll
+                    for (int q = 0; q < SR / 2; ++q) {
+                        double2 t = src[q];
+                        v[2 * q] = t.x;
+                        v[2 * q + 1] = t.y;
+                    }
+#pragma unroll
+                    for (int e = 0; e < NC2; ++e) acc[m][e] += v[e];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2b: sums in CSR layout over the staging area
+#pragma unroll
+        for (int m = 0; m < MAXB; ++m) {
+            if (where[m] >= 0) {
+#pragma unroll
+                for (int i = 0; i < NC; ++i)
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) s_stage[where[m] + i * stride[m] + j] = acc[m][i * NC + j];
+            }
+        }
+        __syncthreads();
+        // ---- phase 2c: coalesced streaming copy of the tile
+        double *dst = vals + (int64_t)NC2 * b0;
+        for (int v = threadIdx.x; v < n_blocks * NC2; v += FUSED_THREADS) __stcs(dst + v, s_stage[v]);
+        __syncthreads();
     }
 }
 
@@ -426,21 +530,31 @@ static int run_fused(const nfa_bplan *bp, const double *Mref, const double *coor
     constexpr int NC = (FORM == 0) ? DIM : 1;
     if (bp->n_comp != NC) return fail("fused H1: plan n_comp does not match the form");
     constexpr int GS = GeoRec<DIM, FORM>::STRIDE;
-    static_assert(GS <= 12, "geometry record exceeds the plan's scratch stride");
+    static_assert(GS <= 12 && GS % 2 == 0, "geometry record exceeds the plan's scratch stride");
     const DevBuf &geo = bp->geo;
     geo_records_kernel<DIM, FORM><<<grid_for(bp->n_cells, 128), 128, 0, s>>>(coords, cell_nodes, bp->n_cells, c0, s0,
                                                                              c1, s1, (double *)geo.p);
     NFA_LAUNCH_CHECK();
     int p2 = bp->n_phi * bp->n_phi;
-    int stage_cap = bp->max_chunk_contrib;
-    size_t smem = sizeof(double) * ((size_t)p2 * DIM * DIM + (size_t)stage_cap * NC * NC) + 4 * 1100;
-    auto kern = fused_h1_kernel<DIM, FORM>;
+    int stage_cap = bp->max_chunk_contrib, block_cap = bp->max_chunk_bnz;
+    constexpr int SR = (NC * NC + 1) & ~1, MR = (DIM * DIM + 1) & ~1;
+    size_t smem = sizeof(double) * ((size_t)p2 * MR + (size_t)stage_cap * SR) + sizeof(int) * (2 * (size_t)block_cap + 8);
+    const int maxb = (block_cap + FUSED_THREADS - 1) / FUSED_THREADS;
+    if (maxb > 4) return fail("fused H1: a chunk holds more blocks than the kernel is instantiated for");
+    auto kern = maxb <= 1 ? fused_h1_kernel<DIM, FORM, 1>
+                          : (maxb == 2 ? fused_h1_kernel<DIM, FORM, 2> : fused_h1_kernel<DIM, FORM, 4>);
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1, device = 0, n_sm = 148;
+    NFA_CUDA(cudaGetDevice(&device));
+    NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, smem));
+    if (per_sm < 1) return fail("fused H1: kernel does not fit on an SM");
+    int64_t grid = std::min<int64_t>(bp->n_chunks, (int64_t)n_sm * per_sm);
     if (timing_enabled()) timing_begin(s);
-    kern<<<(unsigned)bp->n_chunks, FUSED_THREADS, smem, s>>>(
-        (const int32_t *)bp->chunk_row.p, (const int32_t *)bp->bptr.p, (const uint32_t *)bp->bseg.p,
+    kern<<<(unsigned)grid, FUSED_THREADS, smem, s>>>(
+        (int)bp->n_chunks, (const int4 *)bp->chunk_hdr.p, (const int32_t *)bp->bptr.p, (const uint32_t *)bp->bseg.p,
         (const uint32_t *)bp->contrib.p, (const uint16_t *)bp->contrib_slot.p, (const double *)geo.p, Mref, bp->n_phi,
-        stage_cap, vals);
+        bp->pair_bits, stage_cap, block_cap, vals);
     if (timing_enabled()) timing_end(s);
     NFA_LAUNCH_CHECK();
     return 0;

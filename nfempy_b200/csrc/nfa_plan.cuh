@@ -56,15 +56,17 @@ struct nfa_plan {
 // cell so that geometry loads broadcast, each with the staging slot that orders the sum by ascending cell.
 struct nfa_bplan {
     int64_t n_nodes = 0, n_cells = 0, n_bnz = 0, n_contrib = 0;
-    int n_phi = 0, n_comp = 0;
+    int n_phi = 0, n_comp = 0, pair_bits = 0;
     int64_t n_chunks = 0;
     int max_chunk_contrib = 0, max_chunk_bnz = 0;
     nfa::DevBuf bptr;         // int32 [n_nodes + 1]
     nfa::DevBuf bcols;        // int32 [n_bnz]
     nfa::DevBuf bseg;         // uint32 [n_bnz + 1]  contribution range of each block (output order)
     nfa::DevBuf chunk_row;    // int32 [n_chunks + 1] first block row of each chunk
+    nfa::DevBuf chunk_hdr;    // int32 [n_chunks][8]: r0, n_rows, b0, n_blocks, c0, n_contrib, 0, 0
     nfa::DevBuf contrib;      // uint32 [n_contrib]  (cell-ordered within chunk): cell * n_phi^2 + a * n_phi + b
-    nfa::DevBuf contrib_slot; // uint16 [n_contrib]  staging slot within the chunk (output order)
+    nfa::DevBuf contrib_slot; // uint16 [n_contrib]  gather_pos: for the k-th contribution in output order, its
+                              // position in the chunk's cell order (= its staging slot)
     nfa::DevBuf indptr, indices;  // scalar CSR pattern int32
     nfa::DevBuf geo;              // scratch: per-cell geometry records [n_cells][12], rewritten every assembly
 };

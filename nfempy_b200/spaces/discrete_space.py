@@ -108,7 +108,8 @@ class DoFMap:
             if self.e_dofs[d] == 0:
                 continue
             sub = topo.mesh.sub_cells_of(dim, d)[topo.selected_local]
-            parts.append(self.entity_block(d, sub).reshape(len(sub), -1))
+            width = sub.shape[1] * int(self.e_dofs[d] * self.n_components)
+            parts.append(self.entity_block(d, sub).reshape(len(sub), width))
         if not parts:
             return np.zeros((len(topo.selected), 0), dtype=np.int64)
         return np.concatenate(parts, axis=1)
@@ -138,7 +139,8 @@ class DoFMap:
             if self.e_dofs[d] == 0:
                 continue
             sub = mesh.sub_cells_of(dim - 1, d)[local]
-            parts.append(self.entity_block(d, sub).reshape(len(sub), -1))
+            width = sub.shape[1] * int(self.e_dofs[d] * self.n_components)
+            parts.append(self.entity_block(d, sub).reshape(len(sub), width))
         if not parts:
             return np.zeros((len(local), 0), dtype=np.int64)
         return np.concatenate(parts, axis=1)

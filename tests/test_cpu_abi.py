@@ -1,0 +1,67 @@
+"""CPU tests of the drop-in boundary: libnfa.so loads, exports every symbol include/nfa.h declares, and the host
+layer refuses to compute without a GPU (no CPU fallback)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from nfempy_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "nfa.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(nfa_[a-z0-9_]+)\s*\(", text))
+
+
+def test_library_loads_and_reports_version():
+    lib = _lib.load()
+    assert lib.nfa_version() >= 100
+    assert isinstance(_lib.launch_count(), int)
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    declared = _declared()
+    assert len(declared) >= 20
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert declared <= exported, sorted(declared - exported)
+    assert declared == set(_lib.SIGNATURES), sorted(declared ^ set(_lib.SIGNATURES))
+
+
+def test_abi_has_no_torch_or_cxx_types_in_signatures():
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    nfa = [ln.split()[-1] for ln in out.splitlines() if " T " in ln and "nfa_" in ln.split()[-1]]
+    assert all(not s.startswith("_Z") for s in nfa)  # extern "C": unmangled
+    ldd = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in ldd and "c10" not in ldd
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_path_fails_loudly_without_gpu():
+    from nfempy_b200.assembly import GPUAssembler
+    from tests.parity_helpers import elasticity_case
+
+    case = elasticity_case(n=1, with_bc=False)
+    space = case.space()
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+    asm.form_to_input_list = case.gpu_forms(space, np.zeros(space.n_dof))
+    with pytest.raises(_lib.NfaError):
+        asm.scatter_forms()
+
+
+def test_product_does_not_import_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's cpu legs may touch oracle/."""
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "nfempy_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(base, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
+                    bad.append(os.path.join(base, f))
+    assert not bad, bad

@@ -1,0 +1,120 @@
+"""CPU tests: array-based mesh numbering, DoF numbering and destination tables vs the cell-by-cell oracle, and
+vs the committed numbering fixture of the reference's own gmsh mesh."""
+import numpy as np
+import pytest
+
+from nfempy_b200.mesh import Mesh, box_tet_mesh, square_tri_mesh
+from nfempy_b200.spaces import ProductSpace
+from oracle.ref_mesh import RefMesh
+from oracle.ref_spaces import RefProductSpace
+from tests.golden_cases import GOLDEN, load_mesh_blocks
+
+
+def _same_cells(mesh):
+    ref = RefMesh(mesh.dimension, mesh.points, mesh._blocks)
+    ref.build_conformal_mesh()
+    assert len(ref.cells) == mesh.n_cells
+    for c in ref.cells:
+        if c is None:
+            continue
+        p = mesh.cells[c.id]
+        assert p.dimension == c.dimension and p.material_id == c.material_id
+        assert np.array_equal(p.node_tags, c.node_tags)
+        for d in range(c.dimension + 1):
+            assert np.array_equal(p.sub_cells_ids[d], c.sub_cells_ids[d])
+    return ref
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_box_mesh_numbering_matches_oracle(shuffle):
+    _same_cells(box_tet_mesh(3, shuffle_local_nodes=shuffle))
+
+
+def test_square_mesh_numbering_matches_oracle():
+    _same_cells(square_tri_mesh(5, jitter=0.2))
+
+
+def test_reference_gmsh_fixture_numbering():
+    points, blocks = load_mesh_blocks("mesh_ex3_3d_l0.npz")
+    mesh = Mesh.from_arrays(3, points, blocks)
+    mesh.build_conformal_mesh()
+    z = np.load(GOLDEN + "/numbering_ex3_3d_l0.npz")
+    assert mesh.n_cells == len(z["dims"])
+    assert np.array_equal(mesh.cell_dimension(np.arange(mesh.n_cells)), z["dims"])
+    assert np.array_equal(mesh.material, z["material"])
+    assert np.array_equal(mesh.vol_edges, z["vol_edges"]) and np.array_equal(mesh.vol_faces, z["vol_faces"])
+    for dim in (1, 2, 3):
+        ids = mesh.ids_of_dimension(dim)
+        assert np.array_equal(mesh.node_tags_of(dim), z["node_tags"][ids, : dim + 1])
+    _same_cells(mesh)
+
+
+def test_mixed_block_order_materialisation():
+    """Tets listed BEFORE boundary triangles: sub-entities keep the tet's local node order (mesh.py:180-219)."""
+    m = box_tet_mesh(2)
+    blocks = [b for b in m._blocks if b[0] == "tetra"] + [b for b in m._blocks if b[0] != "tetra"]
+    m2 = Mesh.from_arrays(3, m.points, blocks)
+    m2.build_conformal_mesh()
+    _same_cells(m2)
+
+
+def _check_space(mesh, data_fn, tags, btags, disc=None):
+    ref = RefMesh(mesh.dimension, mesh.points, mesh._blocks)
+    ref.build_conformal_mesh()
+    ps = ProductSpace(data_fn(mesh))
+    rs = RefProductSpace(data_fn(ref))
+    for s in (ps, rs):
+        s.make_subspaces_discontinuous(disc or {})
+        s.build_structures(tags, btags)
+    assert ps.n_dof == rs.n_dof
+    first = ps.names[0]
+    n_el = len(ps.discrete_spaces[first].elements)
+    assert n_el == len(rs.discrete_spaces[first].element_ids)
+    for i in range(n_el):
+        assert np.array_equal(ps.destination_indexes(i), rs.destination_indexes(i))
+    n_bc = len(ps.discrete_spaces[first].bc_elements)
+    assert n_bc == len(rs.discrete_spaces[first].bc_element_ids)
+    for i in range(n_bc):
+        assert np.array_equal(ps.bc_destination_indexes(i), rs.bc_destination_indexes(i))
+    return ps
+
+
+def test_dof_numbering_vector_p2_3d():
+    mesh = box_tet_mesh(3, shuffle_local_nodes=True)
+    ps = _check_space(mesh, lambda g: {"u": (3, 3, "Lagrange", 2, g)}, {"u": [1]}, {"u": [2, 3, 4, 5, 6, 7]})
+    assert ps.destination_table().shape[1] == 30
+
+
+def test_dof_numbering_two_fields_with_discontinuous():
+    mesh = box_tet_mesh(2)
+    data = lambda g: {"u": (3, 3, "Lagrange", 2, g), "p": (3, 1, "Lagrange", 1, g)}
+    _check_space(mesh, data, {"u": [1], "p": [1]}, {"u": [2, 3]}, {"p": True})
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_dof_numbering_2d(k):
+    mesh = square_tri_mesh(4, jitter=0.1)
+    _check_space(mesh, lambda g: {"p": (2, 1, "Lagrange", k, g)}, {"p": [1]}, {"p": [2, 3, 4, 5]})
+
+
+def test_dof_shift_and_field_access():
+    mesh = box_tet_mesh(2)
+    ps = ProductSpace({"u": (3, 3, "Lagrange", 1, mesh)})
+    ps.build_structures({"u": [1]}, {})
+    base = ps.destination_indexes(3).copy()
+    ps.dof_shift = 100
+    assert np.array_equal(ps.destination_indexes(3), base + 100)
+    assert np.array_equal(ps.destination_indexes(3, "u"), base + 100)
+    with pytest.raises(ValueError):
+        ps.dof_shift = -1
+    with pytest.raises(TypeError):
+        ps.dof_shift = 1.5
+
+
+def test_empty_physical_tag_selects_no_cells():
+    """The reference's projector test passes tags that match nothing; the space is then empty."""
+    mesh = box_tet_mesh(2)
+    ps = ProductSpace({"u": (3, 1, "Lagrange", 1, mesh)})
+    ps.build_structures({"u": []}, {})
+    assert ps.n_dof == 0 and len(ps.discrete_spaces["u"].elements) == 0
+    assert ps.destination_table().shape[0] == 0
