@@ -119,9 +119,9 @@ def run_reference(args):
 class ClockSampler:
     """Samples nvidia-smi clocks and throttle reasons during the timed region."""
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
@@ -132,7 +132,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -140,9 +140,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, window=None, probe=None):
+        """``window`` / ``probe``: (t0, t1) host times of the timed region and of the identical load-probe loop that
+        follows it; samples inside the timed region are used when there are at least three, else the probe's."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -150,21 +152,34 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            tok = [t.strip() for t in ln.split(",")]
-            if len(tok) < 9:
-                continue
-            try:
-                sm.append(float(tok[1]))
-                mx.append(float(tok[2]))
-            except ValueError:
-                continue
-            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], tok[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+        def collect(lo, hi):
+            sm, mx, pw, reasons = [], [], [], set()
+            for stamp, ln in self.lines:
+                if lo is not None and not (lo <= stamp <= hi + 0.02):
+                    continue
+                tok = [t.strip() for t in ln.split(",")]
+                if len(tok) < 9:
+                    continue
+                try:
+                    sm.append(float(tok[1]))
+                    mx.append(float(tok[2]))
+                    pw.append(float(tok[3]))
+                except ValueError:
+                    continue
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for name, val in zip(names, tok[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, pw, reasons
+
+        which = "timed region"
+        sm, mx, pw, reasons = collect(*window) if window else collect(None, None)
+        if len(sm) < 3 and probe:
+            which = "load probe (same step loop, right after the timed region)"
+            sm, mx, pw, reasons = collect(*probe)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
+                "sampled": which}
 
 
 def run_graft(args):
@@ -217,26 +232,35 @@ def run_graft(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     lib.nfa_timing_enable(1)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    w1 = time.time()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0 + args.steps  # + rhs_dev.zero_() per step (torch fill kernel)
     k_ms, k_n = ctypes.c_double(), ctypes.c_int64()
     _lib.check(lib.nfa_timing_read(ctypes.byref(k_ms), ctypes.byref(k_n)), "nfa_timing_read")
     lib.nfa_timing_enable(0)
+    # load probe for the clock record: the same step loop for ~0.6 s (not part of any reported time)
+    p0 = time.time()
+    while time.time() - p0 < 0.6:
+        for _ in range(10):
+            step()
+        torch.cuda.synchronize()
+    p1 = time.time()
+    clocks = sampler.stop(window=(w0, w1), probe=(p0, p1))
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
