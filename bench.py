@@ -10,8 +10,9 @@ every cell (the API-faithful general load), alpha = 0.  One step = one complete 
 right-hand side: geometry records -> fused local-contraction + deterministic global reduce -> load vector ->
 right-hand-side reduce.  The sparsity plan is built once, outside the timed region, and reported separately.
 
-At N > 1 every rank assembles its own z-slab of an N-times taller box (cells are partitioned, no data-path
-collective inside the timed step; weak scaling).
+At N > 1 the mesh is an N-times longer box (N x 998 250 tets); every rank owns a contiguous x-slab of cells, assembles
+it with the same fused kernel (plus one halo layer of zero-weight cells) and the interface rows are summed onto their
+owners by an NCCL send/recv inside the timed step (weak scaling; nfempy_b200/assembly/sharding.py).
 """
 import argparse
 import ctypes
@@ -204,18 +205,27 @@ def run_graft(args):
     lib = _lib.load()
 
     # ---- workload: rank r owns the z-slab [r, r+1) of an n x n x (n * world) box
+    # (one global mesh of world x 998 250 tets, replicated host numbering; cells partitioned into x-slabs)
     t0 = time.perf_counter()
-    mesh = box_tet_mesh(args.n, jitter=0.2, seed=1234 + rank)
+    mesh = box_tet_mesh(args.n, jitter=0.2, seed=1234, nx=args.n * world)
     space = ProductSpace({"u": (3, 3, "Lagrange", 2, mesh)})
     space.build_structures({"u": [1]}, {})
-    n_cells = len(space.discrete_spaces["u"].elements)
     t_host = time.perf_counter() - t0
     form = LEPrimalWeakForm(space)
     form.functions = {"rhs": f_load, "lambda": lambda x, y, z: np.ones_like(x), "mu": lambda x, y, z: np.ones_like(x)}
-    asm = GPUAssembler(space, None, np.zeros(space.n_dof), device=device)
-    asm.form_to_input_list = {"volume": ["form", range(n_cells), form, np.zeros(space.n_dof)]}
     t0 = time.perf_counter()
-    state = asm.prepare()
+    sharded = None
+    if world > 1:
+        from nfempy_b200.assembly.sharding import ShardedAssembler
+
+        sharded = ShardedAssembler(space, form, world, rank, device=device).prepare()
+        asm, state = sharded.asm, sharded.state
+        n_cells = len(sharded.shard.own_cells)
+    else:
+        n_cells = len(space.discrete_spaces["u"].elements)
+        asm = GPUAssembler(space, None, np.zeros(space.n_dof), device=device)
+        asm.form_to_input_list = {"volume": ["form", range(n_cells), form, np.zeros(space.n_dof)]}
+        state = asm.prepare()
     torch.cuda.synchronize()
     t_prepare = time.perf_counter() - t0
     dev, entries, datas, dests, plan, key = state
@@ -223,6 +233,9 @@ def run_graft(args):
     rhs_dev = torch.zeros(plan.n_dof, dtype=torch.float64, device=device)
 
     def step():
+        if sharded is not None:  # local fused assembly + NCCL interface-row exchange
+            sharded.assemble(dist)
+            return
         asm.jacobian.is_zero = True  # fresh assembly: the fused kernel overwrites every value
         rhs_dev.zero_()
         asm.run(state, rhs_dev)
@@ -287,7 +300,7 @@ def run_graft(args):
 
     # ---- end to end through the host-buffer API: H2D of every input, kernels, D2H of CSR values + rhs
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
         e2e = run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, rhs_dev)
 
     cpu = None
@@ -303,7 +316,8 @@ def run_graft(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": "3D Cauchy linear elasticity, vector H1 p=2, %d tets per GPU (Kuhn box n=%d, jittered), "
-                            "lambda=mu=1, tabulated load, CSR values + rhs" % (n_cells, args.n),
+                            "lambda=mu=1, tabulated load, CSR values + rhs%s" % (
+                                n_cells, args.n, "" if world == 1 else "; x-slab cell partition, NCCL interface-row reduce"),
                 "cells_per_gpu": n_cells, "n_dof_per_gpu": plan.n_dof, "nnz_per_gpu": nnz,
                 "nonzeros_per_s": nnz * world / (ms_step * 1e-3),
                 "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % ((b_step * n_cells + 6 * 100 * n_cells) / 1e9),

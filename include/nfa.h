@@ -116,6 +116,17 @@ int nfa_plan_reduce(const nfa_plan *plan, const double *const *d_Ke, const doubl
 int nfa_csr_spmv(const nfa_plan *plan, const double *d_vals, const double *d_x, int accumulate, double *d_y,
                  nfa_stream stream);
 
+/* ---- K8 multi-GPU interface rows: after the local reduce a rank holds partial sums on rows owned by a
+ * lower rank.  nfa_pack_rows copies the CSR segments of `rows` (int32 global row ids, ascending) into a contiguous
+ * send buffer (buf_off[k] = prefix sum of the row lengths, int64); the owner calls nfa_unpack_add_rows on the
+ * received buffer, once per sender in ascending rank order (fixed order => deterministic).  Both sides hold the same
+ * pattern for these rows, so segments line up entry by entry.  The transfer itself is ncclSend/ncclRecv issued by the
+ * host layer (torch.distributed) between the two calls. */
+int nfa_pack_rows(const int32_t *d_indptr, const double *d_vals, const int32_t *d_rows, const int64_t *d_buf_off,
+                  int64_t n_rows, double *d_buf, nfa_stream stream);
+int nfa_unpack_add_rows(const int32_t *d_indptr, double *d_vals, const int32_t *d_rows, const int64_t *d_buf_off,
+                        int64_t n_rows, const double *d_buf, nfa_stream stream);
+
 /* ---- fused H1 path (affine cells, cell-wise constant coefficients): local B^T D B contraction and the global
  * reduce in ONE kernel, no local matrices in HBM.  The node-block plan groups the n_comp x n_comp blocks of the
  * CSR by (row node, col node); d_node_dest int32 [n_cells, n_phi] = dest[:, ::n_comp] / n_comp. */

@@ -38,6 +38,8 @@ SIGNATURES = {
     "nfa_plan_csr": (_i, [_vp, _vp, _vp, _vp]),
     "nfa_plan_reduce": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _vp, _i, _vp, _vp]),
     "nfa_csr_spmv": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "nfa_pack_rows": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nfa_unpack_add_rows": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nfa_bplan_create": (_i, [_i64, _i, _i, _vp, _i64, ctypes.POINTER(_vp), _vp]),
     "nfa_bplan_destroy": (None, [_vp]),
     "nfa_bplan_nnz": (_i64, [_vp]),

@@ -1,0 +1,217 @@
+"""Multi-GPU assembly: cells partitioned into contiguous ranges, one rank per GPU.
+
+The reference is single-process; this is the N-GPU extension the north star asks for.  Design:
+
+* rank r owns the cells ``[bounds[r], bounds[r+1])``; a dof (matrix row) is owned by the rank of the FIRST cell
+  touching it -- consistent with the reference's first-appearance numbering (R/src/mesh/mesh_topology.py:28-35),
+  so a rank's owned rows are contiguous intervals inside each entity block of the numbering
+  (R/src/spaces/dof_map.py:74-84);
+* the rank's local plan covers its own cells plus every other cell touching one of its rows ("halo" cells, a
+  single layer), with the halo cells' coefficients and load set to zero: the local CSR then has the complete global
+  pattern for every row the rank touches, while the values only hold the rank's own cells' contributions;
+* after the local (fused) assembly, rows owned by a lower rank carry partial sums: their CSR segments and
+  right-hand-side entries are packed (``nfa_pack_rows``), sent to the owner (``ncclSend/ncclRecv`` through
+  ``torch.distributed`` P2P ops) and added there in ascending sender rank (``nfa_unpack_add_rows``).  Both sides
+  hold the same pattern for those rows, so the segments line up entry by entry;
+* result: every rank holds the finished rows it owns, in global numbering -- a row-block CSR.
+
+``ShardPlan`` is pure host logic (numpy) on the replicated destination table; the exchange takes pack/unpack
+callables so that the same code runs over NCCL on device buffers and over gloo on CPU tensors (tests).
+"""
+import numpy as np
+
+
+class ShardPlan:
+    def __init__(self, dest, n_dof, world, rank, bounds=None):
+        dest = np.asarray(dest)
+        n_cells, n_loc = dest.shape
+        self.world, self.rank, self.n_dof = world, rank, int(n_dof)
+        if bounds is None:
+            bounds = np.linspace(0, n_cells, world + 1).astype(np.int64)
+        self.bounds = np.asarray(bounds, dtype=np.int64)
+        c0, c1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
+        cell_rank = np.searchsorted(self.bounds, np.arange(n_cells), side="right") - 1
+        first_cell = np.full(self.n_dof, n_cells, dtype=np.int64)
+        np.minimum.at(first_cell, dest.ravel(), np.repeat(np.arange(n_cells), n_loc))
+        owner = np.full(self.n_dof, -1, dtype=np.int64)
+        touched_any = first_cell < n_cells
+        owner[touched_any] = cell_rank[first_cell[touched_any]]
+        self.owner = owner
+        self.own_cells = np.arange(c0, c1, dtype=np.int64)
+        rows_touched = np.unique(dest[c0:c1])
+        self.rows_touched = rows_touched
+        mask = np.zeros(self.n_dof, dtype=bool)
+        mask[rows_touched] = True
+        self.local_cells = np.flatnonzero(mask[dest].any(axis=1)).astype(np.int64)  # own + halo, ascending
+        self.is_own = (self.local_cells >= c0) & (self.local_cells < c1)
+        self.owned_rows = rows_touched[owner[rows_touched] == rank]
+        # rows I touch but a lower rank owns -> I send my partial sums there
+        self.send_rows = {}
+        for q in np.unique(owner[rows_touched]):
+            q = int(q)
+            if q != rank:
+                if q > rank:
+                    raise AssertionError("first-touch ownership: a row touched by rank %d is owned by %d" % (rank, q))
+                self.send_rows[q] = rows_touched[owner[rows_touched] == q].astype(np.int32)
+        # rows I own that higher ranks touch -> I receive their partial sums (same lists, computed locally)
+        self.recv_rows = {}
+        for q in range(rank + 1, world):
+            rq = np.unique(dest[int(self.bounds[q]) : int(self.bounds[q + 1])])
+            rq = rq[owner[rq] == rank]
+            if len(rq):
+                self.recv_rows[q] = rq.astype(np.int32)
+
+    def row_block_ranges(self):
+        """Owned rows as a list of maximal contiguous ``(start, stop)`` intervals."""
+        r = self.owned_rows
+        if len(r) == 0:
+            return []
+        cut = np.flatnonzero(np.diff(r) != 1) + 1
+        starts = np.concatenate([[0], cut])
+        stops = np.concatenate([cut, [len(r)]])
+        return [(int(r[a]), int(r[b - 1]) + 1) for a, b in zip(starts, stops)]
+
+
+def buffer_offsets(indptr, rows):
+    """Prefix sums of the CSR row lengths of ``rows`` (numpy int64 ``[len(rows)+1]``)."""
+    lengths = (indptr[rows.astype(np.int64) + 1] - indptr[rows.astype(np.int64)]).astype(np.int64)
+    return np.concatenate([[0], np.cumsum(lengths)])
+
+
+def exchange_interface_rows(dist, plan, make_buffer, pack, unpack_add, device_sync=None):
+    """Sums the interface rows onto their owners.
+
+    ``make_buffer(n)`` allocates a float64 buffer tensor; ``pack(rows, buf)`` fills it with [matrix segments | rhs
+    entries] of ``rows``; ``unpack_add(rows, buf)`` adds a received buffer.  Buffer sizes are known on both sides
+    from the shared pattern (``sizes[q]``), so no size handshake is needed."""
+    ops, recv_bufs, keep = [], {}, []
+    for q, rows in sorted(plan.send_rows.items()):
+        buf = make_buffer(("send", q), rows)
+        pack(rows, buf)
+        keep.append(buf)
+        ops.append(dist.P2POp(dist.isend, buf, q))
+    for q, rows in sorted(plan.recv_rows.items()):
+        buf = make_buffer(("recv", q), rows)
+        recv_bufs[q] = (rows, buf)
+        ops.append(dist.P2POp(dist.irecv, buf, q))
+    if ops:
+        if device_sync is not None:
+            device_sync()
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for q in sorted(recv_bufs):  # fixed ascending-rank order => deterministic sums
+        rows, buf = recv_bufs[q]
+        unpack_add(rows, buf)
+
+
+class ShardedAssembler:
+    """One rank's share of a cell-partitioned assembly on its GPU.
+
+    ``space`` is the (replicated) global ``ProductSpace``; ``form`` a fused-capable volume form on it.  ``assemble``
+    returns ``(indptr, indices, values, rhs)`` device tensors in GLOBAL numbering whose owned rows
+    (``shard.owned_rows`` / ``shard.row_block_ranges()``) are final."""
+
+    def __init__(self, space, form, world, rank, device=None, bounds=None):
+        import torch
+
+        from ..device import space_device
+        from .gpu_assembler import GPUAssembler
+
+        self.space, self.form, self.world, self.rank = space, form, world, rank
+        dest = space.destination_table()
+        self.shard = ShardPlan(dest, space.n_dof, world, rank, bounds)
+        self.dev = space_device(space, device)
+        self.asm = GPUAssembler(space, None, None, device=device)
+        self.asm.form_to_input_list = {"volume": ["form", self.shard.local_cells, form, None]}
+        self.state = None
+        self._bufs = {}
+        self._torch = torch
+
+    def prepare(self):
+        torch = self._torch
+        dev, entries, datas, dests, plan, key = self.asm.prepare()
+        if plan.fused_index is None:
+            raise NotImplementedError("ShardedAssembler needs the fused path (affine H1 form, cell-wise coefficients)")
+        data = datas[0]
+        own = torch.as_tensor(self.shard.is_own.astype(np.float64)).to(dev.device)
+        coefs = {}
+        for name, (arr, sc, sq, kind) in data.coefs.items():
+            if kind == "constant":
+                coefs[name] = ((arr * own).contiguous(), 1, 0, "cell")  # halo cells contribute exact zeros
+            else:
+                coefs[name] = ((arr * own).contiguous(), sc, sq, kind)
+        data.coefs = coefs
+        if data.f is not None:
+            data.f = (data.f * own[:, None, None]).contiguous()
+        self.state = (dev, entries, datas, dests, plan, key)
+        self.plan = plan
+        self._indptr_host = plan.indptr.cpu().numpy()
+        self._rows_dev, self._off_dev, self._sizes = {}, {}, {}
+        for kind, table in (("send", self.shard.send_rows), ("recv", self.shard.recv_rows)):
+            for q, rows in table.items():
+                off = buffer_offsets(self._indptr_host, rows)
+                self._rows_dev[(kind, q)] = torch.as_tensor(rows).to(dev.device)
+                self._off_dev[(kind, q)] = torch.as_tensor(off).to(dev.device)
+                self._sizes[(kind, q)] = int(off[-1])
+        return self
+
+    # -- the three stages of one assembly ------------------------------------------------------------
+    def local_assemble(self):
+        """Fused assembly of the rank's own cells (halo cells contribute exact zeros)."""
+        torch = self._torch
+        dev, entries, datas, dests, plan, key = self.state
+        self.asm.jacobian.is_zero = True
+        self.rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
+        self.asm.run(self.state, self.rhs)
+        self.vals = self.asm.jacobian.values_dev
+        return self.vals, self.rhs
+
+    def _buffer(self, tag):
+        if tag not in self._bufs:
+            n = self._sizes[tag] + int(self._rows_dev[tag].shape[0])
+            self._bufs[tag] = self._torch.empty(n, dtype=self._torch.float64, device=self.dev.device)
+        return self._bufs[tag]
+
+    def pack(self, q):
+        """Send buffer for owner ``q``: [CSR segments of the rows q owns | their rhs entries]."""
+        from .. import _lib
+
+        tag = ("send", q)
+        buf, rows = self._buffer(tag), self._rows_dev[tag]
+        _lib.check(
+            _lib.load().nfa_pack_rows(_lib.ptr(self.plan.indptr), _lib.ptr(self.vals), _lib.ptr(rows),
+                                      _lib.ptr(self._off_dev[tag]), int(rows.shape[0]), _lib.ptr(buf), _lib.stream_ptr()),
+            "nfa_pack_rows")
+        buf[self._sizes[tag] :] = self.rhs.index_select(0, rows.long())
+        return buf
+
+    def unpack_add(self, q, buf):
+        """Adds the partial sums received from rank ``q`` (call in ascending q)."""
+        from .. import _lib
+
+        tag = ("recv", q)
+        rows = self._rows_dev[tag]
+        _lib.check(
+            _lib.load().nfa_unpack_add_rows(_lib.ptr(self.plan.indptr), _lib.ptr(self.vals), _lib.ptr(rows),
+                                            _lib.ptr(self._off_dev[tag]), int(rows.shape[0]), _lib.ptr(buf),
+                                            _lib.stream_ptr()),
+            "nfa_unpack_add_rows")
+        self.rhs.index_add_(0, rows.long(), buf[self._sizes[tag] :])  # rows are distinct: deterministic
+
+    def assemble(self, dist=None):
+        """Local fused assembly + (for world > 1) the NCCL interface exchange.  Returns device tensors
+        ``(indptr, indices, values, rhs)``; the rank's owned rows are final."""
+        self.local_assemble()
+        if self.world > 1:
+            if dist is None:
+                import torch.distributed as dist
+            exchange_interface_rows(
+                dist, self.shard, lambda tag, rows: self._buffer(tag),
+                lambda rows, buf: self.pack(self._peer(self.shard.send_rows, rows)),
+                lambda rows, buf: self.unpack_add(self._peer(self.shard.recv_rows, rows), buf),
+            )
+        return self.plan.indptr, self.plan.indices, self.vals, self.rhs
+
+    @staticmethod
+    def _peer(table, rows):
+        return next(q for q, v in table.items() if v is rows)

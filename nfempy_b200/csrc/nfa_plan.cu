@@ -394,3 +394,40 @@ extern "C" int nfa_csr_spmv(const nfa_plan *plan, const double *vals, const doub
     NFA_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- multi-GPU interface rows: pack CSR row segments into a contiguous buffer / add a received buffer back ----
+// rows[k] = global row id, buf_off[k] = start of that row's segment in the buffer (prefix sum of row lengths).
+// One warp per row; the add is into distinct addresses (each row appears once), applied in the caller's fixed
+// rank order => deterministic.
+__global__ void pack_rows_kernel(const int32_t *__restrict__ indptr, const double *__restrict__ vals,
+                                 const int32_t *__restrict__ rows, const int64_t *__restrict__ buf_off, int64_t n_rows,
+                                 int add_back, double *__restrict__ buf, double *__restrict__ vals_out) {
+    int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (k >= n_rows) return;
+    int32_t r = rows[k];
+    int32_t b = indptr[r], e = indptr[r + 1];
+    int64_t o = buf_off[k];
+    if (!add_back)
+        for (int32_t t = b + lane; t < e; t += 32) buf[o + (t - b)] = vals[t];
+    else
+        for (int32_t t = b + lane; t < e; t += 32) vals_out[t] += buf[o + (t - b)];
+}
+
+extern "C" int nfa_pack_rows(const int32_t *indptr, const double *vals, const int32_t *rows, const int64_t *buf_off,
+                             int64_t n_rows, double *buf, nfa_stream stream) {
+    if (n_rows == 0) return 0;
+    pack_rows_kernel<<<grid_for(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(indptr, vals, rows, buf_off, n_rows,
+                                                                                   0, buf, nullptr);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nfa_unpack_add_rows(const int32_t *indptr, double *vals, const int32_t *rows, const int64_t *buf_off,
+                                   int64_t n_rows, const double *buf, nfa_stream stream) {
+    if (n_rows == 0) return 0;
+    pack_rows_kernel<<<grid_for(n_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        indptr, nullptr, rows, buf_off, n_rows, 1, const_cast<double *>(buf), vals);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}

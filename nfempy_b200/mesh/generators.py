@@ -12,13 +12,16 @@ import numpy as np
 from .mesh import Mesh, TET_FACES, TRI_EDGES
 
 
-def box_tet_points_cells(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, lengths=(1.0, 1.0, 1.0), nz=None):
-    """Points ``[(n+1)^2 (nz+1), 3]`` and tets ``[6 n^2 nz, 4]`` of a Kuhn-subdivided box (``nz`` defaults to n)."""
+def box_tet_points_cells(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, lengths=(1.0, 1.0, 1.0), nz=None,
+                         nx=None):
+    """Points and tets ``[6 nx n nz, 4]`` of a Kuhn-subdivided box of ``nx x n x nz`` cubes of edge ``1/n``
+    (``nx``, ``nz`` default to n).  Cells are cube-major with x slowest, so contiguous cell ranges are x-slabs."""
     nz = n if nz is None else nz
+    nx = n if nx is None else nx
     rng = np.random.default_rng(seed)
-    gx, gy, gz = np.meshgrid(np.arange(n + 1), np.arange(n + 1), np.arange(nz + 1), indexing="ij")
+    gx, gy, gz = np.meshgrid(np.arange(nx + 1), np.arange(n + 1), np.arange(nz + 1), indexing="ij")
     grid = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1)
-    dims = np.array([n, n, nz])
+    dims = np.array([nx, n, nz])
     h = np.asarray(lengths, dtype=np.float64) / np.array([n, n, n])
     points = grid * h
     if jitter > 0.0:
@@ -29,7 +32,7 @@ def box_tet_points_cells(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, le
     def nid(i, j, k):
         return (i * (n + 1) + j) * (nz + 1) + k
 
-    ci, cj, ck = np.meshgrid(np.arange(n), np.arange(n), np.arange(nz), indexing="ij")
+    ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(n), np.arange(nz), indexing="ij")
     ci, cj, ck = ci.ravel(), cj.ravel(), ck.ravel()
     tets = []
     for perm in itertools.permutations(range(3)):
@@ -47,9 +50,9 @@ def box_tet_points_cells(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, le
     return points, tets.astype(np.int64), grid, dims
 
 
-def box_tet_mesh(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, nz=None, lengths=(1.0, 1.0, 1.0)):
+def box_tet_mesh(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, nz=None, lengths=(1.0, 1.0, 1.0), nx=None):
     """``Mesh`` of the Kuhn box: six boundary triangle blocks (tags 2..7), then the tets (tag 1)."""
-    points, tets, grid, dims = box_tet_points_cells(n, jitter, seed, shuffle_local_nodes, lengths, nz)
+    points, tets, grid, dims = box_tet_points_cells(n, jitter, seed, shuffle_local_nodes, lengths, nz, nx)
     faces = tets[:, TET_FACES].reshape(-1, 3)
     fg = grid[faces]  # [nf, 3 nodes, 3 coords]
     blocks = []

@@ -1,0 +1,54 @@
+"""GPU test of the cell-partitioned assembly: two (and three) ranks' local fused assemblies, interface rows packed /
+added with the library kernels, owned row blocks compared with the single-GPU assembly.  Runs the ranks one after
+the other on one device with a loop-back transfer (the NCCL leg itself is exercised by bench.py --gpus N and
+tests/test_cpu_sharding.py covers the P2P protocol over gloo)."""
+import numpy as np
+import pytest
+
+from nfempy_b200.mesh import box_tet_mesh
+from nfempy_b200.spaces import ProductSpace
+
+pytestmark = pytest.mark.gpu
+
+
+def _f(x, y, z):
+    return np.array([np.sin(x + y), z * x, np.cos(y) + 1.0])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_assembly_matches_single_gpu(world):
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.assembly.sharding import ShardedAssembler
+    from nfempy_b200.weak_forms import LEPrimalWeakForm
+
+    mesh = box_tet_mesh(3, nx=6, jitter=0.2)
+    space = ProductSpace({"u": (3, 3, "Lagrange", 2, mesh)})
+    space.build_structures({"u": [1]}, {})
+    form = LEPrimalWeakForm(space)
+    form.functions = {"rhs": _f, "lambda": lambda x, y, z: 2.0 * np.ones_like(x), "mu": lambda x, y, z: np.ones_like(x)}
+    n_cells = len(space.discrete_spaces["u"].elements)
+    ref = GPUAssembler(space, None, np.zeros(space.n_dof))
+    ref.form_to_input_list = {"volume": ["form", range(n_cells), form, None]}
+    g_indptr, g_indices, g_vals, g_rhs = ref.assemble()
+
+    ranks = [ShardedAssembler(space, form, world, r).prepare() for r in range(world)]
+    for sa in ranks:
+        sa.local_assemble()
+    sent = {(r, q): sa.pack(q).clone() for r, sa in enumerate(ranks) for q in sa.shard.send_rows}
+    for q, sa in enumerate(ranks):
+        for r in sorted(sa.shard.recv_rows):
+            sa.unpack_add(r, sent[(r, q)])
+    owned_total = 0
+    for sa in ranks:
+        indptr = sa.plan.indptr.cpu().numpy()
+        indices = sa.plan.indices.cpu().numpy()
+        vals, rhs = sa.vals.cpu().numpy(), sa.rhs.cpu().numpy()
+        rows = sa.shard.owned_rows
+        owned_total += len(rows)
+        scale = np.abs(g_vals).max()
+        for r in rows:
+            a, b, ga, gb = indptr[r], indptr[r + 1], g_indptr[r], g_indptr[r + 1]
+            assert np.array_equal(indices[a:b], g_indices[ga:gb])
+            assert np.abs(vals[a:b] - g_vals[ga:gb]).max() <= 1e-13 * scale
+        assert np.abs(rhs[rows] - g_rhs[rows]).max() <= 1e-13 * max(np.abs(g_rhs).max(), 1.0)
+    assert owned_total == space.n_dof
