@@ -205,36 +205,48 @@ extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const in
     int cap_c = 512, cap_b = 512;
     if (const char *e = getenv("NFA_FUSED_CAP")) cap_c = cap_b = std::max(64, atoi(e));
     // staging must fit: cap_c * nc2 doubles (+ Mref) within ~200 KB
-    std::vector<int32_t> chunk_row{0};
-    std::vector<uint32_t> chunk_cstart{0};
+    // chunks = runs of consecutive NON-EMPTY block rows (a rank's local plan leaves the rows of other ranks empty)
+    std::vector<int32_t> chunk_r0, chunk_r1;
+    std::vector<uint32_t> chunk_cstart;
     int64_t cur_c = 0, cur_b = 0;
     uint32_t run = 0;
     int max_c = 0, max_b = 0;
+    bool open = false;
+    auto close_at = [&](int64_t r) {
+        chunk_r1.push_back((int32_t)r);
+        max_c = std::max<int>(max_c, (int)cur_c);
+        max_b = std::max<int>(max_b, (int)cur_b);
+        cur_c = cur_b = 0;
+        open = false;
+    };
     for (int64_t r = 0; r < n_nodes; ++r) {
         int64_t rc = h_rowc[r], rb = h_bptr[r + 1] - h_bptr[r];
+        if (rc == 0) {
+            if (open) close_at(r);
+            continue;
+        }
         if (rc > 65535 || rc * nc2 * 8 > 180 * 1024)
             return bail(fail("nfa_bplan_create: a node has too many adjacent cells for the fused staging"));
-        if (cur_c > 0 && (cur_c + rc > cap_c || cur_b + rb > cap_b)) {
-            chunk_row.push_back((int32_t)r);
+        if (open && (cur_c + rc > cap_c || cur_b + rb > cap_b)) close_at(r);
+        if (!open) {
+            chunk_r0.push_back((int32_t)r);
             chunk_cstart.push_back(run);
-            max_c = std::max<int>(max_c, (int)cur_c);
-            max_b = std::max<int>(max_b, (int)cur_b);
-            cur_c = cur_b = 0;
+            open = true;
         }
         cur_c += rc;
         cur_b += rb;
         run += (uint32_t)rc;
     }
-    max_c = std::max<int>(max_c, (int)cur_c);
-    max_b = std::max<int>(max_b, (int)cur_b);
-    chunk_row.push_back((int32_t)n_nodes);
-    bp->n_chunks = (int64_t)chunk_row.size() - 1;
+    if (open) close_at(n_nodes);
+    bp->n_chunks = (int64_t)chunk_r0.size();
+    if (bp->n_chunks == 0) return bail(fail("nfa_bplan_create: no contributions"));
     bp->max_chunk_contrib = max_c;
     bp->max_chunk_bnz = max_b;
     DevBuf d_cstart;
     std::vector<int32_t> hdr(8 * (size_t)bp->n_chunks, 0);
+    std::vector<int32_t> &chunk_row = chunk_r0;
     for (int64_t c = 0; c < bp->n_chunks; ++c) {
-        int32_t ra = chunk_row[c], rz = chunk_row[c + 1];
+        int32_t ra = chunk_r0[c], rz = chunk_r1[c];
         uint32_t ca = chunk_cstart[c], cz = (c + 1 < bp->n_chunks) ? chunk_cstart[c + 1] : run;
         hdr[8 * c + 0] = ra;
         hdr[8 * c + 1] = rz - ra;
