@@ -83,6 +83,28 @@ int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp, const doub
                        int64_t n_facets, const double *d_g, double beta, double r_sign, int with_matrix,
                        double *d_Ke, double *d_re, nfa_stream stream);
 
+/* ---- K3 H(div) x L2 forms (mixed Poisson).  n_u vector basis functions whose first (dim+1)*nfd are the facet dofs
+ * (nfd per facet, facet-major), n_p scalar L2 functions; local dofs = [u | p].
+ * u_val [n_q, n_u, dim], u_div [n_q, n_u]: REFERENCE values and reference divergence tr(grad_hat phi_hat);
+ * p_val [n_q, n_p]; Tcases [n_cases, nfd, nfd]: orientation matrices (R/src/basis/permute_and_transform.py);
+ * cases int8 [n_cells, dim+1]: which matrix each facet of each cell takes (0 = identity).
+ * nfa_local_hdiv_l2: LaplaceDualWeakForm.evaluate_form, R/src/weak_forms/laplace_dual_weak_form.py:10-87:
+ *   J = [[int kappa^-1 psi_j.psi_i, -int w_l div psi_i], [int div psi_j w_k, 0]], r = [0, -int f w]  (the reference
+ *   zeroes alpha, :50).  kappa stride-addressed like the H1 coefficients; f [n, n_q] or NULL.
+ * nfa_local_hdiv_facet: LaplaceDualWeakFormBCDirichlet, R/...:90-154: r_k = int_F p_D (psi_k . n) over the facet dofs
+ *   of the first neighbour cell; trace_tab [n_tabs, n_q, nfd, dim] = reference values of the facet's dofs at the facet
+ *   quadrature points mapped into the neighbour (R/src/basis/parametric_transformation.py:58-98), one table per
+ *   (local facet, vertex permutation); tidx int32 [n] picks the table; cases int8 [n]; normals [n,3]; pd [n, n_q]. */
+int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, const double *d_u_val, const double *d_u_div,
+                      const double *d_p_val, const double *d_weights, const double *d_Tcases, const int8_t *d_cases,
+                      const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_kappa,
+                      int64_t kappa_stride_cell, int64_t kappa_stride_q, const double *d_f, double *d_Ke, double *d_re,
+                      nfa_stream stream);
+int nfa_local_hdiv_facet(int dim, int nfd, int n_q, const double *d_trace_tab, const int32_t *d_tidx,
+                         const double *d_weights, const double *d_Tcases, const int8_t *d_cases, const double *d_coords,
+                         const int32_t *d_facet_nodes, const int32_t *d_neigh_nodes, const double *d_normals,
+                         const double *d_pd, int64_t n_facets, double *d_re, nfa_stream stream);
+
 /* ---- K6 sparsity plan: replaces the implicit pattern growth of PETSc Mat.setValue(..., addv=True) without
  * preallocation (R/src/assembly/ScatterFormData.py:5-11): the pattern is the union of
  * dest x dest over all items of all segments ("full" policy: explicit zeros kept), columns sorted per row.

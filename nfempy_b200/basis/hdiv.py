@@ -1,0 +1,213 @@
+"""H(div) elements on simplices: Raviart-Thomas (degree 1..3, lowest = 1 as in basix) and BDM degree 1, restated
+from their published definition in the conventions of basix (un-vendored, unpinned dependency of the reference:
+R/requirements.txt:2; called at R/src/basis/finite_element.py:85-91 with ``lagrange_variant=gll_centroid``).
+
+Construction (Ciarlet triple, exact rational arithmetic, then one rounding to double):
+
+* polynomial space: RT_k = [P_{k-1}]^d + x * Ptilde_{k-1};  BDM_k = [P_k]^d;
+* dual basis, facet part: for facet f with reference vertices (v0, v1[, v2]) in the sub-entity order the reference
+  hard-codes (R/src/mesh/mesh.py:187-203), ``l(phi) = int_{ref facet} phi(x(s)) . n_f q_i(s) ds`` with the
+  NON-normalised normal ``n_f = (-t_y, t_x)`` (2-D, t = v1 - v0) or ``(v1 - v0) x (v2 - v0)`` (3-D) and ``q_i`` the
+  nodal Lagrange basis of degree k-1 (RT) / k (BDM) on the reference facet;
+* dual basis, interior part (RT, k >= 2): ``l(phi) = int_cell phi_d q_i`` against the nodal Lagrange basis of degree
+  k-2, dof index ``i * dim + d`` (basis function major, direction minor);
+* basis = dual basis: ``l_i(phi_j) = delta_ij``.
+
+PARITY UNPINNED: these conventions are written from basix's documented construction, not checked against a basix
+binary (none is installable here).  What the repository's tests do pin: the space (degrees of freedom are
+unisolvent, divergence theorem, normal-moment biorthogonality) and H(div)-conformity of the assembled global basis
+under the reference's orientation table (R/src/basis/permute_and_transform.py:57-140).
+"""
+import itertools
+from fractions import Fraction
+from math import factorial
+
+import numpy as np
+
+from .reference_element import REF_VERTICES, SUB_ENTITIES, monomial_exponents
+
+
+# ---- tiny exact polynomial algebra: {exponent tuple: Fraction} ------------------------------------------
+def _pmul(p, q):
+    out = {}
+    for ea, ca in p.items():
+        for eb, cb in q.items():
+            e = tuple(x + y for x, y in zip(ea, eb))
+            out[e] = out.get(e, 0) + ca * cb
+    return out
+
+
+def _padd(p, q, s=1):
+    out = dict(p)
+    for e, c in q.items():
+        out[e] = out.get(e, 0) + s * c
+    return out
+
+
+def _ppow(p, n, nvar):
+    out = {(0,) * nvar: Fraction(1)}
+    for _ in range(n):
+        out = _pmul(out, p)
+    return out
+
+
+def _simplex_integral(p):
+    """Integral of a polynomial over the reference simplex of its variable count."""
+    total = Fraction(0)
+    for e, c in p.items():
+        num = 1
+        for a in e:
+            num *= factorial(a)
+        total += c * Fraction(num, factorial(sum(e) + len(e)))
+    return total
+
+
+def _lagrange_nodal_polys(dim, degree):
+    """Nodal Lagrange basis (equispaced; identical to gll_centroid for degree <= 2) on the reference simplex of
+    dimension ``dim`` as exact polynomials, basix dof order (vertices, edges, faces, interior)."""
+    if degree > 2:
+        raise NotImplementedError("facet/interior moment spaces above degree 2 (RT > 3, BDM > 2) are not restated")
+    if dim == 0:
+        return [{(): Fraction(1)}]
+    nvar = dim
+    one = {(0,) * nvar: Fraction(1)}
+    lam = [dict(one)]
+    for d in range(dim):
+        e = tuple(1 if i == d else 0 for i in range(dim))
+        lam.append({e: Fraction(1)})
+        lam[0] = _padd(lam[0], {e: Fraction(1)}, -1)
+    if degree == 0:
+        return [one]
+    if degree == 1:
+        return lam
+    out = [_pmul(l, _padd({k: 2 * v for k, v in l.items()}, one, -1)) for l in lam]  # l (2 l - 1)
+    for a, b in SUB_ENTITIES[dim][1]:
+        out.append({k: 4 * v for k, v in _pmul(lam[a], lam[b]).items()})
+    return out
+
+
+def _space_functions(family, dim, k):
+    """Spanning set of the polynomial space: list of vector polynomials [dim] of exact polys in x."""
+    zero = {}
+    fns = []
+    base_deg = k - 1 if family == "RT" else k
+    for c in range(dim):
+        for e in monomial_exponents(dim, base_deg):
+            fns.append([({tuple(int(v) for v in e): Fraction(1)} if cc == c else zero) for cc in range(dim)])
+    if family == "RT":
+        for e in monomial_exponents(dim, k - 1):
+            if sum(e) != k - 1:
+                continue
+            m = {tuple(int(v) for v in e): Fraction(1)}
+            fns.append([_pmul(m, {tuple(1 if i == c else 0 for i in range(dim)): Fraction(1)}) for c in range(dim)])
+    return fns
+
+
+def _compose_affine(poly, x_of_s, nvar_s):
+    """poly(x) with x_c = affine polynomial in the facet parameters s."""
+    out = {}
+    for e, c in poly.items():
+        term = {(0,) * nvar_s: Fraction(c)}
+        for d, p in enumerate(e):
+            if p:
+                term = _pmul(term, _ppow(x_of_s[d], p, nvar_s))
+        out = _padd(out, term)
+    return out
+
+
+def _functionals(family, dim, k):
+    """List of (entity_dim, entity_index, functional) with functional(vector poly) -> Fraction."""
+    verts = [[Fraction(int(v)) for v in row] for row in REF_VERTICES[dim].tolist()]
+    out = []
+    fdim = dim - 1
+    q_facet = _lagrange_nodal_polys(fdim, k - 1 if family == "RT" else k)
+    for f, lv in enumerate(SUB_ENTITIES[dim][fdim]):
+        v0 = verts[lv[0]]
+        edges = [[verts[lv[j]][c] - v0[c] for c in range(dim)] for j in range(1, dim)]
+        if dim == 2:
+            t = edges[0]
+            normal = [-t[1], t[0]]
+        else:
+            a, b = edges
+            normal = [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+        x_of_s = []
+        for c in range(dim):
+            p = {(0,) * fdim: v0[c]}
+            for j in range(fdim):
+                e = tuple(1 if i == j else 0 for i in range(fdim))
+                p = _padd(p, {e: edges[j][c]})
+            x_of_s.append(p)
+        for q in q_facet:
+
+            def functional(vec, q=q, normal=normal, x_of_s=x_of_s):
+                total = {}
+                for c in range(dim):
+                    if normal[c] != 0 and vec[c]:
+                        comp = _compose_affine(vec[c], x_of_s, fdim)
+                        total = _padd(total, {e: v * normal[c] for e, v in comp.items()})
+                return _simplex_integral(_pmul(total, q)) if total else Fraction(0)
+
+            out.append((fdim, f, functional))
+    if family == "RT" and k >= 2:
+        for q in _lagrange_nodal_polys(dim, k - 2):
+            for d in range(dim):
+
+                def functional(vec, q=q, d=d):
+                    return _simplex_integral(_pmul(vec[d], q)) if vec[d] else Fraction(0)
+
+                out.append((dim, 0, functional))
+    if family == "BDM" and k >= 2:
+        raise NotImplementedError("BDM degree >= 2 needs Nedelec interior moments, which are not restated yet")
+    return out
+
+
+def _solve_exact(D):
+    """Inverse of a square Fraction matrix by Gauss-Jordan."""
+    n = len(D)
+    A = [row[:] + [Fraction(int(i == j)) for j in range(n)] for i, row in enumerate(D)]
+    for col in range(n):
+        piv = next(r for r in range(col, n) if A[r][col] != 0)
+        A[col], A[piv] = A[piv], A[col]
+        inv = 1 / A[col][col]
+        A[col] = [v * inv for v in A[col]]
+        for r in range(n):
+            if r != col and A[r][col] != 0:
+                f = A[r][col]
+                A[r] = [a - f * b for a, b in zip(A[r], A[col])]
+    return [row[n:] for row in A]
+
+
+def build_hdiv(el):
+    family, dim, k = el.family, el.dim, el.degree
+    if dim not in (2, 3):
+        raise NotImplementedError("H(div) elements live on triangles and tetrahedra")
+    if family == "RT" and not 1 <= k <= 3:
+        raise NotImplementedError("RT degree %d is not restated (1..3 are)" % k)
+    if family == "BDM" and k != 1:
+        raise NotImplementedError("BDM degree %d is not restated (1 is)" % k)
+    fns = _space_functions(family, dim, k)
+    funcs = _functionals(family, dim, k)
+    if len(fns) != len(funcs):
+        raise AssertionError("H(div) element is not square: %d functions, %d functionals" % (len(fns), len(funcs)))
+    D = [[fn(s) for s in fns] for (_, _, fn) in funcs]  # D[i][s] = l_i(space fn s)
+    Dinv = _solve_exact(D)  # phi_j = sum_s Dinv[s][j] space_s
+    max_deg = k
+    el.value_size = dim
+    el.exps = monomial_exponents(dim, max_deg)
+    index = {tuple(int(v) for v in e): m for m, e in enumerate(el.exps)}
+    n = len(funcs)
+    coeffs = [[[Fraction(0)] * len(el.exps) for _ in range(dim)] for _ in range(n)]
+    for j in range(n):
+        for s, vec in enumerate(fns):
+            w = Dinv[s][j]
+            if w == 0:
+                continue
+            for c in range(dim):
+                for e, v in vec[c].items():
+                    coeffs[j][c][index[e]] += w * v
+    el.coeffs = np.array([[[float(v) for v in comp] for comp in fn] for fn in coeffs])
+    el._exact_coeffs = coeffs
+    el._entity_dofs = [[[] for _ in SUB_ENTITIES[dim][d]] for d in range(dim + 1)]
+    for i, (d, e, _) in enumerate(funcs):
+        el._entity_dofs[d][e].append(i)
+    el._interval_T = el._triangle_T = None

@@ -47,6 +47,12 @@ def box_tet_points_cells(n, jitter=0.2, seed=1234, shuffle_local_nodes=False, le
     if shuffle_local_nodes:
         keys = rng.random(tets.shape)
         tets = np.take_along_axis(tets, np.argsort(keys, axis=1), axis=1)
+    # gmsh emits positively oriented tetrahedra; the reference relies on it (its Piola map uses |det J|,
+    # R/src/geometry/mapping.py:28-32), so do the same: swap the last two nodes of left-handed tets
+    X = points[tets]
+    det = np.einsum("ni,ni->n", X[:, 1] - X[:, 0], np.cross(X[:, 2] - X[:, 0], X[:, 3] - X[:, 0]))
+    neg = det < 0
+    tets[neg] = tets[neg][:, [0, 1, 3, 2]]
     return points, tets.astype(np.int64), grid, dims
 
 
@@ -86,7 +92,7 @@ def square_tri_mesh(n, jitter=0.0, seed=1234):
 
     ci, cj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
     ci, cj = ci.ravel(), cj.ravel()
-    lower = np.stack([nid(ci, cj), nid(ci + 1, cj), nid(ci + 1, cj + 1)], axis=1)
+    lower = np.stack([nid(ci, cj), nid(ci + 1, cj), nid(ci + 1, cj + 1)], axis=1)  # counter-clockwise, like gmsh
     upper = np.stack([nid(ci, cj), nid(ci + 1, cj + 1), nid(ci, cj + 1)], axis=1)
     tris = np.stack([lower, upper], axis=1).reshape(-1, 3).astype(np.int64)
     edges = tris[:, TRI_EDGES].reshape(-1, 2)

@@ -244,3 +244,95 @@ def laplace_primal_bc_dirichlet(space, functions, iel, alpha):
         r_el[c : c + n_dof : nc] += res
         j_el[c : c + n_dof : nc, c : c + n_dof : nc] += block
     return r_el, j_el
+
+
+# ---- mixed Poisson (H(div) x L2) ----------------------------------------------------------------------
+def normal(mesh, cell_c0, cell_c1):  # R/src/geometry/compute_normal.py:7-24
+    xc_c1 = np.mean(mesh.points[cell_c1.node_tags], axis=0)
+    xc_c0 = np.mean(mesh.points[cell_c0.node_tags], axis=0)
+    outward = (xc_c1 - xc_c0) / np.linalg.norm(xc_c1 - xc_c0)
+    if cell_c1.dimension == 0:
+        n = outward / np.linalg.norm(outward)
+    elif cell_c1.dimension == 1:
+        v = mesh.points[cell_c1.node_tags[1]] - mesh.points[cell_c1.node_tags[0]]
+        v = v / np.linalg.norm(v)
+        w = np.cross(v, outward) / np.linalg.norm(np.cross(v, outward))
+        n = np.cross(v, w)
+    else:
+        v = mesh.points[cell_c1.node_tags[0]] - xc_c1
+        w = mesh.points[cell_c1.node_tags[1]] - xc_c1
+        n = np.cross(v, w) / np.linalg.norm(np.cross(v, w))
+    if n @ outward < 0.0:
+        n = n * -1.0
+    return n
+
+
+def laplace_dual(space, functions, iel, alpha):
+    """LaplaceDualWeakForm.evaluate_form, R/src/weak_forms/laplace_dual_weak_form.py:10-87.  The reference
+    overwrites ``alpha`` with zeros (:50), so the residual is the load only."""
+    u_space, p_space = space.discrete_spaces["u"], space.discrete_spaces["p"]
+    nu_c, np_c = u_space.n_comp, p_space.n_comp
+    el_u = RefElement(u_space, u_space.element_ids[iel])
+    el_p = RefElement(p_space, p_space.element_ids[iel])
+    dim = el_u.cell.dimension
+    points, weights = space.quadrature[dim]
+    x, jac, det_jac, inv_jac = el_u.evaluate_mapping(points)
+    u_tab = el_u.evaluate_basis(points, jac, det_jac, inv_jac)
+    p_tab = el_p.evaluate_basis(points, jac, det_jac, inv_jac)
+    n_q_dof, n_p_dof = u_tab.shape[2] * nu_c, p_tab.shape[2] * np_c
+    n_dof = n_q_dof + n_p_dof
+    f_val = np.asarray(functions["rhs"](x[:, 0], x[:, 1], x[:, 2]))
+    phi_s_star = det_jac * weights * p_tab[0, :, :, 0].T
+
+    def residual(a, load):
+        a = a.reshape(1, -1)
+        el_form = np.zeros(n_dof)
+        if load:
+            for c in range(np_c):
+                el_form[c + n_q_dof : c + n_q_dof + n_p_dof : np_c] -= phi_s_star @ f_val[c].T
+        for i, omega in enumerate(weights):
+            xv = x[i]
+            psi_h = u_tab[0, i, :, 0:dim]
+            w_h = p_tab[0, i, :, 0:dim]
+            grad_psi_h = u_tab[1 : u_tab.shape[0] + 1, i, :, 0:dim]
+            div_psi_h = np.array([np.trace(grad_psi_h, axis1=0, axis2=2) / det_jac[i]])
+            u_h = a[:, 0:n_q_dof] @ psi_h
+            u_h = u_h * (1.0 / functions["kappa"](xv[0], xv[1], xv[2]))
+            p_h = a[:, n_q_dof:n_dof] @ w_h
+            div_uh = a[:, 0:n_q_dof] @ div_psi_h.T
+            integrand = np.zeros((1, n_dof))
+            integrand[:, 0:n_q_dof] = (u_h @ psi_h.T) - (p_h @ div_psi_h)
+            integrand[:, n_q_dof:n_dof] = div_uh @ w_h.T
+            el_form = el_form + det_jac[i] * omega * integrand.reshape((n_dof,))
+        return el_form
+
+    return _linearise(residual, np.zeros(n_dof), n_dof)
+
+
+def laplace_dual_bc_dirichlet(space, functions, iel, alpha):
+    """LaplaceDualWeakFormBCDirichlet.evaluate_form, R/src/weak_forms/laplace_dual_weak_form.py:90-154."""
+    u_space, el, weights, x, det_jac, q_tab = _bc_setup(space, "u", iel)
+    nc = u_space.n_comp
+    cell = el.cell
+    points, _ = space.bc_quadrature[cell.dimension]
+    n_q_phi = q_tab.shape[2]
+    n_dof = n_q_phi * nc
+    j_el, r_el = np.zeros((n_dof, n_dof)), np.zeros(n_dof)
+    neigh = RefElement(u_space, u_space.first_neighbour(cell.id))
+    mapped = transform_lower_to_higher(np.asarray(points).reshape(len(weights), -1), cell, neigh.cell)
+    _, jac0, det0, inv0 = neigh.evaluate_mapping(mapped)
+    tr_tab = neigh.evaluate_basis(mapped, jac0, det0, inv0)
+    facet_index = neigh.cell.sub_cells_ids[cell.dimension].tolist().index(cell.id)
+    from . import ref_hdiv
+
+    dof_n_index = ref_hdiv.entity_dofs(neigh.family, neigh.cell.dimension, neigh.k)[cell.dimension][facet_index]
+    n = normal(u_space.mesh, neigh.cell, cell)
+    dim = neigh.cell.dimension
+    for c in range(nc):
+        res = np.zeros(n_q_phi)
+        for i, omega in enumerate(weights):
+            p_d = functions["p"](x[i, 0], x[i, 1], x[i, 2])
+            phi = tr_tab[0, i, dof_n_index, 0:dim] @ n[0:dim]
+            res += det_jac[i] * omega * p_d[c] * phi
+        r_el[c : c + n_dof : nc] += res
+    return r_el, j_el

@@ -145,3 +145,36 @@ def laplace_case(n=4, dim=2, k=1, with_bc=True, varying=False, alpha=False, mesh
         mesh, lambda g: {"p": (dim, 1, "Lagrange", k, g)}, {"p": [1]}, {"p": btag_list if with_bc else []},
         gpu_forms, ref_forms_fn, alpha_fn=alpha_fn,
     )
+
+
+def mixed_poisson_case(dim=3, k=1, n=2, family="RT", with_bc=True, varying=False, mesh=None):
+    from nfempy_b200.weak_forms import LaplaceDualWeakForm, LaplaceDualWeakFormBCDirichlet
+
+    if mesh is None:
+        mesh = box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(n, jitter=0.2)
+    btag_list = [2, 3, 4, 5, 6, 7] if dim == 3 else [2, 3, 4, 5]
+    kappa = (lambda x, y, z: 1.0 + x * x + 0.5 * y) if varying else (lambda x, y, z: 2.0)
+    functions = {"rhs": lambda x, y, z: np.array([np.sin(np.pi * x) * (1.0 + y) + z]), "kappa": kappa}
+    bc_functions = {"p": lambda x, y, z: np.array([x + 2.0 * y - z + np.sin(x)])}
+    pk = k - 1 if family == "RT" else k - 1
+
+    def gpu_forms(space, a):
+        wf = LaplaceDualWeakForm(space)
+        wf.functions = functions
+        out = {"volume": ["form", range(len(space.discrete_spaces["u"].elements)), wf, a]}
+        if with_bc:
+            bf = LaplaceDualWeakFormBCDirichlet(space)
+            bf.functions = bc_functions
+            out["bc"] = ["bc_form", range(len(space.discrete_spaces["u"].bc_elements)), bf, a]
+        return out
+
+    def ref_forms_fn(space):
+        out = [("form", ref_forms.laplace_dual, functions, len(space.discrete_spaces["u"].element_ids))]
+        if with_bc:
+            out.append(("bc_form", ref_forms.laplace_dual_bc_dirichlet, bc_functions, len(space.discrete_spaces["u"].bc_element_ids)))
+        return out
+
+    return Case(
+        mesh, lambda g: {"u": (dim, 1, family, k, g), "p": (dim, 1, "Lagrange", pk, g)}, {"u": [1], "p": [1]},
+        {"u": btag_list if with_bc else []}, gpu_forms, ref_forms_fn, disc={"p": True},
+    )
