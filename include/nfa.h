@@ -77,11 +77,13 @@ int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *d_t
  * Dirichlet penalty (beta = 1e12, r_sign = -1): LEPrimalWeakFormBCDirichlet R/.../le_primal_weak_form.py:131-176,
  * LaplacePrimalWeakFormBCDirichlet R/.../laplace_primal_weak_form.py:77-157.  Neumann load (with_matrix = 0,
  * beta = 1, r_sign = +1): LEPrimalWeakFormBCNeumann R/.../le_primal_weak_form.py:179-221.
+ * d_comp_scale [n, n_comp] or NULL scales the (c, c) matrix block of each facet -- n_c^2 for the normal-only penalty
+ * of LEPrimalWeakFormBCNormalDirichlet, R/.../le_primal_weak_form.py:224-286 (whose load is g_c = (u_D . n) n_c).
  * facet_dim = dim-1 (0 = point facets of 1-D cells). */
 int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp, const double *d_tab0,
                        const double *d_weights, const double *d_coords, const int32_t *d_facet_nodes,
-                       int64_t n_facets, const double *d_g, double beta, double r_sign, int with_matrix,
-                       double *d_Ke, double *d_re, nfa_stream stream);
+                       int64_t n_facets, const double *d_g, const double *d_comp_scale, double beta, double r_sign,
+                       int with_matrix, double *d_Ke, double *d_re, nfa_stream stream);
 
 /* ---- K3 H(div) x L2 forms (mixed Poisson).  n_u vector basis functions whose first (dim+1)*nfd are the facet dofs
  * (nfd per facet, facet-major), n_p scalar L2 functions; local dofs = [u | p].

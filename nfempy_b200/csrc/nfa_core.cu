@@ -306,8 +306,8 @@ __global__ void __launch_bounds__(128)
     local_h1_facet_kernel(int n_phi, int n_q, int n_comp, const double *__restrict__ tab0,
                           const double *__restrict__ weights, const double *__restrict__ coords,
                           const int32_t *__restrict__ facet_nodes, int64_t n_facets,
-                          const double *__restrict__ gval, double beta, double r_sign, int with_matrix,
-                          double *__restrict__ Ke, double *__restrict__ re) {
+                          const double *__restrict__ gval, const double *__restrict__ comp_scale, double beta,
+                          double r_sign, int with_matrix, double *__restrict__ Ke, double *__restrict__ re) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_loc = n_phi * n_comp;
     for (int64_t fc = (int64_t)blockIdx.x * 4 + warp; fc < n_facets; fc += (int64_t)gridDim.x * 4) {
@@ -325,9 +325,11 @@ __global__ void __launch_bounds__(128)
                 int ra = e / n_loc, rb = e - ra * n_loc;
                 int a = ra / n_comp, i = ra - a * n_comp, b = rb / n_comp, j = rb - b * n_comp;
                 double acc = 0.0;
-                if (with_matrix && i == j)
+                if (with_matrix && i == j) {
                     for (int q = 0; q < n_q; ++q)
                         acc += beta * det * weights[q] * (tab0[q * n_phi + a] * tab0[q * n_phi + b]);
+                    if (comp_scale) acc *= comp_scale[fc * n_comp + i];
+                }
                 K[e] = acc;
             }
         }
@@ -346,21 +348,21 @@ __global__ void __launch_bounds__(128)
 
 extern "C" int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp, const double *tab0,
                                   const double *weights, const double *coords, const int32_t *facet_nodes,
-                                  int64_t n_facets, const double *gval, double beta, double r_sign,
-                                  int with_matrix, double *Ke, double *re, nfa_stream stream) {
+                                  int64_t n_facets, const double *gval, const double *comp_scale, double beta,
+                                  double r_sign, int with_matrix, double *Ke, double *re, nfa_stream stream) {
     if (n_facets == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     int64_t ctas = (n_facets + 3) / 4;
     int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
     if (facet_dim == 2)
         local_h1_facet_kernel<2><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
-                                                      n_facets, gval, beta, r_sign, with_matrix, Ke, re);
+                                                      n_facets, gval, comp_scale, beta, r_sign, with_matrix, Ke, re);
     else if (facet_dim == 1)
         local_h1_facet_kernel<1><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
-                                                      n_facets, gval, beta, r_sign, with_matrix, Ke, re);
+                                                      n_facets, gval, comp_scale, beta, r_sign, with_matrix, Ke, re);
     else if (facet_dim == 0)
         local_h1_facet_kernel<0><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
-                                                      n_facets, gval, beta, r_sign, with_matrix, Ke, re);
+                                                      n_facets, gval, comp_scale, beta, r_sign, with_matrix, Ke, re);
     else
         return fail("nfa_local_h1_facet: facet_dim must be 0, 1 or 2");
     NFA_LAUNCH_CHECK();
@@ -369,25 +371,37 @@ extern "C" int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp,
 
 // ------------------------------------------------------------------------------------------------
 // Load vector only (fused path): re[cell][a*nc + i] = sign * sum_q w_q det phi_a(q) f[cell][q][i].
+// One warp per cell: the cell's f block (n_q * n_comp contiguous doubles) is read once, coalesced, into shared
+// memory; lane (a, i) then contracts it with the premultiplied table w_q phi_a(q).  HBM-bound on f.
 template <int DIM>
-__global__ void local_h1_load_kernel(int n_phi, int n_q, int n_comp, const double *__restrict__ tab0,
-                                     const double *__restrict__ weights, const double *__restrict__ coords,
-                                     const int32_t *__restrict__ cell_nodes, int64_t n_cells,
-                                     const double *__restrict__ f, double sign, double *__restrict__ re) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_cells * n_phi) return;
-    int64_t cell = idx / n_phi;
-    int a = (int)(idx - cell * n_phi);
-    double X[DIM + 1][3];
-    load_cell_coords<DIM>(coords, cell_nodes, cell, X);
-    Geom<DIM> g;
-    compute_geom<DIM>(X, g);
-    for (int i = 0; i < n_comp; ++i) {
-        double acc = 0.0;
+__global__ void __launch_bounds__(128)
+    local_h1_load_kernel(int n_phi, int n_q, int n_comp, const double *__restrict__ tab0,
+                         const double *__restrict__ weights, const double *__restrict__ coords,
+                         const int32_t *__restrict__ cell_nodes, int64_t n_cells,
+                         const double *__restrict__ f, double sign, double *__restrict__ re) {
+    extern __shared__ double smem[];
+    double *s_wt = smem;                       // [n_q][n_phi]  w_q phi_a(q)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fn = n_q * n_comp, n_loc = n_phi * n_comp;
+    double *s_f = s_wt + n_q * n_phi + warp * fn;  // [n_q][n_comp] of the warp's current cell
+    for (int i = threadIdx.x; i < n_q * n_phi; i += blockDim.x) s_wt[i] = weights[i / n_phi] * tab0[i];
+    __syncthreads();
+    for (int64_t cell = (int64_t)blockIdx.x * 4 + warp; cell < n_cells; cell += (int64_t)gridDim.x * 4) {
+        double X[DIM + 1][3];
+        load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+        Geom<DIM> g;
+        compute_geom<DIM>(X, g);
+        __syncwarp();
         if (f)
-            for (int q = 0; q < n_q; ++q)
-                acc += weights[q] * g.det * tab0[q * n_phi + a] * f[(cell * n_q + q) * n_comp + i];
-        re[(cell * n_phi + a) * n_comp + i] = sign * acc;
+            for (int i = lane; i < fn; i += 32) s_f[i] = f[cell * fn + i];
+        __syncwarp();
+        for (int ra = lane; ra < n_loc; ra += 32) {
+            const int a = ra / n_comp, i = ra - a * n_comp;
+            double acc = 0.0;
+            if (f)
+                for (int q = 0; q < n_q; ++q) acc += s_wt[q * n_phi + a] * g.det * s_f[q * n_comp + i];
+            re[cell * n_loc + ra] = sign * acc;
+        }
     }
 }
 
@@ -396,15 +410,17 @@ extern "C" int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const 
                                  double sign, double *re, nfa_stream stream) {
     if (n_cells == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    int grid = grid_for(n_cells * n_phi, 128);
+    size_t smem = sizeof(double) * ((size_t)n_q * n_phi + 4 * (size_t)n_q * n_comp);
+    int64_t ctas = (n_cells + 3) / 4;
+    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
     if (dim == 3)
-        local_h1_load_kernel<3><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
+        local_h1_load_kernel<3><<<grid, 128, smem, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
                                                      sign, re);
     else if (dim == 2)
-        local_h1_load_kernel<2><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
+        local_h1_load_kernel<2><<<grid, 128, smem, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
                                                      sign, re);
     else if (dim == 1)
-        local_h1_load_kernel<1><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
+        local_h1_load_kernel<1><<<grid, 128, smem, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
                                                      sign, re);
     else
         return fail("nfa_local_h1_load: dim must be 1, 2 or 3");

@@ -1,4 +1,5 @@
 from .weak_form import WeakForm, BatchedWeakForm
-from .le_primal_weak_form import LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet, LEPrimalWeakFormBCNeumann
+from .le_primal_weak_form import (LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet, LEPrimalWeakFormBCNeumann,
+                                  LEPrimalWeakFormBCNormalDirichlet)
 from .laplace_primal_weak_form import LaplacePrimalWeakForm, LaplacePrimalWeakFormBCDirichlet
 from .laplace_dual_weak_form import LaplaceDualWeakForm, LaplaceDualWeakFormBCDirichlet

@@ -117,6 +117,7 @@ class H1FacetForm(BatchedWeakForm):
     beta = 1.0
     r_sign = 1.0
     with_matrix = True
+    normal_only = False
 
     def _field(self):
         return self.space.discrete_spaces[self.field_name]
@@ -149,15 +150,29 @@ class H1FacetForm(BatchedWeakForm):
             g = coefficients.evaluate(self.functions[self.data_name], x, s.n_comp)
         else:
             g = arrays[self.data_name]
+        comp_scale = None
+        if self.normal_only:
+            # LEPrimalWeakFormBCNormalDirichlet: phi n_c on both sides of the penalty, load (u_D . n) n_c
+            rows, _ = s.mesh_topology.first_neighbours(s.bc_element_ids if items is None else s.bc_element_ids[np.asarray(items)])
+            from .laplace_dual_weak_form import _facet_normals
+
+            fn_host = facet_nodes.cpu().numpy().astype(np.int64)
+            normals = _facet_normals(s.mesh.points, fn_host, s.cell_nodes()[rows])
+            nc = s.n_comp
+            un = np.einsum("nqc,nc->nq", g[:, :, :nc], normals[:, :nc]) if nc == 3 else np.einsum(
+                "nqc,nc->nq", g, normals[:, :nc])
+            g = un[:, :, None] * normals[:, None, :nc]
+            comp_scale = torch.as_tensor(np.ascontiguousarray(normals[:, :nc] ** 2)).to(dev.device)
         g_dev = torch.as_tensor(np.ascontiguousarray(g, dtype=np.float64)).to(dev.device)
         return FormData(
             n_items=n, items=items, fdim=fdim, n_q=len(weights), n_phi=ref.n_phi, n_comp=s.n_comp, tab0=tab0, w=w,
-            facet_nodes=facet_nodes, g=g_dev,
+            facet_nodes=facet_nodes, g=g_dev, comp_scale=comp_scale,
         )
 
     def launch_local(self, dev, data, alpha_dev, dest_dev, Ke, re):
         _lib.call(
             "nfa_local_h1_facet", data.fdim, data.n_phi, data.n_q, data.n_comp, _lib.ptr(data.tab0), _lib.ptr(data.w),
-            _lib.ptr(dev.coords), _lib.ptr(data.facet_nodes), data.n_items, _lib.ptr(data.g), float(self.beta),
+            _lib.ptr(dev.coords), _lib.ptr(data.facet_nodes), data.n_items, _lib.ptr(data.g),
+            _lib.ptr(data.comp_scale), float(self.beta),
             float(self.r_sign), int(self.with_matrix), _lib.ptr(Ke), _lib.ptr(re), _lib.stream_ptr(),
         )

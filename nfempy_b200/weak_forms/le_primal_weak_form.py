@@ -4,6 +4,7 @@ R/src/weak_forms/le_primal_weak_form.py (same names, same ``functions`` keys, sa
 * ``LEPrimalWeakForm``            R/...:13-129   r = +int phi.f + int sigma(u_h):grad phi, functions rhs/lambda/mu
 * ``LEPrimalWeakFormBCDirichlet`` R/...:131-176  penalty beta = 1e12, functions u
 * ``LEPrimalWeakFormBCNeumann``   R/...:179-221  traction load, functions t
+* ``LEPrimalWeakFormBCNormalDirichlet`` R/...:224-286  normal-only penalty, functions u
 """
 from .. import _lib
 from .h1_common import H1FacetForm, H1VolumeForm
@@ -40,3 +41,16 @@ class LEPrimalWeakFormBCNeumann(H1FacetForm):
     beta = 1.0
     r_sign = 1.0
     with_matrix = False
+
+
+class LEPrimalWeakFormBCNormalDirichlet(H1FacetForm):
+    """Normal-displacement penalty, R/src/weak_forms/le_primal_weak_form.py:224-286: per component c the basis is
+    phi n_c, so J_cc = beta n_c^2 int phi phi^T (no cross-component blocks, as coded there) and
+    r_c = -beta int (u_D . n) n_c phi."""
+
+    field_name = "u"
+    data_name = "u"
+    beta = 1.0e12
+    r_sign = -1.0
+    with_matrix = True
+    normal_only = True

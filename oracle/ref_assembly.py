@@ -75,7 +75,7 @@ def assemble(space, forms, alpha=None):
     jac_g = DokMatrix(n)
     for kind, form, functions, n_items in forms:
         scatter = scatter_form if kind == "form" else scatter_bc_form
-        for i in range(n_items):
+        for i in (range(n_items) if isinstance(n_items, int) else n_items):  # a count or an explicit sequence
             scatter(space, form, functions, i, res_g, jac_g, alpha)
     indptr, indices, data = jac_g.getValuesCSR()
     return indptr, indices, data, res_g

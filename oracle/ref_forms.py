@@ -336,3 +336,30 @@ def laplace_dual_bc_dirichlet(space, functions, iel, alpha):
             res += det_jac[i] * omega * p_d[c] * phi
         r_el[c : c + n_dof : nc] += res
     return r_el, j_el
+
+
+def le_primal_bc_normal_dirichlet(space, functions, iel, alpha):
+    """LEPrimalWeakFormBCNormalDirichlet.evaluate_form, R/src/weak_forms/le_primal_weak_form.py:224-286."""
+    u_space, el, weights, x, det_jac, tab = _bc_setup(space, "u", iel)
+    nc = u_space.n_comp
+    cell = el.cell
+    dim = cell.dimension
+    n_phi = tab.shape[2]
+    n_dof = n_phi * nc
+    j_el, r_el = np.zeros((n_dof, n_dof)), np.zeros(n_dof)
+    neigh_cell = u_space.mesh.cells[u_space.first_neighbour(cell.id)]
+    n = normal(u_space.mesh, neigh_cell, cell)
+    beta = 1.0e12
+    for c in range(nc):
+        block = np.zeros((n_phi, n_phi))
+        for i, omega in enumerate(weights):
+            phi = tab[0, i, :, 0] * n[c]
+            block += beta * det_jac[i] * omega * np.outer(phi, phi)
+        res = np.zeros(n_phi)
+        for i, omega in enumerate(weights):
+            phi = tab[0, i, :, 0] * n[c]
+            u_d = functions["u"](x[i, 0], x[i, 1], x[i, 2])
+            res -= beta * det_jac[i] * omega * np.dot(u_d, n[0 : dim + 1]) * phi
+        r_el[c : c + n_dof : nc] += res
+        j_el[c : c + n_dof : nc, c : c + n_dof : nc] += block
+    return r_el, j_el

@@ -69,8 +69,10 @@ class Case:
         return ref_assembly.assemble(space, self.ref_forms_fn(space), alpha)
 
 
-def elasticity_case(n=2, with_bc=True, varying=False, alpha=False, k=2, dim=3, mesh=None, neumann=False):
-    from nfempy_b200.weak_forms import LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet, LEPrimalWeakFormBCNeumann
+def elasticity_case(n=2, with_bc=True, varying=False, alpha=False, k=2, dim=3, mesh=None, neumann=False,
+                    normal_bc=False):
+    from nfempy_b200.weak_forms import (LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet, LEPrimalWeakFormBCNeumann,
+                                        LEPrimalWeakFormBCNormalDirichlet)
 
     if mesh is None:
         mesh = box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(n, jitter=0.2)
@@ -86,22 +88,38 @@ def elasticity_case(n=2, with_bc=True, varying=False, alpha=False, k=2, dim=3, m
     functions = {"rhs": rhs, "lambda": f_lam, "mu": f_mu}
     bc_functions = {"u": uex}
     t_functions = {"t": rhs}
-    dir_tags = btag_list[:-1] if neumann else btag_list
+    dir_tags = btag_list
 
     def gpu_forms(space, a):
         wf = LEPrimalWeakForm(space)
         wf.functions = functions
         out = {"volume": ["form", range(len(space.discrete_spaces["u"].elements)), wf, a]}
         if with_bc:
-            bf = LEPrimalWeakFormBCDirichlet(space)
-            bf.functions = bc_functions
-            out["bc"] = ["bc_form", range(len(space.discrete_spaces["u"].bc_elements)), bf, a]
+            n_bc = len(space.discrete_spaces["u"].bc_elements)
+            if neumann or normal_bc:
+                # split the boundary elements between a Dirichlet part and the other condition
+                bf = LEPrimalWeakFormBCDirichlet(space)
+                bf.functions = bc_functions
+                out["bc"] = ["bc_form", list(range(0, n_bc, 2)), bf, a]
+                of = LEPrimalWeakFormBCNeumann(space) if neumann else LEPrimalWeakFormBCNormalDirichlet(space)
+                of.functions = t_functions if neumann else bc_functions
+                out["bc2"] = ["bc_form", list(range(1, n_bc, 2)), of, a]
+            else:
+                bf = LEPrimalWeakFormBCDirichlet(space)
+                bf.functions = bc_functions
+                out["bc"] = ["bc_form", range(n_bc), bf, a]
         return out
 
     def ref_forms_fn(space):
         out = [("form", ref_forms.le_primal, functions, len(space.discrete_spaces["u"].element_ids))]
         if with_bc:
-            out.append(("bc_form", ref_forms.le_primal_bc_dirichlet, bc_functions, len(space.discrete_spaces["u"].bc_element_ids)))
+            n_bc = len(space.discrete_spaces["u"].bc_element_ids)
+            if neumann or normal_bc:
+                out.append(("bc_form", ref_forms.le_primal_bc_dirichlet, bc_functions, list(range(0, n_bc, 2))))
+                other = ref_forms.le_primal_bc_neumann if neumann else ref_forms.le_primal_bc_normal_dirichlet
+                out.append(("bc_form", other, t_functions if neumann else bc_functions, list(range(1, n_bc, 2))))
+            else:
+                out.append(("bc_form", ref_forms.le_primal_bc_dirichlet, bc_functions, n_bc))
         return out
 
     alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None

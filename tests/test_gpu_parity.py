@@ -19,6 +19,15 @@ def test_elasticity_p2_3d(fused, with_bc):
     compare_csr(case.run_gpu(allow_fused=fused), case.run_oracle(), RTOL)
 
 
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("kind", ["neumann", "normal"])
+def test_elasticity_mixed_boundary_forms_on_subsequences(fused, kind):
+    """Dirichlet penalty on every other boundary facet, traction load or normal-only penalty on the rest: exercises
+    explicit (non-range) sequences, three segments in one plan, and the remaining two boundary forms."""
+    case = elasticity_case(n=2, with_bc=True, neumann=(kind == "neumann"), normal_bc=(kind == "normal"))
+    compare_csr(case.run_gpu(allow_fused=fused), case.run_oracle(), RTOL)
+
+
 def test_elasticity_p2_3d_varying_coefficients():
     case = elasticity_case(n=2, with_bc=True, varying=True)
     compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
