@@ -107,6 +107,19 @@ int nfa_local_hdiv_facet(int dim, int nfd, int n_q, const double *d_trace_tab, c
                          const int32_t *d_facet_nodes, const int32_t *d_neigh_nodes, const double *d_normals,
                          const double *d_pd, int64_t n_facets, double *d_re, nfa_stream stream);
 
+/* Two-flux mixed transport with reaction, fields [mp | mc | p | c] (config 5): SundusDualWeakForm.evaluate_form,
+ * R/examples/parabolic_diffusive_problem/SundusWeakForm.py:11-177.  mp, mc share the H(div) tables, p, c the L2 table.
+ * Residual and tangent at the current iterate d_alpha (global vector, gathered through d_dest [n, 2 n_u + 2 n_p]) with
+ * the previous time level d_alpha_prev; R = 1 + eta c_h^2 gives the only nonlinear tangent term 2 eta c_h (w, w).
+ * kappa, delta, eta stride-addressed; f_f, f_r [n, n_q] or NULL. */
+int nfa_local_sundus(int dim, int n_u, int n_p, int n_q, int nfd, const double *d_u_val, const double *d_u_div,
+                     const double *d_p_val, const double *d_weights, const double *d_Tcases, const int8_t *d_cases,
+                     const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_kappa,
+                     int64_t kappa_stride_cell, int64_t kappa_stride_q, const double *d_delta, int64_t delta_stride_cell,
+                     int64_t delta_stride_q, const double *d_eta, int64_t eta_stride_cell, int64_t eta_stride_q,
+                     double delta_t, const double *d_f_f, const double *d_f_r, const double *d_alpha,
+                     const double *d_alpha_prev, const int32_t *d_dest, double *d_Ke, double *d_re, nfa_stream stream);
+
 /* ---- K6 sparsity plan: replaces the implicit pattern growth of PETSc Mat.setValue(..., addv=True) without
  * preallocation (R/src/assembly/ScatterFormData.py:5-11): the pattern is the union of
  * dest x dest over all items of all segments ("full" policy: explicit zeros kept), columns sorted per row.

@@ -34,6 +34,11 @@ SIGNATURES = {
         [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
     ),
     "nfa_local_hdiv_facet": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nfa_local_sundus": (
+        _i,
+        [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
+         _i64, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    ),
     "nfa_plan_create": (_i, [_i64, _i, ctypes.POINTER(_vp), _c_i64p, _c_i32p, _c_i32p, _vp, ctypes.POINTER(_vp), _vp]),
     "nfa_plan_from_bplan": (_i, [_vp, ctypes.POINTER(_vp), _vp]),
     "nfa_plan_destroy": (None, [_vp]),

@@ -22,7 +22,7 @@ from ..device import space_device
 from ..weak_forms.weak_form import BatchedWeakForm
 from .csr_matrix import CSRMatrix
 
-_SUPPORTED = ("form", "bc_form")
+_SUPPORTED = ("form", "bc_form", "time_dependent_form", "time_dependent_bc_form")
 _KNOWN = (
     "form", "bc_form", "interface_form", "bc_interface_form", "time_dependent_form", "time_dependent_bc_form",
 )
@@ -101,6 +101,13 @@ class GPUAssembler:
             if form_type not in _SUPPORTED:
                 raise NotImplementedError("GPUAssembler: form type %r has no CUDA kernel yet" % form_type)
             _, sequence, form, alpha = input_list[:4]
+            t = None
+            if "time_dependent" in form_type:
+                # [type, sequence, form, (alpha_n, alpha), t]; the reference hands alpha_n[dest] to the form as its
+                # first (differentiated) vector and alpha[dest] as the second (ScatterFormData.py:28-33, 43-49)
+                if len(input_list) < 5:
+                    raise ValueError("GPUAssembler: time-dependent forms are listed as [type, sequence, form, (alpha_n, alpha), t]")
+                t = input_list[4]
             if not isinstance(form, BatchedWeakForm):
                 raise NotImplementedError(
                     "GPUAssembler: %s has no CUDA kernel (no CPU fallback is provided)" % type(form).__name__
@@ -108,12 +115,12 @@ class GPUAssembler:
             if form.form_kind != form_type:
                 raise ValueError("GPUAssembler: %s is a %r, listed as %r" % (type(form).__name__, form.form_kind, form_type))
             items = _as_items(sequence, form.n_items_total())
-            out.append((name, form_type, items, form, alpha))
+            out.append((name, form_type, items, form, (alpha, t) if t is not None else alpha))
         return out
 
     @staticmethod
     def _dest_dev(dev, form, items):
-        full = dev.dest() if form.form_kind == "form" else dev.bc_dest()
+        full = dev.dest() if form.form_kind in ("form", "time_dependent_form") else dev.bc_dest()
         if items is None:
             return full
         idx = torch.as_tensor(items).to(full.device)
@@ -182,7 +189,10 @@ class GPUAssembler:
         Returns the state ``run`` consumes; split out so that repeated assemblies reuse it."""
         dev = space_device(self.space, self.device)
         entries = self._entries()
-        datas = [form.prepare(dev, items) for (_, _, items, form, _) in entries]
+        datas = [
+            form.prepare(dev, items, t=al[1]) if "time_dependent" in kind else form.prepare(dev, items)
+            for (_, kind, items, form, al) in entries
+        ]
         dests = [self._dest_dev(dev, form, items) for (_, _, items, form, _) in entries]
         fused_index = None
         if self.allow_fused:
@@ -210,10 +220,23 @@ class GPUAssembler:
             rhs_dev = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
         nseg = len(entries)
         Ke_list, re_list, keep = [None] * nseg, [None] * nseg, []
-        for i, ((_, _, _, form, alpha), data, dest) in enumerate(zip(entries, datas, dests)):
-            alpha_dev = None
-            if alpha is not None and np.any(np.asarray(alpha) != 0.0):
-                alpha_dev = torch.as_tensor(np.ascontiguousarray(alpha, dtype=np.float64)).to(dev.device)
+        def upload(vec):
+            if vec is None or not np.any(np.asarray(vec) != 0.0):
+                return None
+            return torch.as_tensor(np.ascontiguousarray(vec, dtype=np.float64)).to(dev.device)
+
+        for i, ((_, kind, _, form, alpha), data, dest) in enumerate(zip(entries, datas, dests)):
+            if "time_dependent" in kind:
+                (first, second), _t = alpha
+                first_dev, second_dev = upload(first), (upload(second) if kind == "time_dependent_form" else None)
+                nl = form.n_loc()
+                Ke = torch.empty((data.n_items, nl, nl), dtype=torch.float64, device=dev.device)
+                re = torch.empty((data.n_items, nl), dtype=torch.float64, device=dev.device)
+                form.launch_local(dev, data, first_dev, dest, Ke, re, second_dev)
+                Ke_list[i], re_list[i] = Ke, re
+                keep += [Ke, re, first_dev, second_dev]
+                continue
+            alpha_dev = upload(alpha)
             if i == plan.fused_index:
                 spec = form.fused_spec(data)
                 target = jac.values_dev if jac.is_zero else torch.empty_like(jac.values_dev)

@@ -33,8 +33,8 @@ def physical_points(dev, dim, points, cell_nodes_dev):
     return x.cpu().numpy()
 
 
-def evaluate(fn, x, n_comp=None):
-    """Evaluates ``fn(x, y, z)`` over ``x[n, n_q, 3]``.
+def evaluate(fn, x, n_comp=None, extra=()):
+    """Evaluates ``fn(x, y, z, *extra)`` over ``x[n, n_q, 3]`` (``extra`` = e.g. the time of a time-dependent form).
 
     Returns ``[n, n_q]`` for scalar coefficients (``n_comp is None``) or ``[n, n_q, n_comp]`` for vector data.
     Tries one vectorised call; falls back to the reference's point-by-point calling convention when the callable
@@ -42,7 +42,7 @@ def evaluate(fn, x, n_comp=None):
     n, nq, _ = x.shape
     flat = x.reshape(-1, 3)
     try:
-        out = np.asarray(fn(flat[:, 0], flat[:, 1], flat[:, 2]), dtype=np.float64)
+        out = np.asarray(fn(flat[:, 0], flat[:, 1], flat[:, 2], *extra), dtype=np.float64)
         if n_comp is None:
             if out.ndim == 0:
                 out = np.full(n * nq, float(out))
@@ -59,9 +59,9 @@ def evaluate(fn, x, n_comp=None):
     except (ValueError, TypeError, IndexError):
         pass
     if n_comp is None:
-        vals = np.array([float(fn(p[0], p[1], p[2])) for p in flat])
+        vals = np.array([float(fn(p[0], p[1], p[2], *extra)) for p in flat])
         return vals.reshape(n, nq)
-    vals = np.array([np.asarray(fn(p[0], p[1], p[2]), dtype=np.float64).reshape(-1)[:n_comp] for p in flat])
+    vals = np.array([np.asarray(fn(p[0], p[1], p[2], *extra), dtype=np.float64).reshape(-1)[:n_comp] for p in flat])
     return vals.reshape(n, nq, n_comp)
 
 

@@ -99,6 +99,35 @@ __device__ __forceinline__ void compute_geom(const double (&X)[DIM + 1][3], Geom
     }
 }
 
+// |det J| only (no inverse, no division): sqrt(det(J^T J)), i.e. |det J| for DIM = 3.
+template <int DIM>
+__device__ __forceinline__ double compute_det(const double (&X)[DIM + 1][3]) {
+    double J[3][DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) J[r][c] = X[c + 1][r] - X[0][r];
+    if constexpr (DIM == 3) {
+        double d = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) + J[0][1] * (J[1][2] * J[2][0] - J[1][0] * J[2][2]) +
+                   J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        return fabs(d);
+    } else if constexpr (DIM == 2) {
+        double a = 0, b = 0, c = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            a += J[r][0] * J[r][0];
+            b += J[r][0] * J[r][1];
+            c += J[r][1] * J[r][1];
+        }
+        return sqrt(a * c - b * b);
+    } else {
+        double a = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) a += J[r][0] * J[r][0];
+        return sqrt(a);
+    }
+}
+
 template <int DIM>
 __device__ __forceinline__ void load_cell_coords(const double *__restrict__ coords,
                                                  const int32_t *__restrict__ cell_nodes, int64_t cell,

@@ -372,37 +372,82 @@ extern "C" int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp,
 // ------------------------------------------------------------------------------------------------
 // Load vector only (fused path): re[cell][a*nc + i] = sign * sum_q w_q det phi_a(q) f[cell][q][i].
 // One warp per cell: the cell's f block (n_q * n_comp contiguous doubles) is read once, coalesced, into shared
-// memory; lane (a, i) then contracts it with the premultiplied table w_q phi_a(q).  HBM-bound on f.
-template <int DIM>
-__global__ void __launch_bounds__(128)
-    local_h1_load_kernel(int n_phi, int n_q, int n_comp, const double *__restrict__ tab0,
+// memory; lane (a, i) contracts it with its own column of the premultiplied table w_q phi_a(q), which it keeps in
+// registers for the whole kernel when the rule size NQ is a compile-time constant.  HBM-bound on f.
+template <int DIM, int NQ>
+__global__ void __launch_bounds__(128, 12)
+    local_h1_load_kernel(int n_phi, int n_q_rt, int n_comp, const double *__restrict__ tab0,
                          const double *__restrict__ weights, const double *__restrict__ coords,
                          const int32_t *__restrict__ cell_nodes, int64_t n_cells,
                          const double *__restrict__ f, double sign, double *__restrict__ re) {
     extern __shared__ double smem[];
-    double *s_wt = smem;                       // [n_q][n_phi]  w_q phi_a(q)
+    const int n_q = NQ > 0 ? NQ : n_q_rt;
+    double *s_wt = smem;                       // [n_q][n_phi]  w_q phi_a(q)   (runtime-NQ path only)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int fn = n_q * n_comp, n_loc = n_phi * n_comp;
-    double *s_f = s_wt + n_q * n_phi + warp * fn;  // [n_q][n_comp] of the warp's current cell
+    double *s_f = s_wt + n_q * n_phi + warp * 2 * fn;  // [2][n_q][n_comp] of the warp's current two cells
     for (int i = threadIdx.x; i < n_q * n_phi; i += blockDim.x) s_wt[i] = weights[i / n_phi] * tab0[i];
     __syncthreads();
-    for (int64_t cell = (int64_t)blockIdx.x * 4 + warp; cell < n_cells; cell += (int64_t)gridDim.x * 4) {
-        double X[DIM + 1][3];
-        load_cell_coords<DIM>(coords, cell_nodes, cell, X);
-        Geom<DIM> g;
-        compute_geom<DIM>(X, g);
-        __syncwarp();
-        if (f)
-            for (int i = lane; i < fn; i += 32) s_f[i] = f[cell * fn + i];
-        __syncwarp();
-        for (int ra = lane; ra < n_loc; ra += 32) {
-            const int a = ra / n_comp, i = ra - a * n_comp;
-            double acc = 0.0;
-            if (f)
-                for (int q = 0; q < n_q; ++q) acc += s_wt[q * n_phi + a] * g.det * s_f[q * n_comp + i];
-            re[cell * n_loc + ra] = sign * acc;
+    constexpr int NR = NQ > 0 ? NQ : 1;
+    for (int ra0 = 0; ra0 < n_loc; ra0 += 32) {  // one pass when n_loc <= 32
+        const int ra = ra0 + lane;
+        const bool active = ra < n_loc;
+        const int a = active ? ra / n_comp : 0, i = active ? ra - a * n_comp : 0;
+        double wt[NR];
+        if constexpr (NQ > 0) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) wt[q] = s_wt[q * n_phi + a];
+        }
+        // two cells per trip: twice the loads in flight per warp (the kernel is latency bound otherwise)
+        const int64_t stride = (int64_t)gridDim.x * 4;
+        for (int64_t cell = (int64_t)blockIdx.x * 4 + warp; cell < n_cells; cell += 2 * stride) {
+            const int64_t cell2 = cell + stride;
+            const bool two = cell2 < n_cells;
+            double X[DIM + 1][3], X2[DIM + 1][3];
+            load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+            load_cell_coords<DIM>(coords, cell_nodes, two ? cell2 : cell, X2);
+            __syncwarp();
+            if (f) {
+                for (int t = lane; t < fn; t += 32) {
+                    s_f[t] = f[cell * fn + t];
+                    s_f[fn + t] = two ? f[cell2 * fn + t] : 0.0;
+                }
+            }
+            const double det = compute_det<DIM>(X), det2 = compute_det<DIM>(X2);
+            __syncwarp();
+            double acc = 0.0, acc2 = 0.0;
+            if (f && active) {
+                for (int q = 0; q < n_q; ++q) {
+                    const double wv = s_wt[q * n_phi + a];
+                    acc += wv * s_f[q * n_comp + i];
+                    acc2 += wv * s_f[fn + q * n_comp + i];
+                }
+            }
+            if (active) {
+                re[cell * n_loc + ra] = sign * (acc * det);
+                if (two) re[cell2 * n_loc + ra] = sign * (acc2 * det2);
+            }
         }
     }
+}
+
+template <int DIM>
+static int launch_h1_load(int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,
+                          const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *f, double sign,
+                          double *re, cudaStream_t s) {
+    size_t smem = sizeof(double) * ((size_t)n_q * n_phi + 8 * (size_t)n_q * n_comp);
+    int64_t ctas = (n_cells + 3) / 4;
+    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
+#define NFA_LOAD_CASE(NQV)                                                                                          \
+    local_h1_load_kernel<DIM, NQV><<<grid, 128, smem, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes,  \
+                                                           n_cells, f, sign, re)
+    // The register-resident-weights instantiations (NQ > 0) cost 126 registers/thread and left the kernel latency
+    // bound at 25 % occupancy (profiles/r01_load_kernel_ncu_summary.txt); the shared-memory table path keeps 12 CTAs
+    // per SM resident instead.
+    NFA_LOAD_CASE(0);
+#undef NFA_LOAD_CASE
+    NFA_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,
@@ -410,20 +455,8 @@ extern "C" int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const 
                                  double sign, double *re, nfa_stream stream) {
     if (n_cells == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    size_t smem = sizeof(double) * ((size_t)n_q * n_phi + 4 * (size_t)n_q * n_comp);
-    int64_t ctas = (n_cells + 3) / 4;
-    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
-    if (dim == 3)
-        local_h1_load_kernel<3><<<grid, 128, smem, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
-                                                     sign, re);
-    else if (dim == 2)
-        local_h1_load_kernel<2><<<grid, 128, smem, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
-                                                     sign, re);
-    else if (dim == 1)
-        local_h1_load_kernel<1><<<grid, 128, smem, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f,
-                                                     sign, re);
-    else
-        return fail("nfa_local_h1_load: dim must be 1, 2 or 3");
-    NFA_LAUNCH_CHECK();
-    return 0;
+    if (dim == 3) return launch_h1_load<3>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);
+    if (dim == 2) return launch_h1_load<2>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);
+    if (dim == 1) return launch_h1_load<1>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);
+    return fail("nfa_local_h1_load: dim must be 1, 2 or 3");
 }

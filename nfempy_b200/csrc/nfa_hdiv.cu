@@ -159,6 +159,171 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+
+// Two-flux mixed transport (SundusDualWeakForm, R/examples/parabolic_diffusive_problem/SundusWeakForm.py:11-177):
+// fields [mp | mc | p | c], mp/mc in the same H(div) element, p/c in the same L2 element.  Nonlinear in c through the
+// reaction R = 1 + eta c^2, so the kernel evaluates the state at the current iterate and writes residual and tangent.
+template <int DIM>
+__global__ void __launch_bounds__(128)
+    local_sundus_kernel(int n_u, int n_p, int n_q, int nfd, const double *__restrict__ u_val,
+                        const double *__restrict__ u_div, const double *__restrict__ p_val,
+                        const double *__restrict__ weights, const double *__restrict__ Tcases,
+                        const int8_t *__restrict__ cases, const double *__restrict__ coords,
+                        const int32_t *__restrict__ cell_nodes, int64_t n_cells, CoefH kappa, CoefH delta, CoefH eta,
+                        double inv_dt, const double *__restrict__ f_f, const double *__restrict__ f_r,
+                        const double *__restrict__ alpha, const double *__restrict__ alpha_prev,
+                        const int32_t *__restrict__ dest, double *__restrict__ Ke, double *__restrict__ re) {
+    constexpr int NF = DIM + 1;
+    extern __shared__ double smem[];
+    const int n_loc = 2 * n_u + 2 * n_p;
+    double *s_psi = smem;                         // [n_q][n_u][DIM]
+    double *s_div = s_psi + n_q * n_u * DIM;      // [n_q][n_u]
+    double *s_T = s_div + n_q * n_u;              // [NF][nfd][nfd]
+    double *s_a = s_T + NF * nfd * nfd;           // [n_loc] current iterate (local)
+    double *s_an = s_a + n_loc;                   // [n_loc] previous time level (local)
+    double *s_q = s_an + n_loc;                   // [n_q][QS] per-point state
+    constexpr int QS = 8 + 2 * DIM;               // wd, wd/kappa, wd/delta, eta, p_h, c_h, dpdt, dcdt | mp_h[DIM] | mc_h[DIM]
+    double *s_dv = s_q + n_q * QS;                // [n_q][2] div mp_h, div mc_h
+    const int n_fdofs = NF * nfd;
+    for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        double X[DIM + 1][3];
+        load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+        Geom<DIM> g;
+        compute_geom<DIM>(X, g);
+        const double idet = 1.0 / g.det;
+        __syncthreads();
+        for (int i = threadIdx.x; i < NF * nfd * nfd; i += blockDim.x) {
+            int fc = i / (nfd * nfd);
+            s_T[i] = Tcases[(int)cases[cell * NF + fc] * nfd * nfd + (i - fc * nfd * nfd)];
+        }
+        for (int i = threadIdx.x; i < n_loc; i += blockDim.x) {
+            int d = dest[cell * n_loc + i];
+            s_a[i] = alpha ? alpha[d] : 0.0;
+            s_an[i] = alpha_prev ? alpha_prev[d] : 0.0;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < n_q * n_u; idx += blockDim.x) {
+            int q = idx / n_u, j = idx - q * n_u;
+            double vh[DIM], dh;
+            if (j < n_fdofs) {
+                int fc = j / nfd, a = j - fc * nfd;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) vh[k] = 0.0;
+                dh = 0.0;
+                for (int b = 0; b < nfd; ++b) {
+                    double t = s_T[(fc * nfd + a) * nfd + b];
+                    const double *src = u_val + ((int64_t)q * n_u + fc * nfd + b) * DIM;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) vh[k] += t * src[k];
+                    dh += t * u_div[q * n_u + fc * nfd + b];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) vh[k] = u_val[((int64_t)q * n_u + j) * DIM + k];
+                dh = u_div[q * n_u + j];
+            }
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) v += g.J[c][k] * vh[k];
+                s_psi[(q * n_u + j) * DIM + c] = v * idet;
+            }
+            s_div[q * n_u + j] = dh * idet;
+        }
+        __syncthreads();
+        // per-point state at the current iterate
+        for (int q = threadIdx.x; q < n_q; q += blockDim.x) {
+            double *st = s_q + q * QS;
+            double wd = weights[q] * g.det;
+            st[0] = wd;
+            st[1] = wd * (1.0 / kappa.p[cell * kappa.sc + q * kappa.sq]);
+            st[2] = wd * (1.0 / delta.p[cell * delta.sc + q * delta.sq]);
+            st[3] = eta.p[cell * eta.sc + q * eta.sq];
+            double ph = 0, ch = 0, pn = 0, cn = 0;
+            for (int k = 0; k < n_p; ++k) {
+                double w = p_val[q * n_p + k];
+                ph += s_a[2 * n_u + k] * w;
+                ch += s_a[2 * n_u + n_p + k] * w;
+                pn += s_an[2 * n_u + k] * w;
+                cn += s_an[2 * n_u + n_p + k] * w;
+            }
+            st[4] = ph;
+            st[5] = ch;
+            st[6] = (ph - pn) * inv_dt;
+            st[7] = (ch - cn) * inv_dt;
+            double dmp = 0, dmc = 0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) st[8 + c] = st[8 + DIM + c] = 0.0;
+            for (int j = 0; j < n_u; ++j) {
+                const double *ps = s_psi + (q * n_u + j) * DIM;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    st[8 + c] += s_a[j] * ps[c];
+                    st[8 + DIM + c] += s_a[n_u + j] * ps[c];
+                }
+                dmp += s_a[j] * s_div[q * n_u + j];
+                dmc += s_a[n_u + j] * s_div[q * n_u + j];
+            }
+            s_dv[2 * q] = dmp;
+            s_dv[2 * q + 1] = dmc;
+        }
+        __syncthreads();
+        double *K = Ke + cell * (int64_t)n_loc * n_loc;
+        for (int e = threadIdx.x; e < n_loc * n_loc; e += blockDim.x) {
+            int ra = e / n_loc, rb = e - ra * n_loc;
+            // field of row / column: 0 mp, 1 mc, 2 p, 3 c; index inside the field
+            int fa = ra < n_u ? 0 : (ra < 2 * n_u ? 1 : (ra < 2 * n_u + n_p ? 2 : 3));
+            int fb = rb < n_u ? 0 : (rb < 2 * n_u ? 1 : (rb < 2 * n_u + n_p ? 2 : 3));
+            int ia = ra - (fa == 0 ? 0 : fa == 1 ? n_u : fa == 2 ? 2 * n_u : 2 * n_u + n_p);
+            int ib = rb - (fb == 0 ? 0 : fb == 1 ? n_u : fb == 2 ? 2 * n_u : 2 * n_u + n_p);
+            double acc = 0.0;
+            if (fa <= 1 && fb == fa) {  // flux mass with kappa^-1 / delta^-1
+                for (int q = 0; q < n_q; ++q) {
+                    const double *a = s_psi + (q * n_u + ia) * DIM, *b = s_psi + (q * n_u + ib) * DIM;
+                    double dot = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) dot += a[c] * b[c];
+                    acc += s_q[q * QS + 1 + fa] * dot;
+                }
+            } else if (fa <= 1 && fb == fa + 2) {  // -(w_l, div psi_i)
+                for (int q = 0; q < n_q; ++q) acc -= s_q[q * QS] * p_val[q * n_p + ib] * s_div[q * n_u + ia];
+            } else if (fa >= 2 && fb == fa - 2) {  // +(div psi_j, w_k)
+                for (int q = 0; q < n_q; ++q) acc += s_q[q * QS] * s_div[q * n_u + ib] * p_val[q * n_p + ia];
+            } else if (fa >= 2 && fb == fa) {  // time derivative (+ reaction tangent 2 eta c_h on the c block)
+                for (int q = 0; q < n_q; ++q) {
+                    const double *st = s_q + q * QS;
+                    double coef = inv_dt + (fa == 3 ? 2.0 * st[3] * st[5] : 0.0);
+                    acc += st[0] * coef * p_val[q * n_p + ib] * p_val[q * n_p + ia];
+                }
+            }
+            K[e] = acc;
+        }
+        for (int ra = threadIdx.x; ra < n_loc; ra += blockDim.x) {
+            int fa = ra < n_u ? 0 : (ra < 2 * n_u ? 1 : (ra < 2 * n_u + n_p ? 2 : 3));
+            int ia = ra - (fa == 0 ? 0 : fa == 1 ? n_u : fa == 2 ? 2 * n_u : 2 * n_u + n_p);
+            double acc = 0.0;
+            for (int q = 0; q < n_q; ++q) {
+                const double *st = s_q + q * QS;
+                if (fa <= 1) {
+                    const double *ps = s_psi + (q * n_u + ia) * DIM;
+                    double dot = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) dot += st[8 + fa * DIM + c] * ps[c];
+                    acc += st[1 + fa] * dot - st[0] * st[4 + fa] * s_div[q * n_u + ia];
+                } else {
+                    double w = p_val[q * n_p + ia];
+                    double src = (fa == 2) ? (f_f ? f_f[cell * n_q + q] : 0.0) : (f_r ? f_r[cell * n_q + q] : 0.0);
+                    double body = st[6 + (fa - 2)] + s_dv[2 * q + (fa - 2)];
+                    if (fa == 3) body += 1.0 + st[3] * st[5] * st[5];
+                    acc += st[0] * (body - src) * w;
+                }
+            }
+            re[cell * n_loc + ra] = acc;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, const double *u_val,
@@ -206,6 +371,39 @@ extern "C" int nfa_local_hdiv_facet(int dim, int nfd, int n_q, const double *tra
                                                         facet_nodes, neigh_nodes, normals, pd, n_facets, re);
     else
         return fail("nfa_local_hdiv_facet: dim must be 2 or 3");
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nfa_local_sundus(int dim, int n_u, int n_p, int n_q, int nfd, const double *u_val, const double *u_div,
+                                const double *p_val, const double *weights, const double *Tcases, const int8_t *cases,
+                                const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *kappa,
+                                int64_t ksc, int64_t ksq, const double *delta, int64_t dsc, int64_t dsq,
+                                const double *eta, int64_t esc, int64_t esq, double delta_t, const double *f_f,
+                                const double *f_r, const double *alpha, const double *alpha_prev, const int32_t *dest,
+                                double *Ke, double *re, nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (!dest) return fail("nfa_local_sundus: dest is required");
+    if (delta_t == 0.0) return fail("nfa_local_sundus: delta_t is zero");
+    cudaStream_t s = (cudaStream_t)stream;
+    CoefH kp{kappa, ksc, ksq}, dl{delta, dsc, dsq}, et{eta, esc, esq};
+    int n_loc = 2 * n_u + 2 * n_p;
+    size_t smem = sizeof(double) * ((size_t)n_q * n_u * (dim + 1) + (size_t)(dim + 1) * nfd * nfd + 2 * n_loc +
+                                    (size_t)n_q * (8 + 2 * dim) + 2 * n_q);
+    if (smem > 200 * 1024) return fail("nfa_local_sundus: element too large for the shared-memory staging");
+    int grid = (int)(n_cells < 148 * 8 ? n_cells : 148 * 8);
+    if (dim == 3) {
+        auto kern = local_sundus_kernel<3>;
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, s>>>(n_u, n_p, n_q, nfd, u_val, u_div, p_val, weights, Tcases, cases, coords, cell_nodes,
+                                     n_cells, kp, dl, et, 1.0 / delta_t, f_f, f_r, alpha, alpha_prev, dest, Ke, re);
+    } else if (dim == 2) {
+        auto kern = local_sundus_kernel<2>;
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, s>>>(n_u, n_p, n_q, nfd, u_val, u_div, p_val, weights, Tcases, cases, coords, cell_nodes,
+                                     n_cells, kp, dl, et, 1.0 / delta_t, f_f, f_r, alpha, alpha_prev, dest, Ke, re);
+    } else
+        return fail("nfa_local_sundus: dim must be 2 or 3");
     NFA_LAUNCH_CHECK();
     return 0;
 }

@@ -3,3 +3,4 @@ from .le_primal_weak_form import (LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet,
                                   LEPrimalWeakFormBCNormalDirichlet)
 from .laplace_primal_weak_form import LaplacePrimalWeakForm, LaplacePrimalWeakFormBCDirichlet
 from .laplace_dual_weak_form import LaplaceDualWeakForm, LaplaceDualWeakFormBCDirichlet
+from .sundus_weak_form import SundusDualWeakForm, SundusDualWeakFormBCDirichlet

@@ -1,0 +1,154 @@
+"""Two-flux mixed transport with reaction (config 5) -- GPU versions of the example-local forms of
+R/examples/parabolic_diffusive_problem/SundusWeakForm.py (same class names, same ``functions`` keys).
+
+* ``SundusDualWeakForm``            R/...:11-177   fields mp, mc (H(div)), p, c (L2); implicit Euler in time; reaction
+  ``R = 1 + eta c^2`` makes the form nonlinear in c, so residual AND tangent depend on the current iterate.
+  ``evaluate_form(i, alpha_n_p_1, alpha_n, t)`` differentiates with respect to its FIRST vector.
+* ``SundusDualWeakFormBCDirichlet`` R/...:180-269  natural conditions ``int p_D (psi . n)`` on the mp facet dofs and
+  ``int c_D (psi . n)`` on the mc facet dofs, no matrix.
+
+``functions``: ``rhs_f(x,y,z,t)``, ``rhs_r(x,y,z,t)``, ``kappa``, ``delta``, ``eta`` ``(x,y,z)``, ``delta_t`` (a number);
+boundary: ``p(x,y,z,t)``, ``c(x,y,z,t)``.
+"""
+import numpy as np
+import torch
+
+from .. import _lib, coefficients
+from ..basis.orientation import case_matrices
+from .laplace_dual_weak_form import LaplaceDualWeakFormBCDirichlet, _all_cases
+from .weak_form import BatchedWeakForm, FormData, take_rows
+
+_FIELDS = ["mp", "mc", "p", "c"]
+
+
+def _tables(space):
+    if list(space.discrete_spaces.keys()) != _FIELDS:
+        raise _lib.NfaError("Sundus forms expect the fields mp, mc, p, c in this order")
+    mp, mc, p, c = (space.discrete_spaces[n] for n in _FIELDS)
+    if (mp.family, mp.k_order) != (mc.family, mc.k_order) or (p.family, p.k_order) != (c.family, c.k_order):
+        raise _lib.NfaError("Sundus forms: mp/mc and p/c must use the same elements")
+    if mp.family not in ("RT", "BDM") or p.family != "Lagrange" or any(s.n_comp != 1 for s in (mp, mc, p, c)):
+        raise _lib.NfaError("Sundus forms need scalar-component RT/BDM fluxes and Lagrange scalars")
+    ref = mp.ref_element
+    dim = mp.dimension
+    nfd = len(ref.entity_dofs[dim - 1][0])
+    return mp, p, ref, dim, nfd
+
+
+class SundusDualWeakForm(BatchedWeakForm):
+    form_kind = "time_dependent_form"
+
+    def n_items_total(self):
+        return len(self.space.discrete_spaces["mp"].elements)
+
+    def dest_table(self):
+        return self.space.destination_table()
+
+    def prepare(self, dev, items=None, arrays=None, t=0.0):
+        self._check()
+        mp, p, ref, dim, nfd = _tables(self.space)
+        points, weights = self.space.quadrature[dim]
+        key = ("sundus", mp.family, mp.k_order, p.k_order, dim, len(weights))
+        tab = ref.tabulate(1, points)
+        u_val = dev.tensor(key + ("uval",), lambda: tab[0])
+        u_div = dev.tensor(key + ("udiv",), lambda: sum(tab[1 + d][:, :, d] for d in range(dim)))
+        p_val = dev.tensor(key + ("pval",), lambda: p.ref_element.tabulate(0, points)[0, :, :, 0])
+        w = dev.tensor(key + ("w",), lambda: weights)
+        tcases = dev.tensor(key + ("T",), lambda: case_matrices(ref))
+        cases_all = dev._get(key + ("cases",), lambda: torch.as_tensor(_all_cases(mp)).to(dev.device))
+        cases = take_rows(cases_all, items)
+        cell_nodes = take_rows(dev.cell_nodes("mp"), items)
+        n = int(cell_nodes.shape[0])
+        x = coefficients.physical_points(dev, dim, points, cell_nodes)
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev.device)
+        coefs = {}
+        for name in ("kappa", "delta", "eta"):
+            arr, sc, sq, kind = coefficients.classify(coefficients.evaluate(self.functions[name], x))
+            coefs[name] = (up(arr), sc, sq, kind)
+        loads = {}
+        for name in ("rhs_f", "rhs_r"):
+            f = coefficients.evaluate(self.functions[name], x, 1, extra=(t,))[:, :, 0]
+            loads[name] = up(f) if np.any(f) else None
+        return FormData(
+            n_items=n, items=items, dim=dim, n_q=len(weights), n_u=ref.n_phi, n_p=p.ref_element.n_phi, nfd=nfd,
+            u_val=u_val, u_div=u_div, p_val=p_val, w=w, tcases=tcases, cases=cases, cell_nodes=cell_nodes, coefs=coefs,
+            loads=loads, delta_t=float(self.functions["delta_t"]), t=t,
+        )
+
+    def launch_local(self, dev, data, alpha_dev, dest_dev, Ke, re, alpha_prev_dev=None):
+        if dest_dev is None:
+            raise _lib.NfaError("SundusDualWeakForm needs the destination table on the device")
+        k, d, e = data.coefs["kappa"], data.coefs["delta"], data.coefs["eta"]
+        _lib.call(
+            "nfa_local_sundus", data.dim, data.n_u, data.n_p, data.n_q, data.nfd, _lib.ptr(data.u_val),
+            _lib.ptr(data.u_div), _lib.ptr(data.p_val), _lib.ptr(data.w), _lib.ptr(data.tcases), _lib.ptr(data.cases),
+            _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes), data.n_items, _lib.ptr(k[0]), k[1], k[2], _lib.ptr(d[0]),
+            d[1], d[2], _lib.ptr(e[0]), e[1], e[2], data.delta_t, _lib.ptr(data.loads["rhs_f"]),
+            _lib.ptr(data.loads["rhs_r"]), _lib.ptr(alpha_dev), _lib.ptr(alpha_prev_dev), _lib.ptr(dest_dev),
+            _lib.ptr(Ke), _lib.ptr(re), _lib.stream_ptr(),
+        )
+
+    def evaluate_form(self, element_index, alpha_n_p_1, alpha_n, t):
+        """Single-cell evaluation through the same kernel (local vectors in, ``(r_el, j_el)`` out)."""
+        from ..device import space_device
+
+        self._check()
+        dev = space_device(self.space)
+        data = self.prepare(dev, np.array([int(element_index)], dtype=np.int64), t=t)
+        nl = self.n_loc()
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64).reshape(-1)).to(dev.device)
+        dest = torch.arange(nl, dtype=torch.int32, device=dev.device).reshape(1, nl)
+        Ke = torch.empty((1, nl, nl), dtype=torch.float64, device=dev.device)
+        re = torch.empty((1, nl), dtype=torch.float64, device=dev.device)
+        self.launch_local(dev, data, up(alpha_n_p_1), dest, Ke, re, up(alpha_n))
+        return re[0].cpu().numpy(), Ke[0].cpu().numpy()
+
+
+class SundusDualWeakFormBCDirichlet(BatchedWeakForm):
+    form_kind = "time_dependent_bc_form"
+
+    def n_items_total(self):
+        return len(self.space.discrete_spaces["mp"].bc_elements)
+
+    def dest_table(self):
+        return self.space.bc_destination_table()
+
+    def prepare(self, dev, items=None, arrays=None, t=0.0):
+        if self.space is None or self.functions is None:
+            raise ValueError("weak form needs .space and .functions")
+        _tables(self.space)
+        mp, mc = self.space.discrete_spaces["mp"], self.space.discrete_spaces["mc"]
+        if not np.array_equal(mp.bc_element_ids, mc.bc_element_ids):
+            raise _lib.NfaError("Sundus boundary form: mp and mc must carry the same boundary elements")
+        # the geometry / trace tables are those of the natural condition of one H(div) field; evaluate them once
+        # through the LaplaceDual boundary form on a view of the space that names the flux field "u"
+        view = _FluxView(self.space)
+        inner = LaplaceDualWeakFormBCDirichlet(view)
+        datas = []
+        for key in ("p", "c"):
+            fn = self.functions[key]
+            inner.functions = {"p": (lambda x, y, z, fn=fn: fn(x, y, z, t))}
+            datas.append(inner.prepare(dev, items))
+        return FormData(n_items=datas[0].n_items, items=items, parts=datas, inner=inner, nfd=datas[0].nfd)
+
+    def launch_local(self, dev, data, alpha_dev, dest_dev, Ke, re, alpha_prev_dev=None):
+        if Ke is not None:
+            Ke.zero_()
+        nfd = data.nfd
+        for k, part in enumerate(data.parts):
+            tmp = torch.empty((data.n_items, nfd), dtype=torch.float64, device=dev.device)
+            data.inner.launch_local(dev, part, None, None, None, tmp)
+            re[:, k * nfd : (k + 1) * nfd] = tmp
+
+
+class _FluxView:
+    """Presents the (mp, p) pair of a Sundus space under the names (u, p) the LaplaceDual boundary form reads."""
+
+    def __init__(self, space):
+        self._space = space
+        self.discrete_spaces = {"u": space.discrete_spaces["mp"], "p": space.discrete_spaces["p"]}
+        self.quadrature = space.quadrature
+        self.bc_quadrature = space.bc_quadrature
+
+    def __getattr__(self, name):
+        return getattr(self._space, name)

@@ -66,6 +66,37 @@ def scatter_bc_form(space, form, functions, idx, res_g, jac_g, alpha):
     scatter_lhs(jac_g, j_l, dest)
 
 
+def scatter_time_dependent_form(space, form, functions, idx, res_g, jac_g, alpha_n, alpha, t):
+    """scatter_time_dependent_form_data, R/src/assembly/ScatterFormData.py:28-33 (note the argument order it hands on)."""
+    dest = space.destination_indexes(idx)
+    alpha_l, alpha_l_n = alpha[dest], alpha_n[dest]
+    r_l, j_l = form(space, functions, idx, alpha_l_n, alpha_l, t)
+    scatter_rhs(res_g, r_l, dest)
+    scatter_lhs(jac_g, j_l, dest)
+
+
+def scatter_time_dependent_bc_form(space, form, functions, idx, res_g, jac_g, alpha_n, alpha, t):
+    """scatter_time_dependent_bc_form_data, R/src/assembly/ScatterFormData.py:43-49."""
+    dest = space.bc_destination_indexes(idx)
+    r_l, j_l = form(space, functions, idx, alpha_n[dest], t)
+    scatter_rhs(res_g, r_l, dest)
+    scatter_lhs(jac_g, j_l, dest)
+
+
+def assemble_time_dependent(space, forms, alphas, t):
+    """``forms``: ``(kind, form_fn, functions, n_items)`` with kind in {"time_dependent_form", "time_dependent_bc_form"};
+    ``alphas = (alpha_n, alpha)`` exactly as listed in ``form_to_input_list``."""
+    n = space.n_dof
+    alpha_n, alpha = alphas
+    res_g, jac_g = np.zeros(n), DokMatrix(n)
+    for kind, form, functions, n_items in forms:
+        scatter = scatter_time_dependent_form if kind == "time_dependent_form" else scatter_time_dependent_bc_form
+        for i in (range(n_items) if isinstance(n_items, int) else n_items):
+            scatter(space, form, functions, i, res_g, jac_g, alpha_n, alpha, t)
+    indptr, indices, data = jac_g.getValuesCSR()
+    return indptr, indices, data, res_g
+
+
 def assemble(space, forms, alpha=None):
     """``forms``: list of ``(kind, form_fn, functions, n_items)`` with kind in {"form", "bc_form"}.
     Returns ``(indptr, indices, data, rhs)`` exactly as the reference + PETSc would hand them to a solver."""

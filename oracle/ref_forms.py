@@ -363,3 +363,88 @@ def le_primal_bc_normal_dirichlet(space, functions, iel, alpha):
         r_el[c : c + n_dof : nc] += res
         j_el[c : c + n_dof : nc, c : c + n_dof : nc] += block
     return r_el, j_el
+
+
+# ---- two-flux mixed transport with reaction (config 5) --------------------------------------------------------
+def sundus_dual(space, functions, iel, alpha_n_p_1, alpha_n, t):
+    """SundusDualWeakForm.evaluate_form, R/examples/parabolic_diffusive_problem/SundusWeakForm.py:11-177.
+    The form is nonlinear in c (R = 1 + eta c^2); the reference differentiates it with forward AD.  Here the same
+    residual code runs in complex arithmetic and the Jacobian is the complex-step derivative
+    ``Im r(alpha + i h e_j) / h`` (h = 1e-30), which is exact to round-off for this polynomial residual."""
+    sp = [space.discrete_spaces[n] for n in ("mp", "mc", "p", "c")]
+    els = [RefElement(s, s.element_ids[iel]) for s in sp]
+    dim = els[0].cell.dimension
+    points, weights = space.quadrature[dim]
+    x, jac, det_jac, inv_jac = els[0].evaluate_mapping(points)
+    vp, vc, wp, wc = (e.evaluate_basis(points, jac, det_jac, inv_jac) for e in els)
+    n_mp, n_mc, n_p, n_c = vp.shape[2], vc.shape[2], wp.shape[2], wc.shape[2]
+    o_mc, o_p, o_c = n_mp, n_mp + n_mc, n_mp + n_mc + n_p
+    n_dof = o_c + n_c
+    f_f = np.asarray(functions["rhs_f"](x[:, 0], x[:, 1], x[:, 2], t))
+    f_r = np.asarray(functions["rhs_r"](x[:, 0], x[:, 1], x[:, 2], t))
+    wp_star = det_jac * weights * wp[0, :, :, 0].T
+    wc_star = det_jac * weights * wc[0, :, :, 0].T
+    delta_t = functions["delta_t"]
+    alpha_n = np.asarray(alpha_n, dtype=float)
+
+    def residual(a):
+        a = a.reshape(1, -1)
+        el_form = np.zeros(n_dof, dtype=a.dtype)
+        el_form[o_p:o_c] -= wp_star @ f_f[0].T
+        el_form[o_c:n_dof] -= wc_star @ f_r[0].T
+        for i, omega in enumerate(weights):
+            xv = x[i]
+            vp_h, vc_h = vp[0, i, :, 0:dim], vc[0, i, :, 0:dim]
+            wp_h, wc_h = wp[0, i, :, 0:dim], wc[0, i, :, 0:dim]
+            div_vp = np.array([[np.trace(vp[1 : 1 + dim, i, j, 0:dim]) / det_jac[i] for j in range(n_mp)]])
+            div_vc = np.array([[np.trace(vc[1 : 1 + dim, i, j, 0:dim]) / det_jac[i] for j in range(n_mc)]])
+            mp_h = (a[:, 0:o_mc] @ vp_h) * (1.0 / functions["kappa"](xv[0], xv[1], xv[2]))
+            mc_h = (a[:, o_mc:o_p] @ vc_h) * (1.0 / functions["delta"](xv[0], xv[1], xv[2]))
+            p_h, c_h = a[:, o_p:o_c] @ wp_h, a[:, o_c:n_dof] @ wc_h
+            p_n, c_n = alpha_n[o_p:o_c] @ wp_h, alpha_n[o_c:n_dof] @ wc_h
+            div_mp, div_mc = a[:, 0:o_mc] @ div_vp.T, a[:, o_mc:o_p] @ div_vc.T
+            r_h = 1.0 + functions["eta"](xv[0], xv[1], xv[2]) * c_h * c_h
+            dph_dt, dch_dt = (p_h - p_n) / delta_t, (c_h - c_n) / delta_t
+            integrand = np.zeros((1, n_dof), dtype=a.dtype)
+            integrand[:, 0:o_mc] = (mp_h @ vp_h.T) - (p_h @ div_vp)
+            integrand[:, o_mc:o_p] = (mc_h @ vc_h.T) - (c_h @ div_vc)
+            integrand[:, o_p:o_c] = dph_dt @ wp_h.T + div_mp @ wp_h.T
+            integrand[:, o_c:n_dof] = dch_dt @ wc_h.T + div_mc @ wc_h.T + r_h @ wc_h.T
+            el_form = el_form + det_jac[i] * omega * integrand.reshape((n_dof,))
+        return el_form
+
+    a0 = np.asarray(alpha_n_p_1, dtype=float)
+    r_el = residual(a0)
+    j_el = np.zeros((n_dof, n_dof))
+    h = 1.0e-30
+    for j in range(n_dof):
+        ac = a0.astype(complex)
+        ac[j] += 1j * h
+        j_el[:, j] = residual(ac).imag / h
+    return r_el, j_el
+
+
+def sundus_dual_bc_dirichlet(space, functions, iel, alpha, t):
+    """SundusDualWeakFormBCDirichlet.evaluate_form, R/examples/parabolic_diffusive_problem/SundusWeakForm.py:180-269."""
+    from . import ref_hdiv
+
+    out = []
+    for field, key in (("mp", "p"), ("mc", "c")):
+        f_space, el, weights, x, det_jac, _ = _bc_setup(space, field, iel)
+        cell = el.cell
+        points, _ = space.bc_quadrature[cell.dimension]
+        neigh = RefElement(f_space, f_space.first_neighbour(cell.id))
+        mapped = transform_lower_to_higher(np.asarray(points).reshape(len(weights), -1), cell, neigh.cell)
+        _, jac0, det0, inv0 = neigh.evaluate_mapping(mapped)
+        tr_tab = neigh.evaluate_basis(mapped, jac0, det0, inv0)
+        facet_index = neigh.cell.sub_cells_ids[cell.dimension].tolist().index(cell.id)
+        dofs = ref_hdiv.entity_dofs(neigh.family, neigh.cell.dimension, neigh.k)[cell.dimension][facet_index]
+        n = normal(f_space.mesh, neigh.cell, cell)
+        dim = neigh.cell.dimension
+        res = np.zeros(len(dofs))
+        for i, omega in enumerate(weights):
+            val = functions[key](x[i, 0], x[i, 1], x[i, 2], t)
+            res += det_jac[i] * omega * val[0] * (tr_tab[0, i, dofs, 0:dim] @ n[0:dim])
+        out.append(res)
+    r_el = np.concatenate(out)
+    return r_el, np.zeros((len(r_el), len(r_el)))

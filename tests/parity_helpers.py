@@ -196,3 +196,69 @@ def mixed_poisson_case(dim=3, k=1, n=2, family="RT", with_bc=True, varying=False
         mesh, lambda g: {"u": (dim, 1, family, k, g), "p": (dim, 1, "Lagrange", pk, g)}, {"u": [1], "p": [1]},
         {"u": btag_list if with_bc else []}, gpu_forms, ref_forms_fn, disc={"p": True},
     )
+
+
+class SundusCase:
+    """Config 5 style: mp, mc in RT_k, p, c in P_{k-1}^disc, implicit Euler step with a nonlinear reaction."""
+
+    def __init__(self, dim=3, k=1, n=2, mesh=None, t=0.3, delta_t=0.1):
+        self.dim, self.k, self.t = dim, k, t
+        self.mesh = mesh if mesh is not None else (
+            box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(n, jitter=0.2))
+        self.btags = [2, 3, 4, 5, 6, 7] if dim == 3 else [2, 3, 4, 5]
+        self.functions = {
+            "rhs_f": lambda x, y, z, t: np.array([np.sin(x + t) + y]), "rhs_r": lambda x, y, z, t: np.array([x * y + t * z]),
+            "kappa": lambda x, y, z: 2.0 + x, "delta": lambda x, y, z: 1.5, "eta": lambda x, y, z: 0.7 + 0.1 * y,
+            "delta_t": delta_t,
+        }
+        self.bc_functions = {"p": lambda x, y, z, t: np.array([x + t]), "c": lambda x, y, z, t: np.array([y * z - t])}
+
+    def _data(self, g):
+        d, k = self.dim, self.k
+        return {"mp": (d, 1, "RT", k, g), "mc": (d, 1, "RT", k, g), "p": (d, 1, "Lagrange", k - 1, g),
+                "c": (d, 1, "Lagrange", k - 1, g)}
+
+    def _build(self, space):
+        space.make_subspaces_discontinuous({"p": True, "c": True})
+        space.build_structures({n: [1] for n in ("mp", "mc", "p", "c")}, {"mp": self.btags, "mc": self.btags})
+        return space
+
+    def space(self):
+        return self._build(ProductSpace(self._data(self.mesh)))
+
+    def ref_space(self):
+        r = RefMesh(self.mesh.dimension, self.mesh.points, self.mesh._blocks)
+        r.build_conformal_mesh()
+        return self._build(RefProductSpace(self._data(r)))
+
+    @staticmethod
+    def alphas(n_dof):
+        return 0.3 * np.cos(np.arange(n_dof) * 0.37) + 0.05, 0.2 * np.sin(np.arange(n_dof) * 0.11)
+
+    def gpu_forms(self, space, alphas):
+        from nfempy_b200.weak_forms import SundusDualWeakForm, SundusDualWeakFormBCDirichlet
+
+        wf, bf = SundusDualWeakForm(space), SundusDualWeakFormBCDirichlet(space)
+        wf.functions, bf.functions = self.functions, self.bc_functions
+        mp = space.discrete_spaces["mp"]
+        return {
+            "volume": ["time_dependent_form", range(len(mp.elements)), wf, alphas, self.t],
+            "bc": ["time_dependent_bc_form", range(len(mp.bc_elements)), bf, alphas, self.t],
+        }
+
+    def run_gpu(self):
+        from nfempy_b200.assembly import GPUAssembler
+
+        space = self.space()
+        asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+        asm.form_to_input_list = self.gpu_forms(space, self.alphas(space.n_dof))
+        return asm.assemble()
+
+    def run_oracle(self):
+        space = self.ref_space()
+        mp = space.discrete_spaces["mp"]
+        forms = [
+            ("time_dependent_form", ref_forms.sundus_dual, self.functions, len(mp.element_ids)),
+            ("time_dependent_bc_form", ref_forms.sundus_dual_bc_dirichlet, self.bc_functions, len(mp.bc_element_ids)),
+        ]
+        return ref_assembly.assemble_time_dependent(space, forms, self.alphas(space.n_dof), self.t)

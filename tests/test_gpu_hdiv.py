@@ -57,3 +57,36 @@ def test_mixed_poisson_solves_linear_pressure_exactly():
     p = sol[us.n_dof :]
     assert abs(p.min() + 1.0) < 1e-10 and abs(p.max() - 3.0) < 1e-10  # vertex values of x + 2y - z on the cube
     assert np.abs(A @ sol + rhs).max() < 1e-11
+
+
+@pytest.mark.parametrize("dim,k", [(3, 1), (2, 1), (2, 2), (3, 2)])
+def test_sundus_time_dependent_forms(dim, k):
+    """Config 5: RT_k x RT_k x P x P implicit-Euler step with the nonlinear reaction, nonzero iterate and previous
+    time level, time-dependent loads and boundary data."""
+    from tests.parity_helpers import SundusCase
+
+    case = SundusCase(dim=dim, k=k, n=2 if dim == 3 else 3)
+    compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
+
+
+def test_sundus_reassembly_reuses_the_plan():
+    """Newton / time loop usage: zero the system, change the iterate, scatter again -- one plan, new values."""
+    from nfempy_b200.assembly import GPUAssembler
+    from tests.parity_helpers import SundusCase
+
+    case = SundusCase(dim=3, k=1, n=2)
+    space = case.space()
+    a_n, a = case.alphas(space.n_dof)
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+    asm.form_to_input_list = case.gpu_forms(space, (a_n, a))
+    first = [v.copy() for v in asm.assemble()]
+    asm.form_to_input_list = case.gpu_forms(space, (a_n + 0.1, a))
+    asm.jacobian.scale(0.0)
+    asm.residual[:] = 0.0
+    asm.scatter_forms()
+    assert len(asm._plans) == 1
+    second = asm.jacobian.getValuesCSR()
+    assert np.array_equal(first[1], second[1]) and not np.array_equal(first[2], second[2])
+    asm.form_to_input_list = case.gpu_forms(space, (a_n, a))
+    again = asm.assemble()
+    assert np.array_equal(again[2], first[2]) and np.array_equal(again[3], first[3])

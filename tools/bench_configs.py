@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""Secondary measurements for the BASELINE.json configs other than the headline one (which bench.py covers):
+
+  config 1  2-D Poisson, H1 p=1, 64 x 64 x 2 triangles            (launch/latency bound; time only)
+  config 2' 3-D elasticity p=2 through the TWO-STAGE path           (for comparison with the fused path)
+  config 3  3-D mixed Poisson, RT_k x P_{k-1}^disc, k = 1, 2, 3     (two-stage path; k = 3 on a smaller box because
+            the generic plan indexes local entries with 31 bits)
+
+One JSON line per case: elements/s with inputs resident in HBM (CUDA events, K steps after W warm-ups), nnz, local
+sizes, plan-build seconds, and the oracle's rate on a few cells of the same mesh (1 core) for scale.
+Run on the GPU box:  python tools/bench_configs.py > gpurun_out/configs.jsonl
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def time_steps(torch, fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def oracle_rate(case, n_cells):
+    """elements/s of the oracle on the first ``n_cells`` cells of the case's volume form (1 core)."""
+    from oracle import ref_assembly
+
+    space = case.ref_space()
+    kind, form, functions, total = case.ref_forms_fn(space)[0]
+    n_cells = min(n_cells, total)
+    n = space.n_dof
+    res, jac = np.zeros(n), ref_assembly.DokMatrix(n)
+    t0 = time.perf_counter()
+    for i in range(n_cells):
+        ref_assembly.scatter_form(space, form, functions, i, res, jac, np.zeros(n))
+    return n_cells / (time.perf_counter() - t0)
+
+
+def run_case(name, case, small_case, steps, warmup, allow_fused=True, oracle_cells=40):
+    import torch
+
+    from nfempy_b200 import _lib
+    from nfempy_b200.assembly import GPUAssembler
+
+    t0 = time.perf_counter()
+    space = case.space()
+    t_space = time.perf_counter() - t0
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof), allow_fused=allow_fused)
+    asm.form_to_input_list = case.gpu_forms(space, None)
+    t0 = time.perf_counter()
+    state = asm.prepare()
+    torch.cuda.synchronize()
+    t_prepare = time.perf_counter() - t0
+    plan = state[4]
+    rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=state[0].device)
+
+    def step():
+        asm.jacobian.is_zero = True
+        rhs.zero_()
+        asm.run(state, rhs)
+
+    l0 = _lib.launch_count()
+    ms = time_steps(torch, step, steps, warmup)
+    launches = (_lib.launch_count() - l0) / (steps + warmup)
+    first = next(iter(space.discrete_spaces.values()))
+    n_cells = len(first.elements)
+    n_loc = int(space.destination_table().shape[1])
+    line = {
+        "case": name, "cells": n_cells, "n_dof": int(space.n_dof), "nnz": int(plan.nnz), "n_loc": n_loc,
+        "path": "fused" if plan.fused_index is not None else "two-stage", "ms_per_step": ms,
+        "elements_per_s": n_cells / (ms * 1e-3), "nonzeros_per_s": plan.nnz / (ms * 1e-3),
+        "launches_per_step": launches, "plan_build_s": plan.build_seconds, "host_space_s": t_space,
+        "prepare_s": t_prepare, "steps": steps, "warmup": warmup, "dtype": "f64",
+        "local_bytes_per_cell_two_stage": 8 * (n_loc * n_loc + n_loc),
+    }
+    if small_case is not None:
+        line["oracle_elements_per_s_1core"] = oracle_rate(small_case, oracle_cells)
+    print(json.dumps(line), flush=True)
+    del asm, state, plan
+    torch.cuda.empty_cache()
+
+
+def run_sundus(mesh, n_steps):
+    import torch
+
+    from nfempy_b200.assembly import GPUAssembler
+    from tests.parity_helpers import SundusCase
+
+    case = SundusCase(dim=3, k=1, mesh=mesh)
+    space = case.space()
+    a_n, a = case.alphas(space.n_dof)
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+    asm.form_to_input_list = case.gpu_forms(space, (a_n, a))
+    t0 = time.perf_counter()
+    asm.scatter_forms()  # first assembly: callables, uploads, plan build, kernels, residual download
+    first = time.perf_counter() - t0
+    state = asm.prepare()
+    plan = state[4]
+    rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=state[0].device)
+
+    def step():
+        asm.jacobian.is_zero = True
+        rhs.zero_()
+        asm.run(state, rhs)
+
+    ms = time_steps(torch, step, n_steps, 3)
+    # a full API step of a time loop: new time -> loads re-evaluated on the host, kernels, residual downloaded
+    t0 = time.perf_counter()
+    for k in range(3):
+        asm.form_to_input_list = case.gpu_forms(space, (a_n, a))
+        asm.jacobian.scale(0.0)
+        asm.residual[:] = 0.0
+        asm.scatter_forms()
+    api = (time.perf_counter() - t0) / 3
+    n_cells = len(space.discrete_spaces["mp"].elements)
+    print(json.dumps({
+        "case": "config5: two-flux transport (Sundus) RT1 x RT1 x P0 x P0, implicit Euler + reaction, %d reassemblies "
+                "on one plan" % n_steps,
+        "cells": n_cells, "n_dof": int(space.n_dof), "nnz": int(plan.nnz), "n_loc": 10, "path": "two-stage",
+        "ms_per_reassembly_kernels": ms, "elements_per_s": n_cells / (ms * 1e-3), "plans_built": len(asm._plans),
+        "first_assembly_s": first, "api_step_s_with_host_callables": api, "plan_build_s": plan.build_seconds,
+        "steps": n_steps, "dtype": "f64",
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--quick", action="store_true", help="small meshes (smoke run)")
+    args = ap.parse_args()
+    from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
+    from tests.parity_helpers import elasticity_case, laplace_case, mixed_poisson_case
+
+    q = args.quick
+    # config 1
+    run_case("config1: 2D Poisson H1 p=1, 64x64x2 triangles + Dirichlet penalty",
+             laplace_case(dim=2, k=1, mesh=square_tri_mesh(16 if q else 64)), laplace_case(n=4, dim=2, k=1),
+             args.steps, args.warmup)
+    # config 2 through the two-stage path (same mesh as bench.py unless --quick)
+    mesh2 = box_tet_mesh(8 if q else 55, jitter=0.2)
+    run_case("config2 (two-stage path): 3D elasticity H1 p=2", elasticity_case(mesh=mesh2, with_bc=False),
+             elasticity_case(n=2, with_bc=False), args.steps, args.warmup, allow_fused=False)
+    run_case("config2 (fused path) + Dirichlet penalty on all six sides", elasticity_case(mesh=mesh2, with_bc=True),
+             None, args.steps, args.warmup)
+    del mesh2
+    # config 3
+    mesh3 = box_tet_mesh(8 if q else 69, jitter=0.2)
+    for k in (1, 2):
+        run_case("config3: 3D mixed Poisson RT%d x P%d disc + natural BC" % (k, k - 1),
+                 mixed_poisson_case(dim=3, k=k, mesh=mesh3), mixed_poisson_case(dim=3, k=k, n=2), args.steps,
+                 args.warmup)
+    # config 5: reassembly of the two-flux transport system, plan built once, 100 "time steps" of kernels
+    run_sundus(mesh3, 20 if q else 100)
+    del mesh3
+    mesh3s = box_tet_mesh(6 if q else 40, jitter=0.2)
+    run_case("config3: 3D mixed Poisson RT3 x P2 disc + natural BC (40^3 x 6 tets: 31-bit local-entry index)",
+             mixed_poisson_case(dim=3, k=3, mesh=mesh3s), mixed_poisson_case(dim=3, k=3, n=1), args.steps, args.warmup,
+             oracle_cells=6)
+
+
+if __name__ == "__main__":
+    main()
