@@ -71,47 +71,57 @@ def _oracle_cells(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(n_box, n_cells, workers):
+def cpu_baseline(n_box, n_cells, workers, pool=None):
     """elements/s of the oracle port over ``workers`` processes, each assembling ``n_cells / workers`` tets."""
-    import multiprocessing as mp
-
     per = max(1, n_cells // workers)
     jobs = [(n_box, w * per, (w + 1) * per) for w in range(workers)]
     t0 = time.perf_counter()
-    if workers == 1:
-        _oracle_cells(jobs[0])
+    if workers == 1 or pool is None:
+        for job in jobs:
+            _oracle_cells(job)
     else:
-        with mp.get_context("spawn").Pool(workers) as pool:
-            pool.map(_oracle_cells, jobs)
+        pool.map(_oracle_cells, jobs)
     wall = time.perf_counter() - t0
     return per * workers / wall, per * workers, wall
 
 
+WORKLOAD = "3D Cauchy linear elasticity, vector H1 p=2, %d tets per GPU (Kuhn box n=%d, jittered), lambda=mu=1, tabulated load, CSR values + rhs"
+
+
 def run_reference(args):
+    """The reference's algorithm on the host cores: oracle port (cell-by-cell numpy restatement + dict-of-keys
+    scatter), one worker process per core, each step a bounded sample of the same workload."""
+    import multiprocessing as mp
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = max(cores, (args.cpu_cells // cores) * cores)
-    for _ in range(min(args.warmup, 1)):
-        cpu_baseline(min(args.n, 8), cores, cores)
-    times = []
-    for _ in range(args.steps):
-        v, cells, wall = cpu_baseline(min(args.n, 8), per_step, cores)
-        times.append(wall)
+    per_step = max(cores, (max(args.cpu_cells, 60 * cores) // cores) * cores)
+    n_box = min(args.n, 12)
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[var] = "1"  # one BLAS thread per worker, like the reference's CI (python-package.yml:17-20)
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):  # imports + first touches inside the workers
+            cpu_baseline(n_box, cores * 4, cores, pool)
+        times = []
+        for _ in range(args.steps):
+            v, cells, wall = cpu_baseline(n_box, per_step, cores, pool)
+            times.append(wall)
     total = sum(times)
     value = per_step * args.steps / total
-    sample = "%d tets per step (first tets of the jittered Kuhn box), oracle port of the reference algorithm" % per_step
+    n_full = 6 * args.n**3
+    sample = ("%d tets per step = the first tets of the same jittered Kuhn box, split over %d worker processes; "
+              "oracle port of the reference algorithm (the real reference needs basix/auto_diff/petsc4py, absent here)"
+              % (per_step, cores))
     line = {
         "impl": "reference", "metric": "elements/s assembled (3D elasticity p=2)", "value": value, "unit": "elements/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D Cauchy elasticity, vector H1 p=2, Kuhn-tet unit cube (bounded CPU sample)",
-                   "cells_per_step": per_step},
+        "config": {"workload": WORKLOAD % (n_full, args.n), "cells_per_gpu": n_full, "cells_timed_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "the true reference (basix + auto_diff + PETSc) cannot be installed here; this times oracle/ on host cores",
     }
     print(json.dumps(line))
 
@@ -291,8 +301,13 @@ def run_graft(args):
     b_step = b_kernel + 8.0 * plan.n_dof / n_cells + 27 * 3 * 8.0  # + rhs rows + tabulated load
     kernel_ms = k_ms.value / max(k_n.value, 1)
     achieved = b_kernel * n_cells / (kernel_ms * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
+    tpath = os.path.join(ROOT, "profiles", "r01_fused_h1_traffic.json")
+    if os.path.exists(tpath) and args.n == 55 and world == 1:
+        traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "algorithmic_bytes_per_launch": b_kernel * n_cells,
         "kernel": "fused_h1_kernel<3,0>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_tet": b_kernel,
         "peak_source": peak_src, "step_frac": b_step * n_cells / (ms_step * 1e-3) / 1e9 / peak,
         "step_algorithmic_bytes_per_tet": b_step,
@@ -300,12 +315,13 @@ def run_graft(args):
 
     # ---- end to end through the host-buffer API: H2D of every input, kernels, D2H of CSR values + rhs
     e2e = None
-    if not args.no_e2e and world == 1:
-        e2e = run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, rhs_dev)
+    if not args.no_e2e:
+        e2e = run_e2e(args, torch, dist, world, device, asm, state, form, n_cells,
+                      (lambda: sharded.rhs) if sharded is not None else (lambda: rhs_dev), step)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cells, wall = cpu_baseline(min(args.n, 8), args.cpu_cells, 1)
+        v, cells, wall = cpu_baseline(min(args.n, 12), args.cpu_cells, 1)
         cpu = {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
                "sample": "%d tets of the same jittered Kuhn box, oracle port (cell-by-cell numpy restatement of the "
                          "reference, dict-of-keys scatter), %.1f s" % (cells, wall)}
@@ -315,9 +331,8 @@ def run_graft(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "3D Cauchy linear elasticity, vector H1 p=2, %d tets per GPU (Kuhn box n=%d, jittered), "
-                            "lambda=mu=1, tabulated load, CSR values + rhs%s" % (
-                                n_cells, args.n, "" if world == 1 else "; x-slab cell partition, NCCL interface-row reduce"),
+                "workload": WORKLOAD % (n_cells, args.n) + (
+                    "" if world == 1 else "; x-slab cell partition, NCCL interface-row reduce"),
                 "cells_per_gpu": n_cells, "n_dof_per_gpu": plan.n_dof, "nnz_per_gpu": nnz,
                 "nonzeros_per_s": nnz * world / (ms_step * 1e-3),
                 "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % ((b_step * n_cells + 6 * 100 * n_cells) / 1e9),
@@ -331,7 +346,7 @@ def run_graft(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, rhs_dev):
+def run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, asm_rhs, assemble_step):
     """Same step, host buffers in and out: pinned coords / connectivity / coefficient / load arrays are copied to
     the device every step and the CSR values + rhs are copied back."""
     from nfempy_b200 import _lib
@@ -354,11 +369,9 @@ def run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, rhs_dev
         data.f.copy_(host_in["f"], non_blocking=True)
         data.coefs["lambda"][0].copy_(host_in["lambda"], non_blocking=True)
         data.coefs["mu"][0].copy_(host_in["mu"], non_blocking=True)
-        asm.jacobian.is_zero = True
-        rhs_dev.zero_()
-        asm.run(state, rhs_dev)
+        assemble_step()  # same step as the device-resident measurement (incl. the NCCL exchange at N > 1)
         host_vals.copy_(asm.jacobian.values_dev, non_blocking=True)
-        host_rhs.copy_(rhs_dev, non_blocking=True)
+        host_rhs.copy_(asm_rhs(), non_blocking=True)
 
     steps = max(3, min(args.steps, 5))
     step()

@@ -371,62 +371,53 @@ extern "C" int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp,
 
 // ------------------------------------------------------------------------------------------------
 // Load vector only (fused path): re[cell][a*nc + i] = sign * sum_q w_q det phi_a(q) f[cell][q][i].
-// One warp per cell: the cell's f block (n_q * n_comp contiguous doubles) is read once, coalesced, into shared
-// memory; lane (a, i) contracts it with its own column of the premultiplied table w_q phi_a(q), which it keeps in
-// registers for the whole kernel when the rule size NQ is a compile-time constant.  HBM-bound on f.
-template <int DIM, int NQ>
-__global__ void __launch_bounds__(128, 12)
-    local_h1_load_kernel(int n_phi, int n_q_rt, int n_comp, const double *__restrict__ tab0,
+// A CTA takes tiles of TILE consecutive cells: their f blocks are one contiguous span of TILE * n_q * n_comp doubles,
+// copied to shared memory by all threads at once (many loads in flight -- the per-warp version was latency bound,
+// profiles/r01_load_kernel_ncu_summary.txt); thread (cell, a) then contracts its cell's block with column a of the
+// premultiplied table w_q phi_a(q) for all components and writes n_comp consecutive outputs.  HBM-bound on f.
+template <int DIM>
+__global__ void __launch_bounds__(1024, 1)
+    local_h1_load_kernel(int n_phi, int n_q, int n_comp, int tile, const double *__restrict__ tab0,
                          const double *__restrict__ weights, const double *__restrict__ coords,
                          const int32_t *__restrict__ cell_nodes, int64_t n_cells,
                          const double *__restrict__ f, double sign, double *__restrict__ re) {
     extern __shared__ double smem[];
-    const int n_q = NQ > 0 ? NQ : n_q_rt;
-    double *s_wt = smem;                       // [n_q][n_phi]  w_q phi_a(q)   (runtime-NQ path only)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *s_wt = smem;                 // [n_q][n_phi]  w_q phi_a(q)
+    double *s_f = s_wt + n_q * n_phi;    // [tile][n_q][n_comp]
     const int fn = n_q * n_comp, n_loc = n_phi * n_comp;
-    double *s_f = s_wt + n_q * n_phi + warp * 2 * fn;  // [2][n_q][n_comp] of the warp's current two cells
     for (int i = threadIdx.x; i < n_q * n_phi; i += blockDim.x) s_wt[i] = weights[i / n_phi] * tab0[i];
-    __syncthreads();
-    constexpr int NR = NQ > 0 ? NQ : 1;
-    for (int ra0 = 0; ra0 < n_loc; ra0 += 32) {  // one pass when n_loc <= 32
-        const int ra = ra0 + lane;
-        const bool active = ra < n_loc;
-        const int a = active ? ra / n_comp : 0, i = active ? ra - a * n_comp : 0;
-        double wt[NR];
-        if constexpr (NQ > 0) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) wt[q] = s_wt[q * n_phi + a];
+    const int lc = threadIdx.x / n_phi, a = threadIdx.x - lc * n_phi;  // worker = (local cell, basis function)
+    const int64_t n_tiles = (n_cells + tile - 1) / tile;
+    for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+        const int64_t c0 = tl * tile;
+        const int nc_here = (int)((n_cells - c0) < tile ? (n_cells - c0) : tile);
+        __syncthreads();  // previous tile's readers are done (also orders the s_wt fill on the first trip)
+        if (f) {
+            const double *src = f + c0 * fn;
+            for (int t = threadIdx.x; t < nc_here * fn; t += blockDim.x) s_f[t] = __ldg(src + t);
         }
-        // two cells per trip: twice the loads in flight per warp (the kernel is latency bound otherwise)
-        const int64_t stride = (int64_t)gridDim.x * 4;
-        for (int64_t cell = (int64_t)blockIdx.x * 4 + warp; cell < n_cells; cell += 2 * stride) {
-            const int64_t cell2 = cell + stride;
-            const bool two = cell2 < n_cells;
-            double X[DIM + 1][3], X2[DIM + 1][3];
-            load_cell_coords<DIM>(coords, cell_nodes, cell, X);
-            load_cell_coords<DIM>(coords, cell_nodes, two ? cell2 : cell, X2);
-            __syncwarp();
+        double det = 0.0;
+        if (lc < nc_here) {
+            double X[DIM + 1][3];
+            load_cell_coords<DIM>(coords, cell_nodes, c0 + lc, X);
+            det = compute_det<DIM>(X);
+        }
+        __syncthreads();
+        if (lc < nc_here) {
+            double acc[3] = {0.0, 0.0, 0.0};
             if (f) {
-                for (int t = lane; t < fn; t += 32) {
-                    s_f[t] = f[cell * fn + t];
-                    s_f[fn + t] = two ? f[cell2 * fn + t] : 0.0;
-                }
-            }
-            const double det = compute_det<DIM>(X), det2 = compute_det<DIM>(X2);
-            __syncwarp();
-            double acc = 0.0, acc2 = 0.0;
-            if (f && active) {
+                const double *fc = s_f + lc * fn;
                 for (int q = 0; q < n_q; ++q) {
                     const double wv = s_wt[q * n_phi + a];
-                    acc += wv * s_f[q * n_comp + i];
-                    acc2 += wv * s_f[fn + q * n_comp + i];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (i < n_comp) acc[i] += wv * fc[q * n_comp + i];
                 }
             }
-            if (active) {
-                re[cell * n_loc + ra] = sign * (acc * det);
-                if (two) re[cell2 * n_loc + ra] = sign * (acc2 * det2);
-            }
+            double *dst = re + (c0 + lc) * n_loc + a * n_comp;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (i < n_comp) dst[i] = sign * (acc[i] * det);
         }
     }
 }
@@ -435,17 +426,17 @@ template <int DIM>
 static int launch_h1_load(int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,
                           const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *f, double sign,
                           double *re, cudaStream_t s) {
-    size_t smem = sizeof(double) * ((size_t)n_q * n_phi + 8 * (size_t)n_q * n_comp);
-    int64_t ctas = (n_cells + 3) / 4;
-    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
-#define NFA_LOAD_CASE(NQV)                                                                                          \
-    local_h1_load_kernel<DIM, NQV><<<grid, 128, smem, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes,  \
-                                                           n_cells, f, sign, re)
-    // The register-resident-weights instantiations (NQ > 0) cost 126 registers/thread and left the kernel latency
-    // bound at 25 % occupancy (profiles/r01_load_kernel_ncu_summary.txt); the shared-memory table path keeps 12 CTAs
-    // per SM resident instead.
-    NFA_LOAD_CASE(0);
-#undef NFA_LOAD_CASE
+    if (n_comp > 3) return fail("nfa_local_h1_load: at most 3 components");
+    int tile = 1024 / n_phi < 32 ? 1024 / n_phi : 32;
+    if (tile < 1) return fail("nfa_local_h1_load: element too large");
+    int threads = tile * n_phi;
+    size_t smem = sizeof(double) * ((size_t)n_q * n_phi + (size_t)tile * n_q * n_comp);
+    if (smem > 200 * 1024) return fail("nfa_local_h1_load: element too large for the shared-memory tile");
+    auto kern = local_h1_load_kernel<DIM>;
+    NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t tiles = (n_cells + tile - 1) / tile;
+    int grid = (int)(tiles < 148 * 8 ? tiles : 148 * 8);
+    kern<<<grid, threads, smem, s>>>(n_phi, n_q, n_comp, tile, tab0, weights, coords, cell_nodes, n_cells, f, sign, re);
     NFA_LAUNCH_CHECK();
     return 0;
 }
