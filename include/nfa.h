@@ -79,7 +79,8 @@ int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *d_t
  * beta = 1, r_sign = +1): LEPrimalWeakFormBCNeumann R/.../le_primal_weak_form.py:179-221.
  * d_comp_scale [n, n_comp] or NULL scales the (c, c) matrix block of each facet -- n_c^2 for the normal-only penalty
  * of LEPrimalWeakFormBCNormalDirichlet, R/.../le_primal_weak_form.py:224-286 (whose load is g_c = (u_D . n) n_c).
- * facet_dim = dim-1 (0 = point facets of 1-D cells). */
+ * facet_dim = dim-1 (0 = point facets of 1-D cells); facet_dim = dim makes it the Lagrange mass matrix and load of
+ * L2ProjectorWeakForm on volume cells (R/src/weak_forms/l2_projector_weak_form.py:40-68). */
 int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp, const double *d_tab0,
                        const double *d_weights, const double *d_coords, const int32_t *d_facet_nodes,
                        int64_t n_facets, const double *d_g, const double *d_comp_scale, double beta, double r_sign,
@@ -92,7 +93,9 @@ int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp, const doub
  * cases int8 [n_cells, dim+1]: which matrix each facet of each cell takes (0 = identity).
  * nfa_local_hdiv_l2: LaplaceDualWeakForm.evaluate_form, R/src/weak_forms/laplace_dual_weak_form.py:10-87:
  *   J = [[int kappa^-1 psi_j.psi_i, -int w_l div psi_i], [int div psi_j w_k, 0]], r = [0, -int f w]  (the reference
- *   zeroes alpha, :50).  kappa stride-addressed like the H1 coefficients; f [n, n_q] or NULL.
+ *   zeroes alpha, :50).  kappa stride-addressed like the H1 coefficients; f [n, n_q] or NULL.  With n_p = 0, kappa = 1
+ *   and the vector load f_u [n, n_q, dim] (r_u = -int f_u . psi) this is the H(div) block of L2ProjectorWeakForm,
+ *   R/src/weak_forms/l2_projector_weak_form.py:44-74.
  * nfa_local_hdiv_facet: LaplaceDualWeakFormBCDirichlet, R/...:90-154: r_k = int_F p_D (psi_k . n) over the facet dofs
  *   of the first neighbour cell; trace_tab [n_tabs, n_q, nfd, dim] = reference values of the facet's dofs at the facet
  *   quadrature points mapped into the neighbour (R/src/basis/parametric_transformation.py:58-98), one table per
@@ -100,8 +103,8 @@ int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp, const doub
 int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, const double *d_u_val, const double *d_u_div,
                       const double *d_p_val, const double *d_weights, const double *d_Tcases, const int8_t *d_cases,
                       const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_kappa,
-                      int64_t kappa_stride_cell, int64_t kappa_stride_q, const double *d_f, double *d_Ke, double *d_re,
-                      nfa_stream stream);
+                      int64_t kappa_stride_cell, int64_t kappa_stride_q, const double *d_f, const double *d_f_u,
+                      double *d_Ke, double *d_re, nfa_stream stream);
 int nfa_local_hdiv_facet(int dim, int nfd, int n_q, const double *d_trace_tab, const int32_t *d_tidx,
                          const double *d_weights, const double *d_Tcases, const int8_t *d_cases, const double *d_coords,
                          const int32_t *d_facet_nodes, const int32_t *d_neigh_nodes, const double *d_normals,

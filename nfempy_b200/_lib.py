@@ -31,7 +31,7 @@ SIGNATURES = {
     "nfa_local_h1_facet": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _d, _d, _i, _vp, _vp, _vp]),
     "nfa_local_hdiv_l2": (
         _i,
-        [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp],
+        [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
     ),
     "nfa_local_hdiv_facet": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nfa_local_sundus": (

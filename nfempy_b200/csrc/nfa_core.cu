@@ -354,7 +354,10 @@ extern "C" int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp,
     cudaStream_t s = (cudaStream_t)stream;
     int64_t ctas = (n_facets + 3) / 4;
     int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
-    if (facet_dim == 2)
+    if (facet_dim == 3)  // a volume cell: the same kernel is the Lagrange mass matrix / load of L2ProjectorWeakForm
+        local_h1_facet_kernel<3><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
+                                                      n_facets, gval, comp_scale, beta, r_sign, with_matrix, Ke, re);
+    else if (facet_dim == 2)
         local_h1_facet_kernel<2><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
                                                       n_facets, gval, comp_scale, beta, r_sign, with_matrix, Ke, re);
     else if (facet_dim == 1)
@@ -364,7 +367,7 @@ extern "C" int nfa_local_h1_facet(int facet_dim, int n_phi, int n_q, int n_comp,
         local_h1_facet_kernel<0><<<grid, 128, 0, s>>>(n_phi, n_q, n_comp, tab0, weights, coords, facet_nodes,
                                                       n_facets, gval, comp_scale, beta, r_sign, with_matrix, Ke, re);
     else
-        return fail("nfa_local_h1_facet: facet_dim must be 0, 1 or 2");
+        return fail("nfa_local_h1_facet: facet_dim must be 0..3");
     NFA_LAUNCH_CHECK();
     return 0;
 }

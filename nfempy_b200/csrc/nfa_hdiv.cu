@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(128)
                          const double *__restrict__ weights, const double *__restrict__ Tcases,
                          const int8_t *__restrict__ cases, const double *__restrict__ coords,
                          const int32_t *__restrict__ cell_nodes, int64_t n_cells, CoefH kappa,
-                         const double *__restrict__ f, double *__restrict__ Ke, double *__restrict__ re) {
+                         const double *__restrict__ f, const double *__restrict__ f_u, double *__restrict__ Ke,
+                         double *__restrict__ re) {
     constexpr int NF = DIM + 1;
     extern __shared__ double smem[];
     double *s_psi = smem;                         // [n_q][n_u][DIM]
@@ -103,6 +104,14 @@ __global__ void __launch_bounds__(128)
             double acc = 0.0;
             if (ra >= n_u && f)
                 for (int q = 0; q < n_q; ++q) acc -= s_wd[q] * p_val[q * n_p + (ra - n_u)] * f[cell * n_q + q];
+            if (ra < n_u && f_u)  // vector load -int f . psi (L2ProjectorWeakForm on an H(div) field)
+                for (int q = 0; q < n_q; ++q) {
+                    const double *ps = s_psi + (q * n_u + ra) * DIM;
+                    double dot = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) dot += ps[c] * f_u[(cell * n_q + q) * DIM + c];
+                    acc -= s_wd[q] * dot;
+                }
             re[cell * n_loc + ra] = acc;
         }
     }
@@ -330,7 +339,8 @@ extern "C" int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, co
                                  const double *u_div, const double *p_val, const double *weights,
                                  const double *Tcases, const int8_t *cases, const double *coords,
                                  const int32_t *cell_nodes, int64_t n_cells, const double *kappa, int64_t ksc,
-                                 int64_t ksq, const double *f, double *Ke, double *re, nfa_stream stream) {
+                                 int64_t ksq, const double *f, const double *f_u, double *Ke, double *re,
+                                 nfa_stream stream) {
     if (n_cells == 0) return 0;
     if ((dim + 1) * nfd > n_u) return fail("nfa_local_hdiv_l2: facet dofs exceed the basis size");
     cudaStream_t s = (cudaStream_t)stream;
@@ -342,12 +352,12 @@ extern "C" int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, co
         auto kern = local_hdiv_l2_kernel<3>;
         NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 128, smem, s>>>(n_u, n_p, n_q, nfd, u_val, u_div, p_val, weights, Tcases, cases, coords,
-                                     cell_nodes, n_cells, kp, f, Ke, re);
+                                     cell_nodes, n_cells, kp, f, f_u, Ke, re);
     } else if (dim == 2) {
         auto kern = local_hdiv_l2_kernel<2>;
         NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, 128, smem, s>>>(n_u, n_p, n_q, nfd, u_val, u_div, p_val, weights, Tcases, cases, coords,
-                                     cell_nodes, n_cells, kp, f, Ke, re);
+                                     cell_nodes, n_cells, kp, f, f_u, Ke, re);
     } else
         return fail("nfa_local_hdiv_l2: dim must be 2 or 3");
     NFA_LAUNCH_CHECK();

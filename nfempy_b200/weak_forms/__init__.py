@@ -4,3 +4,4 @@ from .le_primal_weak_form import (LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet,
 from .laplace_primal_weak_form import LaplacePrimalWeakForm, LaplacePrimalWeakFormBCDirichlet
 from .laplace_dual_weak_form import LaplaceDualWeakForm, LaplaceDualWeakFormBCDirichlet
 from .sundus_weak_form import SundusDualWeakForm, SundusDualWeakFormBCDirichlet
+from .l2_projector_weak_form import L2ProjectorWeakForm

@@ -94,7 +94,7 @@ class LaplaceDualWeakForm(BatchedWeakForm):
             "nfa_local_hdiv_l2", data.dim, data.n_u, data.n_p, data.n_q, data.nfd, _lib.ptr(data.u_val),
             _lib.ptr(data.u_div), _lib.ptr(data.p_val), _lib.ptr(data.w), _lib.ptr(data.tcases), _lib.ptr(data.cases),
             _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes), data.n_items, _lib.ptr(k[0]), k[1], k[2],
-            _lib.ptr(data.f), _lib.ptr(Ke), _lib.ptr(re), _lib.stream_ptr(),
+            _lib.ptr(data.f), None, _lib.ptr(Ke), _lib.ptr(re), _lib.stream_ptr(),
         )
 
     def evaluate_form(self, element_index, alpha):

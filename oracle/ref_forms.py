@@ -448,3 +448,48 @@ def sundus_dual_bc_dirichlet(space, functions, iel, alpha, t):
         out.append(res)
     r_el = np.concatenate(out)
     return r_el, np.zeros((len(r_el), len(r_el)))
+
+
+def l2_projector(space, functions, iel, alpha):
+    """L2ProjectorWeakForm.evaluate_form, R/src/weak_forms/l2_projector_weak_form.py:8-93."""
+    r_els, j_els = [], []
+    for name, sp in space.discrete_spaces.items():
+        el = RefElement(sp, sp.element_ids[iel])
+        dim = el.cell.dimension
+        points, weights = space.quadrature[dim]
+        x, jac, det_jac, inv_jac = el.evaluate_mapping(points)
+        tab = el.evaluate_basis(points, jac, det_jac, inv_jac)
+        nc = sp.n_comp
+        n_phi = tab.shape[2]
+        n_dof = n_phi * nc
+        j_el, r_el = np.zeros((n_dof, n_dof)), np.zeros(n_dof)
+        f_val = np.asarray(functions[name](x[:, 0], x[:, 1], x[:, 2]))
+        lagrange = sp.family == "Lagrange"
+        if lagrange:
+            phi_s_star = det_jac * weights * tab[0, :, :, 0].T
+            for c in range(nc):
+                r_el[c : c + n_dof : nc] -= (phi_s_star @ f_val[c].T).ravel()
+        else:
+            for c in range(nc):
+                for i, omega in enumerate(weights):
+                    phi_s = det_jac[i] * weights[i] * tab[0, i, :, 0:dim].T
+                    r_el[c : c + n_dof : nc] -= (phi_s.T @ f_val[c, 0:dim, i]).ravel()
+        for c in range(nc):
+            for i, omega in enumerate(weights):
+                if lagrange:
+                    phi = tab[0, i, :, 0]
+                    j_el[c : c + n_dof : nc, c : c + n_dof : nc] += det_jac[i] * omega * np.outer(phi, phi)
+                else:
+                    for d in range(dim):
+                        j_el[c : c + n_dof : nc, c : c + n_dof : nc] += (
+                            det_jac[i] * omega * np.outer(tab[0, i, :, d], tab[0, i, :, d]))
+        r_els.append(r_el)
+        j_els.append(j_el)
+    sizes = [len(r) for r in r_els]
+    off = np.add.accumulate([0] + sizes)
+    n = off[-1]
+    j_all, r_all = np.zeros((n, n)), np.zeros(n)
+    for k in range(len(sizes)):
+        r_all[off[k] : off[k + 1]] += r_els[k]
+        j_all[off[k] : off[k + 1], off[k] : off[k + 1]] += j_els[k]
+    return r_all, j_all
