@@ -110,6 +110,22 @@ int nfa_local_hdiv_facet(int dim, int nfd, int n_q, const double *d_trace_tab, c
                          const int32_t *d_facet_nodes, const int32_t *d_neigh_nodes, const double *d_normals,
                          const double *d_pd, int64_t n_facets, double *d_re, nfa_stream stream);
 
+/* Generalised H(div) x L2 block form for the Arbogast-Taicher family: DegenerateEllipticWeakForm
+ * (R/src/weak_forms/degenerate_elliptic_weak_form.py:41-144), UnscaledEllipticWeakForm
+ * (R/src/weak_forms/unscaled_elliptic_weak_form.py:41-153) and ScaledToPhysicalL2Projection
+ * (R/src/weak_forms/scaled_to_physical_l2_projection.py:27-105).  With D_i = c_d div psi_i + g . psi_i:
+ *   J = [[int c_uu psi_j.psi_i, -int w_l D_i], [int D_j w_k, int c_pp w_l w_k]],
+ *   r = J alpha - [int s_u (beta_u.psi).psi_i ; int s_p (beta_p w) w_k] - [0 ; int load_p w_k].
+ * Per-point arrays [n, n_q] (g: [n, n_q, dim]); c_d NULL = 1, g / c_pp / load_p / s_u / s_p NULL = absent;
+ * alpha, beta: global vectors gathered through d_dest [n, n_u + n_p] (NULL = 0). */
+int nfa_local_hdiv_l2_general(int dim, int n_u, int n_p, int n_q, int nfd, const double *d_u_val,
+                              const double *d_u_div, const double *d_p_val, const double *d_weights,
+                              const double *d_Tcases, const int8_t *d_cases, const double *d_coords,
+                              const int32_t *d_cell_nodes, int64_t n_cells, const double *d_c_uu, const double *d_c_d,
+                              const double *d_g, const double *d_c_pp, const double *d_load_p, const double *d_alpha,
+                              const double *d_beta, const int32_t *d_dest, const double *d_s_u, const double *d_s_p,
+                              double *d_Ke, double *d_re, nfa_stream stream);
+
 /* Two-flux mixed transport with reaction, fields [mp | mc | p | c] (config 5): SundusDualWeakForm.evaluate_form,
  * R/examples/parabolic_diffusive_problem/SundusWeakForm.py:11-177.  mp, mc share the H(div) tables, p, c the L2 table.
  * Residual and tangent at the current iterate d_alpha (global vector, gathered through d_dest [n, 2 n_u + 2 n_p]) with

@@ -34,6 +34,10 @@ SIGNATURES = {
         [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
     ),
     "nfa_local_hdiv_facet": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nfa_local_hdiv_l2_general": (
+        _i,
+        [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64] + [_vp] * 13,
+    ),
     "nfa_local_sundus": (
         _i,
         [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,

@@ -117,6 +117,151 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Generalised H(div) x L2 block form covering the Arbogast-Taicher family of the reference
+// (R/src/weak_forms/degenerate_elliptic_weak_form.py:41-144, unscaled_elliptic_weak_form.py:41-153,
+//  scaled_to_physical_l2_projection.py:27-105).  With D_i = c_d div psi_i + g . psi_i (per point):
+//   J = [[ int c_uu psi_j.psi_i , -int w_l D_i ], [ int D_j w_k , int c_pp w_l w_k ]],
+//   r = J alpha - [ int s_u (beta_u.psi) . psi_i ; int s_p (beta_p w) w_k ] - [0 ; int load w_k].
+// All coefficients are host-evaluated per quadrature point (the reference branches on isclose(porosity, 0) per
+// point; those branches are applied when the arrays are built).
+template <int DIM>
+__global__ void __launch_bounds__(128)
+    local_hdiv_general_kernel(int n_u, int n_p, int n_q, int nfd, const double *__restrict__ u_val,
+                              const double *__restrict__ u_div, const double *__restrict__ p_val,
+                              const double *__restrict__ weights, const double *__restrict__ Tcases,
+                              const int8_t *__restrict__ cases, const double *__restrict__ coords,
+                              const int32_t *__restrict__ cell_nodes, int64_t n_cells,
+                              const double *__restrict__ c_uu, const double *__restrict__ c_d,
+                              const double *__restrict__ gvec, const double *__restrict__ c_pp,
+                              const double *__restrict__ load_p, const double *__restrict__ alpha,
+                              const double *__restrict__ beta, const int32_t *__restrict__ dest,
+                              const double *__restrict__ s_u, const double *__restrict__ s_p,
+                              double *__restrict__ Ke, double *__restrict__ re) {
+    constexpr int NF = DIM + 1;
+    extern __shared__ double smem[];
+    const int n_loc = n_u + n_p;
+    double *s_psi = smem;                         // [n_q][n_u][DIM]
+    double *s_D = s_psi + n_q * n_u * DIM;        // [n_q][n_u]   c_d div psi + g . psi
+    double *s_wd = s_D + n_q * n_u;               // [n_q] w det
+    double *s_T = s_wd + n_q;                     // [NF][nfd][nfd]
+    double *s_a = s_T + NF * nfd * nfd;           // [n_loc] alpha (local)
+    double *s_b = s_a + n_loc;                    // [n_loc] beta (local)
+    double *s_bq = s_b + n_loc;                   // [n_q][DIM + 1] scaled beta field: s_u (beta_u.psi), s_p (beta_p w)
+    const int n_fdofs = NF * nfd;
+    for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        double X[DIM + 1][3];
+        load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+        Geom<DIM> g;
+        compute_geom<DIM>(X, g);
+        const double idet = 1.0 / g.det;
+        __syncthreads();
+        for (int i = threadIdx.x; i < NF * nfd * nfd; i += blockDim.x) {
+            int fc = i / (nfd * nfd);
+            s_T[i] = Tcases[(int)cases[cell * NF + fc] * nfd * nfd + (i - fc * nfd * nfd)];
+        }
+        for (int q = threadIdx.x; q < n_q; q += blockDim.x) s_wd[q] = weights[q] * g.det;
+        for (int i = threadIdx.x; i < n_loc; i += blockDim.x) {
+            int d = dest ? dest[cell * n_loc + i] : 0;
+            s_a[i] = alpha ? alpha[d] : 0.0;
+            s_b[i] = beta ? beta[d] : 0.0;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < n_q * n_u; idx += blockDim.x) {
+            int q = idx / n_u, j = idx - q * n_u;
+            double vh[DIM], dh;
+            if (j < n_fdofs) {
+                int fc = j / nfd, a = j - fc * nfd;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) vh[k] = 0.0;
+                dh = 0.0;
+                for (int b = 0; b < nfd; ++b) {
+                    double t = s_T[(fc * nfd + a) * nfd + b];
+                    const double *src = u_val + ((int64_t)q * n_u + fc * nfd + b) * DIM;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) vh[k] += t * src[k];
+                    dh += t * u_div[q * n_u + fc * nfd + b];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) vh[k] = u_val[((int64_t)q * n_u + j) * DIM + k];
+                dh = u_div[q * n_u + j];
+            }
+            double D = (c_d ? c_d[cell * n_q + q] : 1.0) * (dh * idet);
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) v += g.J[c][k] * vh[k];
+                v *= idet;
+                s_psi[(q * n_u + j) * DIM + c] = v;
+                if (gvec) D += gvec[(cell * n_q + q) * DIM + c] * v;
+            }
+            s_D[q * n_u + j] = D;
+        }
+        __syncthreads();
+        if (beta) {
+            for (int q = threadIdx.x; q < n_q; q += blockDim.x) {
+                double bu[DIM], bp = 0.0;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) bu[c] = 0.0;
+                for (int j = 0; j < n_u; ++j)
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) bu[c] += s_b[j] * s_psi[(q * n_u + j) * DIM + c];
+                for (int k = 0; k < n_p; ++k) bp += s_b[n_u + k] * p_val[q * n_p + k];
+                double su = s_u ? s_u[cell * n_q + q] : 1.0, sp = s_p ? s_p[cell * n_q + q] : 1.0;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) s_bq[q * (DIM + 1) + c] = su * bu[c];
+                s_bq[q * (DIM + 1) + DIM] = sp * bp;
+            }
+        }
+        __syncthreads();
+        double *K = Ke + cell * (int64_t)n_loc * n_loc;
+        for (int e = threadIdx.x; e < n_loc * n_loc; e += blockDim.x) {
+            int ra = e / n_loc, rb = e - ra * n_loc;
+            double acc = 0.0;
+            if (ra < n_u && rb < n_u) {
+                for (int q = 0; q < n_q; ++q) {
+                    const double *a = s_psi + (q * n_u + ra) * DIM, *b = s_psi + (q * n_u + rb) * DIM;
+                    double dot = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) dot += a[c] * b[c];
+                    acc += s_wd[q] * c_uu[cell * n_q + q] * dot;
+                }
+            } else if (ra < n_u) {
+                for (int q = 0; q < n_q; ++q) acc -= s_wd[q] * p_val[q * n_p + (rb - n_u)] * s_D[q * n_u + ra];
+            } else if (rb < n_u) {
+                for (int q = 0; q < n_q; ++q) acc += s_wd[q] * s_D[q * n_u + rb] * p_val[q * n_p + (ra - n_u)];
+            } else if (c_pp) {
+                for (int q = 0; q < n_q; ++q)
+                    acc += s_wd[q] * c_pp[cell * n_q + q] * p_val[q * n_p + (rb - n_u)] * p_val[q * n_p + (ra - n_u)];
+            }
+            K[e] = acc;
+        }
+        __syncthreads();  // K of this cell is complete in global memory for the row products below
+        for (int ra = threadIdx.x; ra < n_loc; ra += blockDim.x) {
+            double acc = 0.0;
+            if (alpha)
+                for (int rb = 0; rb < n_loc; ++rb) acc += K[ra * n_loc + rb] * s_a[rb];
+            for (int q = 0; q < n_q; ++q) {
+                if (ra < n_u) {
+                    if (beta) {
+                        const double *ps = s_psi + (q * n_u + ra) * DIM;
+                        double dot = 0.0;
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) dot += s_bq[q * (DIM + 1) + c] * ps[c];
+                        acc -= s_wd[q] * dot;
+                    }
+                } else {
+                    double w = p_val[q * n_p + (ra - n_u)];
+                    if (beta) acc -= s_wd[q] * s_bq[q * (DIM + 1) + DIM] * w;
+                    if (load_p) acc -= s_wd[q] * load_p[cell * n_q + q] * w;
+                }
+            }
+            re[cell * n_loc + ra] = acc;
+        }
+    }
+}
+
 // Natural boundary load: r_k = sum_q det_F w_q p_D(x_q) (psi_k(x_q) . n), psi = trace of the neighbour's basis.
 template <int DIM>
 __global__ void __launch_bounds__(128)
@@ -414,6 +559,39 @@ extern "C" int nfa_local_sundus(int dim, int n_u, int n_p, int n_q, int nfd, con
                                      n_cells, kp, dl, et, 1.0 / delta_t, f_f, f_r, alpha, alpha_prev, dest, Ke, re);
     } else
         return fail("nfa_local_sundus: dim must be 2 or 3");
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nfa_local_hdiv_l2_general(int dim, int n_u, int n_p, int n_q, int nfd, const double *u_val,
+                                         const double *u_div, const double *p_val, const double *weights,
+                                         const double *Tcases, const int8_t *cases, const double *coords,
+                                         const int32_t *cell_nodes, int64_t n_cells, const double *c_uu,
+                                         const double *c_d, const double *gvec, const double *c_pp,
+                                         const double *load_p, const double *alpha, const double *beta,
+                                         const int32_t *dest, const double *s_u, const double *s_p, double *Ke,
+                                         double *re, nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (!c_uu) return fail("nfa_local_hdiv_l2_general: c_uu is required");
+    if ((alpha || beta) && !dest) return fail("nfa_local_hdiv_l2_general: alpha/beta given without dest");
+    cudaStream_t s = (cudaStream_t)stream;
+    int n_loc = n_u + n_p;
+    size_t smem = sizeof(double) * ((size_t)n_q * n_u * (dim + 1) + n_q + (size_t)(dim + 1) * nfd * nfd + 2 * n_loc +
+                                    (size_t)n_q * (dim + 1));
+    if (smem > 200 * 1024) return fail("nfa_local_hdiv_l2_general: element too large for the shared-memory staging");
+    int grid = (int)(n_cells < 148 * 8 ? n_cells : 148 * 8);
+    if (dim == 3) {
+        auto kern = local_hdiv_general_kernel<3>;
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, s>>>(n_u, n_p, n_q, nfd, u_val, u_div, p_val, weights, Tcases, cases, coords, cell_nodes,
+                                     n_cells, c_uu, c_d, gvec, c_pp, load_p, alpha, beta, dest, s_u, s_p, Ke, re);
+    } else if (dim == 2) {
+        auto kern = local_hdiv_general_kernel<2>;
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, s>>>(n_u, n_p, n_q, nfd, u_val, u_div, p_val, weights, Tcases, cases, coords, cell_nodes,
+                                     n_cells, c_uu, c_d, gvec, c_pp, load_p, alpha, beta, dest, s_u, s_p, Ke, re);
+    } else
+        return fail("nfa_local_hdiv_l2_general: dim must be 2 or 3");
     NFA_LAUNCH_CHECK();
     return 0;
 }

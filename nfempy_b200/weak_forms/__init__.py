@@ -5,3 +5,6 @@ from .laplace_primal_weak_form import LaplacePrimalWeakForm, LaplacePrimalWeakFo
 from .laplace_dual_weak_form import LaplaceDualWeakForm, LaplaceDualWeakFormBCDirichlet
 from .sundus_weak_form import SundusDualWeakForm, SundusDualWeakFormBCDirichlet
 from .l2_projector_weak_form import L2ProjectorWeakForm
+from .degenerate_elliptic_weak_form import DegenerateEllipticWeakForm, DegenerateEllipticWeakFormBCDirichlet
+from .unscaled_elliptic_weak_form import UnscaledEllipticWeakForm, UnscaledEllipticWeakFormBCDirichlet
+from .scaled_to_physical_l2_projection import ScaledToPhysicalL2Projection

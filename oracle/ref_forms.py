@@ -493,3 +493,166 @@ def l2_projector(space, functions, iel, alpha):
         r_all[off[k] : off[k + 1]] += r_els[k]
         j_all[off[k] : off[k + 1], off[k] : off[k + 1]] += j_els[k]
     return r_all, j_all
+
+
+# ---- Arbogast-Taicher degenerate elliptic family ---------------------------------------------------------------
+def _mixed_setup(space, flux, scalar, iel):
+    v_space, q_space = space.discrete_spaces[flux], space.discrete_spaces[scalar]
+    el_v = RefElement(v_space, v_space.element_ids[iel])
+    el_q = RefElement(q_space, q_space.element_ids[iel])
+    dim = el_v.cell.dimension
+    points, weights = space.quadrature[dim]
+    x, jac, det_jac, inv_jac = el_v.evaluate_mapping(points)
+    v_tab = el_v.evaluate_basis(points, jac, det_jac, inv_jac)
+    q_tab = el_q.evaluate_basis(points, jac, det_jac, inv_jac)
+    return dim, weights, x, det_jac, v_tab, q_tab, v_tab.shape[2] * v_space.n_comp, q_tab.shape[2] * q_space.n_comp
+
+
+def degenerate_elliptic(space, functions, iel, alpha):
+    """DegenerateEllipticWeakForm.evaluate_form, R/src/weak_forms/degenerate_elliptic_weak_form.py:41-144."""
+    dim, weights, x, det_jac, v_tab, q_tab, n_v, n_q = _mixed_setup(space, "v", "q", iel)
+    n_dof = n_v + n_q
+    n_v_phi = v_tab.shape[2]
+    phi_star = functions["porosity"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    delta_star = functions["d_phi"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    grad_delta_star = np.asarray(functions["grad_d_phi"](x[:, 0], x[:, 1], x[:, 2]))
+    f_val = np.asarray(functions["rhs"](x[:, 0], x[:, 1], x[:, 2]))
+    phi_q_star = det_jac * weights * q_tab[0, :, :, 0].T
+
+    def residual(a, load):
+        a = a.reshape(1, -1)
+        el_form = np.zeros(n_dof)
+        if load:
+            el_form[n_v:n_dof] -= phi_q_star @ f_val[0].T
+        for i, omega in enumerate(weights):
+            phi, delta, grad_delta = phi_star[i], delta_star[i], grad_delta_star[:, i]
+            psi_h = v_tab[0, i, :, 0:dim]
+            w_h = q_tab[0, i, :, 0:dim]
+            v_h = a[:, 0:n_v] @ psi_h
+            q_h = a[:, n_v:n_dof] @ w_h
+            grad_psi_h = v_tab[1 : v_tab.shape[0] + 1, i, :, 0:dim]
+            div_psi_h = np.array([np.trace(grad_psi_h, axis1=0, axis2=2) / det_jac[i]])
+            gdp = np.array([[np.dot(grad_delta[0:dim], psi_h[j, 0:dim]) for j in range(n_v_phi)]])
+            if not np.isclose(phi, 0.0) and phi > 0.0:
+                div_phi_h_s = (delta * div_psi_h + gdp) / np.sqrt(phi)
+            else:
+                div_phi_h_s = 0.0 * (delta * div_psi_h + gdp)
+            div_delta_v_h = a[:, 0:n_v] @ div_phi_h_s.T
+            integrand = np.zeros((1, n_dof))
+            integrand[:, 0:n_v] = (v_h @ psi_h.T) - (q_h @ div_phi_h_s)
+            integrand[:, n_v:n_dof] = div_delta_v_h @ w_h.T + q_h @ w_h.T
+            el_form = el_form + det_jac[i] * omega * integrand.reshape((n_dof,))
+        return el_form
+
+    return _linearise(residual, alpha, n_dof)
+
+
+def unscaled_elliptic(space, functions, iel, alpha, phi_threshold=1.0e-16):
+    """UnscaledEllipticWeakForm.evaluate_form, R/src/weak_forms/unscaled_elliptic_weak_form.py:59-153."""
+    dim, weights, x, det_jac, u_tab, p_tab, n_u, n_p = _mixed_setup(space, "u", "p", iel)
+    n_dof = n_u + n_p
+    phi_star = functions["porosity"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    with np.errstate(invalid="ignore"):
+        sqrt_phi_star = np.sqrt(phi_star)
+    delta_star = functions["d_phi"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    f_val = np.asarray(functions["rhs"](x[:, 0], x[:, 1], x[:, 2]))
+    phi_q_star = det_jac * weights * p_tab[0, :, :, 0].T
+
+    def residual(a, load):
+        a = a.reshape(1, -1)
+        el_form = np.zeros(n_dof)
+        if load:
+            el_form[n_u:n_dof] -= (sqrt_phi_star * phi_q_star) @ f_val[0].T
+        for i, omega in enumerate(weights):
+            phi, delta = phi_star[i], delta_star[i]
+            psi_h = u_tab[0, i, :, 0:dim]
+            w_h = p_tab[0, i, :, 0:dim]
+            u_h = a[:, 0:n_u] @ psi_h
+            p_h = a[:, n_u:n_dof] @ w_h
+            grad_psi_h = u_tab[1 : u_tab.shape[0] + 1, i, :, 0:dim]
+            div_psi_h = np.array([np.trace(grad_psi_h, axis1=0, axis2=2) / det_jac[i]])
+            if np.isclose(phi, 0.0) or phi < 0.0:
+                phi = phi_threshold
+            if np.isclose(delta, 0.0) or delta < 0.0:
+                delta = phi_threshold
+            div_u_h = a[:, 0:n_u] @ div_psi_h.T
+            integrand = np.zeros((1, n_dof))
+            integrand[:, 0:n_u] = ((1 / (delta * delta)) * u_h @ psi_h.T) - (p_h @ div_psi_h)
+            integrand[:, n_u:n_dof] = div_u_h @ w_h.T + phi * p_h @ w_h.T
+            el_form = el_form + det_jac[i] * omega * integrand.reshape((n_dof,))
+        return el_form
+
+    return _linearise(residual, alpha, n_dof)
+
+
+def scaled_to_physical_l2_projection(space, functions, iel, alpha, alpha_scaled):
+    """ScaledToPhysicalL2Projection.evaluate_form, R/src/weak_forms/scaled_to_physical_l2_projection.py:27-105
+    (three-argument form: the scaled solution enters as data)."""
+    dim, weights, x, det_jac, v_tab, q_tab, n_v, n_q = _mixed_setup(space, "v", "q", iel)
+    n_dof = n_v + n_q
+    phi_star = functions["porosity"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    delta_star = functions["d_phi"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    alpha_scaled = np.asarray(alpha_scaled, dtype=float)
+
+    def residual(a, load):
+        a = a.reshape(1, -1)
+        el_form = np.zeros(n_dof)
+        for i, omega in enumerate(weights):
+            phi, delta = phi_star[i], delta_star[i]
+            psi_h = v_tab[0, i, :, 0:dim]
+            w_h = q_tab[0, i, :, 0:dim]
+            u_h = a[:, 0:n_v] @ psi_h
+            p_h = a[:, n_v:n_dof] @ w_h
+            if load:
+                v_h = alpha_scaled[0:n_v] @ psi_h
+                q_h = alpha_scaled[n_v:n_dof] @ w_h
+                if phi > 0.0:
+                    v_h = v_h * delta
+                    q_h = q_h * (1.0 / np.sqrt(phi))
+            else:
+                v_h, q_h = 0.0 * (alpha_scaled[0:n_v] @ psi_h), 0.0 * (alpha_scaled[n_v:n_dof] @ w_h)
+            integrand = np.zeros((1, n_dof))
+            integrand[:, 0:n_v] = (u_h - v_h) @ psi_h.T
+            integrand[:, n_v:n_dof] = (p_h - q_h) @ w_h.T
+            el_form = el_form + det_jac[i] * omega * integrand.reshape((n_dof,))
+        return el_form
+
+    return _linearise(residual, alpha, n_dof)
+
+
+def _hdiv_natural_bc(space, flux, iel, value_at):
+    """Shared body of the natural boundary forms of the H(div) family: ``int_F g (psi . n)`` on the facet dofs of
+    the first neighbour (degenerate_elliptic_weak_form.py:147-216, unscaled_elliptic_weak_form.py:156-218)."""
+    from . import ref_hdiv
+
+    f_space, el, weights, x, det_jac, _ = _bc_setup(space, flux, iel)
+    cell = el.cell
+    points, _ = space.bc_quadrature[cell.dimension]
+    neigh = RefElement(f_space, f_space.first_neighbour(cell.id))
+    mapped = transform_lower_to_higher(np.asarray(points).reshape(len(weights), -1), cell, neigh.cell)
+    _, jac0, det0, inv0 = neigh.evaluate_mapping(mapped)
+    tr_tab = neigh.evaluate_basis(mapped, jac0, det0, inv0)
+    facet_index = neigh.cell.sub_cells_ids[cell.dimension].tolist().index(cell.id)
+    dofs = ref_hdiv.entity_dofs(neigh.family, neigh.cell.dimension, neigh.k)[cell.dimension][facet_index]
+    n = normal(f_space.mesh, neigh.cell, cell)
+    dim = neigh.cell.dimension
+    res = np.zeros(len(dofs))
+    for i, omega in enumerate(weights):
+        res += det_jac[i] * omega * value_at(x[i, 0], x[i, 1], x[i, 2]) * (tr_tab[0, i, dofs, 0:dim] @ n[0:dim])
+    return res, np.zeros((len(res), len(res)))
+
+
+def degenerate_elliptic_bc_dirichlet(space, functions, iel, alpha):
+    def value_at(xx, yy, zz):
+        q_d = np.array(functions["q"](xx, yy, zz), dtype=float)
+        d_phi = functions["d_phi"](xx, yy, zz)
+        phi_v = functions["porosity"](xx, yy, zz)
+        if not np.isclose(phi_v, 0.0) and phi_v > 0.0:
+            q_d = q_d * (d_phi / np.sqrt(phi_v))
+        return q_d[0]
+
+    return _hdiv_natural_bc(space, "v", iel, value_at)
+
+
+def unscaled_elliptic_bc_dirichlet(space, functions, iel, alpha):
+    return _hdiv_natural_bc(space, "u", iel, lambda xx, yy, zz: functions["p"](xx, yy, zz)[0])

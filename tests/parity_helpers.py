@@ -262,3 +262,62 @@ class SundusCase:
             ("time_dependent_bc_form", ref_forms.sundus_dual_bc_dirichlet, self.bc_functions, len(mp.bc_element_ids)),
         ]
         return ref_assembly.assemble_time_dependent(space, forms, self.alphas(space.n_dof), self.t)
+
+
+def degenerate_case(kind="degenerate", dim=3, k=1, n=2, with_bc=True, alpha=True, mesh=None):
+    """Arbogast-Taicher family (config 3's other form classes): porosity vanishes on part of the domain so that the
+    per-point ``isclose(phi, 0)`` branches of the reference are exercised.  kind: degenerate | unscaled | projection."""
+    from nfempy_b200 import weak_forms as wf_mod
+
+    if mesh is None:
+        mesh = box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(n, jitter=0.2)
+    btag_list = [2, 3, 4, 5, 6, 7] if dim == 3 else [2, 3, 4, 5]
+    porosity = lambda x, y, z: np.maximum(x - 0.4, 0.0) * (1.0 + 0.5 * y)
+    d_phi = lambda x, y, z: np.maximum(x - 0.4, 0.0) ** 1.5 + 0.0 * y
+    grad_d_phi = lambda x, y, z: np.array([1.5 * np.maximum(x - 0.4, 0.0) ** 0.5, 0.1 * y, 0.0 * z])
+    functions = {
+        "rhs": lambda x, y, z: np.array([np.sin(np.pi * x) * (1.0 + y) + z]), "porosity": porosity, "d_phi": d_phi,
+        "grad_d_phi": grad_d_phi,
+    }
+    flux, scalar = ("u", "p") if kind == "unscaled" else ("v", "q")
+    bc_functions = {scalar: lambda x, y, z: np.array([x + 2.0 * y - z + np.sin(x)]), "porosity": porosity, "d_phi": d_phi}
+    scaled_fn = lambda nd: 0.4 * np.sin(np.arange(nd) * 0.23) - 0.1
+    vol_cls, bc_cls, ref_vol, ref_bc = {
+        "degenerate": (wf_mod.DegenerateEllipticWeakForm, wf_mod.DegenerateEllipticWeakFormBCDirichlet,
+                       ref_forms.degenerate_elliptic, ref_forms.degenerate_elliptic_bc_dirichlet),
+        "unscaled": (wf_mod.UnscaledEllipticWeakForm, wf_mod.UnscaledEllipticWeakFormBCDirichlet,
+                     ref_forms.unscaled_elliptic, ref_forms.unscaled_elliptic_bc_dirichlet),
+        "projection": (wf_mod.ScaledToPhysicalL2Projection, None, None, None),
+    }[kind]
+
+    def gpu_forms(space, a):
+        wf = vol_cls(space)
+        wf.functions = functions
+        if kind == "projection":
+            wf.alpha_scaled = scaled_fn(space.n_dof)
+        out = {"volume": ["form", range(len(space.discrete_spaces[flux].elements)), wf, a]}
+        if with_bc and bc_cls is not None:
+            bf = bc_cls(space)
+            bf.functions = bc_functions
+            out["bc"] = ["bc_form", range(len(space.discrete_spaces[flux].bc_elements)), bf, a]
+        return out
+
+    def ref_forms_fn(space):
+        n_el = len(space.discrete_spaces[flux].element_ids)
+        if kind == "projection":
+            scaled = scaled_fn(space.n_dof)
+
+            def proj(sp, fns, iel, alpha_l):
+                return ref_forms.scaled_to_physical_l2_projection(sp, fns, iel, alpha_l, scaled[sp.destination_indexes(iel)])
+
+            return [("form", proj, functions, n_el)]
+        out = [("form", ref_vol, functions, n_el)]
+        if with_bc:
+            out.append(("bc_form", ref_bc, bc_functions, len(space.discrete_spaces[flux].bc_element_ids)))
+        return out
+
+    alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None
+    return Case(
+        mesh, lambda g: {flux: (dim, 1, "RT", k, g), scalar: (dim, 1, "Lagrange", k - 1, g)}, {flux: [1], scalar: [1]},
+        {flux: btag_list if with_bc else []}, gpu_forms, ref_forms_fn, disc={scalar: True}, alpha_fn=alpha_fn,
+    )

@@ -90,3 +90,29 @@ def test_sundus_reassembly_reuses_the_plan():
     asm.form_to_input_list = case.gpu_forms(space, (a_n, a))
     again = asm.assemble()
     assert np.array_equal(again[2], first[2]) and np.array_equal(again[3], first[3])
+
+
+@pytest.mark.parametrize("kind", ["degenerate", "unscaled", "projection"])
+@pytest.mark.parametrize("dim,k", [(3, 1), (3, 2), (2, 2)])
+def test_degenerate_elliptic_family(kind, dim, k):
+    """DegenerateEllipticWeakForm / UnscaledEllipticWeakForm (+ their natural BC forms) and
+    ScaledToPhysicalL2Projection with a porosity that vanishes on part of the domain, nonzero iterate."""
+    from tests.parity_helpers import degenerate_case
+
+    case = degenerate_case(kind=kind, dim=dim, k=k, n=2 if dim == 3 else 3)
+    compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
+
+
+def test_scaled_to_physical_evaluate_form_signature():
+    """The reference's three-argument ``evaluate_form(i, alpha, alpha_scaled)`` on one cell vs the oracle."""
+    from oracle import ref_forms
+    from tests.parity_helpers import degenerate_case
+
+    case = degenerate_case(kind="projection", dim=3, k=1, n=2)
+    space, rspace = case.space(), case.ref_space()
+    form = case.gpu_forms(space, None)["volume"][2]
+    nl = len(space.destination_indexes(3))
+    a, s = np.cos(np.arange(nl) * 0.7), np.sin(np.arange(nl) * 0.3) + 0.2
+    r, j = form.evaluate_form(3, a, s)
+    r0, j0 = ref_forms.scaled_to_physical_l2_projection(rspace, form.functions, 3, a, s)
+    assert np.abs(r - r0).max() <= 1e-12 * np.abs(r0).max() and np.abs(j - j0).max() <= 1e-12 * np.abs(j0).max()

@@ -50,9 +50,14 @@ def oracle_rate(case, n_cells):
     return n_cells / (time.perf_counter() - t0)
 
 
+ONLY = ""
+
+
 def run_case(name, case, small_case, steps, warmup, allow_fused=True, oracle_cells=40):
     import torch
 
+    if ONLY and ONLY not in name:
+        return
     from nfempy_b200 import _lib
     from nfempy_b200.assembly import GPUAssembler
 
@@ -97,6 +102,8 @@ def run_case(name, case, small_case, steps, warmup, allow_fused=True, oracle_cel
 def run_sundus(mesh, n_steps):
     import torch
 
+    if ONLY and ONLY not in "config5 sundus":
+        return
     from nfempy_b200.assembly import GPUAssembler
     from tests.parity_helpers import SundusCase
 
@@ -142,7 +149,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--quick", action="store_true", help="small meshes (smoke run)")
+    ap.add_argument("--only", default="", help="run only the cases whose name contains this text")
     args = ap.parse_args()
+    global ONLY
+    ONLY = args.only
     from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
     from tests.parity_helpers import elasticity_case, laplace_case, mixed_poisson_case
 
