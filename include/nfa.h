@@ -203,6 +203,27 @@ int nfa_assemble_h1_laplace_affine(const nfa_bplan *bp, int dim, const double *d
                                    const double *d_kappa, int64_t kappa_stride,
                                    double *d_vals, nfa_stream stream);
 
+
+/* ---- row-item fused path for vector-P2 elasticity on affine tetrahedra (config 2's headline kernel).
+ * Same plan object, same output (all nnz values of the pattern, written once, deterministic) as
+ * nfa_assemble_h1_elasticity_affine, i.e. the matrix part of LEPrimalWeakForm.evaluate_form
+ * (R/src/weak_forms/le_primal_weak_form.py:91-126) + the scatter (R/src/assembly/ScatterFormData.py:5-11); the
+ * local blocks are evaluated from the physical gradients of the barycentric coordinates, one thread per set of CSR
+ * blocks fed by the same cells.  The item lists are built by the host layer (nfempy_b200/assembly/p2_items.py) from
+ * the plan's block pattern and attached once:
+ *   nfa_bplan_block_pattern  copies bptr int32 [n_nodes + 1] / bcols int32 [n_blocks] to caller buffers (device);
+ *   nfa_bplan_set_p2_items   copies the lists (device pointers; layouts in nfa_plan.cuh / p2_items.py) into the plan.
+ * Requires mu > 0 in every cell (the caller checks); lambda, mu per cell (stride 1) or constant (stride 0). */
+int nfa_bplan_block_pattern(const nfa_bplan *bp, int32_t *d_bptr, int32_t *d_bcols, nfa_stream stream);
+int64_t nfa_bplan_n_blocks(const nfa_bplan *bp);
+int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *d_chunk_hdr, int64_t n_tasks,
+                           const int32_t *d_task_hdr, int64_t n_items, const uint16_t *d_item_hdr, int64_t ell_size,
+                           const uint32_t *d_ell, int max_tile_blocks, nfa_stream stream);
+int nfa_bplan_has_p2_items(const nfa_bplan *bp);
+int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *d_coords, const int32_t *d_cell_nodes,
+                                  const double *d_lambda, int64_t lambda_stride, const double *d_mu,
+                                  int64_t mu_stride, double *d_vals, nfa_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

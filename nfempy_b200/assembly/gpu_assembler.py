@@ -12,6 +12,7 @@ per-cell Python loop + ``Mat.setValue`` calls (R/src/assembly/ScatterFormData.py
 shim).  ``assemble()`` is the one-shot convenience returning ``(indptr, indices, data, rhs)``.
 """
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -166,6 +167,8 @@ class GPUAssembler:
                 "nfa_bplan_create",
             )
             p.bplan = bh
+            if int(node_dest.shape[1]) == 10 and nc == 3 and s.dimension == 3 and os.environ.get("NFA_P2TET", "1") != "0":
+                self._attach_p2_items(lib, dev, p, node_dest, stream)
             ph = ctypes.c_void_p()
             _lib.check(lib.nfa_plan_from_bplan(bh, ctypes.byref(ph), stream), "nfa_plan_from_bplan")
             p.pattern = ph
@@ -182,6 +185,29 @@ class GPUAssembler:
         torch.cuda.synchronize(dev.device)
         p.build_seconds = time.perf_counter() - t0
         return p
+
+    @staticmethod
+    def _attach_p2_items(lib, dev, p, node_dest, stream):
+        """Row-item lists of the vector-P2 tetrahedron kernel (assembly/p2_items.py), built on the device with torch
+        tensor operations from the plan's block pattern and copied into the plan."""
+        from . import p2_items
+
+        n_nodes = p.n_dof // 3
+        n_blocks = int(lib.nfa_bplan_n_blocks(p.bplan))
+        bptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev.device)
+        bcols = torch.empty(n_blocks, dtype=torch.int32, device=dev.device)
+        _lib.check(lib.nfa_bplan_block_pattern(p.bplan, _lib.ptr(bptr), _lib.ptr(bcols), stream), "nfa_bplan_block_pattern")
+        cap = int(os.environ.get("NFA_P2TET_CAP", "448"))
+        items = p2_items.build(node_dest.to(torch.int64), bptr.to(torch.int64), bcols.to(torch.int64), n_nodes, cap=cap)
+        _lib.check(
+            lib.nfa_bplan_set_p2_items(
+                p.bplan, items["n_chunks"], _lib.ptr(items["chunk_hdr"]), items["n_tasks"], _lib.ptr(items["task_hdr"]),
+                items["n_items"], _lib.ptr(items["item_hdr"]), items["ell_size"], _lib.ptr(items["ell"]),
+                items["max_tile_blocks"], stream,
+            ),
+            "nfa_bplan_set_p2_items",
+        )
+        p.p2_stats = {k: v for k, v in items.items() if isinstance(v, int)}
 
     # ------------------------------------------------------------------------------------------
     def prepare(self):
@@ -240,11 +266,16 @@ class GPUAssembler:
             if i == plan.fused_index:
                 spec = form.fused_spec(data)
                 target = jac.values_dev if jac.is_zero else torch.empty_like(jac.values_dev)
-                args = [plan.bplan, data.dim, _lib.ptr(form.mref(dev)), _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes)]
+                kernel = spec["kernel"]
+                if spec.get("p2tet_kernel") and lib.nfa_bplan_has_p2_items(plan.bplan):
+                    kernel = spec["p2tet_kernel"]
+                    args = [plan.bplan, _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes)]
+                else:
+                    args = [plan.bplan, data.dim, _lib.ptr(form.mref(dev)), _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes)]
                 for c in spec["coefs"]:
                     args += [_lib.ptr(c[0]), c[1]]
                 args += [_lib.ptr(target), stream]
-                _lib.check(getattr(lib, spec["kernel"])(*args), spec["kernel"])
+                _lib.check(getattr(lib, kernel)(*args), kernel)
                 if alpha_dev is not None:
                     _lib.check(
                         lib.nfa_csr_spmv(plan.pattern, _lib.ptr(target), _lib.ptr(alpha_dev), 1, _lib.ptr(rhs_dev), stream),

@@ -1,0 +1,515 @@
+// libnfa: row-item fused assembly of vector-P2 elasticity on affine tetrahedra (sm_100a) -- the config-2 headline path.
+//
+// The local matrix of LEPrimalWeakForm (R/src/weak_forms/le_primal_weak_form.py:91-126, integrated exactly for
+// cell-wise constant lambda, mu) is written with the physical gradients g_m of the barycentric coordinates:
+//   grad phi_vertex(i) = (4 lam_i - 1) g_i,   grad phi_edge(ij) = 4 (lam_j g_i + lam_i g_j),
+// whose scalar factors integrate to the universal constants 1/10, -1/30, 4/15, 2/15.  A block of the local matrix is
+// then Kf(sum c u (x) w) with u, w sums of the g_m of the vertices involved and
+//   Kf(T) = det (lambda T + mu T^T + mu tr(T) I).
+// With g' = sqrt(det mu) g and rho = lambda / mu:  Kf(u (x) w) = rho u' w'^T + w' u'^T + (u'.w') I.
+//
+// Work is organised by OUTPUT ROW (no atomics, no staging of contributions): the block row of a node is cut into
+// ITEMS of at most three CSR blocks that receive contributions from exactly the same cells (nfempy_b200/assembly/
+// p2_items.py lists the six item types).  One thread owns one item, walks its cells in ascending cell order -- the
+// order of the reference's Mat.setValue(..., addv=True) calls, R/src/assembly/ScatterFormData.py:5-11 -- sums in
+// registers and writes every CSR value exactly once into the CTA's shared-memory tile (the CSR image of a run of
+// whole block rows), which leaves for HBM as ONE bulk asynchronous copy (cp.async.bulk shared -> global, TMA engine).
+// Inputs per (item, cell): one 32-bit packed entry (coalesced, ELL per warp) and one 32-byte record per vertex used,
+// fetched with 256-bit loads (LDG.E.256) from the per-cell geometry records (L1/L2 resident: 128 B per cell).
+#include <algorithm>
+
+#include "nfa_plan.cuh"
+
+using namespace nfa;
+
+namespace {
+
+#ifndef NFA_P2_THREADS
+#define NFA_P2_THREADS 512
+#endif
+#ifndef NFA_P2_NBUF
+#define NFA_P2_NBUF 4
+#endif
+#ifndef P2_UNROLL_NG
+#define P2_UNROLL_NG 2
+#endif
+constexpr int P2_THREADS = NFA_P2_THREADS;
+constexpr int P2_NBUF = NFA_P2_NBUF;
+
+struct G4 {
+    double x, y, z, rho;
+};
+
+__device__ __forceinline__ G4 ldg256(const double *p) {
+    G4 g;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(g.x), "=d"(g.y), "=d"(g.z), "=d"(g.rho) : "l"(p));
+    return g;
+}
+
+// geometry records [n_cells][4][4]: (sqrt(det mu) g_m, lambda / mu), m = 0..3
+__global__ void p2tet_geo_kernel(const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
+                                 int64_t n_cells, const double *__restrict__ lam, int64_t ls,
+                                 const double *__restrict__ mu, int64_t ms, double *__restrict__ rec) {
+    int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    double X[4][3];
+    load_cell_coords<3>(coords, cell_nodes, cell, X);
+    Geom<3> g;
+    compute_geom<3>(X, g);
+    const double m = mu[cell * ms], l = lam[cell * ls];
+    const double sc = sqrt(g.det * m), rho = l / m;
+    double *r = rec + cell * 16;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double a = sc * g.Jinv[k][0], b = sc * g.Jinv[k][1], c = sc * g.Jinv[k][2];
+        s0 -= a;
+        s1 -= b;
+        s2 -= c;
+        reinterpret_cast<double2 *>(r + 4 * (k + 1))[0] = make_double2(a, b);
+        reinterpret_cast<double2 *>(r + 4 * (k + 1))[1] = make_double2(c, rho);
+    }
+    reinterpret_cast<double2 *>(r)[0] = make_double2(s0, s1);
+    reinterpret_cast<double2 *>(r)[1] = make_double2(s2, rho);
+}
+
+// acc += Kf(u (x) w) without the trace part; returns u.w
+__device__ __forceinline__ double add_general(double (&acc)[9], double rho, const double (&u)[3], const double (&w)[3]) {
+    const double ru[3] = {rho * u[0], rho * u[1], rho * u[2]};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) acc[3 * r + s] = fma(ru[r], w[s], fma(w[r], u[s], acc[3 * r + s]));
+    return fma(u[0], w[0], fma(u[1], w[1], u[2] * w[2]));
+}
+
+// acc (xx, xy, xz, yy, yz, zz) += (rho + 1) u u^T; returns |u|^2
+__device__ __forceinline__ double add_sym(double (&acc)[6], double rho, const double (&u)[3]) {
+    const double r1 = rho + 1.0;
+    const double a = r1 * u[0], b = r1 * u[1], c = r1 * u[2];
+    acc[0] = fma(a, u[0], acc[0]);
+    acc[1] = fma(a, u[1], acc[1]);
+    acc[2] = fma(a, u[2], acc[2]);
+    acc[3] = fma(b, u[1], acc[3]);
+    acc[4] = fma(b, u[2], acc[4]);
+    acc[5] = fma(c, u[2], acc[5]);
+    return fma(u[0], u[0], fma(u[1], u[1], u[2] * u[2]));
+}
+
+__device__ __forceinline__ void store_block(double *tile, unsigned where, unsigned pitch, const double (&k)[9]) {
+    if (where == 0xFFFFu) return;
+    double *p = tile + where;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) p[r * pitch + s] = k[3 * r + s];
+}
+
+__device__ __forceinline__ void sym_to_full(const double (&a)[6], double c, double tr, double (&k)[9]) {
+    k[0] = c * (a[0] + tr);
+    k[1] = k[3] = c * a[1];
+    k[2] = k[6] = c * a[2];
+    k[4] = c * (a[3] + tr);
+    k[5] = k[7] = c * a[4];
+    k[8] = c * (a[5] + tr);
+}
+
+// Where a finished item goes: the chunk's tile (once the tile has been handed over to this chunk) at the item's offsets.
+struct TileCtx {
+    double *tile;
+    volatile int *free_at;
+    int need;
+    unsigned w0, w1, w2, pitch;
+    __device__ __forceinline__ void wait() const {
+        if ((threadIdx.x & 31) == 0) {
+            while (*free_at < need) __nanosleep(32);
+            __threadfence_block();
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void put(int k, const double (&v)[9]) const {
+        store_block(tile, k == 0 ? w0 : (k == 1 ? w1 : w2), pitch, v);
+    }
+};
+
+// ---- per item type: which vertices' records an entry needs, how a cell adds to the sums, how the sums become blocks
+template <int NG>
+struct Rec {
+    G4 g[NG];
+    bool valid;
+};
+
+template <int NG>
+__device__ __forceinline__ Rec<NG> load_rec(uint32_t code, const double *__restrict__ rec) {
+    Rec<NG> r;
+    r.valid = code != 0xFFFFFFFFu;
+#pragma unroll
+    for (int m = 0; m < NG; ++m) r.g[m] = G4{0.0, 0.0, 0.0, 0.0};
+    if (r.valid) {
+        const double *rc = rec + (size_t)(code >> 6) * 16;
+        r.g[0] = ldg256(rc + 4 * ((code >> 4) & 3u));
+        if constexpr (NG > 1) r.g[1] = ldg256(rc + 4 * ((code >> 2) & 3u));
+        if constexpr (NG > 2) r.g[2] = ldg256(rc + 4 * (code & 3u));
+    }
+    return r;
+}
+
+constexpr double C10 = 0.1, C30 = 1.0 / 30.0, C15 = 2.0 / 15.0;
+
+template <int TYPE>
+struct Item;
+
+template <>
+struct Item<0> {  // A: (v, v) = 0.1 Kf(g_i g_i^T)
+    static constexpr int NG = 1;
+    double q[6] = {0, 0, 0, 0, 0, 0}, tr = 0.0;
+    __device__ __forceinline__ void add(const Rec<NG> &r) {
+        const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z};
+        tr += add_sym(q, r.g[0].rho, u);
+    }
+    __device__ __forceinline__ void finish(const TileCtx &ctx) {
+        double o[9];
+        sym_to_full(q, C10, tr, o);
+        ctx.put(0, o);
+    }
+};
+
+template <>
+struct Item<1> {  // B: (v, v') = -1/30 P, (v, E) = 0.1 P - Q / 30 with P = Kf(g_i (x) g_k), Q = Kf(g_i g_i^T)
+    static constexpr int NG = 2;
+    double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, q[6] = {0, 0, 0, 0, 0, 0}, trp = 0.0, trq = 0.0;
+    __device__ __forceinline__ void add(const Rec<NG> &r) {
+        const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z}, w[3] = {r.g[1].x, r.g[1].y, r.g[1].z};
+        trp += add_general(p, r.g[0].rho, u, w);
+        trq += add_sym(q, r.g[0].rho, u);
+    }
+    __device__ __forceinline__ void finish(const TileCtx &ctx) {
+        double o[9];
+#pragma unroll
+        for (int i = 0; i < 9; i += 4) p[i] += trp;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = -C30 * p[i];
+        ctx.put(0, o);
+        sym_to_full(q, -C30, trq, o);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = fma(C10, p[i], o[i]);
+        ctx.put(1, o);
+    }
+};
+
+template <>
+struct Item<2> {  // C: (v, e_xy) = Kf(g_i (x) (g_i + g_z)) / 30, since g_x + g_y = -(g_i + g_z)
+    static constexpr int NG = 2;
+    double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, trp = 0.0;
+    __device__ __forceinline__ void add(const Rec<NG> &r) {
+        const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z};
+        const double w[3] = {u[0] + r.g[1].x, u[1] + r.g[1].y, u[2] + r.g[1].z};
+        trp += add_general(p, r.g[0].rho, u, w);
+    }
+    __device__ __forceinline__ void finish(const TileCtx &ctx) {
+        double o[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = C30 * (p[i] + ((i % 4 == 0) ? trp : 0.0));
+        ctx.put(0, o);
+    }
+};
+
+template <>
+struct Item<3> {  // D: (E, v_i) = 0.1 P^T - Qi / 30, (E, v_j) = 0.1 P - Qj / 30, (E, E) = 2/15 (2 Qi + 2 Qj + P + P^T)
+    static constexpr int NG = 2;
+    double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, qi[6] = {0, 0, 0, 0, 0, 0}, qj[6] = {0, 0, 0, 0, 0, 0};
+    double trp = 0.0, tri = 0.0, trj = 0.0;
+    __device__ __forceinline__ void add(const Rec<NG> &r) {
+        const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z}, w[3] = {r.g[1].x, r.g[1].y, r.g[1].z};
+        trp += add_general(p, r.g[0].rho, u, w);
+        tri += add_sym(qi, r.g[0].rho, u);
+        trj += add_sym(qj, r.g[0].rho, w);
+    }
+    __device__ __forceinline__ void finish(const TileCtx &ctx) {
+        double fi[9], fj[9], o[9];
+        sym_to_full(qi, 1.0, tri, fi);
+        sym_to_full(qj, 1.0, trj, fj);
+#pragma unroll
+        for (int i = 0; i < 9; i += 4) p[i] += trp;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) o[3 * r + s] = C10 * p[3 * s + r] - C30 * fi[3 * r + s];
+        ctx.put(0, o);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) o[i] = C10 * p[i] - C30 * fj[i];
+        ctx.put(1, o);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+                o[3 * r + s] = C15 * (2.0 * (fi[3 * r + s] + fj[3 * r + s]) + p[3 * r + s] + p[3 * s + r]);
+        ctx.put(2, o);
+    }
+};
+
+template <>
+struct Item<4> {  // E: (E, v_x), (E, e_ix), (E, e_jx) with s = g_i + g_j
+    static constexpr int NG = 3;
+    double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+    __device__ __forceinline__ void add(const Rec<NG> &r) {
+        const double rho = r.g[0].rho;
+        const double a[3] = {r.g[0].x, r.g[0].y, r.g[0].z}, b[3] = {r.g[1].x, r.g[1].y, r.g[1].z};
+        const double x[3] = {r.g[2].x, r.g[2].y, r.g[2].z};
+        const double s[3] = {a[0] + b[0], a[1] + b[1], a[2] + b[2]};
+        const double ax[3] = {a[0] + x[0], a[1] + x[1], a[2] + x[2]};
+        const double bx[3] = {b[0] + x[0], b[1] + x[1], b[2] + x[2]};
+        t0 += add_general(k0, rho, s, x);
+        t1 += add_general(k1, rho, s, ax);
+        t1 += add_general(k1, rho, b, x);
+        t2 += add_general(k2, rho, s, bx);
+        t2 += add_general(k2, rho, a, x);
+    }
+    __device__ __forceinline__ void finish(const TileCtx &ctx) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const bool d = (i % 4 == 0);
+            k0[i] = -C30 * (k0[i] + (d ? t0 : 0.0));
+            k1[i] = C15 * (k1[i] + (d ? t1 : 0.0));
+            k2[i] = C15 * (k2[i] + (d ? t2 : 0.0));
+        }
+        ctx.put(0, k0);
+        ctx.put(1, k1);
+        ctx.put(2, k2);
+    }
+};
+
+template <>
+struct Item<5> {  // F: (E, E_opp) = -2/15 Kf(s s^T), since g_x + g_y = -(g_i + g_j)
+    static constexpr int NG = 2;
+    double q[6] = {0, 0, 0, 0, 0, 0}, tr = 0.0;
+    __device__ __forceinline__ void add(const Rec<NG> &r) {
+        const double s[3] = {r.g[0].x + r.g[1].x, r.g[0].y + r.g[1].y, r.g[0].z + r.g[1].z};
+        tr += add_sym(q, r.g[0].rho, s);
+    }
+    __device__ __forceinline__ void finish(const TileCtx &ctx) {
+        double o[9];
+        sym_to_full(q, -C15, tr, o);
+        ctx.put(0, o);
+    }
+};
+
+// One task = up to 32 items of one type; lane = item.  e points at the lane's first ELL entry (stride 32).  Items that
+// read at most two records per cell keep two cells in flight (all 256-bit loads issued before the first is consumed);
+// type E (three records, 27 sums) walks one cell at a time to stay inside the register budget.
+template <int TYPE>
+__device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kmax, const double *__restrict__ rec,
+                                         double *tile, volatile int *free_at, int need, unsigned ihx, unsigned ihy) {
+    const TileCtx ctx = {tile, free_at, need, ihx & 0xFFFFu, ihx >> 16, ihy & 0xFFFFu, ihy >> 16};
+    constexpr int NG = Item<TYPE>::NG;
+    Item<TYPE> item;
+    if constexpr (NG <= P2_UNROLL_NG) {
+        uint32_t c0 = __ldg(e), c1 = kmax > 1 ? __ldg(e + 32) : 0xFFFFFFFFu;
+#pragma unroll 1
+        for (int k = 0; k < kmax; k += 2) {
+            const Rec<NG> r0 = load_rec<NG>(c0, rec), r1 = load_rec<NG>(c1, rec);
+            c0 = (k + 2 < kmax) ? __ldg(e + 32 * (k + 2)) : 0xFFFFFFFFu;
+            c1 = (k + 3 < kmax) ? __ldg(e + 32 * (k + 3)) : 0xFFFFFFFFu;
+            if (r0.valid) item.add(r0);
+            if (r1.valid) item.add(r1);
+        }
+    } else {
+        uint32_t c0 = __ldg(e);
+#pragma unroll 1
+        for (int k = 0; k < kmax; ++k) {
+            const Rec<NG> r0 = load_rec<NG>(c0, rec);
+            c0 = (k + 1 < kmax) ? __ldg(e + 32 * (k + 1)) : 0xFFFFFFFFu;
+            if (r0.valid) item.add(r0);
+        }
+    }
+    ctx.wait();
+    item.finish(ctx);
+}
+
+// Warps of a CTA pull tasks from the CTA's contiguous chunk range through one shared counter; chunk c lives in tile
+// (c - c_begin) % NBUF.  The warp that finishes the last task of a chunk sends the tile to HBM with one bulk copy,
+// waits until the copy engine has read it and hands the tile to chunk c + NBUF.  No CTA-wide barrier in the loop.
+__global__ void __launch_bounds__(P2_THREADS, 1)
+    p2tet_elasticity_kernel(int NBUF, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
+                            const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
+                            const double *__restrict__ rec, int tile_stride, double *__restrict__ vals) {
+    extern __shared__ __align__(128) double smem[];  // NBUF tiles of tile_stride doubles, then the control words
+    // ctrl: [0] next task, [1] c_begin, [2] c_end, [3] task_end, [4 .. 4+NBUF) tasks left per tile, then free_at per tile.
+    // Everything the tail of an iteration needs is re-read from here / from the (L1-resident) headers instead of being
+    // kept in registers across the accumulation loops, which need the whole register file.
+    volatile int *ctrl = reinterpret_cast<volatile int *>(smem + (size_t)NBUF * tile_stride);
+    if (threadIdx.x == 0) {
+        const int c_begin = (int)((int64_t)n_chunks * blockIdx.x / gridDim.x);
+        const int c_end = (int)((int64_t)n_chunks * (blockIdx.x + 1) / gridDim.x);
+        ctrl[1] = c_begin;
+        ctrl[2] = c_end;
+        ctrl[0] = ctrl[3] = 0;
+        if (c_begin < c_end) {
+            ctrl[0] = __ldg(chunk_hdr + c_begin).z;
+            ctrl[3] = __ldg(chunk_hdr + c_end - 1).z + __ldg(chunk_hdr + c_end - 1).w;
+        }
+        for (int b = 0; b < NBUF; ++b) {
+            ctrl[4 + b] = (c_begin + b < c_end) ? __ldg(chunk_hdr + c_begin + b).w : 0;
+            ctrl[4 + NBUF + b] = 0;
+        }
+    }
+    __syncthreads();
+    while (true) {
+        int t = 0;
+        if ((threadIdx.x & 31) == 0) t = atomicAdd(const_cast<int *>(ctrl), 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ctrl[3]) break;
+        {
+            const int lane = threadIdx.x & 31;
+            const int4 th = __ldg(task_hdr + t);
+            const int type = th.x & 0xFF, kmax = th.x >> 8, n_items = th.w & 63, c = (int)((unsigned)th.w >> 6);
+            const uint32_t *e = ell + (uint32_t)th.y + lane;
+            uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
+            if (lane < n_items) ih = __ldg(item_hdr + th.z + lane);
+            const int it = c - ctrl[1], b = it % NBUF;
+            const int b0 = __ldg(chunk_hdr + c).x;
+            double *tile = smem + (size_t)b * tile_stride + (b0 & 1);  // same 16-byte phase as the tile's image in vals
+#ifdef P2_ONLY
+            run_task<P2_ONLY>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
+#else
+            switch (type) {
+                case 0:
+                asm volatile("// item type 0 begin" ::: "memory");
+                run_task<0>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
+                asm volatile("// item type 0 end" ::: "memory");
+                break;
+                case 1:
+                asm volatile("// item type 1 begin" ::: "memory");
+                run_task<1>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
+                asm volatile("// item type 1 end" ::: "memory");
+                break;
+                case 2:
+                asm volatile("// item type 2 begin" ::: "memory");
+                run_task<2>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
+                asm volatile("// item type 2 end" ::: "memory");
+                break;
+                case 3:
+                asm volatile("// item type 3 begin" ::: "memory");
+                run_task<3>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
+                asm volatile("// item type 3 end" ::: "memory");
+                break;
+                case 4:
+                asm volatile("// item type 4 begin" ::: "memory");
+                run_task<4>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
+                asm volatile("// item type 4 end" ::: "memory");
+                break;
+                default:
+                asm volatile("// item type 5 begin" ::: "memory");
+                run_task<5>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
+                asm volatile("// item type 5 end" ::: "memory");
+                break;
+            }
+#endif
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) {
+            int w;
+            asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(w) : "l"(reinterpret_cast<const int *>(task_hdr + t) + 3));
+            const int c = (int)((unsigned)w >> 6), c_begin = ctrl[1], c_end = ctrl[2];
+            const int it = c - c_begin, b = it % NBUF;
+            __threadfence_block();
+            if (atomicSub(const_cast<int *>(ctrl) + 4 + b, 1) == 1) {  // the chunk's last task: the tile is complete
+                __threadfence_block();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const int4 ch = __ldg(chunk_hdr + c);
+                const int b0 = ch.x, n_vals = 9 * ch.y, head = b0 & 1;
+                const int n_bulk = (n_vals - head) & ~1;
+                const double *tile = smem + (size_t)b * tile_stride + head;
+                double *dst = vals + (int64_t)9 * b0;
+                if (n_bulk > 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile + head);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head),
+                                 "r"(src), "r"(n_bulk * 8)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (head) dst[0] = tile[0];
+                if (head + n_bulk < n_vals) dst[n_vals - 1] = tile[n_vals - 1];
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                ctrl[4 + b] = (c + NBUF < c_end) ? __ldg(chunk_hdr + c + NBUF).w : 0;
+                __threadfence_block();
+                ctrl[4 + NBUF + b] = it / NBUF + 1;
+            }
+        }
+    }
+    if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace
+
+extern "C" int nfa_bplan_block_pattern(const nfa_bplan *bp, int32_t *bptr, int32_t *bcols, nfa_stream stream) {
+    if (!bp) return fail("nfa_bplan_block_pattern: plan is NULL");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (bptr) NFA_CUDA(cudaMemcpyAsync(bptr, bp->bptr.p, 4 * (bp->n_nodes + 1), cudaMemcpyDeviceToDevice, s));
+    if (bcols) NFA_CUDA(cudaMemcpyAsync(bcols, bp->bcols.p, 4 * bp->n_bnz, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+extern "C" int64_t nfa_bplan_n_blocks(const nfa_bplan *bp) { return bp ? bp->n_bnz : -1; }
+
+extern "C" int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *chunk_hdr, int64_t n_tasks,
+                                      const int32_t *task_hdr, int64_t n_items, const uint16_t *item_hdr,
+                                      int64_t ell_size, const uint32_t *ell, int max_tile_blocks, nfa_stream stream) {
+    if (!bp) return fail("nfa_bplan_set_p2_items: plan is NULL");
+    if (bp->n_phi != 10 || bp->n_comp != 3) return fail("nfa_bplan_set_p2_items: plan is not vector-P2 on tetrahedra");
+    if (n_chunks <= 0 || n_tasks <= 0 || n_items <= 0 || ell_size <= 0 || max_tile_blocks <= 0)
+        return fail("nfa_bplan_set_p2_items: empty item plan");
+    if ((int64_t)max_tile_blocks * 9 + 2 >= 65535) return fail("nfa_bplan_set_p2_items: tile exceeds 16-bit offsets");
+    cudaStream_t s = (cudaStream_t)stream;
+    nfa_bplan::P2Items &it = bp->p2;
+    if (it.chunk_hdr.alloc(16 * n_chunks) || it.task_hdr.alloc(16 * n_tasks) || it.item_hdr.alloc(8 * n_items) ||
+        it.ell.alloc(4 * ell_size) || it.rec.alloc(sizeof(double) * 16 * bp->n_cells))
+        return 2;
+    NFA_CUDA(cudaMemcpyAsync(it.chunk_hdr.p, chunk_hdr, 16 * n_chunks, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaMemcpyAsync(it.task_hdr.p, task_hdr, 16 * n_tasks, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaMemcpyAsync(it.item_hdr.p, item_hdr, 8 * n_items, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaMemcpyAsync(it.ell.p, ell, 4 * ell_size, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaStreamSynchronize(s));
+    it.n_chunks = n_chunks;
+    it.n_tasks = n_tasks;
+    it.n_items = n_items;
+    it.ell_size = ell_size;
+    it.max_tile_blocks = max_tile_blocks;
+    return 0;
+}
+
+extern "C" int nfa_bplan_has_p2_items(const nfa_bplan *bp) { return bp && bp->p2.n_chunks > 0 ? 1 : 0; }
+
+extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *coords, const int32_t *cell_nodes,
+                                             const double *lam, int64_t ls, const double *mu, int64_t ms, double *vals,
+                                             nfa_stream stream) {
+    if (!bp) return fail("nfa_assemble_p2tet_elasticity: plan is NULL");
+    const nfa_bplan::P2Items &it = bp->p2;
+    if (it.n_chunks <= 0) return fail("nfa_assemble_p2tet_elasticity: the plan carries no row items");
+    cudaStream_t s = (cudaStream_t)stream;
+    p2tet_geo_kernel<<<grid_for(bp->n_cells, 128), 128, 0, s>>>(coords, cell_nodes, bp->n_cells, lam, ls, mu, ms,
+                                                                (double *)it.rec.p);
+    NFA_LAUNCH_CHECK();
+    const int tile_stride = (9 * it.max_tile_blocks + 2 + 15) & ~15;  // doubles; keeps both tiles 128-byte aligned
+    int nbuf = P2_NBUF;  // as many tiles as fit in 200 KB of shared memory, at most P2_NBUF
+    while (nbuf > 1 && sizeof(double) * nbuf * (size_t)tile_stride > 200 * 1024) --nbuf;
+    const size_t smem = sizeof(double) * nbuf * (size_t)tile_stride + sizeof(int) * (4 + 2 * nbuf);
+    if (smem > 220 * 1024) return fail("nfa_assemble_p2tet_elasticity: chunk tile exceeds the shared memory of an SM");
+    auto kern = p2tet_elasticity_kernel;
+    NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1, device = 0, n_sm = 148;
+    NFA_CUDA(cudaGetDevice(&device));
+    NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P2_THREADS, smem));
+    if (per_sm < 1) return fail("nfa_assemble_p2tet_elasticity: kernel does not fit on an SM");
+    const int64_t grid = std::min<int64_t>(it.n_chunks, (int64_t)n_sm * per_sm);
+    if (timing_enabled()) timing_begin(s);
+    kern<<<(unsigned)grid, P2_THREADS, smem, s>>>(nbuf, (int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
+                                                  (const int4 *)it.task_hdr.p, (const uint2 *)it.item_hdr.p,
+                                                  (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride, vals);
+    if (timing_enabled()) timing_end(s);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}

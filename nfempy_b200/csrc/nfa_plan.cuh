@@ -69,4 +69,14 @@ struct nfa_bplan {
                               // position in the chunk's cell order (= its staging slot)
     nfa::DevBuf indptr, indices;  // scalar CSR pattern int32
     nfa::DevBuf geo;              // scratch: per-cell geometry records [n_cells][12], rewritten every assembly
+    // Row-item lists of the vector-P2 tetrahedron kernel (nfa_p2tet.cu), built by nfempy_b200/assembly/p2_items.py
+    struct P2Items {
+        int64_t n_chunks = 0, n_tasks = 0, n_items = 0, ell_size = 0;
+        int max_tile_blocks = 0;
+        nfa::DevBuf chunk_hdr;  // int32 [n_chunks][4]: b0, n_blocks, task0, n_tasks
+        nfa::DevBuf task_hdr;   // int32 [n_tasks][4]: type | kmax << 8, ell_base, item_base, n_items
+        nfa::DevBuf item_hdr;   // uint16 [n_items][4]: tile offsets of up to three blocks, row pitch
+        nfa::DevBuf ell;        // uint32 [ell_size]: cell << 6 | i << 4 | j << 2 | x, 32 lanes interleaved
+        nfa::DevBuf rec;        // scratch: geometry records [n_cells][4][4], rewritten every assembly
+    } p2;
 };

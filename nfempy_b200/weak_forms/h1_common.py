@@ -27,6 +27,7 @@ class H1VolumeForm(BatchedWeakForm):
     coefficient_names = ()  # scalar coefficients, in kernel order
     load_name = "rhs"
     load_sign = 1.0
+    p2tet_kernel = None
 
     def _field(self):
         return self.space.discrete_spaces[self.field_name]
@@ -80,7 +81,14 @@ class H1VolumeForm(BatchedWeakForm):
             k: (torch.as_tensor(v[0]).to(dev.device), v[1], v[2], v[3]) for k, v in coefs.items()
         }
         f_dev = None if f is None else torch.as_tensor(np.ascontiguousarray(f, dtype=np.float64)).to(dev.device)
+        # the row-item kernel of vector-P2 tetrahedra scales by sqrt(det mu): it needs mu > 0 in every cell
+        p2tet_ok = bool(
+            self.p2tet_kernel and dim == 3 and s.ref_element.n_phi == 10 and s.n_comp == 3
+            and all(c[3] != "point" for c in coefs.values()) and float(np.min(coefs["mu"][0])) > 0.0
+            and np.all(np.isfinite(coefs["lambda"][0]))
+        )
         return FormData(
+            p2tet_ok=p2tet_ok,
             n_items=n, items=items, dim=dim, n_q=nq, n_phi=s.ref_element.n_phi, n_comp=s.n_comp, tab=tab, w=w,
             cell_nodes=cell_nodes, coefs=dev_coefs, f=f_dev,
         )
@@ -89,7 +97,10 @@ class H1VolumeForm(BatchedWeakForm):
     def fused_spec(self, data):
         if any(c[3] == "point" for c in data.coefs.values()):
             return None  # coefficients vary inside cells: quadrature-loop kernel + two-stage reduce
-        return {"kernel": self.fused_kernel, "coefs": [data.coefs[n] for n in self.coefficient_names]}
+        spec = {"kernel": self.fused_kernel, "coefs": [data.coefs[n] for n in self.coefficient_names]}
+        if data.get("p2tet_ok"):
+            spec["p2tet_kernel"] = self.p2tet_kernel
+        return spec
 
     def mref(self, dev):
         s = self._field()

@@ -16,6 +16,7 @@ class LEPrimalWeakForm(H1VolumeForm):
     load_name = "rhs"
     load_sign = 1.0
     fused_kernel = "nfa_assemble_h1_elasticity_affine"
+    p2tet_kernel = "nfa_assemble_p2tet_elasticity"
 
     def launch_local(self, dev, data, alpha_dev, dest_dev, Ke, re):
         lam, mu = data.coefs["lambda"], data.coefs["mu"]

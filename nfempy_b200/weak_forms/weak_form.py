@@ -46,6 +46,9 @@ class FormData:
     def __init__(self, **kw):
         self.__dict__.update(kw)
 
+    def get(self, name, default=None):
+        return self.__dict__.get(name, default)
+
 
 class BatchedWeakForm(WeakForm):
     form_kind = "form"  # "form": items index space.elements; "bc_form": items index bc_elements
