@@ -218,7 +218,8 @@ int nfa_bplan_block_pattern(const nfa_bplan *bp, int32_t *d_bptr, int32_t *d_bco
 int64_t nfa_bplan_n_blocks(const nfa_bplan *bp);
 int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *d_chunk_hdr, int64_t n_tasks,
                            const int32_t *d_task_hdr, int64_t n_items, const uint16_t *d_item_hdr, int64_t ell_size,
-                           const uint32_t *d_ell, int max_tile_blocks, nfa_stream stream);
+                           const uint32_t *d_ell, int max_tile_blocks, const int32_t *d_chunk_cells_ptr,
+                           int64_t n_chunk_cells, const int32_t *d_chunk_cells, nfa_stream stream);
 int nfa_bplan_has_p2_items(const nfa_bplan *bp);
 int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *d_coords, const int32_t *d_cell_nodes,
                                   const double *d_lambda, int64_t lambda_stride, const double *d_mu,

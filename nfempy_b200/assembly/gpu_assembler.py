@@ -197,13 +197,14 @@ class GPUAssembler:
         bptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev.device)
         bcols = torch.empty(n_blocks, dtype=torch.int32, device=dev.device)
         _lib.check(lib.nfa_bplan_block_pattern(p.bplan, _lib.ptr(bptr), _lib.ptr(bcols), stream), "nfa_bplan_block_pattern")
-        cap = int(os.environ.get("NFA_P2TET_CAP", "448"))
+        cap = int(os.environ.get("NFA_P2TET_CAP", "640"))
         items = p2_items.build(node_dest.to(torch.int64), bptr.to(torch.int64), bcols.to(torch.int64), n_nodes, cap=cap)
         _lib.check(
             lib.nfa_bplan_set_p2_items(
                 p.bplan, items["n_chunks"], _lib.ptr(items["chunk_hdr"]), items["n_tasks"], _lib.ptr(items["task_hdr"]),
                 items["n_items"], _lib.ptr(items["item_hdr"]), items["ell_size"], _lib.ptr(items["ell"]),
-                items["max_tile_blocks"], stream,
+                items["max_tile_blocks"], _lib.ptr(items["chunk_cells_ptr"]), items["n_chunk_cells"],
+                _lib.ptr(items["chunk_cells"]), stream,
             ),
             "nfa_bplan_set_p2_items",
         )

@@ -22,10 +22,11 @@ operations only (they run on the GPU for production sizes and on the CPU in the 
 
 Layout handed to the kernel:
   chunk_hdr  int32 [n_chunks, 4]   b0, n_blocks, task0, n_tasks      (chunk = contiguous block rows)
-  task_hdr   int32 [n_tasks, 4]    type | kmax << 8, ell_base, item_base, n_items (<= 32) | chunk << 6
+  task_hdr   int32 [n_tasks, 4]    type | kmax << 8 | (b0 & 1) << 16, ell_base, item_base, n_items (<= 32) | chunk << 6
   item_hdr   uint16 [n_items, 4]   tile offsets of the item's blocks (0xFFFF = unused), row pitch
   ell        uint32 [sum 32 kmax]  entry k of lane l of a task at ell_base + 32 k + l:
                                    cell << 6 | i << 4 | j << 2 | x   (0xFFFFFFFF = none)
+  chunk_cells_ptr int32 [n_chunks + 1], chunk_cells int32: the cells each chunk reads (L1 prefetch list)
 """
 import numpy as np
 import torch
@@ -78,7 +79,7 @@ def _templates():
 TEMPLATES = _templates()  # 4 * 7 + 6 * 4 = 52 entries per cell
 
 
-def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296):
+def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8):
     """``node_dest`` int64 [n_cells, 10] global node of each local P2 node, ``bptr``/``bcols`` the block CSR of the
     matrix (int64 tensors on the same device).  Returns a dict of tensors (see module docstring) and sizes."""
     dev = node_dest.device
@@ -129,13 +130,16 @@ def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296):
     # cell-major entry order so that a stable sort keeps ascending cells inside an item
     rowN, typ, code, item_blk = (v.t().reshape(-1) for v in (rowN, typ, code, item_blk))
     blk = blk.permute(1, 0, 2).reshape(-1, 3)
-    # a row belongs to the window its first block falls in; windows are then dealt round-robin into ``riffle`` groups
-    # so that a CTA's contiguous chunk range is a strided sample of the matrix (vertex and edge rows cost differently)
+    # a row belongs to the window its first block falls in; batches of ``batch`` consecutive windows (neighbouring rows:
+    # they share cells, so geometry records stay in L1) are then dealt round-robin into ``riffle`` groups so that a
+    # CTA's contiguous chunk range is a strided sample of the matrix (vertex and edge rows cost differently)
     win = bptr[:-1] // cap
     uniq_win = torch.unique(win[nb_row > 0])
     dense = torch.searchsorted(uniq_win, win)
-    per_group = (int(uniq_win.shape[0]) + riffle - 1) // riffle
-    chunk_of_row = (dense % riffle) * per_group + dense // riffle
+    q, r = dense // batch, dense % batch
+    n_batches = (int(uniq_win.shape[0]) + batch - 1) // batch
+    per_group = (n_batches + riffle - 1) // riffle
+    chunk_of_row = ((q % riffle) * per_group + q // riffle) * batch + r
     chunk_raw = chunk_of_row[rowN]
     key = (chunk_raw << 34) | (typ << 31) | item_blk
     if n_bnz >= (1 << 31):
@@ -217,12 +221,24 @@ def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296):
     task0 = torch.nonzero(tfirst_chunk).reshape(-1)
     ntask = torch.cat([task0[1:], torch.tensor([n_tasks], device=dev)]) - task0
     chunk_hdr = torch.stack([c_b0, c_b1 - c_b0, task0, ntask], dim=1)
-    task_hdr = torch.stack([task_type | (kmax << 8), ell_base, task_first_item, task_items | (chunk_index_of_task << 6)], dim=1)
+    # bit 16 of word 0: parity of the chunk's first block (the tile sits on the same 16-byte phase as its image)
+    task_hdr = torch.stack(
+        [task_type | (kmax << 8) | ((c_b0[chunk_index_of_task] & 1) << 16), ell_base, task_first_item,
+         task_items | (chunk_index_of_task << 6)], dim=1)
+    # cells each chunk reads (ascending, once each): the kernel prefetches the records of the next chunk into L1
+    entry_chunk = torch.searchsorted(chunk_ids, key >> 34)
+    cc = torch.unique((entry_chunk << 26) | (code >> 6))
+    cell_chunk = cc >> 26
+    chunk_cells = cc & ((1 << 26) - 1)
+    chunk_cells_ptr = torch.zeros(n_chunks + 1, dtype=torch.int64, device=dev)
+    chunk_cells_ptr[1:] = torch.cumsum(torch.bincount(cell_chunk, minlength=n_chunks), 0)
     max_tile = int((c_b1 - c_b0).max().item())
     return {
         "chunk_hdr": chunk_hdr.to(torch.int32).contiguous(),
         "task_hdr": task_hdr.to(torch.int32).contiguous(),
         "item_hdr": item_hdr.to(torch.int32).to(torch.uint16 if hasattr(torch, "uint16") else torch.int16).contiguous(),
+        "chunk_cells_ptr": chunk_cells_ptr.to(torch.int32).contiguous(),
+        "chunk_cells": chunk_cells.to(torch.int32).contiguous(), "n_chunk_cells": int(chunk_cells.shape[0]),
         "ell": (ell & NONE32).to(torch.uint32 if hasattr(torch, "uint32") else torch.int64).contiguous(),
         "n_chunks": n_chunks, "n_tasks": n_tasks, "n_items": n_items, "ell_size": ell_size, "max_tile_blocks": max_tile,
         "n_entries": int(key.shape[0]),
@@ -292,7 +308,8 @@ def walk(plan, rec, n_bnz):
     for ci, (b0, nblk, task0, ntask) in enumerate(chunk_hdr):
         tile = np.full(nblk * 9, np.nan)
         for t in range(task0, task0 + ntask):
-            typ, kmax = task_hdr[t, 0] & 0xFF, task_hdr[t, 0] >> 8
+            typ, kmax = task_hdr[t, 0] & 0xFF, (task_hdr[t, 0] >> 8) & 0xFF
+            assert (task_hdr[t, 0] >> 16) == (b0 & 1)
             base, item0, nit = task_hdr[t, 1], task_hdr[t, 2], task_hdr[t, 3] & 63
             assert task_hdr[t, 3] >> 6 == ci
             for lane in range(nit):

@@ -119,7 +119,7 @@ struct TileCtx {
     double *tile;
     volatile int *free_at;
     int need;
-    unsigned w0, w1, w2, pitch;
+    unsigned ihx, ihy;  // packed 16-bit tile offsets of the three blocks and the row pitch (decoded when storing)
     __device__ __forceinline__ void wait() const {
         if ((threadIdx.x & 31) == 0) {
             while (*free_at < need) __nanosleep(32);
@@ -128,7 +128,7 @@ struct TileCtx {
         __syncwarp();
     }
     __device__ __forceinline__ void put(int k, const double (&v)[9]) const {
-        store_block(tile, k == 0 ? w0 : (k == 1 ? w1 : w2), pitch, v);
+        store_block(tile, k == 0 ? (ihx & 0xFFFFu) : (k == 1 ? (ihx >> 16) : (ihy & 0xFFFFu)), ihy >> 16, v);
     }
 };
 
@@ -295,17 +295,18 @@ struct Item<5> {  // F: (E, E_opp) = -2/15 Kf(s s^T), since g_x + g_y = -(g_i + 
     }
 };
 
-// One task = up to 32 items of one type; lane = item.  e points at the lane's first ELL entry (stride 32).  Items that
-// read at most two records per cell keep two cells in flight (all 256-bit loads issued before the first is consumed);
-// type E (three records, 27 sums) walks one cell at a time to stay inside the register budget.
+// One task = up to 32 items of one type; lane = item.  e points at the lane's first ELL entry (stride 32); c0, c1 are
+// the lane's first two entries (fetched while the previous task was computed).  Items that read at most two records per
+// cell keep two cells in flight; type E (three records, 27 sums) walks one cell at a time to stay inside the register
+// budget.  pf0, pf1: first entries of the NEXT task -- their cells' records (one 128-byte line each) are pulled into L1
+// once this task's sums are complete.
 template <int TYPE>
-__device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kmax, const double *__restrict__ rec,
-                                         double *tile, volatile int *free_at, int need, unsigned ihx, unsigned ihy) {
-    const TileCtx ctx = {tile, free_at, need, ihx & 0xFFFFu, ihx >> 16, ihy & 0xFFFFu, ihy >> 16};
+__device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kmax, uint32_t c0, uint32_t c1,
+                                         const double *__restrict__ rec, uint32_t pf0, uint32_t pf1,
+                                         const TileCtx &ctx) {
     constexpr int NG = Item<TYPE>::NG;
     Item<TYPE> item;
     if constexpr (NG <= P2_UNROLL_NG) {
-        uint32_t c0 = __ldg(e), c1 = kmax > 1 ? __ldg(e + 32) : 0xFFFFFFFFu;
 #pragma unroll 1
         for (int k = 0; k < kmax; k += 2) {
             const Rec<NG> r0 = load_rec<NG>(c0, rec), r1 = load_rec<NG>(c1, rec);
@@ -315,14 +316,16 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
             if (r1.valid) item.add(r1);
         }
     } else {
-        uint32_t c0 = __ldg(e);
 #pragma unroll 1
         for (int k = 0; k < kmax; ++k) {
             const Rec<NG> r0 = load_rec<NG>(c0, rec);
-            c0 = (k + 1 < kmax) ? __ldg(e + 32 * (k + 1)) : 0xFFFFFFFFu;
+            c0 = c1;
+            c1 = (k + 2 < kmax) ? __ldg(e + 32 * (k + 2)) : 0xFFFFFFFFu;
             if (r0.valid) item.add(r0);
         }
     }
+    if (pf0 != 0xFFFFFFFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (size_t)(pf0 >> 6) * 16));
+    if (pf1 != 0xFFFFFFFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (size_t)(pf1 >> 6) * 16));
     ctx.wait();
     item.finish(ctx);
 }
@@ -330,10 +333,13 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
 // Warps of a CTA pull tasks from the CTA's contiguous chunk range through one shared counter; chunk c lives in tile
 // (c - c_begin) % NBUF.  The warp that finishes the last task of a chunk sends the tile to HBM with one bulk copy,
 // waits until the copy engine has read it and hands the tile to chunk c + NBUF.  No CTA-wide barrier in the loop.
+template <int LOG_NBUF>
 __global__ void __launch_bounds__(P2_THREADS, 1)
-    p2tet_elasticity_kernel(int NBUF, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
+    p2tet_elasticity_kernel(int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
                             const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
-                            const double *__restrict__ rec, int tile_stride, double *__restrict__ vals) {
+                            const double *__restrict__ rec, int tile_stride, const int32_t *__restrict__ cells_ptr,
+                            const int32_t *__restrict__ cells, double *__restrict__ vals) {
+    constexpr int NBUF = 1 << LOG_NBUF;
     extern __shared__ __align__(128) double smem[];  // NBUF tiles of tile_stride doubles, then the control words
     // ctrl: [0] next task, [1] c_begin, [2] c_end, [3] task_end, [4 .. 4+NBUF) tasks left per tile, then free_at per tile.
     // Everything the tail of an iteration needs is re-read from here / from the (L1-resident) headers instead of being
@@ -355,65 +361,64 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
         }
     }
     __syncthreads();
-    while (true) {
+    // software pipeline over tasks, per warp: while task i is computed, the header of task i+2 and the first two ELL
+    // entries of task i+1 are in flight, and the records task i+1 reads first are prefetched into L1
+    const int lane = threadIdx.x & 31;
+    const int task_end = ctrl[3];
+    const int4 none = make_int4(0, 0, 0, -1);
+    auto grab = [&]() {
         int t = 0;
-        if ((threadIdx.x & 31) == 0) t = atomicAdd(const_cast<int *>(ctrl), 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= ctrl[3]) break;
+        if (lane == 0) t = atomicAdd(const_cast<int *>(ctrl), 1);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    int4 th = none, th1 = none;
+    {
+        const int t0 = grab();
+        if (t0 < task_end) th = __ldg(task_hdr + t0);
+        const int t1 = grab();
+        if (t1 < task_end) th1 = __ldg(task_hdr + t1);
+    }
+    uint32_t c0 = 0xFFFFFFFFu, c1 = 0xFFFFFFFFu;
+    if (th.w != -1) {
+        const uint32_t *e = ell + (uint32_t)th.y + lane;
+        c0 = __ldg(e);
+        if (((th.x >> 8) & 0xFF) > 1) c1 = __ldg(e + 32);
+    }
+    while (th.w != -1) {
+        int4 th2 = none;
         {
-            const int lane = threadIdx.x & 31;
-            const int4 th = __ldg(task_hdr + t);
-            const int type = th.x & 0xFF, kmax = th.x >> 8, n_items = th.w & 63, c = (int)((unsigned)th.w >> 6);
+            const int t2 = grab();
+            if (t2 < task_end) th2 = __ldg(task_hdr + t2);
+        }
+        uint32_t n0 = 0xFFFFFFFFu, n1 = 0xFFFFFFFFu;  // first entries of task i+1
+        if (th1.w != -1) {
+            const uint32_t *e1 = ell + (uint32_t)th1.y + lane;
+            n0 = __ldg(e1);
+            if (((th1.x >> 8) & 0xFF) > 1) n1 = __ldg(e1 + 32);
+        }
+        {
+            const int type = th.x & 0xFF, kmax = (th.x >> 8) & 0xFF, n_items = th.w & 63, c = (int)((unsigned)th.w >> 6);
             const uint32_t *e = ell + (uint32_t)th.y + lane;
             uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
             if (lane < n_items) ih = __ldg(item_hdr + th.z + lane);
-            const int it = c - ctrl[1], b = it % NBUF;
-            const int b0 = __ldg(chunk_hdr + c).x;
-            double *tile = smem + (size_t)b * tile_stride + (b0 & 1);  // same 16-byte phase as the tile's image in vals
-#ifdef P2_ONLY
-            run_task<P2_ONLY>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
-#else
+            const int it = c - ctrl[1], b = it & (NBUF - 1);
+            // the tile sits on the same 16-byte phase as its image in vals (parity of the chunk's first block)
+            double *tile = smem + (size_t)b * tile_stride + ((th.x >> 16) & 1);
+            const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it >> LOG_NBUF, ih.x, ih.y};
             switch (type) {
-                case 0:
-                asm volatile("// item type 0 begin" ::: "memory");
-                run_task<0>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
-                asm volatile("// item type 0 end" ::: "memory");
-                break;
-                case 1:
-                asm volatile("// item type 1 begin" ::: "memory");
-                run_task<1>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
-                asm volatile("// item type 1 end" ::: "memory");
-                break;
-                case 2:
-                asm volatile("// item type 2 begin" ::: "memory");
-                run_task<2>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
-                asm volatile("// item type 2 end" ::: "memory");
-                break;
-                case 3:
-                asm volatile("// item type 3 begin" ::: "memory");
-                run_task<3>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
-                asm volatile("// item type 3 end" ::: "memory");
-                break;
-                case 4:
-                asm volatile("// item type 4 begin" ::: "memory");
-                run_task<4>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
-                asm volatile("// item type 4 end" ::: "memory");
-                break;
-                default:
-                asm volatile("// item type 5 begin" ::: "memory");
-                run_task<5>(e, kmax, rec, tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y);
-                asm volatile("// item type 5 end" ::: "memory");
-                break;
+                case 0: run_task<0>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 1: run_task<1>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 2: run_task<2>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 3: run_task<3>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 4: run_task<4>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                default: run_task<5>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
             }
-#endif
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
-            int w;
-            asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(w) : "l"(reinterpret_cast<const int *>(task_hdr + t) + 3));
-            const int c = (int)((unsigned)w >> 6), c_begin = ctrl[1], c_end = ctrl[2];
-            const int it = c - c_begin, b = it % NBUF;
+            const int c = (int)((unsigned)th.w >> 6), c_begin = ctrl[1], c_end = ctrl[2];
+            const int it = c - c_begin, b = it & (NBUF - 1);
             __threadfence_block();
             if (atomicSub(const_cast<int *>(ctrl) + 4 + b, 1) == 1) {  // the chunk's last task: the tile is complete
                 __threadfence_block();
@@ -435,9 +440,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 ctrl[4 + b] = (c + NBUF < c_end) ? __ldg(chunk_hdr + c + NBUF).w : 0;
                 __threadfence_block();
-                ctrl[4 + NBUF + b] = it / NBUF + 1;
+                ctrl[4 + NBUF + b] = (it >> LOG_NBUF) + 1;
             }
         }
+        th = th1;
+        th1 = th2;
+        c0 = n0;
+        c1 = n1;
     }
     if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -456,7 +465,9 @@ extern "C" int64_t nfa_bplan_n_blocks(const nfa_bplan *bp) { return bp ? bp->n_b
 
 extern "C" int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *chunk_hdr, int64_t n_tasks,
                                       const int32_t *task_hdr, int64_t n_items, const uint16_t *item_hdr,
-                                      int64_t ell_size, const uint32_t *ell, int max_tile_blocks, nfa_stream stream) {
+                                      int64_t ell_size, const uint32_t *ell, int max_tile_blocks,
+                                      const int32_t *chunk_cells_ptr, int64_t n_chunk_cells, const int32_t *chunk_cells,
+                                      nfa_stream stream) {
     if (!bp) return fail("nfa_bplan_set_p2_items: plan is NULL");
     if (bp->n_phi != 10 || bp->n_comp != 3) return fail("nfa_bplan_set_p2_items: plan is not vector-P2 on tetrahedra");
     if (n_chunks <= 0 || n_tasks <= 0 || n_items <= 0 || ell_size <= 0 || max_tile_blocks <= 0)
@@ -465,8 +476,12 @@ extern "C" int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int
     cudaStream_t s = (cudaStream_t)stream;
     nfa_bplan::P2Items &it = bp->p2;
     if (it.chunk_hdr.alloc(16 * n_chunks) || it.task_hdr.alloc(16 * n_tasks) || it.item_hdr.alloc(8 * n_items) ||
-        it.ell.alloc(4 * ell_size) || it.rec.alloc(sizeof(double) * 16 * bp->n_cells))
+        it.ell.alloc(4 * ell_size) || it.rec.alloc(sizeof(double) * 16 * bp->n_cells) ||
+        it.cells_ptr.alloc(4 * (n_chunks + 1)) || it.cells.alloc(4 * std::max<int64_t>(n_chunk_cells, 1)))
         return 2;
+    if (!chunk_cells_ptr || !chunk_cells) return fail("nfa_bplan_set_p2_items: prefetch lists missing");
+    NFA_CUDA(cudaMemcpyAsync(it.cells_ptr.p, chunk_cells_ptr, 4 * (n_chunks + 1), cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaMemcpyAsync(it.cells.p, chunk_cells, 4 * n_chunk_cells, cudaMemcpyDeviceToDevice, s));
     NFA_CUDA(cudaMemcpyAsync(it.chunk_hdr.p, chunk_hdr, 16 * n_chunks, cudaMemcpyDeviceToDevice, s));
     NFA_CUDA(cudaMemcpyAsync(it.task_hdr.p, task_hdr, 16 * n_tasks, cudaMemcpyDeviceToDevice, s));
     NFA_CUDA(cudaMemcpyAsync(it.item_hdr.p, item_hdr, 8 * n_items, cudaMemcpyDeviceToDevice, s));
@@ -493,11 +508,12 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
                                                                 (double *)it.rec.p);
     NFA_LAUNCH_CHECK();
     const int tile_stride = (9 * it.max_tile_blocks + 2 + 15) & ~15;  // doubles; keeps both tiles 128-byte aligned
-    int nbuf = P2_NBUF;  // as many tiles as fit in 200 KB of shared memory, at most P2_NBUF
-    while (nbuf > 1 && sizeof(double) * nbuf * (size_t)tile_stride > 200 * 1024) --nbuf;
+    int log_nbuf = 2;  // 4, 2 or 1 tiles: as many as fit in 200 KB of shared memory
+    while (log_nbuf > 0 && sizeof(double) * ((size_t)tile_stride << log_nbuf) > 200 * 1024) --log_nbuf;
+    const int nbuf = 1 << log_nbuf;
     const size_t smem = sizeof(double) * nbuf * (size_t)tile_stride + sizeof(int) * (4 + 2 * nbuf);
     if (smem > 220 * 1024) return fail("nfa_assemble_p2tet_elasticity: chunk tile exceeds the shared memory of an SM");
-    auto kern = p2tet_elasticity_kernel;
+    auto kern = log_nbuf == 2 ? p2tet_elasticity_kernel<2> : (log_nbuf == 1 ? p2tet_elasticity_kernel<1> : p2tet_elasticity_kernel<0>);
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, device = 0, n_sm = 148;
     NFA_CUDA(cudaGetDevice(&device));
@@ -506,9 +522,10 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     if (per_sm < 1) return fail("nfa_assemble_p2tet_elasticity: kernel does not fit on an SM");
     const int64_t grid = std::min<int64_t>(it.n_chunks, (int64_t)n_sm * per_sm);
     if (timing_enabled()) timing_begin(s);
-    kern<<<(unsigned)grid, P2_THREADS, smem, s>>>(nbuf, (int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
+    kern<<<(unsigned)grid, P2_THREADS, smem, s>>>((int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
                                                   (const int4 *)it.task_hdr.p, (const uint2 *)it.item_hdr.p,
-                                                  (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride, vals);
+                                                  (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride,
+                                                  (const int32_t *)it.cells_ptr.p, (const int32_t *)it.cells.p, vals);
     if (timing_enabled()) timing_end(s);
     NFA_LAUNCH_CHECK();
     return 0;

@@ -77,6 +77,8 @@ struct nfa_bplan {
         nfa::DevBuf task_hdr;   // int32 [n_tasks][4]: type | kmax << 8, ell_base, item_base, n_items
         nfa::DevBuf item_hdr;   // uint16 [n_items][4]: tile offsets of up to three blocks, row pitch
         nfa::DevBuf ell;        // uint32 [ell_size]: cell << 6 | i << 4 | j << 2 | x, 32 lanes interleaved
+        nfa::DevBuf cells_ptr;  // int32 [n_chunks + 1], cells: int32: cells each chunk reads (L1 prefetch lists)
+        nfa::DevBuf cells;
         nfa::DevBuf rec;        // scratch: geometry records [n_cells][4][4], rewritten every assembly
     } p2;
 };

@@ -68,6 +68,16 @@ def test_item_plan_reproduces_the_block_sums(n, cap, riffle):
     hdr = hdr[np.argsort(hdr[:, 0])]  # chunks tile the block range exactly once (they are listed in riffled order)
     assert hdr[0, 0] == 0 and hdr[:, 1].sum() == len(keys) and np.all(hdr[1:, 0] == hdr[:-1, 0] + hdr[:-1, 1])
     assert np.all(hdr[:, 1] <= cap + np.diff(bptr).max())
+    # prefetch lists: exactly the cells the chunk's entries name
+    ell = plan["ell"].numpy().astype(np.int64) & 0xFFFFFFFF
+    cptr, ccells = plan["chunk_cells_ptr"].numpy(), plan["chunk_cells"].numpy()
+    th = plan["task_hdr"].numpy().astype(np.int64)
+    for ci, (_, _, task0, ntask) in enumerate(plan["chunk_hdr"].numpy()):
+        seen = set()
+        for t in range(task0, task0 + ntask):
+            seg = ell[th[t, 1] : th[t, 1] + 32 * ((th[t, 0] >> 8) & 0xFF)]
+            seen.update((seg[seg != 0xFFFFFFFF] >> 6).tolist())
+        assert sorted(seen) == ccells[cptr[ci] : cptr[ci + 1]].tolist()
 
 
 def test_item_plan_entries_are_in_ascending_cell_order():
@@ -76,7 +86,7 @@ def test_item_plan_entries_are_in_ascending_cell_order():
     plan = p2_items.build(torch.as_tensor(node_dest), torch.as_tensor(bptr), torch.as_tensor(bcols), n_nodes)
     ell = plan["ell"].numpy().astype(np.int64) & 0xFFFFFFFF
     for typ_k, base, item0, nit in plan["task_hdr"].numpy():
-        kmax, nit = typ_k >> 8, nit & 63
+        kmax, nit = (typ_k >> 8) & 0xFF, nit & 63
         for lane in range(nit):
             cells = [ell[base + 32 * k + lane] >> 6 for k in range(kmax) if ell[base + 32 * k + lane] != 0xFFFFFFFF]
             assert cells == sorted(cells) and len(set(cells)) == len(cells) and len(cells) >= 1
