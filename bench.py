@@ -302,13 +302,14 @@ def run_graft(args):
     kernel_ms = k_ms.value / max(k_n.value, 1)
     achieved = b_kernel * n_cells / (kernel_ms * 1e-3) / 1e9
     traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
-    tpath = os.path.join(ROOT, "profiles", "r01_fused_h1_traffic.json")
+    row_items = bool(getattr(plan, "p2_stats", None))
+    tpath = os.path.join(ROOT, "profiles", "r01_p2tet_traffic.json" if row_items else "r01_fused_h1_traffic.json")
     if os.path.exists(tpath) and args.n == 55 and world == 1:
         traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "algorithmic_bytes_per_launch": b_kernel * n_cells,
-        "kernel": "fused_h1_kernel<3,0>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_tet": b_kernel,
+        "kernel": "p2tet_elasticity_kernel" if row_items else "fused_h1_kernel<3,0>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_tet": b_kernel,
         "peak_source": peak_src, "step_frac": b_step * n_cells / (ms_step * 1e-3) / 1e9 / peak,
         "step_algorithmic_bytes_per_tet": b_step,
     }
@@ -337,7 +338,7 @@ def run_graft(args):
                 "nonzeros_per_s": nnz * world / (ms_step * 1e-3),
                 "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % ((b_step * n_cells + 6 * 100 * n_cells) / 1e9),
                 "plan_build_s": plan.build_seconds, "host_mesh_space_s": t_host, "prepare_s": t_prepare,
-                "path": "fused" if plan.fused_index is not None else "two-stage",
+                "path": ("fused (row items)" if row_items else "fused") if plan.fused_index is not None else "two-stage",
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

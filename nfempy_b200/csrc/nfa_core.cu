@@ -1,4 +1,5 @@
 // libnfa: error state, geometry (K1) and the quadrature-loop H1 local kernels (K2, K5).  sm_100a.
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <utility>
@@ -425,6 +426,118 @@ __global__ void __launch_bounds__(1024, 1)
     }
 }
 
+// Streaming variant for the common element sizes: the premultiplied table w_q phi_a(q) sits in constant memory (DFMA
+// reads it as an operand: no load instruction), a thread owns (cell, component), reads its N_Q load values from the
+// shared-memory tile and keeps the N_PHI sums in registers.  Tiles of TILE cells (one contiguous span of f) arrive by
+// bulk asynchronous copies (cp.async.bulk global -> shared, mbarrier completion), double buffered.  HBM-bound on f.
+__constant__ double c_load_wt[64 * 20];
+
+template <int DIM, int N_PHI, int N_COMP, int TILE>
+__global__ void __launch_bounds__(TILE *N_COMP)
+    local_h1_load_stream_kernel(int n_q, const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
+                                int64_t n_cells, const double *__restrict__ f, double sign, double *__restrict__ re) {
+    extern __shared__ __align__(128) double smem[];  // two tiles [TILE][n_q][N_COMP], then two mbarriers
+    const int fn = n_q * N_COMP;
+    const int tile_doubles = TILE * fn;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * (size_t)tile_doubles);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bar);
+    const int lc = threadIdx.x / N_COMP, comp = threadIdx.x - lc * N_COMP;
+    const int64_t n_tiles = (n_cells + TILE - 1) / TILE;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int64_t tl, int buf) {  // thread 0 only
+        const int64_t c0 = tl * TILE;
+        const int nc_here = (int)((n_cells - c0) < TILE ? (n_cells - c0) : TILE);
+        const int n_dbl = nc_here * fn;
+        const uint32_t bytes = (uint32_t)((n_dbl & ~1) * 8);  // bulk copies move multiples of 16 bytes
+        double *tile = smem + (size_t)buf * tile_doubles;
+        if (n_dbl & 1) tile[n_dbl - 1] = __ldg(f + c0 * fn + n_dbl - 1);  // odd tail (last tile only), see the loop
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * buf), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+            "l"(f + c0 * fn), "r"(bytes), "r"(bar0 + 8 * buf)
+            : "memory");
+    };
+    if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    int buf = 0;
+    uint32_t phases = 0u;  // bit b = parity the next wait on tile b expects
+    for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, buf ^= 1) {
+        const int64_t next = tl + gridDim.x;
+        if (threadIdx.x == 0 && next < n_tiles) issue(next, buf ^ 1);  // the other tile was released by the barrier below
+        const int64_t c0 = tl * TILE;
+        const int nc_here = (int)((n_cells - c0) < TILE ? (n_cells - c0) : TILE);
+        double det = 0.0;
+        if (lc < nc_here) {
+            double X[DIM + 1][3];
+            load_cell_coords<DIM>(coords, cell_nodes, c0 + lc, X);
+            det = compute_det<DIM>(X);
+        }
+        {  // wait for this tile's bytes
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar0 + 8 * buf), "r"((phases >> buf) & 1u)
+                    : "memory");
+            }
+            phases ^= 1u << buf;
+        }
+        if ((nc_here * fn) & 1) __syncthreads();  // the odd tail element was written by thread 0 with a plain store
+        if (lc < nc_here) {
+            const double *fc = smem + (size_t)buf * tile_doubles + lc * fn + comp;
+            double acc[N_PHI];
+#pragma unroll
+            for (int a = 0; a < N_PHI; ++a) acc[a] = 0.0;
+            for (int q = 0; q < n_q; ++q) {
+                const double v = fc[q * N_COMP];
+#pragma unroll
+                for (int a = 0; a < N_PHI; ++a) acc[a] = fma(c_load_wt[q * N_PHI + a], v, acc[a]);
+            }
+            double *dst = re + (c0 + lc) * (N_PHI * N_COMP) + comp;
+            const double sc = sign * det;
+#pragma unroll
+            for (int a = 0; a < N_PHI; ++a) dst[a * N_COMP] = sc * acc[a];
+        }
+        __syncthreads();  // every reader of this tile is done: it may be refilled on the next trip
+    }
+}
+
+__global__ void load_wt_kernel(int n, int n_phi, const double *__restrict__ tab0, const double *__restrict__ weights,
+                               double *__restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = weights[i / n_phi] * tab0[i];
+}
+
+template <int DIM, int N_PHI, int N_COMP>
+static int launch_h1_load_stream(int n_q, const double *tab0, const double *weights, const double *coords,
+                                 const int32_t *cell_nodes, int64_t n_cells, const double *f, double sign, double *re,
+                                 cudaStream_t s) {
+    constexpr int TILE = 64;
+    double *wt = nullptr;
+    NFA_CUDA(cudaGetSymbolAddress((void **)&wt, c_load_wt));
+    load_wt_kernel<<<grid_for(n_q * N_PHI, 128), 128, 0, s>>>(n_q * N_PHI, N_PHI, tab0, weights, wt);
+    NFA_LAUNCH_CHECK();
+    const size_t smem = sizeof(double) * 2 * (size_t)TILE * n_q * N_COMP + 16;
+    auto kern = local_h1_load_stream_kernel<DIM, N_PHI, N_COMP, TILE>;
+    NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1, device = 0, n_sm = 148;
+    NFA_CUDA(cudaGetDevice(&device));
+    NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE * N_COMP, smem));
+    if (per_sm < 1) return fail("nfa_local_h1_load: streaming kernel does not fit on an SM");
+    const int64_t tiles = (n_cells + TILE - 1) / TILE;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)n_sm * per_sm);
+    kern<<<grid, TILE * N_COMP, smem, s>>>(n_q, coords, cell_nodes, n_cells, f, sign, re);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int DIM>
 static int launch_h1_load(int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,
                           const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *f, double sign,
@@ -449,6 +562,15 @@ extern "C" int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const 
                                  double sign, double *re, nfa_stream stream) {
     if (n_cells == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
+    // streaming kernel: tiles of 64 cells of f start 16-byte aligned whatever n_q * n_comp is
+    if (f && n_q <= 64) {
+        if (dim == 3 && n_phi == 10 && n_comp == 3)
+            return launch_h1_load_stream<3, 10, 3>(n_q, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);
+        if (dim == 3 && n_phi == 4 && n_comp == 3)
+            return launch_h1_load_stream<3, 4, 3>(n_q, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);
+        if (dim == 2 && n_phi == 6 && n_comp == 2)
+            return launch_h1_load_stream<2, 6, 2>(n_q, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);
+    }
     if (dim == 3) return launch_h1_load<3>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);
     if (dim == 2) return launch_h1_load<2>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);
     if (dim == 1) return launch_h1_load<1>(n_phi, n_q, n_comp, tab0, weights, coords, cell_nodes, n_cells, f, sign, re, s);

@@ -56,8 +56,10 @@ __global__ void p2tet_geo_kernel(const double *__restrict__ coords, const int32_
     load_cell_coords<3>(coords, cell_nodes, cell, X);
     Geom<3> g;
     compute_geom<3>(X, g);
+    // mu > 0 is the caller's contract; cells with lambda = mu = 0 (the halo cells of a rank's local plan, whose
+    // coefficients the sharded assembler zeroes) contribute exact zeros
     const double m = mu[cell * ms], l = lam[cell * ls];
-    const double sc = sqrt(g.det * m), rho = l / m;
+    const double sc = m > 0.0 ? sqrt(g.det * m) : 0.0, rho = m > 0.0 ? l / m : 0.0;
     double *r = rec + cell * 16;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll

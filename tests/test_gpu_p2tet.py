@@ -70,3 +70,23 @@ def test_non_positive_mu_falls_back_to_the_generic_kernel():
     new, _ = _assemble(n, lam, mu, True)
     ref, _ = _assemble(n, lam, mu, False)
     compare_csr(new, ref, RTOL)
+
+
+@pytest.mark.parametrize("n_take", [47, 129])
+def test_odd_cell_subsets_through_the_streaming_load_kernel(n_take):
+    """An odd number of cells makes the last tile of the load stream end on an 8-byte (not 16-byte) boundary; the
+    sub-sequence also exercises row items on a partially assembled mesh.  Checked against the oracle."""
+    from nfempy_b200.assembly import GPUAssembler
+    from oracle import ref_assembly, ref_forms
+
+    case = elasticity_case(n=3, with_bc=False)
+    space, rspace = case.space(), case.ref_space()
+    forms = case.gpu_forms(space, np.zeros(space.n_dof))
+    forms["volume"][1] = list(range(n_take))
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+    asm.form_to_input_list = forms
+    got = asm.assemble()
+    kind, fn, functions, _ = case.ref_forms_fn(rspace)[0]
+    ref = ref_assembly.assemble(rspace, [(kind, fn, functions, list(range(n_take)))], np.zeros(rspace.n_dof))
+    # the GPU matrix keeps the full n_dof rows; rows never touched are empty in both
+    compare_csr(got, ref, RTOL)

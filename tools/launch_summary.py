@@ -19,7 +19,7 @@ def short(n):
     return n[:90]
 
 
-fused = [i for i, n in enumerate(names) if "fused_h1_kernel" in n]
+fused = [i for i, n in enumerate(names) if "fused_h1_kernel" in n or "p2tet_elasticity_kernel" in n]
 print("launches:", len(rows), "unit:", units, "fused launches:", len(fused))
 if len(fused) >= 2:
     # one step = from the geo_records launch preceding a fused launch up to the next one
