@@ -204,6 +204,41 @@ int nfa_assemble_h1_laplace_affine(const nfa_bplan *bp, int dim, const double *d
                                    double *d_vals, nfa_stream stream);
 
 
+/* ---- mixed "tensor" forms: row-wise H(div) stresses with vector L2 multipliers (config 4).  One local kernel for the
+ * block structure of the reference's vectorised forms LEDualWeakForm (R/src/weak_forms/le_dual_weak_form.py:354-510),
+ * LCEDualWeakForm (lce_dual_weak_form.py:410-648), LCEScaledDualWeakForm (lce_scaled_dual_weak_form.py:445-699) and the
+ * Riesz-map forms (le_riesz_map_weak_form.py:258-360, lce_riesz_map_weak_form.py:372-546,
+ * lce_scaled_riesz_map_weak_form.py:415-598).  Local dofs [H(div) 0 | H(div) 1 | L2 0 | L2 1], basis-major,
+ * component-minor.  All arrays are device pointers; per-point coefficient arrays are [n_cells, n_q] (g: [.., dim],
+ * load: [.., n_comp]) and optional (NULL = term absent; h_div_cd NULL = 1).
+ *   (F,F)  int a_id (psi_a.psi_b) d_cc' + a_tr psi_b[c] psi_a[c'] + a_vol psi_a[c] psi_b[c'] + a_dd div psi_a div psi_b d_cc'
+ *   (U,F)  div_coupling: d_cc' int w phi_k (cd div^ psi_a + det g.psi_a);  asym_coupling: int w det phi_k eps(c,c',d) psi_a[d]
+ *   (U,U)  d_cc' int a_mass phi_k phi_l;   r_U = -int load_c phi_k;   r += J alpha[dest] when alpha is given. */
+typedef struct nfa_tensor_form {
+    int32_t dim, n_q, n_hdiv, n_l2;
+    const double *weights;                             /* [n_q] */
+    int32_t h_n_phi[2], h_n_comp[2], h_nfd[2];
+    const double *h_val[2], *h_div[2], *h_Tcases[2];   /* reference values [n_q,n_phi,dim], reference divergence, T cases */
+    const int8_t *h_cases[2];                          /* [n_cells, dim+1] orientation case of every facet */
+    const double *h_a_id[2], *h_a_tr[2], *h_a_vol[2], *h_a_dd[2];
+    const double *h_div_cd[2], *h_div_g[2];
+    int32_t l_n_phi[2], l_n_comp[2];
+    const double *l_val[2], *l_a_mass[2], *l_load[2];
+    int32_t div_coupling[2][2], asym_coupling[2][2];   /* [L2 field][H(div) field] */
+} nfa_tensor_form;
+int nfa_local_hdiv_tensor(const nfa_tensor_form *form, const double *d_coords, const int32_t *d_cell_nodes,
+                          int64_t n_cells, const double *d_alpha, const int32_t *d_dest, double *d_Ke, double *d_re,
+                          nfa_stream stream);
+/* Natural boundary load of one H(div) field with n_comp rows: re[facet, re_off + a n_comp + c] = sign int_F g_c (psi_a.n)
+ * over the facet dofs of the first neighbour (the vector-valued form of nfa_local_hdiv_facet; LCEDualWeakFormBCDirichlet
+ * R/src/weak_forms/lce_dual_weak_form.py:651-756, LEDualWeakFormBCDirichlet le_dual_weak_form.py:513-578).
+ * g [n_facets, n_q, n_comp]; re rows have re_stride entries. */
+int nfa_local_hdiv_facet_vec(int dim, int nfd, int n_q, int n_comp, const double *d_trace_tab, const int32_t *d_tidx,
+                             const double *d_weights, const double *d_Tcases, const int8_t *d_cases,
+                             const double *d_coords, const int32_t *d_facet_nodes, const int32_t *d_neigh_nodes,
+                             const double *d_normals, const double *d_g, int64_t n_facets, double sign, int re_off,
+                             int re_stride, double *d_re, nfa_stream stream);
+
 /* ---- row-item fused path for vector-P2 elasticity on affine tetrahedra (config 2's headline kernel).
  * Same plan object, same output (all nnz values of the pattern, written once, deterministic) as
  * nfa_assemble_h1_elasticity_affine, i.e. the matrix part of LEPrimalWeakForm.evaluate_form

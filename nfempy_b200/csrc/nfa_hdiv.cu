@@ -270,8 +270,9 @@ __global__ void __launch_bounds__(128)
                             const int8_t *__restrict__ cases, const double *__restrict__ coords,
                             const int32_t *__restrict__ facet_nodes, const int32_t *__restrict__ neigh_nodes,
                             const double *__restrict__ normals, const double *__restrict__ pd, int64_t n_facets,
-                            double *__restrict__ re) {
+                            double *__restrict__ re, int n_comp = 1, double sign = 1.0, int re_off = 0, int re_stride = 0) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (re_stride == 0) re_stride = nfd;
     for (int64_t fc = (int64_t)blockIdx.x * 4 + warp; fc < n_facets; fc += (int64_t)gridDim.x * 4) {
         double X[DIM + 1][3];
         load_cell_coords<DIM>(coords, neigh_nodes, fc, X);
@@ -295,7 +296,8 @@ __global__ void __launch_bounds__(128)
             for (int c = 0; c < DIM; ++c) v += g.J[c][k] * normals[fc * 3 + c];
             jn[k] = v / g.det;
         }
-        for (int k = lane; k < nfd; k += 32) {
+        for (int kc = lane; kc < nfd * n_comp; kc += 32) {
+            const int k = kc / n_comp, c = kc - k * n_comp;
             double acc = 0.0;
             for (int q = 0; q < n_q; ++q) {
                 double flux = 0.0;
@@ -306,9 +308,9 @@ __global__ void __launch_bounds__(128)
                     for (int kk = 0; kk < DIM; ++kk) t += jn[kk] * src[kk];
                     flux += T[k * nfd + b] * t;
                 }
-                acc += det_f * weights[q] * pd[fc * n_q + q] * flux;
+                acc += det_f * weights[q] * pd[(fc * n_q + q) * n_comp + c] * flux;
             }
-            re[fc * nfd + k] = acc;
+            re[fc * re_stride + re_off + kc] = sign * acc;
         }
     }
 }
@@ -592,6 +594,32 @@ extern "C" int nfa_local_hdiv_l2_general(int dim, int n_u, int n_p, int n_q, int
                                      n_cells, c_uu, c_d, gvec, c_pp, load_p, alpha, beta, dest, s_u, s_p, Ke, re);
     } else
         return fail("nfa_local_hdiv_l2_general: dim must be 2 or 3");
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+
+extern "C" int nfa_local_hdiv_facet_vec(int dim, int nfd, int n_q, int n_comp, const double *trace_tab,
+                                        const int32_t *tidx, const double *weights, const double *Tcases,
+                                        const int8_t *cases, const double *coords, const int32_t *facet_nodes,
+                                        const int32_t *neigh_nodes, const double *normals, const double *g,
+                                        int64_t n_facets, double sign, int re_off, int re_stride, double *re,
+                                        nfa_stream stream) {
+    if (n_facets == 0) return 0;
+    if (n_comp < 1 || re_stride < re_off + nfd * n_comp) return fail("nfa_local_hdiv_facet_vec: bad output layout");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t ctas = (n_facets + 3) / 4;
+    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
+    if (dim == 3)
+        local_hdiv_facet_kernel<3><<<grid, 128, 0, s>>>(nfd, n_q, trace_tab, tidx, weights, Tcases, cases, coords,
+                                                        facet_nodes, neigh_nodes, normals, g, n_facets, re, n_comp, sign,
+                                                        re_off, re_stride);
+    else if (dim == 2)
+        local_hdiv_facet_kernel<2><<<grid, 128, 0, s>>>(nfd, n_q, trace_tab, tidx, weights, Tcases, cases, coords,
+                                                        facet_nodes, neigh_nodes, normals, g, n_facets, re, n_comp, sign,
+                                                        re_off, re_stride);
+    else
+        return fail("nfa_local_hdiv_facet_vec: dim must be 2 or 3");
     NFA_LAUNCH_CHECK();
     return 0;
 }

@@ -1,0 +1,269 @@
+// libnfa: local matrices of the mixed "tensor" forms -- row-wise H(div) stresses with vector L2 multipliers (sm_100a).
+//
+// One kernel covers the block structure shared by the reference's vectorised weakly-symmetric mixed forms
+//   LEDualWeakForm.evaluate_form_vectorized          R/src/weak_forms/le_dual_weak_form.py:354-510        (s, u, t)
+//   LCEDualWeakForm.evaluate_form_vectorized         R/src/weak_forms/lce_dual_weak_form.py:410-648       (s, m, u, t)
+//   LCEScaledDualWeakForm.evaluate_form_vectorized   R/src/weak_forms/lce_scaled_dual_weak_form.py:445-699
+//   LERieszMapWeakForm / LCE(Scaled)RieszMapWeakForm .evaluate_form_vectorized (block-diagonal norm matrices)
+// Local dofs: [H(div) field 0 | H(div) field 1 | L2 field 0 | L2 field 1], basis-major, component-minor; dof (a, c) of
+// an H(div) field is row c of the tensor built from the vector function psi_a (contravariant Piola + orientation).
+//   (F, F)   int A_id (psi_a.psi_b) d_cc' + A_tr psi_b[c] psi_a[c'] + A_vol psi_a[c] psi_b[c'] + A_dd div psi_a div psi_b d_cc'
+//   (U, F)   d_cc' int w phi_k (c_d div^ psi_a + det g.psi_a)        generalised divergence coupling (c_d = 1, g = 0: plain)
+//            + int w det phi_k sum_d eps(c, c', d) psi_a[d]           asymmetry coupling (rotation x stress)
+//   (U, U)   d_cc' int A_m phi_k phi_l
+//   r_U      -int load_c phi_k  (+ J alpha when a state is given)
+// All coefficients are host-evaluated per quadrature point.  One CTA per cell: the mapped bases are staged in shared
+// memory, threads stride the n_loc^2 entries.  Output goes to the two-stage reduce (nfa_plan_reduce).
+#include "nfa_common.cuh"
+
+using namespace nfa;
+
+namespace {
+
+struct TensorDev {  // device copy of nfa_tensor_form, pointers already device pointers
+    nfa_tensor_form f;
+};
+
+__device__ __forceinline__ double levi_civita(int a, int b, int c) {
+    if (a == b || b == c || a == c) return 0.0;
+    return ((b - a + 3) % 3 == 1) ? 1.0 : -1.0;  // (a, b, c) cyclic -> +1
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128)
+    local_hdiv_tensor_kernel(const nfa_tensor_form P, const double *__restrict__ coords,
+                             const int32_t *__restrict__ cell_nodes, int64_t n_cells, const double *__restrict__ alpha,
+                             const int32_t *__restrict__ dest, double *__restrict__ Ke, double *__restrict__ re) {
+    constexpr int NF = DIM + 1;
+    extern __shared__ double smem[];
+    const int n_q = P.n_q;
+    // shared-memory layout
+    double *s_psi[2], *s_div[2], *s_gd[2];
+    double *cur = smem;
+    int off_h[2], off_l[2], n_loc = 0;
+    for (int h = 0; h < 2; ++h) {
+        const int np = h < P.n_hdiv ? P.h_n_phi[h] : 0;
+        s_psi[h] = cur;
+        cur += (size_t)n_q * np * DIM;  // mapped values [q][a][c]
+        s_div[h] = cur;
+        cur += (size_t)n_q * np;  // physical divergence [q][a]
+        s_gd[h] = cur;
+        cur += (size_t)n_q * np;  // generalised divergence x det [q][a]
+        off_h[h] = n_loc;
+        n_loc += np * (h < P.n_hdiv ? P.h_n_comp[h] : 0);
+    }
+    for (int l = 0; l < 2; ++l) {
+        off_l[l] = n_loc;
+        n_loc += l < P.n_l2 ? P.l_n_phi[l] * P.l_n_comp[l] : 0;
+    }
+    double *s_wd = cur;  // [n_q] w det
+    cur += n_q;
+    double *s_T = cur;  // orientation matrices of this cell, per H(div) field [NF][nfd][nfd]
+    int t_off[2] = {0, 0};
+    {
+        int t = 0;
+        for (int h = 0; h < P.n_hdiv; ++h) {
+            t_off[h] = t;
+            t += NF * P.h_nfd[h] * P.h_nfd[h];
+        }
+        cur += t;
+    }
+    double *s_a = cur;  // [n_loc] local state
+
+    for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+        double X[DIM + 1][3];
+        load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+        Geom<DIM> g;
+        compute_geom<DIM>(X, g);
+        const double idet = 1.0 / g.det;
+        __syncthreads();
+        for (int h = 0; h < P.n_hdiv; ++h) {
+            const int nfd = P.h_nfd[h];
+            for (int i = threadIdx.x; i < NF * nfd * nfd; i += blockDim.x) {
+                const int fc = i / (nfd * nfd);
+                s_T[t_off[h] + i] = P.h_Tcases[h][(int)P.h_cases[h][cell * NF + fc] * nfd * nfd + (i - fc * nfd * nfd)];
+            }
+        }
+        for (int q = threadIdx.x; q < n_q; q += blockDim.x) s_wd[q] = P.weights[q] * g.det;
+        for (int i = threadIdx.x; i < n_loc; i += blockDim.x) s_a[i] = (alpha && dest) ? alpha[dest[cell * n_loc + i]] : 0.0;
+        __syncthreads();
+        for (int h = 0; h < P.n_hdiv; ++h) {
+            const int np = P.h_n_phi[h], nfd = P.h_nfd[h], n_fdofs = NF * nfd;
+            const double *val = P.h_val[h], *dv = P.h_div[h];
+            const double *cd = P.h_div_cd[h], *gv = P.h_div_g[h];
+            for (int idx = threadIdx.x; idx < n_q * np; idx += blockDim.x) {
+                const int q = idx / np, j = idx - q * np;
+                double vh[DIM], dh = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) vh[k] = 0.0;
+                if (j < n_fdofs) {
+                    const int fc = j / nfd, a = j - fc * nfd;
+                    for (int b = 0; b < nfd; ++b) {
+                        const double t = s_T[t_off[h] + (fc * nfd + a) * nfd + b];
+                        const double *src = val + ((int64_t)q * np + fc * nfd + b) * DIM;
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) vh[k] += t * src[k];
+                        dh += t * dv[q * np + fc * nfd + b];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) vh[k] = val[((int64_t)q * np + j) * DIM + k];
+                    dh = dv[q * np + j];
+                }
+                double gd = (cd ? cd[cell * n_q + q] : 1.0) * dh;  // c_d div^ psi  (reference divergence: no 1/det)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) v += g.J[c][k] * vh[k];
+                    v *= idet;
+                    s_psi[h][(q * np + j) * DIM + c] = v;
+                    if (gv) gd += g.det * gv[(cell * n_q + q) * DIM + c] * v;
+                }
+                s_div[h][q * np + j] = dh * idet;
+                s_gd[h][q * np + j] = gd;
+            }
+        }
+        __syncthreads();
+        double *K = Ke + cell * (int64_t)n_loc * n_loc;
+        for (int e = threadIdx.x; e < n_loc * n_loc; e += blockDim.x) {
+            int row = e / n_loc, col = e - row * n_loc;
+            // decode (kind, field, basis, comp)
+            int rk, rf, ra, rc, ck, cf, ca, cc;
+            {
+                int r = row;
+                if (r < off_l[0]) {
+                    rk = 0;
+                    rf = (P.n_hdiv > 1 && r >= off_h[1]) ? 1 : 0;
+                    r -= off_h[rf];
+                    ra = r / P.h_n_comp[rf];
+                    rc = r - ra * P.h_n_comp[rf];
+                } else {
+                    rk = 1;
+                    rf = (P.n_l2 > 1 && r >= off_l[1]) ? 1 : 0;
+                    r -= off_l[rf];
+                    ra = r / P.l_n_comp[rf];
+                    rc = r - ra * P.l_n_comp[rf];
+                }
+                int c = col;
+                if (c < off_l[0]) {
+                    ck = 0;
+                    cf = (P.n_hdiv > 1 && c >= off_h[1]) ? 1 : 0;
+                    c -= off_h[cf];
+                    ca = c / P.h_n_comp[cf];
+                    cc = c - ca * P.h_n_comp[cf];
+                } else {
+                    ck = 1;
+                    cf = (P.n_l2 > 1 && c >= off_l[1]) ? 1 : 0;
+                    c -= off_l[cf];
+                    ca = c / P.l_n_comp[cf];
+                    cc = c - ca * P.l_n_comp[cf];
+                }
+            }
+            double acc = 0.0;
+            if (rk == 0 && ck == 0) {
+                if (rf == cf) {
+                    const int h = rf, np = P.h_n_phi[h];
+                    const double *aid = P.h_a_id[h], *atr = P.h_a_tr[h], *avol = P.h_a_vol[h], *add = P.h_a_dd[h];
+                    for (int q = 0; q < n_q; ++q) {
+                        const double *pa = s_psi[h] + (q * np + ra) * DIM, *pb = s_psi[h] + (q * np + ca) * DIM;
+                        double t = 0.0;
+                        if (rc == cc) {
+                            double dot = 0.0;
+#pragma unroll
+                            for (int d = 0; d < DIM; ++d) dot += pa[d] * pb[d];
+                            if (aid) t += aid[cell * n_q + q] * dot;
+                            if (add) t += add[cell * n_q + q] * s_div[h][q * np + ra] * s_div[h][q * np + ca];
+                        }
+                        if (rc < DIM && cc < DIM) {
+                            if (atr) t += atr[cell * n_q + q] * pb[rc] * pa[cc];
+                            if (avol) t += avol[cell * n_q + q] * pa[rc] * pb[cc];
+                        }
+                        acc += s_wd[q] * t;
+                    }
+                }
+            } else if (rk == 1 && ck == 1) {
+                if (rf == cf && rc == cc && P.l_a_mass[rf]) {
+                    const int l = rf, np = P.l_n_phi[l];
+                    const double *am = P.l_a_mass[l], *lv = P.l_val[l];
+                    for (int q = 0; q < n_q; ++q) acc += s_wd[q] * am[cell * n_q + q] * lv[q * np + ra] * lv[q * np + ca];
+                }
+            } else {
+                // L2 x H(div) coupling (symmetric): put the L2 dof in (l, k, lc) and the H(div) dof in (h, a, hc)
+                const int l = rk == 1 ? rf : cf, k = rk == 1 ? ra : ca, lc = rk == 1 ? rc : cc;
+                const int h = rk == 1 ? cf : rf, a = rk == 1 ? ca : ra, hc = rk == 1 ? cc : rc;
+                const int npl = P.l_n_phi[l], nph = P.h_n_phi[h];
+                const double *lv = P.l_val[l];
+                if (P.div_coupling[l][h] && lc == hc) {
+                    for (int q = 0; q < n_q; ++q) acc += P.weights[q] * lv[q * npl + k] * s_gd[h][q * nph + a];
+                }
+                if (P.asym_coupling[l][h]) {
+                    const int ce = P.l_n_comp[l] == 1 ? 2 : lc;  // the single rotation of a 2-D problem is the z one
+                    for (int d = 0; d < DIM; ++d) {
+                        const double eps = levi_civita(ce, hc, d);
+                        if (eps != 0.0)
+                            for (int q = 0; q < n_q; ++q)
+                                acc += eps * s_wd[q] * lv[q * npl + k] * s_psi[h][(q * nph + a) * DIM + d];
+                    }
+                }
+            }
+            K[e] = acc;
+        }
+        __syncthreads();  // K of this cell is complete in global memory for the row products below
+        for (int row = threadIdx.x; row < n_loc; row += blockDim.x) {
+            double acc = 0.0;
+            if (alpha && dest)
+                for (int c = 0; c < n_loc; ++c) acc += K[row * n_loc + c] * s_a[c];
+            if (row >= off_l[0]) {
+                const int l = (P.n_l2 > 1 && row >= off_l[1]) ? 1 : 0;
+                const int r = row - off_l[l], k = r / P.l_n_comp[l], c = r - k * P.l_n_comp[l];
+                const double *ld = P.l_load[l];
+                if (ld) {
+                    const int np = P.l_n_phi[l], ncp = P.l_n_comp[l];
+                    for (int q = 0; q < n_q; ++q)
+                        acc -= s_wd[q] * ld[(cell * n_q + q) * ncp + c] * P.l_val[l][q * np + k];
+                }
+            }
+            re[cell * n_loc + row] = acc;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int nfa_local_hdiv_tensor(const nfa_tensor_form *form, const double *coords, const int32_t *cell_nodes,
+                                     int64_t n_cells, const double *alpha, const int32_t *dest, double *Ke, double *re,
+                                     nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (!form) return fail("nfa_local_hdiv_tensor: form is NULL");
+    const nfa_tensor_form &P = *form;
+    if (P.n_hdiv < 1 || P.n_hdiv > 2 || P.n_l2 < 0 || P.n_l2 > 2) return fail("nfa_local_hdiv_tensor: 1-2 H(div) and 0-2 L2 fields");
+    if (P.dim != 2 && P.dim != 3) return fail("nfa_local_hdiv_tensor: dim must be 2 or 3");
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t dbl = P.n_q;
+    int n_loc = 0;
+    for (int h = 0; h < P.n_hdiv; ++h) {
+        if (!P.h_val[h] || !P.h_div[h] || !P.h_Tcases[h] || !P.h_cases[h]) return fail("nfa_local_hdiv_tensor: H(div) tables missing");
+        dbl += (size_t)P.n_q * P.h_n_phi[h] * (P.dim + 2) + (size_t)(P.dim + 1) * P.h_nfd[h] * P.h_nfd[h];
+        n_loc += P.h_n_phi[h] * P.h_n_comp[h];
+    }
+    for (int l = 0; l < P.n_l2; ++l) {
+        if (!P.l_val[l]) return fail("nfa_local_hdiv_tensor: L2 table missing");
+        n_loc += P.l_n_phi[l] * P.l_n_comp[l];
+    }
+    dbl += n_loc;
+    const size_t smem = sizeof(double) * dbl;
+    if (smem > 220 * 1024) return fail("nfa_local_hdiv_tensor: element too large for the shared-memory staging");
+    const int grid = (int)(n_cells < 148 * 8 ? n_cells : 148 * 8);
+    if (P.dim == 3) {
+        auto kern = local_hdiv_tensor_kernel<3>;
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, s>>>(P, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
+    } else {
+        auto kern = local_hdiv_tensor_kernel<2>;
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, 128, smem, s>>>(P, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
+    }
+    NFA_LAUNCH_CHECK();
+    return 0;
+}

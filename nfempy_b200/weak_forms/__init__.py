@@ -8,3 +8,5 @@ from .l2_projector_weak_form import L2ProjectorWeakForm
 from .degenerate_elliptic_weak_form import DegenerateEllipticWeakForm, DegenerateEllipticWeakFormBCDirichlet
 from .unscaled_elliptic_weak_form import UnscaledEllipticWeakForm, UnscaledEllipticWeakFormBCDirichlet
 from .scaled_to_physical_l2_projection import ScaledToPhysicalL2Projection
+from .tensor_mixed import (LEDualWeakForm, LEDualWeakFormBCDirichlet, LCEDualWeakForm, LCEDualWeakFormBCDirichlet,
+                           LCEScaledDualWeakForm, LCEScaledDualWeakFormBCDirichlet)

@@ -122,6 +122,47 @@ def _facet_normals(points, facet_nodes, neigh_nodes):
     return n
 
 
+def hdiv_facet_setup(space, field_name, dev, items=None):
+    """Everything the natural-boundary kernels need for the boundary facets of one H(div) field: the neighbour's
+    reference trace pre-tabulated per (local facet, vertex permutation) -- the vectorised form of
+    ``transform_lower_to_higher`` (R/src/basis/parametric_transformation.py:58-98) --, orientation cases, normals
+    (R/src/geometry/compute_normal.py:7-24) and the physical quadrature points ``x`` for the boundary data."""
+    u = space.discrete_spaces[field_name]
+    ref, dim = u.ref_element, u.dimension
+    nfd = len(ref.entity_dofs[dim - 1][0])
+    fdim = dim - 1
+    points, weights = space.bc_quadrature[fdim]
+    points = np.asarray(points, dtype=np.float64).reshape(len(weights), fdim)
+    mesh = u.mesh
+    facets = u.bc_element_ids if items is None else u.bc_element_ids[np.asarray(items)]
+    rows, local_f = u.mesh_topology.first_neighbours(facets)
+    neigh_nodes = u.cell_nodes()[rows]
+    facet_nodes = mesh.node_tags_of(fdim)[facets - mesh.offset[fdim]]
+    # local vertex (in the neighbour) of every facet node -> which pre-tabulated permutation to use
+    g = (neigh_nodes[:, None, :] == facet_nodes[:, :, None]).argmax(axis=2)  # [n, fdim+1]
+    perms = {}
+    tabs = []
+    verts = REF_VERTICES[dim]
+    lam = np.concatenate([1.0 - points.sum(axis=1, keepdims=True), points], axis=1)  # [nq, fdim+1]
+    for f, lv in enumerate(SUB_ENTITIES[dim][fdim]):
+        for perm in itertools.permutations(lv):
+            perms[(f,) + tuple(perm)] = len(tabs)
+            mapped = lam @ verts[list(perm)]  # R/src/basis/parametric_transformation.py:58-98
+            tabs.append(ref.tabulate(0, mapped)[0][:, f * nfd : (f + 1) * nfd, :])
+    tidx = np.array([perms[(int(f),) + tuple(int(v) for v in row)] for f, row in zip(local_f, g)], dtype=np.int32)
+    cases = _all_cases(u)[rows, local_f].astype(np.int8)
+    normals = _facet_normals(mesh.points, facet_nodes, neigh_nodes)
+    facet_nodes_dev = torch.as_tensor(np.ascontiguousarray(facet_nodes, dtype=np.int32)).to(dev.device)
+    x = coefficients.physical_points(dev, fdim, points, facet_nodes_dev)
+    to = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).to(dev.device)
+    return FormData(
+        n_items=len(facets), items=items, dim=dim, nfd=nfd, n_q=len(weights), trace_tab=to(np.array(tabs), np.float64),
+        tidx=to(tidx, np.int32), w=to(weights, np.float64), tcases=to(case_matrices(ref), np.float64),
+        cases=to(cases, np.int8), facet_nodes=facet_nodes_dev, neigh_nodes=to(neigh_nodes, np.int32),
+        normals=to(normals, np.float64), x=x,
+    )
+
+
 class LaplaceDualWeakFormBCDirichlet(BatchedWeakForm):
     form_kind = "bc_form"
 
@@ -134,42 +175,14 @@ class LaplaceDualWeakFormBCDirichlet(BatchedWeakForm):
     def prepare(self, dev, items=None, arrays=None):
         if self.space is None or self.functions is None:
             raise ValueError("weak form needs .space and .functions")
-        u, p, ref, dim, nfd = _hdiv_tables(self.space)
-        fdim = dim - 1
-        points, weights = self.space.bc_quadrature[fdim]
-        points = np.asarray(points, dtype=np.float64).reshape(len(weights), fdim)
-        mesh = u.mesh
-        facets = u.bc_element_ids if items is None else u.bc_element_ids[np.asarray(items)]
-        rows, local_f = u.mesh_topology.first_neighbours(facets)
-        neigh_nodes = u.cell_nodes()[rows]
-        facet_nodes = mesh.node_tags_of(fdim)[facets - mesh.offset[fdim]]
-        # local vertex (in the neighbour) of every facet node -> which pre-tabulated permutation to use
-        g = (neigh_nodes[:, None, :] == facet_nodes[:, :, None]).argmax(axis=2)  # [n, fdim+1]
-        perms = {}
-        tabs = []
-        verts = REF_VERTICES[dim]
-        lam = np.concatenate([1.0 - points.sum(axis=1, keepdims=True), points], axis=1)  # [nq, fdim+1]
-        for f, lv in enumerate(SUB_ENTITIES[dim][fdim]):
-            for perm in itertools.permutations(lv):
-                perms[(f,) + tuple(perm)] = len(tabs)
-                mapped = lam @ verts[list(perm)]  # R/src/basis/parametric_transformation.py:58-98
-                tabs.append(ref.tabulate(0, mapped)[0][:, f * nfd : (f + 1) * nfd, :])
-        tidx = np.array([perms[(int(f),) + tuple(int(v) for v in row)] for f, row in zip(local_f, g)], dtype=np.int32)
-        cases = _all_cases(u)[rows, local_f].astype(np.int8)
-        normals = _facet_normals(mesh.points, facet_nodes, neigh_nodes)
-        facet_nodes_dev = torch.as_tensor(np.ascontiguousarray(facet_nodes, dtype=np.int32)).to(dev.device)
+        _hdiv_tables(self.space)
+        data = hdiv_facet_setup(self.space, "u", dev, items)
         if arrays is None:
-            x = coefficients.physical_points(dev, fdim, points, facet_nodes_dev)
-            pd = coefficients.evaluate(self.functions["p"], x, 1)[:, :, 0]
+            pd = coefficients.evaluate(self.functions["p"], data.x, 1)[:, :, 0]
         else:
             pd = arrays["p"]
-        to = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt)).to(dev.device)
-        return FormData(
-            n_items=len(facets), items=items, dim=dim, nfd=nfd, n_q=len(weights), trace_tab=to(np.array(tabs), np.float64),
-            tidx=to(tidx, np.int32), w=to(weights, np.float64), tcases=to(case_matrices(ref), np.float64),
-            cases=to(cases, np.int8), facet_nodes=facet_nodes_dev, neigh_nodes=to(neigh_nodes, np.int32),
-            normals=to(normals, np.float64), pd=to(pd, np.float64),
-        )
+        data.pd = torch.as_tensor(np.ascontiguousarray(pd, dtype=np.float64)).to(dev.device)
+        return data
 
     def launch_local(self, dev, data, alpha_dev, dest_dev, Ke, re):
         if Ke is not None:

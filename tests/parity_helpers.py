@@ -321,3 +321,74 @@ def degenerate_case(kind="degenerate", dim=3, k=1, n=2, with_bc=True, alpha=True
         mesh, lambda g: {flux: (dim, 1, "RT", k, g), scalar: (dim, 1, "Lagrange", k - 1, g)}, {flux: [1], scalar: [1]},
         {flux: btag_list if with_bc else []}, gpu_forms, ref_forms_fn, disc={scalar: True}, alpha_fn=alpha_fn,
     )
+
+
+def tensor_mixed_case(kind="lce", dim=3, s_family="BDM", m_family="RT", k=1, n=2, with_bc=True, alpha=True, mesh=None):
+    """Config 4 style: weakly symmetric mixed elasticity (kind="le": fields s, u, t) and mixed Cosserat elasticity
+    (kind="lce" / "lce_scaled": fields s, m, u, t) on row-wise H(div) stresses with discontinuous P_{k-1} multipliers."""
+    from nfempy_b200 import weak_forms as wf_mod
+    from oracle import ref_tensor_forms as rt
+
+    if mesh is None:
+        mesh = box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(n, jitter=0.2)
+    btag_list = [2, 3, 4, 5, 6, 7] if dim == 3 else [2, 3, 4, 5]
+    tc = 3 if dim == 3 else 1
+    mc = 3 if dim == 3 else 1
+    one = lambda x: np.ones_like(x)
+    functions = {
+        "rhs": lambda x, y, z: np.array([np.sin(x) + y, x * y + 1.0, z - x, np.cos(y), x + 0.5, y * z][: dim + tc] if dim == 3
+                                        else [np.sin(x) + y, x * y + 1.0, np.cos(y) + x]),
+        "lambda": lambda x, y, z: 1.0 + 0.5 * x, "mu": lambda x, y, z: 2.0 + 0.25 * y * y,
+        "lambda_s": lambda x, y, z: 1.0 + 0.5 * x, "mu_s": lambda x, y, z: 2.0 + 0.25 * y * y,
+        "kappa_s": lambda x, y, z: 0.3 + 0.1 * x * y, "lambda_o": lambda x, y, z: 0.7 * one(x),
+        "mu_o": lambda x, y, z: 1.3 + 0.2 * x, "kappa_o": lambda x, y, z: 0.4 * one(x),
+        "l": lambda x, y, z: 0.5 + 0.25 * x + 0.1 * y * y,
+        "grad_l": lambda x, y, z: np.array([0.25 * one(x), 0.2 * y, 0.0 * x]),
+    }
+    bc_functions = {
+        "u": lambda x, y, z: np.array([x + y, np.sin(x) - z, 0.5 * y * z][:dim]),
+        "t": lambda x, y, z: np.array([y - x, 0.3 * z + 1.0, np.cos(x)][:tc]),
+        "l": functions["l"], "grad_l": functions["grad_l"],
+    }
+    if kind == "le":
+        names, bfields = ("s", "u", "t"), ("s",)
+        vol_cls, bc_cls = wf_mod.LEDualWeakForm, wf_mod.LEDualWeakFormBCDirichlet
+        ref_vol, ref_bc = rt.le_dual, rt.le_dual_bc_dirichlet
+    elif kind == "lce":
+        names, bfields = ("s", "m", "u", "t"), ("s", "m")
+        vol_cls, bc_cls = wf_mod.LCEDualWeakForm, wf_mod.LCEDualWeakFormBCDirichlet
+        ref_vol, ref_bc = rt.lce_dual, rt.lce_dual_bc_dirichlet
+    else:
+        names, bfields = ("s", "m", "u", "t"), ("s", "m")
+        vol_cls, bc_cls = wf_mod.LCEScaledDualWeakForm, wf_mod.LCEScaledDualWeakFormBCDirichlet
+        ref_vol, ref_bc = rt.lce_scaled_dual, rt.lce_scaled_dual_bc_dirichlet
+
+    def data_fn(g):
+        d = {"s": (dim, dim, s_family, k, g)}
+        if "m" in names:
+            d["m"] = (dim, mc, m_family, k, g)
+        d["u"] = (dim, dim, "Lagrange", k - 1, g)
+        d["t"] = (dim, tc, "Lagrange", k - 1, g)
+        return d
+
+    def gpu_forms(space, a):
+        wf = vol_cls(space)
+        wf.functions = functions
+        out = {"volume": ["form", range(len(space.discrete_spaces["s"].elements)), wf, a]}
+        if with_bc:
+            bf = bc_cls(space)
+            bf.functions = bc_functions
+            out["bc"] = ["bc_form", range(len(space.discrete_spaces["s"].bc_elements)), bf, a]
+        return out
+
+    def ref_forms_fn(space):
+        out = [("form", ref_vol, functions, len(space.discrete_spaces["s"].element_ids))]
+        if with_bc:
+            out.append(("bc_form", ref_bc, bc_functions, len(space.discrete_spaces["s"].bc_element_ids)))
+        return out
+
+    alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None
+    return Case(
+        mesh, data_fn, {nm: [1] for nm in names}, {nm: (btag_list if with_bc else []) for nm in bfields},
+        gpu_forms, ref_forms_fn, disc={"u": True, "t": True}, alpha_fn=alpha_fn,
+    )
