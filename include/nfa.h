@@ -225,6 +225,7 @@ typedef struct nfa_tensor_form {
     int32_t l_n_phi[2], l_n_comp[2];
     const double *l_val[2], *l_a_mass[2], *l_load[2];
     int32_t div_coupling[2][2], asym_coupling[2][2];   /* [L2 field][H(div) field] */
+    int32_t h_dd_general[2];                           /* a_dd block on (cd div psi + g.psi) instead of div psi */
 } nfa_tensor_form;
 int nfa_local_hdiv_tensor(const nfa_tensor_form *form, const double *d_coords, const int32_t *d_cell_nodes,
                           int64_t n_cells, const double *d_alpha, const int32_t *d_dest, double *d_Ke, double *d_re,

@@ -173,7 +173,12 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
                             for (int d = 0; d < DIM; ++d) dot += pa[d] * pb[d];
                             if (aid) t += aid[cell * n_q + q] * dot;
-                            if (add) t += add[cell * n_q + q] * s_div[h][q * np + ra] * s_div[h][q * np + ca];
+                            if (add) {
+                                if (P.h_dd_general[h])  // s_gd carries det (cd div psi + g.psi)
+                                    t += add[cell * n_q + q] * (s_gd[h][q * np + ra] * idet) * (s_gd[h][q * np + ca] * idet);
+                                else
+                                    t += add[cell * n_q + q] * s_div[h][q * np + ra] * s_div[h][q * np + ca];
+                            }
                         }
                         if (rc < DIM && cc < DIM) {
                             if (atr) t += atr[cell * n_q + q] * pb[rc] * pa[cc];

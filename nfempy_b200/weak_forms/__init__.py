@@ -9,4 +9,5 @@ from .degenerate_elliptic_weak_form import DegenerateEllipticWeakForm, Degenerat
 from .unscaled_elliptic_weak_form import UnscaledEllipticWeakForm, UnscaledEllipticWeakFormBCDirichlet
 from .scaled_to_physical_l2_projection import ScaledToPhysicalL2Projection
 from .tensor_mixed import (LEDualWeakForm, LEDualWeakFormBCDirichlet, LCEDualWeakForm, LCEDualWeakFormBCDirichlet,
-                           LCEScaledDualWeakForm, LCEScaledDualWeakFormBCDirichlet)
+                           LCEScaledDualWeakForm, LCEScaledDualWeakFormBCDirichlet, LERieszMapWeakForm,
+                           LCERieszMapWeakForm, LCEScaledRieszMapWeakForm)

@@ -41,7 +41,7 @@ class TensorFormStruct(ctypes.Structure):
         ("h_div_cd", _vp * 2), ("h_div_g", _vp * 2),
         ("l_n_phi", _i32 * 2), ("l_n_comp", _i32 * 2),
         ("l_val", _vp * 2), ("l_a_mass", _vp * 2), ("l_load", _vp * 2),
-        ("div_coupling", (_i32 * 2) * 2), ("asym_coupling", (_i32 * 2) * 2),
+        ("div_coupling", (_i32 * 2) * 2), ("asym_coupling", (_i32 * 2) * 2), ("h_dd_general", _i32 * 2),
     ]
 
 
@@ -130,6 +130,7 @@ class HdivTensorMixedForm(BatchedWeakForm):
             st.h_a_id[h], st.h_a_tr[h] = arr(c.get("a_id"), (n, nq)), arr(c.get("a_tr"), (n, nq))
             st.h_a_vol[h], st.h_a_dd[h] = arr(c.get("a_vol"), (n, nq)), arr(c.get("a_dd"), (n, nq))
             st.h_div_cd[h], st.h_div_g[h] = arr(c.get("cd"), (n, nq)), arr(c.get("g"), (n, nq, dim))
+            st.h_dd_general[h] = 1 if c.get("dd_general") else 0
         for l, name in enumerate(self.l2_names):
             s = sp[name]
             lv = up(s.ref_element.tabulate(0, points)[0, :, :, 0])
@@ -206,6 +207,47 @@ class LCEDualWeakForm(HdivTensorMixedForm):
 
 
 class LCEScaledDualWeakForm(LCEDualWeakForm):
+    scaled = True
+
+
+class LERieszMapWeakForm(HdivTensorMixedForm):
+    """Block-diagonal norm matrix: H(div) inner product of the stress (compliance-weighted) + L2 masses."""
+
+    hdiv_names, l2_names = ("s",), ("u", "t")
+
+    def point_data(self, x, dim, sp):
+        lam = coefficients.evaluate(self.functions["lambda"], x)
+        mu = coefficients.evaluate(self.functions["mu"], x)
+        cs = 1.0 / (2.0 * mu)
+        one = np.ones_like(mu)
+        return {"s": {"a_id": cs, "a_vol": -cs * (lam / (2.0 * mu + dim * lam)), "a_dd": one},
+                "u": {"a_mass": one}, "t": {"a_mass": one}}
+
+
+class LCERieszMapWeakForm(HdivTensorMixedForm):
+    hdiv_names, l2_names = ("s", "m"), ("u", "t")
+    scaled = False
+
+    def point_data(self, x, dim, sp):
+        ev = lambda k: coefficients.evaluate(self.functions[k], x)
+        a_id, a_tr, a_vol = _stress_coefficients(ev("lambda_s"), ev("mu_s"), ev("kappa_s"), dim)
+        lc = ev("l")
+        one = np.ones_like(lc)
+        m_scale = None if self.scaled else 1.0 / lc
+        if dim == 3:
+            m_id, m_tr, m_vol = _stress_coefficients(ev("lambda_o"), ev("mu_o"), ev("kappa_o"), dim, m_scale)
+            m = {"a_id": m_id, "a_tr": m_tr, "a_vol": m_vol}
+        else:
+            gamma = 1.0 / (ev("mu_o") + ev("kappa_o"))
+            m = {"a_id": gamma if m_scale is None else gamma * m_scale}
+        m["a_dd"] = one
+        if self.scaled:  # norm of div (l m) = grad l . m + l div m  (lce_scaled_riesz_map_weak_form.py:546-566)
+            m["cd"], m["g"], m["dd_general"] = lc, coefficients.evaluate(self.functions["grad_l"], x, dim), True
+        return {"s": {"a_id": a_id, "a_tr": a_tr, "a_vol": a_vol, "a_dd": one}, "m": m,
+                "u": {"a_mass": one}, "t": {"a_mass": one}}
+
+
+class LCEScaledRieszMapWeakForm(LCERieszMapWeakForm):
     scaled = True
 
 

@@ -204,3 +204,79 @@ def lce_dual_bc_dirichlet(space, functions, iel, alpha, scaled=False):
 
 def lce_scaled_dual_bc_dirichlet(space, functions, iel, alpha):
     return lce_dual_bc_dirichlet(space, functions, iel, alpha, scaled=True)
+
+
+def _mass_blocks(j_el, tab, wd, off, n, nc):
+    block = np.array([np.outer(p, p) for p in tab[0, :, :, 0]]).T @ wd
+    for c in range(nc):
+        j_el[off + c : off + n : nc, off + c : off + n : nc] += block
+
+
+def _divdiv_blocks(j_el, div_phys, wd, off, n, nc):
+    """``div_phys[q, a]``: the (generalised) physical divergence of every vector function."""
+    block = np.array([np.outer(d, d) for d in div_phys]).T @ wd
+    for c in range(nc):
+        j_el[off + c : off + n : nc, off + c : off + n : nc] += block
+
+
+def le_riesz_map(space, functions, iel, alpha):
+    """LERieszMapWeakForm.evaluate_form_vectorized, R/src/weak_forms/le_riesz_map_weak_form.py:258-360."""
+    sp, dim, weights, x, det_jac, (s_tab, u_tab, t_tab) = _tables(space, ("s", "u", "t"), iel)
+    sc, uc, tc = (s.n_comp for s in sp)
+    n_s, n_u, n_t = s_tab.shape[2] * sc, u_tab.shape[2] * uc, t_tab.shape[2] * tc
+    n_dof = n_s + n_u + n_t
+    j_el = np.zeros((n_dof, n_dof))
+    lam = functions["lambda"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    mu = functions["mu"](x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+    wd = det_jac * weights
+    s_star = s_tab[0, :, :, 0:dim]
+    mass = np.array([p @ p.T for p in s_star]).T @ (wd / (2.0 * mu))
+    for c in range(sc):
+        j_el[c:n_s:sc, c:n_s:sc] += mass
+    vol_factor = (1.0 / (2.0 * mu)) * (lam / (2.0 * mu + dim * lam))
+    j_el[0:n_s, 0:n_s] += -1.0 * np.array([np.outer(p, p) for p in s_star]).T @ (vol_factor * wd)
+    div_s = np.trace(s_tab[1 : 1 + dim, :, :, 0:dim], axis1=0, axis2=3) / det_jac[:, None]
+    _divdiv_blocks(j_el, div_s, wd, 0, n_s, sc)
+    _mass_blocks(j_el, u_tab, wd, n_s, n_u, uc)
+    _mass_blocks(j_el, t_tab, wd, n_s + n_u, n_t, tc)
+    return _finish(j_el, np.zeros(n_dof), alpha)
+
+
+def lce_riesz_map(space, functions, iel, alpha, scaled=False):
+    """LCERieszMapWeakForm / LCEScaledRieszMapWeakForm .evaluate_form_vectorized,
+    R/src/weak_forms/lce_riesz_map_weak_form.py:372-546, lce_scaled_riesz_map_weak_form.py:415-598."""
+    sp, dim, weights, x, det_jac, (s_tab, m_tab, u_tab, t_tab) = _tables(space, ("s", "m", "u", "t"), iel)
+    sc, mc, uc, tc = (s.n_comp for s in sp)
+    n_s, n_m = s_tab.shape[2] * sc, m_tab.shape[2] * mc
+    n_u, n_t = u_tab.shape[2] * uc, t_tab.shape[2] * tc
+    n_dof = n_s + n_m + n_u + n_t
+    j_el = np.zeros((n_dof, n_dof))
+    ones = np.ones(len(weights))
+    ev = lambda k: functions[k](x[:, 0], x[:, 1], x[:, 2]) * ones
+    wd = det_jac * weights
+    o_u, o_t = n_s + n_m, n_s + n_m + n_u
+    s_star, m_star = s_tab[0, :, :, 0:dim], m_tab[0, :, :, 0:dim]
+    j_el[0:n_s, 0:n_s] += _compliance(s_star, wd, ev("lambda_s"), ev("mu_s"), ev("kappa_s"), dim)
+    lc_v = ev("l")
+    m_scale = ones if scaled else 1.0 / lc_v
+    if dim == 3:
+        j_el[n_s:o_u, n_s:o_u] += _compliance(m_star, wd, ev("lambda_o"), ev("mu_o"), ev("kappa_o"), dim, m_scale)
+    else:
+        block = np.array([p @ p.T for p in m_star]).T @ (wd * m_scale * (1.0 / (ev("mu_o") + ev("kappa_o"))))
+        for c in range(mc):
+            j_el[n_s + c : o_u : mc, n_s + c : o_u : mc] += block
+    div_s = np.trace(s_tab[1 : 1 + dim, :, :, 0:dim], axis1=0, axis2=3) / det_jac[:, None]
+    _divdiv_blocks(j_el, div_s, wd, 0, n_s, sc)
+    div_m = np.trace(m_tab[1 : 1 + dim, :, :, 0:dim], axis1=0, axis2=3) / det_jac[:, None]
+    if scaled:
+        grad_l = np.asarray(functions["grad_l"](x[:, 0], x[:, 1], x[:, 2]))
+        gl_m = np.array([[grad_l[0:dim, i] @ m_tab[0, i, j, 0:dim] for j in range(m_tab.shape[2])] for i in range(len(weights))])
+        div_m = gl_m + div_m * lc_v[:, None]
+    _divdiv_blocks(j_el, div_m, wd, n_s, n_m, mc)
+    _mass_blocks(j_el, u_tab, wd, o_u, n_u, uc)
+    _mass_blocks(j_el, t_tab, wd, o_t, n_t, tc)
+    return _finish(j_el, np.zeros(n_dof), alpha)
+
+
+def lce_scaled_riesz_map(space, functions, iel, alpha):
+    return lce_riesz_map(space, functions, iel, alpha, scaled=True)

@@ -358,10 +358,18 @@ def tensor_mixed_case(kind="lce", dim=3, s_family="BDM", m_family="RT", k=1, n=2
         names, bfields = ("s", "m", "u", "t"), ("s", "m")
         vol_cls, bc_cls = wf_mod.LCEDualWeakForm, wf_mod.LCEDualWeakFormBCDirichlet
         ref_vol, ref_bc = rt.lce_dual, rt.lce_dual_bc_dirichlet
-    else:
+    elif kind == "lce_scaled":
         names, bfields = ("s", "m", "u", "t"), ("s", "m")
         vol_cls, bc_cls = wf_mod.LCEScaledDualWeakForm, wf_mod.LCEScaledDualWeakFormBCDirichlet
         ref_vol, ref_bc = rt.lce_scaled_dual, rt.lce_scaled_dual_bc_dirichlet
+    else:  # Riesz maps (preconditioner matrices): no boundary form
+        with_bc = False
+        names = ("s", "u", "t") if kind == "le_riesz" else ("s", "m", "u", "t")
+        bfields = ("s",) if kind == "le_riesz" else ("s", "m")
+        vol_cls = {"le_riesz": wf_mod.LERieszMapWeakForm, "lce_riesz": wf_mod.LCERieszMapWeakForm,
+                   "lce_scaled_riesz": wf_mod.LCEScaledRieszMapWeakForm}[kind]
+        ref_vol = {"le_riesz": rt.le_riesz_map, "lce_riesz": rt.lce_riesz_map, "lce_scaled_riesz": rt.lce_scaled_riesz_map}[kind]
+        bc_cls = ref_bc = None
 
     def data_fn(g):
         d = {"s": (dim, dim, s_family, k, g)}

@@ -46,3 +46,14 @@ def test_vectorized_variant_returns_the_load_only():
     r_1, _ = rt.lce_dual(rspace, form.functions, 2, a)
     assert np.abs(r_a - r_1).max() <= 1e-12 * np.abs(r_1).max()
     assert np.abs(j_v - j_v.T).max() <= 1e-14 * np.abs(j_v).max()
+
+
+@pytest.mark.parametrize("kind", ["le_riesz", "lce_riesz", "lce_scaled_riesz"])
+@pytest.mark.parametrize("dim,k", [(3, 1), (2, 2)])
+def test_riesz_map_preconditioner_matrices(kind, dim, k):
+    """LERieszMapWeakForm / LCERieszMapWeakForm / LCEScaledRieszMapWeakForm: the block-diagonal norm matrices the
+    Cosserat drivers assemble into ``P`` (R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py:189-240)."""
+    fam = "BDM" if k == 1 else "RT"
+    case = tensor_mixed_case(kind=kind, dim=dim, s_family=fam, m_family="RT", k=k, n=1 if dim == 3 else 2)
+    got, ref = case.run_gpu(), case.run_oracle()
+    compare_csr(got, ref, RTOL)
