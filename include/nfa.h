@@ -151,6 +151,14 @@ int nfa_plan_create(int64_t n_dof, int n_segments, const int32_t *const *d_dest,
                     const int32_t *n_loc, const int32_t *seg_flags, const nfa_plan *base, nfa_plan **out,
                     nfa_stream stream);
 /* adopt the pattern of a node-block plan (no gather lists) */
+/* Value-dependent ("filtered") patterns of the example drivers' inline scatter closures
+ * (R/examples/elasticity/cg_elasticity_example_1.py:92-145, R/examples/cosserat_elasticity/
+ * mfe_cosserat_elasticity_example_3.py:150-243): d_masks[k] is a uint8 [n_items, n_loc, n_loc] table, 0 = the local
+ * entry is left out of the pattern and of the sums.  The host layer builds the masks from the local matrices
+ * (~isclose(v, 1e-16), optional row <= col for the symmetric "sbaij" storage, optional explicit diagonal). */
+int nfa_plan_create_filtered(int64_t n_dof, int n_segments, const int32_t *const *d_dest, const int64_t *n_items,
+                             const int32_t *n_loc, const int32_t *seg_flags, const uint8_t *const *d_masks,
+                             nfa_plan **out, nfa_stream stream);
 int nfa_plan_from_bplan(const nfa_bplan *bp, nfa_plan **out, nfa_stream stream);
 void nfa_plan_destroy(nfa_plan *plan);
 int64_t nfa_plan_nnz(const nfa_plan *plan);

@@ -72,7 +72,18 @@ class _Plan:
 
 
 class GPUAssembler:
-    def __init__(self, space, jacobian=None, residual=None, device=None, allow_fused=True):
+    def __init__(self, space, jacobian=None, residual=None, device=None, allow_fused=True, pattern_policy="full",
+                 explicit_diagonal=False):
+        """``pattern_policy``: "full" = every ``n_loc^2`` pair of every element, exact zeros kept (the library
+        scatter, R/src/assembly/ScatterFormData.py:5-11); "filtered" = only entries with
+        ``~np.isclose(value, 1e-16)``; "filtered_upper" = additionally ``row <= col`` (PETSc "sbaij" storage) -- the
+        inline closures of the example drivers (R/examples/cauchy_elasticity/cg_elasticity_example_1.py:92-145,
+        R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py:150-243).  ``explicit_diagonal`` adds a
+        stored ``(i, i, 0.0)`` for every local dof of the volume forms (``:110-111`` / ``:175-176``)."""
+        if pattern_policy not in ("full", "filtered", "filtered_upper"):
+            raise ValueError("GPUAssembler: unknown pattern policy %r" % (pattern_policy,))
+        self.pattern_policy = pattern_policy
+        self.explicit_diagonal = bool(explicit_diagonal)
         self.space = space
         self.jacobian = jacobian if jacobian is not None else CSRMatrix(getattr(space, "n_dof", None))
         self.residual = residual
@@ -222,6 +233,8 @@ class GPUAssembler:
         ]
         dests = [self._dest_dev(dev, form, items) for (_, _, items, form, _) in entries]
         fused_index = None
+        if self.pattern_policy != "full":
+            return dev, entries, datas, dests, None, None  # the pattern depends on the values: built in run()
         if self.allow_fused:
             for i, ((_, kind, _, form, _), data) in enumerate(zip(entries, datas)):
                 if kind == "form" and form.fused_spec(data) is not None and len(self.space.discrete_spaces) == 1:
@@ -239,6 +252,8 @@ class GPUAssembler:
         lib = _lib.load()
         stream = _lib.stream_ptr()
         jac = self.jacobian
+        if plan is None:
+            return self._run_filtered(state, rhs_dev)
         if jac.plan_key != key:
             if jac.plan_key is not None and not jac.is_zero:
                 raise _lib.NfaError("GPUAssembler: the jacobian holds values assembled on a different sparsity plan")
@@ -305,6 +320,69 @@ class GPUAssembler:
         self._keep = keep  # buffers must outlive the stream-ordered kernels
         return rhs_dev
 
+    def _run_filtered(self, state, rhs_dev):
+        """Value-dependent pattern: local blocks first, then masks, then a plan over the kept entries."""
+        dev, entries, datas, dests, _, _ = state
+        lib = _lib.load()
+        stream = _lib.stream_ptr()
+        jac = self.jacobian
+        if jac.plan_key is not None and not jac.is_zero:
+            raise _lib.NfaError("GPUAssembler: a filtered pattern cannot be accumulated onto existing values; scale(0.0) first")
+        n_dof = int(self.space.n_dof)
+        if rhs_dev is None:
+            rhs_dev = torch.zeros(n_dof, dtype=torch.float64, device=dev.device)
+        nseg = len(entries)
+        Ke_list, re_list, masks, keep = [], [], [], []
+        tol = 1.0e-8 + 1.0e-5 * 1.0e-16  # np.isclose(value, 1e-16): |value - 1e-16| <= atol + rtol * |1e-16|
+        for (_, kind, _, form, alpha), data, dest in zip(entries, datas, dests):
+            if "time_dependent" in kind:
+                raise NotImplementedError("GPUAssembler: filtered patterns are implemented for form / bc_form lists")
+            alpha_dev = None
+            if alpha is not None and np.any(np.asarray(alpha) != 0.0):
+                alpha_dev = torch.as_tensor(np.ascontiguousarray(alpha, dtype=np.float64)).to(dev.device)
+            Ke, re = form.local_blocks(dev, data, alpha_dev, dest if alpha_dev is not None else None)
+            value_kept = (Ke - 1.0e-16).abs() > tol
+            mask = value_kept.clone()
+            if self.pattern_policy == "filtered_upper":
+                mask &= dest[:, :, None] <= dest[:, None, :]
+            if self.explicit_diagonal and kind == "form":
+                idx = torch.arange(Ke.shape[1], device=dev.device)
+                mask[:, idx, idx] = True
+            Ke = torch.where(value_kept, Ke, torch.zeros_like(Ke))  # a forced diagonal entry that failed the test adds 0.0
+            Ke_list.append(Ke)
+            re_list.append(re)
+            masks.append(mask.to(torch.uint8).contiguous())
+            keep += [alpha_dev]
+        t0 = time.perf_counter()
+        p = _Plan()
+        p.n_dof = n_dof
+        dest_ptrs = (ctypes.c_void_p * nseg)(*[d.data_ptr() for d in dests])
+        n_items = (ctypes.c_int64 * nseg)(*[int(d.shape[0]) for d in dests])
+        n_loc = (ctypes.c_int32 * nseg)(*[int(d.shape[1]) for d in dests])
+        mask_ptrs = (ctypes.c_void_p * nseg)(*[m.data_ptr() for m in masks])
+        handle = ctypes.c_void_p()
+        _lib.check(
+            lib.nfa_plan_create_filtered(n_dof, nseg, dest_ptrs, n_items, n_loc, None, mask_ptrs, ctypes.byref(handle), stream),
+            "nfa_plan_create_filtered",
+        )
+        p.plan = handle
+        p.nnz = int(lib.nfa_plan_nnz(p.plan))
+        p.indptr = torch.empty(n_dof + 1, dtype=torch.int32, device=dev.device)
+        p.indices = torch.empty(p.nnz, dtype=torch.int32, device=dev.device)
+        _lib.check(lib.nfa_plan_csr(p.plan, _lib.ptr(p.indptr), _lib.ptr(p.indices), stream), "nfa_plan_csr")
+        p.build_seconds = time.perf_counter() - t0
+        self._filtered_plan = p
+        jac.bind_pattern(("filtered", id(p)), n_dof, p.indptr, p.indices)
+        ke_ptrs = (ctypes.c_void_p * nseg)(*[k.data_ptr() for k in Ke_list])
+        re_ptrs = (ctypes.c_void_p * nseg)(*[r.data_ptr() for r in re_list])
+        _lib.check(
+            lib.nfa_plan_reduce(p.plan, ke_ptrs, re_ptrs, 0, _lib.ptr(jac.values_dev), 1, _lib.ptr(rhs_dev), stream),
+            "nfa_plan_reduce",
+        )
+        jac.is_zero = False
+        self._keep = keep + Ke_list + re_list + masks
+        return rhs_dev
+
     def scatter_forms(self, measure_time_q=False):
         t0 = time.perf_counter()
         state = self.prepare()
@@ -315,7 +393,8 @@ class GPUAssembler:
         if self.residual is None:
             self.residual = np.zeros(len(rhs))
         self.residual += rhs
-        self.last_timings = {"prepare_s": t1 - t0, "kernels_s": t2 - t1, "plan_build_s": state[4].build_seconds}
+        plan = state[4] if state[4] is not None else self._filtered_plan
+        self.last_timings = {"prepare_s": t1 - t0, "kernels_s": t2 - t1, "plan_build_s": plan.build_seconds}
         if measure_time_q:
             print("GPUAssembler:: prepare (callables, upload, plan):", t1 - t0, "seconds")
             print("GPUAssembler:: kernels + residual download:", t2 - t1, "seconds")

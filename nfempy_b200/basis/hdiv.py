@@ -1,4 +1,4 @@
-"""H(div) elements on simplices: Raviart-Thomas (degree 1..3, lowest = 1 as in basix) and BDM degree 1, restated
+"""H(div) elements on simplices: Raviart-Thomas (degree 1..3, lowest = 1 as in basix) and BDM degree 1, 2, restated
 from their published definition in the conventions of basix (un-vendored, unpinned dependency of the reference:
 R/requirements.txt:2; called at R/src/basis/finite_element.py:85-91 with ``lagrange_variant=gll_centroid``).
 
@@ -11,6 +11,8 @@ Construction (Ciarlet triple, exact rational arithmetic, then one rounding to do
   nodal Lagrange basis of degree k-1 (RT) / k (BDM) on the reference facet;
 * dual basis, interior part (RT, k >= 2): ``l(phi) = int_cell phi_d q_i`` against the nodal Lagrange basis of degree
   k-2, dof index ``i * dim + d`` (basis function major, direction minor);
+* dual basis, interior part (BDM_2): ``l(phi) = int_cell phi . w_e`` against the lowest-order Nedelec functions
+  ``w_e = lam_a grad lam_b - lam_b grad lam_a``, one per cell edge (a, b) in the sub-entity order;
 * basis = dual basis: ``l_i(phi_j) = delta_ij``.
 
 PARITY UNPINNED: these conventions are written from basix's documented construction, not checked against a basix
@@ -156,8 +158,31 @@ def _functionals(family, dim, k):
                     return _simplex_integral(_pmul(vec[d], q)) if vec[d] else Fraction(0)
 
                 out.append((dim, 0, functional))
-    if family == "BDM" and k >= 2:
-        raise NotImplementedError("BDM degree >= 2 needs Nedelec interior moments, which are not restated yet")
+    if family == "BDM" and k == 2:
+        # interior moments against the lowest-order Nedelec (first kind) functions lam_i grad lam_j - lam_j grad lam_i,
+        # one per edge of the cell in the sub-entity order
+        one = {(0,) * dim: Fraction(1)}
+        lam = [dict(one)]
+        grad = [[Fraction(-1)] * dim]
+        for d in range(dim):
+            e = tuple(1 if i == d else 0 for i in range(dim))
+            lam.append({e: Fraction(1)})
+            lam[0] = _padd(lam[0], {e: Fraction(1)}, -1)
+            grad.append([Fraction(int(c == d)) for c in range(dim)])
+        for a, b in SUB_ENTITIES[dim][1]:
+            w = [_padd({e: v * grad[b][c] for e, v in lam[a].items()}, {e: v * grad[a][c] for e, v in lam[b].items()}, -1)
+                 for c in range(dim)]
+
+            def functional(vec, w=w):
+                total = Fraction(0)
+                for c in range(dim):
+                    if vec[c]:
+                        total += _simplex_integral(_pmul(vec[c], w[c]))
+                return total
+
+            out.append((dim, 0, functional))
+    elif family == "BDM" and k > 2:
+        raise NotImplementedError("BDM degree >= 3 needs second-order Nedelec interior moments and cubic facet moments")
     return out
 
 
@@ -183,8 +208,8 @@ def build_hdiv(el):
         raise NotImplementedError("H(div) elements live on triangles and tetrahedra")
     if family == "RT" and not 1 <= k <= 3:
         raise NotImplementedError("RT degree %d is not restated (1..3 are)" % k)
-    if family == "BDM" and k != 1:
-        raise NotImplementedError("BDM degree %d is not restated (1 is)" % k)
+    if family == "BDM" and k not in (1, 2):
+        raise NotImplementedError("BDM degree %d is not restated (1 and 2 are)" % k)
     fns = _space_functions(family, dim, k)
     funcs = _functionals(family, dim, k)
     if len(fns) != len(funcs):

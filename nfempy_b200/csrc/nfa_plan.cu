@@ -32,7 +32,8 @@ void DevBuf::release() {
 
 // ---- key generation ------------------------------------------------------------------------------
 __global__ void fill_matrix_keys(const int32_t *__restrict__ dest, int64_t n_items, int n_loc, int64_t n_dof,
-                                 uint32_t entry_base, uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+                                 uint32_t entry_base, uint64_t *__restrict__ keys, uint32_t *__restrict__ ids,
+                                 const uint8_t *__restrict__ mask = nullptr) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t per = (int64_t)n_loc * n_loc;
     if (e >= n_items * per) return;
@@ -40,7 +41,8 @@ __global__ void fill_matrix_keys(const int32_t *__restrict__ dest, int64_t n_ite
     int r = (int)(e - item * per);
     int ra = r / n_loc, rb = r - ra * n_loc;
     uint64_t row = (uint64_t)dest[item * n_loc + ra], col = (uint64_t)dest[item * n_loc + rb];
-    keys[entry_base + e] = row * (uint64_t)n_dof + col;
+    // entries filtered out of the pattern share one sentinel key that sorts last and is dropped after the encode
+    keys[entry_base + e] = (mask && !mask[e]) ? (uint64_t)n_dof * (uint64_t)n_dof : row * (uint64_t)n_dof + col;
     ids[entry_base + e] = entry_base + (uint32_t)e;
 }
 
@@ -158,9 +160,26 @@ static int bits_for(uint64_t max_value) {
     return b;
 }
 
+static int plan_create_impl(int64_t n_dof, int n_segments, const int32_t *const *dest, const int64_t *n_items,
+                            const int32_t *n_loc, const int32_t *seg_flags, const nfa_plan *base,
+                            const uint8_t *const *masks, nfa_plan **out, nfa_stream stream);
+
 extern "C" int nfa_plan_create(int64_t n_dof, int n_segments, const int32_t *const *dest, const int64_t *n_items,
                                const int32_t *n_loc, const int32_t *seg_flags, const nfa_plan *base, nfa_plan **out,
                                nfa_stream stream) {
+    return plan_create_impl(n_dof, n_segments, dest, n_items, n_loc, seg_flags, base, nullptr, out, stream);
+}
+
+extern "C" int nfa_plan_create_filtered(int64_t n_dof, int n_segments, const int32_t *const *dest,
+                                        const int64_t *n_items, const int32_t *n_loc, const int32_t *seg_flags,
+                                        const uint8_t *const *masks, nfa_plan **out, nfa_stream stream) {
+    if (!masks) return fail("nfa_plan_create_filtered: masks is NULL");
+    return plan_create_impl(n_dof, n_segments, dest, n_items, n_loc, seg_flags, nullptr, masks, out, stream);
+}
+
+static int plan_create_impl(int64_t n_dof, int n_segments, const int32_t *const *dest, const int64_t *n_items,
+                            const int32_t *n_loc, const int32_t *seg_flags, const nfa_plan *base,
+                            const uint8_t *const *masks, nfa_plan **out, nfa_stream stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!out) return fail("nfa_plan_create: out is NULL");
     *out = nullptr;
@@ -213,10 +232,10 @@ extern "C" int nfa_plan_create(int64_t n_dof, int n_segments, const int32_t *con
             if (n == 0 || !plan->with_matrix[k]) continue;
             fill_matrix_keys<<<grid_for(n, 256), 256, 0, s>>>(dest[k], n_items[k], n_loc[k], n_dof,
                                                               (uint32_t)plan->mat_off[k], (uint64_t *)keys.p,
-                                                              (uint32_t *)ids.p);
+                                                              (uint32_t *)ids.p, masks ? masks[k] : nullptr);
             count_launch();
         }
-        int end_bit = bits_for((uint64_t)n_dof * (uint64_t)n_dof);
+        int end_bit = bits_for((uint64_t)n_dof * (uint64_t)n_dof + (masks ? 1 : 0));
         int rc = sort_and_encode<uint64_t>((uint64_t *)keys.p, (uint64_t *)keys_alt.p, (uint32_t *)ids.p,
                                            (uint32_t *)ids_alt.p, E, end_bit, ukeys, plan->mat.perm,
                                            plan->mat.seg_ptr, &plan->mat.n_unique, s);
@@ -225,6 +244,12 @@ extern "C" int nfa_plan_create(int64_t n_dof, int n_segments, const int32_t *con
         keys_alt.release();
         ids.release();
         ids_alt.release();
+        if (masks && plan->mat.n_unique > 0) {  // drop the sentinel run (filtered-out entries), if any
+            uint64_t last = 0;
+            cudaMemcpyAsync(&last, (uint64_t *)ukeys.p + plan->mat.n_unique - 1, 8, cudaMemcpyDeviceToHost, s);
+            cudaStreamSynchronize(s);
+            if (last == (uint64_t)n_dof * (uint64_t)n_dof) plan->mat.n_unique -= 1;
+        }
         int64_t nu = plan->mat.n_unique;
         if (!base) {
             plan->nnz = nu;

@@ -110,3 +110,29 @@ def assemble(space, forms, alpha=None):
             scatter(space, form, functions, i, res_g, jac_g, alpha)
     indptr, indices, data = jac_g.getValuesCSR()
     return indptr, indices, data, res_g
+
+
+def assemble_filtered(space, forms, alpha=None, upper=False, explicit_diagonal=False):
+    """The inline scatter closures of the example drivers (R/examples/cauchy_elasticity/cg_elasticity_example_1.py:
+    92-145, R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py:150-243): only entries with
+    ``~np.isclose(value, 1e-16)`` are inserted, optionally only ``row <= col`` ("sbaij"), and every local dof of a
+    volume form gets an explicit ``(i, i, 0.0)``."""
+    n = space.n_dof
+    alpha = np.zeros(n) if alpha is None else alpha
+    res_g, jac_g = np.zeros(n), DokMatrix(n)
+    for kind, form, functions, n_items in forms:
+        for i in (range(n_items) if isinstance(n_items, int) else n_items):
+            dest = space.destination_indexes(i) if kind == "form" else space.bc_destination_indexes(i)
+            r_l, j_l = form(space, functions, i, alpha[dest])
+            scatter_rhs(res_g, r_l, dest)
+            data = j_l.ravel()
+            row, col = np.repeat(dest, len(dest)), np.tile(dest, len(dest))
+            for idx in np.where(np.logical_not(np.isclose(data, 1.0e-16)))[0]:
+                if upper and row[idx] > col[idx]:
+                    continue
+                jac_g.setValue(row=row[idx], col=col[idx], value=data[idx], addv=True)
+            if explicit_diagonal and kind == "form":
+                for idx in dest:
+                    jac_g.setValue(row=idx, col=idx, value=0.0, addv=True)
+    indptr, indices, data = jac_g.getValuesCSR()
+    return indptr, indices, data, res_g

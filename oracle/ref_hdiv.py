@@ -3,7 +3,7 @@
 H(div) pieces of the basix stand-in, written independently of ``nfempy_b200.basis.hdiv`` (numerical quadrature +
 ``numpy.linalg.solve`` here, exact rational arithmetic there):
 
-* ``tabulate``                -- RT_k (k = 1..3) / BDM_1 values and reference derivatives, ``[1+dim, nq, nphi, dim]``;
+* ``tabulate``                -- RT_k (k = 1..3) / BDM_1, BDM_2 values and reference derivatives, ``[1+dim, nq, nphi, dim]``;
 * ``entity_transformations``  -- signed permutations of the facet dof families, as explicit tables;
 * ``permute_and_transform``   -- R/src/basis/permute_and_transform.py:8-149 line by line (edge test in 2-D against the
   edge cell's own ``node_tags``, face table of six permutation cases, forced reflection of tagged faces with
@@ -111,8 +111,18 @@ def _element(family, dim, k):
             for d in range(dim):
                 rows.append(np.einsum("sm,qm->sq", space[:, d, :], val) @ (cw * q[:, i]))
                 entity.append((dim, 0))
-    if family == "BDM" and k >= 2:
-        raise NotImplementedError("oracle BDM degree >= 2")
+    if family == "BDM" and k == 2:
+        # interior moments against the Whitney edge functions lam_a grad lam_b - lam_b grad lam_a
+        cp, cw = ref_basis.gauss_jacobi(dim, qdeg)
+        val, _ = _mono_tab(exps, cp)
+        lam = np.concatenate([1.0 - cp.sum(axis=1, keepdims=True), cp], axis=1)
+        glam = np.concatenate([-np.ones((1, dim)), np.eye(dim)], axis=0)
+        for a, b in SUB[dim][1]:
+            w = lam[:, [a]] * glam[b][None, :] - lam[:, [b]] * glam[a][None, :]  # [nq, dim]
+            rows.append(np.einsum("scm,qm,qc,q->s", space, val, w, cw))
+            entity.append((dim, 0))
+    elif family == "BDM" and k > 2:
+        raise NotImplementedError("oracle BDM degree >= 3")
     D = np.array(rows)  # D[i, s]
     C = np.linalg.solve(D, np.eye(len(D)))  # phi_j = sum_s C[s, j] space_s
     coeffs = np.einsum("sj,scm->jcm", C, space)

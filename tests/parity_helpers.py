@@ -54,18 +54,20 @@ class Case:
         s.build_structures(self.tags, self.btags)
         return s
 
-    def run_gpu(self, allow_fused=True):
+    def run_gpu(self, allow_fused=True, **policy):
         from nfempy_b200.assembly import GPUAssembler
 
         space = self.space()
         alpha = np.zeros(space.n_dof) if self.alpha_fn is None else self.alpha_fn(space.n_dof)
-        asm = GPUAssembler(space, None, np.zeros(space.n_dof), allow_fused=allow_fused)
+        asm = GPUAssembler(space, None, np.zeros(space.n_dof), allow_fused=allow_fused, **policy)
         asm.form_to_input_list = self.gpu_forms(space, alpha)
         return asm.assemble()
 
-    def run_oracle(self):
+    def run_oracle(self, upper=None, explicit_diagonal=False):
         space = self.ref_space()
         alpha = np.zeros(space.n_dof) if self.alpha_fn is None else self.alpha_fn(space.n_dof)
+        if upper is not None:
+            return ref_assembly.assemble_filtered(space, self.ref_forms_fn(space), alpha, upper, explicit_diagonal)
         return ref_assembly.assemble(space, self.ref_forms_fn(space), alpha)
 
 

@@ -13,7 +13,8 @@ from oracle import ref_basis, ref_forms, ref_hdiv
 from oracle.ref_mesh import RefMesh
 from oracle.ref_spaces import RefProductSpace
 
-ELEMENTS = [("RT", 2, 1), ("RT", 2, 2), ("RT", 2, 3), ("RT", 3, 1), ("RT", 3, 2), ("RT", 3, 3), ("BDM", 2, 1), ("BDM", 3, 1)]
+ELEMENTS = [("RT", 2, 1), ("RT", 2, 2), ("RT", 2, 3), ("RT", 3, 1), ("RT", 3, 2), ("RT", 3, 3), ("BDM", 2, 1), ("BDM", 3, 1),
+            ("BDM", 2, 2), ("BDM", 3, 2)]
 
 
 @pytest.mark.parametrize("family,dim,k", ELEMENTS)
@@ -50,7 +51,7 @@ def test_divergence_theorem_and_lowest_order_normal_moments(family, dim, k):
     assert np.abs(lhs - rhs).max() <= 1e-12 * max(1.0, np.abs(lhs).max())
 
 
-@pytest.mark.parametrize("family,k", [("RT", 1), ("RT", 2), ("RT", 3), ("BDM", 1)])
+@pytest.mark.parametrize("family,k", [("RT", 1), ("RT", 2), ("RT", 3), ("BDM", 1), ("BDM", 2)])
 def test_orientation_tables_match_oracle(family, k):
     T3 = case_matrices(create_element(family, 3, k))
     rot, ref = ref_hdiv.entity_transformations(family, 3, k)["triangle"]

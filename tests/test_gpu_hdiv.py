@@ -20,9 +20,9 @@ def test_mixed_poisson_rt_2d(k):
     compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
 
 
-@pytest.mark.parametrize("dim", [2, 3])
-def test_mixed_poisson_bdm1(dim):
-    case = mixed_poisson_case(dim=dim, k=1, n=2, family="BDM")
+@pytest.mark.parametrize("dim,k", [(2, 1), (3, 1), (2, 2), (3, 2)])
+def test_mixed_poisson_bdm(dim, k):
+    case = mixed_poisson_case(dim=dim, k=k, n=2 if k == 1 else (1 if dim == 3 else 2), family="BDM")
     compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
 
 

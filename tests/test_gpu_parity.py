@@ -145,3 +145,12 @@ def test_unknown_form_raises():
     asm.form_to_input_list = {"x": ["form", range(6), HostOnly(space), np.zeros(space.n_dof)]}
     with pytest.raises(NotImplementedError):
         asm.scatter_forms()
+
+
+def test_example_driver_scatter_policy_primal_elasticity():
+    """cg_elasticity_example_1.py:92-145: filtered + upper + explicit diagonal for the volume form, filtered + upper for
+    the Dirichlet penalty form."""
+    case = elasticity_case(n=2, with_bc=True, k=2)
+    got = case.run_gpu(pattern_policy="filtered_upper", explicit_diagonal=True)
+    ref = case.run_oracle(upper=True, explicit_diagonal=True)
+    compare_csr(got, ref, RTOL)

@@ -57,3 +57,23 @@ def test_riesz_map_preconditioner_matrices(kind, dim, k):
     case = tensor_mixed_case(kind=kind, dim=dim, s_family=fam, m_family="RT", k=k, n=1 if dim == 3 else 2)
     got, ref = case.run_gpu(), case.run_oracle()
     compare_csr(got, ref, RTOL)
+
+
+@pytest.mark.parametrize("kind,m_family", [("lce_scaled", "RT"), ("lce", "BDM")])
+def test_reference_example_k_order_1_methods(kind, m_family):
+    """The k_order = 1 methods of R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py:641-658:
+    s in BDM_2, m in RT_2 (wc_rt) or BDM_2 (wc_bdm), u, t in P_1^disc -- 159 / 204 local dofs."""
+    case = tensor_mixed_case(kind=kind, dim=3, s_family="BDM", m_family=m_family, k=2, n=1)
+    compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
+
+
+@pytest.mark.parametrize("policy,diag", [("filtered", False), ("filtered_upper", True)])
+def test_example_driver_scatter_policies_cosserat(policy, diag):
+    """The scatter closure of mfe_cosserat_elasticity_example_3.py:150-176: value-filtered entries, upper triangle for
+    the symmetric storage, explicit diagonal zeros (the L2 multiplier blocks have an exactly zero diagonal)."""
+    case = tensor_mixed_case(kind="lce_scaled", dim=3, n=1, alpha=False)
+    got = case.run_gpu(pattern_policy=policy, explicit_diagonal=diag)
+    ref = case.run_oracle(upper=(policy == "filtered_upper"), explicit_diagonal=diag)
+    full = case.run_oracle()
+    assert len(ref[1]) < len(full[1])
+    compare_csr(got, ref, RTOL)
