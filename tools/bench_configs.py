@@ -154,7 +154,7 @@ def main():
     global ONLY
     ONLY = args.only
     from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
-    from tests.parity_helpers import elasticity_case, laplace_case, mixed_poisson_case
+    from tests.parity_helpers import degenerate_case, elasticity_case, laplace_case, mixed_poisson_case, tensor_mixed_case
 
     q = args.quick
     # config 1
@@ -181,6 +181,25 @@ def main():
     run_case("config3: 3D mixed Poisson RT3 x P2 disc + natural BC (40^3 x 6 tets: 31-bit local-entry index)",
              mixed_poisson_case(dim=3, k=3, mesh=mesh3s), mixed_poisson_case(dim=3, k=3, n=1), args.steps, args.warmup,
              oracle_cells=6)
+    # config 3, other form classes of the same spaces
+    mesh3d = box_tet_mesh(6 if q else 48, jitter=0.2)
+    run_case("config3: DegenerateEllipticWeakForm RT2 x P1 disc + BC", degenerate_case("degenerate", 3, 2, mesh=mesh3d),
+             degenerate_case("degenerate", 3, 2, n=2), args.steps, args.warmup, oracle_cells=20)
+    del mesh3d
+    # config 4: mixed Cosserat elasticity (scaled), the reference example's two methods.  Explicit local matrices:
+    # n_loc^2 * 12 B per cell bounds the mesh that fits (54 dofs: 35 kB / cell, 159 dofs: 303 kB / cell).
+    mesh4 = box_tet_mesh(4 if q else 30, jitter=0.2)
+    run_case("config4: LCEScaledDualWeakForm BDM1 x RT1 x P0 x P0 (k_order 0, 54 local dofs) + BC",
+             tensor_mixed_case("lce_scaled", 3, "BDM", "RT", 1, mesh=mesh4), tensor_mixed_case("lce_scaled", 3, n=1),
+             args.steps, args.warmup, oracle_cells=12)
+    run_case("config4: LCEScaledRieszMapWeakForm BDM1 x RT1 x P0 x P0 (preconditioner matrix)",
+             tensor_mixed_case("lce_scaled_riesz", 3, "BDM", "RT", 1, mesh=mesh4),
+             tensor_mixed_case("lce_scaled_riesz", 3, n=1), args.steps, args.warmup, oracle_cells=12)
+    del mesh4
+    mesh4b = box_tet_mesh(3 if q else 14, jitter=0.2)
+    run_case("config4: LCEScaledDualWeakForm BDM2 x RT2 x P1 x P1 (k_order 1, 159 local dofs) + BC",
+             tensor_mixed_case("lce_scaled", 3, "BDM", "RT", 2, mesh=mesh4b),
+             tensor_mixed_case("lce_scaled", 3, "BDM", "RT", 2, n=1), args.steps, args.warmup, oracle_cells=6)
 
 
 if __name__ == "__main__":
