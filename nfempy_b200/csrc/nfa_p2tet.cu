@@ -17,6 +17,7 @@
 // Inputs per (item, cell): one 32-bit packed entry (coalesced, ELL per warp) and one 32-byte record per vertex used,
 // fetched with 256-bit loads (LDG.E.256) from the per-cell geometry records (L1/L2 resident: 128 B per cell).
 #include <algorithm>
+#include <cstdlib>
 
 #include "nfa_plan.cuh"
 
@@ -75,8 +76,17 @@ __global__ void p2tet_geo_kernel(const double *__restrict__ coords, const int32_
     reinterpret_cast<double2 *>(r)[1] = make_double2(s2, rho);
 }
 
-// acc += Kf(u (x) w) without the trace part; returns u.w
+// acc += Kf(u (x) w) without the trace part; returns u.w.  CR (constant rho = lambda / mu over the mesh): acc += u (x) w
+// only -- Kf is applied once per block when the item is finished (fix_general), which halves the FP64 work.
+template <bool CR>
 __device__ __forceinline__ double add_general(double (&acc)[9], double rho, const double (&u)[3], const double (&w)[3]) {
+    if constexpr (CR) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s) acc[3 * r + s] = fma(u[r], w[s], acc[3 * r + s]);
+        return 0.0;
+    }
     const double ru[3] = {rho * u[0], rho * u[1], rho * u[2]};
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -85,9 +95,10 @@ __device__ __forceinline__ double add_general(double (&acc)[9], double rho, cons
     return fma(u[0], w[0], fma(u[1], w[1], u[2] * w[2]));
 }
 
-// acc (xx, xy, xz, yy, yz, zz) += (rho + 1) u u^T; returns |u|^2
+// acc (xx, xy, xz, yy, yz, zz) += (rho + 1) u u^T; returns |u|^2   (CR: acc += u u^T, see fix_sym)
+template <bool CR>
 __device__ __forceinline__ double add_sym(double (&acc)[6], double rho, const double (&u)[3]) {
-    const double r1 = rho + 1.0;
+    const double r1 = CR ? 1.0 : rho + 1.0;
     const double a = r1 * u[0], b = r1 * u[1], c = r1 * u[2];
     acc[0] = fma(a, u[0], acc[0]);
     acc[1] = fma(a, u[1], acc[1]);
@@ -96,6 +107,33 @@ __device__ __forceinline__ double add_sym(double (&acc)[6], double rho, const do
     acc[4] = fma(b, u[2], acc[4]);
     acc[5] = fma(c, u[2], acc[5]);
     return fma(u[0], u[0], fma(u[1], u[1], u[2] * u[2]));
+}
+
+// CR: turn the plain sums T = sum u (x) w into (Kf(T) without the trace part, tr T)
+template <bool CR>
+__device__ __forceinline__ void fix_general(double (&p)[9], double &tr, double rho) {
+    if constexpr (CR) {
+        tr = p[0] + p[4] + p[8];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            p[4 * r] *= rho + 1.0;
+#pragma unroll
+            for (int s = r + 1; s < 3; ++s) {
+                const double a = p[3 * r + s], b = p[3 * s + r];
+                p[3 * r + s] = fma(rho, a, b);
+                p[3 * s + r] = fma(rho, b, a);
+            }
+        }
+    }
+}
+
+template <bool CR>
+__device__ __forceinline__ void fix_sym(double (&q)[6], double &tr, double rho) {
+    if constexpr (CR) {
+        tr = q[0] + q[3] + q[5];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) q[i] *= rho + 1.0;
+    }
 }
 
 __device__ __forceinline__ void store_block(double *tile, unsigned where, unsigned pitch, const double (&k)[9]) {
@@ -158,35 +196,42 @@ __device__ __forceinline__ Rec<NG> load_rec(uint32_t code, const double *__restr
 
 constexpr double C10 = 0.1, C30 = 1.0 / 30.0, C15 = 2.0 / 15.0;
 
-template <int TYPE>
+template <int TYPE, bool CR>
 struct Item;
 
-template <>
-struct Item<0> {  // A: (v, v) = 0.1 Kf(g_i g_i^T)
+template <bool CR>
+struct Item<0, CR> {
+    double rho = 0.0;  // A: (v, v) = 0.1 Kf(g_i g_i^T)
     static constexpr int NG = 1;
     double q[6] = {0, 0, 0, 0, 0, 0}, tr = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
+        rho = r.g[0].rho;
         const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z};
-        tr += add_sym(q, r.g[0].rho, u);
+        tr += add_sym<CR>(q, r.g[0].rho, u);
     }
     __device__ __forceinline__ void finish(const TileCtx &ctx) {
         double o[9];
+        fix_sym<CR>(q, tr, rho);
         sym_to_full(q, C10, tr, o);
         ctx.put(0, o);
     }
 };
 
-template <>
-struct Item<1> {  // B: (v, v') = -1/30 P, (v, E) = 0.1 P - Q / 30 with P = Kf(g_i (x) g_k), Q = Kf(g_i g_i^T)
+template <bool CR>
+struct Item<1, CR> {
+    double rho = 0.0;  // B: (v, v') = -1/30 P, (v, E) = 0.1 P - Q / 30 with P = Kf(g_i (x) g_k), Q = Kf(g_i g_i^T)
     static constexpr int NG = 2;
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, q[6] = {0, 0, 0, 0, 0, 0}, trp = 0.0, trq = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
+        rho = r.g[0].rho;
         const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z}, w[3] = {r.g[1].x, r.g[1].y, r.g[1].z};
-        trp += add_general(p, r.g[0].rho, u, w);
-        trq += add_sym(q, r.g[0].rho, u);
+        trp += add_general<CR>(p, r.g[0].rho, u, w);
+        trq += add_sym<CR>(q, r.g[0].rho, u);
     }
     __device__ __forceinline__ void finish(const TileCtx &ctx) {
         double o[9];
+        fix_general<CR>(p, trp, rho);
+        fix_sym<CR>(q, trq, rho);
 #pragma unroll
         for (int i = 0; i < 9; i += 4) p[i] += trp;
 #pragma unroll
@@ -199,36 +244,44 @@ struct Item<1> {  // B: (v, v') = -1/30 P, (v, E) = 0.1 P - Q / 30 with P = Kf(g
     }
 };
 
-template <>
-struct Item<2> {  // C: (v, e_xy) = Kf(g_i (x) (g_i + g_z)) / 30, since g_x + g_y = -(g_i + g_z)
+template <bool CR>
+struct Item<2, CR> {
+    double rho = 0.0;  // C: (v, e_xy) = Kf(g_i (x) (g_i + g_z)) / 30, since g_x + g_y = -(g_i + g_z)
     static constexpr int NG = 2;
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, trp = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
+        rho = r.g[0].rho;
         const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z};
         const double w[3] = {u[0] + r.g[1].x, u[1] + r.g[1].y, u[2] + r.g[1].z};
-        trp += add_general(p, r.g[0].rho, u, w);
+        trp += add_general<CR>(p, r.g[0].rho, u, w);
     }
     __device__ __forceinline__ void finish(const TileCtx &ctx) {
         double o[9];
+        fix_general<CR>(p, trp, rho);
 #pragma unroll
         for (int i = 0; i < 9; ++i) o[i] = C30 * (p[i] + ((i % 4 == 0) ? trp : 0.0));
         ctx.put(0, o);
     }
 };
 
-template <>
-struct Item<3> {  // D: (E, v_i) = 0.1 P^T - Qi / 30, (E, v_j) = 0.1 P - Qj / 30, (E, E) = 2/15 (2 Qi + 2 Qj + P + P^T)
+template <bool CR>
+struct Item<3, CR> {
+    double rho = 0.0;  // D: (E, v_i) = 0.1 P^T - Qi / 30, (E, v_j) = 0.1 P - Qj / 30, (E, E) = 2/15 (2 Qi + 2 Qj + P + P^T)
     static constexpr int NG = 2;
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, qi[6] = {0, 0, 0, 0, 0, 0}, qj[6] = {0, 0, 0, 0, 0, 0};
     double trp = 0.0, tri = 0.0, trj = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
+        rho = r.g[0].rho;
         const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z}, w[3] = {r.g[1].x, r.g[1].y, r.g[1].z};
-        trp += add_general(p, r.g[0].rho, u, w);
-        tri += add_sym(qi, r.g[0].rho, u);
-        trj += add_sym(qj, r.g[0].rho, w);
+        trp += add_general<CR>(p, r.g[0].rho, u, w);
+        tri += add_sym<CR>(qi, r.g[0].rho, u);
+        trj += add_sym<CR>(qj, r.g[0].rho, w);
     }
     __device__ __forceinline__ void finish(const TileCtx &ctx) {
         double fi[9], fj[9], o[9];
+        fix_general<CR>(p, trp, rho);
+        fix_sym<CR>(qi, tri, rho);
+        fix_sym<CR>(qj, trj, rho);
         sym_to_full(qi, 1.0, tri, fi);
         sym_to_full(qj, 1.0, trj, fj);
 #pragma unroll
@@ -250,25 +303,30 @@ struct Item<3> {  // D: (E, v_i) = 0.1 P^T - Qi / 30, (E, v_j) = 0.1 P - Qj / 30
     }
 };
 
-template <>
-struct Item<4> {  // E: (E, v_x), (E, e_ix), (E, e_jx) with s = g_i + g_j
+template <bool CR>
+struct Item<4, CR> {
+    double rho = 0.0;  // E: (E, v_x), (E, e_ix), (E, e_jx) with s = g_i + g_j
     static constexpr int NG = 3;
     double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
+        rho = r.g[0].rho;
         const double rho = r.g[0].rho;
         const double a[3] = {r.g[0].x, r.g[0].y, r.g[0].z}, b[3] = {r.g[1].x, r.g[1].y, r.g[1].z};
         const double x[3] = {r.g[2].x, r.g[2].y, r.g[2].z};
         const double s[3] = {a[0] + b[0], a[1] + b[1], a[2] + b[2]};
         const double ax[3] = {a[0] + x[0], a[1] + x[1], a[2] + x[2]};
         const double bx[3] = {b[0] + x[0], b[1] + x[1], b[2] + x[2]};
-        t0 += add_general(k0, rho, s, x);
-        t1 += add_general(k1, rho, s, ax);
-        t1 += add_general(k1, rho, b, x);
-        t2 += add_general(k2, rho, s, bx);
-        t2 += add_general(k2, rho, a, x);
+        t0 += add_general<CR>(k0, rho, s, x);
+        t1 += add_general<CR>(k1, rho, s, ax);
+        t1 += add_general<CR>(k1, rho, b, x);
+        t2 += add_general<CR>(k2, rho, s, bx);
+        t2 += add_general<CR>(k2, rho, a, x);
     }
     __device__ __forceinline__ void finish(const TileCtx &ctx) {
+        fix_general<CR>(k0, t0, rho);
+        fix_general<CR>(k1, t1, rho);
+        fix_general<CR>(k2, t2, rho);
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             const bool d = (i % 4 == 0);
@@ -282,16 +340,19 @@ struct Item<4> {  // E: (E, v_x), (E, e_ix), (E, e_jx) with s = g_i + g_j
     }
 };
 
-template <>
-struct Item<5> {  // F: (E, E_opp) = -2/15 Kf(s s^T), since g_x + g_y = -(g_i + g_j)
+template <bool CR>
+struct Item<5, CR> {
+    double rho = 0.0;  // F: (E, E_opp) = -2/15 Kf(s s^T), since g_x + g_y = -(g_i + g_j)
     static constexpr int NG = 2;
     double q[6] = {0, 0, 0, 0, 0, 0}, tr = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
+        rho = r.g[0].rho;
         const double s[3] = {r.g[0].x + r.g[1].x, r.g[0].y + r.g[1].y, r.g[0].z + r.g[1].z};
-        tr += add_sym(q, r.g[0].rho, s);
+        tr += add_sym<CR>(q, r.g[0].rho, s);
     }
     __device__ __forceinline__ void finish(const TileCtx &ctx) {
         double o[9];
+        fix_sym<CR>(q, tr, rho);
         sym_to_full(q, -C15, tr, o);
         ctx.put(0, o);
     }
@@ -302,13 +363,13 @@ struct Item<5> {  // F: (E, E_opp) = -2/15 Kf(s s^T), since g_x + g_y = -(g_i + 
 // cell keep two cells in flight; type E (three records, 27 sums) walks one cell at a time to stay inside the register
 // budget.  pf0, pf1: first entries of the NEXT task -- their cells' records (one 128-byte line each) are pulled into L1
 // once this task's sums are complete.
-template <int TYPE>
+template <int TYPE, bool CR, int UNROLL_NG>
 __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kmax, uint32_t c0, uint32_t c1,
                                          const double *__restrict__ rec, uint32_t pf0, uint32_t pf1,
                                          const TileCtx &ctx) {
-    constexpr int NG = Item<TYPE>::NG;
-    Item<TYPE> item;
-    if constexpr (NG <= P2_UNROLL_NG) {
+    constexpr int NG = Item<TYPE, CR>::NG;
+    Item<TYPE, CR> item;
+    if constexpr (NG <= UNROLL_NG) {
 #pragma unroll 1
         for (int k = 0; k < kmax; k += 2) {
             const Rec<NG> r0 = load_rec<NG>(c0, rec), r1 = load_rec<NG>(c1, rec);
@@ -335,8 +396,8 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
 // Warps of a CTA pull tasks from the CTA's contiguous chunk range through one shared counter; chunk c lives in tile
 // (c - c_begin) % NBUF.  The warp that finishes the last task of a chunk sends the tile to HBM with one bulk copy,
 // waits until the copy engine has read it and hands the tile to chunk c + NBUF.  No CTA-wide barrier in the loop.
-template <int LOG_NBUF>
-__global__ void __launch_bounds__(P2_THREADS, 1)
+template <int LOG_NBUF, bool CR, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
     p2tet_elasticity_kernel(int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
                             const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
                             const double *__restrict__ rec, int tile_stride, const int32_t *__restrict__ cells_ptr,
@@ -408,12 +469,12 @@ __global__ void __launch_bounds__(P2_THREADS, 1)
             double *tile = smem + (size_t)b * tile_stride + ((th.x >> 16) & 1);
             const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it >> LOG_NBUF, ih.x, ih.y};
             switch (type) {
-                case 0: run_task<0>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                case 1: run_task<1>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                case 2: run_task<2>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                case 3: run_task<3>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                case 4: run_task<4>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                default: run_task<5>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 0: run_task<0, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 1: run_task<1, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 2: run_task<2, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 3: run_task<3, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 4: run_task<4, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                default: run_task<5, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -515,16 +576,30 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     const int nbuf = 1 << log_nbuf;
     const size_t smem = sizeof(double) * nbuf * (size_t)tile_stride + sizeof(int) * (4 + 2 * nbuf);
     if (smem > 220 * 1024) return fail("nfa_assemble_p2tet_elasticity: chunk tile exceeds the shared memory of an SM");
-    auto kern = log_nbuf == 2 ? p2tet_elasticity_kernel<2> : (log_nbuf == 1 ? p2tet_elasticity_kernel<1> : p2tet_elasticity_kernel<0>);
+    // both coefficients constant over the mesh: rho = lambda / mu is one number and Kf is applied once per block
+    const bool cr = (ls == 0 && ms == 0);
+    int threads = P2_THREADS;  // 512 (128 registers): more warps spill and lose (1.5 ms), see DESIGN.md
+    if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
+    using kern_t = void (*)(int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
+                            const int32_t *, const int32_t *, double *);
+    kern_t kern = nullptr;
+#define NFA_P2_PICK(LN, CRV, TH) \
+    if (log_nbuf == LN && cr == CRV && threads == TH) kern = p2tet_elasticity_kernel<LN, CRV, TH>;
+#define NFA_P2_PICK_T(LN, CRV) NFA_P2_PICK(LN, CRV, 384) NFA_P2_PICK(LN, CRV, 448) NFA_P2_PICK(LN, CRV, 512)
+    NFA_P2_PICK_T(0, false) NFA_P2_PICK_T(1, false) NFA_P2_PICK_T(2, false)
+    NFA_P2_PICK_T(0, true) NFA_P2_PICK_T(1, true) NFA_P2_PICK_T(2, true)
+#undef NFA_P2_PICK_T
+#undef NFA_P2_PICK
+    if (!kern) return fail("nfa_assemble_p2tet_elasticity: NFA_P2TET_THREADS must be 384, 448 or 512");
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, device = 0, n_sm = 148;
     NFA_CUDA(cudaGetDevice(&device));
     NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-    NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, P2_THREADS, smem));
+    NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) return fail("nfa_assemble_p2tet_elasticity: kernel does not fit on an SM");
     const int64_t grid = std::min<int64_t>(it.n_chunks, (int64_t)n_sm * per_sm);
     if (timing_enabled()) timing_begin(s);
-    kern<<<(unsigned)grid, P2_THREADS, smem, s>>>((int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
+    kern<<<(unsigned)grid, threads, smem, s>>>((int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
                                                   (const int4 *)it.task_hdr.p, (const uint2 *)it.item_hdr.p,
                                                   (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride,
                                                   (const int32_t *)it.cells_ptr.p, (const int32_t *)it.cells.p, vals);
