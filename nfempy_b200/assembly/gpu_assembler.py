@@ -209,7 +209,8 @@ class GPUAssembler:
         bcols = torch.empty(n_blocks, dtype=torch.int32, device=dev.device)
         _lib.check(lib.nfa_bplan_block_pattern(p.bplan, _lib.ptr(bptr), _lib.ptr(bcols), stream), "nfa_bplan_block_pattern")
         cap = int(os.environ.get("NFA_P2TET_CAP", "640"))
-        items = p2_items.build(node_dest.to(torch.int64), bptr.to(torch.int64), bcols.to(torch.int64), n_nodes, cap=cap)
+        items = p2_items.build(node_dest.to(torch.int64), bptr.to(torch.int64), bcols.to(torch.int64), n_nodes, cap=cap,
+                               lane_order=os.environ.get("NFA_P2TET_LANES", "cell"))
         _lib.check(
             lib.nfa_bplan_set_p2_items(
                 p.bplan, items["n_chunks"], _lib.ptr(items["chunk_hdr"]), items["n_tasks"], _lib.ptr(items["task_hdr"]),

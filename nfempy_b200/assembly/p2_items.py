@@ -79,7 +79,7 @@ def _templates():
 TEMPLATES = _templates()  # 4 * 7 + 6 * 4 = 52 entries per cell
 
 
-def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8):
+def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8, lane_order="cell"):
     """``node_dest`` int64 [n_cells, 10] global node of each local P2 node, ``bptr``/``bcols`` the block CSR of the
     matrix (int64 tensors on the same device).  Returns a dict of tensors (see module docstring) and sizes."""
     dev = node_dest.device
@@ -154,10 +154,18 @@ def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8):
     item_end = torch.cat([item_start[1:], torch.tensor([key.shape[0]], device=dev)])
     item_count = item_end - item_start
     item_key = key[item_start] >> 31  # chunk | type
-    # inside a (chunk, type) group order items by descending count: lanes of a task then run about equally long
-    ikey2 = (item_key << 16) | (65535 - torch.clamp(item_count, max=65535))
+    # order of the items (= lanes) inside a (chunk, type) group:
+    #   "cell"  by the first cell they read: neighbouring lanes then read the same 128-byte geometry records in the same
+    #           instruction (one L1 wavefront per distinct line), at the price of some spread in the loop counts;
+    #   "count" by descending count: lanes of a task run equally long.
+    if lane_order == "cell":
+        ikey2 = (item_key << 26) | (code[item_start] >> 6)
+        shift = 26
+    else:
+        ikey2 = (item_key << 16) | (65535 - torch.clamp(item_count, max=65535))
+        shift = 16
     ikey2, iperm = torch.sort(ikey2, stable=True)
-    grp = ikey2 >> 16
+    grp = ikey2 >> shift
     gfirst = torch.ones_like(grp, dtype=torch.bool)
     gfirst[1:] = grp[1:] != grp[:-1]
     gstart = torch.nonzero(gfirst).reshape(-1)

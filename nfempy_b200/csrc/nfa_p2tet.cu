@@ -43,7 +43,11 @@ struct G4 {
 
 __device__ __forceinline__ G4 ldg256(const double *p) {
     G4 g;
+#ifdef NFA_P2_PLAIN_LD
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(g.x), "=d"(g.y), "=d"(g.z), "=d"(g.rho) : "l"(p));
+#else
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(g.x), "=d"(g.y), "=d"(g.z), "=d"(g.rho) : "l"(p));
+#endif
     return g;
 }
 
@@ -368,8 +372,28 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
                                          const double *__restrict__ rec, uint32_t pf0, uint32_t pf1,
                                          const TileCtx &ctx) {
     constexpr int NG = Item<TYPE, CR>::NG;
+    // cells in flight per iteration: long items with few sums walk many cells at once (their task would otherwise
+    // hold its chunk's tile for tens of dependent load latencies); type E stays at one (register budget)
+    constexpr int U = (TYPE == 0) ? 8 : ((TYPE == 1) ? 4 : ((NG <= UNROLL_NG) ? 2 : 1));
     Item<TYPE, CR> item;
-    if constexpr (NG <= UNROLL_NG) {
+    if constexpr (U > 2) {
+        uint32_t c[U];
+        c[0] = c0;
+        c[1] = c1;
+#pragma unroll
+        for (int u = 2; u < U; ++u) c[u] = (u < kmax) ? __ldg(e + 32 * u) : 0xFFFFFFFFu;
+#pragma unroll 1
+        for (int k = 0; k < kmax; k += U) {
+            Rec<NG> r[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) r[u] = load_rec<NG>(c[u], rec);
+#pragma unroll
+            for (int u = 0; u < U; ++u) c[u] = (k + U + u < kmax) ? __ldg(e + 32 * (k + U + u)) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (r[u].valid) item.add(r[u]);
+        }
+    } else if constexpr (U == 2) {
 #pragma unroll 1
         for (int k = 0; k < kmax; k += 2) {
             const Rec<NG> r0 = load_rec<NG>(c0, rec), r1 = load_rec<NG>(c1, rec);
@@ -572,6 +596,7 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     NFA_LAUNCH_CHECK();
     const int tile_stride = (9 * it.max_tile_blocks + 2 + 15) & ~15;  // doubles; keeps both tiles 128-byte aligned
     int log_nbuf = 2;  // 4, 2 or 1 tiles: as many as fit in 200 KB of shared memory
+    if (const char *e = getenv("NFA_P2TET_LOG_NBUF")) log_nbuf = std::max(0, std::min(2, atoi(e)));
     while (log_nbuf > 0 && sizeof(double) * ((size_t)tile_stride << log_nbuf) > 200 * 1024) --log_nbuf;
     const int nbuf = 1 << log_nbuf;
     const size_t smem = sizeof(double) * nbuf * (size_t)tile_stride + sizeof(int) * (4 + 2 * nbuf);
