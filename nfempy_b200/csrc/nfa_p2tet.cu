@@ -420,13 +420,12 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
 // Warps of a CTA pull tasks from the CTA's contiguous chunk range through one shared counter; chunk c lives in tile
 // (c - c_begin) % NBUF.  The warp that finishes the last task of a chunk sends the tile to HBM with one bulk copy,
 // waits until the copy engine has read it and hands the tile to chunk c + NBUF.  No CTA-wide barrier in the loop.
-template <int LOG_NBUF, bool CR, int THREADS>
+template <bool CR, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
-    p2tet_elasticity_kernel(int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
+    p2tet_elasticity_kernel(int NBUF, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
                             const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
                             const double *__restrict__ rec, int tile_stride, const int32_t *__restrict__ cells_ptr,
                             const int32_t *__restrict__ cells, double *__restrict__ vals) {
-    constexpr int NBUF = 1 << LOG_NBUF;
     extern __shared__ __align__(128) double smem[];  // NBUF tiles of tile_stride doubles, then the control words
     // ctrl: [0] next task, [1] c_begin, [2] c_end, [3] task_end, [4 .. 4+NBUF) tasks left per tile, then free_at per tile.
     // Everything the tail of an iteration needs is re-read from here / from the (L1-resident) headers instead of being
@@ -488,10 +487,10 @@ __global__ void __launch_bounds__(THREADS, 1)
             const uint32_t *e = ell + (uint32_t)th.y + lane;
             uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
             if (lane < n_items) ih = __ldg(item_hdr + th.z + lane);
-            const int it = c - ctrl[1], b = it & (NBUF - 1);
+            const int it = c - ctrl[1], b = it % NBUF;
             // the tile sits on the same 16-byte phase as its image in vals (parity of the chunk's first block)
             double *tile = smem + (size_t)b * tile_stride + ((th.x >> 16) & 1);
-            const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it >> LOG_NBUF, ih.x, ih.y};
+            const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y};
             switch (type) {
                 case 0: run_task<0, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
                 case 1: run_task<1, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
@@ -505,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
             const int c = (int)((unsigned)th.w >> 6), c_begin = ctrl[1], c_end = ctrl[2];
-            const int it = c - c_begin, b = it & (NBUF - 1);
+            const int it = c - c_begin, b = it % NBUF;
             __threadfence_block();
             if (atomicSub(const_cast<int *>(ctrl) + 4 + b, 1) == 1) {  // the chunk's last task: the tile is complete
                 __threadfence_block();
@@ -527,7 +526,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 ctrl[4 + b] = (c + NBUF < c_end) ? __ldg(chunk_hdr + c + NBUF).w : 0;
                 __threadfence_block();
-                ctrl[4 + NBUF + b] = (it >> LOG_NBUF) + 1;
+                ctrl[4 + NBUF + b] = it / NBUF + 1;
             }
         }
         th = th1;
@@ -595,25 +594,23 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
                                                                 (double *)it.rec.p);
     NFA_LAUNCH_CHECK();
     const int tile_stride = (9 * it.max_tile_blocks + 2 + 15) & ~15;  // doubles; keeps both tiles 128-byte aligned
-    int log_nbuf = 2;  // 4, 2 or 1 tiles: as many as fit in 200 KB of shared memory
-    if (const char *e = getenv("NFA_P2TET_LOG_NBUF")) log_nbuf = std::max(0, std::min(2, atoi(e)));
-    while (log_nbuf > 0 && sizeof(double) * ((size_t)tile_stride << log_nbuf) > 200 * 1024) --log_nbuf;
-    const int nbuf = 1 << log_nbuf;
+    // as many tiles as fit in 220 KB of shared memory (at most 8): the more chunks are in flight, the less a long task
+    // (a vertex-star item walks ~24 cells) delays the hand-over of its chunk's tile
+    int nbuf = (int)std::min<size_t>(8, (220 * 1024) / (sizeof(double) * (size_t)tile_stride));
+    if (const char *e = getenv("NFA_P2TET_NBUF")) nbuf = std::min(nbuf, std::max(1, atoi(e)));
+    if (nbuf < 1) return fail("nfa_assemble_p2tet_elasticity: chunk tile exceeds the shared memory of an SM");
     const size_t smem = sizeof(double) * nbuf * (size_t)tile_stride + sizeof(int) * (4 + 2 * nbuf);
-    if (smem > 220 * 1024) return fail("nfa_assemble_p2tet_elasticity: chunk tile exceeds the shared memory of an SM");
     // both coefficients constant over the mesh: rho = lambda / mu is one number and Kf is applied once per block
     const bool cr = (ls == 0 && ms == 0);
     int threads = P2_THREADS;  // 512 (128 registers): more warps spill and lose (1.5 ms), see DESIGN.md
     if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
-    using kern_t = void (*)(int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
+    using kern_t = void (*)(int, int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
                             const int32_t *, const int32_t *, double *);
     kern_t kern = nullptr;
-#define NFA_P2_PICK(LN, CRV, TH) \
-    if (log_nbuf == LN && cr == CRV && threads == TH) kern = p2tet_elasticity_kernel<LN, CRV, TH>;
-#define NFA_P2_PICK_T(LN, CRV) NFA_P2_PICK(LN, CRV, 384) NFA_P2_PICK(LN, CRV, 448) NFA_P2_PICK(LN, CRV, 512)
-    NFA_P2_PICK_T(0, false) NFA_P2_PICK_T(1, false) NFA_P2_PICK_T(2, false)
-    NFA_P2_PICK_T(0, true) NFA_P2_PICK_T(1, true) NFA_P2_PICK_T(2, true)
-#undef NFA_P2_PICK_T
+#define NFA_P2_PICK(CRV, TH) \
+    if (cr == CRV && threads == TH) kern = p2tet_elasticity_kernel<CRV, TH>;
+    NFA_P2_PICK(false, 384) NFA_P2_PICK(false, 448) NFA_P2_PICK(false, 512)
+    NFA_P2_PICK(true, 384) NFA_P2_PICK(true, 448) NFA_P2_PICK(true, 512)
 #undef NFA_P2_PICK
     if (!kern) return fail("nfa_assemble_p2tet_elasticity: NFA_P2TET_THREADS must be 384, 448 or 512");
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -624,7 +621,7 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     if (per_sm < 1) return fail("nfa_assemble_p2tet_elasticity: kernel does not fit on an SM");
     const int64_t grid = std::min<int64_t>(it.n_chunks, (int64_t)n_sm * per_sm);
     if (timing_enabled()) timing_begin(s);
-    kern<<<(unsigned)grid, threads, smem, s>>>((int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
+    kern<<<(unsigned)grid, threads, smem, s>>>(nbuf, (int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
                                                   (const int4 *)it.task_hdr.p, (const uint2 *)it.item_hdr.p,
                                                   (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride,
                                                   (const int32_t *)it.cells_ptr.p, (const int32_t *)it.cells.p, vals);
