@@ -248,6 +248,17 @@ int nfa_local_hdiv_facet_vec(int dim, int nfd, int n_q, int n_comp, const double
                              const double *d_normals, const double *d_g, int64_t n_facets, double sign, int re_off,
                              int re_stride, double *d_re, nfa_stream stream);
 
+/* ---- error norms of a discrete solution: l2_error (R/src/postprocess/l2_error_post_processor.py:7-63) and div_error
+ * (:185-237).  kind 0: Lagrange field (val [n_q, n_phi]); kind 1: values of a row-wise H(div) field (val
+ * [n_q, n_phi, dim] reference values, exact [n, n_q, n_comp, dim]); kind 2: its divergence (dv [n_q, n_phi] reference
+ * divergence, exact [n, n_q, n_comp]).  d_alpha is the global vector, read through d_dest[cell, dest_off + a n_comp + c]
+ * (rows of dest_stride entries).  d_out [n_cells] receives each cell's squared-error contribution. */
+int nfa_field_error(int dim, int kind, int n_phi, int n_comp, int n_q, int nfd, const double *d_val,
+                    const double *d_div, const double *d_weights, const double *d_Tcases, const int8_t *d_cases,
+                    const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_alpha,
+                    const int32_t *d_dest, int dest_stride, int dest_off, const double *d_exact, double *d_out,
+                    nfa_stream stream);
+
 /* ---- row-item fused path for vector-P2 elasticity on affine tetrahedra (config 2's headline kernel).
  * Same plan object, same output (all nnz values of the pattern, written once, deterministic) as
  * nfa_assemble_h1_elasticity_affine, i.e. the matrix part of LEPrimalWeakForm.evaluate_form

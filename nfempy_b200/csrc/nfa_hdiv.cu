@@ -623,3 +623,117 @@ extern "C" int nfa_local_hdiv_facet_vec(int dim, int nfd, int n_q, int n_comp, c
     NFA_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- error norms of a discrete field (R/src/postprocess/l2_error_post_processor.py:7-63 l2_error, :185-237 div_error)
+// One warp per cell, one lane per quadrature point: the discrete field (or its divergence) is evaluated at the point
+// from the global vector alpha through the cell's destination indices and compared with host-evaluated exact values.
+//   kind 0  Lagrange, n_comp components:      err = sum_q w det sum_c (e_c - sum_a phi_a alpha_{a,c})^2
+//   kind 1  H(div) values, rows c of a tensor: err = sum_q w det sum_{c,d} (e_{c,d} - sum_a psi_a[d] alpha_{a,c})^2
+//   kind 2  H(div) divergence:                 err = sum_q w det sum_c (e_c - sum_a div psi_a alpha_{a,c})^2
+// out[cell] = the cell's contribution (summed by the caller in cell order: deterministic).
+template <int DIM>
+__global__ void __launch_bounds__(128)
+    field_error_kernel(int kind, int n_phi, int n_comp, int n_q, int nfd, const double *__restrict__ val,
+                       const double *__restrict__ dv, const double *__restrict__ weights,
+                       const double *__restrict__ Tcases, const int8_t *__restrict__ cases,
+                       const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes, int64_t n_cells,
+                       const double *__restrict__ alpha, const int32_t *__restrict__ dest, int dest_stride,
+                       int dest_off, const double *__restrict__ exact, double *__restrict__ out) {
+    constexpr int NF = DIM + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t cell = (int64_t)blockIdx.x * 4 + warp; cell < n_cells; cell += (int64_t)gridDim.x * 4) {
+        double X[DIM + 1][3];
+        load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+        Geom<DIM> g;
+        compute_geom<DIM>(X, g);
+        const double idet = 1.0 / g.det;
+        const int32_t *dd = dest + cell * dest_stride + dest_off;
+        const int n_e = kind == 1 ? n_comp * DIM : n_comp;  // exact values per point
+        double err = 0.0;
+        for (int q = lane; q < n_q; q += 32) {
+            double loc = 0.0;
+            for (int c = 0; c < n_comp; ++c) {
+                double uh[DIM];  // kind 1: the row c of the tensor; else only uh[0]
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) uh[d] = 0.0;
+                for (int a = 0; a < n_phi; ++a) {
+                    const double al = alpha[dd[a * n_comp + c]];
+                    if (kind == 0) {
+                        uh[0] += val[q * n_phi + a] * al;
+                        continue;
+                    }
+                    double vh[DIM], dh = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) vh[k] = 0.0;
+                    if (a < NF * nfd) {
+                        const int fc = a / nfd, ai = a - fc * nfd;
+                        const double *T = Tcases + (int)cases[cell * NF + fc] * nfd * nfd + ai * nfd;
+                        for (int b = 0; b < nfd; ++b) {
+                            const double *src = val + ((int64_t)q * n_phi + fc * nfd + b) * DIM;
+#pragma unroll
+                            for (int k = 0; k < DIM; ++k) vh[k] += T[b] * src[k];
+                            dh += T[b] * dv[q * n_phi + fc * nfd + b];
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) vh[k] = val[((int64_t)q * n_phi + a) * DIM + k];
+                        dh = dv[q * n_phi + a];
+                    }
+                    if (kind == 2) {
+                        uh[0] += dh * idet * al;
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) {
+                            double v = 0.0;
+#pragma unroll
+                            for (int k = 0; k < DIM; ++k) v += g.J[d][k] * vh[k];
+                            uh[d] += v * idet * al;
+                        }
+                    }
+                }
+                const double *ex = exact + ((int64_t)cell * n_q + q) * n_e;
+                if (kind == 1) {
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d) {
+                        const double df = ex[c * DIM + d] - uh[d];
+                        loc += df * df;
+                    }
+                } else {
+                    const double df = ex[c] - uh[0];
+                    loc += df * df;
+                }
+            }
+            err += weights[q] * g.det * loc;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o);
+        if (lane == 0) out[cell] = err;
+    }
+}
+
+extern "C" int nfa_field_error(int dim, int kind, int n_phi, int n_comp, int n_q, int nfd, const double *val,
+                               const double *dv, const double *weights, const double *Tcases, const int8_t *cases,
+                               const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *alpha,
+                               const int32_t *dest, int dest_stride, int dest_off, const double *exact, double *out,
+                               nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (kind < 0 || kind > 2) return fail("nfa_field_error: kind must be 0 (Lagrange), 1 (H(div) value) or 2 (H(div) divergence)");
+    if (kind != 0 && (!dv || !Tcases || !cases)) return fail("nfa_field_error: H(div) tables missing");
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t ctas = (n_cells + 3) / 4;
+    int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
+#define NFA_FE(D)                                                                                              \
+    field_error_kernel<D><<<grid, 128, 0, s>>>(kind, n_phi, n_comp, n_q, nfd, val, dv, weights, Tcases, cases, \
+                                               coords, cell_nodes, n_cells, alpha, dest, dest_stride, dest_off, exact, out)
+    if (dim == 3)
+        NFA_FE(3);
+    else if (dim == 2)
+        NFA_FE(2);
+    else if (dim == 1 && kind == 0)
+        NFA_FE(1);
+    else
+        return fail("nfa_field_error: unsupported dimension");
+#undef NFA_FE
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
