@@ -233,6 +233,14 @@ class GPUAssembler:
             for (_, kind, items, form, al) in entries
         ]
         dests = [self._dest_dev(dev, form, items) for (_, _, items, form, _) in entries]
+        # state vectors are scanned for zeros and uploaded here, once per prepare(): on a 4 M-dof problem that host work
+        # takes longer than the device needs for a whole assembly, so run(state) must not repeat it
+        for (_, kind, _, _, alpha), data in zip(entries, datas):
+            if "time_dependent" in kind:
+                (first, second), _t = alpha
+                data.alpha_dev = (self._upload(dev, first), self._upload(dev, second) if kind == "time_dependent_form" else None)
+            else:
+                data.alpha_dev = self._upload(dev, alpha)
         fused_index = None
         if self.pattern_policy != "full":
             return dev, entries, datas, dests, None, None  # the pattern depends on the values: built in run()
@@ -246,6 +254,12 @@ class GPUAssembler:
             self._plans[key] = self._build_plan(dev, entries, dests, fused_index)
         plan = self._plans[key]
         return dev, entries, datas, dests, plan, key
+
+    @staticmethod
+    def _upload(dev, vec):
+        if vec is None or not np.any(np.asarray(vec) != 0.0):
+            return None
+        return torch.as_tensor(np.ascontiguousarray(vec, dtype=np.float64)).to(dev.device)
 
     def run(self, state, rhs_dev=None):
         """Launches the kernels of one assembly.  Adds into ``self.jacobian`` and returns the device residual."""
@@ -263,15 +277,9 @@ class GPUAssembler:
             rhs_dev = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
         nseg = len(entries)
         Ke_list, re_list, keep = [None] * nseg, [None] * nseg, []
-        def upload(vec):
-            if vec is None or not np.any(np.asarray(vec) != 0.0):
-                return None
-            return torch.as_tensor(np.ascontiguousarray(vec, dtype=np.float64)).to(dev.device)
-
         for i, ((_, kind, _, form, alpha), data, dest) in enumerate(zip(entries, datas, dests)):
             if "time_dependent" in kind:
-                (first, second), _t = alpha
-                first_dev, second_dev = upload(first), (upload(second) if kind == "time_dependent_form" else None)
+                first_dev, second_dev = data.alpha_dev
                 nl = form.n_loc()
                 Ke = torch.empty((data.n_items, nl, nl), dtype=torch.float64, device=dev.device)
                 re = torch.empty((data.n_items, nl), dtype=torch.float64, device=dev.device)
@@ -279,7 +287,7 @@ class GPUAssembler:
                 Ke_list[i], re_list[i] = Ke, re
                 keep += [Ke, re, first_dev, second_dev]
                 continue
-            alpha_dev = upload(alpha)
+            alpha_dev = data.alpha_dev
             if i == plan.fused_index:
                 spec = form.fused_spec(data)
                 target = jac.values_dev if jac.is_zero else torch.empty_like(jac.values_dev)
@@ -321,6 +329,34 @@ class GPUAssembler:
         self._keep = keep  # buffers must outlive the stream-ordered kernels
         return rhs_dev
 
+    def capture(self, state, rhs_dev):
+        """CUDA graph of one fresh assembly (``rhs_dev`` zeroed, every CSR value overwritten) on the buffers of ``state``:
+        ``graph.replay()`` re-runs the kernels without the per-launch host work -- for time / Newton loops that
+        reassemble on one plan (the state vectors captured are the device copies made by ``prepare()``; refresh them
+        in place with ``data.alpha_dev.copy_(...)`` between replays).  Full pattern policy only."""
+        if state[4] is None:
+            raise _lib.NfaError("GPUAssembler.capture: value-dependent pattern policies rebuild the plan every assembly")
+        dev = state[0]
+
+        def body():
+            self.jacobian.is_zero = True
+            rhs_dev.zero_()
+            self.run(state, rhs_dev)
+
+        body()  # binds the pattern, allocates the values
+        cur = torch.cuda.current_stream(dev.device)
+        side = torch.cuda.Stream(device=dev.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            body()
+            body()
+        cur.wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        self._graph_keep = self._keep
+        return graph
+
     def _run_filtered(self, state, rhs_dev):
         """Value-dependent pattern: local blocks first, then masks, then a plan over the kept entries."""
         dev, entries, datas, dests, _, _ = state
@@ -338,9 +374,7 @@ class GPUAssembler:
         for (_, kind, _, form, alpha), data, dest in zip(entries, datas, dests):
             if "time_dependent" in kind:
                 raise NotImplementedError("GPUAssembler: filtered patterns are implemented for form / bc_form lists")
-            alpha_dev = None
-            if alpha is not None and np.any(np.asarray(alpha) != 0.0):
-                alpha_dev = torch.as_tensor(np.ascontiguousarray(alpha, dtype=np.float64)).to(dev.device)
+            alpha_dev = data.alpha_dev
             Ke, re = form.local_blocks(dev, data, alpha_dev, dest if alpha_dev is not None else None)
             value_kept = (Ke - 1.0e-16).abs() > tol
             mask = value_kept.clone()
