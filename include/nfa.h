@@ -276,6 +276,13 @@ int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *d_chu
                            const uint32_t *d_ell, int max_tile_blocks, const int32_t *d_chunk_cells_ptr,
                            int64_t n_chunk_cells, const int32_t *d_chunk_cells, nfa_stream stream);
 int nfa_bplan_has_p2_items(const nfa_bplan *bp);
+/* Optional lists of the shared-memory staged variant of the same kernel (chunk-relative task headers, ELL entries
+ * naming cells by their slot in the chunk's cell list, per-chunk copy extents [ell0, n_ell, item0, n_items] and the
+ * per-chunk maxima that size the buffers).  With them nfa_assemble_p2tet_elasticity stages every chunk's inputs in
+ * shared memory by bulk copies; without them (or with NFA_P2TET_STAGE=0) it reads them with global loads. */
+int nfa_bplan_set_p2_stage(nfa_bplan *bp, const int32_t *d_chunk_ext, const int32_t *d_task_hdr_rel,
+                           const uint32_t *d_ell_local, int max_chunk_cells, int max_chunk_ell, int max_chunk_items,
+                           int max_chunk_tasks, nfa_stream stream);
 int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *d_coords, const int32_t *d_cell_nodes,
                                   const double *d_lambda, int64_t lambda_stride, const double *d_mu,
                                   int64_t mu_stride, double *d_vals, nfa_stream stream);

@@ -220,6 +220,13 @@ class GPUAssembler:
             ),
             "nfa_bplan_set_p2_items",
         )
+        _lib.check(
+            lib.nfa_bplan_set_p2_stage(
+                p.bplan, _lib.ptr(items["chunk_ext"]), _lib.ptr(items["task_hdr_rel"]), _lib.ptr(items["ell_local"]),
+                items["max_chunk_cells"], items["max_chunk_ell"], items["max_chunk_items"], items["max_chunk_tasks"], stream,
+            ),
+            "nfa_bplan_set_p2_stage",
+        )
         p.p2_stats = {k: v for k, v in items.items() if isinstance(v, int)}
 
     # ------------------------------------------------------------------------------------------

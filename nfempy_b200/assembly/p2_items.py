@@ -241,7 +241,29 @@ def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8, lane_or
     chunk_cells_ptr = torch.zeros(n_chunks + 1, dtype=torch.int64, device=dev)
     chunk_cells_ptr[1:] = torch.cumsum(torch.bincount(cell_chunk, minlength=n_chunks), 0)
     max_tile = int((c_b1 - c_b0).max().item())
+    # ---- staged variant: everything a chunk reads is copied to shared memory by bulk copies before its tasks run, so
+    # the ELL entries name the cell by its SLOT in the chunk's cell list and the task headers hold chunk-relative offsets
+    slot = torch.searchsorted(cc, (entry_chunk << 26) | (code >> 6)) - chunk_cells_ptr[entry_chunk]
+    ell_local = torch.full((ell_size,), NONE32, dtype=torch.int64, device=dev)
+    ell_local[ell_base[task_of_item[pos]] + r_in_item * 32 + lane[pos]] = (slot << 6) | (code & 63)
+    ell_end = torch.cat([ell_base[1:], torch.tensor([ell_size], device=dev)])
+    item_end_t = torch.cat([task_first_item[1:], torch.tensor([n_items], device=dev)])
+    last = task0 + ntask - 1
+    c_ell0, c_item0 = ell_base[task0], task_first_item[task0]
+    c_nell, c_nitem = ell_end[last] - c_ell0, item_end_t[last] - c_item0
+    item_src0 = c_item0 & ~1  # the bulk copy starts on a 16-byte boundary (item headers are 8 bytes)
+    item_copy = ((c_item0 + c_nitem + 1) & ~1) - item_src0
+    chunk_ext = torch.stack([c_ell0, c_nell, item_src0, item_copy], dim=1)
+    task_hdr_rel = task_hdr.clone()
+    task_hdr_rel[:, 1] = ell_base - c_ell0[chunk_index_of_task]
+    task_hdr_rel[:, 2] = task_first_item - item_src0[chunk_index_of_task]
+    n_cc = chunk_cells_ptr[1:] - chunk_cells_ptr[:-1]
     return {
+        "ell_local": (ell_local & NONE32).to(torch.uint32 if hasattr(torch, "uint32") else torch.int64).contiguous(),
+        "chunk_ext": chunk_ext.to(torch.int32).contiguous(),
+        "task_hdr_rel": task_hdr_rel.to(torch.int32).contiguous(),
+        "max_chunk_cells": int(n_cc.max().item()), "max_chunk_ell": int(c_nell.max().item()),
+        "max_chunk_items": int(item_copy.max().item()), "max_chunk_tasks": int(ntask.max().item()),
         "chunk_hdr": chunk_hdr.to(torch.int32).contiguous(),
         "task_hdr": task_hdr.to(torch.int32).contiguous(),
         "item_hdr": item_hdr.to(torch.int32).to(torch.uint16 if hasattr(torch, "uint16") else torch.int16).contiguous(),
@@ -306,18 +328,33 @@ def item_blocks(typ, entries, rec):
     return K
 
 
-def walk(plan, rec, n_bnz):
-    """CSR block values ``[n_bnz * 9]`` in the scalar CSR order of the fused path (row pitch = 3 * blocks in row)."""
+def walk(plan, rec, n_bnz, staged=False):
+    """CSR block values ``[n_bnz * 9]`` in the scalar CSR order of the fused path (row pitch = 3 * blocks in row).
+    ``staged``: walk the lists of the shared-memory staged kernel instead (chunk-local copies of the ELL entries, item
+    headers, task headers and geometry records, addressed by chunk-relative offsets and cell slots)."""
     chunk_hdr = plan["chunk_hdr"].cpu().numpy().astype(np.int64)
-    task_hdr = plan["task_hdr"].cpu().numpy().astype(np.int64)
+    task_hdr = plan["task_hdr_rel" if staged else "task_hdr"].cpu().numpy().astype(np.int64)
     item_hdr = plan["item_hdr"].cpu().numpy().astype(np.int64) & 0xFFFF
-    ell = plan["ell"].cpu().numpy().astype(np.int64) & NONE32
+    ell = plan["ell_local" if staged else "ell"].cpu().numpy().astype(np.int64) & NONE32
+    if staged:
+        chunk_ext = plan["chunk_ext"].cpu().numpy().astype(np.int64)
+        cells_ptr = plan["chunk_cells_ptr"].cpu().numpy().astype(np.int64)
+        chunk_cells = plan["chunk_cells"].cpu().numpy().astype(np.int64)
     vals = np.full(n_bnz * 9, np.nan)
+    ell_all, item_all, rec_all = ell, item_hdr, rec
     for ci, (b0, nblk, task0, ntask) in enumerate(chunk_hdr):
         tile = np.full(nblk * 9, np.nan)
+        if staged:  # what the bulk copies put into the chunk's buffer
+            e0, ne, i0, ni = chunk_ext[ci]
+            assert e0 % 32 == 0 and ne % 32 == 0 and i0 % 2 == 0 and ni % 2 == 0
+            assert ne <= plan["max_chunk_ell"] and ni <= plan["max_chunk_items"] and ntask <= plan["max_chunk_tasks"]
+            ell, item_hdr = ell_all[e0 : e0 + ne], item_all[i0 : i0 + ni]
+            cl = chunk_cells[cells_ptr[ci] : cells_ptr[ci + 1]]
+            assert len(cl) <= plan["max_chunk_cells"]
+            rec = rec_all[cl]
         for t in range(task0, task0 + ntask):
             typ, kmax = task_hdr[t, 0] & 0xFF, (task_hdr[t, 0] >> 8) & 0xFF
-            assert (task_hdr[t, 0] >> 16) == (b0 & 1)
+            assert ((task_hdr[t, 0] >> 16) & 1) == (b0 & 1)
             base, item0, nit = task_hdr[t, 1], task_hdr[t, 2], task_hdr[t, 3] & 63
             assert task_hdr[t, 3] >> 6 == ci
             for lane in range(nit):

@@ -537,6 +537,254 @@ __global__ void __launch_bounds__(THREADS, 1)
     if ((threadIdx.x & 31) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+
+// =====================================================================================================================
+// Staged variant: no global load on the compute path.  Everything a chunk reads -- its ELL entries, item headers, task
+// headers and the 128-byte geometry records of the cells it touches (entries name a cell by its slot in the chunk's
+// cell list) -- is copied into the chunk's shared-memory buffer by bulk asynchronous copies (cp.async.bulk global ->
+// shared, completion counted on the buffer's mbarrier) issued when the buffer is handed over, i.e. NBUF chunks ahead of
+// use.  The warp that retires a chunk sends its tile to HBM, waits until the copy engine has read it and refills the
+// buffer for chunk c + NBUF; the mbarrier phase a task waits for therefore means "tile free and inputs present".
+struct StageLayout {
+    int rec_off, ell_off, item_off, task_off, buf_bytes;  // byte offsets inside a buffer (the tile sits at offset 0)
+};
+
+__device__ __forceinline__ G4 lds_g4(const double *p) {
+    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
+    return G4{a.x, a.y, b.x, b.y};
+}
+
+template <int NG>
+__device__ __forceinline__ Rec<NG> load_rec_s(uint32_t code, const double *rec_s) {
+    Rec<NG> r;
+    r.valid = code != 0xFFFFFFFFu;
+#pragma unroll
+    for (int m = 0; m < NG; ++m) r.g[m] = G4{0.0, 0.0, 0.0, 0.0};
+    if (r.valid) {
+        const double *rc = rec_s + (size_t)(code >> 6) * 16;
+        r.g[0] = lds_g4(rc + 4 * ((code >> 4) & 3u));
+        if constexpr (NG > 1) r.g[1] = lds_g4(rc + 4 * ((code >> 2) & 3u));
+        if constexpr (NG > 2) r.g[2] = lds_g4(rc + 4 * (code & 3u));
+    }
+    return r;
+}
+
+#ifndef NFA_P2S_UA
+#define NFA_P2S_UA 4
+#endif
+#ifndef NFA_P2S_U
+#define NFA_P2S_U 2
+#endif
+
+template <int TYPE, bool CR>
+__device__ __forceinline__ void run_task_s(const uint32_t *e, int kmax, const double *rec_s, const TileCtx &ctx) {
+    constexpr int NG = Item<TYPE, CR>::NG;
+    constexpr int U = (TYPE == 0) ? NFA_P2S_UA : ((TYPE == 4) ? 1 : NFA_P2S_U);
+    Item<TYPE, CR> item;
+#pragma unroll 1
+    for (int k = 0; k < kmax; k += U) {
+        uint32_t c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) c[u] = (k + u < kmax) ? e[32 * (k + u)] : 0xFFFFFFFFu;
+        Rec<NG> r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = load_rec_s<NG>(c[u], rec_s);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r[u].valid) item.add(r[u]);
+    }
+    item.finish(ctx);
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+template <bool CR, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+    p2tet_staged_kernel(int NBUF, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ chunk_ext,
+                        const int4 *__restrict__ task_hdr_rel, const uint2 *__restrict__ item_hdr,
+                        const uint32_t *__restrict__ ell_local, const int32_t *__restrict__ cells_ptr,
+                        const int32_t *__restrict__ cells, const double *__restrict__ rec, StageLayout L,
+                        int rec_tma, double *__restrict__ vals) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *ctrl_base = smem_raw + (size_t)NBUF * L.buf_bytes;
+    // ctrl: [0] next task, [1] c_begin, [2] c_end, [3] task_end, [4 .. 4+NBUF) tasks left in the buffer's chunk,
+    // [12 .. 12+NBUF) generation of the buffer = (chunk offset / NBUF) of the chunk it was last handed to.  A task first
+    // waits for its generation (monotonic, so a warp that ran 2 NBUF chunks ahead cannot mistake an older phase of the
+    // mbarrier for its own: the parity alone repeats every two phases), then for the mbarrier phase of that fill.
+    volatile int *ctrl = reinterpret_cast<volatile int *>(ctrl_base);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(ctrl_base + 128);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        const int c_begin = (int)((int64_t)n_chunks * blockIdx.x / gridDim.x);
+        const int c_end = (int)((int64_t)n_chunks * (blockIdx.x + 1) / gridDim.x);
+        ctrl[1] = c_begin;
+        ctrl[2] = c_end;
+        ctrl[0] = ctrl[3] = 0;
+        if (c_begin < c_end) {
+            ctrl[0] = __ldg(chunk_hdr + c_begin).z;
+            ctrl[3] = __ldg(chunk_hdr + c_end - 1).z + __ldg(chunk_hdr + c_end - 1).w;
+        }
+        for (int b = 0; b < NBUF; ++b) {
+            ctrl[4 + b] = 0;
+            ctrl[12 + b] = -1;
+            // arrivals per phase: lane 0's arrive.expect_tx + one deferred cp.async arrival per lane of the filling warp
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 33;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar + b)));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int c_begin = ctrl[1], c_end = ctrl[2], task_end = ctrl[3];
+
+    // hands buffer b to chunk cn: the whole warp issues the copies (one 128-byte record per lane and trip)
+    auto fill = [&](int b, int cn) {
+        const int4 ch = __ldg(chunk_hdr + cn), ex = __ldg(chunk_ext + cn);
+        const int cp0 = __ldg(cells_ptr + cn), n_cells = __ldg(cells_ptr + cn + 1) - cp0;
+        unsigned char *buf = smem_raw + (size_t)b * L.buf_bytes;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar + b);
+        if (lane == 0) {
+            ctrl[4 + b] = ch.w;
+            ctrl[12 + b] = (cn - c_begin) / NBUF;
+            __threadfence_block();
+            const uint32_t bytes = (rec_tma ? (uint32_t)n_cells * 128u : 0u) + (uint32_t)ex.y * 4u + (uint32_t)ex.w * 8u +
+                                   (uint32_t)ch.w * 16u;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            bulk_g2s(buf + L.ell_off, ell_local + ex.x, (uint32_t)ex.y * 4u, bar);
+            bulk_g2s(buf + L.item_off, item_hdr + ex.z, (uint32_t)ex.w * 8u, bar);
+            bulk_g2s(buf + L.task_off, task_hdr_rel + ch.z, (uint32_t)ch.w * 16u, bar);
+        }
+        // records.  The cell list is read with coalesced loads (128 cells per trip) before any copy is issued, so the
+        // copies do not wait on one dependent load each.  rec_tma: one bulk copy per 128-byte record line; else 16-byte
+        // asynchronous copies (LDGSTS, L2 only), eight per line, a warp trip moves four lines.  Completion is counted on
+        // the same mbarrier (bulk copies: bytes; LDGSTS: one deferred arrival per lane).
+        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(buf + L.rec_off);
+        for (int m0 = 0; m0 < n_cells; m0 += 128) {
+            int cid[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int q = m0 + 32 * m + lane;
+                cid[m] = q < n_cells ? __ldg(cells + cp0 + q) : 0;
+            }
+            if (rec_tma) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int q = m0 + 32 * m + lane;
+                    if (q < n_cells) bulk_g2s(buf + L.rec_off + (size_t)q * 128, rec + (size_t)cid[m] * 16, 128u, bar);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int q = m0 + 32 * m + 4 * jj + (lane >> 3);
+                        const int c = __shfl_sync(0xffffffffu, cid[m], 4 * jj + (lane >> 3));
+                        if (q < n_cells)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 128u * (uint32_t)q + 16u * (lane & 7)),
+                                         "l"(rec + (size_t)c * 16 + 2 * (lane & 7))
+                                         : "memory");
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+        // the lists the NEXT fill of this buffer starts with (chunk cn + NBUF; a CTA's chunks are contiguous in every
+        // array, so its cell list starts about NBUF lists further on) are pulled into L2 now
+        if (cn + NBUF < c_end) {
+            const void *pf = lane == 0   ? (const void *)(chunk_hdr + cn + NBUF)
+                             : lane == 1 ? (const void *)(chunk_ext + cn + NBUF)
+                             : lane == 2 ? (const void *)(cells_ptr + cn + NBUF)
+                                         : (const void *)(cells + cp0 + (size_t)(NBUF - 1) * n_cells + 32 * (lane - 3));
+            if (lane < 3 + 2 * NBUF) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        }
+    };
+    if (warp < NBUF && c_begin + warp < c_end) fill(warp, c_begin + warp);
+
+    int it = 0;  // the chunk (offset from c_begin) this warp's current task belongs to
+    int4 chh = make_int4(0, 0, 0, 0);
+    if (c_begin < c_end) chh = __ldg(chunk_hdr + c_begin);
+    int t = 0;
+    if (lane == 0) t = atomicAdd(const_cast<int *>(ctrl), 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    while (t < task_end) {
+        while (t >= chh.z + chh.w) {
+            ++it;
+            chh = __ldg(chunk_hdr + c_begin + it);
+        }
+        int tn = 0;  // next task: the round trip of the shared-memory atomic hides behind this task
+        if (lane == 0) tn = atomicAdd(const_cast<int *>(ctrl), 1);
+        const int b = it % NBUF;
+        {
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar + b), parity = (uint32_t)(it / NBUF) & 1u;
+            while (ctrl[12 + b] < it / NBUF) __nanosleep(64);
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(bar), "r"(parity)
+                    : "memory");
+            }
+        }
+        unsigned char *buf = smem_raw + (size_t)b * L.buf_bytes;
+        {
+            const int4 th = reinterpret_cast<const int4 *>(buf + L.task_off)[t - chh.z];
+            const int type = th.x & 0xFF, kmax = (th.x >> 8) & 0xFF, n_items = th.w & 63;
+            const uint32_t *e = reinterpret_cast<const uint32_t *>(buf + L.ell_off) + th.y + lane;
+            uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
+            if (lane < n_items) ih = reinterpret_cast<const uint2 *>(buf + L.item_off)[th.z + lane];
+            // the tile sits on the same 16-byte phase as its image in vals (parity of the chunk's first block)
+            double *tile = reinterpret_cast<double *>(buf) + ((th.x >> 16) & 1);
+            const double *rec_s = reinterpret_cast<const double *>(buf + L.rec_off);
+            const TileCtx ctx = {tile, nullptr, 0, ih.x, ih.y};
+            switch (type) {
+                case 0: run_task_s<0, CR>(e, kmax, rec_s, ctx); break;
+                case 1: run_task_s<1, CR>(e, kmax, rec_s, ctx); break;
+                case 2: run_task_s<2, CR>(e, kmax, rec_s, ctx); break;
+                case 3: run_task_s<3, CR>(e, kmax, rec_s, ctx); break;
+                case 4: run_task_s<4, CR>(e, kmax, rec_s, ctx); break;
+                default: run_task_s<5, CR>(e, kmax, rec_s, ctx); break;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            __threadfence_block();
+            last = atomicSub(const_cast<int *>(ctrl) + 4 + b, 1) == 1;  // the chunk's last task: the tile is complete
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            if (lane == 0) {
+                __threadfence_block();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const int b0 = chh.x, n_vals = 9 * chh.y, head = b0 & 1;
+                const int n_bulk = (n_vals - head) & ~1;
+                const double *tile = reinterpret_cast<const double *>(buf) + head;
+                double *dst = vals + (int64_t)9 * b0;
+                if (n_bulk > 0) {
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile + head);
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head),
+                                 "r"(src), "r"(n_bulk * 8)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (head) dst[0] = tile[0];
+                if (head + n_bulk < n_vals) dst[n_vals - 1] = tile[n_vals - 1];
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp();
+            const int cn = c_begin + it + NBUF;
+            if (cn < c_end) fill(b, cn);
+        }
+        t = __shfl_sync(0xffffffffu, tn, 0);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 }  // namespace
 
 extern "C" int nfa_bplan_block_pattern(const nfa_bplan *bp, int32_t *bptr, int32_t *bcols, nfa_stream stream) {
@@ -561,7 +809,7 @@ extern "C" int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int
     if ((int64_t)max_tile_blocks * 9 + 2 >= 65535) return fail("nfa_bplan_set_p2_items: tile exceeds 16-bit offsets");
     cudaStream_t s = (cudaStream_t)stream;
     nfa_bplan::P2Items &it = bp->p2;
-    if (it.chunk_hdr.alloc(16 * n_chunks) || it.task_hdr.alloc(16 * n_tasks) || it.item_hdr.alloc(8 * n_items) ||
+    if (it.chunk_hdr.alloc(16 * n_chunks) || it.task_hdr.alloc(16 * n_tasks) || it.item_hdr.alloc(8 * (n_items + 2)) ||
         it.ell.alloc(4 * ell_size) || it.rec.alloc(sizeof(double) * 16 * bp->n_cells) ||
         it.cells_ptr.alloc(4 * (n_chunks + 1)) || it.cells.alloc(4 * std::max<int64_t>(n_chunk_cells, 1)))
         return 2;
@@ -583,6 +831,82 @@ extern "C" int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int
 
 extern "C" int nfa_bplan_has_p2_items(const nfa_bplan *bp) { return bp && bp->p2.n_chunks > 0 ? 1 : 0; }
 
+extern "C" int nfa_bplan_set_p2_stage(nfa_bplan *bp, const int32_t *chunk_ext, const int32_t *task_hdr_rel,
+                                      const uint32_t *ell_local, int max_chunk_cells, int max_chunk_ell,
+                                      int max_chunk_items, int max_chunk_tasks, nfa_stream stream) {
+    if (!bp) return fail("nfa_bplan_set_p2_stage: plan is NULL");
+    nfa_bplan::P2Items &it = bp->p2;
+    if (it.n_chunks <= 0) return fail("nfa_bplan_set_p2_stage: set the row items first (nfa_bplan_set_p2_items)");
+    if (!chunk_ext || !task_hdr_rel || !ell_local) return fail("nfa_bplan_set_p2_stage: NULL list");
+    if (max_chunk_cells <= 0 || max_chunk_ell <= 0 || max_chunk_items <= 0 || max_chunk_tasks <= 0)
+        return fail("nfa_bplan_set_p2_stage: empty chunk bounds");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (it.chunk_ext.alloc(16 * it.n_chunks) || it.task_hdr_rel.alloc(16 * it.n_tasks) || it.ell_local.alloc(4 * it.ell_size))
+        return 2;
+    NFA_CUDA(cudaMemcpyAsync(it.chunk_ext.p, chunk_ext, 16 * it.n_chunks, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaMemcpyAsync(it.task_hdr_rel.p, task_hdr_rel, 16 * it.n_tasks, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaMemcpyAsync(it.ell_local.p, ell_local, 4 * it.ell_size, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaStreamSynchronize(s));
+    it.max_chunk_cells = max_chunk_cells;
+    it.max_chunk_ell = max_chunk_ell;
+    it.max_chunk_items = max_chunk_items;
+    it.max_chunk_tasks = max_chunk_tasks;
+    return 0;
+}
+
+// The staged kernel when the plan carries its lists and at least two chunk buffers fit in shared memory.
+static int launch_p2tet_staged(const nfa_bplan *bp, double *vals, bool cr, cudaStream_t s, bool *launched) {
+    const nfa_bplan::P2Items &it = bp->p2;
+    *launched = false;
+    if (it.max_chunk_cells <= 0) return 0;
+    // opt-in (NFA_P2TET_STAGE=1): measured 1.23 ms against 0.95 ms for the global-load kernel on the bench workload --
+    // the random 128-bit shared-memory reads of the records cost 3x the LSU wavefronts of the 256-bit global loads and
+    // the in-order hand-over of filled buffers leaves the warps spinning (profiles/r01_p2tet_staged_ncu_summary.txt)
+    const char *e_stage = getenv("NFA_P2TET_STAGE");
+    if (!e_stage || atoi(e_stage) == 0) return 0;
+    auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
+    StageLayout L;
+    const size_t tile_bytes = r128(sizeof(double) * (9 * (size_t)it.max_tile_blocks + 2));
+    L.rec_off = (int)tile_bytes;
+    L.ell_off = L.rec_off + 128 * it.max_chunk_cells;
+    L.item_off = L.ell_off + (int)r128(4 * (size_t)it.max_chunk_ell);
+    L.task_off = L.item_off + (int)r128(8 * (size_t)it.max_chunk_items);
+    L.buf_bytes = L.task_off + (int)r128(16 * (size_t)it.max_chunk_tasks);
+    const size_t ctrl_bytes = 256, limit = 227 * 1024;
+    int nbuf = (int)std::min<size_t>(8, (limit - ctrl_bytes) / (size_t)L.buf_bytes);
+    if (const char *e = getenv("NFA_P2TET_NBUF")) nbuf = std::min(nbuf, std::max(1, atoi(e)));
+    if (nbuf < 2) return 0;  // chunks too large for two buffers: the caller falls back to the global-load kernel
+    const size_t smem = (size_t)nbuf * L.buf_bytes + ctrl_bytes;
+    int threads = 512, rec_tma = 0;
+    if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
+    if (const char *e = getenv("NFA_P2TET_REC_TMA")) rec_tma = atoi(e) != 0;
+    using kern_t = void (*)(int, int, const int4 *, const int4 *, const int4 *, const uint2 *, const uint32_t *,
+                            const int32_t *, const int32_t *, const double *, StageLayout, int, double *);
+    kern_t kern = nullptr;
+#define NFA_P2S_PICK(CRV, TH) \
+    if (cr == CRV && threads == TH) kern = p2tet_staged_kernel<CRV, TH>;
+    NFA_P2S_PICK(false, 512) NFA_P2S_PICK(false, 640) NFA_P2S_PICK(false, 768) NFA_P2S_PICK(false, 1024)
+    NFA_P2S_PICK(true, 512) NFA_P2S_PICK(true, 640) NFA_P2S_PICK(true, 768) NFA_P2S_PICK(true, 1024)
+#undef NFA_P2S_PICK
+    if (!kern) return fail("nfa_assemble_p2tet_elasticity: NFA_P2TET_THREADS must be 512, 640, 768 or 1024 (staged kernel)");
+    NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int device = 0, n_sm = 148;
+    NFA_CUDA(cudaGetDevice(&device));
+    NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    int64_t grid = std::min<int64_t>(it.n_chunks, (int64_t)n_sm);
+    if (const char *e = getenv("NFA_P2TET_GRID")) grid = std::max<int64_t>(1, std::min<int64_t>(grid, atoi(e)));  // tests
+    if (timing_enabled()) timing_begin(s);
+    kern<<<(unsigned)grid, threads, smem, s>>>(nbuf, (int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
+                                               (const int4 *)it.chunk_ext.p, (const int4 *)it.task_hdr_rel.p,
+                                               (const uint2 *)it.item_hdr.p, (const uint32_t *)it.ell_local.p,
+                                               (const int32_t *)it.cells_ptr.p, (const int32_t *)it.cells.p,
+                                               (const double *)it.rec.p, L, rec_tma, vals);
+    if (timing_enabled()) timing_end(s);
+    NFA_LAUNCH_CHECK();
+    *launched = true;
+    return 0;
+}
+
 extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *coords, const int32_t *cell_nodes,
                                              const double *lam, int64_t ls, const double *mu, int64_t ms, double *vals,
                                              nfa_stream stream) {
@@ -593,6 +917,11 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     p2tet_geo_kernel<<<grid_for(bp->n_cells, 128), 128, 0, s>>>(coords, cell_nodes, bp->n_cells, lam, ls, mu, ms,
                                                                 (double *)it.rec.p);
     NFA_LAUNCH_CHECK();
+    {
+        bool launched = false;
+        if (int rc = launch_p2tet_staged(bp, vals, ls == 0 && ms == 0, s, &launched)) return rc;
+        if (launched) return 0;
+    }
     const int tile_stride = (9 * it.max_tile_blocks + 2 + 15) & ~15;  // doubles; keeps both tiles 128-byte aligned
     // as many tiles as fit in 220 KB of shared memory (at most 8): the more chunks are in flight, the less a long task
     // (a vertex-star item walks ~24 cells) delays the hand-over of its chunk's tile
@@ -604,6 +933,7 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     const bool cr = (ls == 0 && ms == 0);
     int threads = P2_THREADS;  // 512 (128 registers): more warps spill and lose (1.5 ms), see DESIGN.md
     if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
+    if (threads > 512) threads = 512;  // a staged-kernel setting; this kernel needs 128 registers per thread
     using kern_t = void (*)(int, int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
                             const int32_t *, const int32_t *, double *);
     kern_t kern = nullptr;

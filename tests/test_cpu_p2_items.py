@@ -64,6 +64,8 @@ def test_item_plan_reproduces_the_block_sums(n, cap, riffle):
     assert not np.isnan(got).any(), "some CSR block was never written"
     ref = _brute_force(space, s, mesh, node_dest, n_nodes, cell_nodes, keys, bptr, lam, mu)
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+    # the staged kernel's chunk-local lists (cell slots, relative offsets) describe the same sums, bit for bit
+    assert np.array_equal(p2_items.walk(plan, rec, len(keys), staged=True), got)
     hdr = plan["chunk_hdr"].numpy()
     hdr = hdr[np.argsort(hdr[:, 0])]  # chunks tile the block range exactly once (they are listed in riffled order)
     assert hdr[0, 0] == 0 and hdr[:, 1].sum() == len(keys) and np.all(hdr[1:, 0] == hdr[:-1, 0] + hdr[:-1, 1])

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
-def _assemble(n, lam, mu, p2tet, cap=None, seed_mesh=True):
+def _assemble(n, lam, mu, p2tet, cap=None, seed_mesh=True, stage=True, threads=None, grid=None, nbuf=None):
     from nfempy_b200.assembly import GPUAssembler
     from nfempy_b200.mesh import box_tet_mesh
     from nfempy_b200.spaces import ProductSpace
@@ -21,8 +21,16 @@ def _assemble(n, lam, mu, p2tet, cap=None, seed_mesh=True):
         def prepare(self, dev, items=None, arrays=None):
             return super().prepare(dev, items, arrays={"lambda": lam, "mu": mu, "rhs": None})
 
-    old = {k: os.environ.get(k) for k in ("NFA_P2TET", "NFA_P2TET_CAP")}
+    old = {k: os.environ.get(k) for k in ("NFA_P2TET", "NFA_P2TET_CAP", "NFA_P2TET_STAGE", "NFA_P2TET_THREADS", "NFA_P2TET_GRID", "NFA_P2TET_NBUF")}
     os.environ["NFA_P2TET"] = "1" if p2tet else "0"
+    os.environ["NFA_P2TET_STAGE"] = "1" if stage else "0"
+    os.environ.pop("NFA_P2TET_THREADS", None)
+    if threads:
+        os.environ["NFA_P2TET_THREADS"] = str(threads)
+    for k, v in (("NFA_P2TET_GRID", grid), ("NFA_P2TET_NBUF", nbuf)):
+        os.environ.pop(k, None)
+        if v:
+            os.environ[k] = str(v)
     if cap is not None:
         os.environ["NFA_P2TET_CAP"] = str(cap)
     try:
@@ -45,17 +53,46 @@ def _assemble(n, lam, mu, p2tet, cap=None, seed_mesh=True):
                 os.environ[k] = v
 
 
+@pytest.mark.parametrize("stage,threads", [(True, None), (True, 640), (True, 768), (False, None)])
 @pytest.mark.parametrize("n,cap", [(2, None), (5, None), (5, 64), (6, 1024)])
-def test_row_item_kernel_matches_the_reference_tensor_kernel(n, cap):
+def test_row_item_kernel_matches_the_reference_tensor_kernel(n, cap, stage, threads):
+    """``stage``: the shared-memory staged kernel (bulk-copied chunk inputs) or the global-load kernel."""
     n_cells = 6 * n**3
     rng = np.random.default_rng(11)
     lam, mu = 0.5 + 3.0 * rng.random(n_cells), 0.2 + rng.random(n_cells)
-    new, used_new = _assemble(n, lam, mu, True, cap)
+    new, used_new = _assemble(n, lam, mu, True, cap, stage=stage, threads=threads)
     ref, used_ref = _assemble(n, lam, mu, False)
     assert used_new and not used_ref
     compare_csr(new, ref, RTOL)
-    again, _ = _assemble(n, lam, mu, True, cap)
+    again, _ = _assemble(n, lam, mu, True, cap, stage=stage, threads=threads)
     assert np.array_equal(new[2], again[2]), "row-item kernel is not bit-reproducible"
+    if stage:  # both variants walk the same items in the same order: same sums up to the compiler's choice of FMA
+        other, _ = _assemble(n, lam, mu, True, cap, stage=False)  # contraction in each instantiation
+        compare_csr(new, other, 1e-14)
+
+
+@pytest.mark.parametrize("grid,nbuf,cap", [(1, 2, 64), (3, 2, 64), (2, 3, 100), (5, None, 48)])
+def test_staged_kernel_buffer_hand_over(grid, nbuf, cap):
+    """Few CTAs and few buffers: every CTA walks tens of chunks, so buffers are refilled many times (the bench-sized
+    launch does this on every SM; the small meshes of the other tests give each CTA a single chunk)."""
+    n = 6
+    n_cells = 6 * n**3
+    rng = np.random.default_rng(3)
+    lam, mu = 0.5 + 3.0 * rng.random(n_cells), 0.2 + rng.random(n_cells)
+    new, used = _assemble(n, lam, mu, True, cap, stage=True, grid=grid, nbuf=nbuf)
+    ref, _ = _assemble(n, lam, mu, True, cap, stage=False)
+    assert used
+    assert np.array_equal(new[2], ref[2])
+
+
+@pytest.mark.parametrize("stage", [True, False])
+def test_row_item_kernel_constant_coefficients(stage):
+    """lambda, mu constant over the mesh (stride 0): the constant-rho instantiation of both kernel variants."""
+    n = 4
+    new, used = _assemble(n, np.array([2.5]), np.array([0.75]), True, None, stage=stage)
+    ref, _ = _assemble(n, np.array([2.5]), np.array([0.75]), False)
+    assert used
+    compare_csr(new, ref, RTOL)
 
 
 def test_row_item_kernel_against_the_oracle_with_boundary_forms():
