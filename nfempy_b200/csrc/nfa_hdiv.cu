@@ -4,6 +4,9 @@
 // (1/|det|) J phi_hat on the values, divergence = tr(grad_hat phi_hat)/|det|, then the orientation transformation of
 // permute_and_transform (R/src/basis/permute_and_transform.py:110-140) as a small matrix per facet chosen by a
 // per-cell case id computed on the host.
+#include <algorithm>
+#include <cstdlib>
+
 #include "nfa_common.cuh"
 
 using namespace nfa;
@@ -113,6 +116,326 @@ __global__ void __launch_bounds__(128)
                     acc -= s_wd[q] * dot;
                 }
             re[cell * n_loc + ra] = acc;
+        }
+    }
+}
+
+// Register-tiled version of local_hdiv_l2_kernel.  The per-entry loop above reads two shared-memory vectors per DFMA
+// group (7 LDS for 4 DFMA: bound by shared-memory bandwidth, 37 ms for RT2 on 2 M tets); here a lane owns a T x T tile
+// of the symmetric flux mass block (tiles on and above the diagonal only, mirrored on store: 2T LDS for T*T DFMA per
+// point and component) or T rows of one pressure column of the divergence coupling (stored with both signs).
+// G lanes share a cell (8 / 16 / 32: sub-warp groups synchronised with __syncwarp on the group's mask, several cells per
+// CTA; 128: one CTA per cell), so that small elements do not idle a whole CTA.
+// Staging: pass 1 writes the Piola-mapped reference basis J psi_hat / |det| and div_hat / |det| ([q][c][j], rows padded
+// with zeros to a multiple of T), pass 2 applies the facet orientation matrices in place.
+constexpr int HT_MAXFD = 10;  // facet dofs per facet: RT_k 1 / 3 / 6, BDM_k 3 / 6 / 10
+
+template <int G>
+__device__ __forceinline__ void group_sync() {
+    if constexpr (G >= 128) {
+        __syncthreads();
+    } else if constexpr (G == 32) {
+        __syncwarp();
+    } else {
+        const unsigned lane = threadIdx.x & 31u;
+        __syncwarp((G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane / G * G));
+    }
+}
+
+// Stages the oriented, Piola-mapped basis of one cell in the group's shared memory: s_psi [n_q][DIM][n_up] and
+// s_div [n_q][n_up] (rows n_u .. n_up are zero).  Ends with a group_sync: the arrays are ready for every lane.
+template <int DIM, int G>
+__device__ __forceinline__ void stage_hdiv_basis(bool live, int r, int n_u, int n_up, int n_q, int nfd,
+                                                 const double *__restrict__ u_val, const double *__restrict__ u_div,
+                                                 const double *__restrict__ Tcases, const int8_t *__restrict__ cases,
+                                                 int64_t cell, const double (&J)[3][DIM], double idet, double *s_psi,
+                                                 double *s_div, double *s_T) {
+    constexpr int NF = DIM + 1;
+    if (live) {
+        for (int i = r; i < NF * nfd * nfd; i += G) {
+            const int fc = i / (nfd * nfd);
+            s_T[i] = Tcases[(int)cases[cell * NF + fc] * nfd * nfd + (i - fc * nfd * nfd)];
+        }
+        // pass 1: Piola map of the reference basis (no orientation yet), zero padding of the tile rows
+            for (int idx = r; idx < n_q * n_up; idx += G) {
+                const int q = idx / n_up, j = idx - q * n_up;
+                double vh[DIM], dh = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) vh[k] = 0.0;
+                if (j < n_u) {
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) vh[k] = __ldg(u_val + ((int64_t)q * n_u + j) * DIM + k);
+                    dh = __ldg(u_div + q * n_u + j);
+                }
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) v += J[c][k] * vh[k];
+                    s_psi[(q * DIM + c) * n_up + j] = v * idet;
+                }
+                s_div[q * n_up + j] = dh * idet;
+            }
+        }
+        group_sync<G>();
+        if (live && nfd > 1) {
+            // pass 2: orientation of the facet dofs, psi_a <- sum_b T[a][b] psi_b inside each facet block, in place: one
+            // lane reads the facet's nfd values of one (point, component or divergence) and writes them back transformed
+            for (int idx = r; idx < n_q * NF * (DIM + 1); idx += G) {
+                const int q = idx / (NF * (DIM + 1)), rest = idx - q * NF * (DIM + 1);
+                const int fc = rest / (DIM + 1), c = rest - fc * (DIM + 1);
+                double *v = (c < DIM ? s_psi + (q * DIM + c) * n_up : s_div + q * n_up) + fc * nfd;
+                const double *Tm = s_T + fc * nfd * nfd;
+                double in[HT_MAXFD];
+#pragma unroll
+                for (int b = 0; b < HT_MAXFD; ++b) in[b] = b < nfd ? v[b] : 0.0;
+                for (int a = 0; a < nfd; ++a) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int b = 0; b < HT_MAXFD; ++b)
+                        if (b < nfd) acc += Tm[a * nfd + b] * in[b];
+                    v[a] = acc;
+                }
+            }
+        } else if (live && nfd == 1) {
+            for (int idx = r; idx < n_q * NF * (DIM + 1); idx += G) {
+                const int q = idx / (NF * (DIM + 1)), rest = idx - q * NF * (DIM + 1);
+                const int fc = rest / (DIM + 1), c = rest - fc * (DIM + 1);
+                double *v = (c < DIM ? s_psi + (q * DIM + c) * n_up : s_div + q * n_up) + fc;
+                v[0] *= s_T[fc];
+            }
+        }
+    group_sync<G>();
+}
+
+template <int DIM, int G, int T>
+__global__ void __launch_bounds__(128)
+    hdiv_l2_tiled_kernel(int n_u, int n_p, int n_q, int nfd, const double *__restrict__ u_val,
+                         const double *__restrict__ u_div, const double *__restrict__ p_val,
+                         const double *__restrict__ weights, const double *__restrict__ Tcases,
+                         const int8_t *__restrict__ cases, const double *__restrict__ coords,
+                         const int32_t *__restrict__ cell_nodes, int64_t n_cells, CoefH kappa,
+                         const double *__restrict__ f, const double *__restrict__ f_u, double *__restrict__ Ke,
+                         double *__restrict__ re) {
+    constexpr int NF = DIM + 1;
+    constexpr int GROUPS = 128 / G;
+    extern __shared__ double smem[];
+    const int nt = (n_u + T - 1) / T, n_up = nt * T;
+    const int n_loc = n_u + n_p, n_fdofs = NF * nfd;
+    const int group_doubles = n_q * DIM * n_up + n_q * n_up + 2 * n_q + NF * nfd * nfd;
+    const int g = threadIdx.x / G, r = threadIdx.x - g * G;
+    double *s_psi = smem + (size_t)g * group_doubles;  // [n_q][DIM][n_up]
+    double *s_div = s_psi + n_q * DIM * n_up;           // [n_q][n_up]
+    double *s_wk = s_div + n_q * n_up;                  // [n_q] w det / kappa
+    double *s_wd = s_wk + n_q;                          // [n_q] w det
+    double *s_T = s_wd + n_q;                           // [NF][nfd][nfd]
+    const int n_mass = nt * (nt + 1) / 2, n_cpl = nt * n_p, n_zero = n_p * n_p;
+    const int n_work = n_mass + n_cpl + n_zero + n_loc;
+    const int64_t n_trips = (n_cells + (int64_t)gridDim.x * GROUPS - 1) / ((int64_t)gridDim.x * GROUPS);
+    // the vertex coordinates of the NEXT cell are loaded while the current one is computed (cell_nodes -> coords is a
+    // chain of two dependent global loads that would otherwise sit at the head of every trip)
+    double Xn[DIM + 1][3];
+    {
+        const int64_t c0 = (int64_t)blockIdx.x * GROUPS + g;
+        if (c0 < n_cells) load_cell_coords<DIM>(coords, cell_nodes, c0, Xn);
+    }
+    for (int64_t trip = 0; trip < n_trips; ++trip) {
+        // every group of a warp makes the same number of trips (group_sync names the group's lanes only, but all lanes of
+        // a warp must reach the loop's convergence points); a group without a cell skips the work
+        const int64_t cell = (trip * gridDim.x + blockIdx.x) * GROUPS + g;
+        const bool live = cell < n_cells;
+        double J[3][DIM], idet = 0.0, det = 0.0;
+        if (live) {
+            double X[DIM + 1][3];
+#pragma unroll
+            for (int a = 0; a <= DIM; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) X[a][b] = Xn[a][b];
+            Geom<DIM> gm;
+            compute_geom<DIM>(X, gm);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < DIM; ++b) J[a][b] = gm.J[a][b];
+            det = gm.det;
+            idet = 1.0 / gm.det;
+        }
+        group_sync<G>();  // the previous cell's readers are done with the group's shared memory
+        if (live)
+            for (int q = r; q < n_q; q += G) {
+                const double wd = weights[q] * det;
+                s_wd[q] = wd;
+                s_wk[q] = wd * (1.0 / kappa.p[cell * kappa.sc + q * kappa.sq]);
+            }
+        stage_hdiv_basis<DIM, G>(live, r, n_u, n_up, n_q, nfd, u_val, u_div, Tcases, cases, cell, J, idet, s_psi, s_div, s_T);
+        {
+            const int64_t cn = ((trip + 1) * gridDim.x + blockIdx.x) * GROUPS + g;
+            if (cn < n_cells) {
+                load_cell_coords<DIM>(coords, cell_nodes, cn, Xn);
+                if (r == 0) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(cases + cn * NF));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(kappa.p + cn * kappa.sc));
+                }
+            }
+        }
+        // few mass tiles (at most G / 2): lanes r and r + G / 2 share a tile, each sums one half of the quadrature points
+        // and the halves are combined with a shuffle, so that all lanes of the group work in the dominant phase
+        const bool split = G <= 32 && n_mass <= G / 2;
+        if (G <= 32 && split) {
+            constexpr int H = G / 2;
+            const int half = r / H, w = r - half * H;
+            const bool mine = live && w < n_mass;
+            int ti = 0, rem = mine ? w : 0;
+            while (rem >= nt - ti) {
+                rem -= nt - ti;
+                ++ti;
+            }
+            const int tj = ti + rem;
+            double acc[T][T];
+#pragma unroll
+            for (int i = 0; i < T; ++i)
+#pragma unroll
+                for (int j = 0; j < T; ++j) acc[i][j] = 0.0;
+            const int q_mid = (n_q + 1) / 2, q0 = half ? q_mid : 0, q1 = half ? n_q : q_mid;
+            if (mine) {
+#pragma unroll 2
+                for (int q = q0; q < q1; ++q) {
+                    double sq[T][T];
+#pragma unroll
+                    for (int i = 0; i < T; ++i)
+#pragma unroll
+                        for (int j = 0; j < T; ++j) sq[i][j] = 0.0;
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) {
+                        const double *row = s_psi + (q * DIM + c) * n_up;
+                        double a[T], b[T];
+#pragma unroll
+                        for (int i = 0; i < T; ++i) {
+                            a[i] = row[ti * T + i];
+                            b[i] = row[tj * T + i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < T; ++i)
+#pragma unroll
+                            for (int j = 0; j < T; ++j) sq[i][j] = fma(a[i], b[j], sq[i][j]);
+                    }
+                    const double wk = s_wk[q];
+#pragma unroll
+                    for (int i = 0; i < T; ++i)
+#pragma unroll
+                        for (int j = 0; j < T; ++j) acc[i][j] = fma(wk, sq[i][j], acc[i][j]);
+                }
+            }
+            // lanes without a cell or a tile take part in the shuffle with zeros
+            const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << ((threadIdx.x & 31u) / G * G);
+#pragma unroll
+            for (int i = 0; i < T; ++i)
+#pragma unroll
+                for (int j = 0; j < T; ++j) acc[i][j] += __shfl_xor_sync(gmask, acc[i][j], H);
+            if (mine) {
+                double *K = Ke + cell * (int64_t)n_loc * n_loc;
+#pragma unroll
+                for (int i = 0; i < T; ++i)
+#pragma unroll
+                    for (int j = 0; j < T; ++j) {
+                        const int ra = ti * T + i, rb = tj * T + j;
+                        if (ra < n_u && rb < n_u) {
+                            if (half == 0) K[ra * n_loc + rb] = acc[i][j];
+                            if (half == 1 && ti != tj) K[rb * n_loc + ra] = acc[i][j];
+                        }
+                    }
+            }
+        }
+        if (live) {
+            double *K = Ke + cell * (int64_t)n_loc * n_loc;
+            for (int w = (split ? n_mass : 0) + r; w < n_work; w += G) {
+                if (w < n_mass) {
+                    // tile (ti, tj), ti <= tj, from the linear index over the upper triangle
+                    int ti = 0, rem = w;
+                    while (rem >= nt - ti) {
+                        rem -= nt - ti;
+                        ++ti;
+                    }
+                    const int tj = ti + rem;
+                    double acc[T][T];
+#pragma unroll
+                    for (int i = 0; i < T; ++i)
+#pragma unroll
+                        for (int j = 0; j < T; ++j) acc[i][j] = 0.0;
+#pragma unroll 2
+                    for (int q = 0; q < n_q; ++q) {
+                        double sq[T][T];
+#pragma unroll
+                        for (int i = 0; i < T; ++i)
+#pragma unroll
+                            for (int j = 0; j < T; ++j) sq[i][j] = 0.0;
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) {
+                            const double *row = s_psi + (q * DIM + c) * n_up;
+                            double a[T], b[T];
+#pragma unroll
+                            for (int i = 0; i < T; ++i) {
+                                a[i] = row[ti * T + i];
+                                b[i] = row[tj * T + i];
+                            }
+#pragma unroll
+                            for (int i = 0; i < T; ++i)
+#pragma unroll
+                                for (int j = 0; j < T; ++j) sq[i][j] = fma(a[i], b[j], sq[i][j]);
+                        }
+                        const double wk = s_wk[q];
+#pragma unroll
+                        for (int i = 0; i < T; ++i)
+#pragma unroll
+                            for (int j = 0; j < T; ++j) acc[i][j] = fma(wk, sq[i][j], acc[i][j]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < T; ++i)
+#pragma unroll
+                        for (int j = 0; j < T; ++j) {
+                            const int ra = ti * T + i, rb = tj * T + j;
+                            if (ra < n_u && rb < n_u) {
+                                K[ra * n_loc + rb] = acc[i][j];
+                                if (ti != tj) K[rb * n_loc + ra] = acc[i][j];
+                            }
+                        }
+                } else if (w < n_mass + n_cpl) {
+                    const int wc = w - n_mass, ti = wc / n_p, l = wc - ti * n_p;
+                    double acc[T];
+#pragma unroll
+                    for (int i = 0; i < T; ++i) acc[i] = 0.0;
+                    for (int q = 0; q < n_q; ++q) {
+                        const double pw = s_wd[q] * __ldg(p_val + q * n_p + l);
+#pragma unroll
+                        for (int i = 0; i < T; ++i) acc[i] = fma(pw, s_div[q * n_up + ti * T + i], acc[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < T; ++i) {
+                        const int ra = ti * T + i;
+                        if (ra < n_u) {
+                            K[ra * n_loc + n_u + l] = -acc[i];
+                            K[(n_u + l) * n_loc + ra] = acc[i];
+                        }
+                    }
+                } else if (w < n_mass + n_cpl + n_zero) {
+                    const int wz = w - n_mass - n_cpl, k = wz / n_p, l = wz - k * n_p;
+                    K[(n_u + k) * n_loc + n_u + l] = 0.0;
+                } else {
+                    const int ra = w - n_mass - n_cpl - n_zero;
+                    double acc = 0.0;
+                    if (ra >= n_u && f)
+                        for (int q = 0; q < n_q; ++q) acc -= s_wd[q] * __ldg(p_val + q * n_p + (ra - n_u)) * f[cell * n_q + q];
+                    if (ra < n_u && f_u)  // vector load -int f . psi (L2ProjectorWeakForm on an H(div) field)
+                        for (int q = 0; q < n_q; ++q) {
+                            double dot = 0.0;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c)
+                                dot += s_psi[(q * DIM + c) * n_up + ra] * f_u[(cell * n_q + q) * DIM + c];
+                            acc -= s_wd[q] * dot;
+                        }
+                    re[cell * n_loc + ra] = acc;
+                }
+            }
         }
     }
 }
@@ -480,6 +803,237 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Register-tiled, several-cells-per-CTA version of local_sundus_kernel (same staging and tile scheme as
+// hdiv_l2_tiled_kernel).  The two flux mass blocks share the basis products (one tile pass, two weights), the two
+// divergence couplings are the same numbers, every other block is zero or an L2 mass.
+template <int DIM, int G, int T>
+__global__ void __launch_bounds__(128)
+    sundus_tiled_kernel(int n_u, int n_p, int n_q, int nfd, const double *__restrict__ u_val,
+                        const double *__restrict__ u_div, const double *__restrict__ p_val,
+                        const double *__restrict__ weights, const double *__restrict__ Tcases,
+                        const int8_t *__restrict__ cases, const double *__restrict__ coords,
+                        const int32_t *__restrict__ cell_nodes, int64_t n_cells, CoefH kappa, CoefH delta, CoefH eta,
+                        double inv_dt, const double *__restrict__ f_f, const double *__restrict__ f_r,
+                        const double *__restrict__ alpha, const double *__restrict__ alpha_prev,
+                        const int32_t *__restrict__ dest, double *__restrict__ Ke, double *__restrict__ re) {
+    constexpr int NF = DIM + 1;
+    constexpr int GROUPS = 128 / G;
+    constexpr int QS = 8 + 2 * DIM;  // wd, wd/kappa, wd/delta, eta, p_h, c_h, dpdt, dcdt | mp_h[DIM] | mc_h[DIM]
+    extern __shared__ double smem[];
+    const int nt = (n_u + T - 1) / T, n_up = nt * T;
+    const int n_loc = 2 * n_u + 2 * n_p;
+    const int group_doubles = n_q * DIM * n_up + n_q * n_up + NF * nfd * nfd + 2 * n_loc + n_q * QS + 2 * n_q;
+    const int g = threadIdx.x / G, r = threadIdx.x - g * G;
+    double *s_psi = smem + (size_t)g * group_doubles;  // [n_q][DIM][n_up]
+    double *s_div = s_psi + n_q * DIM * n_up;           // [n_q][n_up]
+    double *s_T = s_div + n_q * n_up;                   // [NF][nfd][nfd]
+    double *s_a = s_T + NF * nfd * nfd;                 // [n_loc] current iterate (local)
+    double *s_an = s_a + n_loc;                         // [n_loc] previous time level (local)
+    double *s_q = s_an + n_loc;                         // [n_q][QS] per-point state
+    double *s_dv = s_q + n_q * QS;                      // [n_q][2] div mp_h, div mc_h
+    const int n_mass = nt * (nt + 1) / 2, n_cpl = nt * n_p, n_pp = n_p * n_p;
+    const int n_work = n_mass + n_cpl + n_pp + n_loc;
+    const int oc = n_u, op = 2 * n_u, occ = 2 * n_u + n_p;  // offsets of mc, p, c in the local numbering
+    const int64_t n_trips = (n_cells + (int64_t)gridDim.x * GROUPS - 1) / ((int64_t)gridDim.x * GROUPS);
+    double Xn[DIM + 1][3];
+    {
+        const int64_t c0 = (int64_t)blockIdx.x * GROUPS + g;
+        if (c0 < n_cells) load_cell_coords<DIM>(coords, cell_nodes, c0, Xn);
+    }
+    for (int64_t trip = 0; trip < n_trips; ++trip) {
+        const int64_t cell = (trip * gridDim.x + blockIdx.x) * GROUPS + g;
+        const bool live = cell < n_cells;
+        double J[3][DIM], idet = 0.0, det = 0.0;
+        if (live) {
+            double X[DIM + 1][3];
+#pragma unroll
+            for (int a = 0; a <= DIM; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) X[a][b] = Xn[a][b];
+            Geom<DIM> gm;
+            compute_geom<DIM>(X, gm);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < DIM; ++b) J[a][b] = gm.J[a][b];
+            det = gm.det;
+            idet = 1.0 / gm.det;
+        }
+        group_sync<G>();  // the previous cell's readers are done with the group's shared memory
+        if (live) {
+            for (int i = r; i < n_loc; i += G) {
+                const int d = dest[cell * n_loc + i];
+                s_a[i] = alpha ? alpha[d] : 0.0;
+                s_an[i] = alpha_prev ? alpha_prev[d] : 0.0;
+            }
+            double *K = Ke + cell * (int64_t)n_loc * n_loc;
+            for (int e = r; e < n_loc * n_loc; e += G) K[e] = 0.0;  // the structurally zero blocks; the rest is overwritten
+        }
+        stage_hdiv_basis<DIM, G>(live, r, n_u, n_up, n_q, nfd, u_val, u_div, Tcases, cases, cell, J, idet, s_psi, s_div, s_T);
+        {
+            const int64_t cn = ((trip + 1) * gridDim.x + blockIdx.x) * GROUPS + g;
+            if (cn < n_cells) load_cell_coords<DIM>(coords, cell_nodes, cn, Xn);
+        }
+        if (live) {
+            // per-point state at the current iterate
+            for (int q = r; q < n_q; q += G) {
+                double *st = s_q + q * QS;
+                const double wd = weights[q] * det;
+                st[0] = wd;
+                st[1] = wd * (1.0 / kappa.p[cell * kappa.sc + q * kappa.sq]);
+                st[2] = wd * (1.0 / delta.p[cell * delta.sc + q * delta.sq]);
+                st[3] = eta.p[cell * eta.sc + q * eta.sq];
+                double ph = 0, ch = 0, pn = 0, cn = 0;
+                for (int k = 0; k < n_p; ++k) {
+                    const double w = __ldg(p_val + q * n_p + k);
+                    ph += s_a[op + k] * w;
+                    ch += s_a[occ + k] * w;
+                    pn += s_an[op + k] * w;
+                    cn += s_an[occ + k] * w;
+                }
+                st[4] = ph;
+                st[5] = ch;
+                st[6] = (ph - pn) * inv_dt;
+                st[7] = (ch - cn) * inv_dt;
+                double mp[DIM], mc[DIM], dmp = 0, dmc = 0;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) mp[c] = mc[c] = 0.0;
+                for (int j = 0; j < n_u; ++j) {
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) {
+                        const double ps = s_psi[(q * DIM + c) * n_up + j];
+                        mp[c] += s_a[j] * ps;
+                        mc[c] += s_a[oc + j] * ps;
+                    }
+                    dmp += s_a[j] * s_div[q * n_up + j];
+                    dmc += s_a[oc + j] * s_div[q * n_up + j];
+                }
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    st[8 + c] = mp[c];
+                    st[8 + DIM + c] = mc[c];
+                }
+                s_dv[2 * q] = dmp;
+                s_dv[2 * q + 1] = dmc;
+            }
+        }
+        group_sync<G>();  // state ready; the zero fill of K is ordered before the block stores below
+        if (live) {
+            double *K = Ke + cell * (int64_t)n_loc * n_loc;
+            for (int w = r; w < n_work; w += G) {
+                if (w < n_mass) {
+                    int ti = 0, rem = w;
+                    while (rem >= nt - ti) {
+                        rem -= nt - ti;
+                        ++ti;
+                    }
+                    const int tj = ti + rem;
+                    double ak[T][T], ad[T][T];
+#pragma unroll
+                    for (int i = 0; i < T; ++i)
+#pragma unroll
+                        for (int j = 0; j < T; ++j) ak[i][j] = ad[i][j] = 0.0;
+                    for (int q = 0; q < n_q; ++q) {
+                        double sq[T][T];
+#pragma unroll
+                        for (int i = 0; i < T; ++i)
+#pragma unroll
+                            for (int j = 0; j < T; ++j) sq[i][j] = 0.0;
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) {
+                            const double *row = s_psi + (q * DIM + c) * n_up;
+                            double a[T], b[T];
+#pragma unroll
+                            for (int i = 0; i < T; ++i) {
+                                a[i] = row[ti * T + i];
+                                b[i] = row[tj * T + i];
+                            }
+#pragma unroll
+                            for (int i = 0; i < T; ++i)
+#pragma unroll
+                                for (int j = 0; j < T; ++j) sq[i][j] = fma(a[i], b[j], sq[i][j]);
+                        }
+                        const double wk = s_q[q * QS + 1], wl = s_q[q * QS + 2];
+#pragma unroll
+                        for (int i = 0; i < T; ++i)
+#pragma unroll
+                            for (int j = 0; j < T; ++j) {
+                                ak[i][j] = fma(wk, sq[i][j], ak[i][j]);
+                                ad[i][j] = fma(wl, sq[i][j], ad[i][j]);
+                            }
+                    }
+#pragma unroll
+                    for (int i = 0; i < T; ++i)
+#pragma unroll
+                        for (int j = 0; j < T; ++j) {
+                            const int ra = ti * T + i, rb = tj * T + j;
+                            if (ra < n_u && rb < n_u) {
+                                K[ra * n_loc + rb] = ak[i][j];
+                                K[(oc + ra) * n_loc + oc + rb] = ad[i][j];
+                                if (ti != tj) {
+                                    K[rb * n_loc + ra] = ak[i][j];
+                                    K[(oc + rb) * n_loc + oc + ra] = ad[i][j];
+                                }
+                            }
+                        }
+                } else if (w < n_mass + n_cpl) {
+                    const int wc = w - n_mass, ti = wc / n_p, l = wc - ti * n_p;
+                    double acc[T];
+#pragma unroll
+                    for (int i = 0; i < T; ++i) acc[i] = 0.0;
+                    for (int q = 0; q < n_q; ++q) {
+                        const double pw = s_q[q * QS] * __ldg(p_val + q * n_p + l);
+#pragma unroll
+                        for (int i = 0; i < T; ++i) acc[i] = fma(pw, s_div[q * n_up + ti * T + i], acc[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < T; ++i) {
+                        const int ra = ti * T + i;
+                        if (ra < n_u) {
+                            K[ra * n_loc + op + l] = -acc[i];         // -(w_l, div psi_i), flux mp / pressure p
+                            K[(op + l) * n_loc + ra] = acc[i];        // +(div psi_j, w_k)
+                            K[(oc + ra) * n_loc + occ + l] = -acc[i];  // the same for mc / c
+                            K[(occ + l) * n_loc + oc + ra] = acc[i];
+                        }
+                    }
+                } else if (w < n_mass + n_cpl + n_pp) {
+                    const int wz = w - n_mass - n_cpl, k = wz / n_p, l = wz - k * n_p;
+                    double app = 0.0, acc = 0.0;  // time derivative (+ reaction tangent 2 eta c_h on the c block)
+                    for (int q = 0; q < n_q; ++q) {
+                        const double *st = s_q + q * QS;
+                        const double ww = st[0] * __ldg(p_val + q * n_p + k) * __ldg(p_val + q * n_p + l);
+                        app = fma(inv_dt, ww, app);
+                        acc = fma(inv_dt + 2.0 * st[3] * st[5], ww, acc);
+                    }
+                    K[(op + k) * n_loc + op + l] = app;
+                    K[(occ + k) * n_loc + occ + l] = acc;
+                } else {
+                    const int ra = w - n_mass - n_cpl - n_pp;
+                    const int fa = ra < n_u ? 0 : (ra < 2 * n_u ? 1 : (ra < 2 * n_u + n_p ? 2 : 3));
+                    const int ia = ra - (fa == 0 ? 0 : fa == 1 ? n_u : fa == 2 ? 2 * n_u : 2 * n_u + n_p);
+                    double acc = 0.0;
+                    for (int q = 0; q < n_q; ++q) {
+                        const double *st = s_q + q * QS;
+                        if (fa <= 1) {
+                            double dot = 0.0;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) dot += st[8 + fa * DIM + c] * s_psi[(q * DIM + c) * n_up + ia];
+                            acc += st[1 + fa] * dot - st[0] * st[4 + fa] * s_div[q * n_up + ia];
+                        } else {
+                            const double wv = __ldg(p_val + q * n_p + ia);
+                            const double src = (fa == 2) ? (f_f ? f_f[cell * n_q + q] : 0.0) : (f_r ? f_r[cell * n_q + q] : 0.0);
+                            double body = st[6 + (fa - 2)] + s_dv[2 * q + (fa - 2)];
+                            if (fa == 3) body += 1.0 + st[3] * st[5] * st[5];
+                            acc += st[0] * (body - src) * wv;
+                        }
+                    }
+                    re[cell * n_loc + ra] = acc;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, const double *u_val,
@@ -495,6 +1049,40 @@ extern "C" int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, co
     size_t smem = sizeof(double) * ((size_t)n_q * n_u * (dim + 1) + 2 * n_q + (size_t)(dim + 1) * nfd * nfd);
     if (smem > 200 * 1024) return fail("nfa_local_hdiv_l2: element too large for the shared-memory staging");
     int grid = (int)(n_cells < 148 * 8 ? n_cells : 148 * 8);
+    const char *e_tiled = getenv("NFA_HDIV_TILED");
+    if ((!e_tiled || atoi(e_tiled) != 0) && nfd <= HT_MAXFD) {
+        // register-tiled kernel: lanes per cell from the number of heavy work items (mass tiles + coupling columns)
+        constexpr int T = 3;
+        const int nt = (n_u + T - 1) / T, n_up = nt * T, heavy = nt * (nt + 1) / 2 + nt * n_p;
+        int G = heavy <= 8 ? 8 : (heavy <= 16 ? 16 : (heavy <= 48 ? 32 : 128));
+        if (const char *e = getenv("NFA_HDIV_LANES")) G = atoi(e);
+        const size_t group_doubles = (size_t)n_q * dim * n_up + (size_t)n_q * n_up + 2 * n_q + (size_t)(dim + 1) * nfd * nfd;
+        const size_t tsmem = sizeof(double) * group_doubles * (128 / G);
+        if (tsmem <= 200 * 1024 && (G == 8 || G == 16 || G == 32 || G == 128)) {
+            int device = 0, n_sm = 148, per_sm = 1;
+            NFA_CUDA(cudaGetDevice(&device));
+            NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+#define NFA_HT_LAUNCH(D, GG)                                                                                         \
+    {                                                                                                                \
+        auto kern = hdiv_l2_tiled_kernel<D, GG, T>;                                                                  \
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));               \
+        NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, tsmem));                          \
+        const int64_t want = (n_cells + (128 / GG) - 1) / (128 / GG);                                                \
+        const int tgrid = (int)std::min<int64_t>(want, (int64_t)n_sm * std::max(per_sm, 1));                         \
+        kern<<<tgrid, 128, tsmem, s>>>(n_u, n_p, n_q, nfd, u_val, u_div, p_val, weights, Tcases, cases, coords,      \
+                                       cell_nodes, n_cells, kp, f, f_u, Ke, re);                                     \
+    }
+            if (dim == 3) {
+                if (G == 8) NFA_HT_LAUNCH(3, 8) else if (G == 16) NFA_HT_LAUNCH(3, 16) else if (G == 32) NFA_HT_LAUNCH(3, 32) else NFA_HT_LAUNCH(3, 128)
+            } else if (dim == 2) {
+                if (G == 8) NFA_HT_LAUNCH(2, 8) else if (G == 16) NFA_HT_LAUNCH(2, 16) else if (G == 32) NFA_HT_LAUNCH(2, 32) else NFA_HT_LAUNCH(2, 128)
+            } else
+                return fail("nfa_local_hdiv_l2: dim must be 2 or 3");
+#undef NFA_HT_LAUNCH
+            NFA_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (dim == 3) {
         auto kern = local_hdiv_l2_kernel<3>;
         NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -549,6 +1137,41 @@ extern "C" int nfa_local_sundus(int dim, int n_u, int n_p, int n_q, int nfd, con
                                     (size_t)n_q * (8 + 2 * dim) + 2 * n_q);
     if (smem > 200 * 1024) return fail("nfa_local_sundus: element too large for the shared-memory staging");
     int grid = (int)(n_cells < 148 * 8 ? n_cells : 148 * 8);
+    const char *e_tiled = getenv("NFA_HDIV_TILED");
+    if ((!e_tiled || atoi(e_tiled) != 0) && nfd <= HT_MAXFD) {
+        constexpr int T = 3;
+        const int nt = (n_u + T - 1) / T, n_up = nt * T, heavy = nt * (nt + 1) / 2 + nt * n_p + n_p * n_p;
+        int G = heavy <= 8 ? 8 : (heavy <= 16 ? 16 : (heavy <= 48 ? 32 : 128));
+        if (const char *e = getenv("NFA_HDIV_LANES")) G = atoi(e);
+        const size_t group_doubles = (size_t)n_q * dim * n_up + (size_t)n_q * n_up + (size_t)(dim + 1) * nfd * nfd +
+                                     2 * n_loc + (size_t)n_q * (8 + 2 * dim) + 2 * n_q;
+        const size_t tsmem = sizeof(double) * group_doubles * (128 / G);
+        if (tsmem <= 200 * 1024 && (G == 8 || G == 16 || G == 32 || G == 128)) {
+            int device = 0, n_sm = 148, per_sm = 1;
+            NFA_CUDA(cudaGetDevice(&device));
+            NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+#define NFA_ST_LAUNCH(D, GG)                                                                                          \
+    {                                                                                                                 \
+        auto kern = sundus_tiled_kernel<D, GG, T>;                                                                    \
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));                \
+        NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, tsmem));                           \
+        const int64_t want = (n_cells + (128 / GG) - 1) / (128 / GG);                                                 \
+        const int tgrid = (int)std::min<int64_t>(want, (int64_t)n_sm * std::max(per_sm, 1));                          \
+        kern<<<tgrid, 128, tsmem, s>>>(n_u, n_p, n_q, nfd, u_val, u_div, p_val, weights, Tcases, cases, coords,       \
+                                       cell_nodes, n_cells, kp, dl, et, 1.0 / delta_t, f_f, f_r, alpha, alpha_prev,   \
+                                       dest, Ke, re);                                                                 \
+    }
+            if (dim == 3) {
+                if (G == 8) NFA_ST_LAUNCH(3, 8) else if (G == 16) NFA_ST_LAUNCH(3, 16) else if (G == 32) NFA_ST_LAUNCH(3, 32) else NFA_ST_LAUNCH(3, 128)
+            } else if (dim == 2) {
+                if (G == 8) NFA_ST_LAUNCH(2, 8) else if (G == 16) NFA_ST_LAUNCH(2, 16) else if (G == 32) NFA_ST_LAUNCH(2, 32) else NFA_ST_LAUNCH(2, 128)
+            } else
+                return fail("nfa_local_sundus: dim must be 2 or 3");
+#undef NFA_ST_LAUNCH
+            NFA_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     if (dim == 3) {
         auto kern = local_sundus_kernel<3>;
         NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
