@@ -287,6 +287,23 @@ int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *d_coords, c
                                   const double *d_lambda, int64_t lambda_stride, const double *d_mu,
                                   int64_t mu_stride, double *d_vals, nfa_stream stream);
 
+/* ---- generic multi-field Lagrange volume form: the local kernel of LCEPrimalWeakForm
+ * (R/src/weak_forms/lce_primal_weak_form.py:9-220), LETaylorHoodWeakForm (R/src/weak_forms/le_taylor_hood_weak_form.py:9-186)
+ * and LEPrimalStressConstraintWeakForm (R/src/weak_forms/le_primal_stress_constraint_weak_form.py:10-126).
+ * Local dof i = (basis dof_a[i] of the concatenated table d_tab [1 + dim][n_q][n_phi], component row dof_cr[i]);
+ * J[i][j] = sum_q w det sum_{terms of (cr_i, cr_j)} val * coef_m(q) * D^s phi_a(q) * D^t phi_b(q) with terms packed as
+ * s | t << 4 | m << 8 in d_term_code[d_term_ptr[cr_i * n_crow + cr_j] ..), D^0 = value, D^{1 + d} = d/dx_d;
+ * r = J alpha[dest] + sum_q w det sum_l load[cell][q][l] D^{s_l} phi_a (rows with cr_l = cr_i; d_load_code = cr | s << 8).
+ * coef_ptrs / strides are HOST arrays of n_coef (<= 8) device pointers, cell strides and point strides. */
+int nfa_local_h1_multifield(int dim, int n_q, int n_phi, int n_loc, int n_crow, const double *d_tab,
+                            const double *d_weights, const int32_t *d_dof_a, const int32_t *d_dof_cr,
+                            const int32_t *d_term_ptr, const int32_t *d_term_code, const double *d_term_val,
+                            int n_coef, const double *const *coef_ptrs, const int64_t *coef_cell_stride,
+                            const int64_t *coef_point_stride, int n_load, const int32_t *d_load_code,
+                            const double *d_load, const double *d_coords, const int32_t *d_cell_nodes,
+                            int64_t n_cells, const double *d_alpha, const int32_t *d_dest, double *d_Ke, double *d_re,
+                            nfa_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

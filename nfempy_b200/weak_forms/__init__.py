@@ -11,3 +11,5 @@ from .scaled_to_physical_l2_projection import ScaledToPhysicalL2Projection
 from .tensor_mixed import (LEDualWeakForm, LEDualWeakFormBCDirichlet, LCEDualWeakForm, LCEDualWeakFormBCDirichlet,
                            LCEScaledDualWeakForm, LCEScaledDualWeakFormBCDirichlet, LERieszMapWeakForm,
                            LCERieszMapWeakForm, LCEScaledRieszMapWeakForm)
+from .h1_multifield import (LCEPrimalWeakForm, LCEPrimalWeakFormBCDirichlet, LETaylorHoodWeakForm,
+                            LETaylorHoodWeakFormBCDirichlet, LEPrimalStressConstraintWeakForm)

@@ -143,7 +143,7 @@ class H1FacetForm(BatchedWeakForm):
         if self.space is None or self.functions is None:
             raise ValueError("weak form needs .space and .functions")
         s = self._field()
-        if len(self.space.discrete_spaces) != 1:
+        if len(self.space.discrete_spaces) != 1 and not getattr(self, "_multi", False):
             bc_fields = [n for n, sp in self.space.discrete_spaces.items() if len(sp.bc_elements) != 0]
             if bc_fields != [self.field_name]:
                 raise _lib.NfaError("H1 facet form: only one field may carry boundary elements")

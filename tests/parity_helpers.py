@@ -402,3 +402,118 @@ def tensor_mixed_case(kind="lce", dim=3, s_family="BDM", m_family="RT", k=1, n=2
         mesh, data_fn, {nm: [1] for nm in names}, {nm: (btag_list if with_bc else []) for nm in bfields},
         gpu_forms, ref_forms_fn, disc={"u": True, "t": True}, alpha_fn=alpha_fn,
     )
+
+
+# ---- primal forms on several Lagrange fields (W8): LCE primal, Taylor-Hood, stress constraint ------------------
+def _t_exact(x, y, z):
+    return np.array([np.cos(y) * x, 0.5 * z - x * y, np.sin(z) + 0.1])
+
+
+def lce_primal_case(dim=3, k=2, n=2, varying=False, alpha=False, with_bc=True, kt=None, mesh=None):
+    from nfempy_b200.weak_forms import LCEPrimalWeakForm, LCEPrimalWeakFormBCDirichlet
+    from oracle import ref_h1_multi
+
+    if mesh is None:
+        mesh = box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(n, jitter=0.2)
+    btags = [2, 3, 4, 5, 6, 7] if dim == 3 else [2, 3, 4, 5]
+    nt = 3 if dim == 3 else 1
+    kt = k if kt is None else kt
+    if varying:
+        mats = {"lambda": lambda x, y, z: 1.0 + x + 2.0 * y * y, "mu": lambda x, y, z: 2.0 + np.sin(z + x),
+                "kappa": lambda x, y, z: 0.3 + 0.1 * x * y, "gamma": lambda x, y, z: 1.5 + z * z}
+    else:
+        mats = {"lambda": lambda x, y, z: 3.0 + 0.0 * x, "mu": lambda x, y, z: 0.5 + 0.0 * x,
+                "kappa": lambda x, y, z: 0.1 + 0.0 * x, "gamma": lambda x, y, z: 2.0 + 0.0 * x}
+
+    def rhs(x, y, z):
+        f, t = _f_rhs(x, y, z), _t_exact(x, y, z)
+        return np.array(list(f[:dim]) + list(t[:nt]))
+
+    functions = dict(mats, rhs=rhs)
+    bc_functions = {"u": lambda x, y, z: _u_exact(x, y, z)[:dim], "t": lambda x, y, z: _t_exact(x, y, z)[:nt]}
+
+    def gpu_forms(space, a):
+        wf = LCEPrimalWeakForm(space)
+        wf.functions = functions
+        out = {"volume": ["form", range(len(space.discrete_spaces["u"].elements)), wf, a]}
+        if with_bc:
+            bf = LCEPrimalWeakFormBCDirichlet(space)
+            bf.functions = bc_functions
+            out["bc"] = ["bc_form", range(len(space.discrete_spaces["u"].bc_elements)), bf, a]
+        return out
+
+    def ref_forms_fn(space):
+        out = [("form", ref_h1_multi.lce_primal, functions, len(space.discrete_spaces["u"].element_ids))]
+        if with_bc:
+            out.append(("bc_form", ref_h1_multi.lce_primal_bc_dirichlet, bc_functions,
+                        len(space.discrete_spaces["u"].bc_element_ids)))
+        return out
+
+    alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None
+    return Case(
+        mesh, lambda g: {"u": (dim, dim, "Lagrange", k, g), "t": (dim, nt, "Lagrange", kt, g)},
+        {"u": [1], "t": [1]}, {"u": btags if with_bc else [], "t": btags if with_bc else []}, gpu_forms, ref_forms_fn,
+        alpha_fn=alpha_fn,
+    )
+
+
+def taylor_hood_case(n=3, varying=False, alpha=False, with_bc=True):
+    from nfempy_b200.weak_forms import LETaylorHoodWeakForm, LETaylorHoodWeakFormBCDirichlet
+    from oracle import ref_h1_multi
+
+    mesh = square_tri_mesh(n, jitter=0.2)
+    if varying:
+        mats = {"lambda": lambda x, y, z: 10.0 + x + 2.0 * y * y, "mu": lambda x, y, z: 2.0 + np.sin(x)}
+    else:
+        mats = {"lambda": lambda x, y, z: 1.0e3 + 0.0 * x, "mu": lambda x, y, z: 0.5 + 0.0 * x}
+    functions = dict(mats, rhs=lambda x, y, z: _f_rhs(x, y, z)[:2])
+    bc_functions = {"u": lambda x, y, z: _u_exact(x, y, z)[:2]}
+
+    def gpu_forms(space, a):
+        wf = LETaylorHoodWeakForm(space)
+        wf.functions = functions
+        out = {"volume": ["form", range(len(space.discrete_spaces["u"].elements)), wf, a]}
+        if with_bc:
+            bf = LETaylorHoodWeakFormBCDirichlet(space)
+            bf.functions = bc_functions
+            out["bc"] = ["bc_form", range(len(space.discrete_spaces["u"].bc_elements)), bf, a]
+        return out
+
+    def ref_forms_fn(space):
+        out = [("form", ref_h1_multi.le_taylor_hood, functions, len(space.discrete_spaces["u"].element_ids))]
+        if with_bc:
+            out.append(("bc_form", ref_h1_multi.le_taylor_hood_bc_dirichlet, bc_functions,
+                        len(space.discrete_spaces["u"].bc_element_ids)))
+        return out
+
+    alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None
+    return Case(
+        mesh, lambda g: {"u": (2, 2, "Lagrange", 2, g), "p": (2, 1, "Lagrange", 1, g)},
+        {"u": [1], "p": [1]}, {"u": [2, 3, 4, 5] if with_bc else []}, gpu_forms, ref_forms_fn, alpha_fn=alpha_fn,
+    )
+
+
+def stress_constraint_case(dim=3, k=2, n=2, alpha=False):
+    from nfempy_b200.weak_forms import LEPrimalStressConstraintWeakForm
+    from oracle import ref_h1_multi
+
+    mesh = box_tet_mesh(n, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(n, jitter=0.2)
+
+    def s_target(x, y, z):
+        rows = [[1.0 + x, 0.5 * y, z * x], [0.5 * y, 2.0 - y * y, 0.1 + 0.0 * x], [z * x, 0.1 + 0.0 * x, np.sin(z)]]
+        return np.array([[rows[c][d] * np.ones_like(x) for d in range(dim)] for c in range(dim)])
+
+    functions = {"s_target": s_target, "lambda": lambda x, y, z: 1.0 + x + 2.0 * y * y,
+                 "mu": lambda x, y, z: 2.0 + np.sin(x)}
+
+    def gpu_forms(space, a):
+        wf = LEPrimalStressConstraintWeakForm(space)
+        wf.functions = functions
+        return {"volume": ["form", range(len(space.discrete_spaces["u"].elements)), wf, a]}
+
+    def ref_forms_fn(space):
+        return [("form", ref_h1_multi.le_stress_constraint, functions, len(space.discrete_spaces["u"].element_ids))]
+
+    alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None
+    return Case(mesh, lambda g: {"u": (dim, dim, "Lagrange", k, g)}, {"u": [1]}, {"u": []}, gpu_forms, ref_forms_fn,
+                alpha_fn=alpha_fn)
