@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--n", type=int, default=55, help="cubes per box edge (55 -> 998250 tets)")
-    ap.add_argument("--cpu-cells", type=int, default=240, help="cells in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-cells", type=int, default=720, help="cells in the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")

@@ -69,6 +69,12 @@ __global__ void __launch_bounds__(128)
         cur += t;
     }
     double *s_a = cur;  // [n_loc] local state
+    cur += n_loc;
+    double *s_cq = cur;  // [2][n_q][4] w det (A_id, A_tr, A_vol, A_dd) of the two H(div) fields at this cell's points
+    // the (F, F) blocks are computed per PAIR of vector basis functions (all row components at once) when every stress
+    // field has DIM rows; the per-entry loop below then only handles the couplings and the L2 masses
+    bool pair_pass = true;
+    for (int h = 0; h < P.n_hdiv; ++h) pair_pass = pair_pass && P.h_n_comp[h] == DIM;
 
     for (int64_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         double X[DIM + 1][3];
@@ -84,7 +90,17 @@ __global__ void __launch_bounds__(128)
                 s_T[t_off[h] + i] = P.h_Tcases[h][(int)P.h_cases[h][cell * NF + fc] * nfd * nfd + (i - fc * nfd * nfd)];
             }
         }
-        for (int q = threadIdx.x; q < n_q; q += blockDim.x) s_wd[q] = P.weights[q] * g.det;
+        for (int q = threadIdx.x; q < n_q; q += blockDim.x) {
+            const double wd = P.weights[q] * g.det;
+            s_wd[q] = wd;
+            for (int h = 0; h < P.n_hdiv; ++h) {
+                double *cq = s_cq + ((size_t)h * n_q + q) * 4;
+                cq[0] = P.h_a_id[h] ? wd * P.h_a_id[h][cell * n_q + q] : 0.0;
+                cq[1] = P.h_a_tr[h] ? wd * P.h_a_tr[h][cell * n_q + q] : 0.0;
+                cq[2] = P.h_a_vol[h] ? wd * P.h_a_vol[h][cell * n_q + q] : 0.0;
+                cq[3] = P.h_a_dd[h] ? wd * P.h_a_dd[h][cell * n_q + q] : 0.0;
+            }
+        }
         for (int i = threadIdx.x; i < n_loc; i += blockDim.x) s_a[i] = (alpha && dest) ? alpha[dest[cell * n_loc + i]] : 0.0;
         __syncthreads();
         for (int h = 0; h < P.n_hdiv; ++h) {
@@ -126,6 +142,57 @@ __global__ void __launch_bounds__(128)
         }
         __syncthreads();
         double *K = Ke + cell * (int64_t)n_loc * n_loc;
+        if (pair_pass) {
+            for (int h = 0; h < P.n_hdiv; ++h) {
+                const int np = P.h_n_phi[h], n_pairs = np * (np + 1) / 2;
+                const double *dd = P.h_dd_general[h] ? s_gd[h] : s_div[h];
+                const double dds = P.h_dd_general[h] ? idet : 1.0;  // s_gd carries det (cd div psi + g.psi)
+                const double *cqh = s_cq + (size_t)h * n_q * 4;
+                for (int pr = threadIdx.x; pr < n_pairs; pr += blockDim.x) {
+                    int a = 0, rem = pr;  // pair (a, b), a <= b, from the linear index over the upper triangle
+                    while (rem >= np - a) {
+                        rem -= np - a;
+                        ++a;
+                    }
+                    const int b = a + rem;
+                    double acc[DIM][DIM];
+#pragma unroll
+                    for (int r = 0; r < DIM; ++r)
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) acc[r][c] = 0.0;
+                    for (int q = 0; q < n_q; ++q) {
+                        const double *pa = s_psi[h] + (q * np + a) * DIM, *pb = s_psi[h] + (q * np + b) * DIM;
+                        const double *cq = cqh + q * 4;
+                        double va[DIM], vb[DIM], dot = 0.0;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) {
+                            va[d] = pa[d];
+                            vb[d] = pb[d];
+                            dot = fma(va[d], vb[d], dot);
+                        }
+                        const double diag = cq[0] * dot + cq[3] * (dd[q * np + a] * dds) * (dd[q * np + b] * dds);
+                        const double ctr = cq[1], cvol = cq[2];
+#pragma unroll
+                        for (int r = 0; r < DIM; ++r)
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) {
+                                // row (a, r), column (b, c): A_tr psi_b[r] psi_a[c] + A_vol psi_a[r] psi_b[c]
+                                double t = ctr * vb[r] * va[c] + cvol * va[r] * vb[c];
+                                if (r == c) t += diag;
+                                acc[r][c] += t;
+                            }
+                    }
+                    const int ra0 = off_h[h] + a * DIM, rb0 = off_h[h] + b * DIM;
+#pragma unroll
+                    for (int r = 0; r < DIM; ++r)
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) {
+                            K[(ra0 + r) * n_loc + rb0 + c] = acc[r][c];
+                            if (a != b) K[(rb0 + c) * n_loc + ra0 + r] = acc[r][c];  // the block is symmetric
+                        }
+                }
+            }
+        }
         for (int e = threadIdx.x; e < n_loc * n_loc; e += blockDim.x) {
             int row = e / n_loc, col = e - row * n_loc;
             // decode (kind, field, basis, comp)
@@ -161,6 +228,7 @@ __global__ void __launch_bounds__(128)
                 }
             }
             double acc = 0.0;
+            if (pair_pass && rk == 0 && ck == 0 && rf == cf) continue;  // written by the pair pass above
             if (rk == 0 && ck == 0) {
                 if (rf == cf) {
                     const int h = rf, np = P.h_n_phi[h];
@@ -256,7 +324,7 @@ extern "C" int nfa_local_hdiv_tensor(const nfa_tensor_form *form, const double *
         if (!P.l_val[l]) return fail("nfa_local_hdiv_tensor: L2 table missing");
         n_loc += P.l_n_phi[l] * P.l_n_comp[l];
     }
-    dbl += n_loc;
+    dbl += n_loc + (size_t)2 * P.n_q * 4;
     const size_t smem = sizeof(double) * dbl;
     if (smem > 220 * 1024) return fail("nfa_local_hdiv_tensor: element too large for the shared-memory staging");
     const int grid = (int)(n_cells < 148 * 8 ? n_cells : 148 * 8);
