@@ -1,4 +1,4 @@
-"""H(div) elements on simplices: Raviart-Thomas (degree 1..3, lowest = 1 as in basix) and BDM degree 1, 2, restated
+"""H(div) elements on simplices: Raviart-Thomas (degree 1..3, lowest = 1 as in basix) and BDM degree 1..3, restated
 from their published definition in the conventions of basix (un-vendored, unpinned dependency of the reference:
 R/requirements.txt:2; called at R/src/basis/finite_element.py:85-91 with ``lagrange_variant=gll_centroid``).
 
@@ -13,6 +13,8 @@ Construction (Ciarlet triple, exact rational arithmetic, then one rounding to do
   k-2, dof index ``i * dim + d`` (basis function major, direction minor);
 * dual basis, interior part (BDM_2): ``l(phi) = int_cell phi . w_e`` against the lowest-order Nedelec functions
   ``w_e = lam_a grad lam_b - lam_b grad lam_a``, one per cell edge (a, b) in the sub-entity order;
+* dual basis, interior part (BDM_3): moments against a basis of the degree-2 Nedelec space (``nedelec2_test_functions``);
+  the facet moments of BDM_3 use the equispaced cubic nodal family (``cubic_lattice``);
 * basis = dual basis: ``l_i(phi_j) = delta_ij``.
 
 PARITY UNPINNED: these conventions are written from basix's documented construction, not checked against a basix
@@ -67,8 +69,10 @@ def _simplex_integral(p):
 def _lagrange_nodal_polys(dim, degree):
     """Nodal Lagrange basis (equispaced; identical to gll_centroid for degree <= 2) on the reference simplex of
     dimension ``dim`` as exact polynomials, basix dof order (vertices, edges, faces, interior)."""
-    if degree > 2:
-        raise NotImplementedError("facet/interior moment spaces above degree 2 (RT > 3, BDM > 2) are not restated")
+    if degree > 3:
+        raise NotImplementedError("facet/interior moment spaces above degree 3 (RT > 4, BDM > 3) are not restated")
+    if degree == 3 and dim > 0:
+        return _nodal_polys_from_nodes(dim, 3, cubic_lattice(dim))
     if dim == 0:
         return [{(): Fraction(1)}]
     nvar = dim
@@ -86,6 +90,71 @@ def _lagrange_nodal_polys(dim, degree):
     for a, b in SUB_ENTITIES[dim][1]:
         out.append({k: 4 * v for k, v in _pmul(lam[a], lam[b]).items()})
     return out
+
+
+def cubic_lattice(dim):
+    """Equispaced cubic lattice on the reference interval / triangle in the dof order vertices, edges (two nodes per
+    edge at 1/3 and 2/3 from the edge's first vertex, edges in the sub-entity order), interior (triangle centroid).
+    basix's ``gll_centroid`` variant moves the edge nodes to Gauss-Lobatto points (irrational); the moment SPACE is the
+    same, the individual facet dofs of BDM_3 differ by a fixed invertible map -- part of the unpinned conventions."""
+    verts = [[Fraction(int(v)) for v in row] for row in REF_VERTICES[dim].tolist()]
+    nodes = [v[:] for v in verts]
+    for a, b in SUB_ENTITIES[dim][1]:
+        for t in (Fraction(1, 3), Fraction(2, 3)):
+            nodes.append([(1 - t) * verts[a][c] + t * verts[b][c] for c in range(dim)])
+    if dim == 2:
+        nodes.append([Fraction(1, 3), Fraction(1, 3)])
+    elif dim != 1:
+        raise NotImplementedError("cubic moment family on cells of dimension %d" % dim)
+    return nodes
+
+
+def _nodal_polys_from_nodes(dim, degree, nodes):
+    """Exact nodal basis of P_degree for the given (rational) nodes: inverse of the Vandermonde matrix."""
+    exps = [tuple(int(v) for v in e) for e in monomial_exponents(dim, degree)]
+    if len(exps) != len(nodes):
+        raise AssertionError("node count does not match the polynomial space")
+    V = []
+    for x in nodes:
+        row = []
+        for e in exps:
+            v = Fraction(1)
+            for c, p in enumerate(e):
+                v *= x[c] ** p
+            row.append(v)
+        V.append(row)
+    Vinv = _solve_exact(V)  # column i = monomial coefficients of the nodal function of node i
+    return [{e: Vinv[m][i] for m, e in enumerate(exps) if Vinv[m][i] != 0} for i in range(len(nodes))]
+
+
+def nedelec2_test_functions(dim):
+    """A basis of the first-kind Nedelec space of degree 2, ``[P_1]^d + {p in [Ptilde_2]^d : p . x = 0}``, as exact vector
+    polynomials: the 2-D rotated / 3-D cross products ``x x (x_i e_j)`` span the second summand (in 3-D they satisfy one
+    relation, ``x x x = 0``: the pair (z, e_z) is left out).  BDM_3's interior dofs are the moments against them."""
+    fns = []
+    mono = lambda *e: {tuple(e): Fraction(1)}
+    for c in range(dim):
+        for e in monomial_exponents(dim, 1):
+            fns.append([({tuple(int(v) for v in e): Fraction(1)} if cc == c else {}) for cc in range(dim)])
+    if dim == 2:
+        for e in ((1, 0), (0, 1)):  # (-y, x) * x, (-y, x) * y
+            m = mono(*e)
+            fns.append([{k: -v for k, v in _pmul(m, mono(0, 1)).items()}, _pmul(m, mono(1, 0))])
+    else:
+        unit = lambda i: tuple(1 if d == i else 0 for d in range(3))
+        for i in range(3):
+            for j in range(3):
+                if (i, j) == (2, 2):
+                    continue
+                # x x (x_i e_j): component c = eps(c, a, j) x_a x_i
+                vec = [{} for _ in range(3)]
+                for c in range(3):
+                    for a in range(3):
+                        sgn = ((c, a, j) in ((0, 1, 2), (1, 2, 0), (2, 0, 1))) - ((c, a, j) in ((0, 2, 1), (2, 1, 0), (1, 0, 2)))
+                        if sgn:
+                            vec[c] = _padd(vec[c], _pmul(mono(*unit(a)), mono(*unit(i))), sgn)
+                fns.append(vec)
+    return fns
 
 
 def _space_functions(family, dim, k):
@@ -181,8 +250,19 @@ def _functionals(family, dim, k):
                 return total
 
             out.append((dim, 0, functional))
-    elif family == "BDM" and k > 2:
-        raise NotImplementedError("BDM degree >= 3 needs second-order Nedelec interior moments and cubic facet moments")
+    elif family == "BDM" and k == 3:
+        for w in nedelec2_test_functions(dim):
+
+            def functional(vec, w=w):
+                total = Fraction(0)
+                for c in range(dim):
+                    if vec[c] and w[c]:
+                        total += _simplex_integral(_pmul(vec[c], w[c]))
+                return total
+
+            out.append((dim, 0, functional))
+    elif family == "BDM" and k > 3:
+        raise NotImplementedError("BDM degree >= 4 is not restated")
     return out
 
 
@@ -208,8 +288,8 @@ def build_hdiv(el):
         raise NotImplementedError("H(div) elements live on triangles and tetrahedra")
     if family == "RT" and not 1 <= k <= 3:
         raise NotImplementedError("RT degree %d is not restated (1..3 are)" % k)
-    if family == "BDM" and k not in (1, 2):
-        raise NotImplementedError("BDM degree %d is not restated (1 and 2 are)" % k)
+    if family == "BDM" and k not in (1, 2, 3):
+        raise NotImplementedError("BDM degree %d is not restated (1, 2 and 3 are)" % k)
     fns = _space_functions(family, dim, k)
     funcs = _functionals(family, dim, k)
     if len(fns) != len(funcs):

@@ -25,7 +25,7 @@ ROTATION_IS_FORWARD_SHIFT = True
 
 
 def _lagrange_nodes(dim, degree):
-    """Nodes of the nodal family of degree <= 2 on the reference simplex, basix order."""
+    """Nodes of the nodal family of degree <= 3 on the reference simplex, basix order."""
     verts = REF_VERTICES[dim] if dim > 0 else np.zeros((1, 0))
     if degree == 0:
         return verts.mean(axis=0, keepdims=True)
@@ -33,8 +33,14 @@ def _lagrange_nodes(dim, degree):
     if degree == 2:
         for a, b in SUB_ENTITIES[dim][1]:
             nodes.append(0.5 * (verts[a] + verts[b]))
+    elif degree == 3:  # the equispaced cubic lattice of basis/hdiv.py (BDM_3 facet moments)
+        for a, b in SUB_ENTITIES[dim][1]:
+            for t in (1.0 / 3.0, 2.0 / 3.0):
+                nodes.append((1.0 - t) * verts[a] + t * verts[b])
+        if dim == 2:
+            nodes.append(verts.mean(axis=0))
     elif degree != 1:
-        raise NotImplementedError("transformation of sub-entity dof families above degree 2")
+        raise NotImplementedError("transformation of sub-entity dof families above degree 3")
     return np.array(nodes)
 
 

@@ -14,6 +14,9 @@
 //   r_U      -int load_c phi_k  (+ J alpha when a state is given)
 // All coefficients are host-evaluated per quadrature point.  One CTA per cell: the mapped bases are staged in shared
 // memory, threads stride the n_loc^2 entries.  Output goes to the two-stage reduce (nfa_plan_reduce).
+#include <algorithm>
+#include <cstdlib>
+
 #include "nfa_common.cuh"
 
 using namespace nfa;
@@ -31,13 +34,17 @@ __device__ __forceinline__ double levi_civita(int a, int b, int c) {
 
 template <int DIM>
 __global__ void __launch_bounds__(128)
-    local_hdiv_tensor_kernel(const nfa_tensor_form P, const double *__restrict__ coords,
+    local_hdiv_tensor_kernel(const nfa_tensor_form P, int n_qc, const double *__restrict__ coords,
                              const int32_t *__restrict__ cell_nodes, int64_t n_cells, const double *__restrict__ alpha,
                              const int32_t *__restrict__ dest, double *__restrict__ Ke, double *__restrict__ re) {
     constexpr int NF = DIM + 1;
     extern __shared__ double smem[];
-    const int n_q = P.n_q;
-    // shared-memory layout
+    const int n_q_all = P.n_q;
+    // the quadrature points are processed in chunks of n_qc (all of them when the staged bases fit in shared memory;
+    // BDM_3 x RT_3 with 64 points does not): the first chunk writes the local matrix, the following ones add to it --
+    // every entry is owned by the same thread in every chunk
+    const int n_q = n_qc;
+    // shared-memory layout (sized for one chunk)
     double *s_psi[2], *s_div[2], *s_gd[2];
     double *cur = smem;
     int off_h[2], off_l[2], n_loc = 0;
@@ -82,6 +89,10 @@ __global__ void __launch_bounds__(128)
         Geom<DIM> g;
         compute_geom<DIM>(X, g);
         const double idet = 1.0 / g.det;
+        double *K = Ke + cell * (int64_t)n_loc * n_loc;
+        for (int q0 = 0; q0 < n_q_all; q0 += n_qc) {
+        const int nq = min(n_qc, n_q_all - q0);  // points of this chunk; global point index = q0 + q
+        const int64_t cq_base = cell * (int64_t)n_q_all + q0;
         __syncthreads();
         for (int h = 0; h < P.n_hdiv; ++h) {
             const int nfd = P.h_nfd[h];
@@ -90,24 +101,24 @@ __global__ void __launch_bounds__(128)
                 s_T[t_off[h] + i] = P.h_Tcases[h][(int)P.h_cases[h][cell * NF + fc] * nfd * nfd + (i - fc * nfd * nfd)];
             }
         }
-        for (int q = threadIdx.x; q < n_q; q += blockDim.x) {
-            const double wd = P.weights[q] * g.det;
+        for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+            const double wd = P.weights[q0 + q] * g.det;
             s_wd[q] = wd;
             for (int h = 0; h < P.n_hdiv; ++h) {
                 double *cq = s_cq + ((size_t)h * n_q + q) * 4;
-                cq[0] = P.h_a_id[h] ? wd * P.h_a_id[h][cell * n_q + q] : 0.0;
-                cq[1] = P.h_a_tr[h] ? wd * P.h_a_tr[h][cell * n_q + q] : 0.0;
-                cq[2] = P.h_a_vol[h] ? wd * P.h_a_vol[h][cell * n_q + q] : 0.0;
-                cq[3] = P.h_a_dd[h] ? wd * P.h_a_dd[h][cell * n_q + q] : 0.0;
+                cq[0] = P.h_a_id[h] ? wd * P.h_a_id[h][cq_base + q] : 0.0;
+                cq[1] = P.h_a_tr[h] ? wd * P.h_a_tr[h][cq_base + q] : 0.0;
+                cq[2] = P.h_a_vol[h] ? wd * P.h_a_vol[h][cq_base + q] : 0.0;
+                cq[3] = P.h_a_dd[h] ? wd * P.h_a_dd[h][cq_base + q] : 0.0;
             }
         }
         for (int i = threadIdx.x; i < n_loc; i += blockDim.x) s_a[i] = (alpha && dest) ? alpha[dest[cell * n_loc + i]] : 0.0;
         __syncthreads();
         for (int h = 0; h < P.n_hdiv; ++h) {
             const int np = P.h_n_phi[h], nfd = P.h_nfd[h], n_fdofs = NF * nfd;
-            const double *val = P.h_val[h], *dv = P.h_div[h];
+            const double *val = P.h_val[h] + (size_t)q0 * np * DIM, *dv = P.h_div[h] + (size_t)q0 * np;
             const double *cd = P.h_div_cd[h], *gv = P.h_div_g[h];
-            for (int idx = threadIdx.x; idx < n_q * np; idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < nq * np; idx += blockDim.x) {
                 const int q = idx / np, j = idx - q * np;
                 double vh[DIM], dh = 0.0;
 #pragma unroll
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(128)
                     for (int k = 0; k < DIM; ++k) vh[k] = val[((int64_t)q * np + j) * DIM + k];
                     dh = dv[q * np + j];
                 }
-                double gd = (cd ? cd[cell * n_q + q] : 1.0) * dh;  // c_d div^ psi  (reference divergence: no 1/det)
+                double gd = (cd ? cd[cq_base + q] : 1.0) * dh;  // c_d div^ psi  (reference divergence: no 1/det)
 #pragma unroll
                 for (int c = 0; c < DIM; ++c) {
                     double v = 0.0;
@@ -134,14 +145,13 @@ __global__ void __launch_bounds__(128)
                     for (int k = 0; k < DIM; ++k) v += g.J[c][k] * vh[k];
                     v *= idet;
                     s_psi[h][(q * np + j) * DIM + c] = v;
-                    if (gv) gd += g.det * gv[(cell * n_q + q) * DIM + c] * v;
+                    if (gv) gd += g.det * gv[(cq_base + q) * DIM + c] * v;
                 }
                 s_div[h][q * np + j] = dh * idet;
                 s_gd[h][q * np + j] = gd;
             }
         }
         __syncthreads();
-        double *K = Ke + cell * (int64_t)n_loc * n_loc;
         if (pair_pass) {
             for (int h = 0; h < P.n_hdiv; ++h) {
                 const int np = P.h_n_phi[h], n_pairs = np * (np + 1) / 2;
@@ -160,7 +170,7 @@ __global__ void __launch_bounds__(128)
                     for (int r = 0; r < DIM; ++r)
 #pragma unroll
                         for (int c = 0; c < DIM; ++c) acc[r][c] = 0.0;
-                    for (int q = 0; q < n_q; ++q) {
+                    for (int q = 0; q < nq; ++q) {
                         const double *pa = s_psi[h] + (q * np + a) * DIM, *pb = s_psi[h] + (q * np + b) * DIM;
                         const double *cq = cqh + q * 4;
                         double va[DIM], vb[DIM], dot = 0.0;
@@ -187,8 +197,9 @@ __global__ void __launch_bounds__(128)
                     for (int r = 0; r < DIM; ++r)
 #pragma unroll
                         for (int c = 0; c < DIM; ++c) {
-                            K[(ra0 + r) * n_loc + rb0 + c] = acc[r][c];
-                            if (a != b) K[(rb0 + c) * n_loc + ra0 + r] = acc[r][c];  // the block is symmetric
+                            const double v = q0 == 0 ? acc[r][c] : K[(ra0 + r) * n_loc + rb0 + c] + acc[r][c];
+                            K[(ra0 + r) * n_loc + rb0 + c] = v;
+                            if (a != b) K[(rb0 + c) * n_loc + ra0 + r] = v;  // the block is symmetric
                         }
                 }
             }
@@ -233,24 +244,24 @@ __global__ void __launch_bounds__(128)
                 if (rf == cf) {
                     const int h = rf, np = P.h_n_phi[h];
                     const double *aid = P.h_a_id[h], *atr = P.h_a_tr[h], *avol = P.h_a_vol[h], *add = P.h_a_dd[h];
-                    for (int q = 0; q < n_q; ++q) {
+                    for (int q = 0; q < nq; ++q) {
                         const double *pa = s_psi[h] + (q * np + ra) * DIM, *pb = s_psi[h] + (q * np + ca) * DIM;
                         double t = 0.0;
                         if (rc == cc) {
                             double dot = 0.0;
 #pragma unroll
                             for (int d = 0; d < DIM; ++d) dot += pa[d] * pb[d];
-                            if (aid) t += aid[cell * n_q + q] * dot;
+                            if (aid) t += aid[cq_base + q] * dot;
                             if (add) {
                                 if (P.h_dd_general[h])  // s_gd carries det (cd div psi + g.psi)
-                                    t += add[cell * n_q + q] * (s_gd[h][q * np + ra] * idet) * (s_gd[h][q * np + ca] * idet);
+                                    t += add[cq_base + q] * (s_gd[h][q * np + ra] * idet) * (s_gd[h][q * np + ca] * idet);
                                 else
-                                    t += add[cell * n_q + q] * s_div[h][q * np + ra] * s_div[h][q * np + ca];
+                                    t += add[cq_base + q] * s_div[h][q * np + ra] * s_div[h][q * np + ca];
                             }
                         }
                         if (rc < DIM && cc < DIM) {
-                            if (atr) t += atr[cell * n_q + q] * pb[rc] * pa[cc];
-                            if (avol) t += avol[cell * n_q + q] * pa[rc] * pb[cc];
+                            if (atr) t += atr[cq_base + q] * pb[rc] * pa[cc];
+                            if (avol) t += avol[cq_base + q] * pa[rc] * pb[cc];
                         }
                         acc += s_wd[q] * t;
                     }
@@ -258,30 +269,31 @@ __global__ void __launch_bounds__(128)
             } else if (rk == 1 && ck == 1) {
                 if (rf == cf && rc == cc && P.l_a_mass[rf]) {
                     const int l = rf, np = P.l_n_phi[l];
-                    const double *am = P.l_a_mass[l], *lv = P.l_val[l];
-                    for (int q = 0; q < n_q; ++q) acc += s_wd[q] * am[cell * n_q + q] * lv[q * np + ra] * lv[q * np + ca];
+                    const double *am = P.l_a_mass[l], *lv = P.l_val[l] + (size_t)q0 * np;
+                    for (int q = 0; q < nq; ++q) acc += s_wd[q] * am[cq_base + q] * lv[q * np + ra] * lv[q * np + ca];
                 }
             } else {
                 // L2 x H(div) coupling (symmetric): put the L2 dof in (l, k, lc) and the H(div) dof in (h, a, hc)
                 const int l = rk == 1 ? rf : cf, k = rk == 1 ? ra : ca, lc = rk == 1 ? rc : cc;
                 const int h = rk == 1 ? cf : rf, a = rk == 1 ? ca : ra, hc = rk == 1 ? cc : rc;
                 const int npl = P.l_n_phi[l], nph = P.h_n_phi[h];
-                const double *lv = P.l_val[l];
+                const double *lv = P.l_val[l] + (size_t)q0 * npl;
                 if (P.div_coupling[l][h] && lc == hc) {
-                    for (int q = 0; q < n_q; ++q) acc += P.weights[q] * lv[q * npl + k] * s_gd[h][q * nph + a];
+                    for (int q = 0; q < nq; ++q) acc += P.weights[q0 + q] * lv[q * npl + k] * s_gd[h][q * nph + a];
                 }
                 if (P.asym_coupling[l][h]) {
                     const int ce = P.l_n_comp[l] == 1 ? 2 : lc;  // the single rotation of a 2-D problem is the z one
                     for (int d = 0; d < DIM; ++d) {
                         const double eps = levi_civita(ce, hc, d);
                         if (eps != 0.0)
-                            for (int q = 0; q < n_q; ++q)
+                            for (int q = 0; q < nq; ++q)
                                 acc += eps * s_wd[q] * lv[q * npl + k] * s_psi[h][(q * nph + a) * DIM + d];
                     }
                 }
             }
-            K[e] = acc;
+            K[e] = q0 == 0 ? acc : K[e] + acc;
         }
+        }  // quadrature chunks
         __syncthreads();  // K of this cell is complete in global memory for the row products below
         for (int row = threadIdx.x; row < n_loc; row += blockDim.x) {
             double acc = 0.0;
@@ -293,8 +305,8 @@ __global__ void __launch_bounds__(128)
                 const double *ld = P.l_load[l];
                 if (ld) {
                     const int np = P.l_n_phi[l], ncp = P.l_n_comp[l];
-                    for (int q = 0; q < n_q; ++q)
-                        acc -= s_wd[q] * ld[(cell * n_q + q) * ncp + c] * P.l_val[l][q * np + k];
+                    for (int q = 0; q < n_q_all; ++q)
+                        acc -= P.weights[q] * g.det * ld[(cell * (int64_t)n_q_all + q) * ncp + c] * P.l_val[l][q * np + k];
                 }
             }
             re[cell * n_loc + row] = acc;
@@ -313,29 +325,36 @@ extern "C" int nfa_local_hdiv_tensor(const nfa_tensor_form *form, const double *
     if (P.n_hdiv < 1 || P.n_hdiv > 2 || P.n_l2 < 0 || P.n_l2 > 2) return fail("nfa_local_hdiv_tensor: 1-2 H(div) and 0-2 L2 fields");
     if (P.dim != 2 && P.dim != 3) return fail("nfa_local_hdiv_tensor: dim must be 2 or 3");
     cudaStream_t s = (cudaStream_t)stream;
-    size_t dbl = P.n_q;
+    size_t per_q = 1 + 2 * 4, fixed = 0;  // doubles per staged quadrature point / independent of the chunk size
     int n_loc = 0;
     for (int h = 0; h < P.n_hdiv; ++h) {
         if (!P.h_val[h] || !P.h_div[h] || !P.h_Tcases[h] || !P.h_cases[h]) return fail("nfa_local_hdiv_tensor: H(div) tables missing");
-        dbl += (size_t)P.n_q * P.h_n_phi[h] * (P.dim + 2) + (size_t)(P.dim + 1) * P.h_nfd[h] * P.h_nfd[h];
+        per_q += (size_t)P.h_n_phi[h] * (P.dim + 2);
+        fixed += (size_t)(P.dim + 1) * P.h_nfd[h] * P.h_nfd[h];
         n_loc += P.h_n_phi[h] * P.h_n_comp[h];
     }
     for (int l = 0; l < P.n_l2; ++l) {
         if (!P.l_val[l]) return fail("nfa_local_hdiv_tensor: L2 table missing");
         n_loc += P.l_n_phi[l] * P.l_n_comp[l];
     }
-    dbl += n_loc + (size_t)2 * P.n_q * 4;
-    const size_t smem = sizeof(double) * dbl;
-    if (smem > 220 * 1024) return fail("nfa_local_hdiv_tensor: element too large for the shared-memory staging");
+    fixed += n_loc;
+    // all points at once when the staged bases fit in 200 KB of shared memory, else equal chunks of points
+    const size_t budget = 200 * 1024 / sizeof(double);
+    if (fixed + per_q > budget) return fail("nfa_local_hdiv_tensor: element too large for the shared-memory staging");
+    int n_qc = (int)std::min<size_t>((size_t)P.n_q, (budget - fixed) / per_q);
+    if (const char *e = getenv("NFA_TENSOR_QCHUNK")) n_qc = std::max(1, std::min(n_qc, atoi(e)));  // tests
+    const int n_chunks = (P.n_q + n_qc - 1) / n_qc;
+    n_qc = (P.n_q + n_chunks - 1) / n_chunks;
+    const size_t smem = sizeof(double) * (fixed + per_q * (size_t)n_qc);
     const int grid = (int)(n_cells < 148 * 8 ? n_cells : 148 * 8);
     if (P.dim == 3) {
         auto kern = local_hdiv_tensor_kernel<3>;
         NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 128, smem, s>>>(P, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
+        kern<<<grid, 128, smem, s>>>(P, n_qc, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
     } else {
         auto kern = local_hdiv_tensor_kernel<2>;
         NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 128, smem, s>>>(P, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
+        kern<<<grid, 128, smem, s>>>(P, n_qc, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
     }
     NFA_LAUNCH_CHECK();
     return 0;

@@ -90,7 +90,8 @@ def _barycentric(dim, pts):
 
 
 def tabulate_lagrange(dim, k, pts):
-    """Closed-form P0/P1/P2 values and reference gradients, basix dof order (vertices, then edges)."""
+    """Closed-form P0/P1/P2 (numerical Vandermonde for P3) values and reference gradients, basix dof order (vertices,
+    edges, faces)."""
     pts = np.asarray(pts, dtype=float).reshape(-1, dim)
     nq = len(pts)
     lam, dlam = _barycentric(dim, pts)
@@ -117,7 +118,43 @@ def tabulate_lagrange(dim, k, pts):
             for d in range(dim):
                 tab[1 + d, :, dim + 1 + e, 0] = 4 * (lam[:, a] * dlam[b, d] + lam[:, b] * dlam[a, d])
         return tab
+    if k == 3:
+        return _tabulate_lagrange_p3(dim, pts)
     raise NotImplementedError("oracle Lagrange degree %d" % k)
+
+
+def _tabulate_lagrange_p3(dim, pts):
+    """Cubic nodal basis for the ``gll_centroid`` nodes (vertices, two Gauss-Lobatto points per edge listed from the edge's
+    lower to its higher local vertex, face centroids), by a numerical Vandermonde solve in the monomial basis."""
+    verts = np.concatenate([np.zeros((1, dim)), np.eye(dim)], axis=0)
+    g = (1.0 - 1.0 / np.sqrt(5.0)) / 2.0
+    nodes = [v for v in verts]
+    for a, b in SUB[dim][1]:
+        nodes += [verts[a] + t * (verts[b] - verts[a]) for t in (g, 1.0 - g)]
+    if dim >= 2:
+        for lv in SUB[dim][2]:
+            nodes.append(verts[list(lv)].mean(axis=0))
+    nodes = np.array(nodes)
+    exps = [e for total in range(4) for e in np.ndindex(*([total + 1] * dim)) if sum(e) == total]
+
+    def mono(x):
+        val = np.stack([np.prod(x ** np.array(e), axis=1) for e in exps], axis=1)
+        grad = np.zeros((dim, len(x), len(exps)))
+        for m, e in enumerate(exps):
+            for d in range(dim):
+                if e[d] > 0:
+                    ee = np.array(e)
+                    ee[d] -= 1
+                    grad[d, :, m] = e[d] * np.prod(x**ee, axis=1)
+        return val, grad
+
+    C = np.linalg.inv(mono(nodes)[0])  # column i: monomial coefficients of the nodal function of node i
+    val, grad = mono(np.asarray(pts, dtype=float).reshape(-1, dim))
+    tab = np.zeros((1 + dim, len(val), len(nodes), 1))
+    tab[0, :, :, 0] = val @ C
+    for d in range(dim):
+        tab[1 + d, :, :, 0] = grad[d] @ C
+    return tab
 
 
 def tabulate(family, dim, k, pts, discontinuous=False):

@@ -3,7 +3,7 @@
 H(div) pieces of the basix stand-in, written independently of ``nfempy_b200.basis.hdiv`` (numerical quadrature +
 ``numpy.linalg.solve`` here, exact rational arithmetic there):
 
-* ``tabulate``                -- RT_k (k = 1..3) / BDM_1, BDM_2 values and reference derivatives, ``[1+dim, nq, nphi, dim]``;
+* ``tabulate``                -- RT_k (k = 1..3) / BDM_1..3 values and reference derivatives, ``[1+dim, nq, nphi, dim]``;
 * ``entity_transformations``  -- signed permutations of the facet dof families, as explicit tables;
 * ``permute_and_transform``   -- R/src/basis/permute_and_transform.py:8-149 line by line (edge test in 2-D against the
   edge cell's own ``node_tags``, face table of six permutation cases, forced reflection of tagged faces with
@@ -50,11 +50,53 @@ def _mono_tab(exps, pts):
     return val, grad
 
 
+def _cubic_lattice(fdim):
+    """Equispaced cubic nodes on the reference interval / triangle: vertices, two per edge (1/3, 2/3 from the edge's first
+    vertex, edges (1,2), (0,2), (0,1) on the triangle), centroid."""
+    v = _REF_V[fdim]
+    nodes = [x for x in v]
+    for a, b in SUB[fdim][1]:
+        nodes += [(2.0 * v[a] + v[b]) / 3.0, (v[a] + 2.0 * v[b]) / 3.0]
+    if fdim == 2:
+        nodes.append(v.mean(axis=0))
+    return np.array(nodes)
+
+
 def _facet_family(fdim, degree, s):
     """Nodal Lagrange family of ``degree`` on the reference facet at parameter points ``s`` -> [nq, n]."""
     if fdim == 0:
         return np.ones((len(s), 1))
+    if degree == 3:  # BDM_3: equispaced cubic family, by a numerical Vandermonde solve
+        exps = _monomials(fdim, 3)
+        V, _ = _mono_tab(exps, _cubic_lattice(fdim))
+        return _mono_tab(exps, s)[0] @ np.linalg.inv(V)
     return ref_basis.tabulate_lagrange(fdim, degree, s)[0, :, :, 0]
+
+
+def _nedelec2(dim, pts):
+    """[n_fn, nq, dim]: a basis of the degree-2 first-kind Nedelec space at ``pts`` -- [P1]^d, then (-y, x) x, (-y, x) y
+    (2-D) or x cross (x_i e_j), (i, j) != (2, 2) (3-D).  BDM_3's interior moments are taken against these."""
+    pts = np.asarray(pts, dtype=float)
+    nq = len(pts)
+    out = []
+    p1 = _mono_tab(_monomials(dim, 1), pts)[0].T  # the P1 monomials in the exponent order both implementations use
+    for c in range(dim):
+        for m in p1:
+            w = np.zeros((nq, dim))
+            w[:, c] = m
+            out.append(w)
+    if dim == 2:
+        rot = np.stack([-pts[:, 1], pts[:, 0]], axis=1)
+        out += [rot * pts[:, [0]], rot * pts[:, [1]]]
+    else:
+        for i in range(3):
+            for j in range(3):
+                if (i, j) == (2, 2):
+                    continue
+                e = np.zeros(3)
+                e[j] = 1.0
+                out.append(np.cross(pts, pts[:, [i]] * e[None, :]))
+    return np.array(out)
 
 
 _CACHE = {}
@@ -121,8 +163,14 @@ def _element(family, dim, k):
             w = lam[:, [a]] * glam[b][None, :] - lam[:, [b]] * glam[a][None, :]  # [nq, dim]
             rows.append(np.einsum("scm,qm,qc,q->s", space, val, w, cw))
             entity.append((dim, 0))
-    elif family == "BDM" and k > 2:
-        raise NotImplementedError("oracle BDM degree >= 3")
+    elif family == "BDM" and k == 3:
+        cp, cw = ref_basis.gauss_jacobi(dim, qdeg)
+        val, _ = _mono_tab(exps, cp)
+        for w in _nedelec2(dim, cp):
+            rows.append(np.einsum("scm,qm,qc,q->s", space, val, w, cw))
+            entity.append((dim, 0))
+    elif family == "BDM" and k > 3:
+        raise NotImplementedError("oracle BDM degree >= 4")
     D = np.array(rows)  # D[i, s]
     C = np.linalg.solve(D, np.eye(len(D)))  # phi_j = sum_s C[s, j] space_s
     coeffs = np.einsum("sj,scm->jcm", C, space)
@@ -162,11 +210,12 @@ def entity_transformations(family, dim, k):
     m = k - 1 if family == "RT" else k
     out = {}
     if dim == 2:
-        image = {0: [0], 1: [1, 0], 2: [1, 0, 2]}[m]
+        image = {0: [0], 1: [1, 0], 2: [1, 0, 2], 3: [1, 0, 3, 2]}[m]
         out["interval"] = [-_perm_matrix(image)]
     else:
-        rot = {0: [0], 1: [1, 2, 0], 2: [1, 2, 0, 4, 5, 3]}[m]
-        ref = {0: [0], 1: [0, 2, 1], 2: [0, 2, 1, 3, 5, 4]}[m]
+        # degree 3: nodes v0 v1 v2 | edge (1,2): 3 4 | edge (0,2): 5 6 | edge (0,1): 7 8 | centroid 9
+        rot = {0: [0], 1: [1, 2, 0], 2: [1, 2, 0, 4, 5, 3], 3: [1, 2, 0, 6, 5, 8, 7, 3, 4, 9]}[m]
+        ref = {0: [0], 1: [0, 2, 1], 2: [0, 2, 1, 3, 5, 4], 3: [0, 2, 1, 4, 3, 7, 8, 5, 6, 9]}[m]
         out["interval"] = [np.zeros((0, 0))]
         out["triangle"] = [_perm_matrix(rot), -_perm_matrix(ref)]
     return out

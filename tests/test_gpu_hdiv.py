@@ -20,10 +20,13 @@ def test_mixed_poisson_rt_2d(k):
     compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
 
 
-@pytest.mark.parametrize("dim,k", [(2, 1), (3, 1), (2, 2), (3, 2)])
+@pytest.mark.parametrize("dim,k", [(2, 1), (3, 1), (2, 2), (3, 2), (2, 3), (3, 3)])
 def test_mixed_poisson_bdm(dim, k):
-    case = mixed_poisson_case(dim=dim, k=k, n=2 if k == 1 else (1 if dim == 3 else 2), family="BDM")
-    compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
+    """BDM_3 (k = 3): cubic facet families (4 / 10 dofs per facet with their orientation matrices) and interior moments
+    against the degree-2 Nedelec space; its oracle inverts a 20 x 20 / 60 x 60 dual matrix numerically and is the less accurate
+    side (see tests/test_cpu_hdiv.py), hence the wider tolerance for that case."""
+    case = mixed_poisson_case(dim=dim, k=k, n=2 if k == 1 else (1 if dim == 3 else 2), family="BDM", varying=(k == 3))
+    compare_csr(case.run_gpu(), case.run_oracle(), 1e-10 if k == 3 else RTOL)
 
 
 def test_mixed_poisson_varying_kappa_no_bc():

@@ -77,3 +77,21 @@ def test_example_driver_scatter_policies_cosserat(policy, diag):
     full = case.run_oracle()
     assert len(ref[1]) < len(full[1])
     compare_csr(got, ref, RTOL)
+
+
+@pytest.mark.parametrize("kind,m_family", [("lce_scaled", "RT"), ("lce", "BDM")])
+def test_config_4_order_bdm3(kind, m_family):
+    """BASELINE config 4's order: s in BDM_3, m in RT_3 (348 local dofs) or BDM_3 (420), u, t in P_2^disc, 64 quadrature
+    points -- the staged bases exceed shared memory, so the kernel walks the points in chunks.  The oracle's BDM_3 comes
+    from a numerical 60 x 60 solve (the less accurate side): tolerance 1e-10."""
+    case = tensor_mixed_case(kind=kind, dim=3, s_family="BDM", m_family=m_family, k=3, n=1)
+    compare_csr(case.run_gpu(), case.run_oracle(), 1e-10)
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 5])
+def test_quadrature_chunking_is_transparent(chunk, monkeypatch):
+    """Forcing small chunks of quadrature points (NFA_TENSOR_QCHUNK) must not change the result beyond round-off."""
+    case = tensor_mixed_case(kind="lce_scaled", dim=3, s_family="BDM", m_family="RT", k=2, n=1)
+    ref = case.run_oracle()
+    monkeypatch.setenv("NFA_TENSOR_QCHUNK", str(chunk))
+    compare_csr(case.run_gpu(), ref, RTOL)
