@@ -287,6 +287,18 @@ int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *d_coords, c
                                   const double *d_lambda, int64_t lambda_stride, const double *d_mu,
                                   int64_t mu_stride, double *d_vals, nfa_stream stream);
 
+/* ---- penalised normal trace of a row-wise H(div) field on boundary facets: LCEDualWeakFormBCNeumann
+ * (R/src/weak_forms/lce_dual_weak_form.py:759-871; the same class in le_dual_weak_form.py:581-644 and
+ * lce_scaled_dual_weak_form.py:814-917).  Same facet inputs as nfa_local_hdiv_facet_vec; writes the field's block
+ * J[(k,c),(l,c)] = beta int (psi_k.n)(psi_l.n) at [off, off + nfd * n_comp) of the facet's n_loc x n_loc local matrix
+ * (zeroed by the caller) and r[(k,c)] = -beta int g_c (psi_k.n). */
+int nfa_local_hdiv_facet_penalty(int dim, int nfd, int n_q, int n_comp, const double *d_trace_tab,
+                                 const int32_t *d_tidx, const double *d_weights, const double *d_Tcases,
+                                 const int8_t *d_cases, const double *d_coords, const int32_t *d_facet_nodes,
+                                 const int32_t *d_neigh_nodes, const double *d_normals, const double *d_g,
+                                 int64_t n_facets, double beta, int off, int n_loc, double *d_Ke, double *d_re,
+                                 nfa_stream stream);
+
 /* ---- generic multi-field Lagrange volume form: the local kernel of LCEPrimalWeakForm
  * (R/src/weak_forms/lce_primal_weak_form.py:9-220), LETaylorHoodWeakForm (R/src/weak_forms/le_taylor_hood_weak_form.py:9-186)
  * and LEPrimalStressConstraintWeakForm (R/src/weak_forms/le_primal_stress_constraint_weak_form.py:10-126).

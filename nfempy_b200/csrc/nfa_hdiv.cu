@@ -639,6 +639,79 @@ __global__ void __launch_bounds__(128)
 }
 
 
+// Penalised normal trace ("Neumann" condition of the mixed elasticity forms: LCEDualWeakFormBCNeumann,
+// R/src/weak_forms/lce_dual_weak_form.py:759-871, le_dual_weak_form.py:581-644, lce_scaled_dual_weak_form.py:814-917):
+// with phi_k = psi_k . n the normal trace of the neighbour's facet functions, per component c of the row-wise field
+//   J[(k, c), (l, c)] = beta sum_q det_F w phi_k phi_l,     r[(k, c)] = -beta sum_q det_F w g_c(x_q) phi_k.
+// One warp per facet; the block of this field sits at [off, off + nfd * n_comp) of the facet's local numbering (the
+// caller zeroes Ke: blocks coupling different fields / components are stored zeros).
+template <int DIM>
+__global__ void __launch_bounds__(128)
+    local_hdiv_facet_penalty_kernel(int nfd, int n_q, int n_comp, const double *__restrict__ trace_tab,
+                                    const int32_t *__restrict__ tidx, const double *__restrict__ weights,
+                                    const double *__restrict__ Tcases, const int8_t *__restrict__ cases,
+                                    const double *__restrict__ coords, const int32_t *__restrict__ facet_nodes,
+                                    const int32_t *__restrict__ neigh_nodes, const double *__restrict__ normals,
+                                    const double *__restrict__ g, int64_t n_facets, double beta, int off, int n_loc,
+                                    double *__restrict__ Ke, double *__restrict__ re) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *s_phi = smem + (size_t)warp * (nfd * n_q + n_q);  // [n_q][nfd] normal traces, then [n_q] det_F w
+    double *s_w = s_phi + nfd * n_q;
+    for (int64_t fc = (int64_t)blockIdx.x * 4 + warp; fc < n_facets; fc += (int64_t)gridDim.x * 4) {
+        double X[DIM + 1][3];
+        load_cell_coords<DIM>(coords, neigh_nodes, fc, X);
+        Geom<DIM> gm;
+        compute_geom<DIM>(X, gm);
+        double det_f = 1.0;
+        if constexpr (DIM > 1) {
+            double XF[DIM][3];
+            load_cell_coords<DIM - 1>(coords, facet_nodes, fc, XF);
+            Geom<DIM - 1> gf;
+            compute_geom<DIM - 1>(XF, gf);
+            det_f = gf.det;
+        }
+        const double *T = Tcases + (int)cases[fc] * nfd * nfd;
+        const double *tab = trace_tab + (int64_t)tidx[fc] * n_q * nfd * DIM;
+        double jn[DIM];  // (J^T n) / det: psi . n = (1 / det) n^T J psi_hat
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) v += gm.J[c][k] * normals[fc * 3 + c];
+            jn[k] = v / gm.det;
+        }
+        __syncwarp();
+        for (int i = lane; i < n_q * nfd; i += 32) {
+            const int q = i / nfd, k = i - q * nfd;
+            double flux = 0.0;
+            for (int b = 0; b < nfd; ++b) {
+                const double *src = tab + ((int64_t)q * nfd + b) * DIM;
+                double t = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < DIM; ++kk) t += jn[kk] * src[kk];
+                flux += T[k * nfd + b] * t;
+            }
+            s_phi[i] = flux;
+        }
+        for (int q = lane; q < n_q; q += 32) s_w[q] = det_f * weights[q];
+        __syncwarp();
+        double *K = Ke + fc * (int64_t)n_loc * n_loc;
+        for (int i = lane; i < nfd * nfd; i += 32) {
+            const int k = i / nfd, l = i - k * nfd;
+            double acc = 0.0;
+            for (int q = 0; q < n_q; ++q) acc += beta * s_w[q] * s_phi[q * nfd + k] * s_phi[q * nfd + l];
+            for (int c = 0; c < n_comp; ++c) K[(off + k * n_comp + c) * (int64_t)n_loc + off + l * n_comp + c] = acc;
+        }
+        for (int kc = lane; kc < nfd * n_comp; kc += 32) {
+            const int k = kc / n_comp, c = kc - k * n_comp;
+            double acc = 0.0;
+            for (int q = 0; q < n_q; ++q) acc -= beta * s_w[q] * g[(fc * n_q + q) * n_comp + c] * s_phi[q * nfd + k];
+            re[fc * n_loc + off + kc] = acc;
+        }
+    }
+}
+
 // Two-flux mixed transport (SundusDualWeakForm, R/examples/parabolic_diffusive_problem/SundusWeakForm.py:11-177):
 // fields [mp | mc | p | c], mp/mc in the same H(div) element, p/c in the same L2 element.  Nonlinear in c through the
 // reaction R = 1 + eta c^2, so the kernel evaluates the state at the current iterate and writes residual and tangent.
@@ -1243,6 +1316,34 @@ extern "C" int nfa_local_hdiv_facet_vec(int dim, int nfd, int n_q, int n_comp, c
                                                         re_off, re_stride);
     else
         return fail("nfa_local_hdiv_facet_vec: dim must be 2 or 3");
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nfa_local_hdiv_facet_penalty(int dim, int nfd, int n_q, int n_comp, const double *trace_tab,
+                                            const int32_t *tidx, const double *weights, const double *Tcases,
+                                            const int8_t *cases, const double *coords, const int32_t *facet_nodes,
+                                            const int32_t *neigh_nodes, const double *normals, const double *g,
+                                            int64_t n_facets, double beta, int off, int n_loc, double *Ke, double *re,
+                                            nfa_stream stream) {
+    if (n_facets == 0) return 0;
+    if (n_comp < 1 || n_loc < off + nfd * n_comp) return fail("nfa_local_hdiv_facet_penalty: bad output layout");
+    if (!Ke || !re || !g) return fail("nfa_local_hdiv_facet_penalty: NULL buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ctas = (n_facets + 3) / 4;
+    const int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
+    const size_t smem = sizeof(double) * 4 * ((size_t)nfd * n_q + n_q);
+    if (smem > 48 * 1024) return fail("nfa_local_hdiv_facet_penalty: facet family too large");
+    if (dim == 3)
+        local_hdiv_facet_penalty_kernel<3><<<grid, 128, smem, s>>>(nfd, n_q, n_comp, trace_tab, tidx, weights, Tcases, cases,
+                                                                   coords, facet_nodes, neigh_nodes, normals, g, n_facets,
+                                                                   beta, off, n_loc, Ke, re);
+    else if (dim == 2)
+        local_hdiv_facet_penalty_kernel<2><<<grid, 128, smem, s>>>(nfd, n_q, n_comp, trace_tab, tidx, weights, Tcases, cases,
+                                                                   coords, facet_nodes, neigh_nodes, normals, g, n_facets,
+                                                                   beta, off, n_loc, Ke, re);
+    else
+        return fail("nfa_local_hdiv_facet_penalty: dim must be 2 or 3");
     NFA_LAUNCH_CHECK();
     return 0;
 }

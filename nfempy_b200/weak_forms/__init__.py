@@ -10,6 +10,7 @@ from .unscaled_elliptic_weak_form import UnscaledEllipticWeakForm, UnscaledEllip
 from .scaled_to_physical_l2_projection import ScaledToPhysicalL2Projection
 from .tensor_mixed import (LEDualWeakForm, LEDualWeakFormBCDirichlet, LCEDualWeakForm, LCEDualWeakFormBCDirichlet,
                            LCEScaledDualWeakForm, LCEScaledDualWeakFormBCDirichlet, LERieszMapWeakForm,
-                           LCERieszMapWeakForm, LCEScaledRieszMapWeakForm)
+                           LCERieszMapWeakForm, LCEScaledRieszMapWeakForm, LEDualWeakFormBCNeumann,
+                           LCEDualWeakFormBCNeumann)
 from .h1_multifield import (LCEPrimalWeakForm, LCEPrimalWeakFormBCDirichlet, LETaylorHoodWeakForm,
                             LETaylorHoodWeakFormBCDirichlet, LEPrimalStressConstraintWeakForm)

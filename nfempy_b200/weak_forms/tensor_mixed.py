@@ -313,3 +313,35 @@ class LCEScaledDualWeakFormBCDirichlet(HdivTensorNaturalBC):
         if field == "m":
             g = g * (coefficients.evaluate(self.functions["l"], x) + 1.0e-16)[:, :, None]  # :743
         return g
+
+
+class HdivTensorPenaltyBC(HdivTensorNaturalBC):
+    """Penalised normal trace on the boundary facets: per H(div) field and row component ``J = beta int (psi.n)(psi.n)^T``,
+    ``r = -beta int g_c (psi.n)``, beta = 1e12 -- the reference's ``LCEDualWeakFormBCNeumann``
+    (R/src/weak_forms/lce_dual_weak_form.py:759-871).  Blocks between different fields / components are stored zeros."""
+
+    beta = 1.0e12
+
+    def launch_local(self, dev, data, alpha_dev, dest_dev, Ke, re):
+        Ke.zero_()
+        for d in data.parts:
+            _lib.call(
+                "nfa_local_hdiv_facet_penalty", d.dim, d.nfd, d.n_q, d.n_comp, _lib.ptr(d.trace_tab), _lib.ptr(d.tidx),
+                _lib.ptr(d.w), _lib.ptr(d.tcases), _lib.ptr(d.cases), _lib.ptr(dev.coords), _lib.ptr(d.facet_nodes),
+                _lib.ptr(d.neigh_nodes), _lib.ptr(d.normals), _lib.ptr(d.g), d.n_items, float(self.beta), int(d.off),
+                int(data.n_loc), _lib.ptr(Ke), _lib.ptr(re), _lib.stream_ptr(),
+            )
+
+
+class LEDualWeakFormBCNeumann(HdivTensorPenaltyBC):
+    """Stress penalty of the three-field form (the class the reference names ``LCEDualWeakFormBCNeumann`` inside
+    le_dual_weak_form.py:581-644: field ``s`` only), functions key ``s``."""
+
+    field_data = (("s", "s"),)
+
+
+class LCEDualWeakFormBCNeumann(HdivTensorPenaltyBC):
+    """Stress and couple-stress penalty, functions keys ``s`` and ``m`` (R/src/weak_forms/lce_dual_weak_form.py:759-871;
+    the copy in lce_scaled_dual_weak_form.py:814-917 is identical)."""
+
+    field_data = (("s", "s"), ("m", "m"))

@@ -184,6 +184,52 @@ def _trace_normal_load(space, field, iel, value_at, n_comp):
     return r
 
 
+def _trace_normal_penalty(space, field, iel, value_at, n_comp, beta=1.0e12):
+    """Penalty blocks of one field: ``J_cc = beta int (psi.n)(psi.n)^T``, ``r_c = -beta int g_c (psi.n)`` on the facet dofs
+    of the first neighbour (lce_dual_weak_form.py:835-869)."""
+    f_space, el, weights, x, det_jac, _ = _bc_setup(space, field, iel)
+    cell = el.cell
+    points, _ = space.bc_quadrature[cell.dimension]
+    neigh = RefElement(f_space, f_space.first_neighbour(cell.id))
+    mapped = transform_lower_to_higher(np.asarray(points).reshape(len(weights), -1), cell, neigh.cell)
+    _, jac0, det0, inv0 = neigh.evaluate_mapping(mapped)
+    tr_tab = neigh.evaluate_basis(mapped, jac0, det0, inv0)
+    facet_index = neigh.cell.sub_cells_ids[cell.dimension].tolist().index(cell.id)
+    dofs = ref_hdiv.entity_dofs(neigh.family, neigh.cell.dimension, neigh.k)[cell.dimension][facet_index]
+    n = normal(f_space.mesh, neigh.cell, cell)
+    dim = neigh.cell.dimension
+    n_phi = len(dofs)
+    n_dof = n_phi * n_comp
+    r, j = np.zeros(n_dof), np.zeros((n_dof, n_dof))
+    for c in range(n_comp):
+        res, block = np.zeros(n_phi), np.zeros((n_phi, n_phi))
+        for i, omega in enumerate(weights):
+            phi = tr_tab[0, i, dofs, 0:dim] @ n[0:dim]
+            res -= beta * det_jac[i] * omega * value_at(x[i], c) * phi
+            block += beta * det_jac[i] * omega * np.outer(phi, phi)
+        r[c : c + n_dof : n_comp] += res
+        j[c : c + n_dof : n_comp, c : c + n_dof : n_comp] += block
+    return r, j
+
+
+def le_dual_bc_neumann(space, functions, iel, alpha):
+    """le_dual_weak_form.py:581-644 (there named LCEDualWeakFormBCNeumann): stress field only."""
+    sc = space.discrete_spaces["s"].n_comp
+    return _trace_normal_penalty(space, "s", iel, lambda p, c: functions["s"](p[0], p[1], p[2])[c], sc)
+
+
+def lce_dual_bc_neumann(space, functions, iel, alpha):
+    """lce_dual_weak_form.py:759-871 (= lce_scaled_dual_weak_form.py:814-917)."""
+    sc, mc = space.discrete_spaces["s"].n_comp, space.discrete_spaces["m"].n_comp
+    r_s, j_s = _trace_normal_penalty(space, "s", iel, lambda p, c: functions["s"](p[0], p[1], p[2])[c], sc)
+    r_m, j_m = _trace_normal_penalty(space, "m", iel, lambda p, c: functions["m"](p[0], p[1], p[2])[c], mc)
+    n_s, n_m = len(r_s), len(r_m)
+    j = np.zeros((n_s + n_m, n_s + n_m))
+    j[:n_s, :n_s] = j_s
+    j[n_s:, n_s:] = j_m
+    return np.concatenate([r_s, r_m]), j
+
+
 def le_dual_bc_dirichlet(space, functions, iel, alpha):
     sc = space.discrete_spaces["s"].n_comp
     r = _trace_normal_load(space, "s", iel, lambda p, c: functions["u"](p[0], p[1], p[2])[c], sc)

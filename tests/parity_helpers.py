@@ -325,7 +325,8 @@ def degenerate_case(kind="degenerate", dim=3, k=1, n=2, with_bc=True, alpha=True
     )
 
 
-def tensor_mixed_case(kind="lce", dim=3, s_family="BDM", m_family="RT", k=1, n=2, with_bc=True, alpha=True, mesh=None):
+def tensor_mixed_case(kind="lce", dim=3, s_family="BDM", m_family="RT", k=1, n=2, with_bc=True, alpha=True, mesh=None,
+                      neumann=False):
     """Config 4 style: weakly symmetric mixed elasticity (kind="le": fields s, u, t) and mixed Cosserat elasticity
     (kind="lce" / "lce_scaled": fields s, m, u, t) on row-wise H(div) stresses with discontinuous P_{k-1} multipliers."""
     from nfempy_b200 import weak_forms as wf_mod
@@ -351,6 +352,11 @@ def tensor_mixed_case(kind="lce", dim=3, s_family="BDM", m_family="RT", k=1, n=2
         "u": lambda x, y, z: np.array([x + y, np.sin(x) - z, 0.5 * y * z][:dim]),
         "t": lambda x, y, z: np.array([y - x, 0.3 * z + 1.0, np.cos(x)][:tc]),
         "l": functions["l"], "grad_l": functions["grad_l"],
+    }
+    # prescribed normal stresses of the penalised ("Neumann") condition, one value per row of the tensor
+    neumann_functions = {
+        "s": lambda x, y, z: np.array([1.0 + x * y, np.cos(z) - y, 0.25 * x + z][:dim]),
+        "m": lambda x, y, z: np.array([0.5 - y, x * z + 0.1, np.sin(y)][:mc]),
     }
     if kind == "le":
         names, bfields = ("s", "u", "t"), ("s",)
@@ -388,13 +394,26 @@ def tensor_mixed_case(kind="lce", dim=3, s_family="BDM", m_family="RT", k=1, n=2
         if with_bc:
             bf = bc_cls(space)
             bf.functions = bc_functions
-            out["bc"] = ["bc_form", range(len(space.discrete_spaces["s"].bc_elements)), bf, a]
+            n_bc = len(space.discrete_spaces["s"].bc_elements)
+            if neumann:  # natural condition on the even boundary facets, penalised normal stresses on the odd ones
+                out["bc"] = ["bc_form", list(range(0, n_bc, 2)), bf, a]
+                nf = (wf_mod.LEDualWeakFormBCNeumann if kind == "le" else wf_mod.LCEDualWeakFormBCNeumann)(space)
+                nf.functions = neumann_functions
+                out["bc_n"] = ["bc_form", list(range(1, n_bc, 2)), nf, a]
+            else:
+                out["bc"] = ["bc_form", range(n_bc), bf, a]
         return out
 
     def ref_forms_fn(space):
         out = [("form", ref_vol, functions, len(space.discrete_spaces["s"].element_ids))]
         if with_bc:
-            out.append(("bc_form", ref_bc, bc_functions, len(space.discrete_spaces["s"].bc_element_ids)))
+            n_bc = len(space.discrete_spaces["s"].bc_element_ids)
+            if neumann:
+                out.append(("bc_form", ref_bc, bc_functions, list(range(0, n_bc, 2))))
+                ref_n = rt.le_dual_bc_neumann if kind == "le" else rt.lce_dual_bc_neumann
+                out.append(("bc_form", ref_n, neumann_functions, list(range(1, n_bc, 2))))
+            else:
+                out.append(("bc_form", ref_bc, bc_functions, n_bc))
         return out
 
     alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None

@@ -95,3 +95,12 @@ def test_quadrature_chunking_is_transparent(chunk, monkeypatch):
     ref = case.run_oracle()
     monkeypatch.setenv("NFA_TENSOR_QCHUNK", str(chunk))
     compare_csr(case.run_gpu(), ref, RTOL)
+
+
+@pytest.mark.parametrize("kind,dim,s_family,k", [("le", 3, "BDM", 1), ("lce", 3, "BDM", 1), ("lce_scaled", 2, "RT", 2),
+                                                  ("lce", 3, "RT", 2), ("le", 2, "BDM", 2)])
+def test_penalised_normal_stress_boundary_forms(kind, dim, s_family, k):
+    """LCEDualWeakFormBCNeumann (all three copies of the reference): beta = 1e12 penalty on the normal trace of the
+    stress (and couple stress) on half of the boundary facets, the natural condition on the other half."""
+    case = tensor_mixed_case(kind=kind, dim=dim, s_family=s_family, m_family="RT", k=k, n=1 if dim == 3 else 2, neumann=True)
+    compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
