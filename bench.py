@@ -271,6 +271,13 @@ def run_graft(args):
     # per-launch host work (Python + ctypes, ~1.3 ms per step, about what the device needs) cannot gate the device
     launches_per_step = None
     graph = None
+    local_launches = 0
+    if sharded is not None and not args.no_graph:
+        # N > 1: the local kernels are replayed from a CUDA graph, the exchange (pack, NCCL send/recv, unpack) stays eager
+        l0 = _lib.launch_count()
+        sharded.local_assemble()
+        local_launches = _lib.launch_count() - l0 + 1  # + the rhs fill
+        sharded.capture_local()
     if sharded is None and not args.no_graph:
         l0 = _lib.launch_count()
         step()
@@ -298,6 +305,8 @@ def run_graft(args):
         launches = launches_per_step * args.steps  # replayed kernel nodes: counted on the eager step that was captured
     else:
         launches = _lib.launch_count() - launches0 + args.steps  # + rhs_dev.zero_() per step (torch fill kernel)
+        if sharded is not None and not args.no_graph:  # the replayed local kernels + the eager exchange kernels counted above
+            launches = _lib.launch_count() - launches0 + local_launches * args.steps
     # load probe for the clock record: the same step loop for ~0.6 s (not part of any reported time)
     p0 = time.time()
     while time.time() - p0 < 0.6:
@@ -361,7 +370,9 @@ def run_graft(args):
                 "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % ((b_step * n_cells + 6 * 100 * n_cells) / 1e9),
                 "plan_build_s": plan.build_seconds, "host_mesh_space_s": t_host, "prepare_s": t_prepare,
                 "path": ("fused (row items)" if row_items else "fused") if plan.fused_index is not None else "two-stage",
-                "launch": "CUDA graph replay of the captured step" if graph is not None else "eager launches",
+                "launch": ("CUDA graph replay of the captured step" if graph is not None else
+                           ("CUDA graph replay of the local assembly + eager NCCL exchange" if (sharded is not None and not args.no_graph)
+                            else "eager launches")),
             },
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

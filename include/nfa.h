@@ -276,6 +276,10 @@ int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *d_chu
                            const uint32_t *d_ell, int max_tile_blocks, const int32_t *d_chunk_cells_ptr,
                            int64_t n_chunk_cells, const int32_t *d_chunk_cells, nfa_stream stream);
 int nfa_bplan_has_p2_items(const nfa_bplan *bp);
+/* Optional cell mask of the row-item kernel (uint8 per cell of the plan, device pointer; NULL clears it): cells with
+ * mask 0 contribute exact zeros.  The sharded assembler switches off the halo cells of a rank's local plan this way,
+ * so that mesh-constant lambda, mu stay single numbers (stride 0) on every rank. */
+int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *d_mask, nfa_stream stream);
 /* Optional lists of the shared-memory staged variant of the same kernel (chunk-relative task headers, ELL entries
  * naming cells by their slot in the chunk's cell list, per-chunk copy extents [ell0, n_ell, item0, n_items] and the
  * per-chunk maxima that size the buffers).  With them nfa_assemble_p2tet_elasticity stages every chunk's inputs in

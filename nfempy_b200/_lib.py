@@ -71,6 +71,7 @@ SIGNATURES = {
     "nfa_bplan_n_blocks": (_i64, [_vp]),
     "nfa_bplan_set_p2_items": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _vp, _i64, _vp, _vp]),
     "nfa_bplan_has_p2_items": (_i, [_vp]),
+    "nfa_bplan_set_cell_mask": (_i, [_vp, _vp, _vp]),
     "nfa_bplan_set_p2_stage": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nfa_assemble_p2tet_elasticity": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
 }

@@ -125,6 +125,8 @@ class ShardedAssembler:
         self.asm.form_to_input_list = {"volume": ["form", self.shard.local_cells, form, None]}
         self.state = None
         self._bufs = {}
+        self._graph = None
+        self.rhs = None
         self._torch = torch
 
     def prepare(self):
@@ -134,13 +136,23 @@ class ShardedAssembler:
             raise NotImplementedError("ShardedAssembler needs the fused path (affine H1 form, cell-wise coefficients)")
         data = datas[0]
         own = torch.as_tensor(self.shard.is_own.astype(np.float64)).to(dev.device)
-        coefs = {}
-        for name, (arr, sc, sq, kind) in data.coefs.items():
-            if kind == "constant":
-                coefs[name] = ((arr * own).contiguous(), 1, 0, "cell")  # halo cells contribute exact zeros
-            else:
-                coefs[name] = ((arr * own).contiguous(), sc, sq, kind)
-        data.coefs = coefs
+        from .. import _lib
+
+        lib = _lib.load()
+        row_items = bool(data.get("p2tet_ok")) and bool(lib.nfa_bplan_has_p2_items(plan.bplan))
+        if row_items and all(kind == "constant" for (_, _, _, kind) in data.coefs.values()):
+            # row-item kernel with mesh-constant coefficients: the halo cells are switched off by the plan's cell mask and
+            # lambda, mu stay single numbers, so every rank runs the constant-rho instantiation like a single GPU does
+            self._mask = torch.as_tensor(self.shard.is_own.astype(np.uint8)).to(dev.device)
+            _lib.check(lib.nfa_bplan_set_cell_mask(plan.bplan, _lib.ptr(self._mask), _lib.stream_ptr()), "nfa_bplan_set_cell_mask")
+        else:
+            coefs = {}
+            for name, (arr, sc, sq, kind) in data.coefs.items():
+                if kind == "constant":
+                    coefs[name] = ((arr * own).contiguous(), 1, 0, "cell")  # halo cells contribute exact zeros
+                else:
+                    coefs[name] = ((arr * own).contiguous(), sc, sq, kind)
+            data.coefs = coefs
         if data.f is not None:
             data.f = (data.f * own[:, None, None]).contiguous()
         self.state = (dev, entries, datas, dests, plan, key)
@@ -160,11 +172,28 @@ class ShardedAssembler:
         """Fused assembly of the rank's own cells (halo cells contribute exact zeros)."""
         torch = self._torch
         dev, entries, datas, dests, plan, key = self.state
-        self.asm.jacobian.is_zero = True
-        self.rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
-        self.asm.run(self.state, self.rhs)
+        if getattr(self, "rhs", None) is None:
+            self.rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
+        if self._graph is not None:
+            self._graph.replay()  # zeroes rhs, overwrites every CSR value (GPUAssembler.capture)
+        else:
+            self.asm.jacobian.is_zero = True
+            self.rhs.zero_()
+            self.asm.run(self.state, self.rhs)
         self.vals = self.asm.jacobian.values_dev
         return self.vals, self.rhs
+
+    def capture_local(self):
+        """Captures the local assembly (the kernels between two interface exchanges) in a CUDA graph: the per-launch host
+        work of the eager path (Python + ctypes, about as long as the device needs) then no longer gates the device.
+        The exchange itself (pack kernels, NCCL send/recv, unpack kernels) stays eager."""
+        torch = self._torch
+        dev, entries, datas, dests, plan, key = self.state
+        if getattr(self, "rhs", None) is None:
+            self.rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
+        self._graph = self.asm.capture(self.state, self.rhs)
+        self.vals = self.asm.jacobian.values_dev
+        return self
 
     def _buffer(self, tag):
         if tag not in self._bufs:

@@ -54,7 +54,8 @@ __device__ __forceinline__ G4 ldg256(const double *p) {
 // geometry records [n_cells][4][4]: (sqrt(det mu) g_m, lambda / mu), m = 0..3
 __global__ void p2tet_geo_kernel(const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
                                  int64_t n_cells, const double *__restrict__ lam, int64_t ls,
-                                 const double *__restrict__ mu, int64_t ms, double *__restrict__ rec) {
+                                 const double *__restrict__ mu, int64_t ms, const uint8_t *__restrict__ mask,
+                                 double *__restrict__ rec) {
     int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n_cells) return;
     double X[4][3];
@@ -63,7 +64,10 @@ __global__ void p2tet_geo_kernel(const double *__restrict__ coords, const int32_
     compute_geom<3>(X, g);
     // mu > 0 is the caller's contract; cells with lambda = mu = 0 (the halo cells of a rank's local plan, whose
     // coefficients the sharded assembler zeroes) contribute exact zeros
-    const double m = mu[cell * ms], l = lam[cell * ls];
+    // cells switched off by the plan's mask (the halo cells of a rank's local plan when lambda, mu are constants: the
+    // coefficients then stay single numbers and the constant-rho instantiation runs) contribute exact zeros as well
+    const bool off = mask && !mask[cell];
+    const double m = off ? 0.0 : mu[cell * ms], l = lam[cell * ls];
     const double sc = m > 0.0 ? sqrt(g.det * m) : 0.0, rho = m > 0.0 ? l / m : 0.0;
     double *r = rec + cell * 16;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -831,6 +835,20 @@ extern "C" int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int
 
 extern "C" int nfa_bplan_has_p2_items(const nfa_bplan *bp) { return bp && bp->p2.n_chunks > 0 ? 1 : 0; }
 
+extern "C" int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *mask, nfa_stream stream) {
+    if (!bp) return fail("nfa_bplan_set_cell_mask: plan is NULL");
+    nfa_bplan::P2Items &it = bp->p2;
+    if (!mask) {
+        it.cell_mask.release();
+        return 0;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (it.cell_mask.alloc(bp->n_cells)) return 2;
+    NFA_CUDA(cudaMemcpyAsync(it.cell_mask.p, mask, bp->n_cells, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 extern "C" int nfa_bplan_set_p2_stage(nfa_bplan *bp, const int32_t *chunk_ext, const int32_t *task_hdr_rel,
                                       const uint32_t *ell_local, int max_chunk_cells, int max_chunk_ell,
                                       int max_chunk_items, int max_chunk_tasks, nfa_stream stream) {
@@ -915,7 +933,7 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     if (it.n_chunks <= 0) return fail("nfa_assemble_p2tet_elasticity: the plan carries no row items");
     cudaStream_t s = (cudaStream_t)stream;
     p2tet_geo_kernel<<<grid_for(bp->n_cells, 128), 128, 0, s>>>(coords, cell_nodes, bp->n_cells, lam, ls, mu, ms,
-                                                                (double *)it.rec.p);
+                                                                (const uint8_t *)it.cell_mask.p, (double *)it.rec.p);
     NFA_LAUNCH_CHECK();
     {
         bool launched = false;

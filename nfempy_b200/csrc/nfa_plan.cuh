@@ -80,6 +80,7 @@ struct nfa_bplan {
         nfa::DevBuf cells_ptr;  // int32 [n_chunks + 1], cells: int32: cells each chunk reads (L1 prefetch lists)
         nfa::DevBuf cells;
         nfa::DevBuf rec;        // scratch: geometry records [n_cells][4][4], rewritten every assembly
+        nfa::DevBuf cell_mask;  // optional uint8 [n_cells]: 0 = the cell contributes zeros (halo cell of a sharded plan)
         // staged variant (everything a chunk reads is bulk-copied to shared memory): chunk-relative lists
         int max_chunk_cells = 0, max_chunk_ell = 0, max_chunk_items = 0, max_chunk_tasks = 0;
         nfa::DevBuf chunk_ext;     // int32 [n_chunks][4]: ell0, n_ell, item0 (even), n_items copied (even)
