@@ -66,9 +66,10 @@ __global__ void p2tet_geo_kernel(const double *__restrict__ coords, const int32_
     // coefficients the sharded assembler zeroes) contribute exact zeros
     // cells switched off by the plan's mask (the halo cells of a rank's local plan when lambda, mu are constants: the
     // coefficients then stay single numbers and the constant-rho instantiation runs) contribute exact zeros as well
+    // (zero gradient vectors; rho keeps its value, which the constant-rho instantiation reads from any record)
     const bool off = mask && !mask[cell];
-    const double m = off ? 0.0 : mu[cell * ms], l = lam[cell * ls];
-    const double sc = m > 0.0 ? sqrt(g.det * m) : 0.0, rho = m > 0.0 ? l / m : 0.0;
+    const double m = mu[cell * ms], l = lam[cell * ls];
+    const double sc = (m > 0.0 && !off) ? sqrt(g.det * m) : 0.0, rho = m > 0.0 ? l / m : 0.0;
     double *r = rec + cell * 16;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll

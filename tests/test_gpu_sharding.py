@@ -15,8 +15,12 @@ def _f(x, y, z):
     return np.array([np.sin(x + y), z * x, np.cos(y) + 1.0])
 
 
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("varying", [False, True])
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_assembly_matches_single_gpu(world):
+def test_sharded_assembly_matches_single_gpu(world, varying, graph):
+    """``varying``: cell-wise lambda (halo cells get zero coefficients) instead of mesh constants (halo cells switched off
+    by the plan's cell mask, constant-rho kernel); ``graph``: local assembly replayed from a CUDA graph."""
     from nfempy_b200.assembly import GPUAssembler
     from nfempy_b200.assembly.sharding import ShardedAssembler
     from nfempy_b200.weak_forms import LEPrimalWeakForm
@@ -24,15 +28,24 @@ def test_sharded_assembly_matches_single_gpu(world):
     mesh = box_tet_mesh(3, nx=6, jitter=0.2)
     space = ProductSpace({"u": (3, 3, "Lagrange", 2, mesh)})
     space.build_structures({"u": [1]}, {})
-    form = LEPrimalWeakForm(space)
-    form.functions = {"rhs": _f, "lambda": lambda x, y, z: 2.0 * np.ones_like(x), "mu": lambda x, y, z: np.ones_like(x)}
     n_cells = len(space.discrete_spaces["u"].elements)
+    lam_cell = 2.0 + np.random.default_rng(7).random(n_cells)
+
+    class CellwiseForm(LEPrimalWeakForm):  # lambda given per cell (no load): the general-rho instantiation
+        def prepare(self, dev, items=None, arrays=None):
+            sel = lam_cell if items is None else lam_cell[np.asarray(items)]
+            return super().prepare(dev, items, arrays={"lambda": sel, "mu": np.array([1.0]), "rhs": None})
+
+    form = (CellwiseForm if varying else LEPrimalWeakForm)(space)
+    form.functions = {"rhs": _f, "lambda": lambda x, y, z: 2.0 * np.ones_like(x), "mu": lambda x, y, z: np.ones_like(x)}
     ref = GPUAssembler(space, None, np.zeros(space.n_dof))
     ref.form_to_input_list = {"volume": ["form", range(n_cells), form, None]}
     g_indptr, g_indices, g_vals, g_rhs = ref.assemble()
 
     ranks = [ShardedAssembler(space, form, world, r).prepare() for r in range(world)]
     for sa in ranks:
+        if graph:
+            sa.capture_local()
         sa.local_assemble()
     sent = {(r, q): sa.pack(q).clone() for r, sa in enumerate(ranks) for q in sa.shard.send_rows}
     for q, sa in enumerate(ranks):
