@@ -425,12 +425,16 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
 // Warps of a CTA pull tasks from the CTA's contiguous chunk range through one shared counter; chunk c lives in tile
 // (c - c_begin) % NBUF.  The warp that finishes the last task of a chunk sends the tile to HBM with one bulk copy,
 // waits until the copy engine has read it and hands the tile to chunk c + NBUF.  No CTA-wide barrier in the loop.
-template <bool CR, int THREADS>
+template <bool CR, int THREADS, int NB>
 __global__ void __launch_bounds__(THREADS, 1)
-    p2tet_elasticity_kernel(int NBUF, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
+    p2tet_elasticity_kernel(int nbuf_rt, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
                             const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
                             const double *__restrict__ rec, int tile_stride, const int32_t *__restrict__ cells_ptr,
                             const int32_t *__restrict__ cells, double *__restrict__ vals) {
+    // NB > 0: the number of tiles is a compile-time power of two, so that the tile of a chunk ((c - c_begin) % NBUF) and its
+    // round ((c - c_begin) / NBUF) cost a mask and a shift instead of two integer divisions per task (the task loop's scalar
+    // bookkeeping is 40 % of the instructions the kernel executes)
+    const int NBUF = NB > 0 ? NB : nbuf_rt;
     extern __shared__ __align__(128) double smem[];  // NBUF tiles of tile_stride doubles, then the control words
     // ctrl: [0] next task, [1] c_begin, [2] c_end, [3] task_end, [4 .. 4+NBUF) tasks left per tile, then free_at per tile.
     // Everything the tail of an iteration needs is re-read from here / from the (L1-resident) headers instead of being
@@ -455,11 +459,13 @@ __global__ void __launch_bounds__(THREADS, 1)
     // software pipeline over tasks, per warp: while task i is computed, the header of task i+2 and the first two ELL
     // entries of task i+1 are in flight, and the records task i+1 reads first are prefetched into L1
     const int lane = threadIdx.x & 31;
-    const int task_end = ctrl[3];
+    const int task_end = ctrl[3], c_begin_r = ctrl[1];
     const int4 none = make_int4(0, 0, 0, -1);
+    const uint32_t ctrl_s = (uint32_t)__cvta_generic_to_shared(const_cast<int *>(ctrl));
     auto grab = [&]() {
         int t = 0;
-        if (lane == 0) t = atomicAdd(const_cast<int *>(ctrl), 1);
+        if (lane == 0)  // plain shared-memory atomic (the compiler wraps atomicAdd in its warp-aggregation sequence)
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(ctrl_s) : "memory");
         return __shfl_sync(0xffffffffu, t, 0);
     };
     int4 th = none, th1 = none;
@@ -492,7 +498,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             const uint32_t *e = ell + (uint32_t)th.y + lane;
             uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
             if (lane < n_items) ih = __ldg(item_hdr + th.z + lane);
-            const int it = c - ctrl[1], b = it % NBUF;
+            const int it = c - c_begin_r, b = it % NBUF;
             // the tile sits on the same 16-byte phase as its image in vals (parity of the chunk's first block)
             double *tile = smem + (size_t)b * tile_stride + ((th.x >> 16) & 1);
             const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y};
@@ -508,10 +514,12 @@ __global__ void __launch_bounds__(THREADS, 1)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if ((threadIdx.x & 31) == 0) {
-            const int c = (int)((unsigned)th.w >> 6), c_begin = ctrl[1], c_end = ctrl[2];
-            const int it = c - c_begin, b = it % NBUF;
+            const int c = (int)((unsigned)th.w >> 6);
+            const int it = c - c_begin_r, b = it % NBUF;
             __threadfence_block();
-            if (atomicSub(const_cast<int *>(ctrl) + 4 + b, 1) == 1) {  // the chunk's last task: the tile is complete
+            int left;
+            asm volatile("atom.shared.add.u32 %0, [%1], -1;" : "=r"(left) : "r"(ctrl_s + 4u * (4u + (unsigned)b)) : "memory");
+            if (left == 1) {  // the chunk's last task: the tile is complete
                 __threadfence_block();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 const int4 ch = __ldg(chunk_hdr + c);
@@ -529,7 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                 if (head) dst[0] = tile[0];
                 if (head + n_bulk < n_vals) dst[n_vals - 1] = tile[n_vals - 1];
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                ctrl[4 + b] = (c + NBUF < c_end) ? __ldg(chunk_hdr + c + NBUF).w : 0;
+                ctrl[4 + b] = (c + NBUF < ctrl[2]) ? __ldg(chunk_hdr + c + NBUF).w : 0;
                 __threadfence_block();
                 ctrl[4 + NBUF + b] = it / NBUF + 1;
             }
@@ -956,8 +964,10 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     using kern_t = void (*)(int, int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
                             const int32_t *, const int32_t *, double *);
     kern_t kern = nullptr;
-#define NFA_P2_PICK(CRV, TH) \
-    if (cr == CRV && threads == TH) kern = p2tet_elasticity_kernel<CRV, TH>;
+    const bool nb4 = nbuf == 4 && !getenv("NFA_P2TET_RT_NBUF");
+#define NFA_P2_PICK(CRV, TH)                                                      \
+    if (cr == CRV && threads == TH)                                               \
+        kern = nb4 ? p2tet_elasticity_kernel<CRV, TH, 4> : p2tet_elasticity_kernel<CRV, TH, 0>;
     NFA_P2_PICK(false, 384) NFA_P2_PICK(false, 448) NFA_P2_PICK(false, 512)
     NFA_P2_PICK(true, 384) NFA_P2_PICK(true, 448) NFA_P2_PICK(true, 512)
 #undef NFA_P2_PICK
