@@ -209,8 +209,9 @@ class GPUAssembler:
         bcols = torch.empty(n_blocks, dtype=torch.int32, device=dev.device)
         _lib.check(lib.nfa_bplan_block_pattern(p.bplan, _lib.ptr(bptr), _lib.ptr(bcols), stream), "nfa_bplan_block_pattern")
         cap = int(os.environ.get("NFA_P2TET_CAP", "640"))
+        staged = os.environ.get("NFA_P2TET_STAGE", "0") not in ("", "0")  # the opt-in staged kernel needs extra lists
         items = p2_items.build(node_dest.to(torch.int64), bptr.to(torch.int64), bcols.to(torch.int64), n_nodes, cap=cap,
-                               lane_order=os.environ.get("NFA_P2TET_LANES", "cell"))
+                               lane_order=os.environ.get("NFA_P2TET_LANES", "cell"), staged=staged)
         _lib.check(
             lib.nfa_bplan_set_p2_items(
                 p.bplan, items["n_chunks"], _lib.ptr(items["chunk_hdr"]), items["n_tasks"], _lib.ptr(items["task_hdr"]),
@@ -220,13 +221,15 @@ class GPUAssembler:
             ),
             "nfa_bplan_set_p2_items",
         )
-        _lib.check(
-            lib.nfa_bplan_set_p2_stage(
-                p.bplan, _lib.ptr(items["chunk_ext"]), _lib.ptr(items["task_hdr_rel"]), _lib.ptr(items["ell_local"]),
-                items["max_chunk_cells"], items["max_chunk_ell"], items["max_chunk_items"], items["max_chunk_tasks"], stream,
-            ),
-            "nfa_bplan_set_p2_stage",
-        )
+        if staged:
+            _lib.check(
+                lib.nfa_bplan_set_p2_stage(
+                    p.bplan, _lib.ptr(items["chunk_ext"]), _lib.ptr(items["task_hdr_rel"]), _lib.ptr(items["ell_local"]),
+                    items["max_chunk_cells"], items["max_chunk_ell"], items["max_chunk_items"], items["max_chunk_tasks"],
+                    stream,
+                ),
+                "nfa_bplan_set_p2_stage",
+            )
         p.p2_stats = {k: v for k, v in items.items() if isinstance(v, int)}
 
     # ------------------------------------------------------------------------------------------

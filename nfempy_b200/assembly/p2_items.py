@@ -79,7 +79,7 @@ def _templates():
 TEMPLATES = _templates()  # 4 * 7 + 6 * 4 = 52 entries per cell
 
 
-def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8, lane_order="cell"):
+def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8, lane_order="cell", staged=True):
     """``node_dest`` int64 [n_cells, 10] global node of each local P2 node, ``bptr``/``bcols`` the block CSR of the
     matrix (int64 tensors on the same device).  Returns a dict of tensors (see module docstring) and sizes."""
     dev = node_dest.device
@@ -241,6 +241,18 @@ def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8, lane_or
     chunk_cells_ptr = torch.zeros(n_chunks + 1, dtype=torch.int64, device=dev)
     chunk_cells_ptr[1:] = torch.cumsum(torch.bincount(cell_chunk, minlength=n_chunks), 0)
     max_tile = int((c_b1 - c_b0).max().item())
+    base = {
+        "chunk_hdr": chunk_hdr.to(torch.int32).contiguous(),
+        "task_hdr": task_hdr.to(torch.int32).contiguous(),
+        "item_hdr": item_hdr.to(torch.int32).to(torch.uint16 if hasattr(torch, "uint16") else torch.int16).contiguous(),
+        "chunk_cells_ptr": chunk_cells_ptr.to(torch.int32).contiguous(),
+        "chunk_cells": chunk_cells.to(torch.int32).contiguous(), "n_chunk_cells": int(chunk_cells.shape[0]),
+        "ell": (ell & NONE32).to(torch.uint32 if hasattr(torch, "uint32") else torch.int64).contiguous(),
+        "n_chunks": n_chunks, "n_tasks": n_tasks, "n_items": n_items, "ell_size": ell_size, "max_tile_blocks": max_tile,
+        "n_entries": int(key.shape[0]),
+    }
+    if not staged:  # the lists of the (opt-in) staged kernel cost 0.45 GB at 1 M tets: only built on request
+        return base
     # ---- staged variant: everything a chunk reads is copied to shared memory by bulk copies before its tasks run, so
     # the ELL entries name the cell by its SLOT in the chunk's cell list and the task headers hold chunk-relative offsets
     slot = torch.searchsorted(cc, (entry_chunk << 26) | (code >> 6)) - chunk_cells_ptr[entry_chunk]
@@ -264,14 +276,7 @@ def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8, lane_or
         "task_hdr_rel": task_hdr_rel.to(torch.int32).contiguous(),
         "max_chunk_cells": int(n_cc.max().item()), "max_chunk_ell": int(c_nell.max().item()),
         "max_chunk_items": int(item_copy.max().item()), "max_chunk_tasks": int(ntask.max().item()),
-        "chunk_hdr": chunk_hdr.to(torch.int32).contiguous(),
-        "task_hdr": task_hdr.to(torch.int32).contiguous(),
-        "item_hdr": item_hdr.to(torch.int32).to(torch.uint16 if hasattr(torch, "uint16") else torch.int16).contiguous(),
-        "chunk_cells_ptr": chunk_cells_ptr.to(torch.int32).contiguous(),
-        "chunk_cells": chunk_cells.to(torch.int32).contiguous(), "n_chunk_cells": int(chunk_cells.shape[0]),
-        "ell": (ell & NONE32).to(torch.uint32 if hasattr(torch, "uint32") else torch.int64).contiguous(),
-        "n_chunks": n_chunks, "n_tasks": n_tasks, "n_items": n_items, "ell_size": ell_size, "max_tile_blocks": max_tile,
-        "n_entries": int(key.shape[0]),
+        **base,
     }
 
 

@@ -208,7 +208,12 @@ __device__ __forceinline__ void stage_hdiv_basis(bool live, int r, int n_u, int 
     group_sync<G>();
 }
 
-template <int DIM, int G, int T>
+// MMA (G >= 32): the symmetric flux mass block M = Psi^T diag(w det / kappa) Psi, Psi [(n_q DIM) x n_u], is a small dense
+// SYRK; a warp computes 8 x 8 tiles of it on the FP64 tensor cores (mma.sync m8n8k4, DMMA): per step of four (point,
+// component) rows a lane loads one element of each operand from the staged basis -- 3 LDS + 1 DMUL + 1 DMMA for 256
+// multiply-adds instead of 6 LDS + 9 DFMA for 9 per lane.  n_up is then padded to a multiple of 8 and the staged rows to a
+// multiple of 4 (zero rows).
+template <int DIM, int G, int T, bool MMA>
 __global__ void __launch_bounds__(128)
     hdiv_l2_tiled_kernel(int n_u, int n_p, int n_q, int nfd, const double *__restrict__ u_val,
                          const double *__restrict__ u_div, const double *__restrict__ p_val,
@@ -220,15 +225,21 @@ __global__ void __launch_bounds__(128)
     constexpr int NF = DIM + 1;
     constexpr int GROUPS = 128 / G;
     extern __shared__ double smem[];
-    const int nt = (n_u + T - 1) / T, n_up = nt * T;
+    const int nt = (n_u + T - 1) / T;
+    const int n_up = MMA ? ((n_u + 2 + 7) & ~7) : nt * T;
+    const int n_rows = MMA ? ((n_q * DIM + 3) & ~3) : n_q * DIM;  // staged (point, component) rows of psi
     const int n_loc = n_u + n_p, n_fdofs = NF * nfd;
-    const int group_doubles = n_q * DIM * n_up + n_q * n_up + 2 * n_q + NF * nfd * nfd;
+    const int group_doubles = n_rows * n_up + n_q * n_up + 2 * (n_q + 2) + NF * nfd * nfd;
     const int g = threadIdx.x / G, r = threadIdx.x - g * G;
-    double *s_psi = smem + (size_t)g * group_doubles;  // [n_q][DIM][n_up]
-    double *s_div = s_psi + n_q * DIM * n_up;           // [n_q][n_up]
-    double *s_wk = s_div + n_q * n_up;                  // [n_q] w det / kappa
-    double *s_wd = s_wk + n_q;                          // [n_q] w det
-    double *s_T = s_wd + n_q;                           // [NF][nfd][nfd]
+    double *s_psi = smem + (size_t)g * group_doubles;  // [n_q][DIM][n_up] (+ zero rows up to n_rows)
+    double *s_div = s_psi + n_rows * n_up;              // [n_q][n_up]
+    double *s_wk = s_div + n_q * n_up;                  // [n_q + 2] w det / kappa (zero beyond n_q)
+    double *s_wd = s_wk + n_q + 2;                      // [n_q + 2] w det
+    double *s_T = s_wd + n_q + 2;                       // [NF][nfd][nfd]
+    if (MMA) {  // the padding rows are never written again
+        for (int i = r; i < (n_rows - n_q * DIM) * n_up; i += G) s_psi[n_q * DIM * n_up + i] = 0.0;
+        if (r < 2) s_wk[n_q + r] = 0.0;
+    }
     const int n_mass = nt * (nt + 1) / 2, n_cpl = nt * n_p, n_zero = n_p * n_p;
     const int n_work = n_mass + n_cpl + n_zero + n_loc;
     const int64_t n_trips = (n_cells + (int64_t)gridDim.x * GROUPS - 1) / ((int64_t)gridDim.x * GROUPS);
@@ -278,9 +289,67 @@ __global__ void __launch_bounds__(128)
                 }
             }
         }
+        if constexpr (MMA) {
+            constexpr int WARPS = G / 32;
+            const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3, wig = (threadIdx.x >> 5) % WARPS;
+            const int nt8 = (n_u + 7) / 8, n_tiles8 = nt8 * (nt8 + 1) / 2, k_steps = n_rows / 4;
+            if (live) {
+                double *K = Ke + cell * (int64_t)n_loc * n_loc;
+                // up to four tiles per trip: their accumulation chains are independent, which hides the latency of the
+                // dependent DMMA sequence of a single tile
+                constexpr int NT = 4;
+                for (int w0 = wig * NT; w0 < n_tiles8; w0 += WARPS * NT) {
+                    int ti[NT], tj[NT];
+                    const double *pa[NT], *pb[NT];
+                    double c0[NT], c1[NT];
+#pragma unroll
+                    for (int u = 0; u < NT; ++u) {
+                        int t = 0, rem = min(w0 + u, n_tiles8 - 1);  // a surplus slot repeats the last tile (not stored)
+                        while (rem >= nt8 - t) {
+                            rem -= nt8 - t;
+                            ++t;
+                        }
+                        ti[u] = t;
+                        tj[u] = t + rem;
+                        pa[u] = s_psi + tig * n_up + 8 * ti[u] + gid;
+                        pb[u] = s_psi + tig * n_up + 8 * tj[u] + gid;
+                        c0[u] = c1[u] = 0.0;
+                    }
+#pragma unroll 2
+                    for (int st = 0; st < k_steps; ++st) {
+                        const double wq = s_wk[(4 * st + tig) / DIM];
+                        const size_t off = (size_t)4 * st * n_up;
+#pragma unroll
+                        for (int u = 0; u < NT; ++u) {
+                            const double a = pa[u][off] * wq;  // row k of diag(w) Psi, column 8 ti + gid
+                            const double b = pb[u][off];       // row k of Psi, column 8 tj + gid
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                         : "+d"(c0[u]), "+d"(c1[u])
+                                         : "d"(a), "d"(b));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < NT; ++u) {
+                        if (w0 + u >= n_tiles8) continue;
+                        // accumulator layout: (row gid, columns 2 tig and 2 tig + 1) of the 8 x 8 tile
+                        const int ra = 8 * ti[u] + gid, rb = 8 * tj[u] + 2 * tig;
+                        if (ra < n_u) {
+                            if (rb < n_u) {
+                                K[ra * n_loc + rb] = c0[u];
+                                if (ti[u] != tj[u]) K[rb * n_loc + ra] = c0[u];
+                            }
+                            if (rb + 1 < n_u) {
+                                K[ra * n_loc + rb + 1] = c1[u];
+                                if (ti[u] != tj[u]) K[(rb + 1) * n_loc + ra] = c1[u];
+                            }
+                        }
+                    }
+                }
+            }
+        }
         // few mass tiles (at most G / 2): lanes r and r + G / 2 share a tile, each sums one half of the quadrature points
         // and the halves are combined with a shuffle, so that all lanes of the group work in the dominant phase
-        const bool split = G <= 32 && n_mass <= G / 2;
+        const bool split = !MMA && G <= 32 && n_mass <= G / 2;
         if (G <= 32 && split) {
             constexpr int H = G / 2;
             const int half = r / H, w = r - half * H;
@@ -348,7 +417,7 @@ __global__ void __launch_bounds__(128)
         }
         if (live) {
             double *K = Ke + cell * (int64_t)n_loc * n_loc;
-            for (int w = (split ? n_mass : 0) + r; w < n_work; w += G) {
+            for (int w = ((split || MMA) ? n_mass : 0) + r; w < n_work; w += G) {
                 if (w < n_mass) {
                     // tile (ti, tj), ti <= tj, from the linear index over the upper triangle
                     int ti = 0, rem = w;
@@ -1126,10 +1195,18 @@ extern "C" int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, co
     if ((!e_tiled || atoi(e_tiled) != 0) && nfd <= HT_MAXFD) {
         // register-tiled kernel: lanes per cell from the number of heavy work items (mass tiles + coupling columns)
         constexpr int T = 3;
-        const int nt = (n_u + T - 1) / T, n_up = nt * T, heavy = nt * (nt + 1) / 2 + nt * n_p;
+        const int nt = (n_u + T - 1) / T, heavy = nt * (nt + 1) / 2 + nt * n_p;
         int G = heavy <= 8 ? 8 : (heavy <= 16 ? 16 : (heavy <= 48 ? 32 : 128));
         if (const char *e = getenv("NFA_HDIV_LANES")) G = atoi(e);
-        const size_t group_doubles = (size_t)n_q * dim * n_up + (size_t)n_q * n_up + 2 * n_q + (size_t)(dim + 1) * nfd * nfd;
+        // FP64 tensor cores (DMMA) for the mass block when whole warps share a cell (RT_2 and up, BDM_2 and up): opt-in
+        // (NFA_HDIV_MMA=1).  Measured on B200 it is SLOWER than the register-tiled DFMA tiles: RT_2 36.6 vs 24.5 ms,
+        // RT_3 38.8 vs 33.2 ms, and the same with four independent accumulation chains per warp (37.3 / 38.6 ms): the
+        // DMMA rate itself is the limit, not the latency of the dependent sequence.
+        const char *e_mma = getenv("NFA_HDIV_MMA");
+        const bool mma = G >= 32 && e_mma && atoi(e_mma) != 0;
+        const int n_up = mma ? ((n_u + 2 + 7) & ~7) : nt * T;
+        const int n_rows = mma ? ((n_q * dim + 3) & ~3) : n_q * dim;
+        const size_t group_doubles = (size_t)n_rows * n_up + (size_t)n_q * n_up + 2 * (n_q + 2) + (size_t)(dim + 1) * nfd * nfd;
         const size_t tsmem = sizeof(double) * group_doubles * (128 / G);
         if (tsmem <= 200 * 1024 && (G == 8 || G == 16 || G == 32 || G == 128)) {
             int device = 0, n_sm = 148, per_sm = 1;
@@ -1137,7 +1214,7 @@ extern "C" int nfa_local_hdiv_l2(int dim, int n_u, int n_p, int n_q, int nfd, co
             NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
 #define NFA_HT_LAUNCH(D, GG)                                                                                         \
     {                                                                                                                \
-        auto kern = hdiv_l2_tiled_kernel<D, GG, T>;                                                                  \
+        auto kern = (mma && GG >= 32) ? hdiv_l2_tiled_kernel<D, GG, T, (GG >= 32)> : hdiv_l2_tiled_kernel<D, GG, T, false>; \
         NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));               \
         NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, tsmem));                          \
         const int64_t want = (n_cells + (128 / GG) - 1) / (128 / GG);                                                \

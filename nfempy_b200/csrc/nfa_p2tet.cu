@@ -171,8 +171,13 @@ struct TileCtx {
     unsigned ihx, ihy;  // packed 16-bit tile offsets of the three blocks and the row pitch (decoded when storing)
     __device__ __forceinline__ void wait() const {
         if ((threadIdx.x & 31) == 0) {
-            while (*free_at < need) __nanosleep(32);
-            __threadfence_block();
+            const uint32_t a = (uint32_t)__cvta_generic_to_shared(const_cast<int *>(free_at));
+            for (;;) {  // acquire load instead of a plain load + MEMBAR
+                int v;
+                asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+                if (v >= need) break;
+                __nanosleep(32);
+            }
         }
         __syncwarp();
     }
@@ -516,11 +521,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         if ((threadIdx.x & 31) == 0) {
             const int c = (int)((unsigned)th.w >> 6);
             const int it = c - c_begin_r, b = it % NBUF;
-            __threadfence_block();
+            // release of this task's tile stores / acquire of the other tasks' in one acq_rel atomic (no separate MEMBAR)
             int left;
-            asm volatile("atom.shared.add.u32 %0, [%1], -1;" : "=r"(left) : "r"(ctrl_s + 4u * (4u + (unsigned)b)) : "memory");
+            asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], -1;" : "=r"(left) : "r"(ctrl_s + 4u * (4u + (unsigned)b)) : "memory");
             if (left == 1) {  // the chunk's last task: the tile is complete
-                __threadfence_block();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 const int4 ch = __ldg(chunk_hdr + c);
                 const int b0 = ch.x, n_vals = 9 * ch.y, head = b0 & 1;

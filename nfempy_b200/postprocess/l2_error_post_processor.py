@@ -1,6 +1,7 @@
-"""Error norms of a discrete solution -- GPU versions of ``l2_error`` and ``div_error``
-(R/src/postprocess/l2_error_post_processor.py:7-63, 185-237): same signatures, same return value (one norm per field,
-in field order).  The exact functions are evaluated on the host over all quadrature points at once, the discrete field
+"""Error norms of a discrete solution -- GPU versions of ``l2_error``, ``l2_error_projected`` and ``div_error``
+(R/src/postprocess/l2_error_post_processor.py:7-63, 66-117, 185-237): same signatures, same return value (one norm per
+field, in field order).  ``grad_error`` (:120-182) and ``devia_l2_error`` (:308-) read attributes the current reference
+spaces no longer have (``el_data.quadrature``, ``fe_space.quadrature`` as a pair) and are not restated.  The exact functions are evaluated on the host over all quadrature points at once, the discrete field
 is evaluated and compared on the device (``nfa_field_error``), cell contributions are summed in cell order."""
 import numpy as np
 import torch
@@ -86,3 +87,16 @@ def l2_error(dim, fe_space, functions, alpha, skip_fields=[]):
 
 def div_error(dim, fe_space, functions, alpha, skip_fields=[]):
     return _field_errors(dim, fe_space, functions, np.asarray(alpha, dtype=np.float64), skip_fields, True)
+
+
+def _zero_like_field(s, dim):
+    if s.family in ("RT", "BDM"):
+        return lambda x, y, z: np.zeros((s.n_comp, 3) + np.shape(x))
+    return lambda x, y, z: np.zeros((max(s.n_comp, dim),) + np.shape(x))
+
+
+def l2_error_projected(dim, fe_space, alpha, skip_fields=[], dof_shift=0):
+    """L2 norm of every discrete field itself (the reference's "error" against zero,
+    R/src/postprocess/l2_error_post_processor.py:66-117); ``dof_shift`` offsets the destination indices into ``alpha``."""
+    zero = {name: _zero_like_field(s, dim) for name, s in fe_space.discrete_spaces.items()}
+    return _field_errors(dim, fe_space, zero, np.asarray(alpha, dtype=np.float64)[dof_shift:], skip_fields, False)

@@ -128,3 +128,43 @@ def test_global_basis_is_hdiv_conforming(family, dim, k):
             jump = max(jump, np.abs(flux[0] - flux[1]).max())
     scale = float(k * k * 50)
     assert jump <= 1e-12 * scale and leak <= 1e-11 * scale
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_bdm3_moment_families(dim):
+    """The two families BDM_3's dual basis is built from: the degree-2 Nedelec test functions span [P1]^d + {p in
+    [Ptilde_2]^d : p . x = 0} (dimension 8 / 20), and the cubic facet lattice is invariant under the facet symmetries
+    (so the orientation matrices are signed permutations)."""
+    from fractions import Fraction
+
+    from nfempy_b200.basis.hdiv import _pmul, _padd, cubic_lattice, nedelec2_test_functions
+    from nfempy_b200.basis.transformations import _node_permutation
+
+    fns = nedelec2_test_functions(dim)
+    assert len(fns) == (8 if dim == 2 else 20)
+    n_p1 = dim * (dim + 1)
+    for w in fns[n_p1:]:  # homogeneous quadratic part: x . p = 0 identically
+        dot = {}
+        for c in range(dim):
+            unit = tuple(1 if d == c else 0 for d in range(dim))
+            dot = _padd(dot, _pmul(w[c], {unit: Fraction(1)}))
+        assert all(v == 0 for v in dot.values())
+        assert all(sum(e) == 2 for comp in w for e, v in comp.items() if v != 0)
+    # linear independence: evaluate at random points and take the rank
+    rng = np.random.default_rng(1)
+    pts = rng.random((40, dim))
+    M = np.zeros((len(fns), 40 * dim))
+    for i, w in enumerate(fns):
+        for c in range(dim):
+            val = np.zeros(40)
+            for e, v in w[c].items():
+                val += float(v) * np.prod(pts ** np.array(e), axis=1)
+            M[i, c::dim] = val
+    assert np.linalg.matrix_rank(M) == len(fns)
+    fdim = dim - 1
+    nodes = cubic_lattice(fdim)
+    assert len(nodes) == (4 if fdim == 1 else 10)
+    images = [[1, 0]] if fdim == 1 else [[1, 2, 0], [0, 2, 1]]
+    for image in images:
+        P = _node_permutation(fdim, 3, image)
+        assert np.all(P.sum(axis=0) == 1) and np.all(P.sum(axis=1) == 1)

@@ -119,3 +119,12 @@ def test_scaled_to_physical_evaluate_form_signature():
     r, j = form.evaluate_form(3, a, s)
     r0, j0 = ref_forms.scaled_to_physical_l2_projection(rspace, form.functions, 3, a, s)
     assert np.abs(r - r0).max() <= 1e-12 * np.abs(r0).max() and np.abs(j - j0).max() <= 1e-12 * np.abs(j0).max()
+
+
+@pytest.mark.parametrize("dim,k,family", [(3, 2, "RT"), (3, 3, "RT"), (2, 3, "RT"), (3, 2, "BDM"), (3, 3, "BDM")])
+def test_mass_block_on_the_fp64_tensor_cores(dim, k, family, monkeypatch):
+    """NFA_HDIV_MMA=1: the symmetric flux mass block as 8 x 8 DMMA tiles (mma.sync m8n8k4) -- same matrix."""
+    case = mixed_poisson_case(dim=dim, k=k, n=1 if dim == 3 else 2, family=family, varying=True)
+    ref = case.run_oracle()
+    monkeypatch.setenv("NFA_HDIV_MMA", "1")
+    compare_csr(case.run_gpu(), ref, 1e-10 if (family, k) == ("BDM", 3) else RTOL)

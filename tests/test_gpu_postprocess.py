@@ -5,7 +5,7 @@ end-to-end property -- the projection of an in-space polynomial has (machine-)ze
 import numpy as np
 import pytest
 
-from nfempy_b200.postprocess import div_error, l2_error, l2_projector
+from nfempy_b200.postprocess import div_error, div_norm, l2_error, l2_error_projected, l2_norm, l2_projector
 from oracle import ref_postprocess
 from tests.parity_helpers import tensor_mixed_case
 
@@ -35,6 +35,13 @@ def test_error_norms_match_the_oracle(dim, k, fam):
     got_d, ref_d = div_error(dim, space, fn, alpha), ref_postprocess.div_error(dim, rspace, fn, alpha)
     assert len(got_d) == 2 and np.allclose(got_d, ref_d, rtol=1e-12, atol=0.0)
     assert np.allclose(l2_error(dim, space, fn, alpha, skip_fields=["m", "t"]), [ref[0], ref[2]], rtol=1e-12)
+    # norms of the discrete fields themselves and of the exact functions (solution_norms_post_processor.py)
+    assert np.allclose(l2_error_projected(dim, space, alpha), ref_postprocess.l2_error_projected(dim, rspace, alpha), rtol=1e-12)
+    shifted = np.concatenate([np.full(5, 7.0), alpha])
+    assert np.allclose(l2_error_projected(dim, space, shifted, dof_shift=5),
+                       ref_postprocess.l2_error_projected(dim, rspace, shifted, dof_shift=5), rtol=1e-12)
+    assert np.allclose(l2_norm(dim, space, fn), ref_postprocess.l2_norm(dim, rspace, fn), rtol=1e-12)
+    assert np.allclose(div_norm(dim, space, fn), ref_postprocess.div_norm(dim, rspace, fn), rtol=1e-12)
 
 
 @pytest.mark.parametrize("dim", [2, 3])
