@@ -86,6 +86,27 @@ def cpu_baseline(n_box, n_cells, workers, pool=None):
     return per * workers / wall, per * workers, wall
 
 
+def cpu_strong_baseline(space, n_cells_sample, repeats=3):
+    """The "strong CPU" baseline of BASELINE.md section 3: batched numpy + scipy COO -> CSR (oracle/strong_cpu.py) on the
+    first ``n_cells_sample`` tets of the SAME mesh and numbering, all host threads numpy / BLAS choose to use; best of
+    ``repeats``.  Matrix only (the dominant part), lambda = mu = 1."""
+    from oracle import strong_cpu
+
+    u = space.discrete_spaces["u"]
+    n = min(n_cells_sample, len(u.elements))
+    dest = np.asarray(space.destination_table()[:n], dtype=np.int64)
+    cell_nodes = np.asarray(u.cell_nodes()[:n], dtype=np.int64)
+    points = u.mesh.points
+    strong_cpu.assemble_elasticity(points, cell_nodes[:256], dest[:256], space.n_dof, 1.0, 1.0)  # warm-up (imports, einsum paths)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        strong_cpu.assemble_elasticity(points, cell_nodes, dest, space.n_dof, 1.0, 1.0)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n / best, n, best
+
+
 WORKLOAD = "3D Cauchy linear elasticity, vector H1 p=2, %d tets per GPU (Kuhn box n=%d, jittered), lambda=mu=1, tabulated load, CSR values + rhs"
 
 
@@ -357,6 +378,11 @@ def run_graft(args):
         cpu = {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
                "sample": "%d tets of the same jittered Kuhn box, oracle port (cell-by-cell numpy restatement of the "
                          "reference, dict-of-keys scatter), %.1f s" % (cells, wall)}
+    cpu_strong = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cells, wall = cpu_strong_baseline(space, 40000)
+        cpu_strong = {"value": v, "unit": "elements/s", "cores": os.cpu_count(), "kind": "vectorised numpy + scipy COO->CSR",
+                      "sample": "matrix of the first %d tets of the same mesh, best of 3, %.2f s" % (cells, wall)}
     if rank == 0:
         line = {
             "metric": "elements/s assembled (3D elasticity p=2)", "value": value, "unit": "elements/s",
@@ -374,7 +400,7 @@ def run_graft(args):
                            ("CUDA graph replay of the local assembly + eager NCCL exchange" if (sharded is not None and not args.no_graph)
                             else "eager launches")),
             },
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_strong": cpu_strong, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
