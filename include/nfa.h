@@ -258,6 +258,14 @@ int nfa_field_error(int dim, int kind, int n_phi, int n_comp, int n_q, int nfd, 
                     const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_alpha,
                     const int32_t *d_dest, int dest_stride, int dest_off, const double *d_exact, double *d_out,
                     nfa_stream stream);
+/* Same with kind 3: error of the SCALED divergence  l div psi + grad l . psi  of an H(div) field against d_exact
+ * (div_scaled_error, R/src/postprocess/l2_error_post_processor.py:240-305); d_scale [n_cells][n_q], d_gscale
+ * [n_cells][n_q][dim] are the host-evaluated l and grad l.  kinds 0..2 ignore them (nfa_field_error forwards here). */
+int nfa_field_error_scaled(int dim, int kind, int n_phi, int n_comp, int n_q, int nfd, const double *d_val,
+                           const double *d_div, const double *d_weights, const double *d_Tcases, const int8_t *d_cases,
+                           const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_alpha,
+                           const int32_t *d_dest, int dest_stride, int dest_off, const double *d_exact,
+                           const double *d_scale, const double *d_gscale, double *d_out, nfa_stream stream);
 
 /* ---- row-item fused path for vector-P2 elasticity on affine tetrahedra (config 2's headline kernel).
  * Same plan object, same output (all nnz values of the pattern, written once, deterministic) as

@@ -64,6 +64,8 @@ SIGNATURES = {
     "nfa_local_hdiv_tensor": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nfa_local_hdiv_facet_vec": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _i, _i, _vp, _vp]),
     "nfa_field_error": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "nfa_field_error_scaled": (_i, [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _vp, _vp,
+                                    _vp, _vp, _vp]),
     "nfa_local_hdiv_facet_penalty": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _i, _i, _vp, _vp, _vp]),
     "nfa_local_h1_multifield": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp,
                                      _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

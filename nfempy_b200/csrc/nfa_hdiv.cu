@@ -1439,7 +1439,8 @@ __global__ void __launch_bounds__(128)
                        const double *__restrict__ Tcases, const int8_t *__restrict__ cases,
                        const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes, int64_t n_cells,
                        const double *__restrict__ alpha, const int32_t *__restrict__ dest, int dest_stride,
-                       int dest_off, const double *__restrict__ exact, double *__restrict__ out) {
+                       int dest_off, const double *__restrict__ exact, const double *__restrict__ scale,
+                       const double *__restrict__ gscale, double *__restrict__ out) {
     constexpr int NF = DIM + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t cell = (int64_t)blockIdx.x * 4 + warp; cell < n_cells; cell += (int64_t)gridDim.x * 4) {
@@ -1482,6 +1483,16 @@ __global__ void __launch_bounds__(128)
                     }
                     if (kind == 2) {
                         uh[0] += dh * idet * al;
+                    } else if (kind == 3) {  // scaled divergence: l div psi + grad l . psi
+                        double D = scale[cell * n_q + q] * dh * idet;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) {
+                            double v = 0.0;
+#pragma unroll
+                            for (int k = 0; k < DIM; ++k) v += g.J[d][k] * vh[k];
+                            D += gscale[(cell * n_q + q) * DIM + d] * v * idet;
+                        }
+                        uh[0] += D * al;
                     } else {
 #pragma unroll
                         for (int d = 0; d < DIM; ++d) {
@@ -1517,15 +1528,28 @@ extern "C" int nfa_field_error(int dim, int kind, int n_phi, int n_comp, int n_q
                                const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *alpha,
                                const int32_t *dest, int dest_stride, int dest_off, const double *exact, double *out,
                                nfa_stream stream) {
+    return nfa_field_error_scaled(dim, kind, n_phi, n_comp, n_q, nfd, val, dv, weights, Tcases, cases, coords, cell_nodes,
+                                  n_cells, alpha, dest, dest_stride, dest_off, exact, nullptr, nullptr, out, stream);
+}
+
+extern "C" int nfa_field_error_scaled(int dim, int kind, int n_phi, int n_comp, int n_q, int nfd, const double *val,
+                                      const double *dv, const double *weights, const double *Tcases, const int8_t *cases,
+                                      const double *coords, const int32_t *cell_nodes, int64_t n_cells,
+                                      const double *alpha, const int32_t *dest, int dest_stride, int dest_off,
+                                      const double *exact, const double *scale, const double *gscale, double *out,
+                                      nfa_stream stream) {
     if (n_cells == 0) return 0;
-    if (kind < 0 || kind > 2) return fail("nfa_field_error: kind must be 0 (Lagrange), 1 (H(div) value) or 2 (H(div) divergence)");
+    if (kind < 0 || kind > 3)
+        return fail("nfa_field_error: kind must be 0 (Lagrange), 1 (H(div) value), 2 (H(div) divergence) or 3 (scaled divergence)");
+    if (kind == 3 && (!scale || !gscale)) return fail("nfa_field_error_scaled: scale / grad scale arrays missing");
     if (kind != 0 && (!dv || !Tcases || !cases)) return fail("nfa_field_error: H(div) tables missing");
     cudaStream_t s = (cudaStream_t)stream;
     int64_t ctas = (n_cells + 3) / 4;
     int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
 #define NFA_FE(D)                                                                                              \
     field_error_kernel<D><<<grid, 128, 0, s>>>(kind, n_phi, n_comp, n_q, nfd, val, dv, weights, Tcases, cases, \
-                                               coords, cell_nodes, n_cells, alpha, dest, dest_stride, dest_off, exact, out)
+                                               coords, cell_nodes, n_cells, alpha, dest, dest_stride, dest_off, exact, \
+                                               scale, gscale, out)
     if (dim == 3)
         NFA_FE(3);
     else if (dim == 2)

@@ -46,6 +46,8 @@ def _field_errors(dim, fe_space, functions, alpha, skip_fields, divergence):
         vector_family = s.family in ("RT", "BDM")
         if divergence and not vector_family:
             continue
+        if divergence == "scaled" and (functions.get("l") is None or functions.get("grad_l") is None):
+            continue  # the reference skips the field when no scale is given (:296-298)
         ref = s.ref_element
         cell_nodes = dev.cell_nodes(name)
         n = int(cell_nodes.shape[0])
@@ -68,13 +70,19 @@ def _field_errors(dim, fe_space, functions, alpha, skip_fields, divergence):
                 exact = _exact_values(functions["div_" + name], x, (s.n_comp,))
             else:
                 exact = _exact_values(functions[name], x, (s.n_comp, dim))
-            args = (2 if divergence else 1, ref.n_phi, s.n_comp, len(weights), nfd, _lib.ptr(val), _lib.ptr(dv),
+            kind = 3 if divergence == "scaled" else (2 if divergence else 1)
+            args = (kind, ref.n_phi, s.n_comp, len(weights), nfd, _lib.ptr(val), _lib.ptr(dv),
                     _lib.ptr(w), _lib.ptr(tc), _lib.ptr(cases))
             keep = [val, dv, tc, cases]
         ex = up(exact)
+        scale = gscale = None
+        if divergence == "scaled":
+            scale = up(coefficients.evaluate(functions["l"], x))
+            gscale = up(coefficients.evaluate(functions["grad_l"], x, dim))
         _lib.call(
-            "nfa_field_error", dim, *args, _lib.ptr(dev.coords), _lib.ptr(cell_nodes), n, _lib.ptr(alpha_dev),
-            _lib.ptr(dest), int(dest.shape[1]), int(strides[name]), _lib.ptr(ex), _lib.ptr(per_cell), _lib.stream_ptr(),
+            "nfa_field_error_scaled", dim, *args, _lib.ptr(dev.coords), _lib.ptr(cell_nodes), n, _lib.ptr(alpha_dev),
+            _lib.ptr(dest), int(dest.shape[1]), int(strides[name]), _lib.ptr(ex), _lib.ptr(scale), _lib.ptr(gscale),
+            _lib.ptr(per_cell), _lib.stream_ptr(),
         )
         out.append(float(np.sqrt(per_cell.cpu().numpy().sum())))
         del keep
@@ -100,3 +108,9 @@ def l2_error_projected(dim, fe_space, alpha, skip_fields=[], dof_shift=0):
     R/src/postprocess/l2_error_post_processor.py:66-117); ``dof_shift`` offsets the destination indices into ``alpha``."""
     zero = {name: _zero_like_field(s, dim) for name, s in fe_space.discrete_spaces.items()}
     return _field_errors(dim, fe_space, zero, np.asarray(alpha, dtype=np.float64)[dof_shift:], skip_fields, False)
+
+
+def div_scaled_error(dim, fe_space, functions, alpha, skip_fields=[]):
+    """Error of the scaled divergence ``l div s + grad l . s`` of every H(div) field against ``functions["div_" + name]``
+    (R/src/postprocess/l2_error_post_processor.py:240-305); fields are skipped when ``l`` / ``grad_l`` are missing."""
+    return _field_errors(dim, fe_space, functions, np.asarray(alpha, dtype=np.float64), skip_fields, "scaled")

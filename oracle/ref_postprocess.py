@@ -114,3 +114,31 @@ def div_norm(dim, space, functions, skip_fields=()):
             total += np.sum((f_e * f_e).T @ (det_jac * weights))
         out.append(np.sqrt(total))
     return out
+
+
+def div_scaled_error(dim, space, functions, alpha, skip_fields=()):
+    """R/src/postprocess/l2_error_post_processor.py:240-305."""
+    out = []
+    for name, fs in space.discrete_spaces.items():
+        if fs.family not in ("RT", "BDM") or name in skip_fields:
+            continue
+        exact = functions["div_" + name]
+        scale, grad_scale = functions.get("l"), functions.get("grad_l")
+        if scale is None or grad_scale is None:
+            continue
+        total = 0.0
+        for i in range(len(fs.element_ids)):
+            _, weights, x, det_jac, tab = _cell_tables(space, fs, i)
+            alpha_l = alpha[space.destination_indexes(i, name)]
+            n_phi = tab.shape[2]
+            alpha_star = np.array(np.split(alpha_l, n_phi))
+            gamma = scale(x[:, 0], x[:, 1], x[:, 2]) * np.ones(len(weights))
+            grad_gamma = np.asarray(grad_scale(x[:, 0], x[:, 1], x[:, 2]))
+            div_v_star = np.array([[np.trace(np.outer(grad_gamma[:, q], tab[0, q, j, 0:dim])) for q in range(len(weights))]
+                                   for j in range(n_phi)])
+            div_v_star = div_v_star + np.trace(tab[1 : 1 + dim, :, :, 0:dim], axis1=0, axis2=3).T * (gamma / det_jac)
+            f_e = np.array([exact(xv[0], xv[1], xv[2]) for xv in x])
+            f_h = div_v_star.T @ alpha_star
+            total += np.sum(((f_e - f_h) * (f_e - f_h)).T @ (det_jac * weights))
+        out.append(np.sqrt(total))
+    return out

@@ -5,7 +5,8 @@ end-to-end property -- the projection of an in-space polynomial has (machine-)ze
 import numpy as np
 import pytest
 
-from nfempy_b200.postprocess import div_error, div_norm, l2_error, l2_error_projected, l2_norm, l2_projector
+from nfempy_b200.postprocess import (div_error, div_norm, div_scaled_error, l2_error, l2_error_projected, l2_norm,
+                                     l2_projector)
 from oracle import ref_postprocess
 from tests.parity_helpers import tensor_mixed_case
 
@@ -42,6 +43,12 @@ def test_error_norms_match_the_oracle(dim, k, fam):
                        ref_postprocess.l2_error_projected(dim, rspace, shifted, dof_shift=5), rtol=1e-12)
     assert np.allclose(l2_norm(dim, space, fn), ref_postprocess.l2_norm(dim, rspace, fn), rtol=1e-12)
     assert np.allclose(div_norm(dim, space, fn), ref_postprocess.div_norm(dim, rspace, fn), rtol=1e-12)
+    # scaled divergence (the scaled Cosserat forms): skipped without a scale, else l div s + grad l . s
+    assert div_scaled_error(dim, space, fn, alpha) == []
+    fn_l = dict(fn, l=lambda x, y, z: 0.5 + 0.25 * x + 0.1 * y * y,
+                grad_l=lambda x, y, z: np.array([0.25 * np.ones_like(x), 0.2 * y, 0.0 * x]))
+    got_s, ref_s = div_scaled_error(dim, space, fn_l, alpha), ref_postprocess.div_scaled_error(dim, rspace, fn_l, alpha)
+    assert len(got_s) == 2 and np.allclose(got_s, ref_s, rtol=1e-12, atol=0.0)
 
 
 @pytest.mark.parametrize("dim", [2, 3])
