@@ -467,27 +467,12 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int task_end = ctrl[3], c_begin_r = ctrl[1];
     const int4 none = make_int4(0, 0, 0, -1);
     const uint32_t ctrl_s = (uint32_t)__cvta_generic_to_shared(const_cast<int *>(ctrl));
-#ifdef NFA_P2_GRAB2
-    // tasks are taken two at a time (one shared-memory atomic + shuffle per pair)
-    int grab_next = 0, grab_left = 0;
-    auto grab = [&]() {
-        if (grab_left == 0) {
-            int t = 0;
-            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 2;" : "=r"(t) : "r"(ctrl_s) : "memory");
-            grab_next = __shfl_sync(0xffffffffu, t, 0);
-            grab_left = 2;
-        }
-        --grab_left;
-        return grab_next++;
-    };
-#else
     auto grab = [&]() {
         int t = 0;
         if (lane == 0)  // plain shared-memory atomic (the compiler wraps atomicAdd in its warp-aggregation sequence)
             asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t) : "r"(ctrl_s) : "memory");
         return __shfl_sync(0xffffffffu, t, 0);
     };
-#endif
     int4 th = none, th1 = none;
     {
         const int t0 = grab();
