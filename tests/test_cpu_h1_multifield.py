@@ -85,3 +85,41 @@ def test_field_order_is_checked():
     space.build_structures({"u": [1], "t": [1]}, {})
     with pytest.raises(_lib.NfaError):
         LCEPrimalWeakForm(space)._fields()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_primal_cosserat_rigid_motions_are_in_the_null_space(dim):
+    """Known answer for the oracle's LCE primal restatement (sign of Theta(t), skew part, couple stress): a translation
+    and an infinitesimal rigid rotation u = W x with the matching micro-rotation t (Theta(t) = -W, grad t = 0) produce no
+    strain, no curvature and therefore a vanishing homogeneous residual J alpha on every cell."""
+    from oracle import ref_assembly
+
+    case = lce_primal_case(dim=dim, k=2, kt=1, n=1 if dim == 3 else 2, varying=True, with_bc=False)
+    rspace = case.ref_space()
+    functions = dict(case.ref_forms_fn(rspace)[0][2])
+    functions["rhs"] = lambda x, y, z: np.zeros((6 if dim == 3 else 3,) + np.shape(x))
+    u, t = rspace.discrete_spaces["u"], rspace.discrete_spaces["t"]
+    nt = 3 if dim == 3 else 1
+    # nodal coordinates of the Lagrange dofs: interpolate by evaluating at the cell's nodes through the oracle's own basis
+    omega = np.array([0.3, -0.2, 0.5])
+    W = np.array([[0.0, -omega[2], omega[1]], [omega[2], 0.0, -omega[0]], [-omega[1], omega[0], 0.0]])
+    n_cells = len(u.element_ids)
+    for motion in ("translation", "rotation"):
+        for iel in range(n_cells):
+            cell = u.mesh.cells[u.element_ids[iel]]
+            X = u.mesh.points[cell.node_tags]  # vertices
+            edges = [(2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1)] if dim == 3 else [(1, 2), (0, 2), (0, 1)]
+            nodes_u = np.vstack([X] + [0.5 * (X[a] + X[b])[None, :] for a, b in edges])  # P2 nodes: vertices, edge midpoints
+            nodes_t = X  # P1 nodes
+            if motion == "translation":
+                a_u = np.tile(np.array([0.7, -0.4, 0.2])[:dim], len(nodes_u))
+                a_t = np.zeros(len(nodes_t) * nt)
+            else:
+                Wd = W if dim == 3 else W[:2, :2]
+                a_u = (nodes_u[:, :dim] @ Wd.T).reshape(-1)
+                # Theta(t) = [[0, -t2, t1], [t2, 0, -t0], [-t1, t0, 0]] must equal -W: t = -omega (2-D: t = -omega_z)
+                tv = -omega if dim == 3 else np.array([-omega[2]])
+                a_t = np.tile(tv, len(nodes_t))
+            alpha_l = np.concatenate([a_u, a_t])
+            r_el, j_el = ref_h1_multi.lce_primal(rspace, functions, iel, alpha_l)
+            assert np.abs(r_el).max() <= 1e-12 * np.abs(j_el).max(), (motion, iel)
