@@ -233,6 +233,9 @@ def run_graft(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its version banner / warnings to STDOUT when NCCL_DEBUG is set (it is on the GPU boxes); stdout must
+        # carry the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load()
 
