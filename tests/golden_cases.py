@@ -30,3 +30,28 @@ def load_mesh_blocks(name):
         for i in range(int(z["n_blocks"]))
     ]
     return z["points"], blocks
+
+
+def fixture_mesh(dim):
+    """The reference's own gmsh fixture (example_3_{2d,3d}_l_0.msh) as a product mesh, rebuilt from the committed arrays."""
+    from nfempy_b200.mesh import Mesh
+
+    points, blocks = load_mesh_blocks("mesh_ex3_%dd_l0.npz" % dim)
+    mesh = Mesh.from_arrays(dim, points, blocks)
+    mesh.build_conformal_mesh()
+    return mesh
+
+
+def multi_cases():
+    """name -> (case, tolerance) of the golden fixtures in multi_ex3_2d_l0.npz: forms added after the first two fixtures,
+    all on the reference's 2-D gmsh mesh (116 triangles, boundary tags 2..5)."""
+    from tests.parity_helpers import lce_primal_case, mixed_poisson_case, taylor_hood_case, tensor_mixed_case
+
+    mesh = fixture_mesh(2)
+    return {
+        "lce_primal": (lce_primal_case(dim=2, k=2, kt=1, varying=True, alpha=True, mesh=mesh), 1e-12),
+        "taylor_hood": (taylor_hood_case(varying=True, alpha=True, mesh=mesh), 1e-12),
+        "mixed_poisson_bdm3": (mixed_poisson_case(dim=2, k=3, family="BDM", varying=True, mesh=mesh), 1e-10),
+        "lce_dual_neumann": (tensor_mixed_case(kind="lce", dim=2, s_family="BDM", m_family="RT", k=1, mesh=mesh,
+                                               neumann=True), 1e-12),
+    }

@@ -476,11 +476,12 @@ def lce_primal_case(dim=3, k=2, n=2, varying=False, alpha=False, with_bc=True, k
     )
 
 
-def taylor_hood_case(n=3, varying=False, alpha=False, with_bc=True):
+def taylor_hood_case(n=3, varying=False, alpha=False, with_bc=True, mesh=None):
     from nfempy_b200.weak_forms import LETaylorHoodWeakForm, LETaylorHoodWeakFormBCDirichlet
     from oracle import ref_h1_multi
 
-    mesh = square_tri_mesh(n, jitter=0.2)
+    if mesh is None:
+        mesh = square_tri_mesh(n, jitter=0.2)
     if varying:
         mats = {"lambda": lambda x, y, z: 10.0 + x + 2.0 * y * y, "mu": lambda x, y, z: 2.0 + np.sin(x)}
     else:

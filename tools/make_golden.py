@@ -6,7 +6,10 @@
   without /root/reference;
 * numbering_ex3_3d_l0.npz       -- cell numbering (node_tags / sub-cell ids / material) from oracle.ref_mesh;
 * le_p2_ex3_3d_l0.npz           -- oracle CSR + rhs: LEPrimalWeakForm P2 x 3 + Dirichlet penalty on the six sides;
-* laplace_p1_ex3_2d_l0.npz      -- oracle CSR + rhs: LaplacePrimalWeakForm P1 + Dirichlet penalty (config 1 style).
+* laplace_p1_ex3_2d_l0.npz      -- oracle CSR + rhs: LaplacePrimalWeakForm P1 + Dirichlet penalty (config 1 style);
+* multi_ex3_2d_l0.npz           -- oracle CSR + rhs of four later form families on the 2-D fixture (primal Cosserat + BC,
+  Taylor-Hood + BC, mixed Poisson on BDM_3 + natural BC, mixed Cosserat with natural and penalised stress BCs);
+  ``python tools/make_golden.py multi`` regenerates only this file (needs no /root/reference: the mesh arrays are committed).
 
 The reference itself cannot run here (basix / auto_diff / petsc4py / meshio absent), so these are ORACLE outputs:
 they pin the oracle against regressions and give the GPU tests a fixed target; they do not pin the oracle to the
@@ -88,5 +91,21 @@ def main():
     print("laplace_p1_ex3_2d_l0: n_dof", space.n_dof, "nnz", len(indices))
 
 
+def main_multi():
+    """multi_ex3_2d_l0.npz: oracle CSR + rhs of the later form families on the 2-D fixture mesh (tests/golden_cases.py)."""
+    from tests.golden_cases import multi_cases
+
+    arrays = {}
+    for name, (case, _) in multi_cases().items():
+        indptr, indices, data, rhs = case.run_oracle()
+        arrays.update({name + "_indptr": indptr, name + "_indices": indices, name + "_data": data, name + "_rhs": rhs})
+        print(name, "n_dof", len(rhs), "nnz", len(indices))
+    np.savez_compressed(os.path.join(OUT, "multi_ex3_2d_l0.npz"), **arrays)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "multi":
+        main_multi()
+    else:
+        main()
+        main_multi()
