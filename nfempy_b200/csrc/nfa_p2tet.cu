@@ -28,14 +28,10 @@ namespace {
 #ifndef NFA_P2_THREADS
 #define NFA_P2_THREADS 512
 #endif
-#ifndef NFA_P2_NBUF
-#define NFA_P2_NBUF 4
-#endif
 #ifndef P2_UNROLL_NG
 #define P2_UNROLL_NG 2
 #endif
 constexpr int P2_THREADS = NFA_P2_THREADS;
-constexpr int P2_NBUF = NFA_P2_NBUF;
 
 struct G4 {
     double x, y, z, rho;
