@@ -65,3 +65,45 @@ def test_product_does_not_import_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M):
                     bad.append(os.path.join(base, f))
     assert not bad, bad
+
+
+def test_error_behaviour_of_the_assembler_front_end():
+    """The reference's error behaviour at the boundary, checked without a GPU: unknown form
+    types raise KeyError like its dispatch dictionary, known types without a kernel and foreign weak-form classes raise
+    NotImplementedError (never a silent host path), an unset form list / unset ``functions`` raise ValueError."""
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.weak_forms import LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet, WeakForm
+    from tests.parity_helpers import elasticity_case
+
+    case = elasticity_case(n=1, with_bc=True)
+    space = case.space()
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+    with pytest.raises(ValueError):
+        asm._entries()  # form_to_input_list not set
+    form = LEPrimalWeakForm(space)
+    form.functions = {"rhs": lambda x, y, z: np.zeros((3,) + np.shape(x)), "lambda": lambda x, y, z: 1.0, "mu": lambda x, y, z: 1.0}
+    asm.form_to_input_list = {"v": ["no_such_form_type", range(6), form, None]}
+    with pytest.raises(KeyError):
+        asm._entries()
+    for kind in ("interface_form", "bc_interface_form"):
+        asm.form_to_input_list = {"v": [kind, range(6), form, None]}
+        with pytest.raises(NotImplementedError):
+            asm._entries()
+    asm.form_to_input_list = {"v": ["bc_form", range(6), form, None]}  # a volume form listed as a boundary form
+    with pytest.raises(ValueError):
+        asm._entries()
+    asm.form_to_input_list = {"v": ["form", [0, 99], form, None]}  # cell index out of range
+    with pytest.raises(IndexError):
+        asm._entries()
+
+    class Foreign(WeakForm):  # a user form without a CUDA kernel
+        def evaluate_form(self, element_index, alpha):
+            return None
+
+    asm.form_to_input_list = {"v": ["form", range(6), Foreign(space), None]}
+    with pytest.raises(NotImplementedError):
+        asm._entries()
+    with pytest.raises(ValueError):  # functions unset (R/src/weak_forms/le_primal_weak_form.py:15-16)
+        LEPrimalWeakFormBCDirichlet(space).evaluate_form(0, None)
+    with pytest.raises(ValueError):
+        GPUAssembler(space, pattern_policy="no_such_policy")
