@@ -144,6 +144,10 @@ class ReferenceElement:
             from .hdiv import build_hdiv
 
             build_hdiv(self)
+        elif family == "N1E":
+            from .hcurl import build_hcurl
+
+            build_hcurl(self)
         else:
             raise NotImplementedError("ReferenceElement: family %r is not restated" % family)
         self.n_phi = self.coeffs.shape[0]

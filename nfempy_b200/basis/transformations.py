@@ -75,6 +75,11 @@ def entity_transformations(el):
     out = {}
     if el.dim < 2:
         return out
+    if el.family == "N1E":  # one tangential moment per edge: reversing the edge flips its sign; no face dofs at degree 1
+        out["interval"] = [-np.ones((1, 1))]
+        if el.dim == 3:
+            out["triangle"] = [np.zeros((0, 0)), np.zeros((0, 0))]
+        return out
     hdiv = el.family in ("RT", "BDM")
     if el.dim == 2 or not hdiv:
         # dofs attached to edges: H(div) facets of a triangle, or interior edge nodes of Lagrange P3
