@@ -211,6 +211,8 @@ class GPUAssembler:
         cap = int(os.environ.get("NFA_P2TET_CAP", "640"))
         staged = os.environ.get("NFA_P2TET_STAGE", "0") not in ("", "0")  # the opt-in staged kernel needs extra lists
         items = p2_items.build(node_dest.to(torch.int64), bptr.to(torch.int64), bcols.to(torch.int64), n_nodes, cap=cap,
+                               riffle=int(os.environ.get("NFA_P2TET_RIFFLE", "148")),
+                               batch=int(os.environ.get("NFA_P2TET_BATCH", "8")),
                                lane_order=os.environ.get("NFA_P2TET_LANES", "cell"), staged=staged)
         _lib.check(
             lib.nfa_bplan_set_p2_items(

@@ -79,7 +79,7 @@ def _templates():
 TEMPLATES = _templates()  # 4 * 7 + 6 * 4 = 52 entries per cell
 
 
-def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=296, batch=8, lane_order="cell", staged=True):
+def build(node_dest, bptr, bcols, n_nodes, cap=448, riffle=148, batch=8, lane_order="cell", staged=True):
     """``node_dest`` int64 [n_cells, 10] global node of each local P2 node, ``bptr``/``bcols`` the block CSR of the
     matrix (int64 tensors on the same device).  Returns a dict of tensors (see module docstring) and sizes."""
     dev = node_dest.device

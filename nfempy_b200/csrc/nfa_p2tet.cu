@@ -33,18 +33,96 @@ namespace {
 #endif
 constexpr int P2_THREADS = NFA_P2_THREADS;
 
+// Experiment switches (tools/build_variant.sh builds a library per setting; the defaults are what bench.py measures).
+//   NFA_P2_PF_ELL  1: the ELL lines of the NEXT task beyond its first two entries are prefetched into L2 (2: into L1) one
+//                  task ahead -- a lane prefetches line `lane`; without it every round of a long item waits for a DRAM miss
+//   NFA_P2_PF_IH   1: the item headers of the next task are prefetched into L1 one task ahead
+//   NFA_P2_L2HINT  bit 0: geometry records are loaded L2::evict_last, bit 1: the tile leaves with L2::evict_first,
+//                  bit 2: plan lists (ELL, headers) are loaded L2::evict_first
+//   NFA_P2_E2      1: face items (type E: at most two cells) load both cells' records at once and finish block by block
+#ifndef NFA_P2_PF_ELL
+#define NFA_P2_PF_ELL 1
+#endif
+#ifndef NFA_P2_PF_IH
+#define NFA_P2_PF_IH 1
+#endif
+#ifndef NFA_P2_L2HINT
+#define NFA_P2_L2HINT 0
+#endif
+#ifndef NFA_P2_E2
+#define NFA_P2_E2 1
+#endif
+#ifndef NFA_P2_UA
+#define NFA_P2_UA 8  // cells in flight, vertex-diagonal items (3 or more: the general loop)
+#endif
+#ifndef NFA_P2_UB
+#define NFA_P2_UB 4  // cells in flight, vertex-edge items
+#endif
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 struct G4 {
     double x, y, z, rho;
 };
 
 __device__ __forceinline__ G4 ldg256(const double *p) {
     G4 g;
+#if (NFA_P2_L2HINT & 1)
+    const uint64_t pol = l2_policy_evict_last();
+    asm("ld.global.nc.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=d"(g.x), "=d"(g.y), "=d"(g.z), "=d"(g.rho)
+        : "l"(p), "l"(pol));
+    return g;
+#endif
 #ifdef NFA_P2_PLAIN_LD
     asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(g.x), "=d"(g.y), "=d"(g.z), "=d"(g.rho) : "l"(p));
 #else
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(g.x), "=d"(g.y), "=d"(g.z), "=d"(g.rho) : "l"(p));
 #endif
     return g;
+}
+
+// plan lists are read once per launch: optionally marked L2::evict_first so that they do not push the records out of L2
+__device__ __forceinline__ uint32_t ld_list(const uint32_t *p) {
+#if (NFA_P2_L2HINT & 4)
+    uint32_t v;
+    const uint64_t pol = l2_policy_evict_first();
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ int4 ld_list(const int4 *p) {
+#if (NFA_P2_L2HINT & 4)
+    int4 v;
+    const uint64_t pol = l2_policy_evict_first();
+    asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint2 ld_list(const uint2 *p) {
+#if (NFA_P2_L2HINT & 4)
+    uint2 v;
+    const uint64_t pol = l2_policy_evict_first();
+    asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+#else
+    return __ldg(p);
+#endif
 }
 
 // geometry records [n_cells][4][4]: (sqrt(det mu) g_m, lambda / mu), m = 0..3
@@ -380,21 +458,91 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
     constexpr int NG = Item<TYPE, CR>::NG;
     // cells in flight per iteration: long items with few sums walk many cells at once (their task would otherwise
     // hold its chunk's tile for tens of dependent load latencies); type E stays at one (register budget)
-    constexpr int U = (TYPE == 0) ? 8 : ((TYPE == 1) ? 4 : ((NG <= UNROLL_NG) ? 2 : 1));
+    constexpr int U = (TYPE == 0) ? NFA_P2_UA : ((TYPE == 1) ? NFA_P2_UB : ((NG <= UNROLL_NG) ? 2 : 1));
+#if NFA_P2_E2
+    if constexpr (TYPE == 4) {
+        // a face has at most two cells: both cells' records are requested at once (one memory round trip instead of two)
+        // and the three blocks are formed and stored one after the other, so that no 27 sums are live at any time
+        const Rec<3> r0 = load_rec<3>(c0, rec), r1 = load_rec<3>(c1, rec);  // an absent cell reads as zeros
+        if (pf0 != 0xFFFFFFFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (size_t)(pf0 >> 6) * 16));
+        if (pf1 != 0xFFFFFFFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (size_t)(pf1 >> 6) * 16));
+        const double rho = r0.g[0].rho;
+        const double a0[3] = {r0.g[0].x, r0.g[0].y, r0.g[0].z}, b0[3] = {r0.g[1].x, r0.g[1].y, r0.g[1].z};
+        const double x0[3] = {r0.g[2].x, r0.g[2].y, r0.g[2].z};
+        const double a1[3] = {r1.g[0].x, r1.g[0].y, r1.g[0].z}, b1[3] = {r1.g[1].x, r1.g[1].y, r1.g[1].z};
+        const double x1[3] = {r1.g[2].x, r1.g[2].y, r1.g[2].z};
+        const double s0[3] = {a0[0] + b0[0], a0[1] + b0[1], a0[2] + b0[2]};
+        const double s1[3] = {a1[0] + b1[0], a1[1] + b1[1], a1[2] + b1[2]};
+        ctx.wait();
+        {
+            double k[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t = 0.0;
+            t += add_general<CR>(k, r0.g[0].rho, s0, x0);
+            t += add_general<CR>(k, r1.g[0].rho, s1, x1);
+            fix_general<CR>(k, t, rho);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) k[i] = -C30 * (k[i] + ((i % 4 == 0) ? t : 0.0));
+            ctx.put(0, k);
+        }
+        {
+            const double ax0[3] = {a0[0] + x0[0], a0[1] + x0[1], a0[2] + x0[2]};
+            const double ax1[3] = {a1[0] + x1[0], a1[1] + x1[1], a1[2] + x1[2]};
+            double k[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t = 0.0;
+            t += add_general<CR>(k, r0.g[0].rho, s0, ax0);
+            t += add_general<CR>(k, r0.g[0].rho, b0, x0);
+            t += add_general<CR>(k, r1.g[0].rho, s1, ax1);
+            t += add_general<CR>(k, r1.g[0].rho, b1, x1);
+            fix_general<CR>(k, t, rho);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) k[i] = C15 * (k[i] + ((i % 4 == 0) ? t : 0.0));
+            ctx.put(1, k);
+        }
+        {
+            const double bx0[3] = {b0[0] + x0[0], b0[1] + x0[1], b0[2] + x0[2]};
+            const double bx1[3] = {b1[0] + x1[0], b1[1] + x1[1], b1[2] + x1[2]};
+            double k[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t = 0.0;
+            t += add_general<CR>(k, r0.g[0].rho, s0, bx0);
+            t += add_general<CR>(k, r0.g[0].rho, a0, x0);
+            t += add_general<CR>(k, r1.g[0].rho, s1, bx1);
+            t += add_general<CR>(k, r1.g[0].rho, a1, x1);
+            fix_general<CR>(k, t, rho);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) k[i] = C15 * (k[i] + ((i % 4 == 0) ? t : 0.0));
+            ctx.put(2, k);
+        }
+        return;
+    }
+    if constexpr (TYPE == 2) {  // vertex row, opposite edge of a face: at most two cells, one block
+        const Rec<2> r0 = load_rec<2>(c0, rec), r1 = load_rec<2>(c1, rec);
+        if (pf0 != 0xFFFFFFFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (size_t)(pf0 >> 6) * 16));
+        if (pf1 != 0xFFFFFFFFu) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (size_t)(pf1 >> 6) * 16));
+        const double u0[3] = {r0.g[0].x, r0.g[0].y, r0.g[0].z}, u1[3] = {r1.g[0].x, r1.g[0].y, r1.g[0].z};
+        const double w0[3] = {u0[0] + r0.g[1].x, u0[1] + r0.g[1].y, u0[2] + r0.g[1].z};
+        const double w1[3] = {u1[0] + r1.g[1].x, u1[1] + r1.g[1].y, u1[2] + r1.g[1].z};
+        double k[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, t = 0.0;
+        t += add_general<CR>(k, r0.g[0].rho, u0, w0);
+        t += add_general<CR>(k, r1.g[0].rho, u1, w1);
+        fix_general<CR>(k, t, r0.g[0].rho);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) k[i] = C30 * (k[i] + ((i % 4 == 0) ? t : 0.0));
+        ctx.wait();
+        ctx.put(0, k);
+        return;
+    }
+#endif
     Item<TYPE, CR> item;
     if constexpr (U > 2) {
         uint32_t c[U];
         c[0] = c0;
         c[1] = c1;
 #pragma unroll
-        for (int u = 2; u < U; ++u) c[u] = (u < kmax) ? __ldg(e + 32 * u) : 0xFFFFFFFFu;
+        for (int u = 2; u < U; ++u) c[u] = (u < kmax) ? ld_list(e + 32 * u) : 0xFFFFFFFFu;
 #pragma unroll 1
         for (int k = 0; k < kmax; k += U) {
             Rec<NG> r[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) r[u] = load_rec<NG>(c[u], rec);
 #pragma unroll
-            for (int u = 0; u < U; ++u) c[u] = (k + U + u < kmax) ? __ldg(e + 32 * (k + U + u)) : 0xFFFFFFFFu;
+            for (int u = 0; u < U; ++u) c[u] = (k + U + u < kmax) ? ld_list(e + 32 * (k + U + u)) : 0xFFFFFFFFu;
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (r[u].valid) item.add(r[u]);
@@ -403,8 +551,8 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
 #pragma unroll 1
         for (int k = 0; k < kmax; k += 2) {
             const Rec<NG> r0 = load_rec<NG>(c0, rec), r1 = load_rec<NG>(c1, rec);
-            c0 = (k + 2 < kmax) ? __ldg(e + 32 * (k + 2)) : 0xFFFFFFFFu;
-            c1 = (k + 3 < kmax) ? __ldg(e + 32 * (k + 3)) : 0xFFFFFFFFu;
+            c0 = (k + 2 < kmax) ? ld_list(e + 32 * (k + 2)) : 0xFFFFFFFFu;
+            c1 = (k + 3 < kmax) ? ld_list(e + 32 * (k + 3)) : 0xFFFFFFFFu;
             if (r0.valid) item.add(r0);
             if (r1.valid) item.add(r1);
         }
@@ -413,7 +561,7 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
         for (int k = 0; k < kmax; ++k) {
             const Rec<NG> r0 = load_rec<NG>(c0, rec);
             c0 = c1;
-            c1 = (k + 2 < kmax) ? __ldg(e + 32 * (k + 2)) : 0xFFFFFFFFu;
+            c1 = (k + 2 < kmax) ? ld_list(e + 32 * (k + 2)) : 0xFFFFFFFFu;
             if (r0.valid) item.add(r0);
         }
     }
@@ -472,33 +620,50 @@ __global__ void __launch_bounds__(THREADS, 1)
     int4 th = none, th1 = none;
     {
         const int t0 = grab();
-        if (t0 < task_end) th = __ldg(task_hdr + t0);
+        if (t0 < task_end) th = ld_list(task_hdr + t0);
         const int t1 = grab();
-        if (t1 < task_end) th1 = __ldg(task_hdr + t1);
+        if (t1 < task_end) th1 = ld_list(task_hdr + t1);
     }
     uint32_t c0 = 0xFFFFFFFFu, c1 = 0xFFFFFFFFu;
     if (th.w != -1) {
         const uint32_t *e = ell + (uint32_t)th.y + lane;
-        c0 = __ldg(e);
-        if (((th.x >> 8) & 0xFF) > 1) c1 = __ldg(e + 32);
+        c0 = ld_list(e);
+        if (((th.x >> 8) & 0xFF) > 1) c1 = ld_list(e + 32);
     }
     while (th.w != -1) {
         int4 th2 = none;
         {
             const int t2 = grab();
-            if (t2 < task_end) th2 = __ldg(task_hdr + t2);
+            if (t2 < task_end) th2 = ld_list(task_hdr + t2);
         }
         uint32_t n0 = 0xFFFFFFFFu, n1 = 0xFFFFFFFFu;  // first entries of task i+1
         if (th1.w != -1) {
             const uint32_t *e1 = ell + (uint32_t)th1.y + lane;
-            n0 = __ldg(e1);
-            if (((th1.x >> 8) & 0xFF) > 1) n1 = __ldg(e1 + 32);
+            n0 = ld_list(e1);
+            const int kmax1 = (th1.x >> 8) & 0xFF;
+            if (kmax1 > 1) n1 = ld_list(e1 + 32);
+#if NFA_P2_PF_ELL
+            // the rest of task i+1's ELL lines (one 128-byte line per entry index): a lane prefetches line `lane`, so that
+            // the later rounds of a long item find their entries in cache instead of waiting for a DRAM miss each
+            for (int k = 2 + lane; k < kmax1; k += 32) {
+                const uint32_t *pl = ell + (uint32_t)th1.y + 32 * k;
+#if NFA_P2_PF_ELL == 2
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pl));
+#else
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+#endif
+            }
+#endif
+#if NFA_P2_PF_IH
+            // task i+1's item headers (32 x 8 bytes = two lines): lanes 0 and 16 pull them into L1
+            if ((lane & 15) == 0 && lane < (th1.w & 63)) asm volatile("prefetch.global.L1 [%0];" ::"l"(item_hdr + th1.z + lane));
+#endif
         }
         {
             const int type = th.x & 0xFF, kmax = (th.x >> 8) & 0xFF, n_items = th.w & 63, c = (int)((unsigned)th.w >> 6);
             const uint32_t *e = ell + (uint32_t)th.y + lane;
             uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
-            if (lane < n_items) ih = __ldg(item_hdr + th.z + lane);
+            if (lane < n_items) ih = ld_list(item_hdr + th.z + lane);
             const int it = c - c_begin_r, b = it % NBUF;
             // the tile sits on the same 16-byte phase as its image in vals (parity of the chunk's first block)
             double *tile = smem + (size_t)b * tile_stride + ((th.x >> 16) & 1);
@@ -529,9 +694,16 @@ __global__ void __launch_bounds__(THREADS, 1)
                 double *dst = vals + (int64_t)9 * b0;
                 if (n_bulk > 0) {
                     const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile + head);
+#if (NFA_P2_L2HINT & 2)
+                    const uint64_t pol = l2_policy_evict_first();  // the values are not read again by this kernel
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + head),
+                                 "r"(src), "r"(n_bulk * 8), "l"(pol)
+                                 : "memory");
+#else
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head),
                                  "r"(src), "r"(n_bulk * 8)
                                  : "memory");
+#endif
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if (head) dst[0] = tile[0];
@@ -960,7 +1132,7 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     const bool cr = (ls == 0 && ms == 0);
     int threads = P2_THREADS;  // 512 (128 registers): more warps spill and lose (1.5 ms), see DESIGN.md
     if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
-    if (threads > 512) threads = 512;  // a staged-kernel setting; this kernel needs 128 registers per thread
+    if (threads > 640) threads = 512;  // larger counts are staged-kernel settings
     using kern_t = void (*)(int, int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
                             const int32_t *, const int32_t *, double *);
     kern_t kern = nullptr;
@@ -968,10 +1140,10 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
 #define NFA_P2_PICK(CRV, TH)                                                      \
     if (cr == CRV && threads == TH)                                               \
         kern = nb4 ? p2tet_elasticity_kernel<CRV, TH, 4> : p2tet_elasticity_kernel<CRV, TH, 0>;
-    NFA_P2_PICK(false, 384) NFA_P2_PICK(false, 448) NFA_P2_PICK(false, 512)
-    NFA_P2_PICK(true, 384) NFA_P2_PICK(true, 448) NFA_P2_PICK(true, 512)
+    NFA_P2_PICK(false, 384) NFA_P2_PICK(false, 448) NFA_P2_PICK(false, 512) NFA_P2_PICK(false, 576) NFA_P2_PICK(false, 640)
+    NFA_P2_PICK(true, 384) NFA_P2_PICK(true, 448) NFA_P2_PICK(true, 512) NFA_P2_PICK(true, 576) NFA_P2_PICK(true, 640)
 #undef NFA_P2_PICK
-    if (!kern) return fail("nfa_assemble_p2tet_elasticity: NFA_P2TET_THREADS must be 384, 448 or 512");
+    if (!kern) return fail("nfa_assemble_p2tet_elasticity: NFA_P2TET_THREADS must be 384, 448, 512, 576 or 640");
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, device = 0, n_sm = 148;
     NFA_CUDA(cudaGetDevice(&device));

@@ -97,17 +97,16 @@ def test_oracle_reproduces_golden_elasticity_fixture():
     space.build_structures({"u": [1]}, {"u": [2, 3, 4, 5, 6, 7]})
     z = np.load(GOLDEN + "/le_p2_ex3_3d_l0.npz")
     us = space.discrete_spaces["u"]
-    # the first 25 cells + all boundary facets are re-evaluated and compared entry by entry through the scatter
-    n = space.n_dof
-    res, jac = np.zeros(n), ref_assembly.DokMatrix(n)
-    for i in range(25):
-        ref_assembly.scatter_form(space, ref_forms.le_primal, LE_FUNCTIONS, i, res, jac, np.zeros(n))
-    indptr, indices, data = jac.getValuesCSR()
-    G = sp.csr_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
-    # pattern of the partial assembly is contained in the golden pattern
-    P = sp.csr_matrix((np.ones_like(data), indices, indptr), shape=(n, n))
-    assert (P.multiply(G != 0) != P).nnz == 0 or True
-    assert z["indptr"].dtype == np.int32 and len(z["rhs"]) == n
+    # the whole fixture (298 tets + every boundary facet) is re-assembled cell by cell and must reproduce the committed
+    # CSR bit for bit: pattern, values and right-hand side
+    forms = [
+        ("form", ref_forms.le_primal, LE_FUNCTIONS, len(us.element_ids)),
+        ("bc_form", ref_forms.le_primal_bc_dirichlet, LE_BC_FUNCTIONS, len(us.bc_element_ids)),
+    ]
+    indptr, indices, data, rhs = ref_assembly.assemble(space, forms)
+    assert z["indptr"].dtype == np.int32 and len(z["rhs"]) == space.n_dof
+    assert np.array_equal(indptr, z["indptr"]) and np.array_equal(indices, z["indices"])
+    assert np.array_equal(data, z["data"]) and np.array_equal(rhs, z["rhs"])
     assert len(us.bc_element_ids) > 0
 
 
