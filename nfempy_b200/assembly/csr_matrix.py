@@ -22,6 +22,10 @@ class CSRMatrix:
         self._indptr = None
         self._indices = None
         self.is_zero = True
+        # True: getValuesCSR() returns a view of ONE pinned host buffer that the next call overwrites (a solver loop that
+        # consumes the arrays before reassembling); False (PETSc's behaviour): a fresh array per call
+        self.reuse_host_buffer = False
+        self._values_host = None
 
     # -- filled by the assembler -------------------------------------------------------------------
     def bind_pattern(self, plan_key, n_dof, indptr_dev, indices_dev):
@@ -29,6 +33,7 @@ class CSRMatrix:
         self.n = n_dof
         self.indptr_dev, self.indices_dev = indptr_dev, indices_dev
         self._indptr = self._indices = None
+        self._values_host = None
         self.values_dev = torch.zeros(indices_dev.shape[0], dtype=torch.float64, device=indices_dev.device)
         self.is_zero = True
 
@@ -79,7 +84,12 @@ class CSRMatrix:
         if self._indptr is None:
             self._indptr = self.indptr_dev.cpu().numpy()
             self._indices = self.indices_dev.cpu().numpy()
-        return self._indptr, self._indices, self.values_dev.cpu().numpy()
+        if not self.reuse_host_buffer:
+            return self._indptr, self._indices, self.values_dev.cpu().numpy()
+        if self._values_host is None or self._values_host.shape != self.values_dev.shape:
+            self._values_host = torch.empty(self.values_dev.shape, dtype=torch.float64).pin_memory()
+        self._values_host.copy_(self.values_dev, non_blocking=False)
+        return self._indptr, self._indices, self._values_host.numpy()
 
     def createVecLeft(self):
         return _Vec(self.n)

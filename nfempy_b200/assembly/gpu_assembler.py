@@ -73,13 +73,21 @@ class _Plan:
 
 class GPUAssembler:
     def __init__(self, space, jacobian=None, residual=None, device=None, allow_fused=True, pattern_policy="full",
-                 explicit_diagonal=False):
+                 explicit_diagonal=False, cache_coefficients=True):
         """``pattern_policy``: "full" = every ``n_loc^2`` pair of every element, exact zeros kept (the library
         scatter, R/src/assembly/ScatterFormData.py:5-11); "filtered" = only entries with
         ``~np.isclose(value, 1e-16)``; "filtered_upper" = additionally ``row <= col`` (PETSc "sbaij" storage) -- the
         inline closures of the example drivers (R/examples/cauchy_elasticity/cg_elasticity_example_1.py:92-145,
         R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py:150-243).  ``explicit_diagonal`` adds a
-        stored ``(i, i, 0.0)`` for every local dof of the volume forms (``:110-111`` / ``:175-176``)."""
+        stored ``(i, i, 0.0)`` for every local dof of the volume forms (``:110-111`` / ``:175-176``).
+
+        ``cache_coefficients``: the reference evaluates ``form.functions[name](x, y, z)`` inside every ``evaluate_form``
+        call; here the callables are evaluated over all quadrature points once per (form, sequence, functions, t) and the
+        device arrays are kept across ``scatter_forms()`` calls -- a Newton / time loop written the reference's way
+        (R/examples/geothermal_flow/three_fields_advection_diffusion.py:397-431) then only uploads the state vectors.
+        The cache is keyed on the IDENTITY of the form, of its ``functions`` dictionary and of every callable in it
+        (numbers by value) and on ``t``: rebind ``form.functions`` (or an entry) to change a coefficient, or call
+        ``invalidate()``; closures that read mutable globals need ``cache_coefficients=False``."""
         if pattern_policy not in ("full", "filtered", "filtered_upper"):
             raise ValueError("GPUAssembler: unknown pattern policy %r" % (pattern_policy,))
         self.pattern_policy = pattern_policy
@@ -92,6 +100,15 @@ class GPUAssembler:
         self._form_to_input_list = None
         self._plans = {}
         self.last_timings = {}
+        self.cache_coefficients = bool(cache_coefficients)
+        self._entry_cache = []  # [(signature, FormData, dest)] most recent last
+        self._rhs_dev = None
+        self._rhs_host = None
+        self._capturing = False
+
+    def invalidate(self):
+        """Drops the cached coefficient arrays (the sparsity plans stay)."""
+        self._entry_cache = []
 
     @property
     def form_to_input_list(self):
@@ -235,24 +252,78 @@ class GPUAssembler:
         p.p2_stats = {k: v for k, v in items.items() if isinstance(v, int)}
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _signature(kind, items, form, t):
+        fns = form.functions
+        vals = tuple(fns.values()) if isinstance(fns, dict) else ()
+        return (kind, form, None if items is None else items.tobytes(), fns, vals, t)
+
+    @staticmethod
+    def _same_signature(a, b):
+        if a[0] != b[0] or a[1] is not b[1] or a[2] != b[2] or a[3] is not b[3] or len(a[4]) != len(b[4]):
+            return False
+        for u, v in zip(a[4], b[4]):
+            if u is v:
+                continue
+            if callable(u) or callable(v) or type(u) is not type(v):
+                return False
+            try:
+                if not bool(np.all(u == v)):
+                    return False
+            except Exception:
+                return False
+        return a[5] == b[5]
+
+    def _entry_data(self, dev, kind, items, form, t):
+        """``(FormData, dest)`` of one entry: from the cache when form / sequence / functions / t are the ones seen
+        before, else evaluated (``form.prepare``: host callables over all quadrature points, upload)."""
+        sig = self._signature(kind, items, form, t)
+        previous = None
+        if self.cache_coefficients:
+            for k, (old, data, dest) in enumerate(self._entry_cache):
+                if data.device_key == (dev.device, id(dev)) and self._same_signature(old, sig):
+                    self._entry_cache.append(self._entry_cache.pop(k))
+                    return data, dest
+            for old, data, dest in reversed(self._entry_cache):  # same entry at another time: geometry / tables reusable
+                if data.device_key == (dev.device, id(dev)) and self._same_signature(old[:5] + (t,), sig):
+                    previous = (data, dest)
+                    break
+        if "time_dependent" in kind:
+            data = form.prepare(dev, items, t=t, reuse=previous[0]) if previous and getattr(form, "supports_reuse", False) \
+                else form.prepare(dev, items, t=t)
+        else:
+            data = form.prepare(dev, items)
+        dest = previous[1] if previous else self._dest_dev(dev, form, items)
+        data.device_key = (dev.device, id(dev))
+        data.alpha_dev = None
+        data.alpha_zero = True
+        if self.cache_coefficients:
+            self._entry_cache.append((sig, data, dest))
+            if len(self._entry_cache) > 16:
+                self._entry_cache.pop(0)
+        return data, dest
+
     def prepare(self):
-        """Evaluates the coefficient callables, uploads them and builds (or fetches) the sparsity plan.
-        Returns the state ``run`` consumes; split out so that repeated assemblies reuse it."""
+        """Evaluates the coefficient callables (or fetches their cached device arrays), uploads the state vectors and
+        builds (or fetches) the sparsity plan.  Returns the state ``run`` consumes."""
         dev = space_device(self.space, self.device)
         entries = self._entries()
-        datas = [
-            form.prepare(dev, items, t=al[1]) if "time_dependent" in kind else form.prepare(dev, items)
-            for (_, kind, items, form, al) in entries
-        ]
-        dests = [self._dest_dev(dev, form, items) for (_, _, items, form, _) in entries]
-        # state vectors are scanned for zeros and uploaded here, once per prepare(): on a 4 M-dof problem that host work
-        # takes longer than the device needs for a whole assembly, so run(state) must not repeat it
+        datas, dests = [], []
+        for (_, kind, items, form, al) in entries:
+            data, dest = self._entry_data(dev, kind, items, form, al[1] if "time_dependent" in kind else None)
+            datas.append(data)
+            dests.append(dest)
+        # state vectors: one persistent device buffer per entry, refreshed in place on every call (a captured graph
+        # reads the same buffers); ``alpha_zero`` lets eager runs skip the K.alpha terms of an all-zero vector
         for (_, kind, _, _, alpha), data in zip(entries, datas):
             if "time_dependent" in kind:
                 (first, second), _t = alpha
-                data.alpha_dev = (self._upload(dev, first), self._upload(dev, second) if kind == "time_dependent_form" else None)
+                a0, z0 = self._upload(dev, first, data.alpha_dev[0] if data.alpha_dev else None)
+                a1, z1 = (self._upload(dev, second, data.alpha_dev[1] if data.alpha_dev else None)
+                          if kind == "time_dependent_form" else (None, True))
+                data.alpha_dev, data.alpha_zero = (a0, a1), (z0 and z1)
             else:
-                data.alpha_dev = self._upload(dev, alpha)
+                data.alpha_dev, data.alpha_zero = self._upload(dev, alpha, data.alpha_dev)
         fused_index = None
         if self.pattern_policy != "full":
             return dev, entries, datas, dests, None, None  # the pattern depends on the values: built in run()
@@ -268,10 +339,17 @@ class GPUAssembler:
         return dev, entries, datas, dests, plan, key
 
     @staticmethod
-    def _upload(dev, vec):
-        if vec is None or not np.any(np.asarray(vec) != 0.0):
-            return None
-        return torch.as_tensor(np.ascontiguousarray(vec, dtype=np.float64)).to(dev.device)
+    def _upload(dev, vec, buf=None):
+        """``(device buffer, is_zero)`` of a state vector; ``None`` stays ``None`` (the form then has no state at all).
+        The buffer is allocated once and refreshed in place."""
+        if vec is None:
+            return None, True
+        host = np.ascontiguousarray(vec, dtype=np.float64).reshape(-1)
+        src = torch.from_numpy(host)
+        if buf is None or buf.shape != src.shape:
+            buf = torch.empty(src.shape, dtype=torch.float64, device=dev.device)
+        buf.copy_(src, non_blocking=False)
+        return buf, not bool(host.any())
 
     def run(self, state, rhs_dev=None):
         """Launches the kernels of one assembly.  Adds into ``self.jacobian`` and returns the device residual."""
@@ -299,7 +377,9 @@ class GPUAssembler:
                 Ke_list[i], re_list[i] = Ke, re
                 keep += [Ke, re, first_dev, second_dev]
                 continue
-            alpha_dev = data.alpha_dev
+            # an all-zero state vector skips the K.alpha terms in eager runs; a captured graph always carries them (the
+            # replayed kernels read the persistent buffer, whatever it holds by then)
+            alpha_dev = data.alpha_dev if (self._capturing or not data.alpha_zero) else None
             if i == plan.fused_index:
                 spec = form.fused_spec(data)
                 target = jac.values_dev if jac.is_zero else torch.empty_like(jac.values_dev)
@@ -344,8 +424,10 @@ class GPUAssembler:
     def capture(self, state, rhs_dev):
         """CUDA graph of one fresh assembly (``rhs_dev`` zeroed, every CSR value overwritten) on the buffers of ``state``:
         ``graph.replay()`` re-runs the kernels without the per-launch host work -- for time / Newton loops that
-        reassemble on one plan (the state vectors captured are the device copies made by ``prepare()``; refresh them
-        in place with ``data.alpha_dev.copy_(...)`` between replays).  Full pattern policy only."""
+        reassemble on one plan.  Every entry listed with a state vector (``alpha`` not ``None``) keeps its state terms
+        in the graph even when the vector is all zero at capture time: the kernels read the persistent device buffers
+        ``data.alpha_dev`` of ``state[2]``, which ``prepare()`` refreshes in place (or ``data.alpha_dev.copy_(...)``).
+        List ``alpha=None`` for a form whose state is identically zero to leave those terms out.  Full pattern policy only."""
         if state[4] is None:
             raise _lib.NfaError("GPUAssembler.capture: value-dependent pattern policies rebuild the plan every assembly")
         dev = state[0]
@@ -353,7 +435,11 @@ class GPUAssembler:
         def body():
             self.jacobian.is_zero = True
             rhs_dev.zero_()
-            self.run(state, rhs_dev)
+            self._capturing = True
+            try:
+                self.run(state, rhs_dev)
+            finally:
+                self._capturing = False
 
         body()  # binds the pattern, allocates the values
         cur = torch.cuda.current_stream(dev.device)
@@ -386,7 +472,7 @@ class GPUAssembler:
         for (_, kind, _, form, alpha), data, dest in zip(entries, datas, dests):
             if "time_dependent" in kind:
                 raise NotImplementedError("GPUAssembler: filtered patterns are implemented for form / bc_form lists")
-            alpha_dev = data.alpha_dev
+            alpha_dev = None if data.alpha_zero else data.alpha_dev
             Ke, re = form.local_blocks(dev, data, alpha_dev, dest if alpha_dev is not None else None)
             value_kept = (Ke - 1.0e-16).abs() > tol
             mask = value_kept.clone()
@@ -431,11 +517,21 @@ class GPUAssembler:
         return rhs_dev
 
     def scatter_forms(self, measure_time_q=False):
+        """The reference's call (R/src/assembly/SequentialAssembler.py:69-86): adds every listed form into ``jacobian`` and
+        ``residual``.  From the second call on the coefficient arrays, destination tables and the plan come from the
+        caches; only the state vectors go up and the residual comes down."""
         t0 = time.perf_counter()
         state = self.prepare()
         t1 = time.perf_counter()
-        rhs_dev = self.run(state)
-        rhs = rhs_dev.cpu().numpy()
+        dev = state[0]
+        n_dof = int(self.space.n_dof)
+        if self._rhs_dev is None or self._rhs_dev.shape[0] != n_dof or self._rhs_dev.device != dev.device:
+            self._rhs_dev = torch.empty(n_dof, dtype=torch.float64, device=dev.device)
+            self._rhs_host = torch.empty(n_dof, dtype=torch.float64).pin_memory()
+        self._rhs_dev.zero_()
+        rhs_dev = self.run(state, self._rhs_dev)
+        self._rhs_host.copy_(rhs_dev, non_blocking=False)
+        rhs = self._rhs_host.numpy()
         t2 = time.perf_counter()
         if self.residual is None:
             self.residual = np.zeros(len(rhs))

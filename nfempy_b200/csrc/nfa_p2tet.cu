@@ -52,6 +52,22 @@ constexpr int P2_THREADS = NFA_P2_THREADS;
 #ifndef NFA_P2_E2
 #define NFA_P2_E2 1
 #endif
+//   NFA_P2_DEEP    1: task headers run three tasks ahead and the ELL lines + item headers of task i+2 are prefetched into
+//                  L2, so that the first entries of task i+1 (loaded while task i computes) are L2 hits, not DRAM misses
+//   NFA_P2_RELAXED 1: the per-task decrement of the tile's task counter is a relaxed shared-memory atomic; the warp that
+//                  takes the counter to zero issues the acquire fence.  (The acq_rel form made every task wait for all of
+//                  its outstanding global loads -- the look-ahead loads of the next tasks -- before it could retire.)
+//   NFA_P2_GRAB2   1: the ticket of the task counter is taken one iteration before it is used (the shared-memory atomic's
+//                  round trip hides behind a task instead of stalling the top of the loop)
+#ifndef NFA_P2_DEEP
+#define NFA_P2_DEEP 0  // measured: 0.872 ms against 0.845 -- three claimed tasks per warp overrun the four-tile window
+#endif
+#ifndef NFA_P2_GRAB2
+#define NFA_P2_GRAB2 0  // measured: 0.870 ms against 0.845 (same reason: one more claimed task per warp)
+#endif
+#ifndef NFA_P2_RELAXED
+#define NFA_P2_RELAXED 1
+#endif
 #ifndef NFA_P2_UA
 #define NFA_P2_UA 8  // cells in flight, vertex-diagonal items (3 or more: the general loop)
 #endif
@@ -618,12 +634,30 @@ __global__ void __launch_bounds__(THREADS, 1)
         return __shfl_sync(0xffffffffu, t, 0);
     };
     int4 th = none, th1 = none;
+#if NFA_P2_DEEP
+    int4 th2 = none;
+#endif
     {
         const int t0 = grab();
         if (t0 < task_end) th = ld_list(task_hdr + t0);
         const int t1 = grab();
         if (t1 < task_end) th1 = ld_list(task_hdr + t1);
+#if NFA_P2_DEEP
+        const int t2 = grab();
+        if (t2 < task_end) th2 = ld_list(task_hdr + t2);
+#endif
     }
+#if NFA_P2_GRAB2
+    int t_pending = 0;  // lane 0: the ticket taken for the NEXT iteration
+    if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t_pending) : "r"(ctrl_s) : "memory");
+    auto grab_ahead = [&]() {
+        const int t = __shfl_sync(0xffffffffu, t_pending, 0);
+        if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(t_pending) : "r"(ctrl_s) : "memory");
+        return t;
+    };
+#else
+    auto grab_ahead = grab;
+#endif
     uint32_t c0 = 0xFFFFFFFFu, c1 = 0xFFFFFFFFu;
     if (th.w != -1) {
         const uint32_t *e = ell + (uint32_t)th.y + lane;
@@ -631,18 +665,31 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (((th.x >> 8) & 0xFF) > 1) c1 = ld_list(e + 32);
     }
     while (th.w != -1) {
+#if NFA_P2_DEEP
+        int4 th3 = none;
+        {
+            const int t3 = grab_ahead();
+            if (t3 < task_end) th3 = ld_list(task_hdr + t3);
+        }
+        if (th2.w != -1) {  // task i+2: its ELL lines (a lane per line) and item headers go to L2
+            const int kmax2 = (th2.x >> 8) & 0xFF;
+            for (int k = lane; k < kmax2; k += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ell + (uint32_t)th2.y + 32 * k));
+            if ((lane & 15) == 0 && lane < (th2.w & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(item_hdr + th2.z + lane));
+        }
+#else
         int4 th2 = none;
         {
-            const int t2 = grab();
+            const int t2 = grab_ahead();
             if (t2 < task_end) th2 = ld_list(task_hdr + t2);
         }
+#endif
         uint32_t n0 = 0xFFFFFFFFu, n1 = 0xFFFFFFFFu;  // first entries of task i+1
         if (th1.w != -1) {
             const uint32_t *e1 = ell + (uint32_t)th1.y + lane;
             n0 = ld_list(e1);
             const int kmax1 = (th1.x >> 8) & 0xFF;
             if (kmax1 > 1) n1 = ld_list(e1 + 32);
-#if NFA_P2_PF_ELL
+#if NFA_P2_PF_ELL && !NFA_P2_DEEP
             // the rest of task i+1's ELL lines (one 128-byte line per entry index): a lane prefetches line `lane`, so that
             // the later rounds of a long item find their entries in cache instead of waiting for a DRAM miss each
             for (int k = 2 + lane; k < kmax1; k += 32) {
@@ -684,8 +731,17 @@ __global__ void __launch_bounds__(THREADS, 1)
             const int it = c - c_begin_r, b = it % NBUF;
             // release of this task's tile stores / acquire of the other tasks' in one acq_rel atomic (no separate MEMBAR)
             int left;
+#if NFA_P2_RELAXED
+            // the task's tile stores and this decrement pass through the SM's shared-memory pipe in program order; the warp
+            // that sees the count reach zero fences before it hands the tile to the copy engine
+            asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], -1;" : "=r"(left) : "r"(ctrl_s + 4u * (4u + (unsigned)b)) : "memory");
+#else
             asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], -1;" : "=r"(left) : "r"(ctrl_s + 4u * (4u + (unsigned)b)) : "memory");
+#endif
             if (left == 1) {  // the chunk's last task: the tile is complete
+#if NFA_P2_RELAXED
+                asm volatile("fence.acq_rel.cta;" ::: "memory");
+#endif
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 const int4 ch = __ldg(chunk_hdr + c);
                 const int b0 = ch.x, n_vals = 9 * ch.y, head = b0 & 1;
@@ -716,6 +772,9 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         th = th1;
         th1 = th2;
+#if NFA_P2_DEEP
+        th2 = th3;
+#endif
         c0 = n0;
         c1 = n1;
     }

@@ -44,8 +44,29 @@ class SundusDualWeakForm(BatchedWeakForm):
     def dest_table(self):
         return self.space.destination_table()
 
-    def prepare(self, dev, items=None, arrays=None, t=0.0):
+    supports_reuse = True
+
+    def prepare(self, dev, items=None, arrays=None, t=0.0, reuse=None):
+        """``reuse``: the ``FormData`` of the same form / sequence / functions at another time -- tables, connectivity, the
+        mapped quadrature points and the time-independent coefficients are taken from it and only the loads
+        ``rhs_f(x, y, z, t)``, ``rhs_r(x, y, z, t)`` are evaluated again (the time loop of
+        R/examples/parabolic_diffusive_problem: one ``scatter_forms`` per Newton iteration, t fixed within a step)."""
         self._check()
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev.device)
+
+        def loads_at(x):
+            out = {}
+            for name in ("rhs_f", "rhs_r"):
+                f = coefficients.evaluate(self.functions[name], x, 1, extra=(t,))[:, :, 0]
+                out[name] = up(f) if np.any(f) else None
+            return out
+
+        if reuse is not None:
+            data = FormData(**reuse.__dict__)
+            data.loads = loads_at(reuse.x_host)
+            data.t = t
+            data.delta_t = float(self.functions["delta_t"])
+            return data
         mp, p, ref, dim, nfd = _tables(self.space)
         points, weights = self.space.quadrature[dim]
         key = ("sundus", mp.family, mp.k_order, p.k_order, dim, len(weights))
@@ -60,19 +81,14 @@ class SundusDualWeakForm(BatchedWeakForm):
         cell_nodes = take_rows(dev.cell_nodes("mp"), items)
         n = int(cell_nodes.shape[0])
         x = coefficients.physical_points(dev, dim, points, cell_nodes)
-        up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev.device)
         coefs = {}
         for name in ("kappa", "delta", "eta"):
             arr, sc, sq, kind = coefficients.classify(coefficients.evaluate(self.functions[name], x))
             coefs[name] = (up(arr), sc, sq, kind)
-        loads = {}
-        for name in ("rhs_f", "rhs_r"):
-            f = coefficients.evaluate(self.functions[name], x, 1, extra=(t,))[:, :, 0]
-            loads[name] = up(f) if np.any(f) else None
         return FormData(
             n_items=n, items=items, dim=dim, n_q=len(weights), n_u=ref.n_phi, n_p=p.ref_element.n_phi, nfd=nfd,
             u_val=u_val, u_div=u_div, p_val=p_val, w=w, tcases=tcases, cases=cases, cell_nodes=cell_nodes, coefs=coefs,
-            loads=loads, delta_t=float(self.functions["delta_t"]), t=t,
+            loads=loads_at(x), delta_t=float(self.functions["delta_t"]), t=t, x_host=x,
         )
 
     def launch_local(self, dev, data, alpha_dev, dest_dev, Ke, re, alpha_prev_dev=None):

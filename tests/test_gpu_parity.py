@@ -154,3 +154,84 @@ def test_example_driver_scatter_policy_primal_elasticity():
     got = case.run_gpu(pattern_policy="filtered_upper", explicit_diagonal=True)
     ref = case.run_oracle(upper=True, explicit_diagonal=True)
     compare_csr(got, ref, RTOL)
+
+
+def test_scatter_forms_reuses_cached_coefficients_and_tracks_the_state_vector():
+    """Second and later ``scatter_forms()`` calls (a Newton loop written the reference's way,
+    R/examples/geothermal_flow/three_fields_advection_diffusion.py:397-431) reuse the evaluated coefficient arrays and the
+    plan, only refresh the state vector, and give the same system as a fresh assembler; rebinding ``functions`` is seen."""
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.weak_forms import LEPrimalWeakForm
+
+    case = elasticity_case(n=2, with_bc=True, alpha=True)
+    space = case.space()
+    n = space.n_dof
+    rng = np.random.default_rng(3)
+    calls = {"n": 0}
+
+    def lam(x, y, z):
+        calls["n"] += 1
+        return 2.0 * np.ones_like(x)
+
+    form = LEPrimalWeakForm(space)
+    form.functions = {"rhs": lambda x, y, z: np.array([x, y * z, 1.0 + 0 * x]), "lambda": lam, "mu": lambda x, y, z: np.ones_like(x)}
+    n_cells = len(space.discrete_spaces["u"].elements)
+
+    def fresh(alpha, functions):
+        f2 = LEPrimalWeakForm(space)
+        f2.functions = functions
+        a2 = GPUAssembler(space, None, np.zeros(n), cache_coefficients=False)
+        a2.form_to_input_list = {"v": ["form", range(n_cells), f2, alpha]}
+        return a2.assemble()
+
+    asm = GPUAssembler(space, None, np.zeros(n))
+    alpha = np.zeros(n)  # first iterate: zero state
+    asm.form_to_input_list = {"v": ["form", range(n_cells), form, alpha]}
+    for it in range(3):
+        asm.jacobian.scale(0.0)
+        asm.residual[:] = 0.0
+        asm.scatter_forms()
+        got = asm.jacobian.getValuesCSR() + (asm.residual.copy(),)
+        ref = fresh(alpha.copy(), form.functions)
+        compare_csr(got, ref, 1e-13)
+        alpha += rng.standard_normal(n)  # mutated in place, like alpha += delta in the reference's loop
+    assert calls["n"] == 1 + 3, "the cached assembler evaluates lambda once (the three fresh ones once each)"
+    # a rebound coefficient is picked up
+    form.functions = dict(form.functions, **{"lambda": lambda x, y, z: 5.0 * np.ones_like(x)})
+    asm.jacobian.scale(0.0)
+    asm.residual[:] = 0.0
+    asm.scatter_forms()
+    compare_csr(asm.jacobian.getValuesCSR() + (asm.residual.copy(),), fresh(alpha.copy(), form.functions), 1e-13)
+
+
+def test_captured_graph_follows_a_state_vector_that_starts_at_zero():
+    """a graph captured while alpha == 0 must still carry the K.alpha term once alpha is refreshed."""
+    import torch
+
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.weak_forms import LEPrimalWeakForm
+
+    case = elasticity_case(n=2, with_bc=False)
+    space = case.space()
+    n = space.n_dof
+    form = LEPrimalWeakForm(space)
+    form.functions = {"rhs": lambda x, y, z: np.array([x, y, z]), "lambda": lambda x, y, z: np.ones_like(x),
+                      "mu": lambda x, y, z: np.ones_like(x)}
+    n_cells = len(space.discrete_spaces["u"].elements)
+    asm = GPUAssembler(space, None, np.zeros(n))
+    alpha = np.zeros(n)
+    asm.form_to_input_list = {"v": ["form", range(n_cells), form, alpha]}
+    state = asm.prepare()
+    rhs = torch.zeros(n, dtype=torch.float64, device=state[0].device)
+    graph = asm.capture(state, rhs)
+    graph.replay()
+    torch.cuda.synchronize()
+    r0 = rhs.cpu().numpy().copy()
+    alpha[:] = np.random.default_rng(1).standard_normal(n)
+    asm.prepare()  # refreshes the persistent device state vector in place
+    graph.replay()
+    torch.cuda.synchronize()
+    r1 = rhs.cpu().numpy()
+    K = asm.jacobian.to_scipy()
+    assert np.abs(r1 - (r0 + K @ alpha)).max() <= 1e-12 * np.abs(r1).max()
+    assert np.abs(r1 - r0).max() > 1e-3
