@@ -126,10 +126,12 @@ def ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Current torch stream of ``device`` (default: the current device).  libnfa launches on the CURRENT CUDA device:
+    callers working on another device wrap their calls in ``torch.cuda.device(device)`` (``GPUAssembler`` does)."""
     import torch
 
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def launch_count():

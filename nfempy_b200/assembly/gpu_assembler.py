@@ -183,9 +183,16 @@ class GPUAssembler:
             form = entries[fused_index][3]
             s = form._field()
             nc = s.n_comp
-            node_dest = (dests[fused_index][:, ::nc] // nc).contiguous()
+            fd = dests[fused_index]
+            node_dest = (fd[:, ::nc] // nc).contiguous()
             if p.n_dof % nc != 0:
                 raise _lib.NfaError("fused path: n_dof is not a multiple of n_comp")
+            # the block path reads dof = node * n_comp + component (R/src/spaces/dof_map.py:68-83: an entity's components
+            # are consecutive); anything else goes through the two-stage path
+            for c in range(nc):
+                if not bool(torch.equal(fd[:, c::nc], fd[:, ::nc] + c)) or int(node_dest.min()) < 0 or \
+                        int(node_dest.max()) >= p.n_dof // nc:
+                    raise _lib.NfaError("fused path: destination table is not node-major / component-minor")
             bh = ctypes.c_void_p()
             _lib.check(
                 lib.nfa_bplan_create(
@@ -307,6 +314,10 @@ class GPUAssembler:
         """Evaluates the coefficient callables (or fetches their cached device arrays), uploads the state vectors and
         builds (or fetches) the sparsity plan.  Returns the state ``run`` consumes."""
         dev = space_device(self.space, self.device)
+        with torch.cuda.device(dev.device):  # libnfa launches on the current device
+            return self._prepare(dev)
+
+    def _prepare(self, dev):
         entries = self._entries()
         datas, dests = [], []
         for (_, kind, items, form, al) in entries:
@@ -334,7 +345,17 @@ class GPUAssembler:
                     break
         key = self._plan_key(entries, fused_index)
         if key not in self._plans:
-            self._plans[key] = self._build_plan(dev, entries, dests, fused_index)
+            try:
+                self._plans[key] = self._build_plan(dev, entries, dests, fused_index)
+            except _lib.NfaError:
+                if fused_index is None:
+                    raise
+                # e.g. a second volume form on other cells couples dofs outside the fused form's pattern: the reference
+                # accepts such lists, so they take the generic two-stage plan instead of failing
+                fused_index = None
+                key = self._plan_key(entries, None)
+                if key not in self._plans:
+                    self._plans[key] = self._build_plan(dev, entries, dests, None)
         plan = self._plans[key]
         return dev, entries, datas, dests, plan, key
 
@@ -353,6 +374,10 @@ class GPUAssembler:
 
     def run(self, state, rhs_dev=None):
         """Launches the kernels of one assembly.  Adds into ``self.jacobian`` and returns the device residual."""
+        with torch.cuda.device(state[0].device):
+            return self._run(state, rhs_dev)
+
+    def _run(self, state, rhs_dev=None):
         dev, entries, datas, dests, plan, key = state
         lib = _lib.load()
         stream = _lib.stream_ptr()
@@ -430,6 +455,10 @@ class GPUAssembler:
         List ``alpha=None`` for a form whose state is identically zero to leave those terms out.  Full pattern policy only."""
         if state[4] is None:
             raise _lib.NfaError("GPUAssembler.capture: value-dependent pattern policies rebuild the plan every assembly")
+        with torch.cuda.device(state[0].device):
+            return self._capture(state, rhs_dev)
+
+    def _capture(self, state, rhs_dev):
         dev = state[0]
 
         def body():

@@ -41,10 +41,16 @@ def _field_errors(dim, fe_space, functions, alpha, skip_fields, divergence):
         off += s.ref_element.n_phi * s.n_comp
     w = up(weights)
     for name, s in fe_space.discrete_spaces.items():
-        if name in skip_fields or s.dimension != dim:
+        if name in skip_fields:
             continue
         vector_family = s.family in ("RT", "BDM")
         if divergence and not vector_family:
+            continue
+        if s.dimension != dim:
+            # the reference sums over the field's elements of dimension `dim` and appends sqrt(0.0) when there are none
+            # (R/src/postprocess/l2_error_post_processor.py:15-19, 61): the list keeps one entry per non-skipped field
+            if not divergence:
+                out.append(0.0)
             continue
         if divergence == "scaled" and (functions.get("l") is None or functions.get("grad_l") is None):
             continue  # the reference skips the field when no scale is given (:296-298)
