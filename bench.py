@@ -107,6 +107,44 @@ def cpu_strong_baseline(space, n_cells_sample, repeats=3):
     return n / best, n, best
 
 
+def parity_check(torch, space, asm, plan, step, n_sample):
+    """The values the timed step produced, checked in the same run: every matrix row whose cells all lie among the first
+    ``n_sample`` tets is compared, entry by entry, with oracle/strong_cpu.py's assembly of those tets on the host (same
+    mesh, same numbering; the strong baseline is itself pinned to the cell-by-cell oracle in the CPU tests)."""
+    from oracle import strong_cpu
+
+    u = space.discrete_spaces["u"]
+    dest = np.asarray(space.destination_table(), dtype=np.int64)
+    n_cells, n_loc = dest.shape
+    m = min(n_sample, n_cells)
+    last = np.full(space.n_dof, -1, dtype=np.int64)
+    last[dest.ravel()] = np.repeat(np.arange(n_cells), n_loc)  # ascending cells: the last writer is the last cell
+    rows = np.flatnonzero((last >= 0) & (last < m))
+    ref_ptr, ref_idx, ref_val = strong_cpu.assemble_elasticity(u.mesh.points, np.asarray(u.cell_nodes()[:m], dtype=np.int64),
+                                                               dest[:m], space.n_dof, 1.0, 1.0)
+    step()
+    torch.cuda.synchronize()
+    indptr = plan.indptr.cpu().numpy().astype(np.int64)
+    lens = indptr[rows + 1] - indptr[rows]
+    if not np.array_equal(lens, ref_ptr[rows + 1].astype(np.int64) - ref_ptr[rows]):
+        return {"rows_checked": int(len(rows)), "pattern_equal": False, "max_rel": None}
+    pos = np.repeat(indptr[rows] - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) + np.arange(int(lens.sum()))
+    rpos = np.repeat(ref_ptr[rows].astype(np.int64) - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) + np.arange(int(lens.sum()))
+    dpos = torch.as_tensor(pos).to(plan.indices.device)
+    got_val = asm.jacobian.values_dev.index_select(0, dpos).cpu().numpy()
+    got_idx = plan.indices.index_select(0, dpos).cpu().numpy()
+    want = ref_val[rpos]
+    row_of = np.repeat(np.arange(len(rows)), lens)
+    row_max = np.zeros(len(rows))
+    np.maximum.at(row_max, row_of, np.abs(want))
+    scale = np.maximum(np.abs(want), row_max[row_of])
+    rel = np.abs(got_val - want) / np.where(scale > 0, scale, 1.0)
+    return {"rows_checked": int(len(rows)), "values_checked": int(len(want)), "sample_cells": int(m),
+            "pattern_equal": bool(np.array_equal(got_idx, ref_idx[rpos])), "max_rel": float(rel.max(initial=0.0)),
+            "against": "oracle/strong_cpu.py (vectorised numpy restatement, pinned to the cell-by-cell oracle)",
+            "tolerance": 1e-12}
+
+
 WORKLOAD = "3D Cauchy linear elasticity, vector H1 p=2, %d tets per GPU (Kuhn box n=%d, jittered), lambda=mu=1, tabulated load, CSR values + rhs"
 
 
@@ -384,6 +422,9 @@ def run_graft(args):
         # host buffers (there is no multi-process form of the reference's API to mirror)
         e2e = run_e2e_api(args, torch, device, space, form, n_cells, asm) if sharded is None else e2e_all
 
+    parity = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        parity = parity_check(torch, space, asm, plan, step, 40000)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cells, wall = cpu_baseline(min(args.n, 12), args.cpu_cells, 1)
@@ -412,7 +453,7 @@ def run_graft(args):
                            ("CUDA graph replay of the local assembly + eager NCCL exchange" if (sharded is not None and not args.no_graph)
                             else "eager launches")),
             },
-            "roofline": roofline, "cpu_baseline": cpu, "cpu_strong": cpu_strong, "e2e": e2e, "e2e_all_inputs": e2e_all, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "cpu_strong": cpu_strong, "e2e": e2e, "e2e_all_inputs": e2e_all, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

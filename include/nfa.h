@@ -280,21 +280,19 @@ int nfa_field_error_scaled(int dim, int kind, int n_phi, int n_comp, int n_q, in
 int nfa_bplan_block_pattern(const nfa_bplan *bp, int32_t *d_bptr, int32_t *d_bcols, nfa_stream stream);
 int64_t nfa_bplan_n_blocks(const nfa_bplan *bp);
 int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *d_chunk_hdr, int64_t n_tasks,
-                           const int32_t *d_task_hdr, int64_t n_items, const uint16_t *d_item_hdr, int64_t ell_size,
-                           const uint32_t *d_ell, int max_tile_blocks, const int32_t *d_chunk_cells_ptr,
-                           int64_t n_chunk_cells, const int32_t *d_chunk_cells, nfa_stream stream);
+                           const int32_t *d_task_hdr, int64_t n_slots, const uint16_t *d_item_hdr, int64_t ell_size,
+                           const uint32_t *d_ell, int max_tile_blocks, nfa_stream stream);
+/* Bank-aware order of the items (= lanes) inside their (chunk, type) groups: d_group_ptr int64 [n_groups + 1] item ranges,
+ * d_hdr6 int32 [n_items][6] = three tile offsets, row pitch, two opposite-edge tile offsets (0xFFFF = unused);
+ * d_perm int64 [n_items] receives the new order (new position -> old index) within every group.  A thread per group deals
+ * the items into half warps whose shared-memory tile stores hit distinct banks (greedy over a window of `window` items). */
+int nfa_p2_lane_order(int64_t n_groups, const int64_t *d_group_ptr, const int32_t *d_hdr6, int window, int64_t *d_perm,
+                      nfa_stream stream);
 int nfa_bplan_has_p2_items(const nfa_bplan *bp);
 /* Optional cell mask of the row-item kernel (uint8 per cell of the plan, device pointer; NULL clears it): cells with
  * mask 0 contribute exact zeros.  The sharded assembler switches off the halo cells of a rank's local plan this way,
  * so that mesh-constant lambda, mu stay single numbers (stride 0) on every rank. */
 int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *d_mask, nfa_stream stream);
-/* Optional lists of the shared-memory staged variant of the same kernel (chunk-relative task headers, ELL entries
- * naming cells by their slot in the chunk's cell list, per-chunk copy extents [ell0, n_ell, item0, n_items] and the
- * per-chunk maxima that size the buffers).  With them nfa_assemble_p2tet_elasticity stages every chunk's inputs in
- * shared memory by bulk copies; without them (or with NFA_P2TET_STAGE=0) it reads them with global loads. */
-int nfa_bplan_set_p2_stage(nfa_bplan *bp, const int32_t *d_chunk_ext, const int32_t *d_task_hdr_rel,
-                           const uint32_t *d_ell_local, int max_chunk_cells, int max_chunk_ell, int max_chunk_items,
-                           int max_chunk_tasks, nfa_stream stream);
 int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *d_coords, const int32_t *d_cell_nodes,
                                   const double *d_lambda, int64_t lambda_stride, const double *d_mu,
                                   int64_t mu_stride, double *d_vals, nfa_stream stream);
@@ -327,6 +325,26 @@ int nfa_local_h1_multifield(int dim, int n_q, int n_phi, int n_loc, int n_crow, 
                             const double *d_load, const double *d_coords, const int32_t *d_cell_nodes,
                             int64_t n_cells, const double *d_alpha, const int32_t *d_dest, double *d_Ke, double *d_re,
                             nfa_stream stream);
+
+/* ---- interface-row exchange over NVLink peer memory (multi-GPU extension; the reference is one process).
+ * nfa_p2p_alloc: cudaMalloc'ed, zeroed area + its 64-byte CUDA IPC handle; nfa_p2p_open maps a peer's area into this
+ * process (peer access enabled lazily); nfa_p2p_close / nfa_p2p_free release them.
+ * nfa_push_rows: the CSR segments of `d_rows` (d_buf_off int64 [n_rows + 1] prefix sums of their lengths) and their
+ * right-hand-side entries are stored into the OWNER's area (d_remote_buf: [segments | rhs entries]) once the owner has
+ * acknowledged the previous payload (d_local_ack, written by the owner); then d_remote_flag receives the epoch.
+ * nfa_pull_add_rows: waits for the flag of the next epoch in its own area, adds the payload to vals / rhs and publishes
+ * the acknowledgement at the sender (d_remote_ack).  d_state: uint64 [2] per (peer, direction) in LOCAL memory, zeroed
+ * once.  All stream-ordered device work (capturable in a CUDA graph); call the pulls in ascending sender rank. */
+int nfa_p2p_alloc(int64_t bytes, void **d_ptr, void *handle64);
+int nfa_p2p_open(const void *handle64, void **d_peer_ptr);
+int nfa_p2p_close(void *d_peer_ptr);
+int nfa_p2p_free(void *d_ptr);
+int nfa_push_rows(const int32_t *d_indptr, const double *d_vals, const double *d_rhs, const int32_t *d_rows,
+                  const int64_t *d_buf_off, int64_t n_rows, double *d_remote_buf, uint64_t *d_remote_flag,
+                  const uint64_t *d_local_ack, uint64_t *d_state, nfa_stream stream);
+int nfa_pull_add_rows(const int32_t *d_indptr, double *d_vals, double *d_rhs, const int32_t *d_rows,
+                      const int64_t *d_buf_off, int64_t n_rows, const double *d_local_buf, const uint64_t *d_local_flag,
+                      uint64_t *d_remote_ack, uint64_t *d_state, nfa_stream stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,12 @@ SIGNATURES = {
     "nfa_csr_spmv": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "nfa_pack_rows": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nfa_unpack_add_rows": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nfa_p2p_alloc": (_i, [_i64, ctypes.POINTER(_vp), _vp]),
+    "nfa_p2p_open": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "nfa_p2p_close": (_i, [_vp]),
+    "nfa_p2p_free": (_i, [_vp]),
+    "nfa_push_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
+    "nfa_pull_add_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_bplan_create": (_i, [_i64, _i, _i, _vp, _i64, ctypes.POINTER(_vp), _vp]),
     "nfa_bplan_destroy": (None, [_vp]),
     "nfa_bplan_nnz": (_i64, [_vp]),
@@ -71,10 +77,10 @@ SIGNATURES = {
                                      _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "nfa_bplan_block_pattern": (_i, [_vp, _vp, _vp, _vp]),
     "nfa_bplan_n_blocks": (_i64, [_vp]),
-    "nfa_bplan_set_p2_items": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _vp, _i64, _vp, _vp]),
+    "nfa_bplan_set_p2_items": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _vp]),
+    "nfa_p2_lane_order": (_i, [_i64, _vp, _vp, _i, _vp, _vp]),
     "nfa_bplan_has_p2_items": (_i, [_vp]),
     "nfa_bplan_set_cell_mask": (_i, [_vp, _vp, _vp]),
-    "nfa_bplan_set_p2_stage": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "nfa_assemble_p2tet_elasticity": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
 }
 

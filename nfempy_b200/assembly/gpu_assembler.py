@@ -233,29 +233,31 @@ class GPUAssembler:
         bcols = torch.empty(n_blocks, dtype=torch.int32, device=dev.device)
         _lib.check(lib.nfa_bplan_block_pattern(p.bplan, _lib.ptr(bptr), _lib.ptr(bcols), stream), "nfa_bplan_block_pattern")
         cap = int(os.environ.get("NFA_P2TET_CAP", "640"))
-        staged = os.environ.get("NFA_P2TET_STAGE", "0") not in ("", "0")  # the opt-in staged kernel needs extra lists
+        lane_optimizer = None
+        if os.environ.get("NFA_P2TET_LANEOPT", "1") != "0":
+            window = int(os.environ.get("NFA_P2TET_LANEWIN", "48"))
+
+            def lane_optimizer(group_ptr, hdr6):
+                # bank-aware lane order inside the (chunk, type) groups: one device thread per group (nfa_p2_lane_order)
+                gp = group_ptr.to(torch.int64).contiguous()
+                h = hdr6.to(torch.int32).contiguous()
+                perm = torch.empty(int(h.shape[0]), dtype=torch.int64, device=h.device)
+                _lib.check(lib.nfa_p2_lane_order(int(gp.shape[0]) - 1, _lib.ptr(gp), _lib.ptr(h), window, _lib.ptr(perm), stream),
+                           "nfa_p2_lane_order")
+                return perm
+
         items = p2_items.build(node_dest.to(torch.int64), bptr.to(torch.int64), bcols.to(torch.int64), n_nodes, cap=cap,
                                riffle=int(os.environ.get("NFA_P2TET_RIFFLE", "148")),
                                batch=int(os.environ.get("NFA_P2TET_BATCH", "8")),
-                               lane_order=os.environ.get("NFA_P2TET_LANES", "cell"), staged=staged)
+                               lane_order=os.environ.get("NFA_P2TET_LANES", "cell"), lane_optimizer=lane_optimizer)
         _lib.check(
             lib.nfa_bplan_set_p2_items(
                 p.bplan, items["n_chunks"], _lib.ptr(items["chunk_hdr"]), items["n_tasks"], _lib.ptr(items["task_hdr"]),
-                items["n_items"], _lib.ptr(items["item_hdr"]), items["ell_size"], _lib.ptr(items["ell"]),
-                items["max_tile_blocks"], _lib.ptr(items["chunk_cells_ptr"]), items["n_chunk_cells"],
-                _lib.ptr(items["chunk_cells"]), stream,
+                items["n_slots"], _lib.ptr(items["item_hdr"]), items["ell_size"], _lib.ptr(items["ell"]),
+                items["max_tile_blocks"], stream,
             ),
             "nfa_bplan_set_p2_items",
         )
-        if staged:
-            _lib.check(
-                lib.nfa_bplan_set_p2_stage(
-                    p.bplan, _lib.ptr(items["chunk_ext"]), _lib.ptr(items["task_hdr_rel"]), _lib.ptr(items["ell_local"]),
-                    items["max_chunk_cells"], items["max_chunk_ell"], items["max_chunk_items"], items["max_chunk_tasks"],
-                    stream,
-                ),
-                "nfa_bplan_set_p2_stage",
-            )
         p.p2_stats = {k: v for k, v in items.items() if isinstance(v, int)}
 
     # ------------------------------------------------------------------------------------------

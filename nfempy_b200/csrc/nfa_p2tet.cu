@@ -10,7 +10,7 @@
 //
 // Work is organised by OUTPUT ROW (no atomics, no staging of contributions): the block row of a node is cut into
 // ITEMS of at most three CSR blocks that receive contributions from exactly the same cells (nfempy_b200/assembly/
-// p2_items.py lists the six item types).  One thread owns one item, walks its cells in ascending cell order -- the
+// p2_items.py lists the five item types).  One thread owns one item, walks its cells in ascending cell order -- the
 // order of the reference's Mat.setValue(..., addv=True) calls, R/src/assembly/ScatterFormData.py:5-11 -- sums in
 // registers and writes every CSR value exactly once into the CTA's shared-memory tile (the CSR image of a run of
 // whole block rows), which leaves for HBM as ONE bulk asynchronous copy (cp.async.bulk shared -> global, TMA engine).
@@ -259,6 +259,7 @@ struct TileCtx {
     volatile int *free_at;
     int need;
     unsigned ihx, ihy;  // packed 16-bit tile offsets of the three blocks and the row pitch (decoded when storing)
+    unsigned ihz;       // type E: tile offsets of the opposite-edge blocks of the item's first / second cell
     __device__ __forceinline__ void wait() const {
         if ((threadIdx.x & 31) == 0) {
             const uint32_t a = (uint32_t)__cvta_generic_to_shared(const_cast<int *>(free_at));
@@ -273,6 +274,9 @@ struct TileCtx {
     }
     __device__ __forceinline__ void put(int k, const double (&v)[9]) const {
         store_block(tile, k == 0 ? (ihx & 0xFFFFu) : (k == 1 ? (ihx >> 16) : (ihy & 0xFFFFu)), ihy >> 16, v);
+    }
+    __device__ __forceinline__ void put_opposite(int cell, const double (&v)[9]) const {
+        store_block(tile, cell == 0 ? (ihz & 0xFFFFu) : (ihz >> 16), ihy >> 16, v);
     }
 };
 
@@ -444,24 +448,6 @@ struct Item<4, CR> {
     }
 };
 
-template <bool CR>
-struct Item<5, CR> {
-    double rho = 0.0;  // F: (E, E_opp) = -2/15 Kf(s s^T), since g_x + g_y = -(g_i + g_j)
-    static constexpr int NG = 2;
-    double q[6] = {0, 0, 0, 0, 0, 0}, tr = 0.0;
-    __device__ __forceinline__ void add(const Rec<NG> &r) {
-        rho = r.g[0].rho;
-        const double s[3] = {r.g[0].x + r.g[1].x, r.g[0].y + r.g[1].y, r.g[0].z + r.g[1].z};
-        tr += add_sym<CR>(q, r.g[0].rho, s);
-    }
-    __device__ __forceinline__ void finish(const TileCtx &ctx) {
-        double o[9];
-        fix_sym<CR>(q, tr, rho);
-        sym_to_full(q, -C15, tr, o);
-        ctx.put(0, o);
-    }
-};
-
 // One task = up to 32 items of one type; lane = item.  e points at the lane's first ELL entry (stride 32); c0, c1 are
 // the lane's first two entries (fetched while the previous task was computed).  Items that read at most two records per
 // cell keep two cells in flight; type E (three records, 27 sums) walks one cell at a time to stay inside the register
@@ -524,6 +510,22 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
 #pragma unroll
             for (int i = 0; i < 9; ++i) k[i] = C15 * (k[i] + ((i % 4 == 0) ? t : 0.0));
             ctx.put(2, k);
+        }
+        // (E, E_opp) of the cells that name this face as their designated one: a single contribution each,
+        // -2/15 Kf(s s^T) with s = g_i + g_j (the opposite edge's g_x + g_y = -s)
+        if ((ctx.ihz & 0xFFFFu) != 0xFFFFu) {
+            double q[6] = {0, 0, 0, 0, 0, 0}, o[9];
+            double t = add_sym<CR>(q, r0.g[0].rho, s0);
+            fix_sym<CR>(q, t, r0.g[0].rho);
+            sym_to_full(q, -C15, t, o);
+            ctx.put_opposite(0, o);
+        }
+        if ((ctx.ihz >> 16) != 0xFFFFu) {
+            double q[6] = {0, 0, 0, 0, 0, 0}, o[9];
+            double t = add_sym<CR>(q, r1.g[0].rho, s1);
+            fix_sym<CR>(q, t, r1.g[0].rho);
+            sym_to_full(q, -C15, t, o);
+            ctx.put_opposite(1, o);
         }
         return;
     }
@@ -594,8 +596,7 @@ template <bool CR, int THREADS, int NB>
 __global__ void __launch_bounds__(THREADS, 1)
     p2tet_elasticity_kernel(int nbuf_rt, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
                             const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
-                            const double *__restrict__ rec, int tile_stride, const int32_t *__restrict__ cells_ptr,
-                            const int32_t *__restrict__ cells, double *__restrict__ vals) {
+                            const double *__restrict__ rec, int tile_stride, double *__restrict__ vals) {
     // NB > 0: the number of tiles is a compile-time power of two, so that the tile of a chunk ((c - c_begin) % NBUF) and its
     // round ((c - c_begin) / NBUF) cost a mask and a shift instead of two integer divisions per task (the task loop's scalar
     // bookkeeping is 40 % of the instructions the kernel executes)
@@ -674,7 +675,9 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (th2.w != -1) {  // task i+2: its ELL lines (a lane per line) and item headers go to L2
             const int kmax2 = (th2.x >> 8) & 0xFF;
             for (int k = lane; k < kmax2; k += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ell + (uint32_t)th2.y + 32 * k));
-            if ((lane & 15) == 0 && lane < (th2.w & 63)) asm volatile("prefetch.global.L2 [%0];" ::"l"(item_hdr + th2.z + lane));
+            const int per2 = ((th2.x & 0xFF) == 4) ? 2 : 1;
+            if ((lane & (15 >> (per2 - 1))) == 0 && lane < (th2.w & 63))
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(item_hdr + th2.z + per2 * lane));
         }
 #else
         int4 th2 = none;
@@ -703,25 +706,37 @@ __global__ void __launch_bounds__(THREADS, 1)
 #endif
 #if NFA_P2_PF_IH
             // task i+1's item headers (32 x 8 bytes = two lines): lanes 0 and 16 pull them into L1
-            if ((lane & 15) == 0 && lane < (th1.w & 63)) asm volatile("prefetch.global.L1 [%0];" ::"l"(item_hdr + th1.z + lane));
+            {
+                const int per1 = ((th1.x & 0xFF) == 4) ? 2 : 1;  // type E items take two 8-byte slots
+                if ((lane & (15 >> (per1 - 1))) == 0 && lane < (th1.w & 63))
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(item_hdr + th1.z + per1 * lane));
+            }
 #endif
         }
         {
             const int type = th.x & 0xFF, kmax = (th.x >> 8) & 0xFF, n_items = th.w & 63, c = (int)((unsigned)th.w >> 6);
             const uint32_t *e = ell + (uint32_t)th.y + lane;
             uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
-            if (lane < n_items) ih = ld_list(item_hdr + th.z + lane);
+            unsigned ihz = 0xFFFFFFFFu;
+            if (lane < n_items) {
+                if (type == 4) {  // two slots per item: blocks + pitch, then the opposite-edge blocks
+                    const uint2 *hp = item_hdr + th.z + 2 * lane;
+                    ih = ld_list(hp);
+                    ihz = ld_list(hp + 1).x;
+                } else {
+                    ih = ld_list(item_hdr + th.z + lane);
+                }
+            }
             const int it = c - c_begin_r, b = it % NBUF;
             // the tile sits on the same 16-byte phase as its image in vals (parity of the chunk's first block)
             double *tile = smem + (size_t)b * tile_stride + ((th.x >> 16) & 1);
-            const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y};
+            const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y, ihz};
             switch (type) {
                 case 0: run_task<0, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
                 case 1: run_task<1, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
                 case 2: run_task<2, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
                 case 3: run_task<3, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                case 4: run_task<4, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                default: run_task<5, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                default: run_task<4, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -782,253 +797,6 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 
-// =====================================================================================================================
-// Staged variant: no global load on the compute path.  Everything a chunk reads -- its ELL entries, item headers, task
-// headers and the 128-byte geometry records of the cells it touches (entries name a cell by its slot in the chunk's
-// cell list) -- is copied into the chunk's shared-memory buffer by bulk asynchronous copies (cp.async.bulk global ->
-// shared, completion counted on the buffer's mbarrier) issued when the buffer is handed over, i.e. NBUF chunks ahead of
-// use.  The warp that retires a chunk sends its tile to HBM, waits until the copy engine has read it and refills the
-// buffer for chunk c + NBUF; the mbarrier phase a task waits for therefore means "tile free and inputs present".
-struct StageLayout {
-    int rec_off, ell_off, item_off, task_off, buf_bytes;  // byte offsets inside a buffer (the tile sits at offset 0)
-};
-
-__device__ __forceinline__ G4 lds_g4(const double *p) {
-    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
-    return G4{a.x, a.y, b.x, b.y};
-}
-
-template <int NG>
-__device__ __forceinline__ Rec<NG> load_rec_s(uint32_t code, const double *rec_s) {
-    Rec<NG> r;
-    r.valid = code != 0xFFFFFFFFu;
-#pragma unroll
-    for (int m = 0; m < NG; ++m) r.g[m] = G4{0.0, 0.0, 0.0, 0.0};
-    if (r.valid) {
-        const double *rc = rec_s + (size_t)(code >> 6) * 16;
-        r.g[0] = lds_g4(rc + 4 * ((code >> 4) & 3u));
-        if constexpr (NG > 1) r.g[1] = lds_g4(rc + 4 * ((code >> 2) & 3u));
-        if constexpr (NG > 2) r.g[2] = lds_g4(rc + 4 * (code & 3u));
-    }
-    return r;
-}
-
-#ifndef NFA_P2S_UA
-#define NFA_P2S_UA 4
-#endif
-#ifndef NFA_P2S_U
-#define NFA_P2S_U 2
-#endif
-
-template <int TYPE, bool CR>
-__device__ __forceinline__ void run_task_s(const uint32_t *e, int kmax, const double *rec_s, const TileCtx &ctx) {
-    constexpr int NG = Item<TYPE, CR>::NG;
-    constexpr int U = (TYPE == 0) ? NFA_P2S_UA : ((TYPE == 4) ? 1 : NFA_P2S_U);
-    Item<TYPE, CR> item;
-#pragma unroll 1
-    for (int k = 0; k < kmax; k += U) {
-        uint32_t c[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) c[u] = (k + u < kmax) ? e[32 * (k + u)] : 0xFFFFFFFFu;
-        Rec<NG> r[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) r[u] = load_rec_s<NG>(c[u], rec_s);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (r[u].valid) item.add(r[u]);
-    }
-    item.finish(ctx);
-}
-
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (uint32_t)__cvta_generic_to_shared(dst)),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-template <bool CR, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1)
-    p2tet_staged_kernel(int NBUF, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ chunk_ext,
-                        const int4 *__restrict__ task_hdr_rel, const uint2 *__restrict__ item_hdr,
-                        const uint32_t *__restrict__ ell_local, const int32_t *__restrict__ cells_ptr,
-                        const int32_t *__restrict__ cells, const double *__restrict__ rec, StageLayout L,
-                        int rec_tma, double *__restrict__ vals) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *ctrl_base = smem_raw + (size_t)NBUF * L.buf_bytes;
-    // ctrl: [0] next task, [1] c_begin, [2] c_end, [3] task_end, [4 .. 4+NBUF) tasks left in the buffer's chunk,
-    // [12 .. 12+NBUF) generation of the buffer = (chunk offset / NBUF) of the chunk it was last handed to.  A task first
-    // waits for its generation (monotonic, so a warp that ran 2 NBUF chunks ahead cannot mistake an older phase of the
-    // mbarrier for its own: the parity alone repeats every two phases), then for the mbarrier phase of that fill.
-    volatile int *ctrl = reinterpret_cast<volatile int *>(ctrl_base);
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(ctrl_base + 128);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        const int c_begin = (int)((int64_t)n_chunks * blockIdx.x / gridDim.x);
-        const int c_end = (int)((int64_t)n_chunks * (blockIdx.x + 1) / gridDim.x);
-        ctrl[1] = c_begin;
-        ctrl[2] = c_end;
-        ctrl[0] = ctrl[3] = 0;
-        if (c_begin < c_end) {
-            ctrl[0] = __ldg(chunk_hdr + c_begin).z;
-            ctrl[3] = __ldg(chunk_hdr + c_end - 1).z + __ldg(chunk_hdr + c_end - 1).w;
-        }
-        for (int b = 0; b < NBUF; ++b) {
-            ctrl[4 + b] = 0;
-            ctrl[12 + b] = -1;
-            // arrivals per phase: lane 0's arrive.expect_tx + one deferred cp.async arrival per lane of the filling warp
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 33;" ::"r"((uint32_t)__cvta_generic_to_shared(mbar + b)));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int c_begin = ctrl[1], c_end = ctrl[2], task_end = ctrl[3];
-
-    // hands buffer b to chunk cn: the whole warp issues the copies (one 128-byte record per lane and trip)
-    auto fill = [&](int b, int cn) {
-        const int4 ch = __ldg(chunk_hdr + cn), ex = __ldg(chunk_ext + cn);
-        const int cp0 = __ldg(cells_ptr + cn), n_cells = __ldg(cells_ptr + cn + 1) - cp0;
-        unsigned char *buf = smem_raw + (size_t)b * L.buf_bytes;
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar + b);
-        if (lane == 0) {
-            ctrl[4 + b] = ch.w;
-            ctrl[12 + b] = (cn - c_begin) / NBUF;
-            __threadfence_block();
-            const uint32_t bytes = (rec_tma ? (uint32_t)n_cells * 128u : 0u) + (uint32_t)ex.y * 4u + (uint32_t)ex.w * 8u +
-                                   (uint32_t)ch.w * 16u;
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            bulk_g2s(buf + L.ell_off, ell_local + ex.x, (uint32_t)ex.y * 4u, bar);
-            bulk_g2s(buf + L.item_off, item_hdr + ex.z, (uint32_t)ex.w * 8u, bar);
-            bulk_g2s(buf + L.task_off, task_hdr_rel + ch.z, (uint32_t)ch.w * 16u, bar);
-        }
-        // records.  The cell list is read with coalesced loads (128 cells per trip) before any copy is issued, so the
-        // copies do not wait on one dependent load each.  rec_tma: one bulk copy per 128-byte record line; else 16-byte
-        // asynchronous copies (LDGSTS, L2 only), eight per line, a warp trip moves four lines.  Completion is counted on
-        // the same mbarrier (bulk copies: bytes; LDGSTS: one deferred arrival per lane).
-        const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(buf + L.rec_off);
-        for (int m0 = 0; m0 < n_cells; m0 += 128) {
-            int cid[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int q = m0 + 32 * m + lane;
-                cid[m] = q < n_cells ? __ldg(cells + cp0 + q) : 0;
-            }
-            if (rec_tma) {
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    const int q = m0 + 32 * m + lane;
-                    if (q < n_cells) bulk_g2s(buf + L.rec_off + (size_t)q * 128, rec + (size_t)cid[m] * 16, 128u, bar);
-                }
-            } else {
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const int q = m0 + 32 * m + 4 * jj + (lane >> 3);
-                        const int c = __shfl_sync(0xffffffffu, cid[m], 4 * jj + (lane >> 3));
-                        if (q < n_cells)
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 128u * (uint32_t)q + 16u * (lane & 7)),
-                                         "l"(rec + (size_t)c * 16 + 2 * (lane & 7))
-                                         : "memory");
-                    }
-                }
-            }
-        }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-        // the lists the NEXT fill of this buffer starts with (chunk cn + NBUF; a CTA's chunks are contiguous in every
-        // array, so its cell list starts about NBUF lists further on) are pulled into L2 now
-        if (cn + NBUF < c_end) {
-            const void *pf = lane == 0   ? (const void *)(chunk_hdr + cn + NBUF)
-                             : lane == 1 ? (const void *)(chunk_ext + cn + NBUF)
-                             : lane == 2 ? (const void *)(cells_ptr + cn + NBUF)
-                                         : (const void *)(cells + cp0 + (size_t)(NBUF - 1) * n_cells + 32 * (lane - 3));
-            if (lane < 3 + 2 * NBUF) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-        }
-    };
-    if (warp < NBUF && c_begin + warp < c_end) fill(warp, c_begin + warp);
-
-    int it = 0;  // the chunk (offset from c_begin) this warp's current task belongs to
-    int4 chh = make_int4(0, 0, 0, 0);
-    if (c_begin < c_end) chh = __ldg(chunk_hdr + c_begin);
-    int t = 0;
-    if (lane == 0) t = atomicAdd(const_cast<int *>(ctrl), 1);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    while (t < task_end) {
-        while (t >= chh.z + chh.w) {
-            ++it;
-            chh = __ldg(chunk_hdr + c_begin + it);
-        }
-        int tn = 0;  // next task: the round trip of the shared-memory atomic hides behind this task
-        if (lane == 0) tn = atomicAdd(const_cast<int *>(ctrl), 1);
-        const int b = it % NBUF;
-        {
-            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar + b), parity = (uint32_t)(it / NBUF) & 1u;
-            while (ctrl[12 + b] < it / NBUF) __nanosleep(64);
-            uint32_t done = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done)
-                    : "r"(bar), "r"(parity)
-                    : "memory");
-            }
-        }
-        unsigned char *buf = smem_raw + (size_t)b * L.buf_bytes;
-        {
-            const int4 th = reinterpret_cast<const int4 *>(buf + L.task_off)[t - chh.z];
-            const int type = th.x & 0xFF, kmax = (th.x >> 8) & 0xFF, n_items = th.w & 63;
-            const uint32_t *e = reinterpret_cast<const uint32_t *>(buf + L.ell_off) + th.y + lane;
-            uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
-            if (lane < n_items) ih = reinterpret_cast<const uint2 *>(buf + L.item_off)[th.z + lane];
-            // the tile sits on the same 16-byte phase as its image in vals (parity of the chunk's first block)
-            double *tile = reinterpret_cast<double *>(buf) + ((th.x >> 16) & 1);
-            const double *rec_s = reinterpret_cast<const double *>(buf + L.rec_off);
-            const TileCtx ctx = {tile, nullptr, 0, ih.x, ih.y};
-            switch (type) {
-                case 0: run_task_s<0, CR>(e, kmax, rec_s, ctx); break;
-                case 1: run_task_s<1, CR>(e, kmax, rec_s, ctx); break;
-                case 2: run_task_s<2, CR>(e, kmax, rec_s, ctx); break;
-                case 3: run_task_s<3, CR>(e, kmax, rec_s, ctx); break;
-                case 4: run_task_s<4, CR>(e, kmax, rec_s, ctx); break;
-                default: run_task_s<5, CR>(e, kmax, rec_s, ctx); break;
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) {
-            __threadfence_block();
-            last = atomicSub(const_cast<int *>(ctrl) + 4 + b, 1) == 1;  // the chunk's last task: the tile is complete
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-            if (lane == 0) {
-                __threadfence_block();
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                const int b0 = chh.x, n_vals = 9 * chh.y, head = b0 & 1;
-                const int n_bulk = (n_vals - head) & ~1;
-                const double *tile = reinterpret_cast<const double *>(buf) + head;
-                double *dst = vals + (int64_t)9 * b0;
-                if (n_bulk > 0) {
-                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile + head);
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + head),
-                                 "r"(src), "r"(n_bulk * 8)
-                                 : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                if (head) dst[0] = tile[0];
-                if (head + n_bulk < n_vals) dst[n_vals - 1] = tile[n_vals - 1];
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            }
-            __syncwarp();
-            const int cn = c_begin + it + NBUF;
-            if (cn < c_end) fill(b, cn);
-        }
-        t = __shfl_sync(0xffffffffu, tn, 0);
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
 }  // namespace
 
 extern "C" int nfa_bplan_block_pattern(const nfa_bplan *bp, int32_t *bptr, int32_t *bcols, nfa_stream stream) {
@@ -1042,34 +810,101 @@ extern "C" int nfa_bplan_block_pattern(const nfa_bplan *bp, int32_t *bptr, int32
 extern "C" int64_t nfa_bplan_n_blocks(const nfa_bplan *bp) { return bp ? bp->n_bnz : -1; }
 
 extern "C" int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *chunk_hdr, int64_t n_tasks,
-                                      const int32_t *task_hdr, int64_t n_items, const uint16_t *item_hdr,
-                                      int64_t ell_size, const uint32_t *ell, int max_tile_blocks,
-                                      const int32_t *chunk_cells_ptr, int64_t n_chunk_cells, const int32_t *chunk_cells,
-                                      nfa_stream stream) {
+                                      const int32_t *task_hdr, int64_t n_slots, const uint16_t *item_hdr,
+                                      int64_t ell_size, const uint32_t *ell, int max_tile_blocks, nfa_stream stream) {
     if (!bp) return fail("nfa_bplan_set_p2_items: plan is NULL");
     if (bp->n_phi != 10 || bp->n_comp != 3) return fail("nfa_bplan_set_p2_items: plan is not vector-P2 on tetrahedra");
-    if (n_chunks <= 0 || n_tasks <= 0 || n_items <= 0 || ell_size <= 0 || max_tile_blocks <= 0)
+    if (n_chunks <= 0 || n_tasks <= 0 || n_slots <= 0 || ell_size <= 0 || max_tile_blocks <= 0)
         return fail("nfa_bplan_set_p2_items: empty item plan");
     if ((int64_t)max_tile_blocks * 9 + 2 >= 65535) return fail("nfa_bplan_set_p2_items: tile exceeds 16-bit offsets");
     cudaStream_t s = (cudaStream_t)stream;
     nfa_bplan::P2Items &it = bp->p2;
-    if (it.chunk_hdr.alloc(16 * n_chunks) || it.task_hdr.alloc(16 * n_tasks) || it.item_hdr.alloc(8 * (n_items + 2)) ||
-        it.ell.alloc(4 * ell_size) || it.rec.alloc(sizeof(double) * 16 * bp->n_cells) ||
-        it.cells_ptr.alloc(4 * (n_chunks + 1)) || it.cells.alloc(4 * std::max<int64_t>(n_chunk_cells, 1)))
+    if (it.chunk_hdr.alloc(16 * n_chunks) || it.task_hdr.alloc(16 * n_tasks) || it.item_hdr.alloc(8 * (n_slots + 2)) ||
+        it.ell.alloc(4 * ell_size) || it.rec.alloc(sizeof(double) * 16 * bp->n_cells))
         return 2;
-    if (!chunk_cells_ptr || !chunk_cells) return fail("nfa_bplan_set_p2_items: prefetch lists missing");
-    NFA_CUDA(cudaMemcpyAsync(it.cells_ptr.p, chunk_cells_ptr, 4 * (n_chunks + 1), cudaMemcpyDeviceToDevice, s));
-    NFA_CUDA(cudaMemcpyAsync(it.cells.p, chunk_cells, 4 * n_chunk_cells, cudaMemcpyDeviceToDevice, s));
     NFA_CUDA(cudaMemcpyAsync(it.chunk_hdr.p, chunk_hdr, 16 * n_chunks, cudaMemcpyDeviceToDevice, s));
     NFA_CUDA(cudaMemcpyAsync(it.task_hdr.p, task_hdr, 16 * n_tasks, cudaMemcpyDeviceToDevice, s));
-    NFA_CUDA(cudaMemcpyAsync(it.item_hdr.p, item_hdr, 8 * n_items, cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaMemcpyAsync(it.item_hdr.p, item_hdr, 8 * n_slots, cudaMemcpyDeviceToDevice, s));
     NFA_CUDA(cudaMemcpyAsync(it.ell.p, ell, 4 * ell_size, cudaMemcpyDeviceToDevice, s));
     NFA_CUDA(cudaStreamSynchronize(s));
     it.n_chunks = n_chunks;
     it.n_tasks = n_tasks;
-    it.n_items = n_items;
+    it.n_items = n_slots;
     it.ell_size = ell_size;
     it.max_tile_blocks = max_tile_blocks;
+    return 0;
+}
+
+// ---- bank-aware lane order ------------------------------------------------------------------------------------------
+// The items of a (chunk, type) group become the lanes of consecutive tasks, 16 to a half warp.  A half warp's tile stores
+// (STS.64, nine per block) serialise when two lanes hit the same bank pair; with the items in first-cell order the
+// positions are effectively random (2.6 wavefronts per store instead of 1).  One thread per group deals the items greedily:
+// the next lane takes, among the next `window` unassigned items, the one that raises the fewest per-position maxima of the
+// half warp's bank counts (ties: smaller sum of counts, then first in order).  nfempy_b200/assembly/p2_items.py
+// greedy_lane_order is the same algorithm on the host (tests).
+namespace {
+__global__ void p2_lane_order_kernel(int64_t n_groups, const int64_t *__restrict__ group_ptr, const int32_t *__restrict__ hdr6,
+                                     int window, int64_t *__restrict__ perm) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int64_t g0 = group_ptr[g], g1 = group_ptr[g + 1];
+    for (int64_t k = g0; k < g1; ++k) perm[k] = k;  // perm[pos ..] = the unassigned items, in order
+    unsigned char cnt[15][16], mx[15];
+    const int cols[5] = {0, 1, 2, 4, 5};
+    for (int64_t pos = g0; pos < g1; ++pos) {
+        if (((pos - g0) & 15) == 0) {
+            for (int p = 0; p < 15; ++p) {
+                mx[p] = 0;
+                for (int b = 0; b < 16; ++b) cnt[p][b] = 0;
+            }
+        }
+        const int64_t c_end = (pos + window < g1) ? pos + window : g1;
+        int64_t best = pos;
+        int best_key = 0x7fffffff;
+        for (int64_t c = pos; c < c_end; ++c) {
+            const int32_t *h = hdr6 + 6 * perm[c];
+            const int pitch = h[3];
+            int inc = 0, tie = 0;
+            for (int s = 0; s < 5; ++s) {
+                const int w = h[cols[s]];
+                if (w == 0xFFFF) continue;
+                for (int r = 0; r < 3; ++r) {
+                    const int cc = cnt[3 * s + r][(w + r * pitch) & 15];
+                    inc += (cc + 1 > mx[3 * s + r]) ? 1 : 0;
+                    tie += cc;
+                }
+            }
+            const int key = inc * 65536 + tie;
+            if (key < best_key) {
+                best_key = key;
+                best = c;
+            }
+        }
+        const int64_t chosen = perm[best];
+        for (int64_t c = best; c > pos; --c) perm[c] = perm[c - 1];
+        perm[pos] = chosen;
+        const int32_t *h = hdr6 + 6 * chosen;
+        const int pitch = h[3];
+        for (int s = 0; s < 5; ++s) {
+            const int w = h[cols[s]];
+            if (w == 0xFFFF) continue;
+            for (int r = 0; r < 3; ++r) {
+                unsigned char &cc = cnt[3 * s + r][(w + r * pitch) & 15];
+                ++cc;
+                if (cc > mx[3 * s + r]) mx[3 * s + r] = cc;
+            }
+        }
+    }
+}
+}  // namespace
+
+extern "C" int nfa_p2_lane_order(int64_t n_groups, const int64_t *group_ptr, const int32_t *hdr6, int window,
+                                 int64_t *perm, nfa_stream stream) {
+    if (n_groups <= 0) return 0;
+    if (!group_ptr || !hdr6 || !perm) return fail("nfa_p2_lane_order: NULL argument");
+    if (window < 1) return fail("nfa_p2_lane_order: window must be positive");
+    p2_lane_order_kernel<<<grid_for(n_groups, 64), 64, 0, (cudaStream_t)stream>>>(n_groups, group_ptr, hdr6, window, perm);
+    NFA_LAUNCH_CHECK();
     return 0;
 }
 
@@ -1089,82 +924,6 @@ extern "C" int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *mask, nfa_s
     return 0;
 }
 
-extern "C" int nfa_bplan_set_p2_stage(nfa_bplan *bp, const int32_t *chunk_ext, const int32_t *task_hdr_rel,
-                                      const uint32_t *ell_local, int max_chunk_cells, int max_chunk_ell,
-                                      int max_chunk_items, int max_chunk_tasks, nfa_stream stream) {
-    if (!bp) return fail("nfa_bplan_set_p2_stage: plan is NULL");
-    nfa_bplan::P2Items &it = bp->p2;
-    if (it.n_chunks <= 0) return fail("nfa_bplan_set_p2_stage: set the row items first (nfa_bplan_set_p2_items)");
-    if (!chunk_ext || !task_hdr_rel || !ell_local) return fail("nfa_bplan_set_p2_stage: NULL list");
-    if (max_chunk_cells <= 0 || max_chunk_ell <= 0 || max_chunk_items <= 0 || max_chunk_tasks <= 0)
-        return fail("nfa_bplan_set_p2_stage: empty chunk bounds");
-    cudaStream_t s = (cudaStream_t)stream;
-    if (it.chunk_ext.alloc(16 * it.n_chunks) || it.task_hdr_rel.alloc(16 * it.n_tasks) || it.ell_local.alloc(4 * it.ell_size))
-        return 2;
-    NFA_CUDA(cudaMemcpyAsync(it.chunk_ext.p, chunk_ext, 16 * it.n_chunks, cudaMemcpyDeviceToDevice, s));
-    NFA_CUDA(cudaMemcpyAsync(it.task_hdr_rel.p, task_hdr_rel, 16 * it.n_tasks, cudaMemcpyDeviceToDevice, s));
-    NFA_CUDA(cudaMemcpyAsync(it.ell_local.p, ell_local, 4 * it.ell_size, cudaMemcpyDeviceToDevice, s));
-    NFA_CUDA(cudaStreamSynchronize(s));
-    it.max_chunk_cells = max_chunk_cells;
-    it.max_chunk_ell = max_chunk_ell;
-    it.max_chunk_items = max_chunk_items;
-    it.max_chunk_tasks = max_chunk_tasks;
-    return 0;
-}
-
-// The staged kernel when the plan carries its lists and at least two chunk buffers fit in shared memory.
-static int launch_p2tet_staged(const nfa_bplan *bp, double *vals, bool cr, cudaStream_t s, bool *launched) {
-    const nfa_bplan::P2Items &it = bp->p2;
-    *launched = false;
-    if (it.max_chunk_cells <= 0) return 0;
-    // opt-in (NFA_P2TET_STAGE=1): measured 1.23 ms against 0.95 ms for the global-load kernel on the bench workload --
-    // the random 128-bit shared-memory reads of the records cost 3x the LSU wavefronts of the 256-bit global loads and
-    // the in-order hand-over of filled buffers leaves the warps spinning (profiles/r01_p2tet_staged_ncu_summary.txt)
-    const char *e_stage = getenv("NFA_P2TET_STAGE");
-    if (!e_stage || atoi(e_stage) == 0) return 0;
-    auto r128 = [](size_t v) { return (v + 127) & ~(size_t)127; };
-    StageLayout L;
-    const size_t tile_bytes = r128(sizeof(double) * (9 * (size_t)it.max_tile_blocks + 2));
-    L.rec_off = (int)tile_bytes;
-    L.ell_off = L.rec_off + 128 * it.max_chunk_cells;
-    L.item_off = L.ell_off + (int)r128(4 * (size_t)it.max_chunk_ell);
-    L.task_off = L.item_off + (int)r128(8 * (size_t)it.max_chunk_items);
-    L.buf_bytes = L.task_off + (int)r128(16 * (size_t)it.max_chunk_tasks);
-    const size_t ctrl_bytes = 256, limit = 227 * 1024;
-    int nbuf = (int)std::min<size_t>(8, (limit - ctrl_bytes) / (size_t)L.buf_bytes);
-    if (const char *e = getenv("NFA_P2TET_NBUF")) nbuf = std::min(nbuf, std::max(1, atoi(e)));
-    if (nbuf < 2) return 0;  // chunks too large for two buffers: the caller falls back to the global-load kernel
-    const size_t smem = (size_t)nbuf * L.buf_bytes + ctrl_bytes;
-    int threads = 512, rec_tma = 0;
-    if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
-    if (const char *e = getenv("NFA_P2TET_REC_TMA")) rec_tma = atoi(e) != 0;
-    using kern_t = void (*)(int, int, const int4 *, const int4 *, const int4 *, const uint2 *, const uint32_t *,
-                            const int32_t *, const int32_t *, const double *, StageLayout, int, double *);
-    kern_t kern = nullptr;
-#define NFA_P2S_PICK(CRV, TH) \
-    if (cr == CRV && threads == TH) kern = p2tet_staged_kernel<CRV, TH>;
-    NFA_P2S_PICK(false, 512) NFA_P2S_PICK(false, 640) NFA_P2S_PICK(false, 768) NFA_P2S_PICK(false, 1024)
-    NFA_P2S_PICK(true, 512) NFA_P2S_PICK(true, 640) NFA_P2S_PICK(true, 768) NFA_P2S_PICK(true, 1024)
-#undef NFA_P2S_PICK
-    if (!kern) return fail("nfa_assemble_p2tet_elasticity: NFA_P2TET_THREADS must be 512, 640, 768 or 1024 (staged kernel)");
-    NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int device = 0, n_sm = 148;
-    NFA_CUDA(cudaGetDevice(&device));
-    NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-    int64_t grid = std::min<int64_t>(it.n_chunks, (int64_t)n_sm);
-    if (const char *e = getenv("NFA_P2TET_GRID")) grid = std::max<int64_t>(1, std::min<int64_t>(grid, atoi(e)));  // tests
-    if (timing_enabled()) timing_begin(s);
-    kern<<<(unsigned)grid, threads, smem, s>>>(nbuf, (int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
-                                               (const int4 *)it.chunk_ext.p, (const int4 *)it.task_hdr_rel.p,
-                                               (const uint2 *)it.item_hdr.p, (const uint32_t *)it.ell_local.p,
-                                               (const int32_t *)it.cells_ptr.p, (const int32_t *)it.cells.p,
-                                               (const double *)it.rec.p, L, rec_tma, vals);
-    if (timing_enabled()) timing_end(s);
-    NFA_LAUNCH_CHECK();
-    *launched = true;
-    return 0;
-}
-
 extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *coords, const int32_t *cell_nodes,
                                              const double *lam, int64_t ls, const double *mu, int64_t ms, double *vals,
                                              nfa_stream stream) {
@@ -1175,11 +934,6 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     p2tet_geo_kernel<<<grid_for(bp->n_cells, 128), 128, 0, s>>>(coords, cell_nodes, bp->n_cells, lam, ls, mu, ms,
                                                                 (const uint8_t *)it.cell_mask.p, (double *)it.rec.p);
     NFA_LAUNCH_CHECK();
-    {
-        bool launched = false;
-        if (int rc = launch_p2tet_staged(bp, vals, ls == 0 && ms == 0, s, &launched)) return rc;
-        if (launched) return 0;
-    }
     const int tile_stride = (9 * it.max_tile_blocks + 2 + 15) & ~15;  // doubles; keeps both tiles 128-byte aligned
     // as many tiles as fit in 220 KB of shared memory (at most 8): the more chunks are in flight, the less a long task
     // (a vertex-star item walks ~24 cells) delays the hand-over of its chunk's tile
@@ -1193,7 +947,7 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
     if (threads > 640) threads = 512;  // larger counts are staged-kernel settings
     using kern_t = void (*)(int, int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
-                            const int32_t *, const int32_t *, double *);
+                            double *);
     kern_t kern = nullptr;
     const bool nb4 = nbuf == 4 && !getenv("NFA_P2TET_RT_NBUF");
 #define NFA_P2_PICK(CRV, TH)                                                      \
@@ -1209,12 +963,12 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) return fail("nfa_assemble_p2tet_elasticity: kernel does not fit on an SM");
-    const int64_t grid = std::min<int64_t>(it.n_chunks, (int64_t)n_sm * per_sm);
+    int64_t grid = std::min<int64_t>(it.n_chunks, (int64_t)n_sm * per_sm);
+    if (const char *e = getenv("NFA_P2TET_GRID")) grid = std::max<int64_t>(1, std::min<int64_t>(grid, atoi(e)));  // tests
     if (timing_enabled()) timing_begin(s);
     kern<<<(unsigned)grid, threads, smem, s>>>(nbuf, (int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
                                                   (const int4 *)it.task_hdr.p, (const uint2 *)it.item_hdr.p,
-                                                  (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride,
-                                                  (const int32_t *)it.cells_ptr.p, (const int32_t *)it.cells.p, vals);
+                                                  (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride, vals);
     if (timing_enabled()) timing_end(s);
     NFA_LAUNCH_CHECK();
     return 0;

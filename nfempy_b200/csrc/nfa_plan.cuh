@@ -75,16 +75,9 @@ struct nfa_bplan {
         int max_tile_blocks = 0;
         nfa::DevBuf chunk_hdr;  // int32 [n_chunks][4]: b0, n_blocks, task0, n_tasks
         nfa::DevBuf task_hdr;   // int32 [n_tasks][4]: type | kmax << 8, ell_base, item_base, n_items
-        nfa::DevBuf item_hdr;   // uint16 [n_items][4]: tile offsets of up to three blocks, row pitch
+        nfa::DevBuf item_hdr;   // uint16 [n_slots][4]: tile offsets of up to three blocks, row pitch; type E: + a second slot
         nfa::DevBuf ell;        // uint32 [ell_size]: cell << 6 | i << 4 | j << 2 | x, 32 lanes interleaved
-        nfa::DevBuf cells_ptr;  // int32 [n_chunks + 1], cells: int32: cells each chunk reads (L1 prefetch lists)
-        nfa::DevBuf cells;
         nfa::DevBuf rec;        // scratch: geometry records [n_cells][4][4], rewritten every assembly
         nfa::DevBuf cell_mask;  // optional uint8 [n_cells]: 0 = the cell contributes zeros (halo cell of a sharded plan)
-        // staged variant (everything a chunk reads is bulk-copied to shared memory): chunk-relative lists
-        int max_chunk_cells = 0, max_chunk_ell = 0, max_chunk_items = 0, max_chunk_tasks = 0;
-        nfa::DevBuf chunk_ext;     // int32 [n_chunks][4]: ell0, n_ell, item0 (even), n_items copied (even)
-        nfa::DevBuf task_hdr_rel;  // task_hdr with ell_base / item_base relative to the chunk's copies
-        nfa::DevBuf ell_local;     // ell with the cell replaced by its slot in the chunk's cell list
     } p2;
 };

@@ -32,11 +32,12 @@ def load_mesh_blocks(name):
     return z["points"], blocks
 
 
-def fixture_mesh(dim):
-    """The reference's own gmsh fixture (example_3_{2d,3d}_l_0.msh) as a product mesh, rebuilt from the committed arrays."""
+def fixture_mesh(dim, level=0):
+    """The reference's own gmsh fixture (example_3_{2d,3d}_l_{level}.msh) as a product mesh, rebuilt from the committed
+    arrays."""
     from nfempy_b200.mesh import Mesh
 
-    points, blocks = load_mesh_blocks("mesh_ex3_%dd_l0.npz" % dim)
+    points, blocks = load_mesh_blocks("mesh_ex3_%dd_l%d.npz" % (dim, level))
     mesh = Mesh.from_arrays(dim, points, blocks)
     mesh.build_conformal_mesh()
     return mesh

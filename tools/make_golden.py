@@ -11,6 +11,9 @@
   Taylor-Hood + BC, mixed Poisson on BDM_3 + natural BC, mixed Cosserat with natural and penalised stress BCs);
   ``python tools/make_golden.py multi`` regenerates only this file (needs no /root/reference: the mesh arrays are committed).
 
+* mesh_ex3_3d_l{1,2}.npz, le_p2_ex3_3d_l1.npz, le_p2_ex3_3d_l2_probe.npz -- the larger levels of the 3-D fixture
+  (``python tools/make_golden.py levels``), see ``main_levels``.
+
 The reference itself cannot run here (basix / auto_diff / petsc4py / meshio absent), so these are ORACLE outputs:
 they pin the oracle against regressions and give the GPU tests a fixed target; they do not pin the oracle to the
 real reference ("parity unpinned").
@@ -91,6 +94,40 @@ def main():
     print("laplace_p1_ex3_2d_l0: n_dof", space.n_dof, "nnz", len(indices))
 
 
+def main_levels():
+    """The larger levels of the reference's 3-D fixture: meshes + oracle results of
+    vector-P2 elasticity with the Dirichlet penalty on the six sides.
+    * level 1 (1 325 tets): the complete CSR + rhs of the cell-by-cell oracle (le_p2_ex3_3d_l1.npz);
+    * level 2 (4 261 tets): a compact fingerprint of the cell-by-cell oracle's result (le_p2_ex3_3d_l2_probe.npz) -- the
+      int32 pattern, the products K v for four seeded vectors, the diagonal, the row sums of |K| and the rhs; the full
+      value array (12 MB) is not committed, the GPU test compares all values against oracle/strong_cpu.py at run time."""
+    for level, full in ((1, True), (2, False)):
+        points, blocks = save_mesh("mesh_ex3_3d_l%d.npz" % level, os.path.join(REF, "example_3_3d_l_%d.msh" % level))
+        mesh = RefMesh(3, points, blocks)
+        mesh.build_conformal_mesh()
+        space = RefProductSpace({"u": (3, 3, "Lagrange", 2, mesh)})
+        space.build_structures({"u": [1]}, {"u": [2, 3, 4, 5, 6, 7]})
+        us = space.discrete_spaces["u"]
+        forms = [
+            ("form", ref_forms.le_primal, LE_FUNCTIONS, len(us.element_ids)),
+            ("bc_form", ref_forms.le_primal_bc_dirichlet, LE_BC_FUNCTIONS, len(us.bc_element_ids)),
+        ]
+        indptr, indices, data, rhs = ref_assembly.assemble(space, forms)
+        print("le_p2_ex3_3d_l%d: n_dof" % level, space.n_dof, "nnz", len(indices))
+        if full:
+            np.savez_compressed(os.path.join(OUT, "le_p2_ex3_3d_l%d.npz" % level), indptr=indptr, indices=indices, data=data, rhs=rhs)
+        else:
+            import scipy.sparse as sp
+
+            n = space.n_dof
+            K = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+            V = np.random.default_rng(2024).standard_normal((n, 4))
+            np.savez_compressed(
+                os.path.join(OUT, "le_p2_ex3_3d_l%d_probe.npz" % level), indptr=indptr, indices=indices, rhs=rhs,
+                KV=K @ V, diag=K.diagonal(), abs_row_sum=np.asarray(abs(K).sum(axis=1)).ravel(), seed=np.array(2024),
+            )
+
+
 def main_multi():
     """multi_ex3_2d_l0.npz: oracle CSR + rhs of the later form families on the 2-D fixture mesh (tests/golden_cases.py)."""
     from tests.golden_cases import multi_cases
@@ -106,6 +143,8 @@ def main_multi():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "multi":
         main_multi()
+    elif len(sys.argv) > 1 and sys.argv[1] == "levels":
+        main_levels()
     else:
         main()
         main_multi()
