@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
+    ap.add_argument("--no-p2p", action="store_true", help="N > 1: exchange the interface rows with NCCL send/recv instead "
+                    "of the library's peer-memory kernels")
     return ap.parse_args()
 
 
@@ -275,6 +277,19 @@ def run_graft(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # pinned host buffers are placed on the NUMA node of the allocating thread: run this rank on the cores next to its GPU
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
+    if world > 1:
         # NCCL writes its version banner / warnings to STDOUT when NCCL_DEBUG is set (it is on the GPU boxes); stdout must
         # carry the JSON line only
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -340,12 +355,21 @@ def run_graft(args):
     launches_per_step = None
     graph = None
     local_launches = 0
+    p2p = False
+    if sharded is not None:
+        # N > 1: interface rows go straight into the owner's memory over NVLink (nfa_push_rows / nfa_pull_add_rows); the whole
+        # step -- local kernels + exchange -- is then ONE CUDA graph.  Fallback (--no-p2p or no CUDA IPC): local graph + eager
+        # pack / NCCL send-recv / unpack.
+        p2p = (not args.no_p2p) and sharded.enable_p2p(dist)
     if sharded is not None and not args.no_graph:
-        # N > 1: the local kernels are replayed from a CUDA graph, the exchange (pack, NCCL send/recv, unpack) stays eager
         l0 = _lib.launch_count()
         sharded.local_assemble()
         local_launches = _lib.launch_count() - l0 + 1  # + the rhs fill
-        sharded.capture_local()
+        if p2p:
+            local_launches += len(sharded.shard.send_rows) + len(sharded.shard.recv_rows)
+            sharded.capture_step()
+        else:
+            sharded.capture_local()
     if sharded is None and not args.no_graph:
         l0 = _lib.launch_count()
         step()
@@ -373,7 +397,7 @@ def run_graft(args):
         launches = launches_per_step * args.steps  # replayed kernel nodes: counted on the eager step that was captured
     else:
         launches = _lib.launch_count() - launches0 + args.steps  # + rhs_dev.zero_() per step (torch fill kernel)
-        if sharded is not None and not args.no_graph:  # the replayed local kernels + the eager exchange kernels counted above
+        if sharded is not None and not args.no_graph:  # the replayed kernels (+ the eager exchange kernels counted above)
             launches = _lib.launch_count() - launches0 + local_launches * args.steps
     # load probe for the clock record: the same step loop for ~0.6 s (not part of any reported time)
     p0 = time.time()
@@ -443,15 +467,18 @@ def run_graft(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": WORKLOAD % (n_cells, args.n) + (
-                    "" if world == 1 else "; x-slab cell partition, NCCL interface-row reduce"),
+                    "" if world == 1 else "; x-slab cell partition, interface rows summed onto their owners"),
                 "cells_per_gpu": n_cells, "n_dof_per_gpu": plan.n_dof, "nnz_per_gpu": nnz,
                 "nonzeros_per_s": nnz * world / (ms_step * 1e-3),
                 "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no explicit flush" % ((b_step * n_cells + 6 * 100 * n_cells) / 1e9),
                 "plan_build_s": plan.build_seconds, "host_mesh_space_s": t_host, "prepare_s": t_prepare,
                 "path": ("fused (row items)" if row_items else "fused") if plan.fused_index is not None else "two-stage",
                 "launch": ("CUDA graph replay of the captured step" if graph is not None else
-                           ("CUDA graph replay of the local assembly + eager NCCL exchange" if (sharded is not None and not args.no_graph)
+                           (("CUDA graph replay of the whole step: local assembly + peer-memory exchange kernels" if p2p else
+                             "CUDA graph replay of the local assembly + eager NCCL exchange") if (sharded is not None and not args.no_graph)
                             else "eager launches")),
+                "exchange": None if sharded is None else ("nfa_push_rows / nfa_pull_add_rows over NVLink peer memory (CUDA IPC)" if p2p
+                                                          else "pack kernels + ncclSend/ncclRecv + unpack kernels"),
             },
             "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "cpu_strong": cpu_strong, "e2e": e2e, "e2e_all_inputs": e2e_all, "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -339,6 +339,8 @@ int nfa_p2p_alloc(int64_t bytes, void **d_ptr, void *handle64);
 int nfa_p2p_open(const void *handle64, void **d_peer_ptr);
 int nfa_p2p_close(void *d_peer_ptr);
 int nfa_p2p_free(void *d_ptr);
+/* number of exchange waits that gave up (a peer never published its epoch); 0 in a healthy run, -1 on a CUDA error */
+int64_t nfa_p2p_timeouts(void);
 int nfa_push_rows(const int32_t *d_indptr, const double *d_vals, const double *d_rhs, const int32_t *d_rows,
                   const int64_t *d_buf_off, int64_t n_rows, double *d_remote_buf, uint64_t *d_remote_flag,
                   const uint64_t *d_local_ack, uint64_t *d_state, nfa_stream stream);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "nfa_p2p_open": (_i, [_vp, ctypes.POINTER(_vp)]),
     "nfa_p2p_close": (_i, [_vp]),
     "nfa_p2p_free": (_i, [_vp]),
+    "nfa_p2p_timeouts": (_i64, []),
     "nfa_push_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_pull_add_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_bplan_create": (_i, [_i64, _i, _i, _vp, _i64, ctypes.POINTER(_vp), _vp]),

@@ -234,7 +234,7 @@ class GPUAssembler:
         _lib.check(lib.nfa_bplan_block_pattern(p.bplan, _lib.ptr(bptr), _lib.ptr(bcols), stream), "nfa_bplan_block_pattern")
         cap = int(os.environ.get("NFA_P2TET_CAP", "640"))
         lane_optimizer = None
-        if os.environ.get("NFA_P2TET_LANEOPT", "1") != "0":
+        if os.environ.get("NFA_P2TET_LANEOPT", "0") != "0":  # measured: costs the lanes' cell-order locality more than it saves
             window = int(os.environ.get("NFA_P2TET_LANEWIN", "48"))
 
             def lane_optimizer(group_ptr, hdr6):
@@ -249,7 +249,8 @@ class GPUAssembler:
         items = p2_items.build(node_dest.to(torch.int64), bptr.to(torch.int64), bcols.to(torch.int64), n_nodes, cap=cap,
                                riffle=int(os.environ.get("NFA_P2TET_RIFFLE", "148")),
                                batch=int(os.environ.get("NFA_P2TET_BATCH", "8")),
-                               lane_order=os.environ.get("NFA_P2TET_LANES", "cell"), lane_optimizer=lane_optimizer)
+                               lane_order=os.environ.get("NFA_P2TET_LANES", "cell"), lane_optimizer=lane_optimizer,
+                               locality=os.environ.get("NFA_P2TET_LOCAL", "1") != "0")
         _lib.check(
             lib.nfa_bplan_set_p2_items(
                 p.bplan, items["n_chunks"], _lib.ptr(items["chunk_hdr"]), items["n_tasks"], _lib.ptr(items["task_hdr"]),

@@ -138,7 +138,8 @@ def greedy_lane_order(group_ptr, hdr, window=48):
     return out
 
 
-def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_order="cell", lane_optimizer=None):
+def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_order="cell", lane_optimizer=None,
+          locality=True):
     """``node_dest`` int64 [n_cells, 10] global node of each local P2 node, ``bptr``/``bcols`` the block CSR of the
     matrix (int64 tensors on the same device).  ``lane_optimizer(group_ptr, hdr6) -> permutation`` reorders the items
     inside their (chunk, type) groups (``nfa_p2_lane_order`` on the device, ``greedy_lane_order`` in the tests; None keeps
@@ -166,7 +167,20 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     win = bptr[:-1] // cap
     nonempty = nb_row > 0
     uniq_win = torch.unique(win[nonempty])
-    dense_win = torch.searchsorted(uniq_win, win)
+    dense_win = torch.clamp(torch.searchsorted(uniq_win, win), max=int(uniq_win.shape[0]) - 1)
+    if locality:
+        # walk order of the windows = ascending first cell they read (not CSR order): vertex rows and edge rows of the same
+        # part of the mesh are then assembled at about the same time, so a cell's geometry record is fetched from DRAM
+        # once instead of once per phase (the CSR itself keeps the reference numbering; only the walk order changes)
+        cells10 = torch.arange(n_cells, device=dev, dtype=torch.int64).repeat_interleave(node_dest.shape[1])
+        first_cell = torch.full((n_nodes,), n_cells, dtype=torch.int64, device=dev)
+        first_cell.scatter_reduce_(0, node_dest.reshape(-1), cells10, reduce="amin", include_self=True)
+        win_key = torch.full((int(uniq_win.shape[0]),), n_cells, dtype=torch.int64, device=dev)
+        rr0 = torch.nonzero(nonempty).reshape(-1)
+        win_key.scatter_reduce_(0, dense_win[rr0], first_cell[rr0], reduce="amin", include_self=True)
+        seq = torch.empty_like(win_key)
+        seq[torch.argsort(win_key, stable=True)] = torch.arange(int(win_key.shape[0]), device=dev)
+        dense_win = seq[dense_win]
     q, r = dense_win // batch, dense_win % batch
     n_batches = (int(uniq_win.shape[0]) + batch - 1) // batch
     per_group = (n_batches + riffle - 1) // riffle

@@ -15,6 +15,11 @@ The reference is single-process; this is the N-GPU extension the north star asks
   hold the same pattern for those rows, so the segments line up entry by entry;
 * result: every rank holds the finished rows it owns, in global numbering -- a row-block CSR.
 
+Exchange paths: ``enable_p2p(dist)`` switches the exchange to the library's peer-memory kernels (``nfa_push_rows`` stores
+the rows straight into the owner's receive area over NVLink, ``nfa_pull_add_rows`` waits for the epoch flag and adds;
+csrc/nfa_p2p.cu) -- pure stream-ordered device work, so ``capture_step()`` records local assembly + exchange in ONE CUDA
+graph.  Without it (or when CUDA IPC is unavailable) the rows go through pack kernels + ``ncclSend/ncclRecv``.
+
 ``ShardPlan`` is pure host logic (numpy) on the replicated destination table; the exchange takes pack/unpack
 callables so that the same code runs over NCCL on device buffers and over gloo on CPU tensors (tests).
 """
@@ -126,6 +131,8 @@ class ShardedAssembler:
         self.state = None
         self._bufs = {}
         self._graph = None
+        self._step_graph = None
+        self._p2p = None
         self.rhs = None
         self._torch = torch
 
@@ -227,11 +234,144 @@ class ShardedAssembler:
             "nfa_unpack_add_rows")
         self.rhs.index_add_(0, rows.long(), buf[self._sizes[tag] :])  # rows are distinct: deterministic
 
+    # -- peer-memory exchange (csrc/nfa_p2p.cu) ---------------------------------------------------------
+    def _arena_layout(self):
+        """Byte offsets inside this rank's receive arena: [flags u64[world] | acks u64[world] | payload of each sender]."""
+        off = (2 * self.world * 8 + 255) & ~255
+        table = {}
+        for q in sorted(self.shard.recv_rows):
+            table[q] = off
+            n = self._sizes[("recv", q)] + int(self._rows_dev[("recv", q)].shape[0])
+            off += (8 * n + 255) & ~255
+        return table, max(off, 256)
+
+    def _p2p_alloc(self):
+        import ctypes
+
+        from .. import _lib
+
+        table, size = self._arena_layout()
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        _lib.check(_lib.load().nfa_p2p_alloc(size, ctypes.byref(ptr), handle), "nfa_p2p_alloc")
+        return {"base": int(ptr.value), "handle": handle.raw, "table": table, "size": size}
+
+    def _p2p_wire(self, mine, peer_base, peer_table):
+        """``peer_base[q]`` = address of rank q's arena in this process, ``peer_table[q]`` its payload offsets."""
+        torch = self._torch
+        w, r = self.world, self.rank
+        self._p2p = {
+            "mine": mine,
+            # one (epoch, blocks-done) state pair per peer and direction, local memory
+            "state": torch.zeros((2 * w, 2), dtype=torch.int64, device=self.dev.device),
+            "push": {q: (peer_base[q] + peer_table[q][r], peer_base[q] + 8 * r, mine["base"] + 8 * (w + q))
+                     for q in self.shard.send_rows},
+            "pull": {q: (mine["base"] + mine["table"][q], mine["base"] + 8 * q, peer_base[q] + 8 * (w + r))
+                     for q in self.shard.recv_rows},
+        }
+
+    def enable_p2p(self, dist):
+        """Collective over the process group: every rank allocates its receive arena, the CUDA IPC handles are exchanged
+        and each rank maps the arenas of the ranks it exchanges rows with.  Returns True when the peer-memory exchange is
+        active on ALL ranks (else the NCCL path stays)."""
+        import ctypes
+
+        from .. import _lib
+
+        lib = _lib.load()
+        ok, mine, err = True, None, ""
+        try:
+            mine = self._p2p_alloc()
+        except _lib.NfaError as exc:
+            ok, err = False, str(exc)
+        info = [None] * self.world
+        dist.all_gather_object(info, (ok, mine["handle"] if ok else None, mine["table"] if ok else None))
+        peer_base, peer_table = {}, {}
+        if all(i[0] for i in info):
+            for q in sorted(set(self.shard.send_rows) | set(self.shard.recv_rows)):
+                ptr = ctypes.c_void_p()
+                try:
+                    _lib.check(lib.nfa_p2p_open(ctypes.create_string_buffer(info[q][1], 64), ctypes.byref(ptr)), "nfa_p2p_open")
+                    peer_base[q], peer_table[q] = int(ptr.value), info[q][2]
+                except _lib.NfaError as exc:
+                    ok, err = False, str(exc)
+                    break
+        else:
+            ok = False
+        flags = [None] * self.world
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            self._p2p, self.p2p_error = None, err or "a peer could not map the exchange arenas"
+            return False
+        self._p2p_wire(mine, peer_base, peer_table)
+        return True
+
+    def exchange_p2p(self):
+        """Pushes this rank's partial rows to their owners and adds the rows pushed to it (ascending sender rank)."""
+        import ctypes
+
+        from .. import _lib
+
+        lib, p, stream = _lib.load(), self._p2p, _lib.stream_ptr()
+        vp = ctypes.c_void_p
+        for q in sorted(self.shard.send_rows):
+            tag = ("send", q)
+            rows, (buf, flag, ack) = self._rows_dev[tag], p["push"][q]
+            _lib.check(lib.nfa_push_rows(_lib.ptr(self.plan.indptr), _lib.ptr(self.vals), _lib.ptr(self.rhs), _lib.ptr(rows),
+                                         _lib.ptr(self._off_dev[tag]), int(rows.shape[0]), vp(buf), vp(flag), vp(ack),
+                                         vp(p["state"][q].data_ptr()), stream), "nfa_push_rows")
+        for q in sorted(self.shard.recv_rows):
+            tag = ("recv", q)
+            rows, (buf, flag, ack) = self._rows_dev[tag], p["pull"][q]
+            _lib.check(lib.nfa_pull_add_rows(_lib.ptr(self.plan.indptr), _lib.ptr(self.vals), _lib.ptr(self.rhs),
+                                             _lib.ptr(rows), _lib.ptr(self._off_dev[tag]), int(rows.shape[0]), vp(buf), vp(flag),
+                                             vp(ack), vp(p["state"][self.world + q].data_ptr()), stream), "nfa_pull_add_rows")
+
+    def capture_step(self):
+        """One CUDA graph for the whole step: local fused assembly + peer-memory exchange (needs ``enable_p2p``)."""
+        torch = self._torch
+        if self._p2p is None:
+            raise RuntimeError("ShardedAssembler.capture_step: the peer-memory exchange is not enabled")
+        dev, entries, datas, dests, plan, key = self.state
+        if getattr(self, "rhs", None) is None:
+            self.rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
+        self._graph = None
+
+        def body():
+            self.asm.jacobian.is_zero = True
+            self.rhs.zero_()
+            self.asm._capturing = True
+            try:
+                self.asm.run(self.state, self.rhs)
+            finally:
+                self.asm._capturing = False
+            self.vals = self.asm.jacobian.values_dev
+            self.exchange_p2p()
+
+        with torch.cuda.device(dev.device):
+            body()  # binds the pattern; every rank runs the same number of real exchanges, so the epochs stay in step
+            cur = torch.cuda.current_stream(dev.device)
+            side = torch.cuda.Stream(device=dev.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                body()
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+        self._step_graph = graph
+        self._graph_keep = self.asm._keep
+        return self
+
     def assemble(self, dist=None):
         """Local fused assembly + (for world > 1) the NCCL interface exchange.  Returns device tensors
         ``(indptr, indices, values, rhs)``; the rank's owned rows are final."""
+        if self._step_graph is not None:
+            self._step_graph.replay()
+            return self.plan.indptr, self.plan.indices, self.vals, self.rhs
         self.local_assemble()
-        if self.world > 1:
+        if self.world > 1 and self._p2p is not None:
+            self.exchange_p2p()
+        elif self.world > 1:
             if dist is None:
                 import torch.distributed as dist
             exchange_interface_rows(

@@ -20,6 +20,10 @@ using namespace nfa;
 
 namespace {
 
+// A peer that never arrives must not hang the device: a wait gives up after ~2^25 polls (tens of seconds) and counts the
+// event here; nfa_p2p_timeouts() reports it (the sums are then incomplete and the caller must treat the step as failed).
+__device__ unsigned int g_p2p_timeouts = 0;
+
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -38,7 +42,14 @@ __global__ void push_rows_kernel(const int32_t *__restrict__ indptr, const doubl
     __shared__ unsigned long long epoch;
     if (threadIdx.x == 0) {
         const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(state);
-        while (ld_acquire_sys(local_ack) < e) __nanosleep(200);
+        unsigned int polls = 0;
+        while (ld_acquire_sys(local_ack) < e) {
+            __nanosleep(500);
+            if (++polls > (1u << 25)) {
+                atomicAdd(&g_p2p_timeouts, 1u);
+                break;
+            }
+        }
         epoch = e;
     }
     __syncthreads();
@@ -72,7 +83,14 @@ __global__ void pull_add_rows_kernel(const int32_t *__restrict__ indptr, double 
     __shared__ unsigned long long epoch;
     if (threadIdx.x == 0) {
         const unsigned long long e = *reinterpret_cast<volatile unsigned long long *>(state);
-        while (ld_acquire_sys(local_flag) < e + 1) __nanosleep(200);
+        unsigned int polls = 0;
+        while (ld_acquire_sys(local_flag) < e + 1) {
+            __nanosleep(500);
+            if (++polls > (1u << 25)) {
+                atomicAdd(&g_p2p_timeouts, 1u);
+                break;
+            }
+        }
         epoch = e;
     }
     __syncthreads();
@@ -137,6 +155,12 @@ extern "C" int nfa_p2p_close(void *d_peer_ptr) {
 extern "C" int nfa_p2p_free(void *d_ptr) {
     if (d_ptr) NFA_CUDA(cudaFree(d_ptr));
     return 0;
+}
+
+extern "C" int64_t nfa_p2p_timeouts() {
+    unsigned int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_p2p_timeouts, sizeof(v)) != cudaSuccess) return -1;
+    return (int64_t)v;
 }
 
 // ---- the exchange kernels ----------------------------------------------------------------------------------------------

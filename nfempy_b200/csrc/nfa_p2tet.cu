@@ -59,6 +59,22 @@ constexpr int P2_THREADS = NFA_P2_THREADS;
 //                  its outstanding global loads -- the look-ahead loads of the next tasks -- before it could retire.)
 //   NFA_P2_GRAB2   1: the ticket of the task counter is taken one iteration before it is used (the shared-memory atomic's
 //                  round trip hides behind a task instead of stalling the top of the loop)
+//   NFA_P2_STREAM_PF  1: the plan lists a CTA reads (task headers, ELL entries, item headers) are contiguous in task order;
+//                  every task prefetches into L2 the part of each list that lies a fixed distance AHEAD of what it
+//                  consumes (a software stream prefetcher: no further tasks are claimed, so the tile window is not
+//                  overrun, and the look-ahead loads of the next task become L2 hits instead of DRAM misses)
+#ifndef NFA_P2_STREAM_PF
+#define NFA_P2_STREAM_PF 1
+#endif
+#ifndef NFA_P2_PFD_ELL
+#define NFA_P2_PFD_ELL 4096  // look-ahead in ELL entries (16 KB, about 35 tasks)
+#endif
+#ifndef NFA_P2_PFD_IH
+#define NFA_P2_PFD_IH 1280  // look-ahead in item-header slots (10 KB)
+#endif
+#ifndef NFA_P2_PFD_TH
+#define NFA_P2_PFD_TH 64  // look-ahead in task headers
+#endif
 #ifndef NFA_P2_DEEP
 #define NFA_P2_DEEP 0  // measured: 0.872 ms against 0.845 -- three claimed tasks per warp overrun the four-tile window
 #endif
@@ -596,7 +612,8 @@ template <bool CR, int THREADS, int NB>
 __global__ void __launch_bounds__(THREADS, 1)
     p2tet_elasticity_kernel(int nbuf_rt, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
                             const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
-                            const double *__restrict__ rec, int tile_stride, double *__restrict__ vals) {
+                            const double *__restrict__ rec, int tile_stride, double *__restrict__ vals,
+                            unsigned ell_size, unsigned n_slots, int n_tasks) {
     // NB > 0: the number of tiles is a compile-time power of two, so that the tile of a chunk ((c - c_begin) % NBUF) and its
     // round ((c - c_begin) / NBUF) cost a mask and a shift instead of two integer divisions per task (the task loop's scalar
     // bookkeeping is 40 % of the instructions the kernel executes)
@@ -684,6 +701,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         {
             const int t2 = grab_ahead();
             if (t2 < task_end) th2 = ld_list(task_hdr + t2);
+#if NFA_P2_STREAM_PF
+            if (lane == 0 && (t2 & 7) == 0 && t2 + NFA_P2_PFD_TH < n_tasks)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(task_hdr + t2 + NFA_P2_PFD_TH));
+#endif
         }
 #endif
         uint32_t n0 = 0xFFFFFFFFu, n1 = 0xFFFFFFFFu;  // first entries of task i+1
@@ -713,6 +734,17 @@ __global__ void __launch_bounds__(THREADS, 1)
             }
 #endif
         }
+#if NFA_P2_STREAM_PF
+        {
+            // as much of each list as this task consumes, a fixed distance further on in the stream
+            const int kmax0 = (th.x >> 8) & 0xFF;
+            const unsigned pe = (unsigned)th.y + NFA_P2_PFD_ELL + 32u * (unsigned)lane;
+            if (lane < kmax0 && pe < ell_size) asm volatile("prefetch.global.L2 [%0];" ::"l"(ell + pe));
+            const int per0 = ((th.x & 0xFF) == 4) ? 2 : 1;
+            const unsigned ps = (unsigned)th.z + NFA_P2_PFD_IH + 16u * (unsigned)lane;  // 16 slots = one 128-byte line
+            if (16 * lane < per0 * (th.w & 63) && ps < n_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(item_hdr + ps));
+        }
+#endif
         {
             const int type = th.x & 0xFF, kmax = (th.x >> 8) & 0xFF, n_items = th.w & 63, c = (int)((unsigned)th.w >> 6);
             const uint32_t *e = ell + (uint32_t)th.y + lane;
@@ -947,7 +979,7 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
     if (threads > 640) threads = 512;  // larger counts are staged-kernel settings
     using kern_t = void (*)(int, int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
-                            double *);
+                            double *, unsigned, unsigned, int);
     kern_t kern = nullptr;
     const bool nb4 = nbuf == 4 && !getenv("NFA_P2TET_RT_NBUF");
 #define NFA_P2_PICK(CRV, TH)                                                      \
@@ -968,7 +1000,8 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     if (timing_enabled()) timing_begin(s);
     kern<<<(unsigned)grid, threads, smem, s>>>(nbuf, (int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
                                                   (const int4 *)it.task_hdr.p, (const uint2 *)it.item_hdr.p,
-                                                  (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride, vals);
+                                                  (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride, vals,
+                                                  (unsigned)it.ell_size, (unsigned)it.n_items, (int)it.n_tasks);
     if (timing_enabled()) timing_end(s);
     NFA_LAUNCH_CHECK();
     return 0;

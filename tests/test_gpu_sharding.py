@@ -65,3 +65,48 @@ def test_sharded_assembly_matches_single_gpu(world, varying, graph):
             assert np.abs(vals[a:b] - g_vals[ga:gb]).max() <= 1e-13 * scale
         assert np.abs(rhs[rows] - g_rhs[rows]).max() <= 1e-13 * max(np.abs(g_rhs).max(), 1.0)
     assert owned_total == space.n_dof
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_memory_exchange_loopback(world):
+    """nfa_push_rows / nfa_pull_add_rows with the ranks' receive arenas wired directly (one process, one device, no CUDA
+    IPC): two consecutive steps exercise the flag / acknowledgement epochs; owned rows equal the single-GPU assembly."""
+    from nfempy_b200 import _lib
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.assembly.sharding import ShardedAssembler
+    from nfempy_b200.weak_forms import LEPrimalWeakForm
+
+    mesh = box_tet_mesh(3, nx=6, jitter=0.2)
+    space = ProductSpace({"u": (3, 3, "Lagrange", 2, mesh)})
+    space.build_structures({"u": [1]}, {})
+    n_cells = len(space.discrete_spaces["u"].elements)
+    form = LEPrimalWeakForm(space)
+    form.functions = {"rhs": _f, "lambda": lambda x, y, z: 2.0 * np.ones_like(x), "mu": lambda x, y, z: np.ones_like(x)}
+    ref = GPUAssembler(space, None, np.zeros(space.n_dof))
+    ref.form_to_input_list = {"volume": ["form", range(n_cells), form, None]}
+    g_indptr, g_indices, g_vals, g_rhs = ref.assemble()
+    ranks = [ShardedAssembler(space, form, world, r).prepare() for r in range(world)]
+    arenas = [sa._p2p_alloc() for sa in ranks]
+    for r, sa in enumerate(ranks):
+        sa._p2p_wire(arenas[r], {q: arenas[q]["base"] for q in range(world)}, {q: arenas[q]["table"] for q in range(world)})
+    for _ in range(2):
+        for sa in reversed(ranks):  # one stream: a rank's pulls need the higher ranks' pushes to be queued before them
+            sa.assemble()
+    import torch
+
+    torch.cuda.synchronize()
+    assert _lib.load().nfa_p2p_timeouts() == 0
+    scale = np.abs(g_vals).max()
+    for sa in ranks:
+        indptr = sa.plan.indptr.cpu().numpy()
+        vals, rhs = sa.vals.cpu().numpy(), sa.rhs.cpu().numpy()
+        for r in sa.shard.owned_rows:
+            a, b, ga, gb = indptr[r], indptr[r + 1], g_indptr[r], g_indptr[r + 1]
+            assert np.abs(vals[a:b] - g_vals[ga:gb]).max() <= 1e-13 * scale
+        rows = sa.shard.owned_rows
+        assert np.abs(rhs[rows] - g_rhs[rows]).max() <= 1e-13 * max(np.abs(g_rhs).max(), 1.0)
+    for a in arenas:
+        import ctypes
+
+        _lib.load().nfa_p2p_free(ctypes.c_void_p(a["base"]))
