@@ -25,6 +25,8 @@ callables so that the same code runs over NCCL on device buffers and over gloo o
 """
 import numpy as np
 
+from ..mesh import _accel
+
 
 class ShardPlan:
     def __init__(self, dest, n_dof, world, rank, bounds=None):
@@ -37,13 +39,14 @@ class ShardPlan:
         c0, c1 = int(self.bounds[rank]), int(self.bounds[rank + 1])
         cell_rank = np.searchsorted(self.bounds, np.arange(n_cells), side="right") - 1
         first_cell = np.full(self.n_dof, n_cells, dtype=np.int64)
-        np.minimum.at(first_cell, dest.ravel(), np.repeat(np.arange(n_cells), n_loc))
+        touched, first_pos = _accel.unique(dest.ravel(), return_index=True)  # cells ascend along the flattened table
+        first_cell[touched] = first_pos // n_loc
         owner = np.full(self.n_dof, -1, dtype=np.int64)
         touched_any = first_cell < n_cells
         owner[touched_any] = cell_rank[first_cell[touched_any]]
         self.owner = owner
         self.own_cells = np.arange(c0, c1, dtype=np.int64)
-        rows_touched = np.unique(dest[c0:c1])
+        rows_touched = _accel.unique(dest[c0:c1].ravel())
         self.rows_touched = rows_touched
         mask = np.zeros(self.n_dof, dtype=bool)
         mask[rows_touched] = True
@@ -61,7 +64,7 @@ class ShardPlan:
         # rows I own that higher ranks touch -> I receive their partial sums (same lists, computed locally)
         self.recv_rows = {}
         for q in range(rank + 1, world):
-            rq = np.unique(dest[int(self.bounds[q]) : int(self.bounds[q + 1])])
+            rq = _accel.unique(dest[int(self.bounds[q]) : int(self.bounds[q + 1])].ravel())
             rq = rq[owner[rq] == rank]
             if len(rq):
                 self.recv_rows[q] = rq.astype(np.int32)

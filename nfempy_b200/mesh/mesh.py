@@ -16,6 +16,7 @@ numpy arrays and ``mesh.cells[id]`` builds a ``MeshCell`` view on demand.
 """
 import numpy as np
 
+from . import _accel
 from .mesh_cell import MeshCell
 from .msh_reader import read_msh
 
@@ -28,23 +29,21 @@ NO_MATERIAL = -1
 
 def _first_appearance(keys):
     """Rank of each key by order of first appearance, plus the number of distinct keys."""
-    uniq, first, inv = np.unique(keys, return_index=True, return_inverse=True)
-    order = np.argsort(first, kind="stable")
-    rank = np.empty(len(uniq), dtype=np.int64)
-    rank[order] = np.arange(len(uniq))
-    return rank[inv], uniq[order]
+    uniq, first = _accel.unique(keys, return_index=True)
+    order = _accel.argsort(first)
+    return None, uniq[order]
 
 
 class _SortedLookup:
     """key -> id for a set of distinct int64 keys."""
 
     def __init__(self, keys, ids):
-        o = np.argsort(keys, kind="stable")
+        o = _accel.argsort(keys)
         self.keys = keys[o]
         self.ids = ids[o]
 
     def __call__(self, keys):
-        pos = np.searchsorted(self.keys, keys)
+        pos = _accel.searchsorted(self.keys, keys)
         pos = np.minimum(pos, max(len(self.keys) - 1, 0))
         if len(self.keys) == 0 or not np.array_equal(self.keys[pos], keys):
             raise KeyError("unknown mesh entity")
@@ -125,7 +124,7 @@ class Mesh:
             return a * P + b
 
         def face_key(trip):
-            s = np.sort(trip, axis=-1)
+            s = _accel.sort_last(trip)
             return (s[..., 0] * P + s[..., 1]) * P + s[..., 2]
 
         # ---- numbering scan (tets, triangles, lines) R/src/mesh/mesh.py:252-324
@@ -136,13 +135,11 @@ class Mesh:
         f_scan = np.concatenate([face_key(tets[:, TET_FACES]).ravel(), face_key(tris)])
         _, f_keys = _first_appearance(f_scan)
         # volumes: distinct sorted node 4-tuples in first-appearance order; pack via (face key of 3 smallest, largest)
-        ts = np.sort(tets, axis=1)
+        ts = _accel.sort_last(tets)
         t_face = (ts[:, 0] * P + ts[:, 1]) * P + ts[:, 2]
         if len(tets):
-            _, t_first, t_inv = np.unique(
-                np.stack([t_face, ts[:, 3]], axis=1), axis=0, return_index=True, return_inverse=True
-            )
-            t_order = np.argsort(t_first, kind="stable")
+            t_first, t_inv = _accel.unique_rows2(t_face, ts[:, 3])
+            t_order = _accel.argsort(t_first)
             t_rank = np.empty(len(t_first), dtype=np.int64)
             t_rank[t_order] = np.arange(len(t_first))
             tet_vol = t_rank[t_inv.ravel()]
@@ -180,7 +177,7 @@ class Mesh:
             elif name == "triangle":
                 ids = face_id(face_key(conn))
                 # insert_polygon creates the face, which first creates its (sorted) edges
-                pairs = np.sort(conn[:, TRI_EDGES], axis=-1).reshape(-1, 2)
+                pairs = _accel.sort_last(conn[:, TRI_EDGES]).reshape(-1, 2)
                 e_cand_id.append(edge_id(edge_key(pairs)))
                 e_cand_nodes.append(pairs)
                 f_cand_id.append(ids)
@@ -196,7 +193,7 @@ class Mesh:
                 vids = tet_vol[tet_seen : tet_seen + len(conn)]
                 tet_seen += len(conn)
                 # first creator keeps node order; later duplicates only overwrite the material id
-                uniq_v, first_v = np.unique(vids, return_index=True)
+                uniq_v, first_v = _accel.unique(vids, return_index=True)
                 fresh = ~vol_done[uniq_v]
                 vol_nodes[uniq_v[fresh]] = conn[first_v[fresh]]
                 vol_done[uniq_v] = True
@@ -209,7 +206,7 @@ class Mesh:
             if len(cand_id):
                 ids = np.concatenate(cand_id) - base
                 cn = np.concatenate(cand_nodes, axis=0)
-                uniq, first = np.unique(ids, return_index=True)
+                uniq, first = _accel.unique(ids, return_index=True)
                 nodes[uniq] = cn[first]
             return nodes
 
@@ -219,7 +216,7 @@ class Mesh:
         self.material = material
         # sub-entity tables (R/src/mesh/mesh.py:150-216)
         self.face_edges = (
-            edge_id(edge_key(np.sort(self.face_nodes[:, TRI_EDGES], axis=-1))) if nf else np.zeros((0, 3), dtype=np.int64)
+            edge_id(edge_key(_accel.sort_last(self.face_nodes[:, TRI_EDGES]))) if nf else np.zeros((0, 3), dtype=np.int64)
         )
         self.vol_edges = (
             edge_id(edge_key(self.vol_nodes[:, TET_EDGES])) if n_vol else np.zeros((0, 6), dtype=np.int64)
@@ -230,7 +227,7 @@ class Mesh:
         self._vol_first_tet = vol_first_tet
         created[nv:] = True
         if ne:
-            created[np.unique(self.edge_nodes)] = True
+            created[self.edge_nodes.ravel()] = True
         self._created_vertex = created[:nv]
 
     # -- array accessors used by the spaces layer ----------------------------------------------

@@ -16,6 +16,7 @@ The reference answers ``destination_indices`` with networkx + dict look-ups per 
 import numpy as np
 
 from ..basis.reference_element import create_element
+from ..mesh import _accel
 from ..basis.finite_element import FiniteElementView
 
 _VECTOR_FAMILIES = ("RT", "BDM", "N1E", "N2E")
@@ -40,8 +41,8 @@ class MeshTopology:
         self.entity_pos = {}
         for d in range(dim + 1):
             sub = mesh.sub_cells_of(dim, d)[self.selected_local].ravel()
-            uniq, first = np.unique(sub, return_index=True)
-            order = np.argsort(first, kind="stable")
+            uniq, first = _accel.unique(sub, return_index=True)
+            order = _accel.argsort(first)
             self.entity_ids[d] = uniq[order]
             pos = np.full(int(mesh.offset[d + 1] - mesh.offset[d]), -1, dtype=np.int64)
             pos[self.entity_ids[d] - mesh.offset[d]] = np.arange(len(order))
@@ -61,7 +62,7 @@ class MeshTopology:
         mesh, dim = self.mesh, self.dimension
         sub = mesh.sub_cells_of(dim, dim - 1)[self.selected_local]
         flat = sub.ravel()
-        uniq, first = np.unique(flat, return_index=True)
+        uniq, first = _accel.unique(flat, return_index=True)
         where = np.searchsorted(uniq, facet_ids)
         if np.any(where >= len(uniq)) or not np.array_equal(uniq[np.minimum(where, len(uniq) - 1)], facet_ids):
             raise ValueError("MeshTopology: facet without a neighbour cell in the selected sub-domain")
