@@ -326,6 +326,20 @@ int nfa_local_h1_multifield(int dim, int n_q, int n_phi, int n_loc, int n_crow, 
                             int64_t n_cells, const double *d_alpha, const int32_t *d_dest, double *d_Ke, double *d_re,
                             nfa_stream stream);
 
+/* ---- H(curl) fields (first-kind Nedelec "N1E", covariant Piola map phi = J^{-T} phi_hat) of L2ProjectorWeakForm
+ * (R/src/weak_forms/l2_projector_weak_form.py:8-93; the family reaches it through FiniteElement.evaluate_basis,
+ * R/src/basis/finite_element.py:156-186, and permute_and_transform, R/src/basis/permute_and_transform.py:8-54) and of
+ * l2_error (R/src/postprocess/l2_error_post_processor.py:7-63).  d_val [n_q][n_phi][dim] reference values, d_signs int8
+ * [n_cells][n_phi] = the edge-orientation factor of every dof, d_f / d_exact [n_cells][n_q][3] host-evaluated data.
+ *   Ke[a][b] = sum_q w det phi_a . phi_b,  re[a] = r_sign sum_q w det f . phi_a;   out[cell] = int |exact - u_h|^2. */
+int nfa_local_hcurl_mass(int dim, int n_phi, int n_q, const double *d_val, const double *d_weights, const int8_t *d_signs,
+                         const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_f,
+                         double r_sign, double *d_Ke, double *d_re, nfa_stream stream);
+int nfa_hcurl_field_error(int dim, int n_phi, int n_q, const double *d_val, const double *d_weights, const int8_t *d_signs,
+                          const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_alpha,
+                          const int32_t *d_dest, int dest_stride, int dest_off, const double *d_exact, double *d_out,
+                          nfa_stream stream);
+
 /* ---- interface-row exchange over NVLink peer memory (multi-GPU extension; the reference is one process).
  * nfa_p2p_alloc: cudaMalloc'ed, zeroed area + its 64-byte CUDA IPC handle; nfa_p2p_open maps a peer's area into this
  * process (peer access enabled lazily); nfa_p2p_close / nfa_p2p_free release them.

@@ -47,6 +47,24 @@ def facet_cases(mesh, dim, selected_local):
     raise NotImplementedError("orientation cases for dimension %d" % dim)
 
 
+def edge_signs(mesh, dim, selected_local):
+    """``int8[n_cells, n_edges]`` factor of every edge dof of the lowest-order Nedelec element ("N1E":
+    ``transformations["interval"][0] = [-1]``): -1 for an edge the reference finds mis-oriented, +1 otherwise.
+    2-D (R/src/basis/permute_and_transform.py:8-19): oriented iff the cell's local edge vertices equal the edge cell's
+    own ``node_tags``, order included; 3-D (:38-54): oriented iff they equal the SORTED tags, i.e. ascend."""
+    if dim == 2:
+        return np.where(facet_cases(mesh, 2, selected_local) == 0, 1, -1).astype(np.int8)
+    if dim == 3:
+        from ..mesh.mesh import TET_EDGES
+
+        tets = mesh.vol_nodes[selected_local]
+        out = np.empty((len(tets), 6), dtype=np.int8)
+        for e, (a, b) in enumerate(TET_EDGES):
+            out[:, e] = np.where(tets[:, a] < tets[:, b], 1, -1)
+        return out
+    raise NotImplementedError("edge orientation for dimension %d" % dim)
+
+
 def case_matrices(ref_element):
     """``float64[n_cases, nfd, nfd]`` with ``T[0] = I`` (n_cases = 6 in 3-D, 2 in 2-D)."""
     dim = ref_element.dim

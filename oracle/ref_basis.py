@@ -73,6 +73,10 @@ def num_entity_dofs(family, dim, k, discontinuous):
         facet = k + 1 if dim == 2 else (k + 1) * (k + 2) // 2
         interior = (k - 1) * (k + 1) if dim == 2 else (k - 1) * (k + 1) * (k + 2) // 2
         per = [0] * (dim - 1) + [facet, interior]
+    elif family == "N1E":
+        if k != 1:
+            raise NotImplementedError("oracle N1E degree >= 2")
+        per = [0, 1, 0, 0][: dim + 1]  # one tangential moment per edge
     else:
         raise NotImplementedError(family)
     out = [[per[d]] * len(SUB[dim][d]) for d in range(dim + 1)]

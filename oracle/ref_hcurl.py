@@ -1,0 +1,58 @@
+"""ORACLE (test infrastructure only -- never imported by the product path).
+
+Lowest-order first-kind Nedelec element ("N1E", the Whitney edge element) written directly in PHYSICAL coordinates,
+independently of the product's reference tables and covariant map (nfempy_b200/basis/hcurl.py, csrc/nfa_hcurl.cu):
+
+    phi_e = s_e (lam_a grad lam_b - lam_b grad lam_a),   e = (a, b) in the reference's local edge order
+    (R/src/mesh/mesh.py:187-203: tetrahedron (2,3),(1,3),(1,2),(0,3),(0,2),(0,1); triangle (1,2),(0,2),(0,1)),
+
+with the physical gradients of the barycentric coordinates -- which is what basix' covariant push-forward of the
+reference Whitney functions gives (R/src/basis/finite_element.py:156-186).  ``s_e = -1`` for an edge the reference finds
+mis-oriented (R/src/basis/permute_and_transform.py:8-19 in 2-D: local edge vertices differ from the edge cell's own
+node_tags; :38-54 in 3-D: they do not ascend), since ``transformations["interval"][0] = [-1]`` for this element.
+
+PARITY UNPINNED against real basix (see oracle/ref_basis.py).
+"""
+import numpy as np
+
+from .ref_basis import SUB
+
+
+def whitney(space, cell_id, points):
+    """``(x[nq, 3], det, phi[nq, n_edges, 3])`` of the oriented Whitney functions of one cell at reference ``points``."""
+    mesh = space.mesh
+    cell = mesh.cells[cell_id]
+    dim = cell.dimension
+    X = mesh.points[cell.node_tags]  # [dim+1, 3]
+    J = (X[1:] - X[0]).T  # [3, dim]
+    G = J.T @ J
+    det = np.sqrt(np.linalg.det(G))
+    Jinv = np.linalg.solve(G, J.T)  # [dim, 3]
+    glam = np.concatenate([-Jinv.sum(axis=0, keepdims=True), Jinv], axis=0)  # [dim+1, 3] physical gradients
+    points = np.asarray(points, dtype=float).reshape(-1, dim)
+    lam = np.concatenate([1.0 - points.sum(axis=1, keepdims=True), points], axis=1)  # [nq, dim+1]
+    x = lam @ X
+    phi = np.zeros((len(points), len(SUB[dim][1]), 3))
+    for e, (a, b) in enumerate(SUB[dim][1]):
+        local = cell.node_tags[[a, b]]
+        if dim == 2:
+            own = mesh.cells[cell.sub_cells_ids[1][e]].node_tags
+            oriented = np.array_equal(local, own)
+        else:
+            oriented = local[0] < local[1]
+        s = 1.0 if oriented else -1.0
+        phi[:, e, :] = s * (lam[:, [a]] * glam[b][None, :] - lam[:, [b]] * glam[a][None, :])
+    return x, det, phi
+
+
+def l2_projector(space, functions, iel, alpha):
+    """L2ProjectorWeakForm.evaluate_form (R/src/weak_forms/l2_projector_weak_form.py:8-93) for a space whose single field
+    is N1E of degree 1: ``J = int phi . phi``, ``r = -int f . phi``."""
+    (name, sp), = space.discrete_spaces.items()
+    dim = sp.dimension
+    points, weights = space.quadrature[dim]
+    x, det, phi = whitney(sp, sp.element_ids[iel], points)
+    f = np.asarray(functions[name](x[:, 0], x[:, 1], x[:, 2]))[0]  # [3, nq]
+    j_el = np.einsum("q,qad,qbd->ab", det * weights, phi, phi)
+    r_el = -np.einsum("q,qad,dq->a", det * weights, phi, f)
+    return r_el, j_el

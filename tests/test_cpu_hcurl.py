@@ -60,3 +60,38 @@ def test_tangential_continuity_across_cells(dim):
                 seen[key] = t_comp
             assert abs(t_comp - 1.0) < 1e-12  # unit tangential moment along the globally oriented edge
     assert checked > 10
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_mapped_oriented_basis_equals_the_physical_whitney_functions(dim):
+    """What the CUDA kernels of csrc/nfa_hcurl.cu evaluate -- reference tables, covariant map, edge signs from
+    basis/orientation.edge_signs -- against the oracle's Whitney functions written directly in physical coordinates, on
+    every cell of a jittered mesh with shuffled local vertices; and the N1E destination tables of product and oracle."""
+    from nfempy_b200.basis.hcurl import covariant_piola
+    from nfempy_b200.basis.orientation import edge_signs
+    from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
+    from nfempy_b200.spaces import ProductSpace
+    from oracle import ref_hcurl
+    from oracle.ref_mesh import RefMesh
+    from oracle.ref_spaces import RefProductSpace
+
+    mesh = box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(3, jitter=0.2)
+    space = ProductSpace({"e": (dim, 1, "N1E", 1, mesh)})
+    space.build_structures({"e": [1]}, {})
+    s = space.discrete_spaces["e"]
+    r = RefMesh(dim, mesh.points, mesh._blocks)
+    r.build_conformal_mesh()
+    rs = RefProductSpace({"e": (dim, 1, "N1E", 1, r)})
+    rs.build_structures({"e": [1]}, {})
+    dest = np.asarray(space.destination_table())
+    assert np.array_equal(dest, np.array([rs.destination_indexes(i) for i in range(len(dest))]))
+    pts, _ = space.quadrature[dim]
+    sg = edge_signs(mesh, dim, s.mesh_topology.selected_local)
+    tab = s.ref_element.tabulate(0, pts)[0]
+    cn = s.cell_nodes()
+    assert (sg == -1).any() and (sg == 1).any()
+    for i in range(len(cn)):
+        X = mesh.points[cn[i]]
+        phi = covariant_piola(tab, (X[1:] - X[0]).T) * sg[i][None, :, None]
+        _, _, ref = ref_hcurl.whitney(rs.discrete_spaces["e"], rs.discrete_spaces["e"].element_ids[i], pts)
+        assert np.abs(phi - ref[:, :, : phi.shape[2]]).max() <= 1e-12
