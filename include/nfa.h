@@ -326,6 +326,22 @@ int nfa_local_h1_multifield(int dim, int n_q, int n_phi, int n_loc, int n_crow, 
                             int64_t n_cells, const double *d_alpha, const int32_t *d_dest, double *d_Ke, double *d_re,
                             nfa_stream stream);
 
+/* ---- mixed-dimensional Robin coupling across a fracture cell: CouplingWeakForm.evaluate_form
+ * (R/examples/md_elliptic_scalar/CouplingWeakForm.py:11-151), scattered by the drivers' interface closure
+ * (R/examples/md_elliptic_scalar/md_elliptic_scalar.py:284-342; library types R/src/assembly/ScatterFormData.py:59-76).
+ * Per interface cell: the boundary facet of the higher-dimensional domain on its + side (arrays *_a) and on its - side
+ * (*_b), each described like the facets of nfa_local_hdiv_facet (trace table index, orientation case, facet / neighbour
+ * vertices, outward normal of the neighbour); d_p_val [n_q][n_p] the fracture's potential basis at the facet points;
+ * d_ainv [n_items][n_q] = (delta / 2) / kappa_normal.  Local dofs [u_+ (nfd) | u_- (nfd) | p (n_p)]; writes
+ * Ke [n_items][n_loc][n_loc] (zero blocks stored) and re = Ke alpha_l (0 without a state vector). */
+int nfa_local_hdiv_coupling(int dim, int nfd, int n_p, int n_q, const double *d_trace_tab, const double *d_weights,
+                            const double *d_Tcases, const double *d_coords, const int32_t *d_tidx_a,
+                            const int8_t *d_cases_a, const int32_t *d_facet_nodes_a, const int32_t *d_neigh_nodes_a,
+                            const double *d_normals_a, const int32_t *d_tidx_b, const int8_t *d_cases_b,
+                            const int32_t *d_facet_nodes_b, const int32_t *d_neigh_nodes_b, const double *d_normals_b,
+                            const double *d_p_val, const double *d_ainv, int64_t n_items, const double *d_alpha,
+                            const int32_t *d_dest, double *d_Ke, double *d_re, nfa_stream stream);
+
 /* ---- H(curl) fields (first-kind Nedelec "N1E", covariant Piola map phi = J^{-T} phi_hat) of L2ProjectorWeakForm
  * (R/src/weak_forms/l2_projector_weak_form.py:8-93; the family reaches it through FiniteElement.evaluate_basis,
  * R/src/basis/finite_element.py:156-186, and permute_and_transform, R/src/basis/permute_and_transform.py:8-54) and of

@@ -55,6 +55,7 @@ SIGNATURES = {
     "nfa_csr_spmv": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "nfa_pack_rows": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "nfa_unpack_add_rows": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nfa_local_hdiv_coupling": (_i, [_i, _i, _i, _i] + [_vp] * 16 + [_i64] + [_vp] * 5),
     "nfa_local_hcurl_mass": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _d, _vp, _vp, _vp]),
     "nfa_hcurl_field_error": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "nfa_p2p_alloc": (_i, [_i64, ctypes.POINTER(_vp), _vp]),

@@ -23,7 +23,7 @@ from ..device import space_device
 from ..weak_forms.weak_form import BatchedWeakForm
 from .csr_matrix import CSRMatrix
 
-_SUPPORTED = ("form", "bc_form", "time_dependent_form", "time_dependent_bc_form")
+_SUPPORTED = ("form", "bc_form", "time_dependent_form", "time_dependent_bc_form", "interface_form")
 _KNOWN = (
     "form", "bc_form", "interface_form", "bc_interface_form", "time_dependent_form", "time_dependent_bc_form",
 )
@@ -41,6 +41,29 @@ def _as_items(sequence, n_total):
     if len(items) and (items.min() < 0 or items.max() >= n_total):
         raise IndexError("GPUAssembler: element index out of range")
     return items
+
+
+class SpaceGroup:
+    """The spaces of a mixed-dimensional problem stacked into one system the way the reference drivers do by hand
+    (R/examples/md_elliptic_scalar/md_elliptic_scalar.py:205-212): space k occupies the dofs
+    ``[dof_shift_k, dof_shift_k + n_dof_k)``; the caller sets the shifts (``ProductSpace.dof_shift``)."""
+
+    def __init__(self, spaces):
+        self.spaces = list(spaces)
+        if not self.spaces:
+            raise ValueError("SpaceGroup: no spaces")
+        self.discrete_spaces = {}  # no single field list: forms address their own space
+        self.dof_shift = 0
+
+    @property
+    def n_dof(self):
+        return int(max(s.dof_shift + s.n_dof for s in self.spaces))
+
+
+def _primary_space(form):
+    if hasattr(form, "primary_space"):
+        return form.primary_space()
+    return form.space
 
 
 class _Plan:
@@ -92,6 +115,8 @@ class GPUAssembler:
             raise ValueError("GPUAssembler: unknown pattern policy %r" % (pattern_policy,))
         self.pattern_policy = pattern_policy
         self.explicit_diagonal = bool(explicit_diagonal)
+        if isinstance(space, (list, tuple)):  # mixed-dimensional problem: one system over several product spaces
+            space = SpaceGroup(space)
         self.space = space
         self.jacobian = jacobian if jacobian is not None else CSRMatrix(getattr(space, "n_dof", None))
         self.residual = residual
@@ -143,12 +168,23 @@ class GPUAssembler:
                 )
             if form.form_kind != form_type:
                 raise ValueError("GPUAssembler: %s is a %r, listed as %r" % (type(form).__name__, form.form_kind, form_type))
-            items = _as_items(sequence, form.n_items_total())
+            if form_type == "interface_form":
+                # (c1_idx, c0_p_idx, c0_n_idx) triples -- or the library's (idx, (idx_p, idx_n)) nesting
+                # (R/src/assembly/ScatterFormData.py:59-68) -- handed to the form, which owns the destination rule
+                if not hasattr(form, "interface_dest"):
+                    raise NotImplementedError("GPUAssembler: %s does not describe its interface destinations" % type(form).__name__)
+                rows = [[int(e[0]), int(e[1][0]), int(e[1][1])] if np.ndim(e[1]) else [int(v) for v in e] for e in sequence] \
+                    if not isinstance(sequence, np.ndarray) else sequence
+                items = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
+            else:
+                items = _as_items(sequence, form.n_items_total())
             out.append((name, form_type, items, form, (alpha, t) if t is not None else alpha))
         return out
 
     @staticmethod
     def _dest_dev(dev, form, items):
+        if form.form_kind == "interface_form":
+            return torch.as_tensor(np.ascontiguousarray(form.interface_dest(items), dtype=np.int32)).to(dev.device)
         full = dev.dest() if form.form_kind in ("form", "time_dependent_form") else dev.bc_dest()
         if items is None:
             return full
@@ -158,7 +194,9 @@ class GPUAssembler:
     def _plan_key(self, entries, fused_index):
         key = [self.space.n_dof, self.space.dof_shift, fused_index]
         for name, kind, items, form, _ in entries:
-            key.append((kind, id(form.space), type(form).__name__, None if items is None else items.tobytes()))
+            spaces = form.space if isinstance(form.space, (list, tuple)) else [form.space]
+            key.append((kind, tuple((id(sp), sp.dof_shift) for sp in spaces), type(form).__name__,
+                        None if items is None else items.tobytes()))
         return tuple(key)
 
     def _build_plan(self, dev, entries, dests, fused_index):
@@ -287,6 +325,7 @@ class GPUAssembler:
     def _entry_data(self, dev, kind, items, form, t):
         """``(FormData, dest)`` of one entry: from the cache when form / sequence / functions / t are the ones seen
         before, else evaluated (``form.prepare``: host callables over all quadrature points, upload)."""
+        dev = space_device(_primary_space(form), self.device)  # the form's own space (mixed-dimensional lists mix spaces)
         sig = self._signature(kind, items, form, t)
         previous = None
         if self.cache_coefficients:
@@ -305,6 +344,7 @@ class GPUAssembler:
             data = form.prepare(dev, items)
         dest = previous[1] if previous else self._dest_dev(dev, form, items)
         data.device_key = (dev.device, id(dev))
+        data.dev = dev
         data.alpha_dev = None
         data.alpha_zero = True
         if self.cache_coefficients:
@@ -316,12 +356,18 @@ class GPUAssembler:
     def prepare(self):
         """Evaluates the coefficient callables (or fetches their cached device arrays), uploads the state vectors and
         builds (or fetches) the sparsity plan.  Returns the state ``run`` consumes."""
-        dev = space_device(self.space, self.device)
+        first = self.space.spaces[0] if isinstance(self.space, SpaceGroup) else self.space
+        dev = space_device(first, self.device)
         with torch.cuda.device(dev.device):  # libnfa launches on the current device
             return self._prepare(dev)
 
     def _prepare(self, dev):
         entries = self._entries()
+        if isinstance(self.space, SpaceGroup):
+            for (_, _, _, form, _) in entries:
+                for sp in (form.space if isinstance(form.space, (list, tuple)) else [form.space]):
+                    if not any(sp is known for known in self.space.spaces):
+                        raise ValueError("GPUAssembler: %s works on a space outside the assembler's group" % type(form).__name__)
         datas, dests = [], []
         for (_, kind, items, form, al) in entries:
             data, dest = self._entry_data(dev, kind, items, form, al[1] if "time_dependent" in kind else None)
@@ -401,7 +447,7 @@ class GPUAssembler:
                 nl = form.n_loc()
                 Ke = torch.empty((data.n_items, nl, nl), dtype=torch.float64, device=dev.device)
                 re = torch.empty((data.n_items, nl), dtype=torch.float64, device=dev.device)
-                form.launch_local(dev, data, first_dev, dest, Ke, re, second_dev)
+                form.launch_local(data.dev, data, first_dev, dest, Ke, re, second_dev)
                 Ke_list[i], re_list[i] = Ke, re
                 keep += [Ke, re, first_dev, second_dev]
                 continue
@@ -431,11 +477,11 @@ class GPUAssembler:
                 jac.is_zero = False
                 if data.f is not None:
                     re = torch.empty((data.n_items, form.n_loc()), dtype=torch.float64, device=dev.device)
-                    form.launch_load(dev, data, re)
+                    form.launch_load(data.dev, data, re)
                     re_list[i] = re
                     keep.append(re)
             else:
-                Ke, re = form.local_blocks(dev, data, alpha_dev, dest if alpha_dev is not None else None)
+                Ke, re = form.local_blocks(data.dev, data, alpha_dev, dest if alpha_dev is not None else None)
                 Ke_list[i], re_list[i] = Ke, re
                 keep += [Ke, re, alpha_dev]
         ke_ptrs = (ctypes.c_void_p * nseg)(*[None if k is None else k.data_ptr() for k in Ke_list])
@@ -505,7 +551,7 @@ class GPUAssembler:
             if "time_dependent" in kind:
                 raise NotImplementedError("GPUAssembler: filtered patterns are implemented for form / bc_form lists")
             alpha_dev = None if data.alpha_zero else data.alpha_dev
-            Ke, re = form.local_blocks(dev, data, alpha_dev, dest if alpha_dev is not None else None)
+            Ke, re = form.local_blocks(data.dev, data, alpha_dev, dest if alpha_dev is not None else None)
             value_kept = (Ke - 1.0e-16).abs() > tol
             mask = value_kept.clone()
             if self.pattern_policy == "filtered_upper":

@@ -708,6 +708,118 @@ __global__ void __launch_bounds__(128)
 }
 
 
+// Mixed-dimensional Robin coupling across a fracture cell (CouplingWeakForm, R/examples/md_elliptic_scalar/
+// CouplingWeakForm.py:11-151): the fracture cell c1 faces one boundary facet of the higher-dimensional domain on each
+// side (+ / -).  With phi^s_k = psi^s_k . n_s the normal traces of the neighbours' facet functions (s = +, -), P_m the
+// fracture's potential basis and 1/alpha = (delta / 2) / kappa_n, local dofs [u_+ (nfd) | u_- (nfd) | p (n_p)]:
+//   J[u_s, u_s] = sum_q det_F w (1/alpha) phi^s phi^s^T,   J[u_s, p] = sum_q det_F w phi^s P^T,   J[p, u_s] = its transpose,
+//   J[u_+, u_-] = J[p, p] = 0 (stored zeros: the reference scatters the whole local matrix),   r = J alpha_l.
+// One warp per interface cell; the traces of both sides are staged in shared memory.
+template <int DIM>
+__global__ void __launch_bounds__(128)
+    local_hdiv_coupling_kernel(int nfd, int n_p, int n_q, const double *__restrict__ trace_tab, const double *__restrict__ weights,
+                               const double *__restrict__ Tcases, const double *__restrict__ coords,
+                               const int32_t *__restrict__ tidx_a, const int8_t *__restrict__ cases_a,
+                               const int32_t *__restrict__ facet_a, const int32_t *__restrict__ neigh_a,
+                               const double *__restrict__ normals_a, const int32_t *__restrict__ tidx_b,
+                               const int8_t *__restrict__ cases_b, const int32_t *__restrict__ facet_b,
+                               const int32_t *__restrict__ neigh_b, const double *__restrict__ normals_b,
+                               const double *__restrict__ p_val, const double *__restrict__ ainv, int64_t n_items,
+                               const double *__restrict__ alpha, const int32_t *__restrict__ dest, double *__restrict__ Ke,
+                               double *__restrict__ re) {
+    extern __shared__ double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_loc = 2 * nfd + n_p;
+    double *s_phi = smem + (size_t)warp * ((2 * nfd + 1) * n_q + n_loc);  // [2][n_q][nfd] traces, [n_q] det_F w, [n_loc] alpha
+    double *s_w = s_phi + 2 * nfd * n_q;
+    double *s_al = s_w + n_q;
+    for (int64_t it = (int64_t)blockIdx.x * 4 + warp; it < n_items; it += (int64_t)gridDim.x * 4) {
+        double det_f = 1.0;
+        for (int side = 0; side < 2; ++side) {
+            const int32_t *tidx = side ? tidx_b : tidx_a;
+            const int8_t *cases = side ? cases_b : cases_a;
+            const int32_t *neigh = side ? neigh_b : neigh_a;
+            const double *normals = side ? normals_b : normals_a;
+            double X[DIM + 1][3];
+            load_cell_coords<DIM>(coords, neigh, it, X);
+            Geom<DIM> g;
+            compute_geom<DIM>(X, g);
+            if (side == 0) {
+                double XF[DIM][3];
+                load_cell_coords<DIM - 1>(coords, facet_a, it, XF);
+                Geom<DIM - 1> gf;
+                compute_geom<DIM - 1>(XF, gf);
+                det_f = gf.det;
+            }
+            double jn[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                double v = 0.0;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) v += g.J[c][k] * normals[it * 3 + c];
+                jn[k] = v / g.det;
+            }
+            const double *T = Tcases + (int)cases[it] * nfd * nfd;
+            const double *tab = trace_tab + (int64_t)tidx[it] * n_q * nfd * DIM;
+            for (int e = lane; e < n_q * nfd; e += 32) {
+                const int q = e / nfd, k = e - q * nfd;
+                double flux = 0.0;
+                for (int b = 0; b < nfd; ++b) {
+                    const double *src = tab + ((int64_t)q * nfd + b) * DIM;
+                    double t = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < DIM; ++kk) t += jn[kk] * src[kk];
+                    flux += T[k * nfd + b] * t;
+                }
+                s_phi[(side * n_q + q) * nfd + k] = flux;
+            }
+        }
+        for (int q = lane; q < n_q; q += 32) s_w[q] = det_f * weights[q];
+        for (int j = lane; j < n_loc; j += 32) s_al[j] = alpha ? alpha[dest[it * n_loc + j]] : 0.0;
+        __syncwarp();
+        for (int e = lane; e < n_loc * n_loc; e += 32) {
+            const int i = e / n_loc, j = e - i * n_loc;
+            const int bi = i < nfd ? 0 : (i < 2 * nfd ? 1 : 2), bj = j < nfd ? 0 : (j < 2 * nfd ? 1 : 2);
+            double acc = 0.0;
+            if (bi < 2 && bj == bi) {
+                const double *pa = s_phi + bi * n_q * nfd + (i - bi * nfd), *pb = s_phi + bi * n_q * nfd + (j - bi * nfd);
+                for (int q = 0; q < n_q; ++q) acc += s_w[q] * ainv[it * n_q + q] * pa[q * nfd] * pb[q * nfd];
+            } else if (bi < 2 && bj == 2) {
+                const double *pa = s_phi + bi * n_q * nfd + (i - bi * nfd);
+                for (int q = 0; q < n_q; ++q) acc += s_w[q] * pa[q * nfd] * p_val[q * n_p + (j - 2 * nfd)];
+            } else if (bi == 2 && bj < 2) {
+                const double *pb = s_phi + bj * n_q * nfd + (j - bj * nfd);
+                for (int q = 0; q < n_q; ++q) acc += s_w[q] * p_val[q * n_p + (i - 2 * nfd)] * pb[q * nfd];
+            }
+            if (Ke) Ke[it * n_loc * n_loc + e] = acc;
+            // r_i = sum_j J_ij alpha_j: lanes of one row are combined below (n_loc is small: done per lane over all j)
+        }
+        for (int i = lane; i < n_loc; i += 32) {
+            double r = 0.0;
+            if (alpha) {
+                const int bi = i < nfd ? 0 : (i < 2 * nfd ? 1 : 2);
+                for (int j = 0; j < n_loc; ++j) {
+                    const int bj = j < nfd ? 0 : (j < 2 * nfd ? 1 : 2);
+                    double acc = 0.0;
+                    if (bi < 2 && bj == bi) {
+                        const double *pa = s_phi + bi * n_q * nfd + (i - bi * nfd), *pb = s_phi + bi * n_q * nfd + (j - bi * nfd);
+                        for (int q = 0; q < n_q; ++q) acc += s_w[q] * ainv[it * n_q + q] * pa[q * nfd] * pb[q * nfd];
+                    } else if (bi < 2 && bj == 2) {
+                        const double *pa = s_phi + bi * n_q * nfd + (i - bi * nfd);
+                        for (int q = 0; q < n_q; ++q) acc += s_w[q] * pa[q * nfd] * p_val[q * n_p + (j - 2 * nfd)];
+                    } else if (bi == 2 && bj < 2) {
+                        const double *pb = s_phi + bj * n_q * nfd + (j - bj * nfd);
+                        for (int q = 0; q < n_q; ++q) acc += s_w[q] * p_val[q * n_p + (i - 2 * nfd)] * pb[q * nfd];
+                    }
+                    r += acc * s_al[j];
+                }
+            }
+            re[it * n_loc + i] = r;
+        }
+        __syncwarp();
+    }
+}
+
 // Penalised normal trace ("Neumann" condition of the mixed elasticity forms: LCEDualWeakFormBCNeumann,
 // R/src/weak_forms/lce_dual_weak_form.py:759-871, le_dual_weak_form.py:581-644, lce_scaled_dual_weak_form.py:814-917):
 // with phi_k = psi_k . n the normal trace of the neighbour's facet functions, per component c of the row-wise field
@@ -1559,6 +1671,36 @@ extern "C" int nfa_field_error_scaled(int dim, int kind, int n_phi, int n_comp, 
     else
         return fail("nfa_field_error: unsupported dimension");
 #undef NFA_FE
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nfa_local_hdiv_coupling(int dim, int nfd, int n_p, int n_q, const double *trace_tab, const double *weights,
+                                       const double *Tcases, const double *coords, const int32_t *tidx_a,
+                                       const int8_t *cases_a, const int32_t *facet_a, const int32_t *neigh_a,
+                                       const double *normals_a, const int32_t *tidx_b, const int8_t *cases_b,
+                                       const int32_t *facet_b, const int32_t *neigh_b, const double *normals_b,
+                                       const double *p_val, const double *ainv, int64_t n_items, const double *alpha,
+                                       const int32_t *dest, double *Ke, double *re, nfa_stream stream) {
+    if (n_items == 0) return 0;
+    if (!trace_tab || !weights || !Tcases || !p_val || !ainv || !re) return fail("nfa_local_hdiv_coupling: NULL argument");
+    if (alpha && !dest) return fail("nfa_local_hdiv_coupling: a state vector needs the destination table");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n_loc = 2 * nfd + n_p;
+    const size_t smem = sizeof(double) * 4 * ((size_t)(2 * nfd + 1) * n_q + n_loc);
+    if (smem > 48 * 1024) return fail("nfa_local_hdiv_coupling: element too large for the shared-memory staging");
+    const int64_t ctas = (n_items + 3) / 4;
+    const int grid = (int)(ctas < 148 * 16 ? ctas : 148 * 16);
+    if (dim == 3)
+        local_hdiv_coupling_kernel<3><<<grid, 128, smem, s>>>(nfd, n_p, n_q, trace_tab, weights, Tcases, coords, tidx_a, cases_a,
+                                                             facet_a, neigh_a, normals_a, tidx_b, cases_b, facet_b, neigh_b,
+                                                             normals_b, p_val, ainv, n_items, alpha, dest, Ke, re);
+    else if (dim == 2)
+        local_hdiv_coupling_kernel<2><<<grid, 128, smem, s>>>(nfd, n_p, n_q, trace_tab, weights, Tcases, coords, tidx_a, cases_a,
+                                                             facet_a, neigh_a, normals_a, tidx_b, cases_b, facet_b, neigh_b,
+                                                             normals_b, p_val, ainv, n_items, alpha, dest, Ke, re);
+    else
+        return fail("nfa_local_hdiv_coupling: dim must be 2 or 3");
     NFA_LAUNCH_CHECK();
     return 0;
 }

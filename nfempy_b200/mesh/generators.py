@@ -105,3 +105,66 @@ def square_tri_mesh(n, jitter=0.0, seed=1234):
     mesh = Mesh.from_arrays(2, points, blocks)
     mesh.build_conformal_mesh()
     return mesh
+
+
+def fractured_box_tet_mesh(n, jitter=0.0, seed=1234, shuffle_local_nodes=False):
+    """Unit cube of ``n^3`` cubes x 6 Kuhn tetrahedra (``n`` even) cut by the horizontal fracture plane ``z = 1/2`` -- the
+    mixed-dimensional mesh of BASELINE config 5 ("fractured 3D mesh"), laid out the way the reference leaves a mesh after
+    ``cut_conformity_along_c1_lines`` (R/src/mesh/mesh_operations.py:274-398, which only handles 2-D): the fracture keeps
+    its own cells on the ORIGINAL nodes (triangles, tag 10; their boundary edges on the box sides, tag 30), and every
+    node of the plane is duplicated twice so that the tetrahedra above (``+``) and below (``-``) the plane no longer share
+    it; the faces of those tetrahedra on the plane are boundary facets of the 3-D domain (tag 50, "clones"), listed with
+    the same vertex order as the fracture triangle they face.  Blocks: six outer sides (tags 2..7), + clones, - clones,
+    fracture boundary edges, fracture triangles, tetrahedra (tag 1).
+
+    Returns ``(mesh, interface)`` with ``interface = {"c1": tri[m, 3], "positive": tri[m, 3], "negative": tri[m, 3]}``
+    (node tags of the fracture triangle and of its two clones, row by row) -- the triples the coupling form is
+    scattered over (R/examples/md_elliptic_scalar/md_elliptic_scalar.py:324-342).  The reference performs the cut in
+    place (clones get fresh cell ids appended to the mesh); here the cut mesh is numbered from scratch by
+    ``Mesh.build_conformal_mesh``, a different but equivalent numbering of the same cells."""
+    if n % 2:
+        raise ValueError("fractured_box_tet_mesh: n must be even (the fracture is the grid plane z = 1/2)")
+    points, tets, grid, dims = box_tet_points_cells(n, jitter, seed, shuffle_local_nodes)
+    k0 = n // 2
+    on_plane = grid[:, 2] == k0
+    points[on_plane, 2] = 0.5  # the plane stays flat under jitter
+    n0 = len(points)
+    plane_nodes = np.flatnonzero(on_plane)
+    slot = np.full(n0, -1, dtype=np.int64)
+    slot[plane_nodes] = np.arange(len(plane_nodes))
+    pos_of = np.arange(n0)
+    neg_of = np.arange(n0)
+    pos_of[plane_nodes] = n0 + slot[plane_nodes]
+    neg_of[plane_nodes] = n0 + len(plane_nodes) + slot[plane_nodes]
+    points = np.concatenate([points, points[plane_nodes], points[plane_nodes]], axis=0)
+    grid = np.concatenate([grid, grid[plane_nodes], grid[plane_nodes]], axis=0)
+    # a tet lies above the plane iff its lowest vertex does
+    above = grid[tets].min(axis=1)[:, 2] >= k0
+    # fracture triangles: faces of the tets above that lie in the plane, in that tet's local face order
+    faces = tets[above][:, TET_FACES].reshape(-1, 3)
+    c1 = faces[np.all(on_plane[faces], axis=1)]
+    new_tets = tets.copy()
+    new_tets[above] = pos_of[tets[above]]
+    new_tets[~above] = neg_of[tets[~above]]
+    positive, negative = pos_of[c1], neg_of[c1]
+    # boundary edges of the fracture: edges of its triangles on the four vertical sides of the box
+    e = c1[:, TRI_EDGES].reshape(-1, 2)
+    eg = grid[e]
+    side = np.zeros(len(e), dtype=bool)
+    for axis, value in ((0, 0), (0, dims[0]), (1, 0), (1, dims[1])):
+        side |= np.all(eg[:, :, axis] == value, axis=1)
+    c1_boundary = e[side]
+    all_faces = new_tets[:, TET_FACES].reshape(-1, 3)
+    fg = grid[all_faces]
+    blocks = []
+    for tag, axis, value in [(2, 1, 0), (3, 0, dims[0]), (4, 1, dims[1]), (5, 0, 0), (6, 2, dims[2]), (7, 2, 0)]:
+        tri = all_faces[np.all(fg[:, :, axis] == value, axis=1)]
+        blocks.append(("triangle", tri, np.full(len(tri), tag, dtype=np.int64)))
+    blocks.append(("triangle", positive, np.full(len(positive), 50, dtype=np.int64)))
+    blocks.append(("triangle", negative, np.full(len(negative), 50, dtype=np.int64)))
+    blocks.append(("line", c1_boundary, np.full(len(c1_boundary), 30, dtype=np.int64)))
+    blocks.append(("triangle", c1, np.full(len(c1), 10, dtype=np.int64)))
+    blocks.append(("tetra", new_tets, np.ones(len(new_tets), dtype=np.int64)))
+    mesh = Mesh.from_arrays(3, points, blocks)
+    mesh.build_conformal_mesh()
+    return mesh, {"c1": c1, "positive": positive, "negative": negative}

@@ -230,6 +230,18 @@ class Mesh:
             created[self.edge_nodes.ravel()] = True
         self._created_vertex = created[:nv]
 
+    def find_cell_ids(self, dim, node_tags):
+        """Global cell ids of the edges (``dim = 1``) / faces (``dim = 2``) with the given vertex sets ``[m, dim + 1]``
+        (any vertex order); raises ``KeyError`` for a set that is not a cell of the mesh."""
+        P = np.int64(self.points.shape[0])
+        nodes = self.node_tags_of(dim)
+        key = lambda a: (np.sort(a, axis=-1) * (P ** np.arange(dim, -1, -1, dtype=np.int64))).sum(axis=-1)
+        if not hasattr(self, "_cell_lookup"):
+            self._cell_lookup = {}
+        if dim not in self._cell_lookup:
+            self._cell_lookup[dim] = _SortedLookup(key(nodes), self.ids_of_dimension(dim))
+        return self._cell_lookup[dim](key(np.asarray(node_tags, dtype=np.int64)))
+
     # -- array accessors used by the spaces layer ----------------------------------------------
     def cell_dimension(self, cell_ids):
         return np.searchsorted(self.offset[1:], np.asarray(cell_ids), side="right")

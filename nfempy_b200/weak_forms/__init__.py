@@ -14,3 +14,4 @@ from .tensor_mixed import (LEDualWeakForm, LEDualWeakFormBCDirichlet, LCEDualWea
                            LCEDualWeakFormBCNeumann)
 from .h1_multifield import (LCEPrimalWeakForm, LCEPrimalWeakFormBCDirichlet, LETaylorHoodWeakForm,
                             LETaylorHoodWeakFormBCDirichlet, LEPrimalStressConstraintWeakForm)
+from .coupling_weak_form import CouplingWeakForm, interface_triples

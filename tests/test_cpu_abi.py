@@ -87,10 +87,12 @@ def test_error_behaviour_of_the_assembler_front_end():
     asm.form_to_input_list = {"v": ["no_such_form_type", range(6), form, None]}
     with pytest.raises(KeyError):
         asm._entries()
-    for kind in ("interface_form", "bc_interface_form"):
-        asm.form_to_input_list = {"v": [kind, range(6), form, None]}
-        with pytest.raises(NotImplementedError):
-            asm._entries()
+    asm.form_to_input_list = {"v": ["bc_interface_form", range(6), form, None]}  # the library has no form of this type
+    with pytest.raises(NotImplementedError):
+        asm._entries()
+    asm.form_to_input_list = {"v": ["interface_form", range(6), form, None]}  # a volume form listed as an interface form
+    with pytest.raises(ValueError):
+        asm._entries()
     asm.form_to_input_list = {"v": ["bc_form", range(6), form, None]}  # a volume form listed as a boundary form
     with pytest.raises(ValueError):
         asm._entries()
