@@ -39,15 +39,17 @@ def _trace_space(md_space, iel_c0, iel_c1, field_pair=("u", "p")):
     return tr_tab, dof_n_index, n, p_tab, (x, weights, det_jac)
 
 
-def coupling(md_space, functions, index_c1, index_c0_p, index_c0_n, alpha):
-    du_p, idx_p, n_p, p_tab_p, map_p = _trace_space(md_space, index_c0_p, index_c1)
-    du_n, idx_n, n_n, p_tab_n, map_n = _trace_space(md_space, index_c0_n, index_c1)
+def coupling(md_space, functions, index_c1, index_c0_p, index_c0_n, alpha, field_pair=("u", "p")):
+    """``field_pair``: (flux field of the higher-dimensional space, potential field of the fracture space) -- ("u", "p")
+    in the reference; the two-flux transport model couples ("mp", "p") and ("mc", "c") the same way."""
+    du_p, idx_p, n_p, p_tab_p, map_p = _trace_space(md_space, index_c0_p, index_c1, field_pair)
+    du_n, idx_n, n_n, p_tab_n, map_n = _trace_space(md_space, index_c0_n, index_c1, field_pair)
     assert np.all(np.isclose(p_tab_p, p_tab_n))
     for a, b in zip(map_p, map_n):
         assert np.all(np.isclose(a, b))
     p_tab = p_tab_p
     x, weights, det_jac = map_p
-    dim = md_space[0].discrete_spaces["u"].dimension
+    dim = md_space[0].discrete_spaces[field_pair[0]].dimension
     n_u_p, n_u_n, n_pd = len(idx_p), len(idx_n), p_tab.shape[2]
     n_dof = n_u_p + n_u_n + n_pd
     s_up, s_un, s_p = slice(0, n_u_p), slice(n_u_p, n_u_p + n_u_n), slice(n_u_p + n_u_n, n_dof)
@@ -75,6 +77,19 @@ def coupling(md_space, functions, index_c1, index_c0_p, index_c0_n, alpha):
     return _linearise(residual, alpha, n_dof)
 
 
+def scatter_coupling(md_space, functions, triples, res_g, jac_g, alpha, field_pair=("u", "p")):
+    """``scatter_coupling_form_data`` over the interface triples, R/examples/md_elliptic_scalar/md_elliptic_scalar.py:284-342."""
+    fu, fp = field_pair
+    for c1_idx, c0_p_idx, c0_n_idx in triples:
+        dest = np.concatenate([
+            md_space[0].bc_destination_indexes(int(c0_p_idx), fu), md_space[0].bc_destination_indexes(int(c0_n_idx), fu),
+            md_space[1].destination_indexes(int(c1_idx), fp),
+        ])
+        r_el, j_el = coupling(md_space, functions, int(c1_idx), int(c0_p_idx), int(c0_n_idx), alpha[dest], field_pair)
+        ref_assembly.scatter_rhs(res_g, r_el, dest)
+        ref_assembly.scatter_lhs(jac_g, j_el, dest)
+
+
 def assemble_md(md_space, space_forms, triples, coupling_functions, alpha=None):
     """``space_forms[k]``: list of ``(kind, form_fn, functions, n_items)`` of space k (kinds "form" / "bc_form"; the
     spaces carry their ``dof_shift``); ``triples``: ``(c1_idx, c0_p_idx, c0_n_idx)`` rows.  Returns the CSR + rhs of the
@@ -87,13 +102,6 @@ def assemble_md(md_space, space_forms, triples, coupling_functions, alpha=None):
             scatter = ref_assembly.scatter_form if kind == "form" else ref_assembly.scatter_bc_form
             for i in (range(n_items) if isinstance(n_items, int) else n_items):
                 scatter(space, form, functions, i, res_g, jac_g, alpha)
-    for c1_idx, c0_p_idx, c0_n_idx in triples:
-        dest = np.concatenate([
-            md_space[0].bc_destination_indexes(int(c0_p_idx), "u"), md_space[0].bc_destination_indexes(int(c0_n_idx), "u"),
-            md_space[1].destination_indexes(int(c1_idx), "p"),
-        ])
-        r_el, j_el = coupling(md_space, coupling_functions, int(c1_idx), int(c0_p_idx), int(c0_n_idx), alpha[dest])
-        ref_assembly.scatter_rhs(res_g, r_el, dest)
-        ref_assembly.scatter_lhs(jac_g, j_el, dest)
+    scatter_coupling(md_space, coupling_functions, triples, res_g, jac_g, alpha)
     indptr, indices, data = jac_g.getValuesCSR()
     return indptr, indices, data, res_g

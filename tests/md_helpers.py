@@ -40,3 +40,43 @@ def md_problem(n=2, k=1, jitter=0.15):
     # (R/examples/md_elliptic_scalar/md_elliptic_scalar.py:309-318)
     outer = [i for i, cid in enumerate(u0.bc_element_ids) if mesh.material[cid] != 50]
     return mesh, spaces, ref_spaces, triples, outer
+
+
+# ---- config 5 in full: the two-flux transport model (Sundus) on the fractured box, fracture included ---------------------
+SUNDUS = {
+    "rhs_f": lambda x, y, z, t: np.array([np.sin(x + t) + y]), "rhs_r": lambda x, y, z, t: np.array([x * y + t * z]),
+    "kappa": lambda x, y, z: 2.0 + x, "delta": lambda x, y, z: 1.5, "eta": lambda x, y, z: 0.7 + 0.1 * y, "delta_t": 0.1,
+}
+SUNDUS_BC = {"p": lambda x, y, z, t: np.array([x + t]), "c": lambda x, y, z, t: np.array([y * z - t])}
+FIELDS = ("mp", "mc", "p", "c")
+
+
+def md_sundus_spaces(mesh, space_class, k=1):
+    out = []
+    for dim, tag, btags in ((3, 1, OUTER + [50]), (2, 10, [30])):
+        s = space_class({"mp": (dim, 1, "RT", k, mesh), "mc": (dim, 1, "RT", k, mesh),
+                         "p": (dim, 1, "Lagrange", k - 1, mesh), "c": (dim, 1, "Lagrange", k - 1, mesh)})
+        s.make_subspaces_discontinuous({"p": True, "c": True})
+        s.build_structures({n: [tag] for n in FIELDS}, {"mp": btags, "mc": btags})
+        out.append(s)
+    out[1].dof_shift = out[0].n_dof
+    return out
+
+
+def md_sundus_forms(spaces, triples, outer, alphas, t):
+    """``form_to_input_list`` of one Newton iteration of the mixed-dimensional transport step: time-dependent volume and
+    boundary forms on both dimensions + the Robin coupling of each flux with the fracture's matching potential."""
+    from nfempy_b200.weak_forms import CouplingWeakForm, SundusDualWeakForm, SundusDualWeakFormBCDirichlet
+
+    forms = {}
+    for tag, space in (("c0", spaces[0]), ("c1", spaces[1])):
+        wf, bf = SundusDualWeakForm(space), SundusDualWeakFormBCDirichlet(space)
+        wf.functions, bf.functions = SUNDUS, SUNDUS_BC
+        mp = space.discrete_spaces["mp"]
+        forms["vol_" + tag] = ["time_dependent_form", range(len(mp.elements)), wf, alphas, t]
+        forms["bc_" + tag] = ["time_dependent_bc_form", outer if tag == "c0" else range(len(mp.bc_elements)), bf, alphas, t]
+    for flux, pot in (("mp", "p"), ("mc", "c")):
+        cpl = type("Coupling_%s_%s" % (flux, pot), (CouplingWeakForm,), {"flux_name": flux, "potential_name": pot})(spaces)
+        cpl.functions = COUPLING
+        forms["coupling_" + flux] = ["interface_form", triples, cpl, alphas[0]]
+    return forms

@@ -62,3 +62,41 @@ def test_coupling_evaluate_form_single_cell():
     r, j = cpl.evaluate_form(*[int(v) for v in triples[2]], a)
     r_ref, j_ref = ref_md.coupling(ref_spaces, COUPLING, *[int(v) for v in triples[2]], a)
     assert np.abs(j - j_ref).max() <= 1e-12 * np.abs(j_ref).max() and np.abs(r - r_ref).max() <= 1e-12 * np.abs(r_ref).max()
+
+
+def test_md_two_flux_transport_step_matches_the_oracle():
+    """BASELINE config 5 as stated -- the parabolic two-flux transport model on a mixed-dimensional fractured 3-D mesh: Sundus
+    forms (time dependent, nonlinear reaction) in the box and on the fracture plane, their boundary forms, and the coupling
+    of (mp, p) and (mc, c) across the fracture, in one stacked system."""
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.mesh import fractured_box_tet_mesh
+    from nfempy_b200.spaces import ProductSpace
+    from nfempy_b200.weak_forms import interface_triples
+    from oracle import ref_assembly
+    from oracle.ref_mesh import RefMesh
+    from oracle.ref_spaces import RefProductSpace
+    from tests.md_helpers import SUNDUS, SUNDUS_BC, md_sundus_forms, md_sundus_spaces
+
+    mesh, interface = fractured_box_tet_mesh(2, jitter=0.15)
+    spaces = md_sundus_spaces(mesh, ProductSpace)
+    rmesh = RefMesh(3, mesh.points, mesh._blocks)
+    rmesh.build_conformal_mesh()
+    rspaces = md_sundus_spaces(rmesh, RefProductSpace)
+    triples = interface_triples(spaces[0], spaces[1], interface, "mp")
+    mp0 = spaces[0].discrete_spaces["mp"]
+    outer = [i for i, cid in enumerate(mp0.bc_element_ids) if mesh.material[cid] != 50]
+    n = spaces[1].dof_shift + spaces[1].n_dof
+    a_n, a = 0.3 * np.cos(np.arange(n) * 0.37) + 0.05, 0.2 * np.sin(np.arange(n) * 0.11)
+    t = 0.3
+    asm = GPUAssembler(spaces, None, np.zeros(n))
+    asm.form_to_input_list = md_sundus_forms(spaces, triples, outer, (a_n, a), t)
+    got = asm.assemble()
+    res_g, jac_g = np.zeros(n), ref_assembly.DokMatrix(n)
+    for space, bc_items in ((rspaces[0], outer), (rspaces[1], range(len(rspaces[1].discrete_spaces["mp"].bc_element_ids)))):
+        for i in range(len(space.discrete_spaces["mp"].element_ids)):
+            ref_assembly.scatter_time_dependent_form(space, ref_forms.sundus_dual, SUNDUS, i, res_g, jac_g, a_n, a, t)
+        for i in bc_items:
+            ref_assembly.scatter_time_dependent_bc_form(space, ref_forms.sundus_dual_bc_dirichlet, SUNDUS_BC, i, res_g, jac_g, a_n, a, t)
+    for pair in (("mp", "p"), ("mc", "c")):
+        ref_md.scatter_coupling(rspaces, COUPLING, triples, res_g, jac_g, a_n, pair)
+    compare_csr(got, jac_g.getValuesCSR() + (res_g,), 1e-12)

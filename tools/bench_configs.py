@@ -144,6 +144,75 @@ def run_sundus(mesh, n_steps):
     }), flush=True)
 
 
+def run_sundus_md(n, n_steps):
+    """BASELINE config 5 as stated: the two-flux transport model on a MIXED-DIMENSIONAL fractured 3-D mesh -- Sundus forms in
+    the box and on the fracture plane, boundary forms, Robin coupling of both fluxes across the fracture
+    (tests/md_helpers.py), one stacked system, plan built once, ``n_steps`` reassemblies."""
+    import torch
+
+    if ONLY and ONLY not in "config5 md sundus":
+        return
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.mesh import fractured_box_tet_mesh
+    from nfempy_b200.spaces import ProductSpace
+    from nfempy_b200.weak_forms import interface_triples
+    from tests.md_helpers import md_sundus_forms, md_sundus_spaces
+
+    t0 = time.perf_counter()
+    mesh, interface = fractured_box_tet_mesh(n, jitter=0.15)
+    spaces = md_sundus_spaces(mesh, ProductSpace)
+    triples = interface_triples(spaces[0], spaces[1], interface, "mp")
+    mp0 = spaces[0].discrete_spaces["mp"]
+    outer = np.flatnonzero(mesh.material[mp0.bc_element_ids] != 50)
+    t_host = time.perf_counter() - t0
+    n_dof = spaces[1].dof_shift + spaces[1].n_dof
+    a_n, a = 0.3 * np.cos(np.arange(n_dof) * 0.37) + 0.05, 0.2 * np.sin(np.arange(n_dof) * 0.11)
+    asm = GPUAssembler(spaces, None, np.zeros(n_dof))
+    forms = md_sundus_forms(spaces, triples, outer, (a_n, a), 0.0)
+    asm.form_to_input_list = forms
+    t0 = time.perf_counter()
+    asm.scatter_forms()
+    first = time.perf_counter() - t0
+    state = asm.prepare()
+    plan = state[4]
+    rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=state[0].device)
+
+    def step():
+        asm.jacobian.is_zero = True
+        rhs.zero_()
+        asm.run(state, rhs)
+
+    ms = time_steps(torch, step, n_steps, 3)
+    # the time loop through the API: a new time per step (loads re-evaluated on the host from the cached points), a new
+    # iterate, kernels, residual downloaded
+    t0 = time.perf_counter()
+    for k in range(5):
+        a_n += 1e-3
+        for key, entry in forms.items():
+            if "time_dependent" in entry[0]:
+                entry[4] = 0.1 * (k + 1)
+        asm.jacobian.scale(0.0)
+        asm.residual[:] = 0.0
+        asm.scatter_forms()
+    api = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    for k in range(5):  # Newton iterations inside one time step: t fixed, only the iterate changes
+        a_n += 1e-3
+        asm.jacobian.scale(0.0)
+        asm.residual[:] = 0.0
+        asm.scatter_forms()
+    api_newton = (time.perf_counter() - t0) / 5
+    n_cells = len(mp0.elements)
+    print(json.dumps({
+        "case": "config5 (mixed-dimensional): two-flux transport RT1 x RT1 x P0 x P0 in the fractured box (z = 1/2) + the same "
+                "fields on the fracture + Robin coupling of both fluxes, %d reassemblies on one plan" % n_steps,
+        "cells": n_cells, "fracture_cells": int(len(triples)), "n_dof": int(n_dof), "nnz": int(plan.nnz), "path": "two-stage",
+        "ms_per_reassembly_kernels": ms, "elements_per_s": (n_cells + len(triples)) / (ms * 1e-3), "plans_built": len(asm._plans),
+        "first_assembly_s": first, "api_step_s_new_time": api, "api_step_s_newton_iteration": api_newton,
+        "plan_build_s": plan.build_seconds, "host_mesh_space_s": t_host, "steps": n_steps, "dtype": "f64",
+    }), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
@@ -177,6 +246,7 @@ def main():
     # config 5: reassembly of the two-flux transport system, plan built once, 100 "time steps" of kernels
     run_sundus(mesh3, 20 if q else 100)
     del mesh3
+    run_sundus_md(8 if q else 68, 20 if q else 100)
     mesh3s = box_tet_mesh(6 if q else 40, jitter=0.2)
     run_case("config3: 3D mixed Poisson RT3 x P2 disc + natural BC (40^3 x 6 tets: 31-bit local-entry index)",
              mixed_poisson_case(dim=3, k=3, mesh=mesh3s), mixed_poisson_case(dim=3, k=3, n=1), args.steps, args.warmup,
