@@ -129,6 +129,7 @@ class GPUAssembler:
         self._entry_cache = []  # [(signature, FormData, dest)] most recent last
         self._rhs_dev = None
         self._rhs_host = None
+        self._state_bufs = []
         self._capturing = False
 
     def invalidate(self):
@@ -288,7 +289,8 @@ class GPUAssembler:
                                riffle=int(os.environ.get("NFA_P2TET_RIFFLE", "148")),
                                batch=int(os.environ.get("NFA_P2TET_BATCH", "8")),
                                lane_order=os.environ.get("NFA_P2TET_LANES", "cell"), lane_optimizer=lane_optimizer,
-                               locality=os.environ.get("NFA_P2TET_LOCAL", "1") != "0")
+                               locality=os.environ.get("NFA_P2TET_LOCAL", "1") != "0",
+                               type_order=tuple(int(c) for c in os.environ.get("NFA_P2TET_TYPEORDER", "01234")))
         _lib.check(
             lib.nfa_bplan_set_p2_items(
                 p.bplan, items["n_chunks"], _lib.ptr(items["chunk_hdr"]), items["n_tasks"], _lib.ptr(items["task_hdr"]),
@@ -375,15 +377,30 @@ class GPUAssembler:
             dests.append(dest)
         # state vectors: one persistent device buffer per entry, refreshed in place on every call (a captured graph
         # reads the same buffers); ``alpha_zero`` lets eager runs skip the K.alpha terms of an all-zero vector
+        # (the same numpy vector listed by several entries -- every form of a Newton iteration names the same iterate --
+        # goes up once: slot k = the k-th distinct vector of the list, one persistent device buffer per slot)
+        slots = {}
+
+        def state(vec):
+            if vec is None:
+                return None, True
+            if id(vec) not in slots:
+                k = len(slots)
+                while len(self._state_bufs) <= k:
+                    self._state_bufs.append(None)
+                buf, zero = self._upload(dev, vec, self._state_bufs[k])
+                self._state_bufs[k] = buf
+                slots[id(vec)] = (buf, zero)
+            return slots[id(vec)]
+
         for (_, kind, _, _, alpha), data in zip(entries, datas):
             if "time_dependent" in kind:
                 (first, second), _t = alpha
-                a0, z0 = self._upload(dev, first, data.alpha_dev[0] if data.alpha_dev else None)
-                a1, z1 = (self._upload(dev, second, data.alpha_dev[1] if data.alpha_dev else None)
-                          if kind == "time_dependent_form" else (None, True))
+                a0, z0 = state(first)
+                a1, z1 = state(second) if kind == "time_dependent_form" else (None, True)
                 data.alpha_dev, data.alpha_zero = (a0, a1), (z0 and z1)
             else:
-                data.alpha_dev, data.alpha_zero = self._upload(dev, alpha, data.alpha_dev)
+                data.alpha_dev, data.alpha_zero = state(alpha)
         fused_index = None
         if self.pattern_policy != "full":
             return dev, entries, datas, dests, None, None  # the pattern depends on the values: built in run()

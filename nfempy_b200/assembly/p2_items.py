@@ -139,11 +139,12 @@ def greedy_lane_order(group_ptr, hdr, window=48):
 
 
 def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_order="cell", lane_optimizer=None,
-          locality=True):
+          locality=True, type_order=(0, 1, 2, 3, 4)):
     """``node_dest`` int64 [n_cells, 10] global node of each local P2 node, ``bptr``/``bcols`` the block CSR of the
     matrix (int64 tensors on the same device).  ``lane_optimizer(group_ptr, hdr6) -> permutation`` reorders the items
     inside their (chunk, type) groups (``nfa_p2_lane_order`` on the device, ``greedy_lane_order`` in the tests; None keeps
-    the first-cell order).  Returns a dict of tensors (see module docstring) and sizes."""
+    the first-cell order).  ``type_order[t]`` = position of item type t (A..E) in a chunk's task list.  Returns a dict of
+    tensors (see module docstring) and sizes."""
     dev = node_dest.device
     n_cells = int(node_dest.shape[0])
     if n_cells >= (1 << 26):
@@ -232,7 +233,10 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
             fblk[t] = torch.where(designated, block_id(N, node_dest[:, tpl["opp"]]), torch.full_like(N, -1))
     rowN, typ, code, item_blk, fblk = (v.t().reshape(-1) for v in (rowN, typ, code, item_blk, fblk))
     blk = blk.permute(1, 0, 2).reshape(-1, 3)
-    key = (chunk_of_row[rowN] << 34) | (typ << 31) | item_blk
+    # tasks of a chunk run in ascending (sort rank of the) type: long items first, so that the last tasks of a chunk --
+    # the ones that decide when its tile can be handed over -- are short ones
+    rank_of_type = torch.as_tensor(type_order, dtype=torch.int64, device=dev)
+    key = (chunk_of_row[rowN] << 34) | (rank_of_type[typ] << 31) | item_blk
     key, order = torch.sort(key, stable=True)
     code, blk, rowN, fblk = code[order], blk[order], rowN[order], fblk[order]
     n_entries = int(key.shape[0])
@@ -244,8 +248,10 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     n_items = int(item_start.shape[0])
     item_end = torch.cat([item_start[1:], torch.tensor([n_entries], device=dev)])
     item_count = item_end - item_start
-    item_key = key[item_start] >> 31  # chunk | type
-    item_type = item_key & 7
+    type_of_rank = torch.empty(5, dtype=torch.int64, device=dev)
+    type_of_rank[rank_of_type] = torch.arange(5, device=dev)
+    item_key = key[item_start] >> 31  # chunk | sort rank of the type
+    item_type = type_of_rank[item_key & 7]
     item_of_entry = torch.cumsum(first.to(torch.int64), 0) - 1
     r_in_item = torch.arange(n_entries, device=dev) - item_start[item_of_entry]
     if int(item_count.max().item()) > 255:
@@ -305,7 +311,7 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     ell_size = int((kmax * 32).sum().item())
     task_first_item = torch.nonzero(tfirst).reshape(-1)
     task_group_key = grp[task_first_item]
-    task_type = task_group_key & 7
+    task_type = type_of_rank[task_group_key & 7]
     task_chunk = task_group_key >> 3
     # item-header slots: one per item, two for type E; every task starts on an even slot
     per_item = torch.where(task_type == TYPE_E, 2, 1)

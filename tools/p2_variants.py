@@ -6,7 +6,7 @@ nfa_plan.cuh).  Each result is compared with the regular library's values.
 
     python tools/p2_variants.py --variants base,pf,e2 --threads 512 --plans 640:296:8,640:148:8 > gpurun_out/p2_variants.jsonl
 
-variant spec: NAME[@THREADS[@NBUF]]; plan spec: CAP:RIFFLE:BATCH[:LANEOPT[:LANEWIN[:LOCALITY]]]
+variant spec: NAME[@THREADS[@NBUF]]; plan spec: CAP:RIFFLE:BATCH[:LANEOPT[:LANEWIN[:LOCALITY[:TYPEORDER]]]]
 """
 import argparse
 import ctypes
@@ -59,9 +59,10 @@ def main():
         return libs[name]
 
     for pspec in args.plans.split(","):
-        tok = pspec.split(":") + ["1", "48", "1"][max(0, len(pspec.split(":")) - 3):]
-        cap, riffle, batch, laneopt, lanewin, local = tok[:6]
+        tok = pspec.split(":") + ["0", "48", "1", "01234"][max(0, len(pspec.split(":")) - 3):]
+        cap, riffle, batch, laneopt, lanewin, local, torder = tok[:7]
         os.environ["NFA_P2TET_LOCAL"] = local
+        os.environ["NFA_P2TET_TYPEORDER"] = torder
         os.environ["NFA_P2TET_CAP"], os.environ["NFA_P2TET_RIFFLE"], os.environ["NFA_P2TET_BATCH"] = cap, riffle, batch
         os.environ["NFA_P2TET_LANEOPT"], os.environ["NFA_P2TET_LANEWIN"] = laneopt, lanewin
         for k in ("NFA_P2TET_THREADS", "NFA_P2TET_NBUF"):
