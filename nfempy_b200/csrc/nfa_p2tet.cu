@@ -64,7 +64,7 @@ constexpr int P2_THREADS = NFA_P2_THREADS;
 //                  consumes (a software stream prefetcher: no further tasks are claimed, so the tile window is not
 //                  overrun, and the look-ahead loads of the next task become L2 hits instead of DRAM misses)
 #ifndef NFA_P2_STREAM_PF
-#define NFA_P2_STREAM_PF 1
+#define NFA_P2_STREAM_PF 0  // measured: no gain (0.778 with, 0.772 without; 0.765 against 0.768 with L1NA = 1)
 #endif
 #ifndef NFA_P2_PFD_ELL
 #define NFA_P2_PFD_ELL 4096  // look-ahead in ELL entries (16 KB, about 35 tasks)
@@ -124,8 +124,17 @@ __device__ __forceinline__ G4 ldg256(const double *p) {
 }
 
 // plan lists are read once per launch: optionally marked L2::evict_first so that they do not push the records out of L2
+//   NFA_P2_L1NA    bit 0: ELL entries, bit 1: task headers, bit 2: item headers are loaded L1::no_allocate -- every line of
+//                  these lists is read exactly once, and the 31 KB of L1 left beside the tiles is better spent on records
+#ifndef NFA_P2_L1NA
+#define NFA_P2_L1NA 1  // measured: ELL no-allocate 0.768 ms against 0.778; headers as well: 0.772 / 0.782
+#endif
 __device__ __forceinline__ uint32_t ld_list(const uint32_t *p) {
-#if (NFA_P2_L2HINT & 4)
+#if (NFA_P2_L1NA & 1)
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#elif (NFA_P2_L2HINT & 4)
     uint32_t v;
     const uint64_t pol = l2_policy_evict_first();
     asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
@@ -135,7 +144,11 @@ __device__ __forceinline__ uint32_t ld_list(const uint32_t *p) {
 #endif
 }
 __device__ __forceinline__ int4 ld_list(const int4 *p) {
-#if (NFA_P2_L2HINT & 4)
+#if (NFA_P2_L1NA & 2)
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+#elif (NFA_P2_L2HINT & 4)
     int4 v;
     const uint64_t pol = l2_policy_evict_first();
     asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
@@ -147,7 +160,11 @@ __device__ __forceinline__ int4 ld_list(const int4 *p) {
 #endif
 }
 __device__ __forceinline__ uint2 ld_list(const uint2 *p) {
-#if (NFA_P2_L2HINT & 4)
+#if (NFA_P2_L1NA & 4)
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+#elif (NFA_P2_L2HINT & 4)
     uint2 v;
     const uint64_t pol = l2_policy_evict_first();
     asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
