@@ -330,9 +330,8 @@ def run_graft(args):
         if sharded is not None:  # local fused assembly + NCCL interface-row exchange
             sharded.assemble(dist)
             return
-        asm.jacobian.is_zero = True  # fresh assembly: the fused kernel overwrites every value
-        rhs_dev.zero_()
-        asm.run(state, rhs_dev)
+        asm.jacobian.is_zero = True  # fresh assembly: the fused kernel overwrites every value (and every rhs row)
+        asm.run(state, rhs_dev, fresh=True)
 
     def barrier():
         if world > 1:
@@ -364,7 +363,7 @@ def run_graft(args):
     if sharded is not None and not args.no_graph:
         l0 = _lib.launch_count()
         sharded.local_assemble()
-        local_launches = _lib.launch_count() - l0 + 1  # + the rhs fill
+        local_launches = _lib.launch_count() - l0 + int(asm.last_rhs_fill)  # + the rhs fill, if one ran
         if p2p:
             local_launches += len(sharded.shard.send_rows) + len(sharded.shard.recv_rows)
             sharded.capture_step()
@@ -373,7 +372,7 @@ def run_graft(args):
     if sharded is None and not args.no_graph:
         l0 = _lib.launch_count()
         step()
-        launches_per_step = _lib.launch_count() - l0 + 1  # + rhs_dev.zero_() (torch fill kernel)
+        launches_per_step = _lib.launch_count() - l0 + int(asm.last_rhs_fill)  # + the torch fill kernel of rhs, if one ran
         graph = asm.capture(state, rhs_dev)
         eager_step = step
         step = graph.replay
@@ -396,7 +395,7 @@ def run_graft(args):
     if graph is not None:
         launches = launches_per_step * args.steps  # replayed kernel nodes: counted on the eager step that was captured
     else:
-        launches = _lib.launch_count() - launches0 + args.steps  # + rhs_dev.zero_() per step (torch fill kernel)
+        launches = _lib.launch_count() - launches0 + args.steps * int(asm.last_rhs_fill)  # + the rhs fill kernel, if any
         if sharded is not None and not args.no_graph:  # the replayed kernels (+ the eager exchange kernels counted above)
             launches = _lib.launch_count() - launches0 + local_launches * args.steps
     # load probe for the clock record: the same step loop for ~0.6 s (not part of any reported time)
@@ -421,6 +420,9 @@ def run_graft(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     nnz_per_tet = nnz / n_cells
     b_kernel = 112.0 + 40.0 + 16.0 + 8.0 * nnz_per_tet  # node ids + coords gather, dof table, lambda/mu, CSR values
+    rhs_folded = bool(asm._folds_load(lib, plan, entries, datas))
+    if rhs_folded:
+        b_kernel += 8.0 * plan.n_dof / n_cells  # the kernel also writes the right-hand-side rows ("+ RHS")
     b_step = b_kernel + 8.0 * plan.n_dof / n_cells + 27 * 3 * 8.0  # + rhs rows + tabulated load
     kernel_ms = k_ms.value / max(k_n.value, 1)
     achieved = b_kernel * n_cells / (kernel_ms * 1e-3) / 1e9
@@ -433,7 +435,7 @@ def run_graft(args):
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
         "algorithmic_bytes_per_launch": b_kernel * n_cells,
         "kernel": "p2tet_elasticity_kernel" if row_items else "fused_h1_kernel<3,0>", "kernel_ms": kernel_ms, "algorithmic_bytes_per_tet": b_kernel,
-        "peak_source": peak_src, "step_frac": b_step * n_cells / (ms_step * 1e-3) / 1e9 / peak,
+        "kernel_writes_rhs": rhs_folded, "peak_source": peak_src, "step_frac": b_step * n_cells / (ms_step * 1e-3) / 1e9 / peak,
         "step_algorithmic_bytes_per_tet": b_step,
     }
 

@@ -71,6 +71,17 @@ int nfa_local_h1_laplace(int dim, int n_phi, int n_q, const double *d_tab, const
 int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *d_tab0, const double *d_weights,
                       const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_f,
                       double sign, double *d_re, nfa_stream stream);
+/* the same as a BACKGROUND kernel (vector P2 on tetrahedra): one small persistent CTA per SM (31 KB of shared memory,
+ * three warps) that fits beside the row-item matrix kernel, so that a second stream can compute the load vector while
+ * nfa_assemble_p2tet_elasticity runs (GPUAssembler forks the step's stream; the matrix kernel then runs 448 threads) */
+int nfa_local_h1_load_bg(int dim, int n_phi, int n_q, int n_comp, const double *d_tab0, const double *d_weights,
+                         const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_f,
+                         double sign, double *d_re, nfa_stream stream);
+/* the same with padded node records: re [n, n_phi, comp_pitch] (comp_pitch = 4 for vector P2 on tetrahedra: one 32-byte
+ * sector per (cell, node), what nfa_assemble_p2tet_elasticity_load gathers) */
+int nfa_local_h1_load_pitched(int dim, int n_phi, int n_q, int n_comp, const double *d_tab0, const double *d_weights,
+                              const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_f,
+                              double sign, double *d_re, int comp_pitch, nfa_stream stream);
 
 /* ---- K5 H1 facet (boundary) forms on (dim-1)-simplices embedded in 3-space.
  * J = beta * int phi phi^T per component, r = r_sign * beta * int g_c phi  (g [n, n_q, n_comp] host-evaluated).
@@ -296,6 +307,18 @@ int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *d_mask, nfa_stream str
 int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *d_coords, const int32_t *d_cell_nodes,
                                   const double *d_lambda, int64_t lambda_stride, const double *d_mu,
                                   int64_t mu_stride, double *d_vals, nfa_stream stream);
+/* Threads per CTA of the row-item kernel for the following calls (384, 448, 480, 512, 640; 0 = default 512).  448 leaves
+ * room on every SM for the background load kernel nfa_local_h1_load_bg. */
+void nfa_p2tet_set_threads(int threads);
+/* Matrix AND load vector in the same pass: the items that own a node's diagonal block walk exactly the cells the node's
+ * right-hand-side rows need, so they also sum the cells' local load vectors d_re4 [n_cells, 10, 4] (from
+ * nfa_local_h1_load_pitched, comp_pitch = 4) in ascending cell order -- the order of res_g[dest] += r_el,
+ * R/src/assembly/ScatterFormData.py:14-18 -- and write rows 3 N .. 3 N + 2 of d_rhs.  rhs_overwrite = 1: the sums
+ * replace the rows (d_rhs is zero on entry, or every node of the plan has cells); 0: they are added to what d_rhs holds. */
+int nfa_assemble_p2tet_elasticity_load(const nfa_bplan *bp, const double *d_coords, const int32_t *d_cell_nodes,
+                                       const double *d_lambda, int64_t lambda_stride, const double *d_mu,
+                                       int64_t mu_stride, double *d_vals, const double *d_re4, double *d_rhs,
+                                       int rhs_overwrite, nfa_stream stream);
 
 /* ---- penalised normal trace of a row-wise H(div) field on boundary facets: LCEDualWeakFormBCNeumann
  * (R/src/weak_forms/lce_dual_weak_form.py:759-871; the same class in le_dual_weak_form.py:581-644 and

@@ -28,6 +28,8 @@ SIGNATURES = {
     ),
     "nfa_local_h1_laplace": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nfa_local_h1_load": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _d, _vp, _vp]),
+    "nfa_local_h1_load_bg": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _d, _vp, _vp]),
+    "nfa_local_h1_load_pitched": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _d, _vp, _i, _vp]),
     "nfa_local_h1_facet": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _d, _d, _i, _vp, _vp, _vp]),
     "nfa_local_hdiv_l2": (
         _i,
@@ -86,6 +88,8 @@ SIGNATURES = {
     "nfa_bplan_has_p2_items": (_i, [_vp]),
     "nfa_bplan_set_cell_mask": (_i, [_vp, _vp, _vp]),
     "nfa_assemble_p2tet_elasticity": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "nfa_p2tet_set_threads": (None, [_i]),
+    "nfa_assemble_p2tet_elasticity_load": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
 }
 
 _lib = None

@@ -438,26 +438,39 @@ class GPUAssembler:
         buf.copy_(src, non_blocking=False)
         return buf, not bool(host.any())
 
-    def run(self, state, rhs_dev=None):
-        """Launches the kernels of one assembly.  Adds into ``self.jacobian`` and returns the device residual."""
+    def run(self, state, rhs_dev=None, fresh=False):
+        """Launches the kernels of one assembly.  Adds into ``self.jacobian`` and into ``rhs_dev`` (the device residual,
+        returned).  ``fresh=True``: ``rhs_dev`` holds nothing the caller wants to keep -- the assembly result replaces it
+        (the buffer is zeroed here unless the fused row-item kernel overwrites every row anyway)."""
         with torch.cuda.device(state[0].device):
-            return self._run(state, rhs_dev)
+            return self._run(state, rhs_dev, fresh)
 
-    def _run(self, state, rhs_dev=None):
+    def _run(self, state, rhs_dev=None, fresh=False):
         dev, entries, datas, dests, plan, key = state
         lib = _lib.load()
         stream = _lib.stream_ptr()
         jac = self.jacobian
         if plan is None:
+            if fresh and rhs_dev is not None:
+                rhs_dev.zero_()
             return self._run_filtered(state, rhs_dev)
         if jac.plan_key != key:
             if jac.plan_key is not None and not jac.is_zero:
                 raise _lib.NfaError("GPUAssembler: the jacobian holds values assembled on a different sparsity plan")
             jac.bind_pattern(key, plan.n_dof, plan.indptr, plan.indices)
+        # the row-item kernel can write the load vector itself (its vertex / edge diagonal items walk the cells a row
+        # needs): rows are then OVERWRITTEN when the buffer is fresh and every node of the plan has cells -- no fill
+        fold = self._folds_load(lib, plan, entries, datas)
+        overwrite = fold and (fresh or rhs_dev is None) and bool(plan.p2_stats.get("all_rows_nonempty"))
+        self.last_rhs_fill = not overwrite and (fresh or rhs_dev is None)  # a torch fill kernel ran (launch accounting)
         if rhs_dev is None:
-            rhs_dev = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
+            rhs_dev = (torch.empty if overwrite else torch.zeros)(plan.n_dof, dtype=torch.float64, device=dev.device)
+        elif fresh and not overwrite:
+            rhs_dev.zero_()
         nseg = len(entries)
         Ke_list, re_list, keep = [None] * nseg, [None] * nseg, []
+        overlap = self._overlaps_load(lib, plan, entries, datas, fold)
+        side, rhs_on_side = None, False
         for i, ((_, kind, _, form, alpha), data, dest) in enumerate(zip(entries, datas, dests)):
             if "time_dependent" in kind:
                 first_dev, second_dev = data.alpha_dev
@@ -482,8 +495,42 @@ class GPUAssembler:
                     args = [plan.bplan, data.dim, _lib.ptr(form.mref(dev)), _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes)]
                 for c in spec["coefs"]:
                     args += [_lib.ptr(c[0]), c[1]]
-                args += [_lib.ptr(target), stream]
-                _lib.check(getattr(lib, kernel)(*args), kernel)
+                args += [_lib.ptr(target)]
+                if fold:
+                    # padded local load vectors [n, 10, 4] first, then matrix + right-hand side in one pass
+                    re4 = torch.empty((data.n_items, 10, 4), dtype=torch.float64, device=dev.device)
+                    form.launch_load(data.dev, data, re4, comp_pitch=4)
+                    keep.append(re4)
+                    kernel += "_load"
+                    args += [_lib.ptr(re4), _lib.ptr(rhs_dev), 1 if overwrite else 0]
+                args += [stream]
+                fork_event = None
+                if overlap:
+                    # fork: the side stream computes the local load vectors (and, when this form is the whole list, sums
+                    # them into the right-hand side) while the matrix kernel runs on the main stream.  The matrix kernel is
+                    # launched FIRST: its CTAs take the SMs, the small background CTAs then fill the room left beside them
+                    main = torch.cuda.current_stream(dev.device)
+                    fork_event = torch.cuda.Event()
+                    fork_event.record(main)
+                    lib.nfa_p2tet_set_threads(int(os.environ.get("NFA_P2TET_OVERLAP_THREADS", "448")))
+                try:
+                    _lib.check(getattr(lib, kernel)(*args), kernel)
+                finally:
+                    if overlap:
+                        lib.nfa_p2tet_set_threads(0)
+                if overlap:
+                    side = self._side_stream(dev)
+                    side.wait_event(fork_event)
+                    re = torch.empty((data.n_items, form.n_loc()), dtype=torch.float64, device=dev.device)
+                    re_list[i] = re
+                    keep.append(re)
+                    with torch.cuda.stream(side):
+                        form.launch_load(data.dev, data, re, background=True)
+                        if nseg == 1 and alpha_dev is None:
+                            re_ptrs = (ctypes.c_void_p * 1)(re.data_ptr())
+                            _lib.check(lib.nfa_plan_reduce(plan.plan, None, re_ptrs, 1, None, 1, _lib.ptr(rhs_dev),
+                                                           _lib.stream_ptr()), "nfa_plan_reduce")
+                            rhs_on_side = True
                 if alpha_dev is not None:
                     _lib.check(
                         lib.nfa_csr_spmv(plan.pattern, _lib.ptr(target), _lib.ptr(alpha_dev), 1, _lib.ptr(rhs_dev), stream),
@@ -492,7 +539,7 @@ class GPUAssembler:
                 if target is not jac.values_dev:
                     jac.values_dev.add_(target)
                 jac.is_zero = False
-                if data.f is not None:
+                if data.f is not None and not fold and not overlap:
                     re = torch.empty((data.n_items, form.n_loc()), dtype=torch.float64, device=dev.device)
                     form.launch_load(data.dev, data, re)
                     re_list[i] = re
@@ -501,16 +548,55 @@ class GPUAssembler:
                 Ke, re = form.local_blocks(data.dev, data, alpha_dev, dest if alpha_dev is not None else None)
                 Ke_list[i], re_list[i] = Ke, re
                 keep += [Ke, re, alpha_dev]
+        if side is not None:
+            torch.cuda.current_stream(dev.device).wait_stream(side)  # join
         ke_ptrs = (ctypes.c_void_p * nseg)(*[None if k is None else k.data_ptr() for k in Ke_list])
-        re_ptrs = (ctypes.c_void_p * nseg)(*[None if r is None else r.data_ptr() for r in re_list])
+        re_ptrs = (ctypes.c_void_p * nseg)(*[None if (r is None or rhs_on_side) else r.data_ptr() for r in re_list])
         accumulate_vals = 0 if (jac.is_zero and plan.fused_index is None) else 1
-        _lib.check(
-            lib.nfa_plan_reduce(plan.plan, ke_ptrs, re_ptrs, accumulate_vals, _lib.ptr(jac.values_dev), 1, _lib.ptr(rhs_dev), stream),
-            "nfa_plan_reduce",
-        )
+        if not (rhs_on_side and all(k is None for k in Ke_list)):
+            _lib.check(
+                lib.nfa_plan_reduce(plan.plan, ke_ptrs, None if rhs_on_side else re_ptrs, accumulate_vals,
+                                    _lib.ptr(jac.values_dev), 1, _lib.ptr(rhs_dev), stream),
+                "nfa_plan_reduce",
+            )
         jac.is_zero = False
         self._keep = keep  # buffers must outlive the stream-ordered kernels
         return rhs_dev
+
+    @staticmethod
+    def _folds_load(lib, plan, entries, datas):
+        """True when the fused form runs on the row-item kernel and has a load: the kernel then also writes the form's
+        right-hand side (``nfa_assemble_p2tet_elasticity_load``; ``NFA_P2TET_RHS=0`` keeps the separate gather)."""
+        i = plan.fused_index
+        # measured: the gather inside the matrix kernel costs more (0.77 -> 0.98 ms) than the separate reduce it replaces
+        # (0.14 ms), so it is opt-in; the default overlaps the load / reduce branch with the matrix kernel instead
+        if i is None or os.environ.get("NFA_P2TET_RHS", "0") == "0" or not getattr(plan, "p2_stats", None):
+            return False
+        form, data = entries[i][3], datas[i]
+        spec = form.fused_spec(data)
+        return bool(spec and spec.get("p2tet_kernel") and data.f is not None and lib.nfa_bplan_has_p2_items(plan.bplan)
+                    and hasattr(lib, spec["p2tet_kernel"] + "_load"))
+
+    @staticmethod
+    def _overlaps_load(lib, plan, entries, datas, fold):
+        """True when the load vector of the fused form is computed on a SIDE stream while the row-item matrix kernel runs:
+        the matrix kernel is latency-bound and leaves a third of the DRAM bandwidth idle, the load kernel is a pure stream.
+        The matrix kernel then runs 448 threads per SM instead of 512, which leaves the registers and the 32 KB of shared
+        memory ``nfa_local_h1_load_bg`` (one small persistent CTA per SM) needs beside it.  ``NFA_P2TET_OVERLAP=0`` keeps
+        the single-stream chain."""
+        i = plan.fused_index
+        if i is None or fold or os.environ.get("NFA_P2TET_OVERLAP", "0") == "0" or not getattr(plan, "p2_stats", None):
+            return False
+        form, data = entries[i][3], datas[i]
+        spec = form.fused_spec(data)
+        return bool(spec and spec.get("p2tet_kernel") and data.f is not None and data.n_q <= 27
+                    and lib.nfa_bplan_has_p2_items(plan.bplan))
+
+    def _side_stream(self, dev):
+        side = getattr(self, "_side", None)
+        if side is None or side.device != dev.device:
+            side = self._side = torch.cuda.Stream(device=dev.device)
+        return side
 
     def capture(self, state, rhs_dev):
         """CUDA graph of one fresh assembly (``rhs_dev`` zeroed, every CSR value overwritten) on the buffers of ``state``:
@@ -529,10 +615,9 @@ class GPUAssembler:
 
         def body():
             self.jacobian.is_zero = True
-            rhs_dev.zero_()
             self._capturing = True
             try:
-                self.run(state, rhs_dev)
+                self.run(state, rhs_dev, fresh=True)
             finally:
                 self._capturing = False
 
@@ -623,8 +708,7 @@ class GPUAssembler:
         if self._rhs_dev is None or self._rhs_dev.shape[0] != n_dof or self._rhs_dev.device != dev.device:
             self._rhs_dev = torch.empty(n_dof, dtype=torch.float64, device=dev.device)
             self._rhs_host = torch.empty(n_dof, dtype=torch.float64).pin_memory()
-        self._rhs_dev.zero_()
-        rhs_dev = self.run(state, self._rhs_dev)
+        rhs_dev = self.run(state, self._rhs_dev, fresh=True)
         self._rhs_host.copy_(rhs_dev, non_blocking=False)
         rhs = self._rhs_host.numpy()
         t2 = time.perf_counter()

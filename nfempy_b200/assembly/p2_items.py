@@ -28,9 +28,12 @@ Layout handed to the kernel:
   chunk_hdr  int32 [n_chunks, 4]   b0, n_blocks, task0, n_tasks      (chunk = contiguous block rows)
   task_hdr   int32 [n_tasks, 4]    type | kmax << 8 | (b0 & 1) << 16, ell_base, item_slot, n_items (<= 32) | chunk << 6
   item_hdr   uint16 [n_slots, 4]   one slot per item: tile offsets of the item's three blocks (0xFFFF = unused), row
-                                   pitch; type E items take two slots, the second one holds the tile offsets of the
-                                   opposite-edge blocks of the item's first / second cell (0xFFFF = not emitted here);
-                                   a task's slots are contiguous and start on an even slot (16-byte aligned)
+                                   pitch; type D and E items take two slots: the second one holds, for type E, the tile
+                                   offsets of the opposite-edge blocks of the item's first / second cell (0xFFFF = not
+                                   emitted here) and, for type D, the row's node id (low, high half).  Type A items carry
+                                   their node id in the two unused block slots.  (Items A and D own the node's three
+                                   right-hand-side rows, nfa_assemble_p2tet_elasticity_load.)  A task's slots are
+                                   contiguous and start on an even slot (16-byte aligned)
   ell        uint32 [sum 32 kmax]  entry k of lane l of a task at ell_base + 32 k + l:
                                    cell << 6 | i << 4 | j << 2 | x   (0xFFFFFFFF = none)
 """
@@ -334,8 +337,8 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     task_group_key = grp[task_first_item]
     task_type = type_of_rank[task_group_key & 7]
     task_chunk = task_group_key >> 3
-    # item-header slots: one per item, two for type E; every task starts on an even slot
-    per_item = torch.where(task_type == TYPE_E, 2, 1)
+    # item-header slots: one per item, two for types D and E; every task starts on an even slot
+    per_item = torch.where(task_type >= TYPE_D, 2, 1)
     task_slots = (task_items * per_item + 1) & ~1
     slot_base = torch.cumsum(task_slots, 0) - task_slots
     n_slots = int(task_slots.sum().item())
@@ -347,6 +350,15 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     es = item_slot[is_e] + 1
     item_hdr[es, 0] = hdr_sorted[is_e, 4]
     item_hdr[es, 1] = hdr_sorted[is_e, 5]
+    # row node of the items that own the right-hand-side rows: A in its unused block slots, D in its second slot
+    row_sorted = it_row[iperm]
+    is_a = item_type[iperm] == TYPE_A
+    item_hdr[item_slot[is_a], 1] = row_sorted[is_a] & 0xFFFF
+    item_hdr[item_slot[is_a], 2] = row_sorted[is_a] >> 16
+    is_d = item_type[iperm] == TYPE_D
+    ds = item_slot[is_d] + 1
+    item_hdr[ds, 0] = row_sorted[is_d] & 0xFFFF
+    item_hdr[ds, 1] = row_sorted[is_d] >> 16
     # ELL fill
     inv = torch.empty_like(iperm)
     inv[iperm] = torch.arange(n_items, device=dev)
@@ -371,6 +383,7 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
         "ell": (ell & NONE32).to(torch.uint32 if hasattr(torch, "uint32") else torch.int64).contiguous(),
         "n_chunks": n_chunks, "n_tasks": n_tasks, "n_items": n_items, "n_slots": n_slots, "ell_size": ell_size,
         "max_tile_blocks": int((c_b1 - c_b0).max().item()), "n_entries": n_entries,
+        "all_rows_nonempty": int(bool(nonempty.all().item())),
     }
 
 
@@ -426,13 +439,20 @@ def item_blocks(typ, entries, rec):
     return K
 
 
-def walk(plan, rec, n_bnz):
-    """CSR block values ``[n_bnz * 9]`` in the scalar CSR order of the fused path (row pitch = 3 * blocks in row)."""
+N_BLOCKS_OF_TYPE = {TYPE_A: 1, TYPE_B: 2, TYPE_C: 1, TYPE_D: 3, TYPE_E: 3}
+EDGE_OF_PAIR = {frozenset(pr): 4 + n for n, pr in enumerate(EDGE_PAIRS)}
+
+
+def walk(plan, rec, n_bnz, re4=None, n_nodes=None):
+    """CSR block values ``[n_bnz * 9]`` in the scalar CSR order of the fused path (row pitch = 3 * blocks in row).
+    With ``re4`` ``[n_cells, 10, 4]`` (padded local load vectors) also the right-hand side ``[3 n_nodes]`` the items A
+    and D write (``nfa_assemble_p2tet_elasticity_load``): returns ``(vals, rhs)``."""
     chunk_hdr = plan["chunk_hdr"].cpu().numpy().astype(np.int64)
     task_hdr = plan["task_hdr"].cpu().numpy().astype(np.int64)
     item_hdr = plan["item_hdr"].cpu().numpy().astype(np.int64) & 0xFFFF
     ell = plan["ell"].cpu().numpy().astype(np.int64) & NONE32
     vals = np.full(n_bnz * 9, np.nan)
+    rhs = np.full(3 * n_nodes, np.nan) if re4 is not None else None
     for ci, (b0, nblk, task0, ntask) in enumerate(chunk_hdr):
         tile = np.full(nblk * 9, np.nan)
         for t in range(task0, task0 + ntask):
@@ -440,18 +460,29 @@ def walk(plan, rec, n_bnz):
             assert ((task_hdr[t, 0] >> 16) & 1) == (b0 & 1)
             base, slot0, nit = task_hdr[t, 1], task_hdr[t, 2], task_hdr[t, 3] & 63
             assert task_hdr[t, 3] >> 6 == ci and slot0 % 2 == 0
-            per = 2 if typ == TYPE_E else 1
+            per = 2 if typ >= TYPE_D else 1
             for lane in range(nit):
                 entries = [ell[base + 32 * k + lane] for k in range(kmax)]
                 entries = [e for e in entries if e != NONE32]
                 assert typ not in (TYPE_C, TYPE_E) or len(entries) <= 2
                 K = item_blocks(typ, entries, rec)
                 w0, w1, w2, pitch = item_hdr[slot0 + per * lane]
-                targets = [(0, w0), (1, w1), (2, w2)]
+                targets = [(0, w0), (1, w1), (2, w2)][: N_BLOCKS_OF_TYPE[int(typ)]]
                 if typ == TYPE_E:
                     f0, f1 = item_hdr[slot0 + per * lane + 1][:2]
                     assert f1 == NONE16 or len(entries) == 2
                     targets += [(3, f0), (4, f1)]
+                if typ in (TYPE_A, TYPE_D):  # the owner of the node's right-hand-side rows
+                    node = (w1 | (w2 << 16)) if typ == TYPE_A else int(
+                        item_hdr[slot0 + per * lane + 1][0] | (item_hdr[slot0 + per * lane + 1][1] << 16))
+                    if rhs is not None:
+                        f = np.zeros(3)
+                        for e in entries:
+                            cell, i, j = int(e) >> 6, (int(e) >> 4) & 3, (int(e) >> 2) & 3
+                            a = i if typ == TYPE_A else EDGE_OF_PAIR[frozenset((i, j))]
+                            f += re4[cell, a, :3]
+                        assert np.all(np.isnan(rhs[3 * node : 3 * node + 3])), "right-hand-side rows written twice"
+                        rhs[3 * node : 3 * node + 3] = f
                 for k, w in targets:
                     if w == NONE16:
                         continue
@@ -459,4 +490,4 @@ def walk(plan, rec, n_bnz):
                         assert np.all(np.isnan(tile[w + r * pitch : w + r * pitch + 3])), "block written twice"
                         tile[w + r * pitch : w + r * pitch + 3] = K[k][r]
         vals[9 * b0 : 9 * (b0 + nblk)] = tile
-    return vals
+    return vals if rhs is None else (vals, rhs)

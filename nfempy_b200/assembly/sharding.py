@@ -188,8 +188,7 @@ class ShardedAssembler:
             self._graph.replay()  # zeroes rhs, overwrites every CSR value (GPUAssembler.capture)
         else:
             self.asm.jacobian.is_zero = True
-            self.rhs.zero_()
-            self.asm.run(self.state, self.rhs)
+            self.asm.run(self.state, self.rhs, fresh=True)  # zeroes rhs where the kernels do not overwrite it
         self.vals = self.asm.jacobian.values_dev
         return self.vals, self.rhs
 
@@ -341,10 +340,9 @@ class ShardedAssembler:
 
         def body():
             self.asm.jacobian.is_zero = True
-            self.rhs.zero_()
             self.asm._capturing = True
             try:
-                self.asm.run(self.state, self.rhs)
+                self.asm.run(self.state, self.rhs, fresh=True)
             finally:
                 self.asm._capturing = False
             self.vals = self.asm.jacobian.values_dev

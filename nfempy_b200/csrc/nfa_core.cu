@@ -435,7 +435,8 @@ __constant__ double c_load_wt[64 * 20];
 template <int DIM, int N_PHI, int N_COMP, int TILE>
 __global__ void __launch_bounds__(TILE *N_COMP)
     local_h1_load_stream_kernel(int n_q, const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
-                                int64_t n_cells, const double *__restrict__ f, double sign, double *__restrict__ re) {
+                                int64_t n_cells, const double *__restrict__ f, double sign, double *__restrict__ re,
+                                int comp_pitch) {
     extern __shared__ __align__(128) double smem[];  // two tiles [TILE][n_q][N_COMP], then two mbarriers
     const int fn = n_q * N_COMP;
     const int tile_doubles = TILE * fn;
@@ -499,10 +500,10 @@ __global__ void __launch_bounds__(TILE *N_COMP)
 #pragma unroll
                 for (int a = 0; a < N_PHI; ++a) acc[a] = fma(c_load_wt[q * N_PHI + a], v, acc[a]);
             }
-            double *dst = re + (c0 + lc) * (N_PHI * N_COMP) + comp;
+            double *dst = re + (c0 + lc) * (N_PHI * comp_pitch) + comp;  // comp_pitch > N_COMP: padded node records
             const double sc = sign * det;
 #pragma unroll
-            for (int a = 0; a < N_PHI; ++a) dst[a * N_COMP] = sc * acc[a];
+            for (int a = 0; a < N_PHI; ++a) dst[a * comp_pitch] = sc * acc[a];
         }
         __syncthreads();  // every reader of this tile is done: it may be refilled on the next trip
     }
@@ -514,11 +515,14 @@ __global__ void load_wt_kernel(int n, int n_phi, const double *__restrict__ tab0
     if (i < n) out[i] = weights[i / n_phi] * tab0[i];
 }
 
-template <int DIM, int N_PHI, int N_COMP>
+// TILE = 64: the stand-alone kernel (two 41 KB tiles, as many CTAs per SM as fit).  TILE = 24 with one CTA per SM is the
+// BACKGROUND form (nfa_local_h1_load_bg): 31 KB of shared memory and three warps, small enough to stay resident beside
+// the row-item matrix kernel of csrc/nfa_p2tet.cu (197 KB, 448 threads x 128 registers) and stream the load array with the
+// DRAM bandwidth that kernel leaves idle.
+template <int DIM, int N_PHI, int N_COMP, int TILE = 64>
 static int launch_h1_load_stream(int n_q, const double *tab0, const double *weights, const double *coords,
                                  const int32_t *cell_nodes, int64_t n_cells, const double *f, double sign, double *re,
-                                 cudaStream_t s) {
-    constexpr int TILE = 64;
+                                 cudaStream_t s, int comp_pitch = N_COMP, int max_per_sm = 0) {
     double *wt = nullptr;
     NFA_CUDA(cudaGetSymbolAddress((void **)&wt, c_load_wt));
     load_wt_kernel<<<grid_for(n_q * N_PHI, 128), 128, 0, s>>>(n_q * N_PHI, N_PHI, tab0, weights, wt);
@@ -526,14 +530,19 @@ static int launch_h1_load_stream(int n_q, const double *tab0, const double *weig
     const size_t smem = sizeof(double) * 2 * (size_t)TILE * n_q * N_COMP + 16;
     auto kern = local_h1_load_stream_kernel<DIM, N_PHI, N_COMP, TILE>;
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // background form: ask for the largest shared-memory carve-out, the one the matrix kernel beside it runs with -- an SM
+    // cannot change its carve-out while a CTA is resident, so with the default (smallest sufficient) carve-out whichever
+    // kernel arrives second would wait for the first to drain
+    if (max_per_sm > 0) NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 1, device = 0, n_sm = 148;
     NFA_CUDA(cudaGetDevice(&device));
     NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE * N_COMP, smem));
     if (per_sm < 1) return fail("nfa_local_h1_load: streaming kernel does not fit on an SM");
+    if (max_per_sm > 0) per_sm = std::min(per_sm, max_per_sm);
     const int64_t tiles = (n_cells + TILE - 1) / TILE;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)n_sm * per_sm);
-    kern<<<grid, TILE * N_COMP, smem, s>>>(n_q, coords, cell_nodes, n_cells, f, sign, re);
+    kern<<<grid, TILE * N_COMP, smem, s>>>(n_q, coords, cell_nodes, n_cells, f, sign, re, comp_pitch);
     NFA_LAUNCH_CHECK();
     return 0;
 }
@@ -555,6 +564,28 @@ static int launch_h1_load(int n_phi, int n_q, int n_comp, const double *tab0, co
     kern<<<grid, threads, smem, s>>>(n_phi, n_q, n_comp, tile, tab0, weights, coords, cell_nodes, n_cells, f, sign, re);
     NFA_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int nfa_local_h1_load_pitched(int dim, int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,
+                                         const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *f,
+                                         double sign, double *re, int comp_pitch, nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (!f) return fail("nfa_local_h1_load_pitched: the load array is NULL");
+    if (!(dim == 3 && n_phi == 10 && n_comp == 3 && n_q <= 64 && comp_pitch >= 3))
+        return fail("nfa_local_h1_load_pitched: vector P2 on tetrahedra with at most 64 quadrature points only");
+    return launch_h1_load_stream<3, 10, 3>(n_q, tab0, weights, coords, cell_nodes, n_cells, f, sign, re,
+                                           (cudaStream_t)stream, comp_pitch);
+}
+
+extern "C" int nfa_local_h1_load_bg(int dim, int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,
+                                    const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *f,
+                                    double sign, double *re, nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (!f) return fail("nfa_local_h1_load_bg: the load array is NULL");
+    if (!(dim == 3 && n_phi == 10 && n_comp == 3 && n_q <= 27))
+        return fail("nfa_local_h1_load_bg: vector P2 on tetrahedra with at most 27 quadrature points only");
+    return launch_h1_load_stream<3, 10, 3, 24>(n_q, tab0, weights, coords, cell_nodes, n_cells, f, sign, re,
+                                               (cudaStream_t)stream, 3, 1);
 }
 
 extern "C" int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,

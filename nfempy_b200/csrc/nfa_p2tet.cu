@@ -87,6 +87,9 @@ constexpr int P2_THREADS = NFA_P2_THREADS;
 #ifndef NFA_P2_UA
 #define NFA_P2_UA 8  // cells in flight, vertex-diagonal items (3 or more: the general loop)
 #endif
+#ifndef NFA_P2_UA_LD
+#define NFA_P2_UA_LD 5  // the same when the items also gather the load vectors (two records per cell)
+#endif
 #ifndef NFA_P2_UB
 #define NFA_P2_UB 4  // cells in flight, vertex-edge items
 #endif
@@ -292,7 +295,9 @@ struct TileCtx {
     volatile int *free_at;
     int need;
     unsigned ihx, ihy;  // packed 16-bit tile offsets of the three blocks and the row pitch (decoded when storing)
-    unsigned ihz;       // type E: tile offsets of the opposite-edge blocks of the item's first / second cell
+    unsigned ihz;       // type E: tile offsets of the opposite-edge blocks of the item's first / second cell; type D: row node
+    double *rhs;        // right-hand side (items A and D own the three rows of their node), or NULL
+    int rhs_overwrite;  // 1: the sums replace the rows (caller: rhs is zero or every node has cells), 0: they are added
     __device__ __forceinline__ void wait() const {
         if ((threadIdx.x & 31) == 0) {
             const uint32_t a = (uint32_t)__cvta_generic_to_shared(const_cast<int *>(free_at));
@@ -311,57 +316,91 @@ struct TileCtx {
     __device__ __forceinline__ void put_opposite(int cell, const double (&v)[9]) const {
         store_block(tile, cell == 0 ? (ihz & 0xFFFFu) : (ihz >> 16), ihy >> 16, v);
     }
+    // the load-vector sums of row node `node` (ascending cell order, like the reference's res_g[dest] += r_el,
+    // R/src/assembly/ScatterFormData.py:14-18): every row has exactly one owner thread, so plain stores / read-add-store
+    __device__ __forceinline__ void put_rhs(unsigned node, const double (&f)[3]) const {
+        double *r = rhs + 3 * (size_t)node;
+        if (rhs_overwrite) {
+            r[0] = f[0];
+            r[1] = f[1];
+            r[2] = f[2];
+        } else {
+            const double o0 = r[0], o1 = r[1], o2 = r[2];
+            r[0] = o0 + f[0];
+            r[1] = o1 + f[1];
+            r[2] = o2 + f[2];
+        }
+    }
 };
 
 // ---- per item type: which vertices' records an entry needs, how a cell adds to the sums, how the sums become blocks
-template <int NG>
+// LDA: 0 = no load vector, 1 = the row node is vertex i (items A), 2 = the row node is the edge (i, j) (items D): the
+// cell's local load vector of that node, re4 [n_cells][10][4] (three components + one pad: one 32-byte sector), rides
+// along as record NG
+template <int NG, int LDA = 0>
 struct Rec {
-    G4 g[NG];
+    G4 g[NG + (LDA ? 1 : 0)];
     bool valid;
 };
 
-template <int NG>
-__device__ __forceinline__ Rec<NG> load_rec(uint32_t code, const double *__restrict__ rec) {
-    Rec<NG> r;
+template <int NG, int LDA = 0>
+__device__ __forceinline__ Rec<NG, LDA> load_rec(uint32_t code, const double *__restrict__ rec,
+                                                 const double *__restrict__ re4 = nullptr) {
+    Rec<NG, LDA> r;
     r.valid = code != 0xFFFFFFFFu;
 #pragma unroll
-    for (int m = 0; m < NG; ++m) r.g[m] = G4{0.0, 0.0, 0.0, 0.0};
+    for (int m = 0; m < NG + (LDA ? 1 : 0); ++m) r.g[m] = G4{0.0, 0.0, 0.0, 0.0};
     if (r.valid) {
         const double *rc = rec + (size_t)(code >> 6) * 16;
-        r.g[0] = ldg256(rc + 4 * ((code >> 4) & 3u));
-        if constexpr (NG > 1) r.g[1] = ldg256(rc + 4 * ((code >> 2) & 3u));
+        const unsigned i = (code >> 4) & 3u, j = (code >> 2) & 3u;
+        r.g[0] = ldg256(rc + 4 * i);
+        if constexpr (NG > 1) r.g[1] = ldg256(rc + 4 * j);
         if constexpr (NG > 2) r.g[2] = ldg256(rc + 4 * (code & 3u));
+        if constexpr (LDA != 0) {
+            // local P2 node: vertex i, or the edge node of (i, j) in the order (2,3),(1,3),(1,2),(0,3),(0,2),(0,1) = 4..9
+            const unsigned a = LDA == 1 ? i : 10u - (i + j) - ((i < j ? i : j) >= 1u ? 1u : 0u);
+            r.g[NG] = ldg256(re4 + ((size_t)(code >> 6) * 10 + a) * 4);
+        }
     }
     return r;
 }
 
 constexpr double C10 = 0.1, C30 = 1.0 / 30.0, C15 = 2.0 / 15.0;
 
-template <int TYPE, bool CR>
+template <int TYPE, bool CR, bool LD>
 struct Item;
 
-template <bool CR>
-struct Item<0, CR> {
-    double rho = 0.0;  // A: (v, v) = 0.1 Kf(g_i g_i^T)
-    static constexpr int NG = 1;
+template <bool CR, bool LD>
+struct Item<0, CR, LD> {
+    double rho = 0.0;  // A: (v, v) = 0.1 Kf(g_i g_i^T); LD: + the three right-hand-side rows of the vertex
+    static constexpr int NG = 1, LDA = LD ? 1 : 0;
     double q[6] = {0, 0, 0, 0, 0, 0}, tr = 0.0;
-    __device__ __forceinline__ void add(const Rec<NG> &r) {
+    double f[3] = {0, 0, 0};
+    __device__ __forceinline__ void add(const Rec<NG, LDA> &r) {
         rho = r.g[0].rho;
         const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z};
         tr += add_sym<CR>(q, r.g[0].rho, u);
+        if constexpr (LD) {
+            f[0] += r.g[NG].x;
+            f[1] += r.g[NG].y;
+            f[2] += r.g[NG].z;
+        }
     }
     __device__ __forceinline__ void finish(const TileCtx &ctx) {
         double o[9];
         fix_sym<CR>(q, tr, rho);
         sym_to_full(q, C10, tr, o);
         ctx.put(0, o);
+        // the vertex's node id rides in the two unused block slots of the item header
+        if constexpr (LD)  // (lanes beyond the task's items carry an all-ones header)
+            if ((ctx.ihx & 0xFFFFu) != 0xFFFFu) ctx.put_rhs((ctx.ihx >> 16) | ((ctx.ihy & 0xFFFFu) << 16), f);
     }
 };
 
-template <bool CR>
-struct Item<1, CR> {
+template <bool CR, bool LD>
+struct Item<1, CR, LD> {
     double rho = 0.0;  // B: (v, v') = -1/30 P, (v, E) = 0.1 P - Q / 30 with P = Kf(g_i (x) g_k), Q = Kf(g_i g_i^T)
-    static constexpr int NG = 2;
+    static constexpr int NG = 2, LDA = 0;
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, q[6] = {0, 0, 0, 0, 0, 0}, trp = 0.0, trq = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
         rho = r.g[0].rho;
@@ -385,10 +424,10 @@ struct Item<1, CR> {
     }
 };
 
-template <bool CR>
-struct Item<2, CR> {
+template <bool CR, bool LD>
+struct Item<2, CR, LD> {
     double rho = 0.0;  // C: (v, e_xy) = Kf(g_i (x) (g_i + g_z)) / 30, since g_x + g_y = -(g_i + g_z)
-    static constexpr int NG = 2;
+    static constexpr int NG = 2, LDA = 0;
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, trp = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
         rho = r.g[0].rho;
@@ -405,18 +444,24 @@ struct Item<2, CR> {
     }
 };
 
-template <bool CR>
-struct Item<3, CR> {
+template <bool CR, bool LD>
+struct Item<3, CR, LD> {
     double rho = 0.0;  // D: (E, v_i) = 0.1 P^T - Qi / 30, (E, v_j) = 0.1 P - Qj / 30, (E, E) = 2/15 (2 Qi + 2 Qj + P + P^T)
-    static constexpr int NG = 2;
+    static constexpr int NG = 2, LDA = LD ? 2 : 0;  // LD: + the three right-hand-side rows of the edge node
     double p[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, qi[6] = {0, 0, 0, 0, 0, 0}, qj[6] = {0, 0, 0, 0, 0, 0};
     double trp = 0.0, tri = 0.0, trj = 0.0;
-    __device__ __forceinline__ void add(const Rec<NG> &r) {
+    double f[3] = {0, 0, 0};
+    __device__ __forceinline__ void add(const Rec<NG, LDA> &r) {
         rho = r.g[0].rho;
         const double u[3] = {r.g[0].x, r.g[0].y, r.g[0].z}, w[3] = {r.g[1].x, r.g[1].y, r.g[1].z};
         trp += add_general<CR>(p, r.g[0].rho, u, w);
         tri += add_sym<CR>(qi, r.g[0].rho, u);
         trj += add_sym<CR>(qj, r.g[0].rho, w);
+        if constexpr (LD) {
+            f[0] += r.g[NG].x;
+            f[1] += r.g[NG].y;
+            f[2] += r.g[NG].z;
+        }
     }
     __device__ __forceinline__ void finish(const TileCtx &ctx) {
         double fi[9], fj[9], o[9];
@@ -441,13 +486,15 @@ struct Item<3, CR> {
             for (int s = 0; s < 3; ++s)
                 o[3 * r + s] = C15 * (2.0 * (fi[3 * r + s] + fj[3 * r + s]) + p[3 * r + s] + p[3 * s + r]);
         ctx.put(2, o);
+        if constexpr (LD)  // second header slot of a type D item: the edge's node id
+            if ((ctx.ihx & 0xFFFFu) != 0xFFFFu) ctx.put_rhs(ctx.ihz, f);
     }
 };
 
-template <bool CR>
-struct Item<4, CR> {
+template <bool CR, bool LD>
+struct Item<4, CR, LD> {
     double rho = 0.0;  // E: (E, v_x), (E, e_ix), (E, e_jx) with s = g_i + g_j
-    static constexpr int NG = 3;
+    static constexpr int NG = 3, LDA = 0;
     double k0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k1[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, k2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     double t0 = 0.0, t1 = 0.0, t2 = 0.0;
     __device__ __forceinline__ void add(const Rec<NG> &r) {
@@ -486,14 +533,14 @@ struct Item<4, CR> {
 // cell keep two cells in flight; type E (three records, 27 sums) walks one cell at a time to stay inside the register
 // budget.  pf0, pf1: first entries of the NEXT task -- their cells' records (one 128-byte line each) are pulled into L1
 // once this task's sums are complete.
-template <int TYPE, bool CR, int UNROLL_NG>
+template <int TYPE, bool CR, bool LD, int UNROLL_NG>
 __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kmax, uint32_t c0, uint32_t c1,
-                                         const double *__restrict__ rec, uint32_t pf0, uint32_t pf1,
-                                         const TileCtx &ctx) {
-    constexpr int NG = Item<TYPE, CR>::NG;
+                                         const double *__restrict__ rec, const double *__restrict__ re4, uint32_t pf0,
+                                         uint32_t pf1, const TileCtx &ctx) {
+    constexpr int NG = Item<TYPE, CR, LD>::NG, LDA = Item<TYPE, CR, LD>::LDA;
     // cells in flight per iteration: long items with few sums walk many cells at once (their task would otherwise
     // hold its chunk's tile for tens of dependent load latencies); type E stays at one (register budget)
-    constexpr int U = (TYPE == 0) ? NFA_P2_UA : ((TYPE == 1) ? NFA_P2_UB : ((NG <= UNROLL_NG) ? 2 : 1));
+    constexpr int U = (TYPE == 0) ? (LD ? NFA_P2_UA_LD : NFA_P2_UA) : ((TYPE == 1) ? NFA_P2_UB : ((NG <= UNROLL_NG) ? 2 : 1));
 #if NFA_P2_E2
     if constexpr (TYPE == 4) {
         // a face has at most two cells: both cells' records are requested at once (one memory round trip instead of two)
@@ -580,7 +627,7 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
         return;
     }
 #endif
-    Item<TYPE, CR> item;
+    Item<TYPE, CR, LD> item;
     if constexpr (U > 2) {
         uint32_t c[U];
         c[0] = c0;
@@ -589,9 +636,9 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
         for (int u = 2; u < U; ++u) c[u] = (u < kmax) ? ld_list(e + 32 * u) : 0xFFFFFFFFu;
 #pragma unroll 1
         for (int k = 0; k < kmax; k += U) {
-            Rec<NG> r[U];
+            Rec<NG, LDA> r[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) r[u] = load_rec<NG>(c[u], rec);
+            for (int u = 0; u < U; ++u) r[u] = load_rec<NG, LDA>(c[u], rec, re4);
 #pragma unroll
             for (int u = 0; u < U; ++u) c[u] = (k + U + u < kmax) ? ld_list(e + 32 * (k + U + u)) : 0xFFFFFFFFu;
 #pragma unroll
@@ -601,7 +648,7 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
     } else if constexpr (U == 2) {
 #pragma unroll 1
         for (int k = 0; k < kmax; k += 2) {
-            const Rec<NG> r0 = load_rec<NG>(c0, rec), r1 = load_rec<NG>(c1, rec);
+            const Rec<NG, LDA> r0 = load_rec<NG, LDA>(c0, rec, re4), r1 = load_rec<NG, LDA>(c1, rec, re4);
             c0 = (k + 2 < kmax) ? ld_list(e + 32 * (k + 2)) : 0xFFFFFFFFu;
             c1 = (k + 3 < kmax) ? ld_list(e + 32 * (k + 3)) : 0xFFFFFFFFu;
             if (r0.valid) item.add(r0);
@@ -610,7 +657,7 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
     } else {
 #pragma unroll 1
         for (int k = 0; k < kmax; ++k) {
-            const Rec<NG> r0 = load_rec<NG>(c0, rec);
+            const Rec<NG, LDA> r0 = load_rec<NG, LDA>(c0, rec, re4);
             c0 = c1;
             c1 = (k + 2 < kmax) ? ld_list(e + 32 * (k + 2)) : 0xFFFFFFFFu;
             if (r0.valid) item.add(r0);
@@ -625,12 +672,16 @@ __device__ __forceinline__ void run_task(const uint32_t *__restrict__ e, int kma
 // Warps of a CTA pull tasks from the CTA's contiguous chunk range through one shared counter; chunk c lives in tile
 // (c - c_begin) % NBUF.  The warp that finishes the last task of a chunk sends the tile to HBM with one bulk copy,
 // waits until the copy engine has read it and hands the tile to chunk c + NBUF.  No CTA-wide barrier in the loop.
-template <bool CR, int THREADS, int NB>
+// LD: items A and D also sum the padded local load vectors re4 [n_cells][10][4] of their node (written by
+// nfa_local_h1_load_pitched) and write the node's three right-hand-side rows -- the row owner walks exactly the cells the
+// rows need, so the separate gather / reduce pass over the local load vectors is gone.
+template <bool CR, int THREADS, int NB, bool LD>
 __global__ void __launch_bounds__(THREADS, 1)
     p2tet_elasticity_kernel(int nbuf_rt, int n_chunks, const int4 *__restrict__ chunk_hdr, const int4 *__restrict__ task_hdr,
                             const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
                             const double *__restrict__ rec, int tile_stride, double *__restrict__ vals,
-                            unsigned ell_size, unsigned n_slots, int n_tasks) {
+                            unsigned ell_size, unsigned n_slots, int n_tasks, const double *__restrict__ re4,
+                            double *__restrict__ rhs, int rhs_overwrite) {
     // NB > 0: the number of tiles is a compile-time power of two, so that the tile of a chunk ((c - c_begin) % NBUF) and its
     // round ((c - c_begin) / NBUF) cost a mask and a shift instead of two integer divisions per task (the task loop's scalar
     // bookkeeping is 40 % of the instructions the kernel executes)
@@ -709,7 +760,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         if (th2.w != -1) {  // task i+2: its ELL lines (a lane per line) and item headers go to L2
             const int kmax2 = (th2.x >> 8) & 0xFF;
             for (int k = lane; k < kmax2; k += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ell + (uint32_t)th2.y + 32 * k));
-            const int per2 = ((th2.x & 0xFF) == 4) ? 2 : 1;
+            const int per2 = ((th2.x & 0xFF) >= 3) ? 2 : 1;
             if ((lane & (15 >> (per2 - 1))) == 0 && lane < (th2.w & 63))
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(item_hdr + th2.z + per2 * lane));
         }
@@ -745,7 +796,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 #if NFA_P2_PF_IH
             // task i+1's item headers (32 x 8 bytes = two lines): lanes 0 and 16 pull them into L1
             {
-                const int per1 = ((th1.x & 0xFF) == 4) ? 2 : 1;  // type E items take two 8-byte slots
+                const int per1 = ((th1.x & 0xFF) >= 3) ? 2 : 1;  // type D and E items take two 8-byte slots
                 if ((lane & (15 >> (per1 - 1))) == 0 && lane < (th1.w & 63))
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(item_hdr + th1.z + per1 * lane));
             }
@@ -757,7 +808,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             const int kmax0 = (th.x >> 8) & 0xFF;
             const unsigned pe = (unsigned)th.y + NFA_P2_PFD_ELL + 32u * (unsigned)lane;
             if (lane < kmax0 && pe < ell_size) asm volatile("prefetch.global.L2 [%0];" ::"l"(ell + pe));
-            const int per0 = ((th.x & 0xFF) == 4) ? 2 : 1;
+            const int per0 = ((th.x & 0xFF) >= 3) ? 2 : 1;
             const unsigned ps = (unsigned)th.z + NFA_P2_PFD_IH + 16u * (unsigned)lane;  // 16 slots = one 128-byte line
             if (16 * lane < per0 * (th.w & 63) && ps < n_slots) asm volatile("prefetch.global.L2 [%0];" ::"l"(item_hdr + ps));
         }
@@ -768,7 +819,7 @@ __global__ void __launch_bounds__(THREADS, 1)
             uint2 ih = make_uint2(0xFFFFFFFFu, 0xFFFFu);
             unsigned ihz = 0xFFFFFFFFu;
             if (lane < n_items) {
-                if (type == 4) {  // two slots per item: blocks + pitch, then the opposite-edge blocks
+                if (type >= 3) {  // two slots per item: blocks + pitch, then the opposite-edge blocks (E) / the row node (D)
                     const uint2 *hp = item_hdr + th.z + 2 * lane;
                     ih = ld_list(hp);
                     ihz = ld_list(hp + 1).x;
@@ -779,13 +830,14 @@ __global__ void __launch_bounds__(THREADS, 1)
             const int it = c - c_begin_r, b = it % NBUF;
             // the tile sits on the same 16-byte phase as its image in vals (parity of the chunk's first block)
             double *tile = smem + (size_t)b * tile_stride + ((th.x >> 16) & 1);
-            const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y, ihz};
+            const TileCtx ctx = {tile, ctrl + 4 + NBUF + b, it / NBUF, ih.x, ih.y, ihz, rhs, rhs_overwrite};
+            constexpr int UNG = THREADS <= 384 ? 3 : P2_UNROLL_NG;
             switch (type) {
-                case 0: run_task<0, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                case 1: run_task<1, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                case 2: run_task<2, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                case 3: run_task<3, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
-                default: run_task<4, CR, (THREADS <= 384 ? 3 : P2_UNROLL_NG)>(e, kmax, c0, c1, rec, n0, n1, ctx); break;
+                case 0: run_task<0, CR, LD, UNG>(e, kmax, c0, c1, rec, re4, n0, n1, ctx); break;
+                case 1: run_task<1, CR, LD, UNG>(e, kmax, c0, c1, rec, re4, n0, n1, ctx); break;
+                case 2: run_task<2, CR, LD, UNG>(e, kmax, c0, c1, rec, re4, n0, n1, ctx); break;
+                case 3: run_task<3, CR, LD, UNG>(e, kmax, c0, c1, rec, re4, n0, n1, ctx); break;
+                default: run_task<4, CR, LD, UNG>(e, kmax, c0, c1, rec, re4, n0, n1, ctx); break;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -973,9 +1025,14 @@ extern "C" int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *mask, nfa_s
     return 0;
 }
 
-extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *coords, const int32_t *cell_nodes,
-                                             const double *lam, int64_t ls, const double *mu, int64_t ms, double *vals,
-                                             nfa_stream stream) {
+// threads per CTA of the row-item kernel: 0 = the default (512, or NFA_P2TET_THREADS); GPUAssembler selects 448 while the
+// background load kernel shares the SMs (nfa_local_h1_load_bg needs 4 K registers and 32 KB of shared memory beside it)
+static int g_p2_threads = 0;
+extern "C" void nfa_p2tet_set_threads(int threads) { g_p2_threads = threads; }
+
+static int assemble_p2tet(const nfa_bplan *bp, const double *coords, const int32_t *cell_nodes, const double *lam,
+                          int64_t ls, const double *mu, int64_t ms, double *vals, const double *re4, double *rhs,
+                          int rhs_overwrite, nfa_stream stream) {
     if (!bp) return fail("nfa_assemble_p2tet_elasticity: plan is NULL");
     const nfa_bplan::P2Items &it = bp->p2;
     if (it.n_chunks <= 0) return fail("nfa_assemble_p2tet_elasticity: the plan carries no row items");
@@ -993,19 +1050,22 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     // both coefficients constant over the mesh: rho = lambda / mu is one number and Kf is applied once per block
     const bool cr = (ls == 0 && ms == 0);
     int threads = P2_THREADS;  // 512 (128 registers): more warps spill and lose (1.5 ms), see DESIGN.md
+    if (g_p2_threads > 0) threads = g_p2_threads;
     if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
     if (threads > 640) threads = 512;  // larger counts are staged-kernel settings
     using kern_t = void (*)(int, int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
-                            double *, unsigned, unsigned, int);
+                            double *, unsigned, unsigned, int, const double *, double *, int);
     kern_t kern = nullptr;
     const bool nb4 = nbuf == 4 && !getenv("NFA_P2TET_RT_NBUF");
-#define NFA_P2_PICK(CRV, TH)                                                      \
-    if (cr == CRV && threads == TH)                                               \
-        kern = nb4 ? p2tet_elasticity_kernel<CRV, TH, 4> : p2tet_elasticity_kernel<CRV, TH, 0>;
-    NFA_P2_PICK(false, 384) NFA_P2_PICK(false, 448) NFA_P2_PICK(false, 512) NFA_P2_PICK(false, 576) NFA_P2_PICK(false, 640)
-    NFA_P2_PICK(true, 384) NFA_P2_PICK(true, 448) NFA_P2_PICK(true, 512) NFA_P2_PICK(true, 576) NFA_P2_PICK(true, 640)
+    const bool ld = re4 != nullptr && rhs != nullptr;
+#define NFA_P2_PICK(CRV, TH)                                                                                          \
+    if (cr == CRV && threads == TH)                                                                                   \
+        kern = ld ? (nb4 ? p2tet_elasticity_kernel<CRV, TH, 4, true> : p2tet_elasticity_kernel<CRV, TH, 0, true>)     \
+                  : (nb4 ? p2tet_elasticity_kernel<CRV, TH, 4, false> : p2tet_elasticity_kernel<CRV, TH, 0, false>);
+    NFA_P2_PICK(false, 384) NFA_P2_PICK(false, 448) NFA_P2_PICK(false, 480) NFA_P2_PICK(false, 512) NFA_P2_PICK(false, 640)
+    NFA_P2_PICK(true, 384) NFA_P2_PICK(true, 448) NFA_P2_PICK(true, 480) NFA_P2_PICK(true, 512) NFA_P2_PICK(true, 640)
 #undef NFA_P2_PICK
-    if (!kern) return fail("nfa_assemble_p2tet_elasticity: NFA_P2TET_THREADS must be 384, 448, 512, 576 or 640");
+    if (!kern) return fail("nfa_assemble_p2tet_elasticity: NFA_P2TET_THREADS must be 384, 448, 480, 512 or 640");
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, device = 0, n_sm = 148;
     NFA_CUDA(cudaGetDevice(&device));
@@ -1018,8 +1078,23 @@ extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *
     kern<<<(unsigned)grid, threads, smem, s>>>(nbuf, (int)it.n_chunks, (const int4 *)it.chunk_hdr.p,
                                                   (const int4 *)it.task_hdr.p, (const uint2 *)it.item_hdr.p,
                                                   (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride, vals,
-                                                  (unsigned)it.ell_size, (unsigned)it.n_items, (int)it.n_tasks);
+                                                  (unsigned)it.ell_size, (unsigned)it.n_items, (int)it.n_tasks, re4, rhs,
+                                                  rhs_overwrite);
     if (timing_enabled()) timing_end(s);
     NFA_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *coords, const int32_t *cell_nodes,
+                                             const double *lam, int64_t ls, const double *mu, int64_t ms, double *vals,
+                                             nfa_stream stream) {
+    return assemble_p2tet(bp, coords, cell_nodes, lam, ls, mu, ms, vals, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int nfa_assemble_p2tet_elasticity_load(const nfa_bplan *bp, const double *coords, const int32_t *cell_nodes,
+                                                  const double *lam, int64_t ls, const double *mu, int64_t ms,
+                                                  double *vals, const double *re4, double *rhs, int rhs_overwrite,
+                                                  nfa_stream stream) {
+    if (!re4 || !rhs) return fail("nfa_assemble_p2tet_elasticity_load: re4 and rhs must not be NULL");
+    return assemble_p2tet(bp, coords, cell_nodes, lam, ls, mu, ms, vals, re4, rhs, rhs_overwrite, stream);
 }

@@ -64,6 +64,14 @@ def test_item_plan_reproduces_the_block_sums(n, cap, riffle, optimise):
     rec = p2_items.geometry_records(mesh.points, cell_nodes, lam, mu)
     got = p2_items.walk(plan, rec, len(keys))
     assert not np.isnan(got).any(), "some CSR block was never written"
+    # the items that own a node's diagonal block also own its right-hand-side rows (nfa_assemble_p2tet_elasticity_load)
+    re4 = rng.standard_normal((len(node_dest), 10, 4))
+    got2, rhs = p2_items.walk(plan, rec, len(keys), re4=re4, n_nodes=n_nodes)
+    assert np.array_equal(got2, got) and not np.isnan(rhs).any(), "some right-hand-side row was never written"
+    rhs_ref = np.zeros((n_nodes, 3))
+    np.add.at(rhs_ref, node_dest.reshape(-1), re4[:, :, :3].reshape(-1, 3))
+    assert np.abs(rhs.reshape(-1, 3) - rhs_ref).max() <= 1e-13 * np.abs(rhs_ref).max()
+    assert plan["all_rows_nonempty"] == 1
     ref = _brute_force(space, s, mesh, node_dest, n_nodes, cell_nodes, keys, bptr, lam, mu)
     assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
     if optimise:  # the lane permutation moves items between lanes, never between sums: same values bit for bit
@@ -84,9 +92,11 @@ def _store_wavefronts(plan):
     total = ideal = 0
     for typ_k, _, slot0, nit in th:
         typ, nit = typ_k & 0xFF, nit & 63
-        per = 2 if typ == p2_items.TYPE_E else 1
-        rows = ih[slot0 + per * np.arange(nit)]
-        extra = ih[slot0 + per * np.arange(nit) + 1][:, :2] if per == 2 else np.full((nit, 2), p2_items.NONE16)
+        per = 2 if typ >= p2_items.TYPE_D else 1
+        rows = ih[slot0 + per * np.arange(nit)].copy()
+        if typ == p2_items.TYPE_A:  # the two unused block slots carry the row's node id
+            rows[:, 1:3] = p2_items.NONE16
+        extra = ih[slot0 + per * np.arange(nit) + 1][:, :2] if typ == p2_items.TYPE_E else np.full((nit, 2), p2_items.NONE16)
         sig = p2_items.store_signature(np.concatenate([rows, extra], axis=1))
         for h in range(0, nit, 16):
             for p in range(p2_items.N_SIG):

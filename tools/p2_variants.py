@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--plans", default="640:296:8")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--varying", action="store_true", help="cell-wise lambda (general-rho instantiation)")
+    ap.add_argument("--load", action="store_true", help="time nfa_assemble_p2tet_elasticity_load (matrix + right-hand side)")
     args = ap.parse_args()
     import torch
 
@@ -51,7 +52,8 @@ def main():
         if name not in libs:
             path = os.path.join(ROOT, "nfempy_b200", "csrc", "variants", "libnfa_%s.so" % name)
             lib = ctypes.CDLL(path)
-            for fn in ("nfa_assemble_p2tet_elasticity", "nfa_timing_enable", "nfa_timing_read", "nfa_last_error"):
+            for fn in ("nfa_assemble_p2tet_elasticity", "nfa_assemble_p2tet_elasticity_load", "nfa_timing_enable",
+                       "nfa_timing_read", "nfa_last_error"):
                 res, at = _lib.SIGNATURES[fn]
                 getattr(lib, fn).restype = res
                 getattr(lib, fn).argtypes = at
@@ -82,9 +84,19 @@ def main():
         lam_c, mu_c = data.coefs["lambda"], data.coefs["mu"]
         stream = _lib.stream_ptr()
 
+        re4 = torch.empty((data.n_items, 10, 4), dtype=torch.float64, device=dev.device)
+        form.launch_load(data.dev, data, re4, comp_pitch=4)
+        rhs_ref = rhs.clone()
+        rhs_out = torch.empty_like(rhs)
+
         def call(lib):
-            rc = lib.nfa_assemble_p2tet_elasticity(plan.bplan, _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes), _lib.ptr(lam_c[0]),
-                                                   lam_c[1], _lib.ptr(mu_c[0]), mu_c[1], _lib.ptr(out), stream)
+            if args.load:
+                rc = lib.nfa_assemble_p2tet_elasticity_load(plan.bplan, _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes),
+                                                            _lib.ptr(lam_c[0]), lam_c[1], _lib.ptr(mu_c[0]), mu_c[1], _lib.ptr(out),
+                                                            _lib.ptr(re4), _lib.ptr(rhs_out), 1, stream)
+            else:
+                rc = lib.nfa_assemble_p2tet_elasticity(plan.bplan, _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes), _lib.ptr(lam_c[0]),
+                                                       lam_c[1], _lib.ptr(mu_c[0]), mu_c[1], _lib.ptr(out), stream)
             if rc != 0:
                 raise RuntimeError((lib.nfa_last_error() or b"").decode())
 
@@ -115,6 +127,8 @@ def main():
                 rec["kernel_ms"] = ms.value / max(cnt.value, 1)
                 rec["max_rel_diff"] = float((out - ref).abs().max().item()) / ref_max
                 rec["nan"] = bool(torch.isnan(out).any().item())
+                if args.load:
+                    rec["rhs_max_rel_diff"] = float((rhs_out - rhs_ref).abs().max().item()) / float(rhs_ref.abs().max().item())
             except Exception as exc:  # report and go on
                 rec["error"] = str(exc)
             print(json.dumps(rec), flush=True)
