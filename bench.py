@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--n", type=int, default=55, help="cubes per box edge (55 -> 998250 tets)")
     ap.add_argument("--cpu-cells", type=int, default=720, help="cells in the bounded CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-varying", action="store_true", help="skip the cell-wise varying lambda, mu leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the captured CUDA graph")
     ap.add_argument("--no-p2p", action="store_true", help="N > 1: exchange the interface rows with NCCL send/recv instead "
@@ -448,6 +449,10 @@ def run_graft(args):
         # host buffers (there is no multi-process form of the reference's API to mirror)
         e2e = run_e2e_api(args, torch, device, space, form, n_cells, asm) if sharded is None else e2e_all
 
+    varying = None
+    if world == 1 and not args.no_varying:
+        varying = run_varying(args, torch, lib, device, space, datas[0], n_cells, b_kernel, b_step, peak)
+
     parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         parity = parity_check(torch, space, asm, plan, step, 40000)
@@ -482,11 +487,68 @@ def run_graft(args):
                 "exchange": None if sharded is None else ("nfa_push_rows / nfa_pull_add_rows over NVLink peer memory (CUDA IPC)" if p2p
                                                           else "pack kernels + ncclSend/ncclRecv + unpack kernels"),
             },
-            "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "cpu_strong": cpu_strong, "e2e": e2e, "e2e_all_inputs": e2e_all, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "varying_coefficients": varying, "parity": parity, "cpu_baseline": cpu, "cpu_strong": cpu_strong, "e2e": e2e, "e2e_all_inputs": e2e_all, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_varying(args, torch, lib, device, space, data0, n_cells, b_kernel, b_step, peak):
+    """The same step with CELL-WISE VARYING Lame coefficients (the general-rho instantiation of the row-item kernel: Kf is
+    applied per contribution instead of once per block -- twice the FP64 work of the constant-coefficient headline).  Same
+    mesh, same load, own plan and CSR; timed like the headline (graph replay, CUDA events, args.steps steps)."""
+    from nfempy_b200 import _lib
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.weak_forms import LEPrimalWeakForm
+
+    rng = np.random.default_rng(99)
+    arrays = {"lambda": 1.0 + rng.random(n_cells), "mu": 0.5 + rng.random(n_cells),
+              "rhs": None if data0.f is None else data0.f.cpu().numpy()}
+
+    class CellwiseForm(LEPrimalWeakForm):
+        def prepare(self, dev, items=None, arrays_=None):
+            return LEPrimalWeakForm.prepare(self, dev, items, arrays=arrays)
+
+    form = CellwiseForm(space)
+    form.functions = {"rhs": None, "lambda": None, "mu": None}
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof), device=device)
+    asm.form_to_input_list = {"volume": ["form", range(n_cells), form, None]}
+    state = asm.prepare()
+    plan = state[4]
+    rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=device)
+
+    def step():
+        asm.jacobian.is_zero = True
+        asm.run(state, rhs, fresh=True)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    lib.nfa_timing_enable(1)
+    for _ in range(max(args.steps, 5)):
+        step()
+    torch.cuda.synchronize()
+    k_ms, k_n = ctypes.c_double(), ctypes.c_int64()
+    _lib.check(lib.nfa_timing_read(ctypes.byref(k_ms), ctypes.byref(k_n)), "nfa_timing_read")
+    lib.nfa_timing_enable(0)
+    replay = step if args.no_graph else asm.capture(state, rhs).replay
+    for _ in range(max(args.warmup, 3)):
+        replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    kernel_ms = k_ms.value / max(k_n.value, 1)
+    return {"coefficients": "lambda in [1, 2), mu in [0.5, 1.5) drawn per cell", "ms_per_step": ms,
+            "value": n_cells / (ms * 1e-3), "unit": "elements/s", "kernel_ms": kernel_ms,
+            "frac": b_kernel * n_cells / (kernel_ms * 1e-3) / 1e9 / peak,
+            "step_frac": b_step * n_cells / (ms * 1e-3) / 1e9 / peak,
+            "path": "fused (row items)" if getattr(plan, "p2_stats", None) else "fused"}
 
 
 def run_e2e_api(args, torch, device, space, form, n_cells, asm):

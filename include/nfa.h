@@ -71,14 +71,8 @@ int nfa_local_h1_laplace(int dim, int n_phi, int n_q, const double *d_tab, const
 int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *d_tab0, const double *d_weights,
                       const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_f,
                       double sign, double *d_re, nfa_stream stream);
-/* the same as a BACKGROUND kernel (vector P2 on tetrahedra): one small persistent CTA per SM (31 KB of shared memory,
- * three warps) that fits beside the row-item matrix kernel, so that a second stream can compute the load vector while
- * nfa_assemble_p2tet_elasticity runs (GPUAssembler forks the step's stream; the matrix kernel then runs 448 threads) */
-int nfa_local_h1_load_bg(int dim, int n_phi, int n_q, int n_comp, const double *d_tab0, const double *d_weights,
-                         const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_f,
-                         double sign, double *d_re, nfa_stream stream);
 /* the same with padded node records: re [n, n_phi, comp_pitch] (comp_pitch = 4 for vector P2 on tetrahedra: one 32-byte
- * sector per (cell, node), what nfa_assemble_p2tet_elasticity_load gathers) */
+ * sector per (cell, node), what nfa_bplan_gather_load and nfa_assemble_p2tet_elasticity_load gather) */
 int nfa_local_h1_load_pitched(int dim, int n_phi, int n_q, int n_comp, const double *d_tab0, const double *d_weights,
                               const double *d_coords, const int32_t *d_cell_nodes, int64_t n_cells, const double *d_f,
                               double sign, double *d_re, int comp_pitch, nfa_stream stream);
@@ -157,7 +151,8 @@ int nfa_local_sundus(int dim, int n_u, int n_p, int n_q, int nfd, const double *
  * base == NULL: the pattern is defined by these segments.  base != NULL: the segments are merged INTO the
  * pattern of `base` (every pair must already be present, else an error) -- used to add boundary forms to a
  * pattern produced by the fused path.  seg_flags[s] & 1: the segment contributes matrix entries (otherwise
- * right-hand-side rows only, e.g. the volume load of the fused path); seg_flags == NULL means all do. */
+ * right-hand-side rows only, e.g. the volume load of the fused path); bit 1 set: the segment's right-hand side is summed
+ * elsewhere (nfa_bplan_gather_load) and stays out of the plan's row lists; seg_flags == NULL means matrix + rhs for all. */
 int nfa_plan_create(int64_t n_dof, int n_segments, const int32_t *const *d_dest, const int64_t *n_items,
                     const int32_t *n_loc, const int32_t *seg_flags, const nfa_plan *base, nfa_plan **out,
                     nfa_stream stream);
@@ -208,6 +203,22 @@ int nfa_unpack_add_rows(const int32_t *d_indptr, double *d_vals, const int32_t *
 int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const int32_t *d_node_dest, int64_t n_cells,
                      nfa_bplan **out, nfa_stream stream);
 void nfa_bplan_destroy(nfa_bplan *bp);
+/* Right-hand side of the fused form by ROW OWNER: row n_comp N + c = sum over the (cell, local node) pairs that are node N,
+ * in ascending cell order, of d_re[(cell n_phi + a) comp_pitch + c] -- res_g[dest] += r_el of
+ * R/src/assembly/ScatterFormData.py:14-18 without the per-row entry lists of nfa_plan_reduce (one 32-bit entry per node
+ * and cell instead of one per row and cell; comp_pitch = 4 with three components: one 32-byte sector per entry).
+ * overwrite != 0: the sums replace the rows (rows of nodes without cells become 0), else they are added. */
+int nfa_bplan_gather_load(const nfa_bplan *bp, const double *d_re, int comp_pitch, int overwrite, double *d_rhs,
+                          nfa_stream stream);
+/* Load vector AND its scatter in two kernels, without the local load vectors in HBM ("tile-merged"): tiles of 64
+ * consecutive cells compute their local load vectors into shared memory (d_f [n_cells, n_q, n_comp] streamed by bulk
+ * copies, like nfa_local_h1_load), sum them per node of the tile (ascending cell) and write one record per (tile, node)
+ * pair -- about 3 per cell instead of n_phi; the second kernel adds a node's pair sums in ascending tile order into rows
+ * n_comp N + c of d_rhs.  Same terms as res_g[dest] += r_el (R/src/assembly/ScatterFormData.py:14-18), associated tile by
+ * tile.  Vector P2 / P1 on tetrahedra, vector P2 on triangles; n_q <= 64.  overwrite as in nfa_bplan_gather_load. */
+int nfa_bplan_load_rhs(const nfa_bplan *bp, int dim, int n_q, const double *d_tab0, const double *d_weights,
+                       const double *d_coords, const int32_t *d_cell_nodes, const double *d_f, double sign, int overwrite,
+                       double *d_rhs, nfa_stream stream);
 int64_t nfa_bplan_nnz(const nfa_bplan *bp);
 int64_t nfa_bplan_bytes(const nfa_bplan *bp);
 /* Mref [n_phi, n_phi, dim, dim] = int_ref d_k phi_a d_l phi_b (exact reference stiffness tensor).
@@ -300,6 +311,11 @@ int nfa_bplan_set_p2_items(nfa_bplan *bp, int64_t n_chunks, const int32_t *d_chu
 int nfa_p2_lane_order(int64_t n_groups, const int64_t *d_group_ptr, const int32_t *d_hdr6, int window, int64_t *d_perm,
                       nfa_stream stream);
 int nfa_bplan_has_p2_items(const nfa_bplan *bp);
+/* Work-balanced chunk ranges: CTA b of a grid of n_cta CTAs (one per SM) walks chunks d_cta_ptr[b] .. d_cta_ptr[b+1]
+ * (int32 [n_cta + 1], non-decreasing, from 0 to n_chunks) instead of an equal COUNT of chunks -- chunks hold equal
+ * numbers of CSR blocks, but rows on the domain boundary have fewer cells to walk.  Used when the launch has exactly
+ * n_cta CTAs; n_cta = 0 removes the split. */
+int nfa_bplan_set_p2_split(nfa_bplan *bp, int n_cta, const int32_t *d_cta_ptr, nfa_stream stream);
 /* Optional cell mask of the row-item kernel (uint8 per cell of the plan, device pointer; NULL clears it): cells with
  * mask 0 contribute exact zeros.  The sharded assembler switches off the halo cells of a rank's local plan this way,
  * so that mesh-constant lambda, mu stay single numbers (stride 0) on every rank. */
@@ -307,9 +323,6 @@ int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *d_mask, nfa_stream str
 int nfa_assemble_p2tet_elasticity(const nfa_bplan *bp, const double *d_coords, const int32_t *d_cell_nodes,
                                   const double *d_lambda, int64_t lambda_stride, const double *d_mu,
                                   int64_t mu_stride, double *d_vals, nfa_stream stream);
-/* Threads per CTA of the row-item kernel for the following calls (384, 448, 480, 512, 640; 0 = default 512).  448 leaves
- * room on every SM for the background load kernel nfa_local_h1_load_bg. */
-void nfa_p2tet_set_threads(int threads);
 /* Matrix AND load vector in the same pass: the items that own a node's diagonal block walk exactly the cells the node's
  * right-hand-side rows need, so they also sum the cells' local load vectors d_re4 [n_cells, 10, 4] (from
  * nfa_local_h1_load_pitched, comp_pitch = 4) in ascending cell order -- the order of res_g[dest] += r_el,

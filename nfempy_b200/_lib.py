@@ -28,7 +28,6 @@ SIGNATURES = {
     ),
     "nfa_local_h1_laplace": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nfa_local_h1_load": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _d, _vp, _vp]),
-    "nfa_local_h1_load_bg": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _d, _vp, _vp]),
     "nfa_local_h1_load_pitched": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _d, _vp, _i, _vp]),
     "nfa_local_h1_facet": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _d, _d, _i, _vp, _vp, _vp]),
     "nfa_local_hdiv_l2": (
@@ -67,6 +66,8 @@ SIGNATURES = {
     "nfa_p2p_timeouts": (_i64, []),
     "nfa_push_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_pull_add_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
+    "nfa_bplan_gather_load": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "nfa_bplan_load_rhs": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp]),
     "nfa_bplan_create": (_i, [_i64, _i, _i, _vp, _i64, ctypes.POINTER(_vp), _vp]),
     "nfa_bplan_destroy": (None, [_vp]),
     "nfa_bplan_nnz": (_i64, [_vp]),
@@ -86,9 +87,9 @@ SIGNATURES = {
     "nfa_bplan_set_p2_items": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _vp]),
     "nfa_p2_lane_order": (_i, [_i64, _vp, _vp, _i, _vp, _vp]),
     "nfa_bplan_has_p2_items": (_i, [_vp]),
+    "nfa_bplan_set_p2_split": (_i, [_vp, _i, _vp, _vp]),
     "nfa_bplan_set_cell_mask": (_i, [_vp, _vp, _vp]),
     "nfa_assemble_p2tet_elasticity": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
-    "nfa_p2tet_set_threads": (None, [_i]),
     "nfa_assemble_p2tet_elasticity_load": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _vp]),
 }
 

@@ -74,6 +74,7 @@ class _Plan:
         self.pattern = None  # nfa_plan* adopting the block plan's pattern (fused mode)
         self.bplan = None
         self.fused_index = None
+        self.rhs_gather = False  # the fused segment's right-hand side is summed by nfa_bplan_gather_load
         self.n_dof = 0
         self.nnz = 0
         self.indptr = None
@@ -246,7 +247,11 @@ class GPUAssembler:
             ph = ctypes.c_void_p()
             _lib.check(lib.nfa_plan_from_bplan(bh, ctypes.byref(ph), stream), "nfa_plan_from_bplan")
             p.pattern = ph
-            flags = (ctypes.c_int32 * nseg)(*[0 if i == fused_index else 1 for i in range(nseg)])
+            # the fused segment carries no local matrices; when it is the first of the list (its rows then come first in the
+            # reference's call order) its right-hand side is summed by row owner (nfa_bplan_gather_load) and its rows stay out
+            # of the plan's generic row lists (flag bit 1)
+            p.rhs_gather = fused_index == 0 and os.environ.get("NFA_RHS_GATHER", "1") != "0"
+            flags = (ctypes.c_int32 * nseg)(*[(2 if p.rhs_gather else 0) if i == fused_index else 1 for i in range(nseg)])
             _lib.check(
                 lib.nfa_plan_create(p.n_dof, nseg, dest_ptrs, n_items, n_loc, flags, ph, ctypes.byref(handle), stream),
                 "nfa_plan_create",
@@ -300,6 +305,11 @@ class GPUAssembler:
             "nfa_bplan_set_p2_items",
         )
         p.p2_stats = {k: v for k, v in items.items() if isinstance(v, int)}
+        if os.environ.get("NFA_P2TET_BALANCE", "1") != "0":  # one CTA per SM: work-balanced chunk ranges
+            n_cta = int(torch.cuda.get_device_properties(dev.device).multi_processor_count)
+            if items["n_chunks"] >= n_cta:
+                split = p2_items.balanced_split(items, n_cta)
+                _lib.check(lib.nfa_bplan_set_p2_split(p.bplan, n_cta, _lib.ptr(split), stream), "nfa_bplan_set_p2_split")
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
@@ -458,19 +468,21 @@ class GPUAssembler:
             if jac.plan_key is not None and not jac.is_zero:
                 raise _lib.NfaError("GPUAssembler: the jacobian holds values assembled on a different sparsity plan")
             jac.bind_pattern(key, plan.n_dof, plan.indptr, plan.indices)
-        # the row-item kernel can write the load vector itself (its vertex / edge diagonal items walk the cells a row
-        # needs): rows are then OVERWRITTEN when the buffer is fresh and every node of the plan has cells -- no fill
-        fold = self._folds_load(lib, plan, entries, datas)
-        overwrite = fold and (fresh or rhs_dev is None) and bool(plan.p2_stats.get("all_rows_nonempty"))
-        self.last_rhs_fill = not overwrite and (fresh or rhs_dev is None)  # a torch fill kernel ran (launch accounting)
+        # Right-hand side of the fused form: summed by ROW OWNER from the cells' local load vectors
+        # (nfa_bplan_gather_load, plan built with the segment's rows left out of the generic lists); the sums OVERWRITE the
+        # rows of a fresh buffer -- no fill.  NFA_P2TET_RHS=1: the row-item matrix kernel gathers them itself (measured slower)
+        gather = bool(getattr(plan, "rhs_gather", False))
+        fold = gather and self._folds_load(lib, plan, entries, datas)
+        fresh = fresh or rhs_dev is None
+        has_load = gather and datas[plan.fused_index].f is not None
+        overwrite = fresh and has_load and (not fold or bool(plan.p2_stats.get("all_rows_nonempty")))
+        self.last_rhs_fill = fresh and not overwrite  # a torch fill kernel ran (launch accounting)
         if rhs_dev is None:
             rhs_dev = (torch.empty if overwrite else torch.zeros)(plan.n_dof, dtype=torch.float64, device=dev.device)
         elif fresh and not overwrite:
             rhs_dev.zero_()
         nseg = len(entries)
         Ke_list, re_list, keep = [None] * nseg, [None] * nseg, []
-        overlap = self._overlaps_load(lib, plan, entries, datas, fold)
-        side, rhs_on_side = None, False
         for i, ((_, kind, _, form, alpha), data, dest) in enumerate(zip(entries, datas, dests)):
             if "time_dependent" in kind:
                 first_dev, second_dev = data.alpha_dev
@@ -488,7 +500,8 @@ class GPUAssembler:
                 spec = form.fused_spec(data)
                 target = jac.values_dev if jac.is_zero else torch.empty_like(jac.values_dev)
                 kernel = spec["kernel"]
-                if spec.get("p2tet_kernel") and lib.nfa_bplan_has_p2_items(plan.bplan):
+                p2tet = bool(spec.get("p2tet_kernel") and lib.nfa_bplan_has_p2_items(plan.bplan))
+                if p2tet:
                     kernel = spec["p2tet_kernel"]
                     args = [plan.bplan, _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes)]
                 else:
@@ -496,41 +509,35 @@ class GPUAssembler:
                 for c in spec["coefs"]:
                     args += [_lib.ptr(c[0]), c[1]]
                 args += [_lib.ptr(target)]
-                if fold:
-                    # padded local load vectors [n, 10, 4] first, then matrix + right-hand side in one pass
-                    re4 = torch.empty((data.n_items, 10, 4), dtype=torch.float64, device=dev.device)
-                    form.launch_load(data.dev, data, re4, comp_pitch=4)
-                    keep.append(re4)
-                    kernel += "_load"
-                    args += [_lib.ptr(re4), _lib.ptr(rhs_dev), 1 if overwrite else 0]
-                args += [stream]
-                fork_event = None
-                if overlap:
-                    # fork: the side stream computes the local load vectors (and, when this form is the whole list, sums
-                    # them into the right-hand side) while the matrix kernel runs on the main stream.  The matrix kernel is
-                    # launched FIRST: its CTAs take the SMs, the small background CTAs then fill the room left beside them
-                    main = torch.cuda.current_stream(dev.device)
-                    fork_event = torch.cuda.Event()
-                    fork_event.record(main)
-                    lib.nfa_p2tet_set_threads(int(os.environ.get("NFA_P2TET_OVERLAP_THREADS", "448")))
-                try:
-                    _lib.check(getattr(lib, kernel)(*args), kernel)
-                finally:
-                    if overlap:
-                        lib.nfa_p2tet_set_threads(0)
-                if overlap:
-                    side = self._side_stream(dev)
-                    side.wait_event(fork_event)
-                    re = torch.empty((data.n_items, form.n_loc()), dtype=torch.float64, device=dev.device)
-                    re_list[i] = re
+                # right-hand side of the form's load: tile-merged (local load vectors never reach HBM) where the streaming
+                # load kernel exists, else local load vectors [n, n_loc] + the row-owner gather (or the plan's generic lists)
+                re = None
+                merged = (gather and not fold and data.f is not None and data.n_q <= 64
+                          and (data.dim, data.n_phi, data.n_comp) in ((3, 10, 3), (3, 4, 3), (2, 6, 2))
+                          and os.environ.get("NFA_LOAD_MERGE", "1") != "0")
+                if data.f is not None and not merged:
+                    if fold:  # padded node records [n, 10, 4]: one 32-byte sector per cell and node
+                        re = torch.empty((data.n_items, 10, 4), dtype=torch.float64, device=dev.device)
+                        form.launch_load(data.dev, data, re, comp_pitch=4)
+                    else:
+                        re = torch.empty((data.n_items, form.n_loc()), dtype=torch.float64, device=dev.device)
+                        form.launch_load(data.dev, data, re)
                     keep.append(re)
-                    with torch.cuda.stream(side):
-                        form.launch_load(data.dev, data, re, background=True)
-                        if nseg == 1 and alpha_dev is None:
-                            re_ptrs = (ctypes.c_void_p * 1)(re.data_ptr())
-                            _lib.check(lib.nfa_plan_reduce(plan.plan, None, re_ptrs, 1, None, 1, _lib.ptr(rhs_dev),
-                                                           _lib.stream_ptr()), "nfa_plan_reduce")
-                            rhs_on_side = True
+                if fold:
+                    kernel += "_load"
+                    args += [_lib.ptr(re), _lib.ptr(rhs_dev), 1 if overwrite else 0]
+                args += [stream]
+                _lib.check(getattr(lib, kernel)(*args), kernel)
+                if merged:
+                    _lib.check(lib.nfa_bplan_load_rhs(plan.bplan, data.dim, data.n_q, _lib.ptr(data.tab[0]), _lib.ptr(data.w),
+                                                      _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes), _lib.ptr(data.f),
+                                                      float(form.load_sign), 1 if overwrite else 0, _lib.ptr(rhs_dev), stream),
+                               "nfa_bplan_load_rhs")
+                elif re is not None and gather and not fold:
+                    _lib.check(lib.nfa_bplan_gather_load(plan.bplan, _lib.ptr(re), data.n_comp, 1 if overwrite else 0,
+                                                         _lib.ptr(rhs_dev), stream), "nfa_bplan_gather_load")
+                elif re is not None and not gather:
+                    re_list[i] = re
                 if alpha_dev is not None:
                     _lib.check(
                         lib.nfa_csr_spmv(plan.pattern, _lib.ptr(target), _lib.ptr(alpha_dev), 1, _lib.ptr(rhs_dev), stream),
@@ -539,24 +546,16 @@ class GPUAssembler:
                 if target is not jac.values_dev:
                     jac.values_dev.add_(target)
                 jac.is_zero = False
-                if data.f is not None and not fold and not overlap:
-                    re = torch.empty((data.n_items, form.n_loc()), dtype=torch.float64, device=dev.device)
-                    form.launch_load(data.dev, data, re)
-                    re_list[i] = re
-                    keep.append(re)
             else:
                 Ke, re = form.local_blocks(data.dev, data, alpha_dev, dest if alpha_dev is not None else None)
                 Ke_list[i], re_list[i] = Ke, re
                 keep += [Ke, re, alpha_dev]
-        if side is not None:
-            torch.cuda.current_stream(dev.device).wait_stream(side)  # join
         ke_ptrs = (ctypes.c_void_p * nseg)(*[None if k is None else k.data_ptr() for k in Ke_list])
-        re_ptrs = (ctypes.c_void_p * nseg)(*[None if (r is None or rhs_on_side) else r.data_ptr() for r in re_list])
+        re_ptrs = (ctypes.c_void_p * nseg)(*[None if r is None else r.data_ptr() for r in re_list])
         accumulate_vals = 0 if (jac.is_zero and plan.fused_index is None) else 1
-        if not (rhs_on_side and all(k is None for k in Ke_list)):
+        if any(k is not None for k in Ke_list) or any(r is not None for r in re_list):
             _lib.check(
-                lib.nfa_plan_reduce(plan.plan, ke_ptrs, None if rhs_on_side else re_ptrs, accumulate_vals,
-                                    _lib.ptr(jac.values_dev), 1, _lib.ptr(rhs_dev), stream),
+                lib.nfa_plan_reduce(plan.plan, ke_ptrs, re_ptrs, accumulate_vals, _lib.ptr(jac.values_dev), 1, _lib.ptr(rhs_dev), stream),
                 "nfa_plan_reduce",
             )
         jac.is_zero = False
@@ -568,35 +567,14 @@ class GPUAssembler:
         """True when the fused form runs on the row-item kernel and has a load: the kernel then also writes the form's
         right-hand side (``nfa_assemble_p2tet_elasticity_load``; ``NFA_P2TET_RHS=0`` keeps the separate gather)."""
         i = plan.fused_index
-        # measured: the gather inside the matrix kernel costs more (0.77 -> 0.98 ms) than the separate reduce it replaces
-        # (0.14 ms), so it is opt-in; the default overlaps the load / reduce branch with the matrix kernel instead
+        # measured: the gather inside the matrix kernel costs more (0.77 -> 0.98 ms) than the separate pass it replaces, so it
+        # is opt-in (profiles/r02_p2tet_variants.md, batch 9)
         if i is None or os.environ.get("NFA_P2TET_RHS", "0") == "0" or not getattr(plan, "p2_stats", None):
             return False
         form, data = entries[i][3], datas[i]
         spec = form.fused_spec(data)
         return bool(spec and spec.get("p2tet_kernel") and data.f is not None and lib.nfa_bplan_has_p2_items(plan.bplan)
                     and hasattr(lib, spec["p2tet_kernel"] + "_load"))
-
-    @staticmethod
-    def _overlaps_load(lib, plan, entries, datas, fold):
-        """True when the load vector of the fused form is computed on a SIDE stream while the row-item matrix kernel runs:
-        the matrix kernel is latency-bound and leaves a third of the DRAM bandwidth idle, the load kernel is a pure stream.
-        The matrix kernel then runs 448 threads per SM instead of 512, which leaves the registers and the 32 KB of shared
-        memory ``nfa_local_h1_load_bg`` (one small persistent CTA per SM) needs beside it.  ``NFA_P2TET_OVERLAP=0`` keeps
-        the single-stream chain."""
-        i = plan.fused_index
-        if i is None or fold or os.environ.get("NFA_P2TET_OVERLAP", "0") == "0" or not getattr(plan, "p2_stats", None):
-            return False
-        form, data = entries[i][3], datas[i]
-        spec = form.fused_spec(data)
-        return bool(spec and spec.get("p2tet_kernel") and data.f is not None and data.n_q <= 27
-                    and lib.nfa_bplan_has_p2_items(plan.bplan))
-
-    def _side_stream(self, dev):
-        side = getattr(self, "_side", None)
-        if side is None or side.device != dev.device:
-            side = self._side = torch.cuda.Stream(device=dev.device)
-        return side
 
     def capture(self, state, rhs_dev):
         """CUDA graph of one fresh assembly (``rhs_dev`` zeroed, every CSR value overwritten) on the buffers of ``state``:

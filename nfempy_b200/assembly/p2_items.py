@@ -387,6 +387,22 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     }
 
 
+def balanced_split(plan, n_cta, task_cost=3):
+    """Chunk range of each of ``n_cta`` CTAs, ``int32 [n_cta + 1]``: equal WORK instead of equal chunk counts.  A chunk costs
+    ``sum over its tasks of (task_cost + kmax)`` -- a fixed part per task (headers, tile hand-over) plus one memory round per
+    ELL row; chunks hold equal numbers of CSR blocks, but the rows next to the domain boundary have fewer cells to walk."""
+    ch, th = plan["chunk_hdr"].to(torch.int64), plan["task_hdr"].to(torch.int64)
+    w = task_cost + ((th[:, 0] >> 8) & 0xFF)
+    cs = torch.cat([torch.zeros(1, dtype=torch.int64, device=w.device), torch.cumsum(w, 0)])
+    cw = cs[ch[:, 2] + ch[:, 3]] - cs[ch[:, 2]]
+    ccs = torch.cat([torch.zeros(1, dtype=torch.int64, device=w.device), torch.cumsum(cw, 0)])
+    target = (ccs[-1].double() * torch.arange(n_cta + 1, device=w.device, dtype=torch.float64) / n_cta)
+    split = torch.searchsorted(ccs.double(), target, right=False)
+    split[0], split[-1] = 0, int(ch.shape[0])
+    split = torch.cummax(split, 0).values  # non-decreasing whatever the rounding did
+    return split.to(torch.int32).contiguous()
+
+
 # ---- reference walk of the plan (numpy): what the kernel does, used by the CPU tests ---------------------------
 def geometry_records(coords, cell_nodes, lam, mu):
     """``[n_cells, 4, 4]``: (sqrt(det mu) g_m, lambda / mu) for the four vertices of every cell."""

@@ -5,7 +5,7 @@
 #include <utility>
 #include <vector>
 
-#include "nfa_common.cuh"
+#include "nfa_plan.cuh"
 
 namespace nfa {
 static std::mutex g_err_mutex;
@@ -432,15 +432,30 @@ __global__ void __launch_bounds__(1024, 1)
 // bulk asynchronous copies (cp.async.bulk global -> shared, mbarrier completion), double buffered.  HBM-bound on f.
 __constant__ double c_load_wt[64 * 20];
 
-template <int DIM, int N_PHI, int N_COMP, int TILE>
+// MERGE (nfa_bplan_load_rhs): the tile's local load vectors stay in shared memory and are summed per NODE of the tile
+// (the plan's (tile, node) pairs, entries in ascending cell order); only the pair sums [n_pairs][N_COMP] go to HBM --
+// about 3.2 node records per cell instead of 10 -- and a second kernel adds a node's pair sums in ascending tile order.
+struct LoadMerge {
+    const int32_t *tile_ptr;   // [n_tiles + 1]
+    const uint32_t *pair_ptr;  // [n_pairs + 1]
+    const uint16_t *tile_ent;  // [n_cells * N_PHI]
+    double *pair_sum;          // [n_pairs][N_COMP]
+};
+
+template <int DIM, int N_PHI, int N_COMP, int TILE, bool MERGE>
 __global__ void __launch_bounds__(TILE *N_COMP)
     local_h1_load_stream_kernel(int n_q, const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
                                 int64_t n_cells, const double *__restrict__ f, double sign, double *__restrict__ re,
-                                int comp_pitch) {
-    extern __shared__ __align__(128) double smem[];  // two tiles [TILE][n_q][N_COMP], then two mbarriers
+                                int comp_pitch, LoadMerge mg) {
+    extern __shared__ __align__(128) double smem[];  // two tiles [TILE][n_q][N_COMP], two mbarriers, (MERGE) re tile + lists
+    constexpr int NT = TILE * N_COMP;
     const int fn = n_q * N_COMP;
     const int tile_doubles = TILE * fn;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * (size_t)tile_doubles);
+    double *re_tile = smem + 2 * (size_t)tile_doubles + 2;  // MERGE: [TILE][N_PHI][N_COMP]
+    // MERGE: the tile's lists -- pair offsets relative to the tile's first entry, then the entries' local ids (two a word)
+    uint16_t *s_ptr = reinterpret_cast<uint16_t *>(re_tile + TILE * N_PHI * N_COMP);  // [TILE * N_PHI + 2]
+    uint32_t *s_ent = reinterpret_cast<uint32_t *>(s_ptr + TILE * N_PHI + 2);          // [TILE * N_PHI / 2]
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bar);
     const int lc = threadIdx.x / N_COMP, comp = threadIdx.x - lc * N_COMP;
     const int64_t n_tiles = (n_cells + TILE - 1) / TILE;
@@ -467,16 +482,60 @@ __global__ void __launch_bounds__(TILE *N_COMP)
     if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
     int buf = 0;
     uint32_t phases = 0u;  // bit b = parity the next wait on tile b expects
+    int np0 = 0, np1 = 0;  // MERGE: pair range of the tile about to be processed (loaded one iteration ahead)
+    if constexpr (MERGE) {
+        if ((int64_t)blockIdx.x < n_tiles) {
+            np0 = __ldg(mg.tile_ptr + blockIdx.x);
+            np1 = __ldg(mg.tile_ptr + blockIdx.x + 1);
+        }
+    }
     for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, buf ^= 1) {
         const int64_t next = tl + gridDim.x;
         if (threadIdx.x == 0 && next < n_tiles) issue(next, buf ^ 1);  // the other tile was released by the barrier below
         const int64_t c0 = tl * TILE;
         const int nc_here = (int)((n_cells - c0) < TILE ? (n_cells - c0) : TILE);
+        // MERGE: the tile's lists go to registers first (their loads overlap the coordinate loads below) and to shared
+        // memory once the determinant is done
+        constexpr int NP_IT = MERGE ? (TILE * N_PHI + 1 + NT - 1) / NT : 1, NE_IT = MERGE ? (TILE * N_PHI / 2 + NT - 1) / NT : 1;
+        uint32_t lp[NP_IT], le[NE_IT];
+        int n_pairs_here = 0, p0 = 0;
+        if constexpr (MERGE) {
+            p0 = np0;
+            n_pairs_here = np1 - np0;
+            if (next < n_tiles) {
+                np0 = __ldg(mg.tile_ptr + next);
+                np1 = __ldg(mg.tile_ptr + next + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < NP_IT; ++j) {
+                const int i = threadIdx.x + j * NT;
+                lp[j] = (i <= n_pairs_here) ? __ldg(mg.pair_ptr + p0 + i) : 0u;
+            }
+            const uint32_t *ent32 = reinterpret_cast<const uint32_t *>(mg.tile_ent + (size_t)c0 * N_PHI);  // even offset
+#pragma unroll
+            for (int j = 0; j < NE_IT; ++j) {
+                const int i = threadIdx.x + j * NT;
+                le[j] = (i < (nc_here * N_PHI) / 2) ? __ldg(ent32 + i) : 0u;
+            }
+        }
         double det = 0.0;
         if (lc < nc_here) {
             double X[DIM + 1][3];
             load_cell_coords<DIM>(coords, cell_nodes, c0 + lc, X);
             det = compute_det<DIM>(X);
+        }
+        if constexpr (MERGE) {
+            const uint32_t e_base = (uint32_t)(c0 * N_PHI);
+#pragma unroll
+            for (int j = 0; j < NP_IT; ++j) {
+                const int i = threadIdx.x + j * NT;
+                if (i <= n_pairs_here) s_ptr[i] = (uint16_t)(lp[j] - e_base);
+            }
+#pragma unroll
+            for (int j = 0; j < NE_IT; ++j) {
+                const int i = threadIdx.x + j * NT;
+                if (i < (nc_here * N_PHI) / 2) s_ent[i] = le[j];
+            }
         }
         {  // wait for this tile's bytes
             uint32_t done = 0;
@@ -500,10 +559,34 @@ __global__ void __launch_bounds__(TILE *N_COMP)
 #pragma unroll
                 for (int a = 0; a < N_PHI; ++a) acc[a] = fma(c_load_wt[q * N_PHI + a], v, acc[a]);
             }
-            double *dst = re + (c0 + lc) * (N_PHI * comp_pitch) + comp;  // comp_pitch > N_COMP: padded node records
             const double sc = sign * det;
+            if constexpr (MERGE) {
+                double *dst = re_tile + lc * (N_PHI * N_COMP) + comp;
 #pragma unroll
-            for (int a = 0; a < N_PHI; ++a) dst[a * comp_pitch] = sc * acc[a];
+                for (int a = 0; a < N_PHI; ++a) dst[a * N_COMP] = sc * acc[a];
+            } else {
+                double *dst = re + (c0 + lc) * (N_PHI * comp_pitch) + comp;  // comp_pitch > N_COMP: padded node records
+#pragma unroll
+                for (int a = 0; a < N_PHI; ++a) dst[a * comp_pitch] = sc * acc[a];
+            }
+        }
+        if constexpr (MERGE) {
+            __syncthreads();  // the tile's local load vectors and lists are complete
+            const uint16_t *ent = reinterpret_cast<const uint16_t *>(s_ent);
+            for (int w = threadIdx.x; w < n_pairs_here * N_COMP; w += NT) {
+                const int k = w / N_COMP, c = w - k * N_COMP;
+                const int e0 = s_ptr[k], e1 = s_ptr[k + 1];
+                double sum = 0.0;
+                for (int e = e0; e < e1; e += 4) {  // four independent loads in flight, added in ascending cell order
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = (e + u < e1) ? re_tile[(int)ent[e + u] * N_COMP + c] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (e + u < e1) sum += v[u];
+                }
+                mg.pair_sum[(size_t)(p0 + k) * N_COMP + c] = sum;
+            }
         }
         __syncthreads();  // every reader of this tile is done: it may be refilled on the next trip
     }
@@ -515,34 +598,77 @@ __global__ void load_wt_kernel(int n, int n_phi, const double *__restrict__ tab0
     if (i < n) out[i] = weights[i / n_phi] * tab0[i];
 }
 
-// TILE = 64: the stand-alone kernel (two 41 KB tiles, as many CTAs per SM as fit).  TILE = 24 with one CTA per SM is the
-// BACKGROUND form (nfa_local_h1_load_bg): 31 KB of shared memory and three warps, small enough to stay resident beside
-// the row-item matrix kernel of csrc/nfa_p2tet.cu (197 KB, 448 threads x 128 registers) and stream the load array with the
-// DRAM bandwidth that kernel leaves idle.
-template <int DIM, int N_PHI, int N_COMP, int TILE = 64>
+template <int DIM, int N_PHI, int N_COMP, int TILE = 64, bool MERGE = false>
 static int launch_h1_load_stream(int n_q, const double *tab0, const double *weights, const double *coords,
                                  const int32_t *cell_nodes, int64_t n_cells, const double *f, double sign, double *re,
-                                 cudaStream_t s, int comp_pitch = N_COMP, int max_per_sm = 0) {
+                                 cudaStream_t s, int comp_pitch = N_COMP, LoadMerge mg = LoadMerge{}) {
     double *wt = nullptr;
     NFA_CUDA(cudaGetSymbolAddress((void **)&wt, c_load_wt));
     load_wt_kernel<<<grid_for(n_q * N_PHI, 128), 128, 0, s>>>(n_q * N_PHI, N_PHI, tab0, weights, wt);
     NFA_LAUNCH_CHECK();
-    const size_t smem = sizeof(double) * 2 * (size_t)TILE * n_q * N_COMP + 16;
-    auto kern = local_h1_load_stream_kernel<DIM, N_PHI, N_COMP, TILE>;
+    const size_t smem = sizeof(double) * 2 * (size_t)TILE * n_q * N_COMP + 16 +
+                        (MERGE ? sizeof(double) * (size_t)TILE * N_PHI * N_COMP + 2 * (TILE * N_PHI + 2) + 2 * TILE * N_PHI + 16 : 0);
+    auto kern = local_h1_load_stream_kernel<DIM, N_PHI, N_COMP, TILE, MERGE>;
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // background form: ask for the largest shared-memory carve-out, the one the matrix kernel beside it runs with -- an SM
-    // cannot change its carve-out while a CTA is resident, so with the default (smallest sufficient) carve-out whichever
-    // kernel arrives second would wait for the first to drain
-    if (max_per_sm > 0) NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     int per_sm = 1, device = 0, n_sm = 148;
     NFA_CUDA(cudaGetDevice(&device));
     NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE * N_COMP, smem));
     if (per_sm < 1) return fail("nfa_local_h1_load: streaming kernel does not fit on an SM");
-    if (max_per_sm > 0) per_sm = std::min(per_sm, max_per_sm);
     const int64_t tiles = (n_cells + TILE - 1) / TILE;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)n_sm * per_sm);
-    kern<<<grid, TILE * N_COMP, smem, s>>>(n_q, coords, cell_nodes, n_cells, f, sign, re, comp_pitch);
+    kern<<<grid, TILE * N_COMP, smem, s>>>(n_q, coords, cell_nodes, n_cells, f, sign, re, comp_pitch, mg);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+// second pass of the tile-merged load: row N_COMP N + c = sum of node N's pair sums in ascending tile order
+template <int NC>
+__global__ void __launch_bounds__(256)
+    pair_gather_kernel(int64_t n_nodes, const int32_t *__restrict__ node_pair_ptr, const uint32_t *__restrict__ node_pair,
+                       const double *__restrict__ pair_sum, int overwrite, double *__restrict__ rhs) {
+    const int64_t N = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (N >= n_nodes) return;
+    const int32_t b = node_pair_ptr[N], e = node_pair_ptr[N + 1];
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    for (int32_t k = b; k < e; ++k) {
+        const double *p = pair_sum + (size_t)__ldg(node_pair + k) * NC;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] += __ldg(p + c);
+    }
+    double *out = rhs + (size_t)N * NC;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) out[c] = overwrite ? acc[c] : out[c] + acc[c];
+}
+
+extern "C" int nfa_bplan_load_rhs(const nfa_bplan *bp, int dim, int n_q, const double *tab0, const double *weights,
+                                  const double *coords, const int32_t *cell_nodes, const double *f, double sign,
+                                  int overwrite, double *rhs, nfa_stream stream) {
+    if (!bp || !tab0 || !weights || !coords || !cell_nodes || !f || !rhs) return fail("nfa_bplan_load_rhs: NULL argument");
+    if (n_q < 1 || n_q > 64) return fail("nfa_bplan_load_rhs: 1 to 64 quadrature points");
+    cudaStream_t s = (cudaStream_t)stream;
+    static_assert(nfa_bplan::LOAD_TILE == 64, "the streaming load kernel runs tiles of 64 cells");
+    const LoadMerge mg = {(const int32_t *)bp->tile_ptr.p, (const uint32_t *)bp->pair_ptr.p, (const uint16_t *)bp->tile_ent.p,
+                          (double *)bp->pair_sum.p};
+    int rc;
+    if (dim == 3 && bp->n_phi == 10 && bp->n_comp == 3)
+        rc = launch_h1_load_stream<3, 10, 3, 64, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 3, mg);
+    else if (dim == 3 && bp->n_phi == 4 && bp->n_comp == 3)
+        rc = launch_h1_load_stream<3, 4, 3, 64, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 3, mg);
+    else if (dim == 2 && bp->n_phi == 6 && bp->n_comp == 2)
+        rc = launch_h1_load_stream<2, 6, 2, 64, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 2, mg);
+    else
+        return fail("nfa_bplan_load_rhs: vector P2 / P1 on tetrahedra and vector P2 on triangles only");
+    if (rc) return rc;
+    const unsigned grid = (unsigned)grid_for(bp->n_nodes, 256);
+    const int32_t *npp = (const int32_t *)bp->node_pair_ptr.p;
+    const uint32_t *np = (const uint32_t *)bp->node_pair.p;
+    if (bp->n_comp == 3)
+        pair_gather_kernel<3><<<grid, 256, 0, s>>>(bp->n_nodes, npp, np, (const double *)bp->pair_sum.p, overwrite, rhs);
+    else
+        pair_gather_kernel<2><<<grid, 256, 0, s>>>(bp->n_nodes, npp, np, (const double *)bp->pair_sum.p, overwrite, rhs);
     NFA_LAUNCH_CHECK();
     return 0;
 }
@@ -575,17 +701,6 @@ extern "C" int nfa_local_h1_load_pitched(int dim, int n_phi, int n_q, int n_comp
         return fail("nfa_local_h1_load_pitched: vector P2 on tetrahedra with at most 64 quadrature points only");
     return launch_h1_load_stream<3, 10, 3>(n_q, tab0, weights, coords, cell_nodes, n_cells, f, sign, re,
                                            (cudaStream_t)stream, comp_pitch);
-}
-
-extern "C" int nfa_local_h1_load_bg(int dim, int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,
-                                    const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *f,
-                                    double sign, double *re, nfa_stream stream) {
-    if (n_cells == 0) return 0;
-    if (!f) return fail("nfa_local_h1_load_bg: the load array is NULL");
-    if (!(dim == 3 && n_phi == 10 && n_comp == 3 && n_q <= 27))
-        return fail("nfa_local_h1_load_bg: vector P2 on tetrahedra with at most 27 quadrature points only");
-    return launch_h1_load_stream<3, 10, 3, 24>(n_q, tab0, weights, coords, cell_nodes, n_cells, f, sign, re,
-                                               (cudaStream_t)stream, 3, 1);
 }
 
 extern "C" int nfa_local_h1_load(int dim, int n_phi, int n_q, int n_comp, const double *tab0, const double *weights,

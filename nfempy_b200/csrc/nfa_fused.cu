@@ -97,6 +97,121 @@ __global__ void unpack_chunk_sorted(const uint64_t *__restrict__ keys, const uin
     gather_pos[cs + slots[k]] = (uint16_t)(k - cs);
 }
 
+// node incidence lists: key = node of (cell, a), id = cell * n_phi + a (ascending id = ascending cell)
+__global__ void fill_node_keys(const int32_t *__restrict__ node_dest, int64_t n, uint32_t *__restrict__ keys,
+                               uint32_t *__restrict__ ids) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    keys[e] = (uint32_t)node_dest[e];
+    ids[e] = (uint32_t)e;
+}
+
+// tile-merged load lists: key = tile * n_nodes + node of (cell, a), id = cell * n_phi + a
+__global__ void fill_tile_node_keys(const int32_t *__restrict__ node_dest, int64_t n, int n_phi, int tile_cells,
+                                    int64_t n_nodes, uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int64_t tile = (e / n_phi) / tile_cells;
+    keys[e] = (uint64_t)tile * (uint64_t)n_nodes + (uint64_t)node_dest[e];
+    ids[e] = (uint32_t)e;
+}
+
+__global__ void tile_local_ids(const uint32_t *__restrict__ ids, int64_t n, int n_phi, int tile_cells,
+                               uint16_t *__restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const uint32_t id = ids[e];
+    const uint32_t tile = (id / (uint32_t)n_phi) / (uint32_t)tile_cells;
+    out[e] = (uint16_t)(id - tile * (uint32_t)(tile_cells * n_phi));
+}
+
+// first unique key >= r * stride (r = 0 .. n_rows): pair range of every tile
+__global__ void lower_bound_u64(const uint64_t *__restrict__ ukeys, int64_t n, int64_t n_rows, uint64_t stride,
+                                int32_t *__restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rows) return;
+    const uint64_t target = (uint64_t)r * stride;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (ukeys[mid] < target)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    out[r] = (int32_t)lo;
+}
+
+__global__ void pair_node_keys(const uint64_t *__restrict__ ukeys, int64_t n, int64_t n_nodes, uint32_t *__restrict__ keys,
+                               uint32_t *__restrict__ ids) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    keys[p] = (uint32_t)(ukeys[p] % (uint64_t)n_nodes);
+    ids[p] = (uint32_t)p;
+}
+
+__global__ void node_ptr_kernel(const uint32_t *__restrict__ sorted_keys, int64_t n, int64_t n_nodes,
+                                int32_t *__restrict__ node_ptr) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_nodes) return;
+    int64_t lo = 0, hi = n;  // first entry whose node is >= r
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (sorted_keys[mid] < (uint32_t)r)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    node_ptr[r] = (int32_t)lo;
+}
+
+// Right-hand-side rows of node N = the sum of the local load vectors of the (cell, local node) pairs that are N, in
+// ascending cell order (res_g[dest] += r_el, R/src/assembly/ScatterFormData.py:14-18).  One thread per node: its entries
+// are consecutive in node_ent, every entry is one record re[id * PITCH .. + NC) (PITCH = 4, NC = 3: one 32-byte sector,
+// fetched with a single 256-bit load); the NC rows of a node are adjacent, so a warp's stores are one contiguous run.
+template <int NC, int PITCH>
+__global__ void __launch_bounds__(256)
+    node_gather_kernel(int64_t n_nodes, const int32_t *__restrict__ node_ptr, const uint32_t *__restrict__ node_ent,
+                       const double *__restrict__ re, int overwrite, double *__restrict__ rhs) {
+    const int64_t N = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (N >= n_nodes) return;
+    const int32_t b = node_ptr[N], e = node_ptr[N + 1];
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+    constexpr int U = 4;  // entries in flight
+    for (int32_t k = b; k < e; k += U) {
+        double v[U][NC];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) v[u][c] = 0.0;
+            if (k + u < e) {
+                const double *p = re + (size_t)__ldg(node_ent + k + u) * PITCH;
+                if constexpr (PITCH == 4 && NC == 3) {
+                    double x, y, z, w;
+                    asm("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(p));
+                    v[u][0] = x;
+                    v[u][1] = y;
+                    v[u][2] = z;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) v[u][c] = __ldg(p + c);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)  // absent entries add +0.0: same sums as the entry-by-entry loop
+            if (k + u < e) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) acc[c] += v[u][c];
+            }
+    }
+    double *out = rhs + (size_t)N * NC;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) out[c] = overwrite ? acc[c] : out[c] + acc[c];
+}
+
 __global__ void scalar_pattern(const int32_t *__restrict__ bptr, const int32_t *__restrict__ bcols, int64_t n_nodes,
                                int nc, int32_t *__restrict__ indptr, int32_t *__restrict__ indices) {
     // one thread per (block row, block): writes its nc x nc column indices; first block of a row writes indptr
@@ -122,7 +237,8 @@ extern "C" int64_t nfa_bplan_nnz(const nfa_bplan *bp) { return bp ? bp->n_bnz * 
 extern "C" int64_t nfa_bplan_bytes(const nfa_bplan *bp) {
     if (!bp) return -1;
     return (int64_t)(bp->bptr.n + bp->bcols.n + bp->bseg.n + bp->chunk_row.n + bp->chunk_hdr.n + bp->contrib.n + bp->contrib_slot.n +
-                     bp->indptr.n + bp->indices.n + bp->geo.n);
+                     bp->indptr.n + bp->indices.n + bp->geo.n + bp->node_ptr.n + bp->node_ent.n + bp->tile_ptr.n + bp->pair_ptr.n +
+                     bp->tile_ent.n + bp->node_pair_ptr.n + bp->node_pair.n + bp->pair_sum.n);
 }
 
 extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const int32_t *node_dest, int64_t n_cells,
@@ -282,6 +398,80 @@ extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const in
     unpack_chunk_sorted<<<grid_for(E, 256), 256, 0, s>>>(dk2.Current(), dv2.Current(), E, (uint32_t *)d_cstart.p,
                                                          (uint32_t *)bp->contrib.p, (uint16_t *)bp->contrib_slot.p);
     count_launch();
+    // ---- node incidence lists (stable radix sort of the node ids: entries stay in ascending cell order)
+    {
+        const int64_t M = n_cells * n_phi;
+        DevBuf nk, nk_alt, ni_alt;
+        if (nk.alloc(4 * M) || nk_alt.alloc(4 * M) || ni_alt.alloc(4 * M) || bp->node_ent.alloc(4 * M) ||
+            bp->node_ptr.alloc(4 * (n_nodes + 1)))
+            return bail(2);
+        fill_node_keys<<<grid_for(M, 256), 256, 0, s>>>(node_dest, M, (uint32_t *)nk.p, (uint32_t *)ni_alt.p);
+        int nbits = 1;
+        while (nbits < 32 && (((uint64_t)n_nodes) >> nbits) != 0) ++nbits;
+        size_t tb2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb2, (uint32_t *)nk.p, (uint32_t *)nk_alt.p, (uint32_t *)ni_alt.p,
+                                        (uint32_t *)bp->node_ent.p, (int)M, 0, nbits, s);
+        if (tmp.alloc(tb2)) return bail(2);
+        if (cub::DeviceRadixSort::SortPairs(tmp.p, tb2, (uint32_t *)nk.p, (uint32_t *)nk_alt.p, (uint32_t *)ni_alt.p,
+                                            (uint32_t *)bp->node_ent.p, (int)M, 0, nbits, s) != cudaSuccess)
+            return bail(fail("nfa_bplan_create: node incidence sort failed"));
+        node_ptr_kernel<<<grid_for(n_nodes + 1, 256), 256, 0, s>>>((uint32_t *)nk_alt.p, M, n_nodes, (int32_t *)bp->node_ptr.p);
+        count_launch(6);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return bail(fail("nfa_bplan_create: node incidence lists failed"));
+    }
+    // ---- tile-merged load lists (nfa_bplan_load_rhs)
+    {
+        constexpr int TL = nfa_bplan::LOAD_TILE;
+        const int64_t M = n_cells * n_phi, n_tiles = (n_cells + TL - 1) / TL;
+        DevBuf k64, k64_alt, id_a, id_b, uk, cnt, nr;
+        if (k64.alloc(8 * M) || k64_alt.alloc(8 * M) || id_a.alloc(4 * M) || id_b.alloc(4 * M)) return bail(2);
+        fill_tile_node_keys<<<grid_for(M, 256), 256, 0, s>>>(node_dest, M, n_phi, TL, n_nodes, (uint64_t *)k64.p,
+                                                             (uint32_t *)id_a.p);
+        int kb = 1;
+        while (kb < 64 && (((uint64_t)n_tiles * (uint64_t)n_nodes) >> kb) != 0) ++kb;
+        cub::DoubleBuffer<uint64_t> tk((uint64_t *)k64.p, (uint64_t *)k64_alt.p);
+        cub::DoubleBuffer<uint32_t> tv((uint32_t *)id_a.p, (uint32_t *)id_b.p);
+        size_t tb3 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb3, tk, tv, (int)M, 0, kb, s);
+        if (tmp.alloc(tb3)) return bail(2);
+        if (cub::DeviceRadixSort::SortPairs(tmp.p, tb3, tk, tv, (int)M, 0, kb, s) != cudaSuccess)
+            return bail(fail("nfa_bplan_create: tile / node sort failed"));
+        if (uk.alloc(8 * M) || cnt.alloc(4 * (M + 1)) || nr.alloc(sizeof(int))) return bail(2);
+        cub::DeviceRunLengthEncode::Encode(nullptr, tb3, tk.Current(), (uint64_t *)uk.p, (uint32_t *)cnt.p, (int *)nr.p,
+                                           (int)M, s);
+        if (tmp.alloc(tb3)) return bail(2);
+        cub::DeviceRunLengthEncode::Encode(tmp.p, tb3, tk.Current(), (uint64_t *)uk.p, (uint32_t *)cnt.p, (int *)nr.p,
+                                           (int)M, s);
+        int h_pairs = 0;
+        cudaMemcpyAsync(&h_pairs, nr.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return bail(fail("nfa_bplan_create: tile / node pairs failed"));
+        const int64_t P = h_pairs;
+        bp->n_pairs = P;
+        if (bp->pair_ptr.alloc(4 * (P + 1)) || bp->tile_ent.alloc(2 * M) || bp->tile_ptr.alloc(4 * (n_tiles + 1)) ||
+            bp->node_pair_ptr.alloc(4 * (n_nodes + 1)) || bp->node_pair.alloc(4 * P) ||
+            bp->pair_sum.alloc(sizeof(double) * P * n_comp))
+            return bail(2);
+        cudaMemsetAsync((uint32_t *)cnt.p + P, 0, 4, s);
+        cub::DeviceScan::ExclusiveSum(nullptr, tb3, (uint32_t *)cnt.p, (uint32_t *)bp->pair_ptr.p, (int)(P + 1), s);
+        if (tmp.alloc(tb3)) return bail(2);
+        cub::DeviceScan::ExclusiveSum(tmp.p, tb3, (uint32_t *)cnt.p, (uint32_t *)bp->pair_ptr.p, (int)(P + 1), s);
+        tile_local_ids<<<grid_for(M, 256), 256, 0, s>>>(tv.Current(), M, n_phi, TL, (uint16_t *)bp->tile_ent.p);
+        lower_bound_u64<<<grid_for(n_tiles + 1, 256), 256, 0, s>>>((uint64_t *)uk.p, P, n_tiles, (uint64_t)n_nodes,
+                                                                   (int32_t *)bp->tile_ptr.p);
+        // a node's pairs in ascending tile order: stable sort of the pair ids by node
+        uint32_t *pk = (uint32_t *)id_a.p, *pk_alt = (uint32_t *)id_b.p;  // M >= P: reuse
+        uint32_t *pi = (uint32_t *)k64.p, *pi_out = (uint32_t *)bp->node_pair.p;
+        pair_node_keys<<<grid_for(P, 256), 256, 0, s>>>((uint64_t *)uk.p, P, n_nodes, pk, pi);
+        int nbits = 1;
+        while (nbits < 32 && (((uint64_t)n_nodes) >> nbits) != 0) ++nbits;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb3, pk, pk_alt, pi, pi_out, (int)P, 0, nbits, s);
+        if (tmp.alloc(tb3)) return bail(2);
+        if (cub::DeviceRadixSort::SortPairs(tmp.p, tb3, pk, pk_alt, pi, pi_out, (int)P, 0, nbits, s) != cudaSuccess)
+            return bail(fail("nfa_bplan_create: pair sort failed"));
+        node_ptr_kernel<<<grid_for(n_nodes + 1, 256), 256, 0, s>>>(pk_alt, P, n_nodes, (int32_t *)bp->node_pair_ptr.p);
+        count_launch(24);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return bail(fail("nfa_bplan_create: tile-merged load lists failed"));
+    }
     // ---- scalar CSR pattern
     int64_t n_dof = n_nodes * n_comp, nnz = nb * nc2;
     if (bp->indptr.alloc(4 * (n_dof + 1)) || bp->indices.alloc(4 * nnz)) return bail(2);
@@ -292,6 +482,27 @@ extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const in
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return bail(fail(std::string("nfa_bplan_create: ") + cudaGetErrorString(e)));
     *out = bp;
+    return 0;
+}
+
+extern "C" int nfa_bplan_gather_load(const nfa_bplan *bp, const double *re, int comp_pitch, int overwrite, double *rhs,
+                                     nfa_stream stream) {
+    if (!bp || !re || !rhs) return fail("nfa_bplan_gather_load: NULL argument");
+    if (comp_pitch != bp->n_comp && !(comp_pitch == 4 && bp->n_comp == 3))
+        return fail("nfa_bplan_gather_load: comp_pitch must be n_comp (or 4 for three components)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int32_t *np = (const int32_t *)bp->node_ptr.p;
+    const uint32_t *ne = (const uint32_t *)bp->node_ent.p;
+    const unsigned grid = (unsigned)grid_for(bp->n_nodes, 256);
+    if (bp->n_comp == 3 && comp_pitch == 4)
+        node_gather_kernel<3, 4><<<grid, 256, 0, s>>>(bp->n_nodes, np, ne, re, overwrite, rhs);
+    else if (bp->n_comp == 3)
+        node_gather_kernel<3, 3><<<grid, 256, 0, s>>>(bp->n_nodes, np, ne, re, overwrite, rhs);
+    else if (bp->n_comp == 2)
+        node_gather_kernel<2, 2><<<grid, 256, 0, s>>>(bp->n_nodes, np, ne, re, overwrite, rhs);
+    else
+        node_gather_kernel<1, 1><<<grid, 256, 0, s>>>(bp->n_nodes, np, ne, re, overwrite, rhs);
+    NFA_LAUNCH_CHECK();
     return 0;
 }
 

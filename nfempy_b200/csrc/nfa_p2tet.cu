@@ -18,6 +18,7 @@
 // fetched with 256-bit loads (LDG.E.256) from the per-cell geometry records (L1/L2 resident: 128 B per cell).
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "nfa_plan.cuh"
 
@@ -681,7 +682,7 @@ __global__ void __launch_bounds__(THREADS, 1)
                             const uint2 *__restrict__ item_hdr, const uint32_t *__restrict__ ell,
                             const double *__restrict__ rec, int tile_stride, double *__restrict__ vals,
                             unsigned ell_size, unsigned n_slots, int n_tasks, const double *__restrict__ re4,
-                            double *__restrict__ rhs, int rhs_overwrite) {
+                            double *__restrict__ rhs, int rhs_overwrite, const int *__restrict__ cta_ptr) {
     // NB > 0: the number of tiles is a compile-time power of two, so that the tile of a chunk ((c - c_begin) % NBUF) and its
     // round ((c - c_begin) / NBUF) cost a mask and a shift instead of two integer divisions per task (the task loop's scalar
     // bookkeeping is 40 % of the instructions the kernel executes)
@@ -692,8 +693,9 @@ __global__ void __launch_bounds__(THREADS, 1)
     // kept in registers across the accumulation loops, which need the whole register file.
     volatile int *ctrl = reinterpret_cast<volatile int *>(smem + (size_t)NBUF * tile_stride);
     if (threadIdx.x == 0) {
-        const int c_begin = (int)((int64_t)n_chunks * blockIdx.x / gridDim.x);
-        const int c_end = (int)((int64_t)n_chunks * (blockIdx.x + 1) / gridDim.x);
+        // chunk range of this CTA: equal chunk counts, or the plan's work-balanced split (nfa_bplan_set_p2_split)
+        const int c_begin = cta_ptr ? __ldg(cta_ptr + blockIdx.x) : (int)((int64_t)n_chunks * blockIdx.x / gridDim.x);
+        const int c_end = cta_ptr ? __ldg(cta_ptr + blockIdx.x + 1) : (int)((int64_t)n_chunks * (blockIdx.x + 1) / gridDim.x);
         ctrl[1] = c_begin;
         ctrl[2] = c_end;
         ctrl[0] = ctrl[3] = 0;
@@ -1009,6 +1011,26 @@ extern "C" int nfa_p2_lane_order(int64_t n_groups, const int64_t *group_ptr, con
     return 0;
 }
 
+extern "C" int nfa_bplan_set_p2_split(nfa_bplan *bp, int n_cta, const int32_t *cta_ptr, nfa_stream stream) {
+    if (!bp) return fail("nfa_bplan_set_p2_split: plan is NULL");
+    nfa_bplan::P2Items &it = bp->p2;
+    if (it.n_chunks <= 0) return fail("nfa_bplan_set_p2_split: the plan carries no row items");
+    it.n_split = 0;
+    if (n_cta <= 0 || !cta_ptr) return 0;  // back to equal chunk counts
+    std::vector<int32_t> h(n_cta + 1);
+    cudaStream_t s = (cudaStream_t)stream;
+    NFA_CUDA(cudaMemcpyAsync(h.data(), cta_ptr, 4 * (n_cta + 1), cudaMemcpyDeviceToHost, s));
+    NFA_CUDA(cudaStreamSynchronize(s));
+    if (h[0] != 0 || h[n_cta] != it.n_chunks) return fail("nfa_bplan_set_p2_split: the split must cover [0, n_chunks]");
+    for (int b = 0; b < n_cta; ++b)
+        if (h[b] > h[b + 1]) return fail("nfa_bplan_set_p2_split: the split must be non-decreasing");
+    if (it.cta_ptr.alloc(4 * (n_cta + 1))) return 2;
+    NFA_CUDA(cudaMemcpyAsync(it.cta_ptr.p, cta_ptr, 4 * (n_cta + 1), cudaMemcpyDeviceToDevice, s));
+    NFA_CUDA(cudaStreamSynchronize(s));
+    it.n_split = n_cta;
+    return 0;
+}
+
 extern "C" int nfa_bplan_has_p2_items(const nfa_bplan *bp) { return bp && bp->p2.n_chunks > 0 ? 1 : 0; }
 
 extern "C" int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *mask, nfa_stream stream) {
@@ -1024,11 +1046,6 @@ extern "C" int nfa_bplan_set_cell_mask(nfa_bplan *bp, const uint8_t *mask, nfa_s
     NFA_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
-
-// threads per CTA of the row-item kernel: 0 = the default (512, or NFA_P2TET_THREADS); GPUAssembler selects 448 while the
-// background load kernel shares the SMs (nfa_local_h1_load_bg needs 4 K registers and 32 KB of shared memory beside it)
-static int g_p2_threads = 0;
-extern "C" void nfa_p2tet_set_threads(int threads) { g_p2_threads = threads; }
 
 static int assemble_p2tet(const nfa_bplan *bp, const double *coords, const int32_t *cell_nodes, const double *lam,
                           int64_t ls, const double *mu, int64_t ms, double *vals, const double *re4, double *rhs,
@@ -1050,11 +1067,10 @@ static int assemble_p2tet(const nfa_bplan *bp, const double *coords, const int32
     // both coefficients constant over the mesh: rho = lambda / mu is one number and Kf is applied once per block
     const bool cr = (ls == 0 && ms == 0);
     int threads = P2_THREADS;  // 512 (128 registers): more warps spill and lose (1.5 ms), see DESIGN.md
-    if (g_p2_threads > 0) threads = g_p2_threads;
     if (const char *e = getenv("NFA_P2TET_THREADS")) threads = atoi(e);
     if (threads > 640) threads = 512;  // larger counts are staged-kernel settings
     using kern_t = void (*)(int, int, const int4 *, const int4 *, const uint2 *, const uint32_t *, const double *, int,
-                            double *, unsigned, unsigned, int, const double *, double *, int);
+                            double *, unsigned, unsigned, int, const double *, double *, int, const int *);
     kern_t kern = nullptr;
     const bool nb4 = nbuf == 4 && !getenv("NFA_P2TET_RT_NBUF");
     const bool ld = re4 != nullptr && rhs != nullptr;
@@ -1079,7 +1095,7 @@ static int assemble_p2tet(const nfa_bplan *bp, const double *coords, const int32
                                                   (const int4 *)it.task_hdr.p, (const uint2 *)it.item_hdr.p,
                                                   (const uint32_t *)it.ell.p, (const double *)it.rec.p, tile_stride, vals,
                                                   (unsigned)it.ell_size, (unsigned)it.n_items, (int)it.n_tasks, re4, rhs,
-                                                  rhs_overwrite);
+                                                  rhs_overwrite, (it.n_split == grid) ? (const int *)it.cta_ptr.p : nullptr);
     if (timing_enabled()) timing_end(s);
     NFA_LAUNCH_CHECK();
     return 0;

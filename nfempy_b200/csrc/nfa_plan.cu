@@ -197,8 +197,9 @@ static int plan_create_impl(int64_t n_dof, int n_segments, const int32_t *const 
         plan->mat_off[k] = E;
         plan->rhs_off[k] = R;
         plan->with_matrix[k] = seg_flags ? (seg_flags[k] & 1) : 1;
+        plan->with_rhs[k] = seg_flags ? ((seg_flags[k] & 2) ? 0 : 1) : 1;
         if (plan->with_matrix[k]) E += n_items[k] * (int64_t)n_loc[k] * n_loc[k];
-        R += n_items[k] * (int64_t)n_loc[k];
+        if (plan->with_rhs[k]) R += n_items[k] * (int64_t)n_loc[k];
     }
     plan->mat_off[n_segments] = E;
     plan->rhs_off[n_segments] = R;
@@ -288,7 +289,7 @@ static int plan_create_impl(int64_t n_dof, int n_segments, const int32_t *const 
         if (keys.alloc(4 * R) || keys_alt.alloc(4 * R) || ids.alloc(4 * R) || ids_alt.alloc(4 * R)) return bail(2);
         for (int k = 0; k < n_segments; ++k) {
             int64_t n = n_items[k] * (int64_t)n_loc[k];
-            if (n == 0) continue;
+            if (n == 0 || !plan->with_rhs[k]) continue;
             fill_row_keys<<<grid_for(n, 256), 256, 0, s>>>(dest[k], n, (uint32_t)plan->rhs_off[k],
                                                            (uint32_t *)keys.p, (uint32_t *)ids.p);
             count_launch();
@@ -385,7 +386,7 @@ extern "C" int nfa_plan_reduce(const nfa_plan *plan, const double *const *Ke, co
         if (plan->rhs.n_unique > 0) {
             SegPtrs sp;
             sp.n = plan->n_segments;
-            for (int k = 0; k < plan->n_segments; ++k) sp.p[k] = re[k];
+            for (int k = 0; k < plan->n_segments; ++k) sp.p[k] = plan->with_rhs[k] ? re[k] : nullptr;
             for (int k = 0; k <= plan->n_segments; ++k) sp.off[k] = plan->rhs_off[k];
             reduce_kernel<<<grid_for(plan->rhs.n_unique, 256), 256, 0, s>>>(
                 plan->rhs.n_unique, (const uint32_t *)plan->rhs.seg_ptr.p, (const uint32_t *)plan->rhs.perm.p,

@@ -37,6 +37,7 @@ struct nfa_plan {
     int64_t n_items[NFA_MAX_SEGMENTS] = {0};
     int32_t n_loc[NFA_MAX_SEGMENTS] = {0};
     int with_matrix[NFA_MAX_SEGMENTS] = {0};
+    int with_rhs[NFA_MAX_SEGMENTS] = {0};  // 0: the segment's right-hand side is summed elsewhere (nfa_bplan_gather_load)
     int64_t mat_off[NFA_MAX_SEGMENTS + 1] = {0}, rhs_off[NFA_MAX_SEGMENTS + 1] = {0};
     nfa::GatherSet mat, rhs;
 
@@ -69,6 +70,22 @@ struct nfa_bplan {
                               // position in the chunk's cell order (= its staging slot)
     nfa::DevBuf indptr, indices;  // scalar CSR pattern int32
     nfa::DevBuf geo;              // scratch: per-cell geometry records [n_cells][12], rewritten every assembly
+    // node incidence lists (nfa_bplan_gather_load): node N is local node a of cell c for the entries c * n_phi + a in
+    // node_ent[node_ptr[N] .. node_ptr[N+1]), ascending = the order of the reference's res_g[dest] += r_el
+    nfa::DevBuf node_ptr;         // int32 [n_nodes + 1]
+    nfa::DevBuf node_ent;         // uint32 [n_cells * n_phi]
+    // Tile-merged load (nfa_bplan_load_rhs): cells are cut into tiles of LOAD_TILE consecutive cells; a PAIR is a (tile,
+    // node) with at least one (cell, local node) of the tile on that node.  Pairs are ordered by (tile, node); the entries
+    // of a pair (ascending cell) are tile_ent[pair_ptr[p] .. pair_ptr[p+1]) as uint16 local ids (cell - tile * LOAD_TILE) *
+    // n_phi + a.  A node's pairs (ascending tile) are node_pair[node_pair_ptr[N] .. node_pair_ptr[N+1]).
+    static constexpr int LOAD_TILE = 64;
+    int64_t n_pairs = 0;
+    nfa::DevBuf tile_ptr;         // int32 [n_tiles + 1]  first pair of each tile
+    nfa::DevBuf pair_ptr;         // uint32 [n_pairs + 1]
+    nfa::DevBuf tile_ent;         // uint16 [n_cells * n_phi]
+    nfa::DevBuf node_pair_ptr;    // int32 [n_nodes + 1]
+    nfa::DevBuf node_pair;        // uint32 [n_pairs]
+    nfa::DevBuf pair_sum;         // scratch: double [n_pairs][n_comp], rewritten every assembly
     // Row-item lists of the vector-P2 tetrahedron kernel (nfa_p2tet.cu), built by nfempy_b200/assembly/p2_items.py
     struct P2Items {
         int64_t n_chunks = 0, n_tasks = 0, n_items = 0, ell_size = 0;
@@ -78,6 +95,8 @@ struct nfa_bplan {
         nfa::DevBuf item_hdr;   // uint16 [n_slots][4]: tile offsets of up to three blocks, row pitch; type E: + a second slot
         nfa::DevBuf ell;        // uint32 [ell_size]: cell << 6 | i << 4 | j << 2 | x, 32 lanes interleaved
         nfa::DevBuf rec;        // scratch: geometry records [n_cells][4][4], rewritten every assembly
+        nfa::DevBuf cta_ptr;    // optional int32 [n_split + 1]: chunk range of every CTA when the grid has n_split CTAs
+        int64_t n_split = 0;
         nfa::DevBuf cell_mask;  // optional uint8 [n_cells]: 0 = the cell contributes zeros (halo cell of a sharded plan)
     } p2;
 };

@@ -109,16 +109,8 @@ class H1VolumeForm(BatchedWeakForm):
         key = (self.field_name, "mref", s.k_order, dim)
         return dev.tensor(key, lambda: reference_stiffness_tensor(s.ref_element, points, weights))
 
-    def launch_load(self, dev, data, re, comp_pitch=None, background=False):
-        """Load vector only (fused path).  ``comp_pitch``: padded node records ``re [n, n_phi, comp_pitch]``;
-        ``background``: the small-footprint kernel that shares the SMs with the row-item matrix kernel."""
-        if background:
-            _lib.call(
-                "nfa_local_h1_load_bg", data.dim, data.n_phi, data.n_q, data.n_comp, _lib.ptr(data.tab[0]),
-                _lib.ptr(data.w), _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes), data.n_items, _lib.ptr(data.f),
-                float(self.load_sign), _lib.ptr(re), _lib.stream_ptr(),
-            )
-            return
+    def launch_load(self, dev, data, re, comp_pitch=None):
+        """Load vector only (fused path).  ``comp_pitch``: padded node records ``re [n, n_phi, comp_pitch]``."""
         if comp_pitch is not None:
             _lib.call(
                 "nfa_local_h1_load_pitched", data.dim, data.n_phi, data.n_q, data.n_comp, _lib.ptr(data.tab[0]),

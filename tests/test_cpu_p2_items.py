@@ -129,3 +129,19 @@ def test_item_plan_entries_are_in_ascending_cell_order():
         for lane in range(nit):
             cells = [ell[base + 32 * k + lane] >> 6 for k in range(kmax) if ell[base + 32 * k + lane] != 0xFFFFFFFF]
             assert cells == sorted(cells) and len(set(cells)) == len(cells) and len(cells) >= 1
+
+
+def test_balanced_split_covers_the_chunks_and_evens_out_the_work():
+    _, _, _, node_dest, n_nodes, _ = _setup(3)
+    bptr, bcols, _ = _block_csr(node_dest, n_nodes)
+    plan = p2_items.build(torch.as_tensor(node_dest), torch.as_tensor(bptr), torch.as_tensor(bcols), n_nodes, cap=64, riffle=4)
+    n_chunks = plan["n_chunks"]
+    for n_cta in (1, 3, 7, n_chunks):
+        split = p2_items.balanced_split(plan, n_cta).numpy()
+        assert split[0] == 0 and split[-1] == n_chunks and len(split) == n_cta + 1 and np.all(np.diff(split) >= 0)
+    th = plan["task_hdr"].numpy().astype(np.int64)
+    ch = plan["chunk_hdr"].numpy().astype(np.int64)
+    cost = np.array([(3 + ((th[t0 : t0 + nt, 0] >> 8) & 0xFF)).sum() for _, _, t0, nt in ch])
+    split = p2_items.balanced_split(plan, 4).numpy()
+    per = np.array([cost[split[b] : split[b + 1]].sum() for b in range(4)])
+    assert per.max() - per.min() <= 2 * cost.max()  # within the granularity of whole chunks

@@ -235,3 +235,19 @@ def test_captured_graph_follows_a_state_vector_that_starts_at_zero():
     K = asm.jacobian.to_scipy()
     assert np.abs(r1 - (r0 + K @ alpha)).max() <= 1e-12 * np.abs(r1).max()
     assert np.abs(r1 - r0).max() > 1e-3
+
+
+@pytest.mark.parametrize("with_bc", [False, True])
+def test_right_hand_side_paths_agree(monkeypatch, with_bc):
+    """The fused form's right-hand side three ways: tile-merged load (nfa_bplan_load_rhs: 750 tets = 11 full tiles of 64
+    cells + a ragged one), local load vectors + row-owner gather (nfa_bplan_gather_load), the plan's generic row lists."""
+    case = elasticity_case(n=5, with_bc=with_bc)
+    merged = case.run_gpu(allow_fused=True)
+    monkeypatch.setenv("NFA_LOAD_MERGE", "0")
+    gathered = case.run_gpu(allow_fused=True)
+    monkeypatch.setenv("NFA_RHS_GATHER", "0")
+    generic = case.run_gpu(allow_fused=True)
+    assert np.array_equal(gathered[3], generic[3])  # both sum cell by cell in ascending order
+    scale = np.abs(generic[3]).max()
+    assert np.abs(merged[3] - generic[3]).max() <= 1e-14 * scale  # associated tile by tile
+    assert np.array_equal(merged[2], generic[2])
