@@ -413,6 +413,39 @@ def run_graft(args):
     ms_step = float(t.item()) / args.steps
     value = n_cells * world / (ms_step * 1e-3)
 
+    # ---- N > 1: where the step goes, per rank (local kernels alone / whole step with the exchange), device-timed
+    breakdown = None
+    if sharded is not None:
+        def timed(fn, sync_ranks):
+            for _ in range(3):
+                fn()
+            if sync_ranks:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / args.steps
+
+        step_ms_rank = timed(step, True)  # own clock of this rank around the same K steps (no max)
+        dist.barrier()
+        local_graph = sharded.asm.capture(sharded.state, sharded.rhs, fresh="rows")  # the local kernels alone, no exchange
+        local_ms_rank = timed(local_graph.replay, False)
+        dist.barrier()
+        payload = int(sum(sharded._sizes[t] + int(sharded._rows_dev[t].shape[0]) for t in sharded._sizes if t[0] == "send")) * 8
+        mine = {"rank": rank, "step_ms": step_ms_rank, "local_ms": local_ms_rank, "send_bytes": payload,
+                "send_to": sorted(int(q) for q in sharded.shard.send_rows), "recv_from": sorted(int(q) for q in sharded.shard.recv_rows),
+                "own_cells": int(n_cells), "plan_cells": int(datas[0].n_items)}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        if rank == 0:
+            loc = [g["local_ms"] for g in gathered]
+            breakdown = {"per_rank": gathered, "local_ms_max": max(loc), "local_ms_min": min(loc),
+                         "step_ms_max_over_ranks": ms_step, "exchange_and_skew_ms": ms_step - max(loc)}
+
     # ---- roofline of the dominant (fused) kernel; algorithmic bytes per tet, SURVEY.md 8(d)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -487,7 +520,7 @@ def run_graft(args):
                 "exchange": None if sharded is None else ("nfa_push_rows / nfa_pull_add_rows over NVLink peer memory (CUDA IPC)" if p2p
                                                           else "pack kernels + ncclSend/ncclRecv + unpack kernels"),
             },
-            "roofline": roofline, "varying_coefficients": varying, "parity": parity, "cpu_baseline": cpu, "cpu_strong": cpu_strong, "e2e": e2e, "e2e_all_inputs": e2e_all, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "breakdown": breakdown, "varying_coefficients": varying, "parity": parity, "cpu_baseline": cpu, "cpu_strong": cpu_strong, "e2e": e2e, "e2e_all_inputs": e2e_all, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

@@ -215,10 +215,13 @@ int nfa_bplan_gather_load(const nfa_bplan *bp, const double *d_re, int comp_pitc
  * copies, like nfa_local_h1_load), sum them per node of the tile (ascending cell) and write one record per (tile, node)
  * pair -- about 3 per cell instead of n_phi; the second kernel adds a node's pair sums in ascending tile order into rows
  * n_comp N + c of d_rhs.  Same terms as res_g[dest] += r_el (R/src/assembly/ScatterFormData.py:14-18), associated tile by
- * tile.  Vector P2 / P1 on tetrahedra, vector P2 on triangles; n_q <= 64.  overwrite as in nfa_bplan_gather_load. */
+ * tile.  Vector P2 / P1 on tetrahedra, vector P2 on triangles; n_q <= 64.  Only the rows of nodes that HAVE cells in this
+ * plan are visited (nfa_bplan_n_active_nodes of them): overwrite != 0 replaces those rows and leaves every other row of
+ * d_rhs alone -- a rank's local plan over the global numbering never touches the other ranks' rows. */
 int nfa_bplan_load_rhs(const nfa_bplan *bp, int dim, int n_q, const double *d_tab0, const double *d_weights,
                        const double *d_coords, const int32_t *d_cell_nodes, const double *d_f, double sign, int overwrite,
                        double *d_rhs, nfa_stream stream);
+int64_t nfa_bplan_n_active_nodes(const nfa_bplan *bp);
 int64_t nfa_bplan_nnz(const nfa_bplan *bp);
 int64_t nfa_bplan_bytes(const nfa_bplan *bp);
 /* Mref [n_phi, n_phi, dim, dim] = int_ref d_k phi_a d_l phi_b (exact reference stiffness tensor).

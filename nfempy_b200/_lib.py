@@ -67,6 +67,7 @@ SIGNATURES = {
     "nfa_push_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_pull_add_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_bplan_gather_load": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "nfa_bplan_n_active_nodes": (_i64, [_vp]),
     "nfa_bplan_load_rhs": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp]),
     "nfa_bplan_create": (_i, [_i64, _i, _i, _vp, _i64, ctypes.POINTER(_vp), _vp]),
     "nfa_bplan_destroy": (None, [_vp]),

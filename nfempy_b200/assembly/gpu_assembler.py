@@ -243,7 +243,7 @@ class GPUAssembler:
             )
             p.bplan = bh
             if int(node_dest.shape[1]) == 10 and nc == 3 and s.dimension == 3 and os.environ.get("NFA_P2TET", "1") != "0":
-                self._attach_p2_items(lib, dev, p, node_dest, stream)
+                self._attach_p2_items(lib, dev, p, node_dest, stream, getattr(self, "p2_cell_live", None))
             ph = ctypes.c_void_p()
             _lib.check(lib.nfa_plan_from_bplan(bh, ctypes.byref(ph), stream), "nfa_plan_from_bplan")
             p.pattern = ph
@@ -266,7 +266,7 @@ class GPUAssembler:
         return p
 
     @staticmethod
-    def _attach_p2_items(lib, dev, p, node_dest, stream):
+    def _attach_p2_items(lib, dev, p, node_dest, stream, cell_live=None):
         """Row-item lists of the vector-P2 tetrahedron kernel (assembly/p2_items.py), built on the device with torch
         tensor operations from the plan's block pattern and copied into the plan."""
         from . import p2_items
@@ -295,7 +295,8 @@ class GPUAssembler:
                                batch=int(os.environ.get("NFA_P2TET_BATCH", "8")),
                                lane_order=os.environ.get("NFA_P2TET_LANES", "cell"), lane_optimizer=lane_optimizer,
                                locality=os.environ.get("NFA_P2TET_LOCAL", "1") != "0",
-                               type_order=tuple(int(c) for c in os.environ.get("NFA_P2TET_TYPEORDER", "01234")))
+                               type_order=tuple(int(c) for c in os.environ.get("NFA_P2TET_TYPEORDER", "01234")),
+                               cell_live=None if cell_live is None else torch.as_tensor(cell_live).to(dev.device))
         _lib.check(
             lib.nfa_bplan_set_p2_items(
                 p.bplan, items["n_chunks"], _lib.ptr(items["chunk_hdr"]), items["n_tasks"], _lib.ptr(items["task_hdr"]),
@@ -451,7 +452,8 @@ class GPUAssembler:
     def run(self, state, rhs_dev=None, fresh=False):
         """Launches the kernels of one assembly.  Adds into ``self.jacobian`` and into ``rhs_dev`` (the device residual,
         returned).  ``fresh=True``: ``rhs_dev`` holds nothing the caller wants to keep -- the assembly result replaces it
-        (the buffer is zeroed here unless the fused row-item kernel overwrites every row anyway)."""
+        (the buffer is zeroed here unless the kernels overwrite every row anyway).  ``fresh="rows"``: the same for the rows of
+        the nodes that have cells in this form list; every other row is the caller's (a rank's share of a sharded assembly)."""
         with torch.cuda.device(state[0].device):
             return self._run(state, rhs_dev, fresh)
 
@@ -473,12 +475,26 @@ class GPUAssembler:
         # rows of a fresh buffer -- no fill.  NFA_P2TET_RHS=1: the row-item matrix kernel gathers them itself (measured slower)
         gather = bool(getattr(plan, "rhs_gather", False))
         fold = gather and self._folds_load(lib, plan, entries, datas)
-        fresh = fresh or rhs_dev is None
-        has_load = gather and datas[plan.fused_index].f is not None
-        overwrite = fresh and has_load and (not fold or bool(plan.p2_stats.get("all_rows_nonempty")))
+        fdata = datas[plan.fused_index] if gather else None
+        has_load = gather and fdata.f is not None
+        # tile-merged load (local load vectors never reach HBM) where the streaming load kernel exists
+        merged = bool(has_load and not fold and fdata.n_q <= 64
+                      and (fdata.dim, fdata.n_phi, fdata.n_comp) in ((3, 10, 3), (3, 4, 3), (2, 6, 2))
+                      and os.environ.get("NFA_LOAD_MERGE", "1") != "0")
+        # fresh == "rows": only the rows of nodes that have cells in this plan are replaced, the caller keeps the others (a
+        # rank's plan over the global numbering must not sweep the other ranks' rows on every step)
+        rows_only = isinstance(fresh, str) and fresh == "rows"
+        fresh = bool(fresh) or rhs_dev is None
+        if merged:
+            all_active = int(lib.nfa_bplan_n_active_nodes(plan.bplan)) * fdata.n_comp == plan.n_dof
+            overwrite = fresh and (all_active or rows_only)
+        elif fold:
+            overwrite = fresh and bool(plan.p2_stats.get("all_rows_nonempty"))
+        else:
+            overwrite = fresh and has_load  # nfa_bplan_gather_load writes every row (zeros for nodes without cells)
         self.last_rhs_fill = fresh and not overwrite  # a torch fill kernel ran (launch accounting)
         if rhs_dev is None:
-            rhs_dev = (torch.empty if overwrite else torch.zeros)(plan.n_dof, dtype=torch.float64, device=dev.device)
+            rhs_dev = (torch.empty if (overwrite and not rows_only) else torch.zeros)(plan.n_dof, dtype=torch.float64, device=dev.device)
         elif fresh and not overwrite:
             rhs_dev.zero_()
         nseg = len(entries)
@@ -512,9 +528,6 @@ class GPUAssembler:
                 # right-hand side of the form's load: tile-merged (local load vectors never reach HBM) where the streaming
                 # load kernel exists, else local load vectors [n, n_loc] + the row-owner gather (or the plan's generic lists)
                 re = None
-                merged = (gather and not fold and data.f is not None and data.n_q <= 64
-                          and (data.dim, data.n_phi, data.n_comp) in ((3, 10, 3), (3, 4, 3), (2, 6, 2))
-                          and os.environ.get("NFA_LOAD_MERGE", "1") != "0")
                 if data.f is not None and not merged:
                     if fold:  # padded node records [n, 10, 4]: one 32-byte sector per cell and node
                         re = torch.empty((data.n_items, 10, 4), dtype=torch.float64, device=dev.device)
@@ -576,7 +589,7 @@ class GPUAssembler:
         return bool(spec and spec.get("p2tet_kernel") and data.f is not None and lib.nfa_bplan_has_p2_items(plan.bplan)
                     and hasattr(lib, spec["p2tet_kernel"] + "_load"))
 
-    def capture(self, state, rhs_dev):
+    def capture(self, state, rhs_dev, fresh=True):
         """CUDA graph of one fresh assembly (``rhs_dev`` zeroed, every CSR value overwritten) on the buffers of ``state``:
         ``graph.replay()`` re-runs the kernels without the per-launch host work -- for time / Newton loops that
         reassemble on one plan.  Every entry listed with a state vector (``alpha`` not ``None``) keeps its state terms
@@ -586,16 +599,16 @@ class GPUAssembler:
         if state[4] is None:
             raise _lib.NfaError("GPUAssembler.capture: value-dependent pattern policies rebuild the plan every assembly")
         with torch.cuda.device(state[0].device):
-            return self._capture(state, rhs_dev)
+            return self._capture(state, rhs_dev, fresh)
 
-    def _capture(self, state, rhs_dev):
+    def _capture(self, state, rhs_dev, fresh=True):
         dev = state[0]
 
         def body():
             self.jacobian.is_zero = True
             self._capturing = True
             try:
-                self.run(state, rhs_dev, fresh=True)
+                self.run(state, rhs_dev, fresh=fresh)
             finally:
                 self._capturing = False
 

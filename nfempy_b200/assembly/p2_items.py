@@ -169,12 +169,14 @@ def greedy_lane_order(group_ptr, hdr, window=48):
 
 
 def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_order="cell", lane_optimizer=None,
-          locality=True, type_order=(0, 1, 2, 3, 4)):
+          locality=True, type_order=(0, 1, 2, 3, 4), cell_live=None):
     """``node_dest`` int64 [n_cells, 10] global node of each local P2 node, ``bptr``/``bcols`` the block CSR of the
     matrix (int64 tensors on the same device).  ``lane_optimizer(group_ptr, hdr6) -> permutation`` reorders the items
     inside their (chunk, type) groups (``nfa_p2_lane_order`` on the device, ``greedy_lane_order`` in the tests; None keeps
     the first-cell order).  ``type_order[t]`` = position of item type t (A..E) in a chunk's task list.  Returns a dict of
-    tensors (see module docstring) and sizes."""
+    tensors (see module docstring) and sizes.  ``cell_live`` (bool [n_cells], optional): cells marked False contribute zeros
+    by contract (the halo cells of a rank's local plan: they only complete the sparsity pattern) -- their entries are
+    left out of the lists, the items (and the zeros they write) stay."""
     dev = node_dest.device
     n_cells = int(node_dest.shape[0])
     if n_cells >= (1 << 26):
@@ -261,7 +263,14 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     # the ones that decide when its tile can be handed over -- are short ones
     rank_of_type = torch.as_tensor(type_order, dtype=torch.int64, device=dev)
     key = (chunk_of_row[rowN] << 34) | (rank_of_type[typ] << 31) | item_blk
-    key, order = torch.sort(key, stable=True)
+    if cell_live is not None:
+        # dead entries go to the end of their item (one more key bit below the item key) and are cut off the lists below
+        dead = (~cell_live.to(torch.bool))[:, None].expand(n_cells, T).reshape(-1).to(torch.int64)
+        key2, order = torch.sort((key << 1) | dead, stable=True)
+        key, dead = key2 >> 1, (key2 & 1).to(torch.bool)
+    else:
+        key, order = torch.sort(key, stable=True)
+        dead = None
     code, blk, rowN, fblk = code[order], blk[order], rowN[order], fblk[order]
     n_entries = int(key.shape[0])
 
@@ -272,6 +281,9 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     n_items = int(item_start.shape[0])
     item_end = torch.cat([item_start[1:], torch.tensor([n_entries], device=dev)])
     item_count = item_end - item_start
+    if dead is not None:  # live entries only (they come first inside an item); an item may keep none
+        live_cum = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum((~dead).to(torch.int64), 0)])
+        item_count = live_cum[item_end] - live_cum[item_start]
     type_of_rank = torch.empty(5, dtype=torch.int64, device=dev)
     type_of_rank[rank_of_type] = torch.arange(5, device=dev)
     item_key = key[item_start] >> 31  # chunk | sort rank of the type
@@ -329,6 +341,7 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     cnt_sorted = item_count[iperm]
     kmax = torch.zeros(n_tasks, dtype=torch.int64, device=dev)
     kmax.scatter_reduce_(0, task_of_item, cnt_sorted, reduce="amax", include_self=True)
+    kmax.clamp_(min=1)  # a task of items without live entries still owns one (empty) ELL row: the kernel reads entry 0
     task_items = torch.zeros(n_tasks, dtype=torch.int64, device=dev)
     task_items.scatter_add_(0, task_of_item, torch.ones_like(task_of_item))
     ell_base = torch.cumsum(kmax * 32, 0) - kmax * 32
@@ -364,7 +377,12 @@ def build(node_dest, bptr, bcols, n_nodes, cap=640, riffle=148, batch=8, lane_or
     inv[iperm] = torch.arange(n_items, device=dev)
     pos = inv[item_of_entry]
     ell = torch.full((ell_size,), NONE32, dtype=torch.int64, device=dev)
-    ell[ell_base[task_of_item[pos]] + r_in_item * 32 + lane[pos]] = code
+    if dead is None:
+        ell[ell_base[task_of_item[pos]] + r_in_item * 32 + lane[pos]] = code
+    else:
+        lv = torch.nonzero(~dead).reshape(-1)
+        ell[ell_base[task_of_item[pos[lv]]] + r_in_item[lv] * 32 + lane[pos[lv]]] = code[lv]
+        n_entries = int(lv.shape[0])
     # chunk headers
     tfirst_chunk = torch.ones(n_tasks, dtype=torch.bool, device=dev)
     tfirst_chunk[1:] = task_chunk[1:] != task_chunk[:-1]
@@ -486,7 +504,7 @@ def walk(plan, rec, n_bnz, re4=None, n_nodes=None):
                 targets = [(0, w0), (1, w1), (2, w2)][: N_BLOCKS_OF_TYPE[int(typ)]]
                 if typ == TYPE_E:
                     f0, f1 = item_hdr[slot0 + per * lane + 1][:2]
-                    assert f1 == NONE16 or len(entries) == 2
+                    # (f1 is set without a second entry when that cell is a dead one: its block is written as zeros)
                     targets += [(3, f0), (4, f1)]
                 if typ in (TYPE_A, TYPE_D):  # the owner of the node's right-hand-side rows
                     node = (w1 | (w2 << 16)) if typ == TYPE_A else int(

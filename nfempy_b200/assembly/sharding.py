@@ -23,6 +23,8 @@ graph.  Without it (or when CUDA IPC is unavailable) the rows go through pack ke
 ``ShardPlan`` is pure host logic (numpy) on the replicated destination table; the exchange takes pack/unpack
 callables so that the same code runs over NCCL on device buffers and over gloo on CPU tensors (tests).
 """
+import os
+
 import numpy as np
 
 from ..mesh import _accel
@@ -141,6 +143,10 @@ class ShardedAssembler:
 
     def prepare(self):
         torch = self._torch
+        if os.environ.get("NFA_P2TET_PRUNE", "1") != "0":
+            # the halo cells contribute zeros by construction: the row-item lists leave their entries out (the items stay and
+            # write the zeros that complete the pattern), so the halo layers cost list space only, no record loads
+            self.asm.p2_cell_live = self.shard.is_own
         dev, entries, datas, dests, plan, key = self.asm.prepare()
         if plan.fused_index is None:
             raise NotImplementedError("ShardedAssembler needs the fused path (affine H1 form, cell-wise coefficients)")
@@ -188,7 +194,7 @@ class ShardedAssembler:
             self._graph.replay()  # zeroes rhs, overwrites every CSR value (GPUAssembler.capture)
         else:
             self.asm.jacobian.is_zero = True
-            self.asm.run(self.state, self.rhs, fresh=True)  # zeroes rhs where the kernels do not overwrite it
+            self.asm.run(self.state, self.rhs, fresh="rows")  # zeroes rhs where the kernels do not overwrite it
         self.vals = self.asm.jacobian.values_dev
         return self.vals, self.rhs
 
@@ -200,7 +206,7 @@ class ShardedAssembler:
         dev, entries, datas, dests, plan, key = self.state
         if getattr(self, "rhs", None) is None:
             self.rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=dev.device)
-        self._graph = self.asm.capture(self.state, self.rhs)
+        self._graph = self.asm.capture(self.state, self.rhs, fresh="rows")
         self.vals = self.asm.jacobian.values_dev
         return self
 
@@ -342,7 +348,7 @@ class ShardedAssembler:
             self.asm.jacobian.is_zero = True
             self.asm._capturing = True
             try:
-                self.asm.run(self.state, self.rhs, fresh=True)
+                self.asm.run(self.state, self.rhs, fresh="rows")
             finally:
                 self.asm._capturing = False
             self.vals = self.asm.jacobian.values_dev

@@ -435,6 +435,7 @@ __constant__ double c_load_wt[64 * 20];
 // MERGE (nfa_bplan_load_rhs): the tile's local load vectors stay in shared memory and are summed per NODE of the tile
 // (the plan's (tile, node) pairs, entries in ascending cell order); only the pair sums [n_pairs][N_COMP] go to HBM --
 // about 3.2 node records per cell instead of 10 -- and a second kernel adds a node's pair sums in ascending tile order.
+constexpr int LOAD_SPLIT = 1;  // measured: 2 (five sums per thread, 24 warps per SM) is slower, 266 us against 204
 struct LoadMerge {
     const int32_t *tile_ptr;   // [n_tiles + 1]
     const uint32_t *pair_ptr;  // [n_pairs + 1]
@@ -442,22 +443,41 @@ struct LoadMerge {
     double *pair_sum;          // [n_pairs][N_COMP]
 };
 
+// sums a = A0 .. A0 + NA of one (cell, component): sc * sum_q w_q phi_a(q) f_q, written to dst[a * pitch]
+template <int N_PHI, int NA, int N_COMP, int A0>
+__device__ __forceinline__ void load_sums(const double *fc, int n_q, double sc, double *dst, int pitch) {
+    double acc[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) acc[a] = 0.0;
+    for (int q = 0; q < n_q; ++q) {
+        const double v = fc[q * N_COMP];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) acc[a] = fma(c_load_wt[q * N_PHI + A0 + a], v, acc[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) dst[(A0 + a) * pitch] = sc * acc[a];
+}
+
 template <int DIM, int N_PHI, int N_COMP, int TILE, bool MERGE>
-__global__ void __launch_bounds__(TILE *N_COMP)
+__global__ void __launch_bounds__(TILE *N_COMP *LOAD_SPLIT)
     local_h1_load_stream_kernel(int n_q, const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes,
                                 int64_t n_cells, const double *__restrict__ f, double sign, double *__restrict__ re,
                                 int comp_pitch, LoadMerge mg) {
     extern __shared__ __align__(128) double smem[];  // two tiles [TILE][n_q][N_COMP], two mbarriers, (MERGE) re tile + lists
-    constexpr int NT = TILE * N_COMP;
+    constexpr int NT = TILE * N_COMP * LOAD_SPLIT;  // LOAD_SPLIT threads share a (cell, component): N_PHI / LOAD_SPLIT sums each
+    constexpr int NA = N_PHI / LOAD_SPLIT;
+    static_assert(N_PHI % LOAD_SPLIT == 0, "basis functions must split evenly");
+    constexpr int LIST_WORDS = (TILE * N_PHI + 2) / 2 + TILE * N_PHI / 2;  // 32-bit words of one tile's lists
     const int fn = n_q * N_COMP;
     const int tile_doubles = TILE * fn;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * (size_t)tile_doubles);
     double *re_tile = smem + 2 * (size_t)tile_doubles + 2;  // MERGE: [TILE][N_PHI][N_COMP]
-    // MERGE: the tile's lists -- pair offsets relative to the tile's first entry, then the entries' local ids (two a word)
-    uint16_t *s_ptr = reinterpret_cast<uint16_t *>(re_tile + TILE * N_PHI * N_COMP);  // [TILE * N_PHI + 2]
-    uint32_t *s_ent = reinterpret_cast<uint32_t *>(s_ptr + TILE * N_PHI + 2);          // [TILE * N_PHI / 2]
+    // MERGE: the lists of two tiles (current / next) -- pair offsets relative to the tile's first entry (uint16
+    // [TILE * N_PHI + 2]), then the entries' local ids (uint16, stored two a word)
+    uint32_t *lists = reinterpret_cast<uint32_t *>(re_tile + TILE * N_PHI * N_COMP);
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(bar);
-    const int lc = threadIdx.x / N_COMP, comp = threadIdx.x - lc * N_COMP;
+    const int part = threadIdx.x / (TILE * N_COMP), within = threadIdx.x - part * (TILE * N_COMP);
+    const int lc = within / N_COMP, comp = within - lc * N_COMP;
     const int64_t n_tiles = (n_cells + TILE - 1) / TILE;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
@@ -480,62 +500,92 @@ __global__ void __launch_bounds__(TILE *N_COMP)
             : "memory");
     };
     if (threadIdx.x == 0 && (int64_t)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    // Geometry pipeline: the vertex ids of a tile are requested two iterations ahead, its coordinates one iteration ahead,
+    // and the determinant is formed at the end of the previous iteration -- the two dependent global round trips
+    // (cell_nodes -> coords) never stall the iteration that needs them.
+    int32_t ids_next[DIM + 1];  // vertex ids of this thread's cell in the next tile
+    double det = 0.0;           // determinant of this thread's cell in the current tile
+    auto load_ids = [&](int64_t tile, int32_t (&ids)[DIM + 1]) {
+        const int64_t cell = tile * TILE + lc;
+#pragma unroll
+        for (int v = 0; v <= DIM; ++v) ids[v] = (tile < n_tiles && cell < n_cells) ? __ldg(cell_nodes + cell * (DIM + 1) + v) : 0;
+    };
+    auto load_X = [&](const int32_t (&ids)[DIM + 1], double (&X)[DIM + 1][3]) {
+#pragma unroll
+        for (int v = 0; v <= DIM; ++v)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) X[v][r] = __ldg(coords + 3 * (int64_t)ids[v] + r);
+    };
+    // List pipeline (MERGE), same idea: pair range two tiles ahead, list words one tile ahead (registers), stored into the
+    // other list buffer at the end of the iteration.
+    constexpr int NP_IT = MERGE ? (TILE * N_PHI + 1 + NT - 1) / NT : 1, NE_IT = MERGE ? (TILE * N_PHI / 2 + NT - 1) / NT : 1;
+    uint32_t lp[NP_IT], le[NE_IT];
+    int pc0 = 0, pc1 = 0, pn0 = 0, pn1 = 0;  // pair ranges of the current / next tile
+    auto load_range = [&](int64_t tile, int &a, int &b) {
+        a = b = 0;
+        if (tile < n_tiles) {
+            a = __ldg(mg.tile_ptr + tile);
+            b = __ldg(mg.tile_ptr + tile + 1);
+        }
+    };
+    auto load_lists = [&](int64_t tile, int q0, int q1) {  // into registers
+        const int64_t c0 = tile * TILE;
+        const int nc_t = (tile < n_tiles) ? (int)((n_cells - c0) < TILE ? (n_cells - c0) : TILE) : 0;
+#pragma unroll
+        for (int j = 0; j < NP_IT; ++j) {
+            const int i = threadIdx.x + j * NT;
+            lp[j] = (nc_t > 0 && i <= q1 - q0) ? __ldg(mg.pair_ptr + q0 + i) : 0u;  // (no arithmetic here: that would wait)
+        }
+        const uint32_t *ent32 = reinterpret_cast<const uint32_t *>(mg.tile_ent + (size_t)c0 * N_PHI);  // even offset
+#pragma unroll
+        for (int j = 0; j < NE_IT; ++j) {
+            const int i = threadIdx.x + j * NT;
+            le[j] = (i < (nc_t * N_PHI) / 2) ? __ldg(ent32 + i) : 0u;
+        }
+    };
+    auto store_lists = [&](int lbuf, int64_t tile) {  // registers -> list buffer lbuf (offsets relative to the tile's entries)
+        const uint32_t e_base = (uint32_t)(tile * TILE * N_PHI);
+        uint16_t *sp = reinterpret_cast<uint16_t *>(lists + lbuf * LIST_WORDS);
+        uint32_t *se = lists + lbuf * LIST_WORDS + (TILE * N_PHI + 2) / 2;
+#pragma unroll
+        for (int j = 0; j < NP_IT; ++j) {
+            const int i = threadIdx.x + j * NT;
+            if (i <= TILE * N_PHI) sp[i] = (uint16_t)(lp[j] - e_base);
+        }
+#pragma unroll
+        for (int j = 0; j < NE_IT; ++j) {
+            const int i = threadIdx.x + j * NT;
+            if (i < TILE * N_PHI / 2) se[i] = le[j];
+        }
+    };
+    {
+        int32_t ids0[DIM + 1];
+        double X0[DIM + 1][3];
+        load_ids(blockIdx.x, ids0);
+        load_ids((int64_t)blockIdx.x + gridDim.x, ids_next);
+        if constexpr (MERGE) {
+            load_range(blockIdx.x, pc0, pc1);
+            load_range((int64_t)blockIdx.x + gridDim.x, pn0, pn1);
+            load_lists(blockIdx.x, pc0, pc1);
+        }
+        load_X(ids0, X0);
+        det = compute_det<DIM>(X0);
+        if constexpr (MERGE) store_lists(0, blockIdx.x);  // visible to the node phase after the barrier that precedes it
+    }
     int buf = 0;
     uint32_t phases = 0u;  // bit b = parity the next wait on tile b expects
-    int np0 = 0, np1 = 0;  // MERGE: pair range of the tile about to be processed (loaded one iteration ahead)
-    if constexpr (MERGE) {
-        if ((int64_t)blockIdx.x < n_tiles) {
-            np0 = __ldg(mg.tile_ptr + blockIdx.x);
-            np1 = __ldg(mg.tile_ptr + blockIdx.x + 1);
-        }
-    }
     for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, buf ^= 1) {
         const int64_t next = tl + gridDim.x;
         if (threadIdx.x == 0 && next < n_tiles) issue(next, buf ^ 1);  // the other tile was released by the barrier below
         const int64_t c0 = tl * TILE;
         const int nc_here = (int)((n_cells - c0) < TILE ? (n_cells - c0) : TILE);
-        // MERGE: the tile's lists go to registers first (their loads overlap the coordinate loads below) and to shared
-        // memory once the determinant is done
-        constexpr int NP_IT = MERGE ? (TILE * N_PHI + 1 + NT - 1) / NT : 1, NE_IT = MERGE ? (TILE * N_PHI / 2 + NT - 1) / NT : 1;
-        uint32_t lp[NP_IT], le[NE_IT];
-        int n_pairs_here = 0, p0 = 0;
+        double X_next[DIM + 1][3];  // coordinates of the next tile's cell (its ids arrived during the previous iteration)
+        load_X(ids_next, X_next);
+        load_ids(next + gridDim.x, ids_next);
+        int pnn0 = 0, pnn1 = 0;
         if constexpr (MERGE) {
-            p0 = np0;
-            n_pairs_here = np1 - np0;
-            if (next < n_tiles) {
-                np0 = __ldg(mg.tile_ptr + next);
-                np1 = __ldg(mg.tile_ptr + next + 1);
-            }
-#pragma unroll
-            for (int j = 0; j < NP_IT; ++j) {
-                const int i = threadIdx.x + j * NT;
-                lp[j] = (i <= n_pairs_here) ? __ldg(mg.pair_ptr + p0 + i) : 0u;
-            }
-            const uint32_t *ent32 = reinterpret_cast<const uint32_t *>(mg.tile_ent + (size_t)c0 * N_PHI);  // even offset
-#pragma unroll
-            for (int j = 0; j < NE_IT; ++j) {
-                const int i = threadIdx.x + j * NT;
-                le[j] = (i < (nc_here * N_PHI) / 2) ? __ldg(ent32 + i) : 0u;
-            }
-        }
-        double det = 0.0;
-        if (lc < nc_here) {
-            double X[DIM + 1][3];
-            load_cell_coords<DIM>(coords, cell_nodes, c0 + lc, X);
-            det = compute_det<DIM>(X);
-        }
-        if constexpr (MERGE) {
-            const uint32_t e_base = (uint32_t)(c0 * N_PHI);
-#pragma unroll
-            for (int j = 0; j < NP_IT; ++j) {
-                const int i = threadIdx.x + j * NT;
-                if (i <= n_pairs_here) s_ptr[i] = (uint16_t)(lp[j] - e_base);
-            }
-#pragma unroll
-            for (int j = 0; j < NE_IT; ++j) {
-                const int i = threadIdx.x + j * NT;
-                if (i < (nc_here * N_PHI) / 2) s_ent[i] = le[j];
-            }
+            load_lists(next, pn0, pn1);
+            load_range(next + gridDim.x, pnn0, pnn1);
         }
         {  // wait for this tile's bytes
             uint32_t done = 0;
@@ -551,28 +601,21 @@ __global__ void __launch_bounds__(TILE *N_COMP)
         if ((nc_here * fn) & 1) __syncthreads();  // the odd tail element was written by thread 0 with a plain store
         if (lc < nc_here) {
             const double *fc = smem + (size_t)buf * tile_doubles + lc * fn + comp;
-            double acc[N_PHI];
-#pragma unroll
-            for (int a = 0; a < N_PHI; ++a) acc[a] = 0.0;
-            for (int q = 0; q < n_q; ++q) {
-                const double v = fc[q * N_COMP];
-#pragma unroll
-                for (int a = 0; a < N_PHI; ++a) acc[a] = fma(c_load_wt[q * N_PHI + a], v, acc[a]);
-            }
+            // the branch on `part` is warp-uniform (TILE * N_COMP is a multiple of 32) and makes the table offsets
+            // compile-time constants: the weights stay uniform constant-bank operands
+            double *dst = MERGE ? re_tile + lc * (N_PHI * N_COMP) + comp : re + (c0 + lc) * (N_PHI * comp_pitch) + comp;
+            const int pitch = MERGE ? N_COMP : comp_pitch;  // comp_pitch > N_COMP: padded node records
             const double sc = sign * det;
-            if constexpr (MERGE) {
-                double *dst = re_tile + lc * (N_PHI * N_COMP) + comp;
-#pragma unroll
-                for (int a = 0; a < N_PHI; ++a) dst[a * N_COMP] = sc * acc[a];
-            } else {
-                double *dst = re + (c0 + lc) * (N_PHI * comp_pitch) + comp;  // comp_pitch > N_COMP: padded node records
-#pragma unroll
-                for (int a = 0; a < N_PHI; ++a) dst[a * comp_pitch] = sc * acc[a];
-            }
+            if (part == 0)
+                load_sums<N_PHI, NA, N_COMP, 0>(fc, n_q, sc, dst, pitch);
+            else
+                load_sums<N_PHI, NA, N_COMP, NA>(fc, n_q, sc, dst, pitch);
         }
         if constexpr (MERGE) {
-            __syncthreads();  // the tile's local load vectors and lists are complete
-            const uint16_t *ent = reinterpret_cast<const uint16_t *>(s_ent);
+            __syncthreads();  // the tile's local load vectors (and its lists, stored an iteration ago) are complete
+            const uint16_t *s_ptr = reinterpret_cast<const uint16_t *>(lists + buf * LIST_WORDS);
+            const uint16_t *ent = reinterpret_cast<const uint16_t *>(lists + buf * LIST_WORDS + (TILE * N_PHI + 2) / 2);
+            const int n_pairs_here = pc1 - pc0;
             for (int w = threadIdx.x; w < n_pairs_here * N_COMP; w += NT) {
                 const int k = w / N_COMP, c = w - k * N_COMP;
                 const int e0 = s_ptr[k], e1 = s_ptr[k + 1];
@@ -585,9 +628,12 @@ __global__ void __launch_bounds__(TILE *N_COMP)
                     for (int u = 0; u < 4; ++u)
                         if (e + u < e1) sum += v[u];
                 }
-                mg.pair_sum[(size_t)(p0 + k) * N_COMP + c] = sum;
+                mg.pair_sum[(size_t)(pc0 + k) * N_COMP + c] = sum;
             }
+            store_lists(buf ^ 1, next);  // the next tile's lists (that buffer was last read two barriers ago)
+            pc0 = pn0, pc1 = pn1, pn0 = pnn0, pn1 = pnn1;
         }
+        det = compute_det<DIM>(X_next);
         __syncthreads();  // every reader of this tile is done: it may be refilled on the next trip
     }
 }
@@ -607,17 +653,17 @@ static int launch_h1_load_stream(int n_q, const double *tab0, const double *weig
     load_wt_kernel<<<grid_for(n_q * N_PHI, 128), 128, 0, s>>>(n_q * N_PHI, N_PHI, tab0, weights, wt);
     NFA_LAUNCH_CHECK();
     const size_t smem = sizeof(double) * 2 * (size_t)TILE * n_q * N_COMP + 16 +
-                        (MERGE ? sizeof(double) * (size_t)TILE * N_PHI * N_COMP + 2 * (TILE * N_PHI + 2) + 2 * TILE * N_PHI + 16 : 0);
+                        (MERGE ? sizeof(double) * (size_t)TILE * N_PHI * N_COMP + 2 * 4 * ((TILE * N_PHI + 2) / 2 + TILE * N_PHI / 2) : 0);
     auto kern = local_h1_load_stream_kernel<DIM, N_PHI, N_COMP, TILE, MERGE>;
     NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1, device = 0, n_sm = 148;
     NFA_CUDA(cudaGetDevice(&device));
     NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
-    NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE * N_COMP, smem));
+    NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE * N_COMP * LOAD_SPLIT, smem));
     if (per_sm < 1) return fail("nfa_local_h1_load: streaming kernel does not fit on an SM");
     const int64_t tiles = (n_cells + TILE - 1) / TILE;
     const int grid = (int)std::min<int64_t>(tiles, (int64_t)n_sm * per_sm);
-    kern<<<grid, TILE * N_COMP, smem, s>>>(n_q, coords, cell_nodes, n_cells, f, sign, re, comp_pitch, mg);
+    kern<<<grid, TILE * N_COMP * LOAD_SPLIT, smem, s>>>(n_q, coords, cell_nodes, n_cells, f, sign, re, comp_pitch, mg);
     NFA_LAUNCH_CHECK();
     return 0;
 }
@@ -625,10 +671,12 @@ static int launch_h1_load_stream(int n_q, const double *tab0, const double *weig
 // second pass of the tile-merged load: row N_COMP N + c = sum of node N's pair sums in ascending tile order
 template <int NC>
 __global__ void __launch_bounds__(256)
-    pair_gather_kernel(int64_t n_nodes, const int32_t *__restrict__ node_pair_ptr, const uint32_t *__restrict__ node_pair,
-                       const double *__restrict__ pair_sum, int overwrite, double *__restrict__ rhs) {
-    const int64_t N = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (N >= n_nodes) return;
+    pair_gather_kernel(int64_t n_active, const int32_t *__restrict__ active, const int32_t *__restrict__ node_pair_ptr,
+                       const uint32_t *__restrict__ node_pair, const double *__restrict__ pair_sum, int overwrite,
+                       double *__restrict__ rhs) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_active) return;
+    const int64_t N = active ? active[t] : t;  // (the list is the identity when every node has cells)
     const int32_t b = node_pair_ptr[N], e = node_pair_ptr[N + 1];
     double acc[NC];
 #pragma unroll
@@ -662,13 +710,15 @@ extern "C" int nfa_bplan_load_rhs(const nfa_bplan *bp, int dim, int n_q, const d
     else
         return fail("nfa_bplan_load_rhs: vector P2 / P1 on tetrahedra and vector P2 on triangles only");
     if (rc) return rc;
-    const unsigned grid = (unsigned)grid_for(bp->n_nodes, 256);
+    // only the nodes that have cells are visited: a rank's local plan (global numbering) leaves the other ranks' rows alone
+    const unsigned grid = (unsigned)grid_for(bp->n_active, 256);
+    const int32_t *act = bp->n_active == bp->n_nodes ? nullptr : (const int32_t *)bp->active_nodes.p;
     const int32_t *npp = (const int32_t *)bp->node_pair_ptr.p;
     const uint32_t *np = (const uint32_t *)bp->node_pair.p;
     if (bp->n_comp == 3)
-        pair_gather_kernel<3><<<grid, 256, 0, s>>>(bp->n_nodes, npp, np, (const double *)bp->pair_sum.p, overwrite, rhs);
+        pair_gather_kernel<3><<<grid, 256, 0, s>>>(bp->n_active, act, npp, np, (const double *)bp->pair_sum.p, overwrite, rhs);
     else
-        pair_gather_kernel<2><<<grid, 256, 0, s>>>(bp->n_nodes, npp, np, (const double *)bp->pair_sum.p, overwrite, rhs);
+        pair_gather_kernel<2><<<grid, 256, 0, s>>>(bp->n_active, act, npp, np, (const double *)bp->pair_sum.p, overwrite, rhs);
     NFA_LAUNCH_CHECK();
     return 0;
 }

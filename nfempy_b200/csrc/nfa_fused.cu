@@ -150,6 +150,11 @@ __global__ void pair_node_keys(const uint64_t *__restrict__ ukeys, int64_t n, in
     ids[p] = (uint32_t)p;
 }
 
+__global__ void nonempty_flags(const int32_t *__restrict__ ptr, int64_t n, uint8_t *__restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = ptr[i + 1] > ptr[i] ? 1 : 0;
+}
+
 __global__ void node_ptr_kernel(const uint32_t *__restrict__ sorted_keys, int64_t n, int64_t n_nodes,
                                 int32_t *__restrict__ node_ptr) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,6 +238,7 @@ __global__ void scalar_pattern(const int32_t *__restrict__ bptr, const int32_t *
 }  // namespace
 
 extern "C" void nfa_bplan_destroy(nfa_bplan *bp) { delete bp; }
+extern "C" int64_t nfa_bplan_n_active_nodes(const nfa_bplan *bp) { return bp ? bp->n_active : -1; }
 extern "C" int64_t nfa_bplan_nnz(const nfa_bplan *bp) { return bp ? bp->n_bnz * bp->n_comp * bp->n_comp : -1; }
 extern "C" int64_t nfa_bplan_bytes(const nfa_bplan *bp) {
     if (!bp) return -1;
@@ -469,7 +475,19 @@ extern "C" int nfa_bplan_create(int64_t n_nodes, int n_phi, int n_comp, const in
         if (cub::DeviceRadixSort::SortPairs(tmp.p, tb3, pk, pk_alt, pi, pi_out, (int)P, 0, nbits, s) != cudaSuccess)
             return bail(fail("nfa_bplan_create: pair sort failed"));
         node_ptr_kernel<<<grid_for(n_nodes + 1, 256), 256, 0, s>>>(pk_alt, P, n_nodes, (int32_t *)bp->node_pair_ptr.p);
-        count_launch(24);
+        // the nodes that have cells at all (a rank's local plan numbers the GLOBAL nodes: the per-step kernels walk this list)
+        DevBuf fl, na;
+        if (fl.alloc(n_nodes) || na.alloc(sizeof(int)) || bp->active_nodes.alloc(4 * n_nodes)) return bail(2);
+        nonempty_flags<<<grid_for(n_nodes, 256), 256, 0, s>>>((const int32_t *)bp->node_pair_ptr.p, n_nodes, (uint8_t *)fl.p);
+        cub::CountingInputIterator<int32_t> iota(0);
+        cub::DeviceSelect::Flagged(nullptr, tb3, iota, (uint8_t *)fl.p, (int32_t *)bp->active_nodes.p, (int *)na.p, (int)n_nodes, s);
+        if (tmp.alloc(tb3)) return bail(2);
+        cub::DeviceSelect::Flagged(tmp.p, tb3, iota, (uint8_t *)fl.p, (int32_t *)bp->active_nodes.p, (int *)na.p, (int)n_nodes, s);
+        int h_active = 0;
+        cudaMemcpyAsync(&h_active, na.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (cudaStreamSynchronize(s) != cudaSuccess) return bail(fail("nfa_bplan_create: active node list failed"));
+        bp->n_active = h_active;
+        count_launch(27);
         if (cudaStreamSynchronize(s) != cudaSuccess) return bail(fail("nfa_bplan_create: tile-merged load lists failed"));
     }
     // ---- scalar CSR pattern

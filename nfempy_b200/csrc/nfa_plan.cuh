@@ -86,6 +86,8 @@ struct nfa_bplan {
     nfa::DevBuf node_pair_ptr;    // int32 [n_nodes + 1]
     nfa::DevBuf node_pair;        // uint32 [n_pairs]
     nfa::DevBuf pair_sum;         // scratch: double [n_pairs][n_comp], rewritten every assembly
+    int64_t n_active = 0;         // nodes with at least one cell (all of them on one GPU; a rank's share when sharded)
+    nfa::DevBuf active_nodes;     // int32 [n_active], ascending
     // Row-item lists of the vector-P2 tetrahedron kernel (nfa_p2tet.cu), built by nfempy_b200/assembly/p2_items.py
     struct P2Items {
         int64_t n_chunks = 0, n_tasks = 0, n_items = 0, ell_size = 0;

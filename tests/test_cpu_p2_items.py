@@ -145,3 +145,26 @@ def test_balanced_split_covers_the_chunks_and_evens_out_the_work():
     split = p2_items.balanced_split(plan, 4).numpy()
     per = np.array([cost[split[b] : split[b + 1]].sum() for b in range(4)])
     assert per.max() - per.min() <= 2 * cost.max()  # within the granularity of whole chunks
+
+
+def test_item_plan_without_the_entries_of_dead_cells():
+    """``cell_live``: the halo cells of a rank's plan contribute zeros; their entries are cut from the lists, the items stay."""
+    mesh, space, s, node_dest, n_nodes, cell_nodes = _setup(2)
+    bptr, bcols, keys = _block_csr(node_dest, n_nodes)
+    rng = np.random.default_rng(11)
+    n = len(node_dest)
+    lam, mu = 1.0 + rng.random(n), 0.5 + rng.random(n)
+    live = rng.random(n) > 0.3
+    live[:6] = False  # a whole cube of dead cells: some items keep no entry at all
+    full = p2_items.build(torch.as_tensor(node_dest), torch.as_tensor(bptr), torch.as_tensor(bcols), n_nodes, cap=64, riffle=3)
+    plan = p2_items.build(torch.as_tensor(node_dest), torch.as_tensor(bptr), torch.as_tensor(bcols), n_nodes, cap=64, riffle=3,
+                          cell_live=torch.as_tensor(live))
+    assert plan["n_items"] == full["n_items"] and plan["n_entries"] < full["n_entries"]
+    ell = plan["ell"].numpy().astype(np.int64) & p2_items.NONE32
+    used = ell[ell != p2_items.NONE32] >> 6
+    assert live[used].all(), "an entry of a dead cell survived"
+    rec = p2_items.geometry_records(mesh.points, cell_nodes, lam, mu)
+    got = p2_items.walk(plan, rec, len(keys))
+    assert not np.isnan(got).any(), "some CSR block was never written"
+    ref = _brute_force(space, s, mesh, node_dest, n_nodes, cell_nodes, keys, bptr, np.where(live, lam, 0.0), np.where(live, mu, 0.0))
+    assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()

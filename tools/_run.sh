@@ -1,6 +1,5 @@
 set -x
-python -m pytest tests/test_gpu_parity.py -x -q > gpurun_out/r5_tests2.log 2>&1; echo "tests rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:"local_h1_load|pair_gather" -c 4 --csv --log-file gpurun_out/r5_l1.csv python bench.py --no-cpu --no-e2e --no-varying --steps 2 --warmup 1 --no-graph > /dev/null 2>&1
-NFA_DEBUG_NONODE=1 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:"local_h1_load|pair_gather" -c 4 --csv --log-file gpurun_out/r5_l2.csv python bench.py --no-cpu --no-e2e --no-varying --steps 2 --warmup 1 --no-graph > /dev/null 2>&1
-grep -v "^==" gpurun_out/r5_l1.csv | cut -d, -f5,15- | head -6
-grep -v "^==" gpurun_out/r5_l2.csv | cut -d, -f5,15- | head -6
+python -m pytest tests/test_gpu_sharding.py -x -q > gpurun_out/r6_tests_sh.log 2>&1; echo "tests rc=$?"
+tail -n 3 gpurun_out/r6_tests_sh.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 --no-e2e --no-cpu > gpurun_out/r6_bench_2gpu_c.json 2> gpurun_out/r6_bench_2gpu_c.err; echo rc=$?
+tail -c 300 gpurun_out/r6_bench_2gpu_c.err
