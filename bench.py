@@ -477,7 +477,7 @@ def run_graft(args):
     e2e = e2e_all = None
     if not args.no_e2e:
         e2e_all = run_e2e(args, torch, dist, world, device, asm, state, form, n_cells,
-                          (lambda: sharded.rhs) if sharded is not None else (lambda: rhs_dev), step)
+                          (lambda: sharded.rhs) if sharded is not None else (lambda: rhs_dev), step, sharded)
         # N = 1: the headline end-to-end number goes through the drop-in API call itself; N > 1: the sharded step with
         # host buffers (there is no multi-process form of the reference's API to mirror)
         e2e = run_e2e_api(args, torch, device, space, form, n_cells, asm) if sharded is None else e2e_all
@@ -626,32 +626,47 @@ def run_e2e_api(args, torch, device, space, form, n_cells, asm):
             "first_call_s": first_call_s, "timings_last_call": api.last_timings}
 
 
-def run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, asm_rhs, assemble_step):
+def run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, asm_rhs, assemble_step, sharded=None):
     """Same step, host buffers in and out: pinned coords / connectivity / coefficient / load arrays are copied to
-    the device every step and the CSR values + rhs are copied back."""
-    from nfempy_b200 import _lib
-
+    the device every step and the CSR values + rhs are copied back.  N > 1: a rank ships ITS share only -- the coordinates
+    of the mesh nodes its cells use go up, the rows it owns (CSR segments + rhs entries, a few contiguous row blocks) come
+    down; the arrays stay global-sized on the device, the PCIe traffic does not."""
     dev, entries, datas, dests, plan, key = state
     data = datas[0]
+    if sharded is None:
+        node_lo, node_hi = 0, int(dev.coords.shape[0])
+        row_blocks = [(0, plan.n_dof)]
+    else:
+        used = torch.unique(data.cell_nodes)
+        node_lo, node_hi = int(used.min().item()), int(used.max().item()) + 1
+        row_blocks = sharded.shard.row_block_ranges()
+        if len(row_blocks) > 64:  # (not the case for slab partitions: one block per entity class)
+            row_blocks = [(0, plan.n_dof)]
+    indptr = plan.indptr.cpu().numpy()
+    val_blocks = [(int(indptr[a]), int(indptr[b])) for a, b in row_blocks]
+    coords_dev = dev.coords[node_lo:node_hi]
     host_in = {
-        "coords": dev.coords.cpu().pin_memory(), "cell_nodes": data.cell_nodes.cpu().pin_memory(),
+        "coords": coords_dev.cpu().pin_memory(), "cell_nodes": data.cell_nodes.cpu().pin_memory(),
         "f": data.f.cpu().pin_memory(), "lambda": data.coefs["lambda"][0].cpu().pin_memory(),
         "mu": data.coefs["mu"][0].cpu().pin_memory(),
     }
-    host_vals = torch.empty(plan.nnz, dtype=torch.float64).pin_memory()
-    host_rhs = torch.empty(plan.n_dof, dtype=torch.float64).pin_memory()
+    host_vals = [torch.empty(b - a, dtype=torch.float64).pin_memory() for a, b in val_blocks]
+    host_rhs = [torch.empty(b - a, dtype=torch.float64).pin_memory() for a, b in row_blocks]
     h2d = sum(t.numel() * t.element_size() for t in host_in.values())
-    d2h = host_vals.numel() * 8 + host_rhs.numel() * 8
+    d2h = sum(t.numel() * 8 for t in host_vals) + sum(t.numel() * 8 for t in host_rhs)
 
     def step():
-        dev.coords.copy_(host_in["coords"], non_blocking=True)
+        coords_dev.copy_(host_in["coords"], non_blocking=True)
         data.cell_nodes.copy_(host_in["cell_nodes"], non_blocking=True)
         data.f.copy_(host_in["f"], non_blocking=True)
         data.coefs["lambda"][0].copy_(host_in["lambda"], non_blocking=True)
         data.coefs["mu"][0].copy_(host_in["mu"], non_blocking=True)
-        assemble_step()  # same step as the device-resident measurement (incl. the NCCL exchange at N > 1)
-        host_vals.copy_(asm.jacobian.values_dev, non_blocking=True)
-        host_rhs.copy_(asm_rhs(), non_blocking=True)
+        assemble_step()  # same step as the device-resident measurement (incl. the interface exchange at N > 1)
+        vals_dev, rhs_dev = asm.jacobian.values_dev, asm_rhs()
+        for (a, b), h in zip(val_blocks, host_vals):
+            h.copy_(vals_dev[a:b], non_blocking=True)
+        for (a, b), h in zip(row_blocks, host_rhs):
+            h.copy_(rhs_dev[a:b], non_blocking=True)
 
     steps = max(3, min(args.steps, 5))
     step()
@@ -670,7 +685,8 @@ def run_e2e(args, torch, dist, world, device, asm, state, form, n_cells, asm_rhs
     ms = float(t.item()) / steps
     return {"value": n_cells * world / (ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": ms, "steps": steps,
-            "call": "every input array re-uploaded from pinned host memory, kernels, CSR values + rhs downloaded"}
+            "call": "every input array re-uploaded from pinned host memory, kernels, CSR values + rhs downloaded"
+                    + ("" if sharded is None else " (per rank: its cells' inputs up, the %d row blocks it owns down)" % len(row_blocks))}
 
 
 if __name__ == "__main__":
