@@ -186,6 +186,21 @@ int nfa_plan_reduce(const nfa_plan *plan, const double *const *d_Ke, const doubl
 int nfa_csr_spmv(const nfa_plan *plan, const double *d_vals, const double *d_x, int accumulate, double *d_y,
                  nfa_stream stream);
 
+/* ---- streamed scatter (csrc/nfa_stream.cu): "full"-pattern assembly of forms whose local matrices cannot all be resident
+ * (BASELINE config 4: LCEScaledDualWeakForm at BDM_3 x RT_3 x P_2 x P_2, 348 local dofs, R/src/weak_forms/
+ * lce_scaled_dual_weak_form.py:445-699) in spaces where a dof belongs to at most two cells.  The CSR position of the local
+ * entry (cell, a, b) is d_indptr[d_dest[cell][a]] + (d_tabs[d_tab_of[cell][a]][b] & 0x7fff): a rank table per cell (cell-
+ * local rows: rank inside the cell's sorted dofs) and per ordered (cell, partner) pair (rank inside the sorted union of
+ * both cells' dofs).  Bit 15 of a table entry: the entry is ADDED in pass 1 (the row's lower cell stored it in pass 0);
+ * clear: STORED in pass 0.  Chunks of cells in ascending order, pass 0 then pass 1 for every chunk: each value is the sum
+ * of its at most two contributions in ascending cell order (R/src/assembly/ScatterFormData.py:5-11), no atomics.
+ * d_indptr is int64 (such matrices exceed 2^31 stored entries).  nfa_rows_copy_i32 fills the column indices: row r
+ * receives d_src[d_src_off[r] ..) (its cell's sorted dofs or its pair's sorted union). */
+int nfa_stream_scatter(int64_t n_cells, int n_loc, const int32_t *d_dest, const int32_t *d_tab_of, const uint16_t *d_tabs,
+                       const int64_t *d_indptr, const double *d_Ke, double *d_vals, int pass, nfa_stream stream);
+int nfa_rows_copy_i32(int64_t n_rows, const int64_t *d_indptr, const int64_t *d_src_off, const int32_t *d_src,
+                      int32_t *d_out, nfa_stream stream);
+
 /* ---- K8 multi-GPU interface rows: after the local reduce a rank holds partial sums on rows owned by a
  * lower rank.  nfa_pack_rows copies the CSR segments of `rows` (int32 global row ids, ascending) into a contiguous
  * send buffer (buf_off[k] = prefix sum of the row lengths, int64); the owner calls nfa_unpack_add_rows on the

@@ -64,6 +64,8 @@ SIGNATURES = {
     "nfa_p2p_close": (_i, [_vp]),
     "nfa_p2p_free": (_i, [_vp]),
     "nfa_p2p_timeouts": (_i64, []),
+    "nfa_stream_scatter": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "nfa_rows_copy_i32": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "nfa_push_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_pull_add_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_bplan_gather_load": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
