@@ -129,6 +129,26 @@ def build_tables(dest, n_dof, pair_batch=32768):
             "src_off": src_off, "n_pairs": n_pairs, "nnz": int(indptr[-1].item())}
 
 
+def partition_cells(dest, world, rank):
+    """Contiguous cell ranges with replicated halo cells instead of an exchange: rank ``r`` owns the cells
+    ``[bounds[r], bounds[r+1])`` and assembles them TOGETHER with the cells that share a dof with them (at most one layer
+    across a partition face: a dof belongs to at most two cells), so that every row its own cells touch is complete on the
+    rank -- no interface sums, no collective.  A row belongs to the rank of the lowest cell that touches it (first-touch,
+    like ``assembly/sharding.py``).  Returns ``(cells to assemble (ascending), owned rows (ascending), (c0, c1))``."""
+    dest = np.asarray(dest)
+    n_cells = len(dest)
+    bounds = [(n_cells * r) // world for r in range(world + 1)]
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    n_dof = int(dest.max()) + 1
+    mine = np.zeros(n_dof, dtype=bool)
+    mine[dest[c0:c1].reshape(-1)] = True
+    touching = np.flatnonzero(mine[dest].any(axis=1))  # own cells + their neighbours across shared dofs
+    first_cell = np.full(n_dof, n_cells, dtype=np.int64)
+    np.minimum.at(first_cell, dest[touching].reshape(-1), np.repeat(touching, dest.shape[1]))
+    owned = np.flatnonzero(mine & (first_cell >= c0) & (first_cell < c1))
+    return touching.astype(np.int64), owned, (c0, c1)
+
+
 class StreamedCSR:
     """Device CSR with 64-bit row pointers.  ``rows(r0, r1)`` copies a row block to the host (scipy-ready triple)."""
 
@@ -150,8 +170,13 @@ class StreamedAssembler:
     ``form`` over all cells plus ``bc_form`` entries that carry no matrix (natural boundary conditions).  ``assemble()``
     returns ``(StreamedCSR, rhs device tensor)``; ``stats`` holds the times of the stages."""
 
-    def __init__(self, space, device=None, chunk_cells=2048):
+    def __init__(self, space, device=None, chunk_cells=2048, cells=None):
+        """``cells`` (ascending global cell ids, optional): assemble these cells only -- one rank's share of a partitioned
+        mesh, see ``partition_cells``.  Rows and columns keep the global numbering."""
         self.space, self.device, self.chunk_cells = space, device, int(chunk_cells)
+        self.cells = None if cells is None else np.ascontiguousarray(cells, dtype=np.int64)
+        if self.cells is not None and len(self.cells) > 1 and not np.all(np.diff(self.cells) > 0):
+            raise ValueError("StreamedAssembler: cells must be ascending and distinct")
         self.form_to_input_list = {}
         self.stats = {}
         self._tables = None
@@ -187,7 +212,10 @@ class StreamedAssembler:
         if n_dof > 2**31 - 1:
             raise NotImplementedError("StreamedAssembler: more than 2^31 dofs")
         t0 = time.perf_counter()
-        dest64 = torch.as_tensor(np.ascontiguousarray(form.dest_table(), dtype=np.int64)).to(dev.device)
+        dest_host = np.asarray(form.dest_table(), dtype=np.int64)
+        cell_ids = np.arange(len(dest_host), dtype=np.int64) if self.cells is None else self.cells
+        dest64 = torch.as_tensor(np.ascontiguousarray(dest_host[cell_ids])).to(dev.device)
+        del dest_host
         n_cells, n_loc = int(dest64.shape[0]), int(dest64.shape[1])
         if self._tables is None:
             self._tables = build_tables(dest64, n_dof)
@@ -210,7 +238,7 @@ class StreamedAssembler:
         for c0 in range(0, n_cells, self.chunk_cells):
             c1 = min(n_cells, c0 + self.chunk_cells)
             tp = time.perf_counter()
-            data = form.prepare(dev, np.arange(c0, c1, dtype=np.int64))  # host callables over the chunk's points, upload
+            data = form.prepare(dev, cell_ids[c0:c1])  # host callables over the chunk's points, upload
             torch.cuda.synchronize(dev.device)
             t_prepare += time.perf_counter() - tp
             dchunk = dest[c0:c1]

@@ -32,8 +32,10 @@ __device__ __forceinline__ double levi_civita(int a, int b, int c) {
     return ((b - a + 3) % 3 == 1) ? 1.0 : -1.0;  // (a, b, c) cyclic -> +1
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(128)
+// THREADS: 128 for elements whose staged bases leave room for several CTAs per SM; 512 for the large ones (BDM_3 x RT_3
+// stages 125 KB per CTA: one CTA per SM, which with 128 threads would be four warps per SM)
+template <int DIM, int THREADS>
+__global__ void __launch_bounds__(THREADS)
     local_hdiv_tensor_kernel(const nfa_tensor_form P, int n_qc, const double *__restrict__ coords,
                              const int32_t *__restrict__ cell_nodes, int64_t n_cells, const double *__restrict__ alpha,
                              const int32_t *__restrict__ dest, double *__restrict__ Ke, double *__restrict__ re) {
@@ -295,20 +297,26 @@ __global__ void __launch_bounds__(128)
         }
         }  // quadrature chunks
         __syncthreads();  // K of this cell is complete in global memory for the row products below
-        for (int row = threadIdx.x; row < n_loc; row += blockDim.x) {
+        // one warp per row: the lanes stride the row of K (coalesced) and the partial products meet in a shuffle tree
+        for (int row = threadIdx.x >> 5; row < n_loc; row += blockDim.x >> 5) {
+            const int lane = threadIdx.x & 31;
             double acc = 0.0;
-            if (alpha && dest)
-                for (int c = 0; c < n_loc; ++c) acc += K[row * n_loc + c] * s_a[c];
+            if (alpha && dest) {
+                for (int c = lane; c < n_loc; c += 32) acc = fma(K[row * n_loc + c], s_a[c], acc);
+            }
             if (row >= off_l[0]) {
                 const int l = (P.n_l2 > 1 && row >= off_l[1]) ? 1 : 0;
                 const int r = row - off_l[l], k = r / P.l_n_comp[l], c = r - k * P.l_n_comp[l];
                 const double *ld = P.l_load[l];
                 if (ld) {
                     const int np = P.l_n_phi[l], ncp = P.l_n_comp[l];
-                    for (int q = 0; q < n_q_all; ++q)
+                    for (int q = lane; q < n_q_all; q += 32)
                         acc -= P.weights[q] * g.det * ld[(cell * (int64_t)n_q_all + q) * ncp + c] * P.l_val[l][q * np + k];
                 }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane != 0) continue;
             re[cell * n_loc + row] = acc;
         }
     }
@@ -347,15 +355,14 @@ extern "C" int nfa_local_hdiv_tensor(const nfa_tensor_form *form, const double *
     n_qc = (P.n_q + n_chunks - 1) / n_chunks;
     const size_t smem = sizeof(double) * (fixed + per_q * (size_t)n_qc);
     const int grid = (int)(n_cells < 148 * 8 ? n_cells : 148 * 8);
-    if (P.dim == 3) {
-        auto kern = local_hdiv_tensor_kernel<3>;
-        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 128, smem, s>>>(P, n_qc, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
-    } else {
-        auto kern = local_hdiv_tensor_kernel<2>;
-        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 128, smem, s>>>(P, n_qc, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
-    }
+    // CTAs that stage more than 56 KB leave room for at most three per SM: they run 512 threads instead of 128
+    const bool big = smem > 56 * 1024;
+    using kern_t = void (*)(const nfa_tensor_form, int, const double *, const int32_t *, int64_t, const double *,
+                            const int32_t *, double *, double *);
+    kern_t kern = P.dim == 3 ? (big ? (kern_t)local_hdiv_tensor_kernel<3, 512> : (kern_t)local_hdiv_tensor_kernel<3, 128>)
+                             : (big ? (kern_t)local_hdiv_tensor_kernel<2, 512> : (kern_t)local_hdiv_tensor_kernel<2, 128>);
+    NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, big ? 512 : 128, smem, s>>>(P, n_qc, coords, cell_nodes, n_cells, alpha, dest, Ke, re);
     NFA_LAUNCH_CHECK();
     return 0;
 }

@@ -79,3 +79,22 @@ def test_a_dof_in_three_cells_is_refused():
     dest = torch.as_tensor(np.asarray(space.destination_table(), dtype=np.int64))
     with pytest.raises(NotImplementedError):
         build_tables(dest, int(space.n_dof))
+
+
+def test_partition_with_replicated_halo_cells():
+    """Every row a rank's own cells touch has all of its cells on that rank; the owned rows partition the dofs."""
+    from nfempy_b200.assembly.streamed import partition_cells
+
+    space = _space(3, 1, 3)
+    dest = np.asarray(space.destination_table(), dtype=np.int64)
+    owned_all = []
+    for r in range(3):
+        cells, owned, (c0, c1) = partition_cells(dest, 3, r)
+        assert np.all(np.diff(cells) > 0) and set(range(c0, c1)) <= set(cells.tolist())
+        rows = np.unique(dest[c0:c1])
+        touching = np.flatnonzero(np.isin(dest, rows).any(axis=1))
+        assert set(touching.tolist()) <= set(cells.tolist())
+        assert np.isin(owned, rows).all()
+        owned_all.append(owned)
+    u = np.concatenate(owned_all)
+    assert len(u) == len(np.unique(u)) == space.n_dof

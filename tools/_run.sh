@@ -1,3 +1,4 @@
 set -x
-python -m pytest tests/test_gpu_streamed.py -x -q > gpurun_out/r7_tests_stream.log 2>&1; echo "tests rc=$?"
-tail -n 25 gpurun_out/r7_tests_stream.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/bench_config4.py --n 8 --chunk 512 > gpurun_out/r7_config4_2gpu_small.jsonl 2> gpurun_out/r7_config4_2gpu_small.err; echo rc=$?
+grep -v "NCCL\|^$\|OMP_NUM\|\*\*\*" gpurun_out/r7_config4_2gpu_small.err | tail -n 12
+cut -c1-900 gpurun_out/r7_config4_2gpu_small.jsonl
