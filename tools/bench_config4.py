@@ -6,7 +6,7 @@ One JSON line: sizes, stage times (CUDA events around the local kernel and the s
 local kernel against the measured DFMA peak, scatter bandwidth against the measured copy bandwidth, and two checks that
 do not depend on the size: (a) sampled rows against local matrices recomputed for just their cells, (b) every row sum
 against the scattered row sums of the local matrices.
-Run on the GPU box:  python tools/bench_config4.py --n 23 > gpurun_out/config4.jsonl"""
+Run on the GPU box:  python tools/bench_config4.py --box 23 > gpurun_out/config4.jsonl"""
 import argparse
 import json
 import os
@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=23, help="box of n^3 cubes, 6 tets each (23 -> 73 002 tets)")
+    ap.add_argument("--box", dest="n", type=int, default=23, help="box of n^3 cubes, 6 tets each (23 -> 73 002 tets)")
     ap.add_argument("--chunk", type=int, default=2048)
     ap.add_argument("--k", type=int, default=3)
     ap.add_argument("--samples", type=int, default=12)
