@@ -462,7 +462,7 @@ def run_graft(args):
     achieved = b_kernel * n_cells / (kernel_ms * 1e-3) / 1e9
     traffic = None  # DRAM bytes per launch from the committed ncu --set full capture of this exact workload
     row_items = bool(getattr(plan, "p2_stats", None))
-    tpath = os.path.join(ROOT, "profiles", "r01_p2tet_traffic.json" if row_items else "r01_fused_h1_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_p2tet_traffic.json" if row_items else "r01_fused_h1_traffic.json")
     if os.path.exists(tpath) and args.n == 55 and world == 1:
         traffic = json.load(open(tpath))["traffic_bytes_per_launch"]
     roofline = {

@@ -1,7 +1,7 @@
 """ORACLE (test infrastructure only -- never imported by the product path).
 
-H(div) pieces of the basix stand-in, written independently of ``nfempy_b200.basis.hdiv`` (numerical quadrature +
-``numpy.linalg.solve`` here, exact rational arithmetic there):
+H(div) pieces of the basix stand-in, written independently of ``nfempy_b200.basis.hdiv`` (numerical quadrature, moments
+snapped to their exact rationals and a 60-digit solve here; exact rational arithmetic from the start there):
 
 * ``tabulate``                -- RT_k (k = 1..3) / BDM_1..3 values and reference derivatives, ``[1+dim, nq, nphi, dim]``;
 * ``entity_transformations``  -- signed permutations of the facet dof families, as explicit tables;
@@ -62,14 +62,47 @@ def _cubic_lattice(fdim):
     return np.array(nodes)
 
 
+_CUBIC = {}
+
+
+def _cubic_family_coefficients(fdim):
+    """Monomial coefficients [n_mono, n_nodes] of the cubic nodal family on the lattice, exact (entries are k / 2)."""
+    if fdim not in _CUBIC:
+        from fractions import Fraction
+
+        exps = _monomials(fdim, 3)
+        nodes = [[Fraction(int(round(3 * float(c))), 3) for c in x] for x in _cubic_lattice(fdim)]
+        n = len(exps)
+        A = [[Fraction(1)] * 0 for _ in range(n)]
+        for i, x in enumerate(nodes):
+            A[i] = [Fraction(1) for _ in exps]
+            for m, e in enumerate(exps):
+                v = Fraction(1)
+                for c, p in zip(x, e):
+                    v *= c ** p
+                A[i][m] = v
+        # Gauss-Jordan on [A | I]
+        aug = [row + [Fraction(int(i == j)) for j in range(n)] for i, row in enumerate(A)]
+        for col in range(n):
+            piv = next(r for r in range(col, n) if aug[r][col] != 0)
+            aug[col], aug[piv] = aug[piv], aug[col]
+            pv = aug[col][col]
+            aug[col] = [v / pv for v in aug[col]]
+            for r in range(n):
+                if r != col and aug[r][col] != 0:
+                    f = aug[r][col]
+                    aug[r] = [a - f * b for a, b in zip(aug[r], aug[col])]
+        _CUBIC[fdim] = np.array([[float(aug[i][n + j]) for j in range(n)] for i in range(n)])
+    return _CUBIC[fdim]
+
+
 def _facet_family(fdim, degree, s):
     """Nodal Lagrange family of ``degree`` on the reference facet at parameter points ``s`` -> [nq, n]."""
     if fdim == 0:
         return np.ones((len(s), 1))
-    if degree == 3:  # BDM_3: equispaced cubic family, by a numerical Vandermonde solve
+    if degree == 3:  # BDM_3: equispaced cubic family; the Vandermonde matrix of the lattice is inverted in rationals
         exps = _monomials(fdim, 3)
-        V, _ = _mono_tab(exps, _cubic_lattice(fdim))
-        return _mono_tab(exps, s)[0] @ np.linalg.inv(V)
+        return _mono_tab(exps, s)[0] @ _cubic_family_coefficients(fdim)
     return ref_basis.tabulate_lagrange(fdim, degree, s)[0, :, :, 0]
 
 
@@ -100,6 +133,30 @@ def _nedelec2(dim, pts):
 
 
 _CACHE = {}
+
+# Every entry of the dual matrix is a moment of a polynomial with integer (cubic facet family: half-integer) coefficients
+# over the reference simplex or one of its facets: a rational whose denominator divides (degree + dim)! times those few
+# factors.  The Gauss-Jacobi rules reproduce the moments to ~1e-16, so each entry can be snapped to the exact rational
+# (asserted unambiguous) and the system solved in 60-digit arithmetic: the basis coefficients are then correct to the last
+# bit of a double, instead of carrying the 1e-11 the condition number of a 60 x 60 float solve leaves (BDM_3).
+_DENOM = 362880 * 16 * 27  # 9! * 2^4 * 3^3
+
+
+def _solve_dual(D):
+    import mpmath
+
+    scaled = D * _DENOM
+    snapped = np.rint(scaled)
+    if np.abs(scaled - snapped).max() > 1e-4:
+        raise AssertionError("oracle H(div) element: a dual-matrix moment is not a multiple of 1 / %d" % _DENOM)
+    old = mpmath.mp.dps
+    mpmath.mp.dps = 60
+    try:
+        M = mpmath.matrix([[mpmath.mpf(int(v)) / _DENOM for v in row] for row in snapped])
+        Ci = mpmath.inverse(M)
+        return np.array([[float(Ci[i, j]) for j in range(Ci.cols)] for i in range(Ci.rows)])
+    finally:
+        mpmath.mp.dps = old
 
 
 def _element(family, dim, k):
@@ -172,7 +229,7 @@ def _element(family, dim, k):
     elif family == "BDM" and k > 3:
         raise NotImplementedError("oracle BDM degree >= 4")
     D = np.array(rows)  # D[i, s]
-    C = np.linalg.solve(D, np.eye(len(D)))  # phi_j = sum_s C[s, j] space_s
+    C = _solve_dual(D)  # phi_j = sum_s C[s, j] space_s
     coeffs = np.einsum("sj,scm->jcm", C, space)
     entity_dofs = [[[] for _ in SUB[dim][d]] for d in range(dim + 1)]
     for i, (d, e) in enumerate(entity):

@@ -52,7 +52,7 @@ def multi_cases():
     return {
         "lce_primal": (lce_primal_case(dim=2, k=2, kt=1, varying=True, alpha=True, mesh=mesh), 1e-12),
         "taylor_hood": (taylor_hood_case(varying=True, alpha=True, mesh=mesh), 1e-12),
-        "mixed_poisson_bdm3": (mixed_poisson_case(dim=2, k=3, family="BDM", varying=True, mesh=mesh), 1e-10),
+        "mixed_poisson_bdm3": (mixed_poisson_case(dim=2, k=3, family="BDM", varying=True, mesh=mesh), 1e-12),
         "lce_dual_neumann": (tensor_mixed_case(kind="lce", dim=2, s_family="BDM", m_family="RT", k=1, mesh=mesh,
                                                neumann=True), 1e-12),
     }

@@ -22,10 +22,9 @@ def test_tables_match_oracle_and_layout(family, dim, k):
     el = create_element(family, dim, k)
     pts, _ = make_quadrature(dim, 2 * k + 1)
     a, b = el.tabulate(1, pts), ref_hdiv.tabulate(family, dim, k, pts)
-    # the product inverts its dual matrix in exact rationals, the oracle numerically: for the 60 x 60 system of BDM_3 on
-    # the tetrahedron the ORACLE is the less accurate side (about 1e-13 of the largest value)
-    tol = 1e-12 if (family, dim, k) == ("BDM", 3, 3) else 1e-13
-    assert np.abs(a - b).max() <= tol * np.abs(b).max()
+    # the product builds its dual matrix in exact rationals; the oracle snaps its quadrature moments to the exact
+    # rationals and solves in 60-digit arithmetic (oracle/ref_hdiv.py _solve_dual): both are correct to the last bits
+    assert np.abs(a - b).max() <= 1e-14 * np.abs(b).max()
     assert el.num_entity_dofs == ref_basis.num_entity_dofs(family, dim, k, False)
     assert el.entity_dofs == ref_hdiv.entity_dofs(family, dim, k)
     assert not el.dof_transformations_are_identity

@@ -26,7 +26,7 @@ def test_mixed_poisson_bdm(dim, k):
     against the degree-2 Nedelec space; its oracle inverts a 20 x 20 / 60 x 60 dual matrix numerically and is the less accurate
     side (see tests/test_cpu_hdiv.py), hence the wider tolerance for that case."""
     case = mixed_poisson_case(dim=dim, k=k, n=2 if k == 1 else (1 if dim == 3 else 2), family="BDM", varying=(k == 3))
-    compare_csr(case.run_gpu(), case.run_oracle(), 1e-10 if k == 3 else RTOL)
+    compare_csr(case.run_gpu(), case.run_oracle(), RTOL)
 
 
 def test_mixed_poisson_varying_kappa_no_bc():
@@ -127,4 +127,4 @@ def test_mass_block_on_the_fp64_tensor_cores(dim, k, family, monkeypatch):
     case = mixed_poisson_case(dim=dim, k=k, n=1 if dim == 3 else 2, family=family, varying=True)
     ref = case.run_oracle()
     monkeypatch.setenv("NFA_HDIV_MMA", "1")
-    compare_csr(case.run_gpu(), ref, 1e-10 if (family, k) == ("BDM", 3) else RTOL)
+    compare_csr(case.run_gpu(), ref, RTOL)
