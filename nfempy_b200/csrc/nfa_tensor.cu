@@ -54,8 +54,10 @@ __global__ void __launch_bounds__(THREADS)
         const int np = h < P.n_hdiv ? P.h_n_phi[h] : 0;
         s_psi[h] = cur;
         cur += (size_t)n_q * np * DIM;  // mapped values [q][a][c]
-        s_div[h] = cur;
-        cur += (size_t)n_q * np;  // physical divergence [q][a]
+        // physical divergence [q][a]: only the plain div-div term reads it (Riesz maps); the dual forms stage nothing here
+        const bool need_div = h < P.n_hdiv && P.h_a_dd[h] != nullptr && !P.h_dd_general[h];
+        s_div[h] = need_div ? cur : nullptr;
+        cur += need_div ? (size_t)n_q * np : 0;
         s_gd[h] = cur;
         cur += (size_t)n_q * np;  // generalised divergence x det [q][a]
         off_h[h] = n_loc;
@@ -149,15 +151,21 @@ __global__ void __launch_bounds__(THREADS)
                     s_psi[h][(q * np + j) * DIM + c] = v;
                     if (gv) gd += g.det * gv[(cq_base + q) * DIM + c] * v;
                 }
-                s_div[h][q * np + j] = dh * idet;
+                if (s_div[h]) s_div[h][q * np + j] = dh * idet;
                 s_gd[h][q * np + j] = gd;
             }
         }
         __syncthreads();
+        if (pair_pass && q0 == 0) {
+            // everything outside the blocks written below (stress-stress of one field, couplings, L2 masses) is structurally
+            // zero: one coalesced sweep instead of a decode-and-test per entry
+            for (int e = threadIdx.x; e < n_loc * n_loc; e += blockDim.x) K[e] = 0.0;
+            __syncthreads();
+        }
         if (pair_pass) {
             for (int h = 0; h < P.n_hdiv; ++h) {
                 const int np = P.h_n_phi[h], n_pairs = np * (np + 1) / 2;
-                const double *dd = P.h_dd_general[h] ? s_gd[h] : s_div[h];
+                const double *dd = (P.h_dd_general[h] || !s_div[h]) ? s_gd[h] : s_div[h];  // (unused without a_dd: cq[3] = 0)
                 const double dds = P.h_dd_general[h] ? idet : 1.0;  // s_gd carries det (cd div psi + g.psi)
                 const double *cqh = s_cq + (size_t)h * n_q * 4;
                 for (int pr = threadIdx.x; pr < n_pairs; pr += blockDim.x) {
@@ -206,7 +214,78 @@ __global__ void __launch_bounds__(THREADS)
                 }
             }
         }
-        for (int e = threadIdx.x; e < n_loc * n_loc; e += blockDim.x) {
+        if (pair_pass) {
+            // L2 x H(div) couplings, one (L2 basis k, H(div) basis a) product per thread: the divergence coupling is one
+            // number for the DIM equal-component entries, the asymmetry coupling one vector B_d = int w det phi_k psi_a[d]
+            // placed with the Levi-Civita signs; both blocks (and their transposes) are written from registers
+            for (int l = 0; l < P.n_l2; ++l)
+                for (int h = 0; h < P.n_hdiv; ++h) {
+                    const bool dv = P.div_coupling[l][h] != 0, as = P.asym_coupling[l][h] != 0;
+                    if (!dv && !as) continue;
+                    const int npl = P.l_n_phi[l], nph = P.h_n_phi[h], ncl = P.l_n_comp[l];
+                    const double *lv = P.l_val[l] + (size_t)q0 * npl;
+                    for (int it = threadIdx.x; it < npl * nph; it += blockDim.x) {
+                        const int k = it / nph, a = it - k * nph;
+                        double cdiv = 0.0, B[DIM];
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d) B[d] = 0.0;
+                        for (int q = 0; q < nq; ++q) {
+                            const double lvq = lv[q * npl + k];
+                            if (dv) cdiv += P.weights[q0 + q] * lvq * s_gd[h][q * nph + a];
+                            if (as) {
+                                const double wl = s_wd[q] * lvq;
+#pragma unroll
+                                for (int d = 0; d < DIM; ++d) B[d] += wl * s_psi[h][(q * nph + a) * DIM + d];
+                            }
+                        }
+                        for (int lc = 0; lc < ncl; ++lc)
+                            for (int hc = 0; hc < DIM; ++hc) {
+                                double v = 0.0;
+                                bool any = false;
+                                if (dv && lc == hc) {
+                                    v = cdiv;
+                                    any = true;
+                                }
+                                if (as) {
+                                    const int ce = ncl == 1 ? 2 : lc;  // the single rotation of a 2-D problem is the z one
+                                    double t = 0.0;
+                                    for (int d = 0; d < DIM; ++d) {
+                                        const double eps = levi_civita(ce, hc, d);
+                                        if (eps != 0.0) t += eps * B[d];
+                                    }
+                                    v += t;
+                                    any = true;
+                                }
+                                if (!any) continue;  // stays the structural zero
+                                const int rl = off_l[l] + k * ncl + lc, ch = off_h[h] + a * DIM + hc;
+                                if (q0 == 0) {
+                                    K[rl * n_loc + ch] = v;
+                                    K[ch * n_loc + rl] = v;
+                                } else {
+                                    K[rl * n_loc + ch] += v;
+                                    K[ch * n_loc + rl] += v;
+                                }
+                            }
+                    }
+                }
+            // L2 masses: one (k, k') product per thread, repeated on the component diagonal
+            for (int l = 0; l < P.n_l2; ++l) {
+                const double *am = P.l_a_mass[l];
+                if (!am) continue;
+                const int npl = P.l_n_phi[l], ncl = P.l_n_comp[l];
+                const double *lv = P.l_val[l] + (size_t)q0 * npl;
+                for (int it = threadIdx.x; it < npl * npl; it += blockDim.x) {
+                    const int k = it / npl, k2 = it - k * npl;
+                    double m = 0.0;
+                    for (int q = 0; q < nq; ++q) m += s_wd[q] * am[cq_base + q] * lv[q * npl + k] * lv[q * npl + k2];
+                    for (int c = 0; c < ncl; ++c) {
+                        const int e = (off_l[l] + k * ncl + c) * n_loc + off_l[l] + k2 * ncl + c;
+                        K[e] = q0 == 0 ? m : K[e] + m;
+                    }
+                }
+            }
+        }
+        for (int e = pair_pass ? n_loc * n_loc : threadIdx.x; e < n_loc * n_loc; e += blockDim.x) {
             int row = e / n_loc, col = e - row * n_loc;
             // decode (kind, field, basis, comp)
             int rk, rf, ra, rc, ck, cf, ca, cc;
@@ -337,7 +416,8 @@ extern "C" int nfa_local_hdiv_tensor(const nfa_tensor_form *form, const double *
     int n_loc = 0;
     for (int h = 0; h < P.n_hdiv; ++h) {
         if (!P.h_val[h] || !P.h_div[h] || !P.h_Tcases[h] || !P.h_cases[h]) return fail("nfa_local_hdiv_tensor: H(div) tables missing");
-        per_q += (size_t)P.h_n_phi[h] * (P.dim + 2);
+        const bool need_div = P.h_a_dd[h] != nullptr && !P.h_dd_general[h];
+        per_q += (size_t)P.h_n_phi[h] * (P.dim + 1 + (need_div ? 1 : 0));
         fixed += (size_t)(P.dim + 1) * P.h_nfd[h] * P.h_nfd[h];
         n_loc += P.h_n_phi[h] * P.h_n_comp[h];
     }
@@ -346,8 +426,8 @@ extern "C" int nfa_local_hdiv_tensor(const nfa_tensor_form *form, const double *
         n_loc += P.l_n_phi[l] * P.l_n_comp[l];
     }
     fixed += n_loc;
-    // all points at once when the staged bases fit in 200 KB of shared memory, else equal chunks of points
-    const size_t budget = 200 * 1024 / sizeof(double);
+    // all points at once when the staged bases fit in shared memory, else equal chunks of points
+    const size_t budget = 222 * 1024 / sizeof(double);  // of the 227 KB a CTA may have
     if (fixed + per_q > budget) return fail("nfa_local_hdiv_tensor: element too large for the shared-memory staging");
     int n_qc = (int)std::min<size_t>((size_t)P.n_q, (budget - fixed) / per_q);
     if (const char *e = getenv("NFA_TENSOR_QCHUNK")) n_qc = std::max(1, std::min(n_qc, atoi(e)));  // tests

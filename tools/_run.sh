@@ -1,4 +1,6 @@
 set -x
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r8_bench_2gpu_full.json 2> gpurun_out/r8_bench_2gpu_full.err; echo rc=$?
-grep -v "NCCL\|^$\|OMP_NUM\|\*\*\*" gpurun_out/r8_bench_2gpu_full.err | tail -n 8
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r8_bench_2gpu_ref.json 2> gpurun_out/r8_bench_2gpu_ref.err; echo rc=$?
+python -m pytest tests/test_gpu_tensor_forms.py tests/test_gpu_streamed.py tests/test_gpu_golden.py -x -q > gpurun_out/r9_tests_tensor.log 2>&1; echo "tests rc=$?"
+tail -n 4 gpurun_out/r9_tests_tensor.log
+timeout 1500 python tools/bench_config4.py --box 23 --chunk 2048 > gpurun_out/r9_config4.jsonl 2> gpurun_out/r9_config4.err; echo rc=$?
+tail -n 5 gpurun_out/r9_config4.err
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"local_hdiv_tensor" -s 1 -c 1 -o gpurun_out/r9_tensor -f python tools/bench_config4.py --box 8 --chunk 1024 > gpurun_out/r9_ncu_tensor.log 2>&1
