@@ -66,6 +66,14 @@ SIGNATURES = {
     "nfa_p2p_timeouts": (_i64, []),
     "nfa_stream_scatter": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "nfa_rows_copy_i32": (_i, [_i64, _vp, _vp, _vp, _vp, _vp]),
+    "nfa_hdiv_rt1_records": (
+        _i,
+        [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _d,
+         _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
+    ),
+    "nfa_rows_locate": (_i, [_i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "nfa_rows_expand": (_i, [_i64, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "nfa_plan_from_csr": (_i, [_i64, _i64, _vp, _vp, ctypes.POINTER(_vp)]),
     "nfa_push_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_pull_add_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_bplan_gather_load": (_i, [_vp, _vp, _i, _i, _vp, _vp]),

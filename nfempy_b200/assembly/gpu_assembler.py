@@ -21,6 +21,7 @@ import torch
 from .. import _lib
 from ..device import space_device
 from ..weak_forms.weak_form import BatchedWeakForm
+from . import hdiv_rows
 from .csr_matrix import CSRMatrix
 
 _SUPPORTED = ("form", "bc_form", "time_dependent_form", "time_dependent_bc_form", "interface_form")
@@ -66,10 +67,16 @@ def _primary_space(form):
     return form.space
 
 
+class _RowsUnavailable(Exception):
+    """The row-owner path does not apply to this form list (a dof with more than two items, rows outside the direct
+    forms' ranges): the list takes the generic two-stage plan."""
+
+
 class _Plan:
     """Owns the native plan handles of one form list."""
 
     def __init__(self):
+        self.rows = None  # row-owner path: {segment index: tables}, see _build_row_plan
         self.plan = None  # nfa_plan* with gather lists
         self.pattern = None  # nfa_plan* adopting the block plan's pattern (fused mode)
         self.bplan = None
@@ -132,6 +139,7 @@ class GPUAssembler:
         self._rhs_host = None
         self._state_bufs = []
         self._capturing = False
+        self._rows_refused = None
 
     def invalidate(self):
         """Drops the cached coefficient arrays (the sparsity plans stay)."""
@@ -201,7 +209,7 @@ class GPUAssembler:
                         None if items is None else items.tobytes()))
         return tuple(key)
 
-    def _build_plan(self, dev, entries, dests, fused_index):
+    def _build_plan(self, dev, entries, dests, fused_index, direct=None, datas=None):
         t0 = time.perf_counter()
         lib = _lib.load()
         p = _Plan()
@@ -213,6 +221,11 @@ class GPUAssembler:
         n_items = (ctypes.c_int64 * nseg)(*[int(d.shape[0]) for d in dests])
         n_loc = (ctypes.c_int32 * nseg)(*[int(d.shape[1]) for d in dests])
         handle = ctypes.c_void_p()
+        if direct:
+            self._build_row_plan(lib, dev, p, entries, dests, datas, direct, dest_ptrs, n_items, n_loc, stream)
+            torch.cuda.synchronize(dev.device)
+            p.build_seconds = time.perf_counter() - t0
+            return p
         if fused_index is None:
             _lib.check(
                 lib.nfa_plan_create(p.n_dof, nseg, dest_ptrs, n_items, n_loc, None, None, ctypes.byref(handle), stream),
@@ -264,6 +277,65 @@ class GPUAssembler:
         torch.cuda.synchronize(dev.device)
         p.build_seconds = time.perf_counter() - t0
         return p
+
+    @staticmethod
+    def _build_row_plan(lib, dev, p, entries, dests, datas, direct, dest_ptrs, n_items, n_loc, stream):
+        """Plan of a form list whose volume forms ``direct`` are assembled by row owner: (1) the CSR of the WHOLE list
+        (every segment's pairs, so boundary / coupling forms may add columns), (2) per direct segment the rows' sources and
+        the CSR slot of every local column (``nfa_rows_locate``), (3) gather lists of the other segments merged into the
+        CSR.  The direct segments' row ranges must tile ``[0, n_dof)``: every value is then written by exactly one row
+        thread before the other segments add to it."""
+        nseg = len(entries)
+        # row sources first (cheap, and the test that decides whether the path applies at all)
+        rows, ranges = {}, []
+        for i in direct:
+            d = dests[i]
+            lo, hi = int(d.min().item()), int(d.max().item()) + 1
+            src = hdiv_rows.row_sources(d, lo, hi)
+            if src is None:
+                raise _RowsUnavailable()
+            rows[i] = {"lo": lo, "hi": hi, "src": src}
+            ranges.append((lo, hi))
+        ranges.sort()
+        if ranges[0][0] != 0 or ranges[-1][1] != p.n_dof or any(a[1] != b[0] for a, b in zip(ranges, ranges[1:])):
+            raise _RowsUnavailable()
+        h0 = ctypes.c_void_p()
+        flags = (ctypes.c_int32 * nseg)(*([3] * nseg))  # matrix pairs of every segment, no right-hand-side lists
+        _lib.check(lib.nfa_plan_create(p.n_dof, nseg, dest_ptrs, n_items, n_loc, flags, None, ctypes.byref(h0), stream),
+                   "nfa_plan_create")
+        try:
+            p.nnz = int(lib.nfa_plan_nnz(h0))
+            p.indptr = torch.empty(p.n_dof + 1, dtype=torch.int32, device=dev.device)
+            p.indices = torch.empty(p.nnz, dtype=torch.int32, device=dev.device)
+            _lib.check(lib.nfa_plan_csr(h0, _lib.ptr(p.indptr), _lib.ptr(p.indices), stream), "nfa_plan_csr")
+            torch.cuda.synchronize(dev.device)
+        finally:
+            lib.nfa_plan_destroy(h0)
+        row_len = p.indptr[1:] - p.indptr[:-1]
+        for i in direct:
+            t = rows[i]
+            form, data = entries[i][3], datas[i]
+            spec = form.row_spec(data)
+            nl = int(dests[i].shape[1])
+            t["max_len"] = int(row_len[t["lo"]:t["hi"]].max().item())
+            if t["max_len"] > 256 or t["max_len"] * 8 * 256 > 200 * 1024:
+                raise _RowsUnavailable()
+            t["slots"] = torch.empty((t["hi"] - t["lo"], 2, nl), dtype=torch.uint8, device=dev.device)
+            _lib.check(lib.nfa_rows_locate(t["lo"], t["hi"], _lib.ptr(p.indptr), _lib.ptr(p.indices), _lib.ptr(t["src"]), nl,
+                                           _lib.ptr(dests[i]), _lib.ptr(t["slots"]), stream), "nfa_rows_locate")
+            t["emap"] = torch.as_tensor(np.ascontiguousarray(spec["emap"], dtype=np.int16)).to(dev.device)
+            t["ridx"] = torch.as_tensor(np.ascontiguousarray(spec["ridx"], dtype=np.int16)).to(dev.device)
+            t["stride"], t["n_loc"] = int(spec["stride"]), nl
+        p.rows = rows
+        ph = ctypes.c_void_p()
+        _lib.check(lib.nfa_plan_from_csr(p.n_dof, p.nnz, _lib.ptr(p.indptr), _lib.ptr(p.indices), ctypes.byref(ph)),
+                   "nfa_plan_from_csr")
+        p.pattern = ph
+        flags = (ctypes.c_int32 * nseg)(*[2 if i in rows else 1 for i in range(nseg)])  # direct: no lists at all
+        handle = ctypes.c_void_p()
+        _lib.check(lib.nfa_plan_create(p.n_dof, nseg, dest_ptrs, n_items, n_loc, flags, ph, ctypes.byref(handle), stream),
+                   "nfa_plan_create")
+        p.plan = handle
 
     @staticmethod
     def _attach_p2_items(lib, dev, p, node_dest, stream, cell_live=None):
@@ -420,10 +492,22 @@ class GPUAssembler:
                 if kind == "form" and form.fused_spec(data) is not None and len(self.space.discrete_spaces) == 1:
                     fused_index = i
                     break
-        key = self._plan_key(entries, fused_index)
+        # lowest-order H(div) x L2 volume forms: records + row-owner expansion instead of local matrices (hdiv_rows.py)
+        direct = None
+        if fused_index is None and self.allow_fused and os.environ.get("NFA_HDIV_ROWS", "1") != "0" \
+                and self._rows_refused != self._plan_key(entries, None):
+            direct = tuple(i for i, ((_, kind, _, form, _), data) in enumerate(zip(entries, datas))
+                           if kind in ("form", "time_dependent_form") and hasattr(form, "row_spec")
+                           and form.row_spec(data) is not None) or None
+        key = self._plan_key(entries, fused_index if direct is None else ("rows",) + direct)
         if key not in self._plans:
             try:
-                self._plans[key] = self._build_plan(dev, entries, dests, fused_index)
+                self._plans[key] = self._build_plan(dev, entries, dests, fused_index, direct, datas)
+            except _RowsUnavailable:
+                self._rows_refused = self._plan_key(entries, None)
+                key = self._rows_refused
+                if key not in self._plans:
+                    self._plans[key] = self._build_plan(dev, entries, dests, None)
             except _lib.NfaError:
                 if fused_index is None:
                     raise
@@ -492,6 +576,8 @@ class GPUAssembler:
             overwrite = fresh and bool(plan.p2_stats.get("all_rows_nonempty"))
         else:
             overwrite = fresh and has_load  # nfa_bplan_gather_load writes every row (zeros for nodes without cells)
+        if plan.rows:  # the row threads write every right-hand-side row of a fresh buffer themselves
+            overwrite = fresh
         self.last_rhs_fill = fresh and not overwrite  # a torch fill kernel ran (launch accounting)
         if rhs_dev is None:
             rhs_dev = (torch.empty if (overwrite and not rows_only) else torch.zeros)(plan.n_dof, dtype=torch.float64, device=dev.device)
@@ -499,7 +585,11 @@ class GPUAssembler:
             rhs_dev.zero_()
         nseg = len(entries)
         Ke_list, re_list, keep = [None] * nseg, [None] * nseg, []
+        if plan.rows:
+            keep += self._run_rows(lib, dev, plan, entries, datas, dests, jac, rhs_dev, 0 if overwrite else 1, stream)
         for i, ((_, kind, _, form, alpha), data, dest) in enumerate(zip(entries, datas, dests)):
+            if plan.rows and i in plan.rows:
+                continue
             if "time_dependent" in kind:
                 first_dev, second_dev = data.alpha_dev
                 nl = form.n_loc()
@@ -565,7 +655,7 @@ class GPUAssembler:
                 keep += [Ke, re, alpha_dev]
         ke_ptrs = (ctypes.c_void_p * nseg)(*[None if k is None else k.data_ptr() for k in Ke_list])
         re_ptrs = (ctypes.c_void_p * nseg)(*[None if r is None else r.data_ptr() for r in re_list])
-        accumulate_vals = 0 if (jac.is_zero and plan.fused_index is None) else 1
+        accumulate_vals = 0 if (jac.is_zero and plan.fused_index is None and not plan.rows) else 1
         if any(k is not None for k in Ke_list) or any(r is not None for r in re_list):
             _lib.check(
                 lib.nfa_plan_reduce(plan.plan, ke_ptrs, re_ptrs, accumulate_vals, _lib.ptr(jac.values_dev), 1, _lib.ptr(rhs_dev), stream),
@@ -574,6 +664,30 @@ class GPUAssembler:
         jac.is_zero = False
         self._keep = keep  # buffers must outlive the stream-ordered kernels
         return rhs_dev
+
+    def _run_rows(self, lib, dev, plan, entries, datas, dests, jac, rhs_dev, rhs_add, stream):
+        """Row-owner segments (hdiv_rows.py): records kernel of the form, then one thread per matrix row.  The rows kernel
+        OVERWRITES the CSR values of its rows; values assembled earlier are kept by expanding into a scratch array first."""
+        target = jac.values_dev if jac.is_zero else torch.empty_like(jac.values_dev)
+        keep = []
+        for i, t in plan.rows.items():
+            (_, kind, _, form, _), data, dest = entries[i], datas[i], dests[i]
+            if "time_dependent" in kind:
+                first_dev, second_dev = data.alpha_dev
+            else:
+                first_dev = data.alpha_dev if (self._capturing or not data.alpha_zero) else None
+                second_dev = None
+            rec = torch.empty((data.n_items, t["stride"]), dtype=torch.float64, device=dev.device)
+            form.launch_records(data.dev, data, first_dev, second_dev, dest, rec, t["stride"])
+            _lib.check(lib.nfa_rows_expand(t["lo"], t["hi"], t["max_len"], _lib.ptr(plan.indptr), _lib.ptr(t["src"]),
+                                           _lib.ptr(t["slots"]), t["n_loc"], _lib.ptr(t["emap"]), _lib.ptr(t["ridx"]),
+                                           _lib.ptr(rec), t["stride"], _lib.ptr(target), _lib.ptr(rhs_dev), rhs_add, stream),
+                       "nfa_rows_expand")
+            keep += [rec, first_dev, second_dev]
+        if target is not jac.values_dev:
+            jac.values_dev.add_(target)
+        jac.is_zero = False
+        return keep
 
     @staticmethod
     def _folds_load(lib, plan, entries, datas):

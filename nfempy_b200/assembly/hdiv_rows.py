@@ -1,0 +1,82 @@
+"""Row-owner assembly of lowest-order H(div) x L2 forms (``csrc/nfa_hdivrows.cu``): the host side.
+
+``LaplaceDualWeakForm`` on RT_1 x P_0 (BASELINE config 3 at k = 1) and ``SundusDualWeakForm`` on RT_1 x RT_1 x P_0 x P_0
+(config 5) take this path inside ``GPUAssembler`` when the pattern policy is "full": the form's ``row_spec`` describes a
+compact per-cell record and which record entry feeds local entry (a, b); one thread per cell writes the records, one thread
+per matrix row expands them into the CSR (lower cell first: the order of the reference's ``Mat.setValue(..., addv=True)``
+calls, R/src/assembly/ScatterFormData.py:5-11).  Works in spaces where a dof belongs to at most two items of the form
+(facet dofs of H(div) fields, cell-local dofs).  Boundary / coupling forms of the same list go through the generic plan,
+merged into the same CSR.
+"""
+import numpy as np
+import torch
+
+
+def row_sources(dest, row_lo, row_hi):
+    """``int32 [row_hi - row_lo, 2]``: the one or two sources of every row in ``[row_lo, row_hi)`` as
+    ``item * 32 + local row`` (``-1`` = none), lower item first.  ``dest``: integer tensor ``[n_items, n_loc]`` of global
+    dofs (any device).  Returns ``None`` when a dof belongs to more than two items or is listed twice by one item."""
+    n_items, n_loc = int(dest.shape[0]), int(dest.shape[1])
+    if n_loc > 32 or n_items >= 2**26:
+        return None
+    flat = dest.reshape(-1).to(torch.int64)
+    if int(flat.min().item()) < row_lo or int(flat.max().item()) >= row_hi:
+        return None
+    order = torch.argsort(flat, stable=True)  # ascending dof; ascending (item, local row) inside a dof
+    sd = flat[order]
+    first = torch.ones_like(sd, dtype=torch.bool)
+    first[1:] = sd[1:] != sd[:-1]
+    start = torch.nonzero(first).reshape(-1)
+    count = torch.cat([start[1:], torch.tensor([sd.shape[0]], device=sd.device)]) - start
+    if int(count.max().item()) > 2:
+        return None
+    item = torch.div(order, n_loc, rounding_mode="floor")
+    code = (item * 32 + (order - item * n_loc)).to(torch.int32)
+    two = count == 2
+    if bool((item[start[two]] == item[start[two] + 1]).any()):
+        return None
+    src = torch.full((row_hi - row_lo, 2), -1, dtype=torch.int32, device=dest.device)
+    rows = sd[start] - row_lo
+    src[rows, 0] = code[start]
+    src[rows[two], 1] = code[start[two] + 1]
+    return src.contiguous()
+
+
+def sundus_maps(n_u):
+    """Record layout of ``nfa_hdiv_rt1_records`` (form 1) as the tables ``nfa_rows_expand`` reads: local order
+    [mp | mc | p | c]; ``emap[a, b]`` = +-(record index + 1) or 0 for a structural zero, ``ridx[a]`` = residual entry."""
+    roww, n_loc = n_u + 2, 2 * n_u + 2
+    soff = 2 * n_u * roww
+    emap = np.zeros((n_loc, n_loc), dtype=np.int16)
+    ridx = np.zeros(n_loc, dtype=np.int16)
+    for F in range(2):
+        s_col = 2 * n_u + F  # the scalar field paired with flux field F
+        for a in range(n_u):
+            base = (F * n_u + a) * roww
+            for b in range(n_u):
+                emap[F * n_u + a, F * n_u + b] = base + b + 1  # flux mass
+            emap[F * n_u + a, s_col] = -(base + n_u + 1)  # -(w, div psi_a)
+            emap[s_col, F * n_u + a] = base + n_u + 1  # +(div psi_a, w)
+            ridx[F * n_u + a] = base + n_u + 1
+        emap[s_col, s_col] = soff + F + 1  # time derivative (+ reaction tangent on c)
+        ridx[s_col] = soff + 2 + F
+    stride = (soff + 4 + 3) // 4 * 4
+    return emap, ridx, stride
+
+
+def laplace_dual_maps(n_u):
+    """The same for the mixed Poisson form (form 0), local order [u | p]; the (p, p) entry is a structural zero."""
+    roww, n_loc = n_u + 2, n_u + 1
+    soff = n_u * roww
+    emap = np.zeros((n_loc, n_loc), dtype=np.int16)
+    ridx = np.zeros(n_loc, dtype=np.int16)
+    for a in range(n_u):
+        base = a * roww
+        for b in range(n_u):
+            emap[a, b] = base + b + 1
+        emap[a, n_u] = -(base + n_u + 1)
+        emap[n_u, a] = base + n_u + 1
+        ridx[a] = base + n_u + 1
+    ridx[n_u] = soff
+    stride = (soff + 1 + 3) // 4 * 4
+    return emap, ridx, stride

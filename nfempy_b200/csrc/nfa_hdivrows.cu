@@ -1,0 +1,371 @@
+// libnfa: lowest-order H(div) x L2 forms assembled by ROW OWNER, without local matrices in HBM (sm_100a).
+//
+// Forms: LaplaceDualWeakForm on RT_1 x P_0 (BASELINE config 3 at k = 1, R/src/weak_forms/laplace_dual_weak_form.py:10-87)
+// and SundusDualWeakForm on RT_1 x RT_1 x P_0 x P_0 (config 5, R/examples/parabolic_diffusive_problem/SundusWeakForm.py:
+// 11-177).  The two-stage path writes a dense n_loc x n_loc block per cell (800 B for the 10 x 10 Sundus block, most of it
+// structural zeros) and reads it back through a sorted 32-bit id per entry; its local kernel gives a cell to 8 lanes that
+// diverge over four kinds of work.  Here
+//   1. rt1_records_kernel: ONE THREAD PER CELL, every accumulator in registers, no divergence: the cell's distinct numbers
+//      -- per flux row a: M[a][0..n_u), C[a], r[a]; then the L2 diagonal entries and residuals -- form a record of
+//      (n_flux n_u (n_u + 2) + 4) doubles (416 B instead of 800 + 80), transposed through shared memory so that the
+//      records leave the SM as full lines;
+//   2. rows_expand_kernel: ONE THREAD PER MATRIX ROW.  In these spaces a dof belongs to at most two cells; the row's thread
+//      reads the record rows of its one or two (cell, local row) sources, places the entries at their CSR slots (uint8 per
+//      (row, side, local column), found once by nfa_rows_locate in the plan's CSR, whatever other forms added to the
+//      pattern) inside a shared-memory image of 256 consecutive CSR rows, lower cell first -- the order of the reference's
+//      Mat.setValue(..., addv=True) calls (R/src/assembly/ScatterFormData.py:5-11) -- and the block writes the image to
+//      HBM with coalesced stores.  Every CSR value of the rows is written exactly once (explicit zeros included), the
+//      right-hand side row is the sum of its one or two record entries: no atomics, no zero fill, bit-reproducible.
+// Which record entry feeds local entry (a, b) is a table (emap: 0 = structural zero, +-(index + 1)) supplied by the host
+// form, so rows_expand_kernel is form-independent.
+#include <algorithm>
+
+#include "nfa_common.cuh"
+
+using namespace nfa;
+
+namespace {
+
+struct CoefR {
+    const double *p;
+    int64_t sc, sq;
+};
+
+constexpr int REC_CELLS = 128;  // cells per CTA pass of the records kernel
+constexpr int ROWS_PER_CTA = 256;
+
+// FORM 0: mixed Poisson [u | p]; FORM 1: Sundus [mp | mc | p | c]
+template <int DIM, int FORM>
+__global__ void __launch_bounds__(REC_CELLS)
+    rt1_records_kernel(int n_q, const double *__restrict__ u_val, const double *__restrict__ u_div,
+                       const double *__restrict__ p_val, const double *__restrict__ weights,
+                       const double *__restrict__ Tcases, const int8_t *__restrict__ cases,
+                       const double *__restrict__ coords, const int32_t *__restrict__ cell_nodes, int64_t n_cells,
+                       CoefR kappa, CoefR delta, CoefR eta, double inv_dt, const double *__restrict__ f_f,
+                       const double *__restrict__ f_r, const double *__restrict__ alpha,
+                       const double *__restrict__ alpha_prev, const int32_t *__restrict__ dest, int stride,
+                       double *__restrict__ rec) {
+    constexpr int NU = DIM + 1, NS = NU * (NU + 1) / 2, NFLUX = FORM == 1 ? 2 : 1;
+    constexpr int NLOC = NFLUX * NU + NFLUX;
+    constexpr int ROWW = NU + 2;             // M[a][0..NU), C[a], r[a]
+    constexpr int SOFF = NFLUX * NU * ROWW;  // scalars: FORM 0: r_p; FORM 1: K_pp, K_cc, r_p, r_c
+    constexpr int USED = SOFF + (FORM == 1 ? 4 : 1);
+    extern __shared__ double sm[];
+    double *s_val = sm;                       // [n_q][NU][DIM]
+    double *s_div = s_val + n_q * NU * DIM;   // [n_q][NU]
+    double *s_pw = s_div + n_q * NU;          // [n_q]
+    double *s_w = s_pw + n_q;                 // [n_q]
+    double *s_rec = s_w + n_q;                // [REC_CELLS][pitch]
+    const int pitch = stride | 1;             // odd pitch: the threads' record rows start in distinct banks
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_q * NU * DIM; i += REC_CELLS) s_val[i] = u_val[i];
+    for (int i = tid; i < n_q * NU; i += REC_CELLS) s_div[i] = u_div[i];
+    for (int i = tid; i < n_q; i += REC_CELLS) {
+        s_pw[i] = p_val[i];
+        s_w[i] = weights[i];
+    }
+    __syncthreads();
+    for (int64_t c0 = (int64_t)blockIdx.x * REC_CELLS; c0 < n_cells; c0 += (int64_t)gridDim.x * REC_CELLS) {
+        const int64_t cell = c0 + tid;
+        double *R = s_rec + tid * pitch;
+        if (cell < n_cells) {
+            double X[DIM + 1][3];
+            load_cell_coords<DIM>(coords, cell_nodes, cell, X);
+            Geom<DIM> g;
+            compute_geom<DIM>(X, g);
+            const double det = g.det, idet = 1.0 / g.det;
+            double sgn[NU];
+#pragma unroll
+            for (int a = 0; a < NU; ++a) sgn[a] = __ldg(Tcases + (int)cases[cell * NU + a]);  // 1 x 1 orientation matrices
+            // state of the cell (Sundus): the scalar fields' local coefficients now (the reaction term needs c_h inside the
+            // point loop), the flux coefficients after the loop (registers)
+            double a_s[NFLUX], an_s[NFLUX];
+#pragma unroll
+            for (int F = 0; F < NFLUX; ++F) a_s[F] = an_s[F] = 0.0;
+            if (FORM == 1) {
+                const int32_t *d = dest + cell * NLOC;
+#pragma unroll
+                for (int F = 0; F < NFLUX; ++F) {
+                    if (alpha) a_s[F] = __ldg(alpha + d[NFLUX * NU + F]);
+                    if (alpha_prev) an_s[F] = __ldg(alpha_prev + d[NFLUX * NU + F]);
+                }
+            }
+            double M[NFLUX][NS], C[NU];
+#pragma unroll
+            for (int F = 0; F < NFLUX; ++F)
+#pragma unroll
+                for (int t = 0; t < NS; ++t) M[F][t] = 0.0;
+#pragma unroll
+            for (int a = 0; a < NU; ++a) C[a] = 0.0;
+            double W2 = 0.0, Wc = 0.0, Ff = 0.0, Rc = 0.0;
+            for (int q = 0; q < n_q; ++q) {
+                const double wd = s_w[q] * det;
+                double wt[NFLUX];
+                wt[0] = wd * (1.0 / kappa.p[cell * kappa.sc + q * kappa.sq]);
+                if (FORM == 1) wt[NFLUX - 1] = wd * (1.0 / delta.p[cell * delta.sc + q * delta.sq]);
+                double psi[NU][DIM];
+#pragma unroll
+                for (int a = 0; a < NU; ++a)
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) v += g.J[c][k] * s_val[(q * NU + a) * DIM + k];
+                        psi[a][c] = (v * idet) * sgn[a];
+                    }
+                int t = 0;
+#pragma unroll
+                for (int a = 0; a < NU; ++a)
+#pragma unroll
+                    for (int b = a; b < NU; ++b) {
+                        double dot = 0.0;
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) dot += psi[a][c] * psi[b][c];
+#pragma unroll
+                        for (int F = 0; F < NFLUX; ++F) M[F][t] = fma(wt[F], dot, M[F][t]);
+                        ++t;
+                    }
+                const double pw = s_pw[q], wp = wd * pw;
+#pragma unroll
+                for (int a = 0; a < NU; ++a) C[a] = fma(wp, (s_div[q * NU + a] * idet) * sgn[a], C[a]);
+                W2 = fma(wp, pw, W2);
+                if (FORM == 1) {
+                    const double et = eta.p[cell * eta.sc + q * eta.sq], ch = a_s[NFLUX - 1] * pw;
+                    Wc = fma(wp * pw, et * ch, Wc);
+                    Ff = fma(wp, f_f ? f_f[cell * n_q + q] : 0.0, Ff);
+                    Rc = fma(wp, 1.0 + et * ch * ch - (f_r ? f_r[cell * n_q + q] : 0.0), Rc);
+                } else {
+                    Ff = fma(wp, f_f ? f_f[cell * n_q + q] : 0.0, Ff);
+                }
+            }
+            double a_f[NFLUX][NU];
+#pragma unroll
+            for (int F = 0; F < NFLUX; ++F)
+#pragma unroll
+                for (int a = 0; a < NU; ++a) a_f[F][a] = (FORM == 1 && alpha) ? __ldg(alpha + dest[cell * NLOC + F * NU + a]) : 0.0;
+            // record rows of the flux dofs: M[a][.], C[a], r[a]
+#pragma unroll
+            for (int F = 0; F < NFLUX; ++F)
+#pragma unroll
+                for (int a = 0; a < NU; ++a) {
+                    double r = 0.0;
+#pragma unroll
+                    for (int b = 0; b < NU; ++b) {
+                        const int lo = a < b ? a : b, hi = a < b ? b : a;
+                        const double m = M[F][lo * NU - lo * (lo - 1) / 2 + (hi - lo)];
+                        R[(F * NU + a) * ROWW + b] = m;
+                        r = fma(m, a_f[F][b], r);
+                    }
+                    R[(F * NU + a) * ROWW + NU] = C[a];
+                    R[(F * NU + a) * ROWW + NU + 1] = FORM == 1 ? r - a_s[F] * C[a] : 0.0;
+                }
+            if (FORM == 1) {
+                const double app = inv_dt * W2;
+                double dmp = 0.0, dmc = 0.0;
+#pragma unroll
+                for (int a = 0; a < NU; ++a) {
+                    dmp = fma(a_f[0][a], C[a], dmp);
+                    dmc = fma(a_f[NFLUX - 1][a], C[a], dmc);
+                }
+                R[SOFF + 0] = app;
+                R[SOFF + 1] = app + 2.0 * Wc;
+                R[SOFF + 2] = (a_s[0] - an_s[0]) * app + dmp - Ff;
+                R[SOFF + 3] = (a_s[NFLUX - 1] - an_s[NFLUX - 1]) * app + dmc + Rc;
+            } else {
+                R[SOFF] = -Ff;
+            }
+            for (int k = USED; k < stride; ++k) R[k] = 0.0;
+        }
+        __syncthreads();
+        const int64_t left = n_cells - c0, live = left < REC_CELLS ? left : REC_CELLS;
+        double *out = rec + c0 * stride;
+        for (int i = tid; i < (int)live * stride; i += REC_CELLS) {
+            const int c = i / stride, k = i - c * stride;
+            out[i] = s_rec[c * pitch + k];
+        }
+        __syncthreads();
+    }
+}
+
+// slot of every local column of a row's one or two sources inside the row's CSR segment (binary search; one-off)
+__global__ void rows_locate_kernel(int64_t n_rows, int64_t row_lo, const int32_t *__restrict__ indptr,
+                                   const int32_t *__restrict__ indices, const int32_t *__restrict__ row_src, int n_loc,
+                                   const int32_t *__restrict__ dest, uint8_t *__restrict__ slots, int *__restrict__ flag) {
+    const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * n_rows) return;
+    const int64_t rl = id >> 1;
+    const int32_t src = row_src[id];
+    uint8_t *out = slots + id * n_loc;
+    if (src < 0) {
+        for (int b = 0; b < n_loc; ++b) out[b] = 0;
+        return;
+    }
+    const int64_t c = src >> 5;
+    const int32_t b0 = indptr[row_lo + rl], b1 = indptr[row_lo + rl + 1];
+    if (dest[c * n_loc + (src & 31)] != (int32_t)(row_lo + rl)) atomicOr(flag, 4);
+    for (int b = 0; b < n_loc; ++b) {
+        const int32_t col = dest[c * n_loc + b];
+        int32_t lo = b0, hi = b1;
+        while (lo < hi) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (indices[mid] < col)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo >= b1 || indices[lo] != col)
+            atomicOr(flag, 1);
+        else if (lo - b0 > 255)
+            atomicOr(flag, 2);
+        out[b] = (uint8_t)(lo - b0);
+    }
+}
+
+__global__ void __launch_bounds__(ROWS_PER_CTA)
+    rows_expand_kernel(int64_t row_lo, int64_t row_hi, const int32_t *__restrict__ indptr,
+                       const int32_t *__restrict__ row_src, const uint8_t *__restrict__ slots, int n_loc,
+                       const int16_t *__restrict__ emap, const int16_t *__restrict__ ridx, const double *__restrict__ rec,
+                       int stride, double *__restrict__ vals, double *__restrict__ rhs, int rhs_add) {
+    extern __shared__ double tile[];
+    __shared__ int16_t s_emap[32 * 32];
+    __shared__ int16_t s_ridx[32];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_loc * n_loc; i += ROWS_PER_CTA) s_emap[i] = emap[i];
+    if (tid < n_loc) s_ridx[tid] = ridx[tid];
+    const int64_t n_blocks = (row_hi - row_lo + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int64_t r0 = row_lo + blk * ROWS_PER_CTA, r1 = r0 + ROWS_PER_CTA < row_hi ? r0 + ROWS_PER_CTA : row_hi;
+        const int32_t base = indptr[r0];
+        const int len = indptr[r1] - base;
+        __syncthreads();  // the previous block's copy-out is done (and the tables are loaded)
+        for (int i = tid; i < len; i += ROWS_PER_CTA) tile[i] = 0.0;
+        __syncthreads();
+        const int64_t r = r0 + tid;
+        if (r < r1) {
+            double *row = tile + (indptr[r] - base);
+            const int64_t rl = r - row_lo;
+            double rv = 0.0;
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int32_t src = row_src[2 * rl + side];
+                if (src < 0) continue;
+                const int a = src & 31;
+                const double *R = rec + (int64_t)(src >> 5) * stride;
+                const uint8_t *sl = slots + (2 * rl + side) * n_loc;
+                const int16_t *em = s_emap + a * n_loc;
+                for (int b = 0; b < n_loc; ++b) {
+                    const int code = em[b];
+                    if (code == 0) continue;
+                    const double v = __ldg(R + (code > 0 ? code : -code) - 1);
+                    row[sl[b]] += code > 0 ? v : -v;
+                }
+                rv += __ldg(R + s_ridx[a]);
+            }
+            if (rhs) {
+                if (rhs_add)
+                    rhs[r] += rv;
+                else
+                    rhs[r] = rv;
+            }
+        }
+        __syncthreads();
+        double *out = vals + base;
+        for (int i = tid; i < len; i += ROWS_PER_CTA) out[i] = tile[i];
+    }
+}
+
+}  // namespace
+
+extern "C" int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *u_val, const double *u_div,
+                                    const double *p_val, const double *weights, const double *Tcases, const int8_t *cases,
+                                    const double *coords, const int32_t *cell_nodes, int64_t n_cells, const double *kappa,
+                                    int64_t ksc, int64_t ksq, const double *delta, int64_t dsc, int64_t dsq,
+                                    const double *eta, int64_t esc, int64_t esq, double delta_t, const double *f_f,
+                                    const double *f_r, const double *alpha, const double *alpha_prev, const int32_t *dest,
+                                    int stride, double *rec, nfa_stream stream) {
+    if (n_cells == 0) return 0;
+    if (dim != 2 && dim != 3) return fail("nfa_hdiv_rt1_records: dim must be 2 or 3");
+    if (form != 0 && form != 1) return fail("nfa_hdiv_rt1_records: form must be 0 (mixed Poisson) or 1 (Sundus)");
+    if (n_q < 1 || n_q > 64) return fail("nfa_hdiv_rt1_records: 1 to 64 quadrature points");
+    if (!u_val || !u_div || !p_val || !weights || !Tcases || !cases || !coords || !cell_nodes || !kappa || !rec)
+        return fail("nfa_hdiv_rt1_records: NULL argument");
+    const int nu = dim + 1, nflux = form == 1 ? 2 : 1;
+    const int used = nflux * nu * (nu + 2) + (form == 1 ? 4 : 1);
+    if (stride < used || (stride & 3)) return fail("nfa_hdiv_rt1_records: record stride too small or not a multiple of 4");
+    if (form == 1) {
+        if (!delta || !eta || !dest) return fail("nfa_hdiv_rt1_records: the Sundus form needs delta, eta and dest");
+        if (delta_t == 0.0) return fail("nfa_hdiv_rt1_records: delta_t is zero");
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CoefR kp{kappa, ksc, ksq}, dl{delta, dsc, dsq}, et{eta, esc, esq};
+    const size_t smem = sizeof(double) * ((size_t)n_q * nu * dim + (size_t)n_q * nu + 2 * n_q + (size_t)REC_CELLS * (stride | 1));
+    int device = 0, n_sm = 148;
+    NFA_CUDA(cudaGetDevice(&device));
+    NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    const int64_t want = (n_cells + REC_CELLS - 1) / REC_CELLS;
+    const int grid = (int)std::min<int64_t>(want, (int64_t)n_sm * 8);
+    const double inv_dt = form == 1 ? 1.0 / delta_t : 0.0;
+#define NFA_REC_LAUNCH(D, F)                                                                                          \
+    {                                                                                                                 \
+        auto kern = rt1_records_kernel<D, F>;                                                                         \
+        NFA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                 \
+        kern<<<grid, REC_CELLS, smem, s>>>(n_q, u_val, u_div, p_val, weights, Tcases, cases, coords, cell_nodes, n_cells, \
+                                           kp, dl, et, inv_dt, f_f, f_r, alpha, alpha_prev, dest, stride, rec);       \
+    }
+    if (dim == 3) {
+        if (form == 1) NFA_REC_LAUNCH(3, 1) else NFA_REC_LAUNCH(3, 0)
+    } else {
+        if (form == 1) NFA_REC_LAUNCH(2, 1) else NFA_REC_LAUNCH(2, 0)
+    }
+#undef NFA_REC_LAUNCH
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nfa_rows_locate(int64_t row_lo, int64_t row_hi, const int32_t *indptr, const int32_t *indices,
+                               const int32_t *row_src, int n_loc, const int32_t *dest, uint8_t *slots,
+                               nfa_stream stream) {
+    const int64_t n_rows = row_hi - row_lo;
+    if (n_rows <= 0) return 0;
+    if (!indptr || !indices || !row_src || !dest || !slots) return fail("nfa_rows_locate: NULL argument");
+    if (n_loc < 1 || n_loc > 32) return fail("nfa_rows_locate: 1 to 32 local dofs");
+    cudaStream_t s = (cudaStream_t)stream;
+    int *d_flag = nullptr, h_flag = 0;
+    NFA_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    cudaMemsetAsync(d_flag, 0, sizeof(int), s);
+    rows_locate_kernel<<<grid_for(2 * n_rows, 256), 256, 0, s>>>(n_rows, row_lo, indptr, indices, row_src, n_loc, dest,
+                                                                 slots, d_flag);
+    count_launch();
+    cudaError_t e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_flag);
+    if (e != cudaSuccess) return fail(std::string("nfa_rows_locate: ") + cudaGetErrorString(e));
+    if (h_flag & 4) return fail("nfa_rows_locate: a row's source does not list the row's dof");
+    if (h_flag & 1) return fail("nfa_rows_locate: a local column is missing from the row's CSR segment");
+    if (h_flag & 2) return fail("nfa_rows_locate: a row holds more than 256 entries");
+    return 0;
+}
+
+extern "C" int nfa_rows_expand(int64_t row_lo, int64_t row_hi, int max_row_len, const int32_t *indptr,
+                               const int32_t *row_src, const uint8_t *slots, int n_loc, const int16_t *emap,
+                               const int16_t *ridx, const double *rec, int stride, double *vals, double *rhs, int rhs_add,
+                               nfa_stream stream) {
+    if (row_hi <= row_lo) return 0;
+    if (!indptr || !row_src || !slots || !emap || !ridx || !rec || !vals) return fail("nfa_rows_expand: NULL argument");
+    if (n_loc < 1 || n_loc > 32) return fail("nfa_rows_expand: 1 to 32 local dofs");
+    if (max_row_len < 1 || max_row_len > 256) return fail("nfa_rows_expand: rows of 1 to 256 entries");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = sizeof(double) * (size_t)ROWS_PER_CTA * max_row_len;
+    if (smem > 200 * 1024) return fail("nfa_rows_expand: rows too long for the shared-memory image");
+    int device = 0, n_sm = 148, per_sm = 1;
+    NFA_CUDA(cudaGetDevice(&device));
+    NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    NFA_CUDA(cudaFuncSetAttribute(rows_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_expand_kernel, ROWS_PER_CTA, smem));
+    const int64_t n_blocks = (row_hi - row_lo + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+    const int grid = (int)std::min<int64_t>(n_blocks, (int64_t)n_sm * std::max(per_sm, 1));
+    rows_expand_kernel<<<grid, ROWS_PER_CTA, smem, s>>>(row_lo, row_hi, indptr, row_src, slots, n_loc, emap, ridx, rec,
+                                                        stride, vals, rhs, rhs_add);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}

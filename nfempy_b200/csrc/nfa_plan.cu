@@ -309,6 +309,23 @@ static int plan_create_impl(int64_t n_dof, int n_segments, const int32_t *const 
     return 0;
 }
 
+// Pattern-only plan over a CSR the caller owns (and keeps alive): the base that nfa_plan_create merges boundary / coupling
+// segments into when the volume forms are assembled by row owner (csrc/nfa_hdivrows.cu).
+extern "C" int nfa_plan_from_csr(int64_t n_dof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                                 nfa_plan **out) {
+    if (!out) return fail("nfa_plan_from_csr: out is NULL");
+    *out = nullptr;
+    if (n_dof <= 0 || n_dof > INT32_MAX || nnz < 0 || nnz > INT32_MAX) return fail("nfa_plan_from_csr: size out of int32 range");
+    if (!d_indptr || (nnz && !d_indices)) return fail("nfa_plan_from_csr: NULL pattern");
+    nfa_plan *plan = new nfa_plan();
+    plan->n_dof = n_dof;
+    plan->nnz = nnz;
+    plan->ext_indptr = d_indptr;
+    plan->ext_indices = d_indices;
+    *out = plan;
+    return 0;
+}
+
 extern "C" void nfa_plan_destroy(nfa_plan *plan) { delete plan; }
 extern "C" int64_t nfa_plan_nnz(const nfa_plan *plan) { return plan ? plan->nnz : -1; }
 extern "C" int64_t nfa_plan_n_dof(const nfa_plan *plan) { return plan ? plan->n_dof : -1; }

@@ -97,6 +97,27 @@ class LaplaceDualWeakForm(BatchedWeakForm):
             _lib.ptr(data.f), None, _lib.ptr(Ke), _lib.ptr(re), _lib.stream_ptr(),
         )
 
+    def row_spec(self, data):
+        """Row-owner path (``assembly/hdiv_rows.py``, ``csrc/nfa_hdivrows.cu``) for RT_1 x P_0 -- BASELINE config 3 at
+        k = 1: record layout and entry maps, or ``None`` for every other element."""
+        from ..assembly import hdiv_rows
+
+        u = self.space.discrete_spaces["u"]
+        if u.family != "RT" or data.nfd != 1 or data.n_u != data.dim + 1 or data.n_p != 1 or data.n_q > 64 \
+                or list(self.space.discrete_spaces.keys()) != ["u", "p"]:
+            return None
+        emap, ridx, stride = hdiv_rows.laplace_dual_maps(data.n_u)
+        return {"emap": emap, "ridx": ridx, "stride": stride}
+
+    def launch_records(self, dev, data, alpha_dev, alpha_prev_dev, dest_dev, rec, stride):
+        k = data.kappa  # the reference discards alpha (:50): no state terms
+        _lib.call(
+            "nfa_hdiv_rt1_records", data.dim, 0, data.n_q, _lib.ptr(data.u_val), _lib.ptr(data.u_div), _lib.ptr(data.p_val),
+            _lib.ptr(data.w), _lib.ptr(data.tcases), _lib.ptr(data.cases), _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes),
+            data.n_items, _lib.ptr(k[0]), k[1], k[2], None, 0, 0, None, 0, 0, 0.0, _lib.ptr(data.f), None, None, None, None,
+            stride, _lib.ptr(rec), _lib.stream_ptr(),
+        )
+
     def evaluate_form(self, element_index, alpha):
         return super().evaluate_form(element_index, None)  # the reference discards alpha (:50)
 

@@ -104,6 +104,27 @@ class SundusDualWeakForm(BatchedWeakForm):
             _lib.ptr(Ke), _lib.ptr(re), _lib.stream_ptr(),
         )
 
+    def row_spec(self, data):
+        """Row-owner path (``assembly/hdiv_rows.py``, ``csrc/nfa_hdivrows.cu``) for the lowest-order pair RT_1 x P_0 --
+        BASELINE config 5's element: record layout and entry maps, or ``None`` for every other element."""
+        from ..assembly import hdiv_rows
+
+        mp = self.space.discrete_spaces["mp"]
+        if mp.family != "RT" or data.nfd != 1 or data.n_u != data.dim + 1 or data.n_p != 1 or data.n_q > 64:
+            return None
+        emap, ridx, stride = hdiv_rows.sundus_maps(data.n_u)
+        return {"emap": emap, "ridx": ridx, "stride": stride}
+
+    def launch_records(self, dev, data, alpha_dev, alpha_prev_dev, dest_dev, rec, stride):
+        k, d, e = data.coefs["kappa"], data.coefs["delta"], data.coefs["eta"]
+        _lib.call(
+            "nfa_hdiv_rt1_records", data.dim, 1, data.n_q, _lib.ptr(data.u_val), _lib.ptr(data.u_div), _lib.ptr(data.p_val),
+            _lib.ptr(data.w), _lib.ptr(data.tcases), _lib.ptr(data.cases), _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes),
+            data.n_items, _lib.ptr(k[0]), k[1], k[2], _lib.ptr(d[0]), d[1], d[2], _lib.ptr(e[0]), e[1], e[2], data.delta_t,
+            _lib.ptr(data.loads["rhs_f"]), _lib.ptr(data.loads["rhs_r"]), _lib.ptr(alpha_dev), _lib.ptr(alpha_prev_dev),
+            _lib.ptr(dest_dev), stride, _lib.ptr(rec), _lib.stream_ptr(),
+        )
+
     def evaluate_form(self, element_index, alpha_n_p_1, alpha_n, t):
         """Single-cell evaluation through the same kernel (local vectors in, ``(r_el, j_el)`` out)."""
         from ..device import space_device

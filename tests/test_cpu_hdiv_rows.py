@@ -1,0 +1,131 @@
+"""Host side of the row-owner H(div) path (``nfempy_b200/assembly/hdiv_rows.py``) on the CPU: the rows' sources, the
+record layouts / entry maps of ``nfa_hdiv_rt1_records`` + ``nfa_rows_expand`` and the slot search, driven with records
+read off the ORACLE's local matrices -- expanding them with a numpy restatement of the two kernels must reproduce the
+oracle's assembled CSR (pattern, values, right-hand side) entry by entry."""
+import numpy as np
+import pytest
+import torch
+
+from nfempy_b200.assembly import hdiv_rows
+from oracle import ref_assembly, ref_forms
+from tests.parity_helpers import SundusCase, mixed_poisson_case
+
+
+def expand_rows_host(indptr, row_lo, row_src, slots, emap, ridx, rec):
+    """numpy restatement of ``rows_expand_kernel`` (used by the CPU tests of the tables; never by the product path)."""
+    n_rows = len(row_src)
+    n_loc = emap.shape[0]
+    vals = np.zeros(int(indptr[row_lo + n_rows] - indptr[row_lo]))
+    rhs = np.zeros(n_rows)
+    base = int(indptr[row_lo])
+    for r in range(n_rows):
+        off = int(indptr[row_lo + r]) - base
+        for side in range(2):
+            s = int(row_src[r, side])
+            if s < 0:
+                continue
+            c, a = s >> 5, s & 31
+            for b in range(n_loc):
+                code = int(emap[a, b])
+                if code == 0:
+                    continue
+                v = rec[c, abs(code) - 1]
+                vals[off + int(slots[r, side, b])] += v if code > 0 else -v
+            rhs[r] += rec[c, int(ridx[a])]
+    return vals, rhs
+
+
+def locate_slots_host(indptr, indices, row_lo, row_src, dest):
+    """numpy restatement of ``rows_locate_kernel`` (CPU tests only)."""
+    n_rows, n_loc = len(row_src), dest.shape[1]
+    slots = np.zeros((n_rows, 2, n_loc), dtype=np.uint8)
+    for r in range(n_rows):
+        b0, b1 = int(indptr[row_lo + r]), int(indptr[row_lo + r + 1])
+        seg = np.asarray(indices[b0:b1])
+        for side in range(2):
+            s = int(row_src[r, side])
+            if s < 0:
+                continue
+            pos = np.searchsorted(seg, dest[s >> 5])
+            if np.any(pos >= len(seg)) or np.any(seg[np.minimum(pos, len(seg) - 1)] != dest[s >> 5]):
+                raise ValueError("a local column is missing from the row's CSR segment")
+            slots[r, side] = pos
+    return slots
+
+
+def _records_from_local(emap, ridx, stride, blocks):
+    """Fills the records from local ``(r_el, j_el)`` pairs THROUGH the entry maps; checks on the way that the maps describe
+    the local matrix completely: structural zeros are zeros, entries sharing a record slot agree (up to the sign)."""
+    rec = np.full((len(blocks), stride), np.nan)
+    for c, (r_el, j_el) in enumerate(blocks):
+        scale = np.abs(j_el).max()
+        for a in range(emap.shape[0]):
+            for b in range(emap.shape[1]):
+                code = int(emap[a, b])
+                if code == 0:
+                    assert abs(j_el[a, b]) <= 1e-13 * scale, (a, b, j_el[a, b])
+                    continue
+                v = j_el[a, b] if code > 0 else -j_el[a, b]
+                k = abs(code) - 1
+                if not np.isnan(rec[c, k]):
+                    assert abs(rec[c, k] - v) <= 1e-12 * scale, (a, b)
+                rec[c, k] = v
+            assert np.isnan(rec[c, ridx[a]])
+            rec[c, ridx[a]] = r_el[a]
+    return np.nan_to_num(rec)
+
+
+def _check(dest, n_dof, emap, ridx, stride, blocks, want):
+    indptr, indices, data, rhs = want
+    src = hdiv_rows.row_sources(torch.as_tensor(dest), 0, n_dof)
+    assert src is not None
+    src = src.numpy()
+    # every row names its (item, local row) sources, lower item first
+    for r in range(n_dof):
+        hits = [(c, a) for c in range(len(dest)) for a in range(dest.shape[1]) if dest[c, a] == r]
+        got = [(int(s) >> 5, int(s) & 31) for s in src[r] if s >= 0]
+        assert got == hits
+    slots = locate_slots_host(indptr, indices, 0, src, dest)
+    rec = _records_from_local(emap, ridx, stride, blocks)
+    vals, res = expand_rows_host(indptr, 0, src, slots, emap, ridx, rec)
+    assert np.allclose(vals, data, rtol=1e-13, atol=1e-13 * np.abs(data).max())
+    assert np.allclose(res, rhs, rtol=1e-13, atol=1e-13 * np.abs(rhs).max())
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_sundus_records_expand_to_the_oracle_matrix(dim):
+    case = SundusCase(dim=dim, k=1, n=2)
+    space, ref = case.space(), case.ref_space()
+    a_n, a = case.alphas(ref.n_dof)
+    mp = ref.discrete_spaces["mp"]
+    n_cells = len(mp.element_ids)
+    forms = [("time_dependent_form", ref_forms.sundus_dual, case.functions, n_cells)]
+    want = ref_assembly.assemble_time_dependent(ref, forms, (a_n, a), case.t)
+    dest = np.asarray(space.destination_table(), dtype=np.int64)
+    blocks = [ref_forms.sundus_dual(ref, case.functions, i, a_n[dest[i]], a[dest[i]], case.t) for i in range(n_cells)]
+    emap, ridx, stride = hdiv_rows.sundus_maps(dim + 1)
+    assert stride % 4 == 0 and stride >= np.abs(emap).max() and stride > ridx.max()
+    _check(dest, ref.n_dof, emap, ridx, stride, blocks, want)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_mixed_poisson_records_expand_to_the_oracle_matrix(dim):
+    case = mixed_poisson_case(dim=dim, k=1, n=2, with_bc=False, varying=True)
+    space, ref = case.space(), case.ref_space()
+    n_cells = len(ref.discrete_spaces["u"].element_ids)
+    forms = [("form", ref_forms.laplace_dual, case.ref_forms_fn(ref)[0][2], n_cells)]
+    want = ref_assembly.assemble(ref, forms)
+    dest = np.asarray(space.destination_table(), dtype=np.int64)
+    functions = case.ref_forms_fn(ref)[0][2]
+    blocks = [ref_forms.laplace_dual(ref, functions, i, np.zeros(dest.shape[1])) for i in range(n_cells)]
+    emap, ridx, stride = hdiv_rows.laplace_dual_maps(dim + 1)
+    _check(dest, ref.n_dof, emap, ridx, stride, blocks, want)
+
+
+def test_row_sources_refuse_spaces_with_widely_shared_dofs():
+    dest = torch.tensor([[0, 1, 2], [2, 3, 4], [4, 2, 5]])  # dof 2 belongs to three items
+    assert hdiv_rows.row_sources(dest, 0, 6) is None
+    assert hdiv_rows.row_sources(torch.tensor([[0, 1, 1]]), 0, 2) is None  # an item lists a dof twice
+    assert hdiv_rows.row_sources(torch.tensor([[0, 1, 7]]), 0, 4) is None  # outside the row range
+    src = hdiv_rows.row_sources(torch.tensor([[3, 1], [1, 2]]), 1, 5).numpy()  # rows 1..4; row 4 has no source
+    assert src.tolist() == [[1, 32], [33, -1], [0, -1], [-1, -1]]

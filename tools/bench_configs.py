@@ -53,10 +53,65 @@ def oracle_rate(case, n_cells):
 ONLY = ""
 
 
+def wanted(name):
+    """--only takes comma-separated pieces of case names"""
+    return not ONLY or any(tok in name for tok in ONLY.split(","))
+
+
+def path_of(plan):
+    if plan.fused_index is not None:
+        return "fused"
+    return "row owner (records + rows, no local matrices)" if plan.rows else "two-stage"
+
+
+def rows_roofline(state, ms):
+    """HBM roofline of an assembly on the row-owner path: ALGORITHMIC bytes = every per-item input array of the direct
+    forms (connectivity, orientation cases, coefficient / load arrays as stored, destination table), the coordinates, the
+    state vectors, and the outputs (8 B per stored CSR value, 8 B per right-hand-side row) -- records and plan tables are
+    not counted -- over the measured time of the whole assembly, against the measured copy bandwidth."""
+    import torch
+
+    dev, entries, datas, dests, plan, _ = state
+    if not plan.rows:
+        return None
+
+    def tensors(obj, n, seen):
+        if isinstance(obj, torch.Tensor):
+            if obj.is_cuda and obj.ndim >= 1 and obj.shape[0] == n and obj.data_ptr() not in seen:
+                seen.add(obj.data_ptr())
+                return obj.numel() * obj.element_size()
+            return 0
+        if isinstance(obj, dict):
+            return sum(tensors(v, n, seen) for v in obj.values())
+        if isinstance(obj, (tuple, list)):
+            return sum(tensors(v, n, seen) for v in obj)
+        return 0
+
+    total, seen = 0, set()
+    for i in plan.rows:
+        data = datas[i]
+        total += tensors({k: v for k, v in data.__dict__.items() if k not in ("x_host", "dev")}, data.n_items, seen)
+        total += dests[i].numel() * dests[i].element_size()
+        total += data.dev.coords.numel() * 8
+        states = data.alpha_dev if isinstance(data.alpha_dev, tuple) else (data.alpha_dev,)
+        total += sum(a.numel() * 8 for a in states if a is not None)
+    total += int(plan.nnz) * 8 + int(plan.n_dof) * 8
+    peak, source = 6548.2, "fallback"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peak, source = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    achieved = total / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic_bytes_per_assembly": total, "kernels": "rt1_records_kernel + rows_expand_kernel (+ boundary forms)",
+            "peak_source": source}
+
+
 def run_case(name, case, small_case, steps, warmup, allow_fused=True, oracle_cells=40):
     import torch
 
-    if ONLY and ONLY not in name:
+    if not wanted(name):
         return
     from nfempy_b200 import _lib
     from nfempy_b200.assembly import GPUAssembler
@@ -86,12 +141,14 @@ def run_case(name, case, small_case, steps, warmup, allow_fused=True, oracle_cel
     n_loc = int(space.destination_table().shape[1])
     line = {
         "case": name, "cells": n_cells, "n_dof": int(space.n_dof), "nnz": int(plan.nnz), "n_loc": n_loc,
-        "path": "fused" if plan.fused_index is not None else "two-stage", "ms_per_step": ms,
+        "path": path_of(plan), "ms_per_step": ms,
         "elements_per_s": n_cells / (ms * 1e-3), "nonzeros_per_s": plan.nnz / (ms * 1e-3),
         "launches_per_step": launches, "plan_build_s": plan.build_seconds, "host_space_s": t_space,
         "prepare_s": t_prepare, "steps": steps, "warmup": warmup, "dtype": "f64",
         "local_bytes_per_cell_two_stage": 8 * (n_loc * n_loc + n_loc),
     }
+    if plan.rows:
+        line["roofline"] = rows_roofline(state, ms)
     if small_case is not None:
         line["oracle_elements_per_s_1core"] = oracle_rate(small_case, oracle_cells)
     print(json.dumps(line), flush=True)
@@ -102,7 +159,7 @@ def run_case(name, case, small_case, steps, warmup, allow_fused=True, oracle_cel
 def run_sundus(mesh, n_steps):
     import torch
 
-    if ONLY and ONLY not in "config5 sundus":
+    if not wanted("config5 sundus"):
         return
     from nfempy_b200.assembly import GPUAssembler
     from tests.parity_helpers import SundusCase
@@ -137,7 +194,8 @@ def run_sundus(mesh, n_steps):
     print(json.dumps({
         "case": "config5: two-flux transport (Sundus) RT1 x RT1 x P0 x P0, implicit Euler + reaction, %d reassemblies "
                 "on one plan" % n_steps,
-        "cells": n_cells, "n_dof": int(space.n_dof), "nnz": int(plan.nnz), "n_loc": 10, "path": "two-stage",
+        "cells": n_cells, "n_dof": int(space.n_dof), "nnz": int(plan.nnz), "n_loc": 10, "path": path_of(plan),
+        "roofline": rows_roofline(state, ms),
         "ms_per_reassembly_kernels": ms, "elements_per_s": n_cells / (ms * 1e-3), "plans_built": len(asm._plans),
         "first_assembly_s": first, "api_step_s_with_host_callables": api, "plan_build_s": plan.build_seconds,
         "steps": n_steps, "dtype": "f64",
@@ -150,7 +208,7 @@ def run_sundus_md(n, n_steps):
     (tests/md_helpers.py), one stacked system, plan built once, ``n_steps`` reassemblies."""
     import torch
 
-    if ONLY and ONLY not in "config5 md sundus":
+    if not wanted("config5 md sundus"):
         return
     from nfempy_b200.assembly import GPUAssembler
     from nfempy_b200.mesh import fractured_box_tet_mesh
@@ -206,7 +264,8 @@ def run_sundus_md(n, n_steps):
     print(json.dumps({
         "case": "config5 (mixed-dimensional): two-flux transport RT1 x RT1 x P0 x P0 in the fractured box (z = 1/2) + the same "
                 "fields on the fracture + Robin coupling of both fluxes, %d reassemblies on one plan" % n_steps,
-        "cells": n_cells, "fracture_cells": int(len(triples)), "n_dof": int(n_dof), "nnz": int(plan.nnz), "path": "two-stage",
+        "cells": n_cells, "fracture_cells": int(len(triples)), "n_dof": int(n_dof), "nnz": int(plan.nnz), "path": path_of(plan),
+        "roofline": rows_roofline(state, ms),
         "ms_per_reassembly_kernels": ms, "elements_per_s": (n_cells + len(triples)) / (ms * 1e-3), "plans_built": len(asm._plans),
         "first_assembly_s": first, "api_step_s_new_time": api, "api_step_s_newton_iteration": api_newton,
         "plan_build_s": plan.build_seconds, "host_mesh_space_s": t_host, "steps": n_steps, "dtype": "f64",
