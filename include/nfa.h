@@ -207,17 +207,21 @@ int nfa_rows_copy_i32(int64_t n_rows, const int64_t *d_indptr, const int64_t *d_
  * 11-177; form = 1, local order [mp | mc | p | c]), the per-cell evaluate_form + n_loc^2 Mat.setValue calls of
  * R/src/assembly/ScatterFormData.py:5-25.
  * nfa_hdiv_rt1_records: one thread per cell writes the cell's distinct numbers as a record of `stride` doubles
- *   (stride a multiple of 4): for flux field F and local facet a, at (F n_u + a)(n_u + 2): M_F[a][0..n_u), C[a], r_F[a]
- *   (M = int w psi_a.psi_b / kappa resp. / delta, C = int div psi_a w, r = residual row at the iterate); then form 0:
- *   r_p; form 1: K_pp, K_cc, r_p, r_c.  Arguments as nfa_local_hdiv_l2 / nfa_local_sundus (d_f_f is the load `rhs` of form
- *   0; delta, eta, delta_t, f_r, alpha, alpha_prev, dest are read by form 1 only).
+ *   (stride a multiple of 4): for flux field F and local facet a, at (F n_u + a) w, w = n_u + 2 rounded up to even:
+ *   M_F[a][0..n_u), C[a], r_F[a]
+ *   (M = int w psi_a.psi_b / kappa resp. / delta, C = int div psi_a w, r = residual row at the iterate); then the block the
+ *   scalar rows read: form 0: r_p, C[0..n_u); form 1: K_pp, K_cc, r_p, r_c, C[0..n_u).  Arguments as nfa_local_hdiv_l2 /
+ *   nfa_local_sundus (d_f_f is the load `rhs` of form 0; delta, eta, delta_t, f_r, alpha, alpha_prev, dest are read by
+ *   form 1 only).
+ * Runs: local row a of an item reads the record doubles [d_roff[a], d_roff[a] + 8) (d_roff even); d_codes int8 [n_loc][8]
+ *   says what entry k of the run is for that row: 0 = nothing, +-(b + 1) = local column b with that sign (each column at
+ *   most once; columns without a code are structural zeros, stored as 0.0), 127 = the row's residual.
  * nfa_rows_locate (one-off): d_row_src int32 [n_rows][2] names the one or two sources of row row_lo + k as
  *   item * 32 + local row (-1 = none; ascending item order), d_dest int32 [n_items][n_loc] the items' global dofs;
- *   writes d_slots uint8 [n_rows][2][n_loc] = position of every local column inside the row's CSR segment.
- * nfa_rows_expand: one thread per row; local entry (a, b) of a source is record[|emap[a n_loc + b]| - 1] with the sign of
- *   the code (0 = structural zero, stored as 0.0), the right-hand side row is the sum of record[ridx[a]] over the sources
- *   (rhs_add: added to d_rhs instead of stored).  Every CSR value of rows [row_lo, row_hi) is overwritten; contributions
- *   are summed lower item first. */
+ *   writes d_slots uint8 [n_rows][2][8] = position of every run entry's column inside the row's CSR segment.
+ * nfa_rows_expand: one thread per row; every CSR value of rows [row_lo, row_hi) is overwritten with the sum of its
+ *   sources' entries, lower item first; the right-hand side row is the sum of the sources' residual entries (rhs_add:
+ *   added to d_rhs instead of stored). */
 int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *d_u_val, const double *d_u_div, const double *d_p_val,
                          const double *d_weights, const double *d_Tcases, const int8_t *d_cases, const double *d_coords,
                          const int32_t *d_cell_nodes, int64_t n_cells, const double *d_kappa, int64_t ksc, int64_t ksq,
@@ -225,9 +229,10 @@ int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *d_u_val, cons
                          double delta_t, const double *d_f_f, const double *d_f_r, const double *d_alpha,
                          const double *d_alpha_prev, const int32_t *d_dest, int stride, double *d_rec, nfa_stream stream);
 int nfa_rows_locate(int64_t row_lo, int64_t row_hi, const int32_t *d_indptr, const int32_t *d_indices,
-                    const int32_t *d_row_src, int n_loc, const int32_t *d_dest, uint8_t *d_slots, nfa_stream stream);
+                    const int32_t *d_row_src, int n_loc, const int8_t *d_codes, const int32_t *d_dest, uint8_t *d_slots,
+                    nfa_stream stream);
 int nfa_rows_expand(int64_t row_lo, int64_t row_hi, int max_row_len, const int32_t *d_indptr, const int32_t *d_row_src,
-                    const uint8_t *d_slots, int n_loc, const int16_t *d_emap, const int16_t *d_ridx, const double *d_rec,
+                    const uint8_t *d_slots, int n_loc, const int32_t *d_roff, const int8_t *d_codes, const double *d_rec,
                     int stride, double *d_vals, double *d_rhs, int rhs_add, nfa_stream stream);
 /* pattern-only plan over a caller-owned CSR (kept alive by the caller): base of nfa_plan_create for the other segments */
 int nfa_plan_from_csr(int64_t n_dof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices, nfa_plan **out);

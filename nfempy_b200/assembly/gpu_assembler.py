@@ -318,13 +318,15 @@ class GPUAssembler:
             spec = form.row_spec(data)
             nl = int(dests[i].shape[1])
             t["max_len"] = int(row_len[t["lo"]:t["hi"]].max().item())
-            if t["max_len"] > 256 or t["max_len"] * 8 * 256 > 200 * 1024:
+            runs = hdiv_rows.row_runs(spec["emap"], spec["ridx"])
+            if t["max_len"] > 256 or t["max_len"] * 8 * 256 > 200 * 1024 or runs is None:
                 raise _RowsUnavailable()
-            t["slots"] = torch.empty((t["hi"] - t["lo"], 2, nl), dtype=torch.uint8, device=dev.device)
+            t["roff"] = torch.as_tensor(runs[0]).to(dev.device)
+            t["codes"] = torch.as_tensor(runs[1]).to(dev.device)
+            t["slots"] = torch.empty((t["hi"] - t["lo"], 2, hdiv_rows.RUN), dtype=torch.uint8, device=dev.device)
             _lib.check(lib.nfa_rows_locate(t["lo"], t["hi"], _lib.ptr(p.indptr), _lib.ptr(p.indices), _lib.ptr(t["src"]), nl,
-                                           _lib.ptr(dests[i]), _lib.ptr(t["slots"]), stream), "nfa_rows_locate")
-            t["emap"] = torch.as_tensor(np.ascontiguousarray(spec["emap"], dtype=np.int16)).to(dev.device)
-            t["ridx"] = torch.as_tensor(np.ascontiguousarray(spec["ridx"], dtype=np.int16)).to(dev.device)
+                                           _lib.ptr(t["codes"]), _lib.ptr(dests[i]), _lib.ptr(t["slots"]), stream),
+                       "nfa_rows_locate")
             t["stride"], t["n_loc"] = int(spec["stride"]), nl
         p.rows = rows
         ph = ctypes.c_void_p()
@@ -680,7 +682,7 @@ class GPUAssembler:
             rec = torch.empty((data.n_items, t["stride"]), dtype=torch.float64, device=dev.device)
             form.launch_records(data.dev, data, first_dev, second_dev, dest, rec, t["stride"])
             _lib.check(lib.nfa_rows_expand(t["lo"], t["hi"], t["max_len"], _lib.ptr(plan.indptr), _lib.ptr(t["src"]),
-                                           _lib.ptr(t["slots"]), t["n_loc"], _lib.ptr(t["emap"]), _lib.ptr(t["ridx"]),
+                                           _lib.ptr(t["slots"]), t["n_loc"], _lib.ptr(t["roff"]), _lib.ptr(t["codes"]),
                                            _lib.ptr(rec), t["stride"], _lib.ptr(target), _lib.ptr(rhs_dev), rhs_add, stream),
                        "nfa_rows_expand")
             keep += [rec, first_dev, second_dev]

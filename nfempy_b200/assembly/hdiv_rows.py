@@ -45,7 +45,7 @@ def row_sources(dest, row_lo, row_hi):
 def sundus_maps(n_u):
     """Record layout of ``nfa_hdiv_rt1_records`` (form 1) as the tables ``nfa_rows_expand`` reads: local order
     [mp | mc | p | c]; ``emap[a, b]`` = +-(record index + 1) or 0 for a structural zero, ``ridx[a]`` = residual entry."""
-    roww, n_loc = n_u + 2, 2 * n_u + 2
+    roww, n_loc = (n_u + 3) // 2 * 2, 2 * n_u + 2  # rows start 16-byte aligned
     soff = 2 * n_u * roww
     emap = np.zeros((n_loc, n_loc), dtype=np.int16)
     ridx = np.zeros(n_loc, dtype=np.int16)
@@ -56,17 +56,17 @@ def sundus_maps(n_u):
             for b in range(n_u):
                 emap[F * n_u + a, F * n_u + b] = base + b + 1  # flux mass
             emap[F * n_u + a, s_col] = -(base + n_u + 1)  # -(w, div psi_a)
-            emap[s_col, F * n_u + a] = base + n_u + 1  # +(div psi_a, w)
+            emap[s_col, F * n_u + a] = soff + 4 + a + 1  # +(div psi_a, w): the copy inside the scalar rows' block
             ridx[F * n_u + a] = base + n_u + 1
         emap[s_col, s_col] = soff + F + 1  # time derivative (+ reaction tangent on c)
         ridx[s_col] = soff + 2 + F
-    stride = (soff + 4 + 3) // 4 * 4
+    stride = (soff + 4 + n_u + 3) // 4 * 4
     return emap, ridx, stride
 
 
 def laplace_dual_maps(n_u):
     """The same for the mixed Poisson form (form 0), local order [u | p]; the (p, p) entry is a structural zero."""
-    roww, n_loc = n_u + 2, n_u + 1
+    roww, n_loc = (n_u + 3) // 2 * 2, n_u + 1
     soff = n_u * roww
     emap = np.zeros((n_loc, n_loc), dtype=np.int16)
     ridx = np.zeros(n_loc, dtype=np.int16)
@@ -75,8 +75,41 @@ def laplace_dual_maps(n_u):
         for b in range(n_u):
             emap[a, b] = base + b + 1
         emap[a, n_u] = -(base + n_u + 1)
-        emap[n_u, a] = base + n_u + 1
+        emap[n_u, a] = soff + 1 + a + 1  # the copy inside the scalar row's block
         ridx[a] = base + n_u + 1
     ridx[n_u] = soff
-    stride = (soff + 1 + 3) // 4 * 4
+    stride = (soff + 1 + n_u + 3) // 4 * 4
     return emap, ridx, stride
+
+
+RUN = 8  # record doubles a local row may read (csrc/nfa_hdivrows.cu)
+CODE_RHS = 127
+
+
+def row_runs(emap, ridx):
+    """The entry maps as the RUNS ``nfa_rows_locate`` / ``nfa_rows_expand`` read: local row ``a`` loads the record doubles
+    ``[roff[a], roff[a] + 8)`` with 16-byte loads; ``codes[a, k]`` says what entry ``k`` is for that row: 0 = nothing,
+    ``+-(b + 1)`` = local column ``b`` with that sign, 127 = the row's residual.  ``None`` when a row's entries do not fit
+    one run or a record entry feeds two columns of a row."""
+    n_loc = emap.shape[0]
+    roff = np.zeros(n_loc, dtype=np.int32)
+    codes = np.zeros((n_loc, RUN), dtype=np.int8)
+    if n_loc > 126:
+        return None
+    for a in range(n_loc):
+        used = {int(ridx[a]): CODE_RHS}
+        for b in range(n_loc):
+            code = int(emap[a, b])
+            if code == 0:
+                continue
+            k = abs(code) - 1
+            if k in used:
+                return None
+            used[k] = (b + 1) if code > 0 else -(b + 1)
+        lo = min(used) // 2 * 2
+        if max(used) - lo >= RUN:
+            return None
+        roff[a] = lo
+        for k, code in used.items():
+            codes[a, k - lo] = code
+    return roff, codes

@@ -10,14 +10,15 @@
 //      (n_flux n_u (n_u + 2) + 4) doubles (416 B instead of 800 + 80), transposed through shared memory so that the
 //      records leave the SM as full lines;
 //   2. rows_expand_kernel: ONE THREAD PER MATRIX ROW.  In these spaces a dof belongs to at most two cells; the row's thread
-//      reads the record rows of its one or two (cell, local row) sources, places the entries at their CSR slots (uint8 per
-//      (row, side, local column), found once by nfa_rows_locate in the plan's CSR, whatever other forms added to the
-//      pattern) inside a shared-memory image of 256 consecutive CSR rows, lower cell first -- the order of the reference's
+//      reads the record runs of its one or two (cell, local row) sources (16-byte loads), places the entries at their CSR
+//      slots (uint8 per (row, source, run entry), found once by nfa_rows_locate in the plan's CSR, whatever other forms
+//      added to the pattern) inside a shared-memory image of 256 consecutive CSR rows, lower cell first -- the order of the reference's
 //      Mat.setValue(..., addv=True) calls (R/src/assembly/ScatterFormData.py:5-11) -- and the block writes the image to
 //      HBM with coalesced stores.  Every CSR value of the rows is written exactly once (explicit zeros included), the
 //      right-hand side row is the sum of its one or two record entries: no atomics, no zero fill, bit-reproducible.
-// Which record entry feeds local entry (a, b) is a table (emap: 0 = structural zero, +-(index + 1)) supplied by the host
-// form, so rows_expand_kernel is form-independent.
+// Which record entries feed local row a is a table supplied by the host form (roff[a] = start of the row's run of up to 8
+// record doubles, codes[a][k] = what entry k of the run is: a local column with its sign, the residual, or nothing), so
+// rows_expand_kernel is form-independent.
 #include <algorithm>
 
 #include "nfa_common.cuh"
@@ -36,7 +37,7 @@ constexpr int ROWS_PER_CTA = 256;
 
 // FORM 0: mixed Poisson [u | p]; FORM 1: Sundus [mp | mc | p | c]
 template <int DIM, int FORM>
-__global__ void __launch_bounds__(REC_CELLS)
+__global__ void __launch_bounds__(REC_CELLS, 3)
     rt1_records_kernel(int n_q, const double *__restrict__ u_val, const double *__restrict__ u_div,
                        const double *__restrict__ p_val, const double *__restrict__ weights,
                        const double *__restrict__ Tcases, const int8_t *__restrict__ cases,
@@ -47,9 +48,10 @@ __global__ void __launch_bounds__(REC_CELLS)
                        double *__restrict__ rec) {
     constexpr int NU = DIM + 1, NS = NU * (NU + 1) / 2, NFLUX = FORM == 1 ? 2 : 1;
     constexpr int NLOC = NFLUX * NU + NFLUX;
-    constexpr int ROWW = NU + 2;             // M[a][0..NU), C[a], r[a]
-    constexpr int SOFF = NFLUX * NU * ROWW;  // scalars: FORM 0: r_p; FORM 1: K_pp, K_cc, r_p, r_c
-    constexpr int USED = SOFF + (FORM == 1 ? 4 : 1);
+    constexpr int ROWW = (NU + 3) & ~1;      // M[a][0..NU), C[a], r[a] (+ one pad in 2-D: rows start 16-byte aligned)
+    constexpr int SOFF = NFLUX * NU * ROWW;  // scalar rows' block: FORM 0: r_p, C[.]; FORM 1: K_pp, K_cc, r_p, r_c, C[.]
+    constexpr int NSC = FORM == 1 ? 4 : 1;
+    constexpr int USED = SOFF + NSC + NU;
     extern __shared__ double sm[];
     double *s_val = sm;                       // [n_q][NU][DIM]
     double *s_div = s_val + n_q * NU * DIM;   // [n_q][NU]
@@ -98,11 +100,29 @@ __global__ void __launch_bounds__(REC_CELLS)
 #pragma unroll
             for (int a = 0; a < NU; ++a) C[a] = 0.0;
             double W2 = 0.0, Wc = 0.0, Ff = 0.0, Rc = 0.0;
+            // coefficient values of point q + 1 are requested before the arithmetic of point q
+            double kq = kappa.p[cell * kappa.sc], dq = 0.0, eq = 0.0, ffq = 0.0, frq = 0.0;
+            if (FORM == 1) {
+                dq = delta.p[cell * delta.sc];
+                eq = eta.p[cell * eta.sc];
+                frq = f_r ? f_r[cell * n_q] : 0.0;
+            }
+            ffq = f_f ? f_f[cell * n_q] : 0.0;
             for (int q = 0; q < n_q; ++q) {
                 const double wd = s_w[q] * det;
+                const double k_now = kq, d_now = dq, e_now = eq, ff_now = ffq, fr_now = frq;
+                if (q + 1 < n_q) {
+                    kq = kappa.p[cell * kappa.sc + (q + 1) * kappa.sq];
+                    if (FORM == 1) {
+                        dq = delta.p[cell * delta.sc + (q + 1) * delta.sq];
+                        eq = eta.p[cell * eta.sc + (q + 1) * eta.sq];
+                        if (f_r) frq = f_r[cell * n_q + q + 1];
+                    }
+                    if (f_f) ffq = f_f[cell * n_q + q + 1];
+                }
                 double wt[NFLUX];
-                wt[0] = wd * (1.0 / kappa.p[cell * kappa.sc + q * kappa.sq]);
-                if (FORM == 1) wt[NFLUX - 1] = wd * (1.0 / delta.p[cell * delta.sc + q * delta.sq]);
+                wt[0] = wd * (1.0 / k_now);
+                if (FORM == 1) wt[NFLUX - 1] = wd * (1.0 / d_now);
                 double psi[NU][DIM];
 #pragma unroll
                 for (int a = 0; a < NU; ++a)
@@ -130,12 +150,12 @@ __global__ void __launch_bounds__(REC_CELLS)
                 for (int a = 0; a < NU; ++a) C[a] = fma(wp, (s_div[q * NU + a] * idet) * sgn[a], C[a]);
                 W2 = fma(wp, pw, W2);
                 if (FORM == 1) {
-                    const double et = eta.p[cell * eta.sc + q * eta.sq], ch = a_s[NFLUX - 1] * pw;
+                    const double et = e_now, ch = a_s[NFLUX - 1] * pw;
                     Wc = fma(wp * pw, et * ch, Wc);
-                    Ff = fma(wp, f_f ? f_f[cell * n_q + q] : 0.0, Ff);
-                    Rc = fma(wp, 1.0 + et * ch * ch - (f_r ? f_r[cell * n_q + q] : 0.0), Rc);
+                    Ff = fma(wp, ff_now, Ff);
+                    Rc = fma(wp, 1.0 + et * ch * ch - fr_now, Rc);
                 } else {
-                    Ff = fma(wp, f_f ? f_f[cell * n_q + q] : 0.0, Ff);
+                    Ff = fma(wp, ff_now, Ff);
                 }
             }
             double a_f[NFLUX][NU];
@@ -158,6 +178,7 @@ __global__ void __launch_bounds__(REC_CELLS)
                     }
                     R[(F * NU + a) * ROWW + NU] = C[a];
                     R[(F * NU + a) * ROWW + NU + 1] = FORM == 1 ? r - a_s[F] * C[a] : 0.0;
+                    if (ROWW > NU + 2) R[(F * NU + a) * ROWW + NU + 2] = 0.0;
                 }
             if (FORM == 1) {
                 const double app = inv_dt * W2;
@@ -174,6 +195,8 @@ __global__ void __launch_bounds__(REC_CELLS)
             } else {
                 R[SOFF] = -Ff;
             }
+#pragma unroll
+            for (int a = 0; a < NU; ++a) R[SOFF + NSC + a] = C[a];  // the scalar rows read their couplings here
             for (int k = USED; k < stride; ++k) R[k] = 0.0;
         }
         __syncthreads();
@@ -187,24 +210,34 @@ __global__ void __launch_bounds__(REC_CELLS)
     }
 }
 
-// slot of every local column of a row's one or two sources inside the row's CSR segment (binary search; one-off)
+// Runs: local row a of a source reads the record doubles [roff[a], roff[a] + 8) (16-byte aligned; as many as the row's
+// codes use); codes[a][k]: 0 = not used by this row, +-(b + 1) = local column b with that sign, 127 = the row's residual.
+constexpr int RUN = 8;
+constexpr int CODE_RHS = 127;
+
+// CSR slot of every run entry of a row's one or two sources inside the row's segment (binary search; one-off)
 __global__ void rows_locate_kernel(int64_t n_rows, int64_t row_lo, const int32_t *__restrict__ indptr,
                                    const int32_t *__restrict__ indices, const int32_t *__restrict__ row_src, int n_loc,
-                                   const int32_t *__restrict__ dest, uint8_t *__restrict__ slots, int *__restrict__ flag) {
+                                   const int8_t *__restrict__ codes, const int32_t *__restrict__ dest,
+                                   uint8_t *__restrict__ slots, int *__restrict__ flag) {
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= 2 * n_rows) return;
     const int64_t rl = id >> 1;
     const int32_t src = row_src[id];
-    uint8_t *out = slots + id * n_loc;
-    if (src < 0) {
-        for (int b = 0; b < n_loc; ++b) out[b] = 0;
+    uint8_t *out = slots + id * RUN;
+    for (int k = 0; k < RUN; ++k) out[k] = 0;
+    if (src < 0) return;
+    const int64_t c = src >> 5;
+    const int a = src & 31;
+    const int32_t b0 = indptr[row_lo + rl], b1 = indptr[row_lo + rl + 1];
+    if (a >= n_loc || dest[c * n_loc + a] != (int32_t)(row_lo + rl)) {
+        atomicOr(flag, 4);
         return;
     }
-    const int64_t c = src >> 5;
-    const int32_t b0 = indptr[row_lo + rl], b1 = indptr[row_lo + rl + 1];
-    if (dest[c * n_loc + (src & 31)] != (int32_t)(row_lo + rl)) atomicOr(flag, 4);
-    for (int b = 0; b < n_loc; ++b) {
-        const int32_t col = dest[c * n_loc + b];
+    for (int k = 0; k < RUN; ++k) {
+        const int code = codes[a * RUN + k];
+        if (code == 0 || code == CODE_RHS) continue;
+        const int32_t col = dest[c * n_loc + (code > 0 ? code : -code) - 1];
         int32_t lo = b0, hi = b1;
         while (lo < hi) {
             const int32_t mid = (lo + hi) >> 1;
@@ -217,60 +250,103 @@ __global__ void rows_locate_kernel(int64_t n_rows, int64_t row_lo, const int32_t
             atomicOr(flag, 1);
         else if (lo - b0 > 255)
             atomicOr(flag, 2);
-        out[b] = (uint8_t)(lo - b0);
+        out[k] = (uint8_t)(lo - b0);
     }
 }
 
 __global__ void __launch_bounds__(ROWS_PER_CTA)
     rows_expand_kernel(int64_t row_lo, int64_t row_hi, const int32_t *__restrict__ indptr,
                        const int32_t *__restrict__ row_src, const uint8_t *__restrict__ slots, int n_loc,
-                       const int16_t *__restrict__ emap, const int16_t *__restrict__ ridx, const double *__restrict__ rec,
+                       const int32_t *__restrict__ roff, const int8_t *__restrict__ codes, const double *__restrict__ rec,
                        int stride, double *__restrict__ vals, double *__restrict__ rhs, int rhs_add) {
     extern __shared__ double tile[];
-    __shared__ int16_t s_emap[32 * 32];
-    __shared__ int16_t s_ridx[32];
+    __shared__ int s_off[32];
+    __shared__ int s_len[32];
+    __shared__ int8_t s_code[32 * RUN];
     const int tid = threadIdx.x;
-    for (int i = tid; i < n_loc * n_loc; i += ROWS_PER_CTA) s_emap[i] = emap[i];
-    if (tid < n_loc) s_ridx[tid] = ridx[tid];
+    for (int i = tid; i < n_loc * RUN; i += ROWS_PER_CTA) s_code[i] = codes[i];
+    if (tid < n_loc) {
+        s_off[tid] = roff[tid];
+        int len = 0;
+        for (int k = 0; k < RUN; ++k)
+            if (codes[tid * RUN + k] != 0) len = k + 1;
+        s_len[tid] = len;
+    }
+    __syncthreads();  // the run tables are read before the first barrier of the loop
     const int64_t n_blocks = (row_hi - row_lo + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         const int64_t r0 = row_lo + blk * ROWS_PER_CTA, r1 = r0 + ROWS_PER_CTA < row_hi ? r0 + ROWS_PER_CTA : row_hi;
         const int32_t base = indptr[r0];
         const int len = indptr[r1] - base;
-        __syncthreads();  // the previous block's copy-out is done (and the tables are loaded)
+        const int64_t r = r0 + tid;
+        // the row's lists and record runs are requested before the image is cleared (single-use lists: streaming loads)
+        int2 srcs = make_int2(-1, -1);
+        uint4 sl = make_uint4(0, 0, 0, 0);
+        int row_at = 0;
+        double v[2][RUN];
+        int a2[2] = {0, 0};
+        if (r < r1) {
+            const int64_t rl = r - row_lo;
+            srcs = __ldcs(reinterpret_cast<const int2 *>(row_src) + rl);
+            sl = __ldcs(reinterpret_cast<const uint4 *>(slots) + rl);
+            row_at = indptr[r] - base;
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int32_t src = side == 0 ? srcs.x : srcs.y;
+#pragma unroll
+                for (int k = 0; k < RUN; ++k) v[side][k] = 0.0;
+                if (src < 0) continue;
+                const int a = src & 31;
+                a2[side] = a;
+                const double2 *R = reinterpret_cast<const double2 *>(rec + (int64_t)(src >> 5) * stride + s_off[a]);
+                const int n2 = (s_len[a] + 1) >> 1;
+#pragma unroll
+                for (int k2 = 0; k2 < RUN / 2; ++k2)
+                    if (k2 < n2) {
+                        const double2 t = __ldg(R + k2);
+                        v[side][2 * k2] = t.x;
+                        v[side][2 * k2 + 1] = t.y;
+                    }
+            }
+        }
+        __syncthreads();  // the previous block's copy-out is done
         for (int i = tid; i < len; i += ROWS_PER_CTA) tile[i] = 0.0;
         __syncthreads();
-        const int64_t r = r0 + tid;
         if (r < r1) {
-            double *row = tile + (indptr[r] - base);
-            const int64_t rl = r - row_lo;
+            double *row = tile + row_at;
             double rv = 0.0;
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
-                const int32_t src = row_src[2 * rl + side];
+                const int32_t src = side == 0 ? srcs.x : srcs.y;
                 if (src < 0) continue;
-                const int a = src & 31;
-                const double *R = rec + (int64_t)(src >> 5) * stride;
-                const uint8_t *sl = slots + (2 * rl + side) * n_loc;
-                const int16_t *em = s_emap + a * n_loc;
-                for (int b = 0; b < n_loc; ++b) {
-                    const int code = em[b];
+                const int8_t *cd = s_code + a2[side] * RUN;
+                const uint32_t w0 = side == 0 ? sl.x : sl.z, w1 = side == 0 ? sl.y : sl.w;
+#pragma unroll
+                for (int k = 0; k < RUN; ++k) {
+                    const int code = cd[k];
                     if (code == 0) continue;
-                    const double v = __ldg(R + (code > 0 ? code : -code) - 1);
-                    row[sl[b]] += code > 0 ? v : -v;
+                    const double val = v[side][k];
+                    if (code == CODE_RHS) {
+                        rv += val;
+                    } else {
+                        const uint32_t slot = ((k < 4 ? w0 : w1) >> (8 * (k & 3))) & 255u;
+                        if (side == 0)
+                            row[slot] = code > 0 ? val : -val;  // a slot is fed at most once per source
+                        else
+                            row[slot] += code > 0 ? val : -val;
+                    }
                 }
-                rv += __ldg(R + s_ridx[a]);
             }
             if (rhs) {
                 if (rhs_add)
                     rhs[r] += rv;
                 else
-                    rhs[r] = rv;
+                    __stcs(rhs + r, rv);
             }
         }
         __syncthreads();
         double *out = vals + base;
-        for (int i = tid; i < len; i += ROWS_PER_CTA) out[i] = tile[i];
+        for (int i = tid; i < len; i += ROWS_PER_CTA) __stcs(out + i, tile[i]);  // written once, never read here
     }
 }
 
@@ -290,7 +366,7 @@ extern "C" int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *u_
     if (!u_val || !u_div || !p_val || !weights || !Tcases || !cases || !coords || !cell_nodes || !kappa || !rec)
         return fail("nfa_hdiv_rt1_records: NULL argument");
     const int nu = dim + 1, nflux = form == 1 ? 2 : 1;
-    const int used = nflux * nu * (nu + 2) + (form == 1 ? 4 : 1);
+    const int used = nflux * nu * ((nu + 3) & ~1) + (form == 1 ? 4 : 1) + nu;
     if (stride < used || (stride & 3)) return fail("nfa_hdiv_rt1_records: record stride too small or not a multiple of 4");
     if (form == 1) {
         if (!delta || !eta || !dest) return fail("nfa_hdiv_rt1_records: the Sundus form needs delta, eta and dest");
@@ -323,18 +399,18 @@ extern "C" int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *u_
 }
 
 extern "C" int nfa_rows_locate(int64_t row_lo, int64_t row_hi, const int32_t *indptr, const int32_t *indices,
-                               const int32_t *row_src, int n_loc, const int32_t *dest, uint8_t *slots,
+                               const int32_t *row_src, int n_loc, const int8_t *codes, const int32_t *dest, uint8_t *slots,
                                nfa_stream stream) {
     const int64_t n_rows = row_hi - row_lo;
     if (n_rows <= 0) return 0;
-    if (!indptr || !indices || !row_src || !dest || !slots) return fail("nfa_rows_locate: NULL argument");
+    if (!indptr || !indices || !row_src || !codes || !dest || !slots) return fail("nfa_rows_locate: NULL argument");
     if (n_loc < 1 || n_loc > 32) return fail("nfa_rows_locate: 1 to 32 local dofs");
     cudaStream_t s = (cudaStream_t)stream;
     int *d_flag = nullptr, h_flag = 0;
     NFA_CUDA(cudaMalloc(&d_flag, sizeof(int)));
     cudaMemsetAsync(d_flag, 0, sizeof(int), s);
-    rows_locate_kernel<<<grid_for(2 * n_rows, 256), 256, 0, s>>>(n_rows, row_lo, indptr, indices, row_src, n_loc, dest,
-                                                                 slots, d_flag);
+    rows_locate_kernel<<<grid_for(2 * n_rows, 256), 256, 0, s>>>(n_rows, row_lo, indptr, indices, row_src, n_loc, codes,
+                                                                 dest, slots, d_flag);
     count_launch();
     cudaError_t e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -347,13 +423,16 @@ extern "C" int nfa_rows_locate(int64_t row_lo, int64_t row_hi, const int32_t *in
 }
 
 extern "C" int nfa_rows_expand(int64_t row_lo, int64_t row_hi, int max_row_len, const int32_t *indptr,
-                               const int32_t *row_src, const uint8_t *slots, int n_loc, const int16_t *emap,
-                               const int16_t *ridx, const double *rec, int stride, double *vals, double *rhs, int rhs_add,
+                               const int32_t *row_src, const uint8_t *slots, int n_loc, const int32_t *roff,
+                               const int8_t *codes, const double *rec, int stride, double *vals, double *rhs, int rhs_add,
                                nfa_stream stream) {
     if (row_hi <= row_lo) return 0;
-    if (!indptr || !row_src || !slots || !emap || !ridx || !rec || !vals) return fail("nfa_rows_expand: NULL argument");
+    if (!indptr || !row_src || !slots || !roff || !codes || !rec || !vals) return fail("nfa_rows_expand: NULL argument");
     if (n_loc < 1 || n_loc > 32) return fail("nfa_rows_expand: 1 to 32 local dofs");
     if (max_row_len < 1 || max_row_len > 256) return fail("nfa_rows_expand: rows of 1 to 256 entries");
+    if (stride & 1) return fail("nfa_rows_expand: the record stride must be even (16-byte aligned runs)");
+    if (((uintptr_t)rec & 15) || ((uintptr_t)slots & 15) || ((uintptr_t)row_src & 7))
+        return fail("nfa_rows_expand: records / slots / sources must be 16- / 16- / 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = sizeof(double) * (size_t)ROWS_PER_CTA * max_row_len;
     if (smem > 200 * 1024) return fail("nfa_rows_expand: rows too long for the shared-memory image");
@@ -364,7 +443,7 @@ extern "C" int nfa_rows_expand(int64_t row_lo, int64_t row_hi, int max_row_len, 
     NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_expand_kernel, ROWS_PER_CTA, smem));
     const int64_t n_blocks = (row_hi - row_lo + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
     const int grid = (int)std::min<int64_t>(n_blocks, (int64_t)n_sm * std::max(per_sm, 1));
-    rows_expand_kernel<<<grid, ROWS_PER_CTA, smem, s>>>(row_lo, row_hi, indptr, row_src, slots, n_loc, emap, ridx, rec,
+    rows_expand_kernel<<<grid, ROWS_PER_CTA, smem, s>>>(row_lo, row_hi, indptr, row_src, slots, n_loc, roff, codes, rec,
                                                         stride, vals, rhs, rhs_add);
     NFA_LAUNCH_CHECK();
     return 0;

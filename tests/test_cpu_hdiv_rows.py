@@ -11,10 +11,9 @@ from oracle import ref_assembly, ref_forms
 from tests.parity_helpers import SundusCase, mixed_poisson_case
 
 
-def expand_rows_host(indptr, row_lo, row_src, slots, emap, ridx, rec):
-    """numpy restatement of ``rows_expand_kernel`` (used by the CPU tests of the tables; never by the product path)."""
+def expand_rows_host(indptr, row_lo, row_src, slots, roff, codes, rec):
+    """numpy restatement of ``rows_expand_kernel`` (csrc/nfa_hdivrows.cu)."""
     n_rows = len(row_src)
-    n_loc = emap.shape[0]
     vals = np.zeros(int(indptr[row_lo + n_rows] - indptr[row_lo]))
     rhs = np.zeros(n_rows)
     base = int(indptr[row_lo])
@@ -25,20 +24,24 @@ def expand_rows_host(indptr, row_lo, row_src, slots, emap, ridx, rec):
             if s < 0:
                 continue
             c, a = s >> 5, s & 31
-            for b in range(n_loc):
-                code = int(emap[a, b])
+            for k in range(hdiv_rows.RUN):
+                code = int(codes[a, k])
                 if code == 0:
                     continue
-                v = rec[c, abs(code) - 1]
-                vals[off + int(slots[r, side, b])] += v if code > 0 else -v
-            rhs[r] += rec[c, int(ridx[a])]
+                v = rec[c, roff[a] + k]
+                if code == hdiv_rows.CODE_RHS:
+                    rhs[r] += v
+                elif side == 0:
+                    vals[off + int(slots[r, side, k])] = v if code > 0 else -v
+                else:
+                    vals[off + int(slots[r, side, k])] += v if code > 0 else -v
     return vals, rhs
 
 
-def locate_slots_host(indptr, indices, row_lo, row_src, dest):
-    """numpy restatement of ``rows_locate_kernel`` (CPU tests only)."""
-    n_rows, n_loc = len(row_src), dest.shape[1]
-    slots = np.zeros((n_rows, 2, n_loc), dtype=np.uint8)
+def locate_slots_host(indptr, indices, row_lo, row_src, codes, dest):
+    """numpy restatement of ``rows_locate_kernel``."""
+    n_rows = len(row_src)
+    slots = np.zeros((n_rows, 2, hdiv_rows.RUN), dtype=np.uint8)
     for r in range(n_rows):
         b0, b1 = int(indptr[row_lo + r]), int(indptr[row_lo + r + 1])
         seg = np.asarray(indices[b0:b1])
@@ -46,10 +49,16 @@ def locate_slots_host(indptr, indices, row_lo, row_src, dest):
             s = int(row_src[r, side])
             if s < 0:
                 continue
-            pos = np.searchsorted(seg, dest[s >> 5])
-            if np.any(pos >= len(seg)) or np.any(seg[np.minimum(pos, len(seg) - 1)] != dest[s >> 5]):
-                raise ValueError("a local column is missing from the row's CSR segment")
-            slots[r, side] = pos
+            c, a = s >> 5, s & 31
+            for k in range(hdiv_rows.RUN):
+                code = int(codes[a, k])
+                if code == 0 or code == hdiv_rows.CODE_RHS:
+                    continue
+                col = dest[c, abs(code) - 1]
+                pos = int(np.searchsorted(seg, col))
+                if pos >= len(seg) or seg[pos] != col:
+                    raise ValueError("a local column is missing from the row's CSR segment")
+                slots[r, side, k] = pos
     return slots
 
 
@@ -85,9 +94,16 @@ def _check(dest, n_dof, emap, ridx, stride, blocks, want):
         hits = [(c, a) for c in range(len(dest)) for a in range(dest.shape[1]) if dest[c, a] == r]
         got = [(int(s) >> 5, int(s) & 31) for s in src[r] if s >= 0]
         assert got == hits
-    slots = locate_slots_host(indptr, indices, 0, src, dest)
+    runs = hdiv_rows.row_runs(emap, ridx)
+    assert runs is not None
+    roff, codes = runs
+    assert not (roff % 2).any() and (roff + hdiv_rows.RUN <= stride + hdiv_rows.RUN - 2).all()
+    for a in range(len(roff)):  # the 16-byte loads of a run stay inside the record
+        used = int(np.flatnonzero(codes[a]).max()) + 1
+        assert roff[a] + (used + 1) // 2 * 2 <= stride
+    slots = locate_slots_host(indptr, indices, 0, src, codes, dest)
     rec = _records_from_local(emap, ridx, stride, blocks)
-    vals, res = expand_rows_host(indptr, 0, src, slots, emap, ridx, rec)
+    vals, res = expand_rows_host(indptr, 0, src, slots, roff, codes, rec)
     assert np.allclose(vals, data, rtol=1e-13, atol=1e-13 * np.abs(data).max())
     assert np.allclose(res, rhs, rtol=1e-13, atol=1e-13 * np.abs(rhs).max())
 
