@@ -35,6 +35,16 @@ def time_steps(torch, fn, steps, warmup):
     return e0.elapsed_time(e1) / steps
 
 
+def graph_ms(torch, asm, state, rhs, steps):
+    """The same reassembly replayed from one CUDA graph (``GPUAssembler.capture``): no per-launch host work."""
+    try:
+        graph = asm.capture(state, rhs)
+    except Exception as exc:  # value-dependent patterns cannot be captured
+        print("graph capture failed: %r" % (exc,), file=sys.stderr)
+        return None
+    return time_steps(torch, graph.replay, steps, 3)
+
+
 def oracle_rate(case, n_cells):
     """elements/s of the oracle on the first ``n_cells`` cells of the case's volume form (1 core)."""
     from oracle import ref_assembly
@@ -182,6 +192,7 @@ def run_sundus(mesh, n_steps):
         asm.run(state, rhs)
 
     ms = time_steps(torch, step, n_steps, 3)
+    ms_graph = graph_ms(torch, asm, state, rhs, n_steps)
     # a full API step of a time loop: new time -> loads re-evaluated on the host, kernels, residual downloaded
     t0 = time.perf_counter()
     for k in range(3):
@@ -196,7 +207,8 @@ def run_sundus(mesh, n_steps):
                 "on one plan" % n_steps,
         "cells": n_cells, "n_dof": int(space.n_dof), "nnz": int(plan.nnz), "n_loc": 10, "path": path_of(plan),
         "roofline": rows_roofline(state, ms),
-        "ms_per_reassembly_kernels": ms, "elements_per_s": n_cells / (ms * 1e-3), "plans_built": len(asm._plans),
+        "ms_per_reassembly_kernels": ms, "ms_per_reassembly_graph_replay": ms_graph,
+        "elements_per_s": n_cells / (ms * 1e-3), "plans_built": len(asm._plans),
         "first_assembly_s": first, "api_step_s_with_host_callables": api, "plan_build_s": plan.build_seconds,
         "steps": n_steps, "dtype": "f64",
     }), flush=True)
@@ -241,6 +253,7 @@ def run_sundus_md(n, n_steps):
         asm.run(state, rhs)
 
     ms = time_steps(torch, step, n_steps, 3)
+    ms_graph = graph_ms(torch, asm, state, rhs, n_steps)
     # the time loop through the API: a new time per step (loads re-evaluated on the host from the cached points), a new
     # iterate, kernels, residual downloaded
     t0 = time.perf_counter()
@@ -266,7 +279,8 @@ def run_sundus_md(n, n_steps):
                 "fields on the fracture + Robin coupling of both fluxes, %d reassemblies on one plan" % n_steps,
         "cells": n_cells, "fracture_cells": int(len(triples)), "n_dof": int(n_dof), "nnz": int(plan.nnz), "path": path_of(plan),
         "roofline": rows_roofline(state, ms),
-        "ms_per_reassembly_kernels": ms, "elements_per_s": (n_cells + len(triples)) / (ms * 1e-3), "plans_built": len(asm._plans),
+        "ms_per_reassembly_kernels": ms, "ms_per_reassembly_graph_replay": ms_graph,
+        "elements_per_s": (n_cells + len(triples)) / (ms * 1e-3), "plans_built": len(asm._plans),
         "first_assembly_s": first, "api_step_s_new_time": api, "api_step_s_newton_iteration": api_newton,
         "plan_build_s": plan.build_seconds, "host_mesh_space_s": t_host, "steps": n_steps, "dtype": "f64",
     }), flush=True)
