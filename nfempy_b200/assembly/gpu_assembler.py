@@ -77,6 +77,7 @@ class _Plan:
 
     def __init__(self):
         self.rows = None  # row-owner path: {segment index: tables}, see _build_row_plan
+        self.rows_cover_all = False
         self.plan = None  # nfa_plan* with gather lists
         self.pattern = None  # nfa_plan* adopting the block plan's pattern (fused mode)
         self.bplan = None
@@ -283,7 +284,7 @@ class GPUAssembler:
         """Plan of a form list whose volume forms ``direct`` are assembled by row owner: (1) the CSR of the WHOLE list
         (every segment's pairs, so boundary / coupling forms may add columns), (2) per direct segment the rows' sources and
         the CSR slot of every local column (``nfa_rows_locate``), (3) gather lists of the other segments merged into the
-        CSR.  The direct segments' row ranges must tile ``[0, n_dof)``: every value is then written by exactly one row
+        CSR.  The direct segments' row ranges must not overlap: every value of those rows is then written by exactly one row
         thread before the other segments add to it."""
         nseg = len(entries)
         # row sources first (cheap, and the test that decides whether the path applies at all)
@@ -297,8 +298,12 @@ class GPUAssembler:
             rows[i] = {"lo": lo, "hi": hi, "src": src}
             ranges.append((lo, hi))
         ranges.sort()
-        if ranges[0][0] != 0 or ranges[-1][1] != p.n_dof or any(a[1] != b[0] for a, b in zip(ranges, ranges[1:])):
+        if any(a[1] > b[0] for a, b in zip(ranges, ranges[1:])):  # a row fed by two direct forms
             raise _RowsUnavailable()
+        # rows outside the direct forms' ranges (a sequence over part of the cells: one rank's share of a partitioned mesh)
+        # are fed by the other segments only, which ADD to the zeroed values
+        p.rows_cover_all = ranges[0][0] == 0 and ranges[-1][1] == p.n_dof and \
+            all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
         h0 = ctypes.c_void_p()
         flags = (ctypes.c_int32 * nseg)(*([3] * nseg))  # matrix pairs of every segment, no right-hand-side lists
         _lib.check(lib.nfa_plan_create(p.n_dof, nseg, dest_ptrs, n_items, n_loc, flags, None, ctypes.byref(h0), stream),
@@ -579,7 +584,7 @@ class GPUAssembler:
         else:
             overwrite = fresh and has_load  # nfa_bplan_gather_load writes every row (zeros for nodes without cells)
         if plan.rows:  # the row threads write every right-hand-side row of a fresh buffer themselves
-            overwrite = fresh
+            overwrite = fresh and plan.rows_cover_all
         self.last_rhs_fill = fresh and not overwrite  # a torch fill kernel ran (launch accounting)
         if rhs_dev is None:
             rhs_dev = (torch.empty if (overwrite and not rows_only) else torch.zeros)(plan.n_dof, dtype=torch.float64, device=dev.device)
@@ -670,7 +675,8 @@ class GPUAssembler:
     def _run_rows(self, lib, dev, plan, entries, datas, dests, jac, rhs_dev, rhs_add, stream):
         """Row-owner segments (hdiv_rows.py): records kernel of the form, then one thread per matrix row.  The rows kernel
         OVERWRITES the CSR values of its rows; values assembled earlier are kept by expanding into a scratch array first."""
-        target = jac.values_dev if jac.is_zero else torch.empty_like(jac.values_dev)
+        target = jac.values_dev if jac.is_zero else \
+            (torch.empty_like if plan.rows_cover_all else torch.zeros_like)(jac.values_dev)
         keep = []
         for i, t in plan.rows.items():
             (_, kind, _, form, _), data, dest = entries[i], datas[i], dests[i]

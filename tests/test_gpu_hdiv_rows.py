@@ -130,3 +130,32 @@ def test_row_owner_is_deterministic():
     one = [np.array(v, copy=True) for v in asm.assemble()]
     two = asm.assemble()
     assert np.array_equal(one[2], two[2]) and np.array_equal(one[3], two[3])
+
+
+def test_row_owner_on_part_of_the_cells(monkeypatch):
+    """A sequence over part of the cells (one rank's share of a partitioned mesh): rows outside the share stay empty or
+    are fed by the boundary form only; same CSR as the two-stage path, also when added onto existing values."""
+    from nfempy_b200.assembly import GPUAssembler
+
+    case = SundusCase(dim=3, k=1, n=3)
+    space = case.space()
+    alphas = SundusCase.alphas(space.n_dof)
+
+    def run():
+        asm = GPUAssembler(space, None, np.zeros(space.n_dof))
+        forms = case.gpu_forms(space, alphas)
+        n_cells = len(space.discrete_spaces["mp"].elements)
+        forms["volume"][1] = list(range(7, n_cells - 5))
+        asm.form_to_input_list = forms
+        once = [np.array(v, copy=True) for v in asm.assemble()]
+        asm.scatter_forms()
+        return asm, once, asm.jacobian.getValuesCSR()[2].copy(), asm.residual.copy()
+
+    asm, once, twice_vals, twice_rhs = run()
+    assert _took_rows(asm) and not list(asm._plans.values())[0].rows_cover_all
+    monkeypatch.setenv("NFA_HDIV_ROWS", "0")
+    asm2, ref, ref_twice_vals, ref_twice_rhs = run()
+    assert not _took_rows(asm2)
+    compare_csr(once, ref, 1e-13)
+    assert np.allclose(twice_vals, ref_twice_vals, rtol=1e-13, atol=1e-13 * np.abs(ref_twice_vals).max())
+    assert np.allclose(twice_rhs, ref_twice_rhs, rtol=1e-13, atol=1e-13 * np.abs(ref_twice_rhs).max())
