@@ -391,3 +391,56 @@ class ShardedAssembler:
     @staticmethod
     def _peer(table, rows):
         return next(q for q, v in table.items() if v is rows)
+
+
+class HaloReplicatedAssembler:
+    """One rank's share of a cell-partitioned assembly WITHOUT an exchange, for spaces in which a dof belongs to at most two
+    cells -- H(div) facet dofs + cell-local dofs: BASELINE configs 3, 4 and 5.
+
+    Rank r owns the cells ``[bounds[r], bounds[r+1])`` and assembles them TOGETHER with the cells that share a dof with
+    them (one layer across a partition face, ``streamed.partition_cells``): every row whose lowest cell is the rank's own is
+    then complete on the rank, so the ranks' row blocks are final without any data-path collective (the
+    path shards by independent partitions; the halo cells are assembled twice instead of exchanged).  Boundary forms keep
+    the items whose rows the rank owns (a boundary facet's dofs belong to one cell).  ``form_to_input_list`` is the
+    GLOBAL list a ``SequentialAssembler`` would get (R/src/assembly/SequentialAssembler.py:13-86); volume forms must run
+    over all cells.  ``assemble()`` returns ``(indptr, indices, values, rhs)`` in global numbering plus ``owned_rows``;
+    only the owned rows are meaningful.  The lowest-order forms go through the row-owner kernels (``hdiv_rows.py``)."""
+
+    _VOLUME = ("form", "time_dependent_form")
+    _BOUNDARY = ("bc_form", "time_dependent_bc_form")
+
+    def __init__(self, space, world, rank, device=None):
+        from .gpu_assembler import GPUAssembler
+        from .streamed import partition_cells
+
+        self.space, self.world, self.rank = space, int(world), int(rank)
+        self.cells, self.owned_rows, self.cell_range = partition_cells(space.destination_table(), self.world, self.rank)
+        self.asm = GPUAssembler(space, None, np.zeros(int(space.n_dof)), device=device)
+        self._owned_mask = np.zeros(int(space.n_dof), dtype=bool)
+        self._owned_mask[self.owned_rows] = True
+
+    def set_forms(self, form_to_input_list):
+        mine = {}
+        for name, entry in form_to_input_list.items():
+            kind, sequence, form = entry[0], entry[1], entry[2]
+            n_total = form.n_items_total()
+            if kind in self._VOLUME:
+                if len(sequence) != n_total:
+                    raise NotImplementedError("HaloReplicatedAssembler: volume forms must be listed over all cells")
+                items = self.cells
+            elif kind in self._BOUNDARY:
+                seq = np.asarray(list(sequence), dtype=np.int64)
+                rows = np.asarray(form.dest_table())[seq]
+                keep = self._owned_mask[rows]
+                if np.any(keep.any(axis=1) != keep.all(axis=1)):
+                    raise NotImplementedError("HaloReplicatedAssembler: a boundary item straddles two ranks' rows")
+                items = seq[keep[:, 0]]
+            else:
+                raise NotImplementedError("HaloReplicatedAssembler: form type %r" % (kind,))
+            mine[name] = [kind, items, form] + list(entry[3:])
+        self.asm.form_to_input_list = mine
+        return self
+
+    def assemble(self):
+        indptr, indices, values, rhs = self.asm.assemble()
+        return indptr, indices, values, rhs, self.owned_rows

@@ -142,3 +142,82 @@ def test_interface_exchange_over_gloo_matches_single_process(world):
         assert p.exitcode == 0
     ok, n_owned, n_dof = out.get(timeout=10)
     assert ok == 1 and n_owned == n_dof
+
+
+# ---- halo-replicated partition (H(div) spaces: no exchange) -----------------------------------------------------------
+def _sundus_space(n=3):
+    from tests.parity_helpers import SundusCase
+
+    case = SundusCase(dim=3, k=1, n=n)
+    return case, case.space()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4])
+def test_halo_replicated_partition_invariants(world):
+    from nfempy_b200.assembly.sharding import HaloReplicatedAssembler
+
+    case, space = _sundus_space()
+    dest = space.destination_table()
+    n_bc = len(space.discrete_spaces["mp"].bc_elements)
+    owned_by, bc_by = np.full(space.n_dof, -1), np.full(n_bc, -1)
+    for r in range(world):
+        h = HaloReplicatedAssembler(space, world, r).set_forms(case.gpu_forms(space, case.alphas(space.n_dof)))
+        assert (owned_by[h.owned_rows] == -1).all()
+        owned_by[h.owned_rows] = r
+        c0, c1 = h.cell_range
+        assembled = np.zeros(len(dest), dtype=bool)
+        assembled[h.cells] = True
+        assert assembled[c0:c1].all()
+        # every cell that feeds an owned row is assembled on the rank: the rows are complete without an exchange
+        feeds = np.isin(dest, h.owned_rows).any(axis=1)
+        assert assembled[feeds].all()
+        kind, items, form = h.asm.form_to_input_list["bc"][:3]
+        assert (bc_by[items] == -1).all()
+        bc_by[items] = r
+        assert np.array_equal(h.asm.form_to_input_list["volume"][1], h.cells)
+    assert (owned_by >= 0).all() and (bc_by >= 0).all()
+
+
+def _halo_worker(rank, world, port, out):
+    from nfempy_b200.assembly.sharding import HaloReplicatedAssembler
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case, space = _sundus_space()
+        dest = space.destination_table()
+        n_dof = space.n_dof
+        h = HaloReplicatedAssembler(space, world, rank)
+        Ke, re = _local_blocks(len(dest), dest.shape[1])
+        indptr, indices, vals, rhs = _assemble(dest, Ke, re, n_dof, h.cells)  # the rank's cells + halo, all weighing 1
+        g_indptr, g_indices, g_vals, g_rhs = _assemble(dest, Ke, re, n_dof, np.arange(len(dest)))
+        ok = True
+        for r in h.owned_rows:
+            a, b = indptr[r], indptr[r + 1]
+            ga, gb = g_indptr[r], g_indptr[r + 1]
+            ok &= np.array_equal(indices[a:b], g_indices[ga:gb]) and np.array_equal(vals[a:b], g_vals[ga:gb])
+        ok &= np.array_equal(rhs[h.owned_rows], g_rhs[h.owned_rows])
+        flag = torch.tensor([1 if ok else 0])
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        owners = torch.zeros(n_dof, dtype=torch.int64)
+        owners[torch.as_tensor(h.owned_rows)] = 1
+        dist.all_reduce(owners)  # every row owned exactly once across the ranks
+        if rank == 0:
+            out.put((int(flag.item()), int(owners.min().item()), int(owners.max().item())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_replicated_rows_are_final_without_exchange_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    assert out.get(timeout=10) == (1, 1, 1)

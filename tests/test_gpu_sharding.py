@@ -110,3 +110,33 @@ def test_peer_memory_exchange_loopback(world):
         import ctypes
 
         _lib.load().nfa_p2p_free(ctypes.c_void_p(a["base"]))
+
+
+@pytest.mark.parametrize("which,world", [("sundus", 3), ("poisson", 2)])
+def test_halo_replicated_ranks_reproduce_the_single_gpu_rows(which, world):
+    """H(div) spaces shard without an exchange (``HaloReplicatedAssembler``): every rank's OWNED rows -- pattern, values,
+    right-hand side -- are bit-identical to the single-GPU assembly of the whole mesh, and the ranks' rows tile the
+    system.  The ranks run one after the other on this device; the row-owner kernels do the work."""
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.assembly.sharding import HaloReplicatedAssembler
+    from nfempy_b200.mesh import box_tet_mesh
+    from tests.parity_helpers import SundusCase, mixed_poisson_case
+
+    mesh = box_tet_mesh(4, jitter=0.2, shuffle_local_nodes=True)
+    case = SundusCase(dim=3, k=1, mesh=mesh) if which == "sundus" else mixed_poisson_case(dim=3, k=1, mesh=mesh, varying=True)
+    space = case.space()
+    alphas = SundusCase.alphas(space.n_dof) if which == "sundus" else None
+    whole = GPUAssembler(space, None, np.zeros(space.n_dof))
+    whole.form_to_input_list = case.gpu_forms(space, alphas)
+    g_indptr, g_indices, g_vals, g_rhs = [np.array(v, copy=True) for v in whole.assemble()]
+    seen = np.zeros(space.n_dof, dtype=int)
+    for rank in range(world):
+        h = HaloReplicatedAssembler(space, world, rank).set_forms(case.gpu_forms(space, alphas))
+        indptr, indices, vals, rhs, owned = h.assemble()
+        assert list(h.asm._plans.values())[0].rows is not None  # the row-owner path, on part of the cells
+        seen[owned] += 1
+        for r in owned:
+            a, b, ga, gb = indptr[r], indptr[r + 1], g_indptr[r], g_indptr[r + 1]
+            assert np.array_equal(indices[a:b], g_indices[ga:gb]) and np.array_equal(vals[a:b], g_vals[ga:gb])
+        assert np.array_equal(rhs[owned], g_rhs[owned])
+    assert (seen == 1).all()
