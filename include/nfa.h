@@ -216,22 +216,24 @@ int nfa_rows_copy_i32(int64_t n_rows, const int64_t *d_indptr, const int64_t *d_
  * Runs: local row a of an item reads the record doubles [d_roff[a], d_roff[a] + 8) (d_roff even); d_codes int8 [n_loc][8]
  *   says what entry k of the run is for that row: 0 = nothing, +-(b + 1) = local column b with that sign (each column at
  *   most once; columns without a code are structural zeros, stored as 0.0), 127 = the row's residual.
- * nfa_rows_locate (one-off): d_row_src int32 [n_rows][2] names the one or two sources of row row_lo + k as
- *   item * 32 + local row (-1 = none; ascending item order), d_dest int32 [n_items][n_loc] the items' global dofs;
- *   writes d_slots uint8 [n_rows][2][8] = position of every run entry's column inside the row's CSR segment.
- * nfa_rows_expand: one thread per row; every CSR value of rows [row_lo, row_hi) is overwritten with the sum of its
- *   sources' entries, lower item first; the right-hand side row is the sum of the sources' residual entries (rhs_add:
- *   added to d_rhs instead of stored). */
+ * nfa_rows_locate (one-off): d_rows int32 [n_rows] lists the rows the items feed (ascending), d_row_src int32 [n_rows][2]
+ *   names the one or two sources of each as item * 32 + local row (-1 = none; ascending item order), d_dest int32
+ *   [n_items][n_loc] the items' global dofs; writes d_slots uint8 [n_rows][2][8] = position of every run entry's column
+ *   inside the row's CSR segment.
+ * nfa_rows_expand: d_blocks int32 [n_blocks][4] = (first row, number of CONSECUTIVE rows <= 256, index of the first row
+ *   in d_rows / d_row_src / d_slots, 0); one CTA pass per block, one thread per row; every CSR value of the listed rows
+ *   is overwritten with the sum of its sources' entries, lower item first; the right-hand side row is the sum of the
+ *   sources' residual entries (rhs_add: added to d_rhs instead of stored).  Rows outside the blocks are not touched. */
 int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *d_u_val, const double *d_u_div, const double *d_p_val,
                          const double *d_weights, const double *d_Tcases, const int8_t *d_cases, const double *d_coords,
                          const int32_t *d_cell_nodes, int64_t n_cells, const double *d_kappa, int64_t ksc, int64_t ksq,
                          const double *d_delta, int64_t dsc, int64_t dsq, const double *d_eta, int64_t esc, int64_t esq,
                          double delta_t, const double *d_f_f, const double *d_f_r, const double *d_alpha,
                          const double *d_alpha_prev, const int32_t *d_dest, int stride, double *d_rec, nfa_stream stream);
-int nfa_rows_locate(int64_t row_lo, int64_t row_hi, const int32_t *d_indptr, const int32_t *d_indices,
+int nfa_rows_locate(int64_t n_rows, const int32_t *d_rows, const int32_t *d_indptr, const int32_t *d_indices,
                     const int32_t *d_row_src, int n_loc, const int8_t *d_codes, const int32_t *d_dest, uint8_t *d_slots,
                     nfa_stream stream);
-int nfa_rows_expand(int64_t row_lo, int64_t row_hi, int max_row_len, const int32_t *d_indptr, const int32_t *d_row_src,
+int nfa_rows_expand(int64_t n_blocks, const int32_t *d_blocks, int max_row_len, const int32_t *d_indptr, const int32_t *d_row_src,
                     const uint8_t *d_slots, int n_loc, const int32_t *d_roff, const int8_t *d_codes, const double *d_rec,
                     int stride, double *d_vals, double *d_rhs, int rhs_add, nfa_stream stream);
 /* pattern-only plan over a caller-owned CSR (kept alive by the caller): base of nfa_plan_create for the other segments */

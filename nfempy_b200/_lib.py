@@ -71,8 +71,8 @@ SIGNATURES = {
         [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _d,
          _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp],
     ),
-    "nfa_rows_locate": (_i, [_i64, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "nfa_rows_expand": (_i, [_i64, _i64, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "nfa_rows_locate": (_i, [_i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "nfa_rows_expand": (_i, [_i64, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "nfa_plan_from_csr": (_i, [_i64, _i64, _vp, _vp, ctypes.POINTER(_vp)]),
     "nfa_push_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),
     "nfa_pull_add_rows": (_i, [_vp] * 5 + [_i64] + [_vp] * 5),

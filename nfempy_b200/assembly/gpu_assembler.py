@@ -284,26 +284,25 @@ class GPUAssembler:
         """Plan of a form list whose volume forms ``direct`` are assembled by row owner: (1) the CSR of the WHOLE list
         (every segment's pairs, so boundary / coupling forms may add columns), (2) per direct segment the rows' sources and
         the CSR slot of every local column (``nfa_rows_locate``), (3) gather lists of the other segments merged into the
-        CSR.  The direct segments' row ranges must not overlap: every value of those rows is then written by exactly one row
-        thread before the other segments add to it."""
+        CSR.  The direct segments' row ranges must not overlap: every value of the rows they feed is then written by exactly
+        one row thread before the other segments add to it; rows they do not feed are never visited."""
         nseg = len(entries)
         # row sources first (cheap, and the test that decides whether the path applies at all)
-        rows, ranges = {}, []
+        rows, ranges, n_active = {}, [], 0
         for i in direct:
-            d = dests[i]
-            lo, hi = int(d.min().item()), int(d.max().item()) + 1
-            src = hdiv_rows.row_sources(d, lo, hi)
-            if src is None:
+            found = hdiv_rows.row_sources(dests[i])
+            if found is None:
                 raise _RowsUnavailable()
-            rows[i] = {"lo": lo, "hi": hi, "src": src}
-            ranges.append((lo, hi))
+            rlist, src = found
+            rows[i] = {"rows": rlist, "src": src, "blocks": hdiv_rows.row_blocks(rlist)}
+            ranges.append((int(rlist[0].item()), int(rlist[-1].item()) + 1))
+            n_active += int(rlist.shape[0])
         ranges.sort()
         if any(a[1] > b[0] for a, b in zip(ranges, ranges[1:])):  # a row fed by two direct forms
             raise _RowsUnavailable()
-        # rows outside the direct forms' ranges (a sequence over part of the cells: one rank's share of a partitioned mesh)
-        # are fed by the other segments only, which ADD to the zeroed values
-        p.rows_cover_all = ranges[0][0] == 0 and ranges[-1][1] == p.n_dof and \
-            all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        # rows the direct forms do not feed (a sequence over part of the cells: one rank's share of a partitioned mesh) are
+        # fed by the other segments only, which ADD to the zeroed values
+        p.rows_cover_all = n_active == p.n_dof
         h0 = ctypes.c_void_p()
         flags = (ctypes.c_int32 * nseg)(*([3] * nseg))  # matrix pairs of every segment, no right-hand-side lists
         _lib.check(lib.nfa_plan_create(p.n_dof, nseg, dest_ptrs, n_items, n_loc, flags, None, ctypes.byref(h0), stream),
@@ -322,16 +321,17 @@ class GPUAssembler:
             form, data = entries[i][3], datas[i]
             spec = form.row_spec(data)
             nl = int(dests[i].shape[1])
-            t["max_len"] = int(row_len[t["lo"]:t["hi"]].max().item())
+            t["max_len"] = int(row_len[t["rows"].to(torch.int64)].max().item())
             runs = hdiv_rows.row_runs(spec["emap"], spec["ridx"])
             if t["max_len"] > 256 or t["max_len"] * 8 * 256 > 200 * 1024 or runs is None:
                 raise _RowsUnavailable()
             t["roff"] = torch.as_tensor(runs[0]).to(dev.device)
             t["codes"] = torch.as_tensor(runs[1]).to(dev.device)
-            t["slots"] = torch.empty((t["hi"] - t["lo"], 2, hdiv_rows.RUN), dtype=torch.uint8, device=dev.device)
-            _lib.check(lib.nfa_rows_locate(t["lo"], t["hi"], _lib.ptr(p.indptr), _lib.ptr(p.indices), _lib.ptr(t["src"]), nl,
-                                           _lib.ptr(t["codes"]), _lib.ptr(dests[i]), _lib.ptr(t["slots"]), stream),
-                       "nfa_rows_locate")
+            n_rows = int(t["rows"].shape[0])
+            t["slots"] = torch.empty((n_rows, 2, hdiv_rows.RUN), dtype=torch.uint8, device=dev.device)
+            _lib.check(lib.nfa_rows_locate(n_rows, _lib.ptr(t["rows"]), _lib.ptr(p.indptr), _lib.ptr(p.indices),
+                                           _lib.ptr(t["src"]), nl, _lib.ptr(t["codes"]), _lib.ptr(dests[i]), _lib.ptr(t["slots"]),
+                                           stream), "nfa_rows_locate")
             t["stride"], t["n_loc"] = int(spec["stride"]), nl
         p.rows = rows
         ph = ctypes.c_void_p()
@@ -584,7 +584,7 @@ class GPUAssembler:
         else:
             overwrite = fresh and has_load  # nfa_bplan_gather_load writes every row (zeros for nodes without cells)
         if plan.rows:  # the row threads write every right-hand-side row of a fresh buffer themselves
-            overwrite = fresh and plan.rows_cover_all
+            overwrite = fresh and (plan.rows_cover_all or rows_only)
         self.last_rhs_fill = fresh and not overwrite  # a torch fill kernel ran (launch accounting)
         if rhs_dev is None:
             rhs_dev = (torch.empty if (overwrite and not rows_only) else torch.zeros)(plan.n_dof, dtype=torch.float64, device=dev.device)
@@ -687,7 +687,7 @@ class GPUAssembler:
                 second_dev = None
             rec = torch.empty((data.n_items, t["stride"]), dtype=torch.float64, device=dev.device)
             form.launch_records(data.dev, data, first_dev, second_dev, dest, rec, t["stride"])
-            _lib.check(lib.nfa_rows_expand(t["lo"], t["hi"], t["max_len"], _lib.ptr(plan.indptr), _lib.ptr(t["src"]),
+            _lib.check(lib.nfa_rows_expand(int(t["blocks"].shape[0]), _lib.ptr(t["blocks"]), t["max_len"], _lib.ptr(plan.indptr), _lib.ptr(t["src"]),
                                            _lib.ptr(t["slots"]), t["n_loc"], _lib.ptr(t["roff"]), _lib.ptr(t["codes"]),
                                            _lib.ptr(rec), t["stride"], _lib.ptr(target), _lib.ptr(rhs_dev), rhs_add, stream),
                        "nfa_rows_expand")

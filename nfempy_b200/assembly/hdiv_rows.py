@@ -12,15 +12,19 @@ import numpy as np
 import torch
 
 
-def row_sources(dest, row_lo, row_hi):
-    """``int32 [row_hi - row_lo, 2]``: the one or two sources of every row in ``[row_lo, row_hi)`` as
-    ``item * 32 + local row`` (``-1`` = none), lower item first.  ``dest``: integer tensor ``[n_items, n_loc]`` of global
-    dofs (any device).  Returns ``None`` when a dof belongs to more than two items or is listed twice by one item."""
+ROWS_PER_BLOCK = 256  # rows of one CTA pass of rows_expand_kernel (csrc/nfa_hdivrows.cu)
+
+
+def row_sources(dest):
+    """The rows the items feed and their sources: ``(rows, src)`` with ``rows`` int32 ``[n_rows]`` (ascending global
+    dofs) and ``src`` int32 ``[n_rows, 2]`` = the one or two sources of each row as ``item * 32 + local row`` (``-1`` =
+    none), lower item first.  ``dest``: integer tensor ``[n_items, n_loc]`` of global dofs (any device).  Returns ``None``
+    when a dof belongs to more than two items or is listed twice by one item."""
     n_items, n_loc = int(dest.shape[0]), int(dest.shape[1])
-    if n_loc > 32 or n_items >= 2**26:
+    if n_loc > 32 or n_items >= 2**26 or n_items == 0:
         return None
     flat = dest.reshape(-1).to(torch.int64)
-    if int(flat.min().item()) < row_lo or int(flat.max().item()) >= row_hi:
+    if int(flat.min().item()) < 0 or int(flat.max().item()) >= 2**31 - 1:
         return None
     order = torch.argsort(flat, stable=True)  # ascending dof; ascending (item, local row) inside a dof
     sd = flat[order]
@@ -35,11 +39,29 @@ def row_sources(dest, row_lo, row_hi):
     two = count == 2
     if bool((item[start[two]] == item[start[two] + 1]).any()):
         return None
-    src = torch.full((row_hi - row_lo, 2), -1, dtype=torch.int32, device=dest.device)
-    rows = sd[start] - row_lo
-    src[rows, 0] = code[start]
-    src[rows[two], 1] = code[start[two] + 1]
-    return src.contiguous()
+    src = torch.full((int(start.shape[0]), 2), -1, dtype=torch.int32, device=dest.device)
+    src[:, 0] = code[start]
+    src[two, 1] = code[start[two] + 1]
+    return sd[start].to(torch.int32).contiguous(), src.contiguous()
+
+
+def row_blocks(rows):
+    """Cuts the ascending row list into blocks of at most ``ROWS_PER_BLOCK`` CONSECUTIVE rows: int32 ``[n_blocks, 4]`` =
+    (first row, number of rows, index of the first row in ``rows``, 0)."""
+    n = int(rows.shape[0])
+    r = rows.to(torch.int64)
+    idx = torch.arange(n, device=rows.device, dtype=torch.int64)
+    brk = torch.ones(n, dtype=torch.bool, device=rows.device)
+    brk[1:] = r[1:] != r[:-1] + 1
+    run_start = torch.cummax(torch.where(brk, idx, torch.zeros_like(idx)), 0).values  # index of the run's first row
+    head = ((idx - run_start) % ROWS_PER_BLOCK) == 0
+    first = torch.nonzero(head).reshape(-1)
+    count = torch.cat([first[1:], torch.tensor([n], device=rows.device)]) - first
+    blocks = torch.zeros((int(first.shape[0]), 4), dtype=torch.int32, device=rows.device)
+    blocks[:, 0] = r[first].to(torch.int32)
+    blocks[:, 1] = count.to(torch.int32)
+    blocks[:, 2] = first.to(torch.int32)
+    return blocks.contiguous()
 
 
 def sundus_maps(n_u):

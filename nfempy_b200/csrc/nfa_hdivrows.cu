@@ -216,21 +216,21 @@ constexpr int RUN = 8;
 constexpr int CODE_RHS = 127;
 
 // CSR slot of every run entry of a row's one or two sources inside the row's segment (binary search; one-off)
-__global__ void rows_locate_kernel(int64_t n_rows, int64_t row_lo, const int32_t *__restrict__ indptr,
+__global__ void rows_locate_kernel(int64_t n_rows, const int32_t *__restrict__ rows, const int32_t *__restrict__ indptr,
                                    const int32_t *__restrict__ indices, const int32_t *__restrict__ row_src, int n_loc,
                                    const int8_t *__restrict__ codes, const int32_t *__restrict__ dest,
                                    uint8_t *__restrict__ slots, int *__restrict__ flag) {
     const int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= 2 * n_rows) return;
-    const int64_t rl = id >> 1;
+    const int32_t row = rows[id >> 1];
     const int32_t src = row_src[id];
     uint8_t *out = slots + id * RUN;
     for (int k = 0; k < RUN; ++k) out[k] = 0;
     if (src < 0) return;
     const int64_t c = src >> 5;
     const int a = src & 31;
-    const int32_t b0 = indptr[row_lo + rl], b1 = indptr[row_lo + rl + 1];
-    if (a >= n_loc || dest[c * n_loc + a] != (int32_t)(row_lo + rl)) {
+    const int32_t b0 = indptr[row], b1 = indptr[row + 1];
+    if (a >= n_loc || dest[c * n_loc + a] != row) {
         atomicOr(flag, 4);
         return;
     }
@@ -255,7 +255,7 @@ __global__ void rows_locate_kernel(int64_t n_rows, int64_t row_lo, const int32_t
 }
 
 __global__ void __launch_bounds__(ROWS_PER_CTA)
-    rows_expand_kernel(int64_t row_lo, int64_t row_hi, const int32_t *__restrict__ indptr,
+    rows_expand_kernel(int64_t n_blocks, const int4 *__restrict__ blocks, const int32_t *__restrict__ indptr,
                        const int32_t *__restrict__ row_src, const uint8_t *__restrict__ slots, int n_loc,
                        const int32_t *__restrict__ roff, const int8_t *__restrict__ codes, const double *__restrict__ rec,
                        int stride, double *__restrict__ vals, double *__restrict__ rhs, int rhs_add) {
@@ -273,9 +273,9 @@ __global__ void __launch_bounds__(ROWS_PER_CTA)
         s_len[tid] = len;
     }
     __syncthreads();  // the run tables are read before the first barrier of the loop
-    const int64_t n_blocks = (row_hi - row_lo + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
     for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const int64_t r0 = row_lo + blk * ROWS_PER_CTA, r1 = r0 + ROWS_PER_CTA < row_hi ? r0 + ROWS_PER_CTA : row_hi;
+        const int4 bd = __ldg(blocks + blk);  // first row, rows (<= ROWS_PER_CTA, consecutive), first table entry
+        const int64_t r0 = bd.x, r1 = r0 + bd.y;
         const int32_t base = indptr[r0];
         const int len = indptr[r1] - base;
         const int64_t r = r0 + tid;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(ROWS_PER_CTA)
         double v[2][RUN];
         int a2[2] = {0, 0};
         if (r < r1) {
-            const int64_t rl = r - row_lo;
+            const int64_t rl = (int64_t)bd.z + tid;
             srcs = __ldcs(reinterpret_cast<const int2 *>(row_src) + rl);
             sl = __ldcs(reinterpret_cast<const uint4 *>(slots) + rl);
             row_at = indptr[r] - base;
@@ -398,19 +398,18 @@ extern "C" int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *u_
     return 0;
 }
 
-extern "C" int nfa_rows_locate(int64_t row_lo, int64_t row_hi, const int32_t *indptr, const int32_t *indices,
+extern "C" int nfa_rows_locate(int64_t n_rows, const int32_t *rows, const int32_t *indptr, const int32_t *indices,
                                const int32_t *row_src, int n_loc, const int8_t *codes, const int32_t *dest, uint8_t *slots,
                                nfa_stream stream) {
-    const int64_t n_rows = row_hi - row_lo;
     if (n_rows <= 0) return 0;
-    if (!indptr || !indices || !row_src || !codes || !dest || !slots) return fail("nfa_rows_locate: NULL argument");
+    if (!rows || !indptr || !indices || !row_src || !codes || !dest || !slots) return fail("nfa_rows_locate: NULL argument");
     if (n_loc < 1 || n_loc > 32) return fail("nfa_rows_locate: 1 to 32 local dofs");
     cudaStream_t s = (cudaStream_t)stream;
     int *d_flag = nullptr, h_flag = 0;
     NFA_CUDA(cudaMalloc(&d_flag, sizeof(int)));
     cudaMemsetAsync(d_flag, 0, sizeof(int), s);
-    rows_locate_kernel<<<grid_for(2 * n_rows, 256), 256, 0, s>>>(n_rows, row_lo, indptr, indices, row_src, n_loc, codes,
-                                                                 dest, slots, d_flag);
+    rows_locate_kernel<<<grid_for(2 * n_rows, 256), 256, 0, s>>>(n_rows, rows, indptr, indices, row_src, n_loc, codes, dest,
+                                                                 slots, d_flag);
     count_launch();
     cudaError_t e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -422,17 +421,18 @@ extern "C" int nfa_rows_locate(int64_t row_lo, int64_t row_hi, const int32_t *in
     return 0;
 }
 
-extern "C" int nfa_rows_expand(int64_t row_lo, int64_t row_hi, int max_row_len, const int32_t *indptr,
+extern "C" int nfa_rows_expand(int64_t n_blocks, const int32_t *blocks, int max_row_len, const int32_t *indptr,
                                const int32_t *row_src, const uint8_t *slots, int n_loc, const int32_t *roff,
                                const int8_t *codes, const double *rec, int stride, double *vals, double *rhs, int rhs_add,
                                nfa_stream stream) {
-    if (row_hi <= row_lo) return 0;
-    if (!indptr || !row_src || !slots || !roff || !codes || !rec || !vals) return fail("nfa_rows_expand: NULL argument");
+    if (n_blocks <= 0) return 0;
+    if (!blocks || !indptr || !row_src || !slots || !roff || !codes || !rec || !vals)
+        return fail("nfa_rows_expand: NULL argument");
     if (n_loc < 1 || n_loc > 32) return fail("nfa_rows_expand: 1 to 32 local dofs");
     if (max_row_len < 1 || max_row_len > 256) return fail("nfa_rows_expand: rows of 1 to 256 entries");
     if (stride & 1) return fail("nfa_rows_expand: the record stride must be even (16-byte aligned runs)");
-    if (((uintptr_t)rec & 15) || ((uintptr_t)slots & 15) || ((uintptr_t)row_src & 7))
-        return fail("nfa_rows_expand: records / slots / sources must be 16- / 16- / 8-byte aligned");
+    if (((uintptr_t)rec & 15) || ((uintptr_t)slots & 15) || ((uintptr_t)row_src & 7) || ((uintptr_t)blocks & 15))
+        return fail("nfa_rows_expand: records / slots / blocks must be 16-byte aligned, sources 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = sizeof(double) * (size_t)ROWS_PER_CTA * max_row_len;
     if (smem > 200 * 1024) return fail("nfa_rows_expand: rows too long for the shared-memory image");
@@ -441,10 +441,9 @@ extern "C" int nfa_rows_expand(int64_t row_lo, int64_t row_hi, int max_row_len, 
     NFA_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
     NFA_CUDA(cudaFuncSetAttribute(rows_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NFA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rows_expand_kernel, ROWS_PER_CTA, smem));
-    const int64_t n_blocks = (row_hi - row_lo + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
     const int grid = (int)std::min<int64_t>(n_blocks, (int64_t)n_sm * std::max(per_sm, 1));
-    rows_expand_kernel<<<grid, ROWS_PER_CTA, smem, s>>>(row_lo, row_hi, indptr, row_src, slots, n_loc, roff, codes, rec,
-                                                        stride, vals, rhs, rhs_add);
+    rows_expand_kernel<<<grid, ROWS_PER_CTA, smem, s>>>(n_blocks, reinterpret_cast<const int4 *>(blocks), indptr, row_src,
+                                                        slots, n_loc, roff, codes, rec, stride, vals, rhs, rhs_add);
     NFA_LAUNCH_CHECK();
     return 0;
 }

@@ -86,9 +86,13 @@ def _records_from_local(emap, ridx, stride, blocks):
 
 def _check(dest, n_dof, emap, ridx, stride, blocks, want):
     indptr, indices, data, rhs = want
-    src = hdiv_rows.row_sources(torch.as_tensor(dest), 0, n_dof)
-    assert src is not None
-    src = src.numpy()
+    found = hdiv_rows.row_sources(torch.as_tensor(dest))
+    assert found is not None
+    rows, src = found[0].numpy(), found[1].numpy()
+    assert np.array_equal(rows, np.arange(n_dof))  # the whole mesh: every row is fed
+    cuts = hdiv_rows.row_blocks(found[0]).numpy()
+    assert np.array_equal(cuts[:, 0], np.arange(0, n_dof, hdiv_rows.ROWS_PER_BLOCK)) and cuts[:, 1].sum() == n_dof
+    assert np.array_equal(cuts[:, 0], cuts[:, 2]) and cuts[:, 1].max() <= hdiv_rows.ROWS_PER_BLOCK
     # every row names its (item, local row) sources, lower item first
     for r in range(n_dof):
         hits = [(c, a) for c in range(len(dest)) for a in range(dest.shape[1]) if dest[c, a] == r]
@@ -140,8 +144,13 @@ def test_mixed_poisson_records_expand_to_the_oracle_matrix(dim):
 
 def test_row_sources_refuse_spaces_with_widely_shared_dofs():
     dest = torch.tensor([[0, 1, 2], [2, 3, 4], [4, 2, 5]])  # dof 2 belongs to three items
-    assert hdiv_rows.row_sources(dest, 0, 6) is None
-    assert hdiv_rows.row_sources(torch.tensor([[0, 1, 1]]), 0, 2) is None  # an item lists a dof twice
-    assert hdiv_rows.row_sources(torch.tensor([[0, 1, 7]]), 0, 4) is None  # outside the row range
-    src = hdiv_rows.row_sources(torch.tensor([[3, 1], [1, 2]]), 1, 5).numpy()  # rows 1..4; row 4 has no source
-    assert src.tolist() == [[1, 32], [33, -1], [0, -1], [-1, -1]]
+    assert hdiv_rows.row_sources(dest) is None
+    assert hdiv_rows.row_sources(torch.tensor([[0, 1, 1]])) is None  # an item lists a dof twice
+    rows, src = hdiv_rows.row_sources(torch.tensor([[3, 1], [1, 2]]))  # rows 1, 2, 3 are fed; 0 and 4.. are not
+    assert rows.tolist() == [1, 2, 3] and src.tolist() == [[1, 32], [33, -1], [0, -1]]
+
+
+def test_row_blocks_cut_runs_of_consecutive_rows():
+    rows = torch.tensor(list(range(5, 8)) + list(range(20, 20 + 600)) + [1000], dtype=torch.int32)
+    blocks = hdiv_rows.row_blocks(rows).tolist()
+    assert blocks == [[5, 3, 0, 0], [20, 256, 3, 0], [276, 256, 259, 0], [532, 88, 515, 0], [1000, 1, 603, 0]]

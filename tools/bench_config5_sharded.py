@@ -58,7 +58,9 @@ def main():
     t_prepare = time.perf_counter() - t0
     plan = state[4]
     rhs = torch.zeros(plan.n_dof, dtype=torch.float64, device=state[0].device)
-    graph = asm.capture(state, rhs)
+    # fresh="rows": the rank's kernels replace the right-hand-side rows its cells feed; the other rows of the global-sized
+    # buffer are never swept (a rank's step must not grow with the number of ranks)
+    graph = asm.capture(state, rhs, fresh="rows")
 
     def sync():
         torch.cuda.synchronize()
