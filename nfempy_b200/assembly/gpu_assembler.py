@@ -141,6 +141,9 @@ class GPUAssembler:
         self._state_bufs = []
         self._capturing = False
         self._rows_refused = None
+        # row-owner path only: bool mask [n_dof] of the rows the caller wants (a rank's owned rows); the other rows the listed
+        # cells feed are neither computed nor written
+        self.rows_wanted = None
 
     def invalidate(self):
         """Drops the cached coefficient arrays (the sparsity plans stay)."""
@@ -223,7 +226,8 @@ class GPUAssembler:
         n_loc = (ctypes.c_int32 * nseg)(*[int(d.shape[1]) for d in dests])
         handle = ctypes.c_void_p()
         if direct:
-            self._build_row_plan(lib, dev, p, entries, dests, datas, direct, dest_ptrs, n_items, n_loc, stream)
+            self._build_row_plan(lib, dev, p, entries, dests, datas, direct, dest_ptrs, n_items, n_loc, stream,
+                                 self.rows_wanted)
             torch.cuda.synchronize(dev.device)
             p.build_seconds = time.perf_counter() - t0
             return p
@@ -280,7 +284,7 @@ class GPUAssembler:
         return p
 
     @staticmethod
-    def _build_row_plan(lib, dev, p, entries, dests, datas, direct, dest_ptrs, n_items, n_loc, stream):
+    def _build_row_plan(lib, dev, p, entries, dests, datas, direct, dest_ptrs, n_items, n_loc, stream, rows_wanted=None):
         """Plan of a form list whose volume forms ``direct`` are assembled by row owner: (1) the CSR of the WHOLE list
         (every segment's pairs, so boundary / coupling forms may add columns), (2) per direct segment the rows' sources and
         the CSR slot of every local column (``nfa_rows_locate``), (3) gather lists of the other segments merged into the
@@ -294,6 +298,11 @@ class GPUAssembler:
             if found is None:
                 raise _RowsUnavailable()
             rlist, src = found
+            if rows_wanted is not None:  # a rank's share: rows it does not own are left alone (their cells' halo layer)
+                keep = torch.as_tensor(rows_wanted).to(rlist.device)[rlist.to(torch.int64)]
+                rlist, src = rlist[keep].contiguous(), src[keep].contiguous()
+                if int(rlist.shape[0]) == 0:
+                    raise _RowsUnavailable()
             rows[i] = {"rows": rlist, "src": src, "blocks": hdiv_rows.row_blocks(rlist)}
             ranges.append((int(rlist[0].item()), int(rlist[-1].item()) + 1))
             n_active += int(rlist.shape[0])
@@ -506,7 +515,7 @@ class GPUAssembler:
             direct = tuple(i for i, ((_, kind, _, form, _), data) in enumerate(zip(entries, datas))
                            if kind in ("form", "time_dependent_form") and hasattr(form, "row_spec")
                            and form.row_spec(data) is not None) or None
-        key = self._plan_key(entries, fused_index if direct is None else ("rows",) + direct)
+        key = self._plan_key(entries, fused_index if direct is None else ("rows", id(self.rows_wanted)) + direct)
         if key not in self._plans:
             try:
                 self._plans[key] = self._build_plan(dev, entries, dests, fused_index, direct, datas)

@@ -404,7 +404,7 @@ class HaloReplicatedAssembler:
     the items whose rows the rank owns (a boundary facet's dofs belong to one cell).  ``form_to_input_list`` is the
     GLOBAL list a ``SequentialAssembler`` would get (R/src/assembly/SequentialAssembler.py:13-86); volume forms must run
     over all cells.  ``assemble()`` returns ``(indptr, indices, values, rhs)`` in global numbering plus ``owned_rows``;
-    only the owned rows are meaningful.  The lowest-order forms go through the row-owner kernels (``hdiv_rows.py``)."""
+    only the owned rows are meaningful (on the row-owner path the others are not even computed).  The lowest-order forms go through the row-owner kernels (``hdiv_rows.py``)."""
 
     _VOLUME = ("form", "time_dependent_form")
     _BOUNDARY = ("bc_form", "time_dependent_bc_form")
@@ -418,6 +418,7 @@ class HaloReplicatedAssembler:
         self.asm = GPUAssembler(space, None, np.zeros(int(space.n_dof)), device=device)
         self._owned_mask = np.zeros(int(space.n_dof), dtype=bool)
         self._owned_mask[self.owned_rows] = True
+        self.asm.rows_wanted = self._owned_mask  # the halo cells' other rows belong to other ranks: not computed here
 
     def set_forms(self, form_to_input_list):
         mine = {}
