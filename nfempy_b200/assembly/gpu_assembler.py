@@ -187,8 +187,15 @@ class GPUAssembler:
                 # (R/src/assembly/ScatterFormData.py:59-68) -- handed to the form, which owns the destination rule
                 if not hasattr(form, "interface_dest"):
                     raise NotImplementedError("GPUAssembler: %s does not describe its interface destinations" % type(form).__name__)
-                rows = [[int(e[0]), int(e[1][0]), int(e[1][1])] if np.ndim(e[1]) else [int(v) for v in e] for e in sequence] \
-                    if not isinstance(sequence, np.ndarray) else sequence
+                rows = sequence
+                if not isinstance(sequence, np.ndarray):
+                    try:  # flat triples: one conversion (a Python loop over 10^4 triples costs more than the kernels)
+                        rows = np.asarray(sequence, dtype=np.int64)
+                        if rows.ndim != 2 or rows.shape[1] != 3:
+                            raise ValueError
+                    except (ValueError, TypeError):  # the library's (idx, (idx_p, idx_n)) nesting
+                        rows = [[int(e[0]), int(e[1][0]), int(e[1][1])] if np.ndim(e[1]) else [int(v) for v in e]
+                                for e in sequence]
                 items = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 3)
             else:
                 items = _as_items(sequence, form.n_items_total())
@@ -480,23 +487,28 @@ class GPUAssembler:
         # goes up once: slot k = the k-th distinct vector of the list, one persistent device buffer per slot)
         slots = {}
 
-        def state(vec):
+        def state(vec, want_zero_flag=True):
+            """``want_zero_flag=False``: the caller launches its state terms whatever the vector holds (time-dependent
+            forms), so the host scan for an all-zero vector (a full pass over n_dof doubles per call) is skipped."""
             if vec is None:
                 return None, True
             if id(vec) not in slots:
                 k = len(slots)
                 while len(self._state_bufs) <= k:
                     self._state_bufs.append(None)
-                buf, zero = self._upload(dev, vec, self._state_bufs[k])
+                buf, zero = self._upload(dev, vec, self._state_bufs[k], want_zero_flag)
                 self._state_bufs[k] = buf
-                slots[id(vec)] = (buf, zero)
-            return slots[id(vec)]
+                slots[id(vec)] = [buf, zero, want_zero_flag]
+            elif want_zero_flag and not slots[id(vec)][2]:  # first listed by a time-dependent form: scan now
+                slots[id(vec)][1] = not bool(np.asarray(vec).any())
+                slots[id(vec)][2] = True
+            return slots[id(vec)][0], slots[id(vec)][1]
 
         for (_, kind, _, _, alpha), data in zip(entries, datas):
             if "time_dependent" in kind:
                 (first, second), _t = alpha
-                a0, z0 = state(first)
-                a1, z1 = state(second) if kind == "time_dependent_form" else (None, True)
+                a0, z0 = state(first, False)
+                a1, z1 = state(second, False) if kind == "time_dependent_form" else (None, True)
                 data.alpha_dev, data.alpha_zero = (a0, a1), (z0 and z1)
             else:
                 data.alpha_dev, data.alpha_zero = state(alpha)
@@ -537,9 +549,10 @@ class GPUAssembler:
         return dev, entries, datas, dests, plan, key
 
     @staticmethod
-    def _upload(dev, vec, buf=None):
+    def _upload(dev, vec, buf=None, want_zero_flag=True):
         """``(device buffer, is_zero)`` of a state vector; ``None`` stays ``None`` (the form then has no state at all).
-        The buffer is allocated once and refreshed in place."""
+        The buffer is allocated once and refreshed in place.  ``want_zero_flag=False`` skips the host scan (``is_zero`` is
+        then reported ``False``)."""
         if vec is None:
             return None, True
         host = np.ascontiguousarray(vec, dtype=np.float64).reshape(-1)
@@ -547,7 +560,7 @@ class GPUAssembler:
         if buf is None or buf.shape != src.shape:
             buf = torch.empty(src.shape, dtype=torch.float64, device=dev.device)
         buf.copy_(src, non_blocking=False)
-        return buf, not bool(host.any())
+        return buf, (not bool(host.any())) if want_zero_flag else False
 
     def run(self, state, rhs_dev=None, fresh=False):
         """Launches the kernels of one assembly.  Adds into ``self.jacobian`` and into ``rhs_dev`` (the device residual,
