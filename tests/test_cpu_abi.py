@@ -111,3 +111,20 @@ def test_error_behaviour_of_the_assembler_front_end():
         LEPrimalWeakFormBCDirichlet(space).evaluate_form(0, None)
     with pytest.raises(ValueError):
         GPUAssembler(space, pattern_policy="no_such_policy")
+
+
+def test_chunked_residual_add_matches_numpy(monkeypatch):
+    """``residual += rhs`` of ``scatter_forms()`` for long vectors: chunks on a few host threads, same result."""
+    import numpy as np
+
+    from nfempy_b200.assembly import gpu_assembler
+
+    monkeypatch.setattr(gpu_assembler, "_CHUNK", 101)
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal(1013), rng.standard_normal(1013)
+    want = a + b
+    gpu_assembler._add_into(a, b)
+    assert np.array_equal(a, want)
+    c = np.ones(5)
+    gpu_assembler._add_into(c, np.arange(5.0))  # short vectors: one plain numpy call
+    assert np.array_equal(c, 1.0 + np.arange(5.0))

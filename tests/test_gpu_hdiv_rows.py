@@ -159,3 +159,18 @@ def test_row_owner_on_part_of_the_cells(monkeypatch):
     compare_csr(once, ref, 1e-13)
     assert np.allclose(twice_vals, ref_twice_vals, rtol=1e-13, atol=1e-13 * np.abs(ref_twice_vals).max())
     assert np.allclose(twice_rhs, ref_twice_rhs, rtol=1e-13, atol=1e-13 * np.abs(ref_twice_rhs).max())
+
+
+def test_chunked_state_upload_and_residual_add(monkeypatch):
+    """The host side of ``scatter_forms()`` for long vectors (threaded staging of the state uploads into pinned memory,
+    chunked ``residual += rhs``), forced onto a small problem: same system as the oracle's."""
+    from nfempy_b200.assembly import gpu_assembler
+
+    monkeypatch.setattr(gpu_assembler, "_CHUNK", 37)
+    case = SundusCase(dim=3, k=1, n=2)
+    _, asm = _assembler(case, SundusCase.alphas)
+    got = [np.array(v, copy=True) for v in asm.assemble()]
+    assert len(asm._state_stage) == 2 and asm._state_stage[0] is not None
+    compare_csr(got, case.run_oracle(), RTOL)
+    again = asm.assemble()  # second call: staging buffers and events reused
+    assert np.array_equal(again[2], got[2]) and np.array_equal(again[3], got[3])

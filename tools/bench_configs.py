@@ -273,6 +273,7 @@ def run_sundus_md(n, n_steps):
         asm.residual[:] = 0.0
         asm.scatter_forms()
     api_newton = (time.perf_counter() - t0) / 5
+    split = dict(asm.last_timings)
     n_cells = len(mp0.elements)
     print(json.dumps({
         "case": "config5 (mixed-dimensional): two-flux transport RT1 x RT1 x P0 x P0 in the fractured box (z = 1/2) + the same "
@@ -281,7 +282,7 @@ def run_sundus_md(n, n_steps):
         "roofline": rows_roofline(state, ms),
         "ms_per_reassembly_kernels": ms, "ms_per_reassembly_graph_replay": ms_graph,
         "elements_per_s": (n_cells + len(triples)) / (ms * 1e-3), "plans_built": len(asm._plans),
-        "first_assembly_s": first, "api_step_s_new_time": api, "api_step_s_newton_iteration": api_newton,
+        "first_assembly_s": first, "api_step_s_new_time": api, "api_step_s_newton_iteration": api_newton, "api_newton_split_s": split,
         "plan_build_s": plan.build_seconds, "host_mesh_space_s": t_host, "steps": n_steps, "dtype": "f64",
     }), flush=True)
 
