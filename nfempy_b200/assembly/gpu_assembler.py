@@ -18,7 +18,7 @@ import time
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _host, _lib
 from ..device import space_device
 from ..weak_forms.weak_form import BatchedWeakForm
 from . import hdiv_rows
@@ -44,21 +44,16 @@ def _as_items(sequence, n_total):
     return items
 
 
-_POOL = None
 _CHUNK = 1 << 21  # doubles per host-side work item (16 MB)
 
 
 def _chunks(n):
     """Host passes over long vectors (state upload staging, ``residual += rhs``) are memory-bound numpy calls that release
-    the GIL: cut into chunks and run on a few threads they cost a fraction of one single-threaded sweep."""
-    global _POOL
-    if n < 2 * _CHUNK:
+    the GIL: cut into chunks and run on a few threads (``_host.pool``) they cost a fraction of one single-threaded sweep."""
+    pool = _host.pool() if n >= 2 * _CHUNK else None
+    if pool is None:
         return None, [(0, n)]
-    if _POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-
-        _POOL = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 4) // 2)))
-    return _POOL, [(a, min(n, a + _CHUNK)) for a in range(0, n, _CHUNK)]
+    return pool, _host.parts(n, _CHUNK)
 
 
 def _add_into(dst, src):

@@ -128,3 +128,31 @@ def test_chunked_residual_add_matches_numpy(monkeypatch):
     c = np.ones(5)
     gpu_assembler._add_into(c, np.arange(5.0))  # short vectors: one plain numpy call
     assert np.array_equal(c, 1.0 + np.arange(5.0))
+
+
+def test_threaded_coefficient_evaluation_matches_one_call(monkeypatch):
+    """Coefficient callables over many points are evaluated chunk by chunk on host threads: same arrays as one call, for
+    scalar, constant, vector and time-dependent callables; callables that do not broadcast still work point by point."""
+    import math
+
+    import numpy as np
+
+    from nfempy_b200 import coefficients
+
+    rng = np.random.default_rng(5)
+    x = rng.random((37, 4, 3))
+    cases = [
+        (lambda x, y, z, t: np.array([np.sin(x + t) + y]), 1, (0.3,)),
+        (lambda x, y, z: 2.0 + x, None, ()),
+        (lambda x, y, z: 1.5, None, ()),
+        (lambda x, y, z: np.array([x * y, z + 1.0, np.cos(x)]), 3, ()),
+        (lambda x, y, z: np.array([1.0, 2.0, 3.0]), 3, ()),
+    ]
+    for fn, nc, extra in cases:
+        monkeypatch.setattr(coefficients, "_EVAL_CHUNK", 1 << 40)
+        want = coefficients.evaluate(fn, x, nc, extra)
+        monkeypatch.setattr(coefficients, "_EVAL_CHUNK", 11)
+        got = coefficients.evaluate(fn, x, nc, extra)
+        assert got.shape == want.shape and np.array_equal(got, want)
+    got = coefficients.evaluate(lambda x, y, z: math.sin(x) + y, x)  # scalars only: the point-by-point convention
+    assert np.allclose(got, np.sin(x[:, :, 0]) + x[:, :, 1])
