@@ -150,9 +150,22 @@ class SundusDualWeakFormBCDirichlet(BatchedWeakForm):
     def dest_table(self):
         return self.space.bc_destination_table()
 
-    def prepare(self, dev, items=None, arrays=None, t=0.0):
+    supports_reuse = True
+
+    def prepare(self, dev, items=None, arrays=None, t=0.0, reuse=None):
+        """``reuse``: the ``FormData`` of the same form / sequence / functions at another time -- the facet geometry, trace
+        tables and mapped boundary points are taken from it and only the boundary data ``p(x, y, z, t)``, ``c(x, y, z, t)``
+        are evaluated again (the facet set-up walks every boundary facet on the host)."""
         if self.space is None or self.functions is None:
             raise ValueError("weak form needs .space and .functions")
+        if reuse is not None:
+            parts = []
+            for key, old in zip(("p", "c"), reuse.parts):
+                part = FormData(**old.__dict__)
+                pd = coefficients.evaluate(self.functions[key], old.x, 1, extra=(t,))[:, :, 0]
+                part.pd = torch.as_tensor(np.ascontiguousarray(pd, dtype=np.float64)).to(dev.device)
+                parts.append(part)
+            return FormData(n_items=reuse.n_items, items=items, parts=parts, inner=reuse.inner, nfd=reuse.nfd)
         _tables(self.space)
         mp, mc = self.space.discrete_spaces["mp"], self.space.discrete_spaces["mc"]
         if not np.array_equal(mp.bc_element_ids, mc.bc_element_ids):
