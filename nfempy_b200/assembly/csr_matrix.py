@@ -63,9 +63,11 @@ class CSRMatrix:
 
     def scale(self, a):
         if self.values_dev is not None:
-            self.values_dev.mul_(float(a))
-            if float(a) == 0.0:
+            if float(a) == 0.0:  # the reassembly idiom jac_g.scale(0.0): a write-only fill instead of read-multiply-write
+                self.values_dev.zero_()
                 self.is_zero = True
+            else:
+                self.values_dev.mul_(float(a))
         return self
 
     def zeroEntries(self):

@@ -44,7 +44,7 @@ def _as_items(sequence, n_total):
     return items
 
 
-_CHUNK = 1 << 21  # doubles per host-side work item (16 MB)
+_CHUNK = 1 << 19  # doubles per host-side work item (4 MB)
 
 
 def _chunks(n):
