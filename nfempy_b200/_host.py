@@ -10,7 +10,8 @@ def n_threads():
     env = os.environ.get("NFA_HOST_THREADS")
     if env:
         return max(1, int(env))
-    return max(2, min(8, (os.cpu_count() or 4) // 2))
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))  # torchrun: one process per GPU shares the host cores
+    return max(1, min(8, (os.cpu_count() or 4) // (2 * ranks)))
 
 
 def pool():
