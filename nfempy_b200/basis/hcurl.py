@@ -8,9 +8,12 @@ degree is 1) on triangles and tetrahedra, restated in exact rational arithmetic 
 * physical element: covariant Piola map ``phi = J^{-T} phi_hat`` (``covariant_piola``); reversing an edge flips the sign
   of its function (``entity_transformations``: ``interval = [[-1]]``).
 
-The reference names the family (R/src/basis/element_family.py:9, R/src/basis/finite_element.py:29) but none of its weak
-forms uses it, and its ``evaluate_basis`` still carries a TODO for the covariant map (R/src/basis/finite_element.py:178):
-the tables are provided for completeness of the basis layer; no CUDA kernel consumes them yet.
+Second-kind Nedelec of degree 1 ("N2E") is the full ``[P_1]^d`` with two tangential moments per edge (``build_hcurl``).
+
+The reference names the families (R/src/basis/element_family.py:9, R/src/basis/finite_element.py:29) and drives them through
+``L2ProjectorWeakForm`` in its projector test (R/tests/test_projectors/test_projectors.py:187-216); its ``evaluate_basis``
+still carries a TODO for the covariant map (R/src/basis/finite_element.py:178).  Consumers here: ``DiscreteSpace``,
+``L2ProjectorWeakForm`` and ``l2_error`` through ``csrc/nfa_hcurl.cu``.
 """
 from fractions import Fraction
 
@@ -40,26 +43,43 @@ def _space_functions(dim):
     return fns
 
 
+def _full_p1_functions(dim):
+    """Basis of ``[P_1]^d``: every monomial of degree <= 1 in every component."""
+    fns = []
+    for c in range(dim):
+        for e in monomial_exponents(dim, 1):
+            key = tuple(int(v) for v in e)
+            fns.append([({key: Fraction(1)} if cc == c else {}) for cc in range(dim)])
+    return fns
+
+
 def build_hcurl(el):
+    """N1E of degree 1 (one tangential moment per edge) and N2E of degree 1 (the full ``[P_1]^d``, two tangential moments
+    per edge against the Legendre functions ``q_0 = 1``, ``q_1 = sqrt(3) (2 s - 1)`` of the edge parameter -- basix'
+    legendre variant, which makes the reversal of an edge a diagonal transformation: the even moment changes sign with the
+    tangent, the odd one does not)."""
     dim, k = el.dim, el.degree
-    if dim not in (2, 3) or k != 1:
-        raise NotImplementedError("N1E is restated for degree 1 on triangles and tetrahedra")
+    if dim not in (2, 3) or k != 1 or el.family not in ("N1E", "N2E"):
+        raise NotImplementedError("N1E / N2E are restated for degree 1 on triangles and tetrahedra")
+    second_kind = el.family == "N2E"
     verts = [[Fraction(int(v)) for v in row] for row in REF_VERTICES[dim].tolist()]
-    fns = _space_functions(dim)
+    fns = _full_p1_functions(dim) if second_kind else _space_functions(dim)
+    moments = [{(0,): Fraction(1)}] + ([{(0,): Fraction(-1), (1,): Fraction(2)}] if second_kind else [])  # 1, 2 s - 1
     funcs = []
     for a, b in SUB_ENTITIES[dim][1]:
         t = [verts[b][c] - verts[a][c] for c in range(dim)]
         x_of_s = [_padd({(0,): verts[a][c]}, {(1,): t[c]}) for c in range(dim)]
+        for q in moments:
 
-        def functional(vec, t=t, x_of_s=x_of_s):
-            total = {}
-            for c in range(dim):
-                if t[c] != 0 and vec[c]:
-                    comp = _compose_affine(vec[c], x_of_s, 1)
-                    total = _padd(total, {e: v * t[c] for e, v in comp.items()})
-            return _simplex_integral(total) if total else Fraction(0)
+            def functional(vec, t=t, x_of_s=x_of_s, q=q):
+                total = {}
+                for c in range(dim):
+                    if t[c] != 0 and vec[c]:
+                        comp = _compose_affine(vec[c], x_of_s, 1)
+                        total = _padd(total, {e: v * t[c] for e, v in _pmul(comp, q).items()})
+                return _simplex_integral(total) if total else Fraction(0)
 
-        funcs.append(functional)
+            funcs.append(functional)
     D = [[fn(s) for s in fns] for fn in funcs]
     Dinv = _solve_exact(D)
     el.value_size = dim
@@ -76,10 +96,13 @@ def build_hcurl(el):
                 for e, v in vec[c].items():
                     coeffs[j][c][index[e]] += w * v
     el.coeffs = np.array([[[float(v) for v in comp] for comp in fn] for fn in coeffs])
-    el._exact_coeffs = coeffs
+    el._exact_coeffs = coeffs  # dual to the moments against 1 and 2 s - 1 (rational)
+    per_edge = len(moments)
+    if second_kind:
+        el.coeffs[1::2] /= np.sqrt(3.0)  # dual to the ORTHONORMAL odd moment sqrt(3) (2 s - 1)
     el._entity_dofs = [[[] for _ in SUB_ENTITIES[dim][d]] for d in range(dim + 1)]
     for i in range(n):
-        el._entity_dofs[1][i].append(i)
+        el._entity_dofs[1][i // per_edge].append(i)
     el._interval_T = el._triangle_T = None
 
 

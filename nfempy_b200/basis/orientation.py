@@ -65,6 +65,17 @@ def edge_signs(mesh, dim, selected_local):
     raise NotImplementedError("edge orientation for dimension %d" % dim)
 
 
+def edge_dof_signs(mesh, dim, selected_local, ref_element):
+    """``int8[n_cells, n_phi]`` factor of every dof of an edge-based H(curl) element whose edge transformation is diagonal
+    (N1E_1: ``[-1]``; N2E_1: ``diag(-1, +1)``): the diagonal entry for a mis-oriented edge, +1 otherwise."""
+    flip = np.diag(np.asarray(ref_element.entity_transformations()["interval"][0])).astype(np.int8)
+    s = edge_signs(mesh, dim, selected_local)  # [n_cells, n_edges]
+    out = np.ones((s.shape[0], s.shape[1] * len(flip)), dtype=np.int8)
+    for k, f in enumerate(flip):
+        out[:, k :: len(flip)] = np.where(s < 0, f, 1)
+    return out
+
+
 def case_matrices(ref_element):
     """``float64[n_cases, nfd, nfd]`` with ``T[0] = I`` (n_cases = 6 in 3-D, 2 in 2-D)."""
     dim = ref_element.dim

@@ -144,7 +144,7 @@ class ReferenceElement:
             from .hdiv import build_hdiv
 
             build_hdiv(self)
-        elif family == "N1E":
+        elif family in ("N1E", "N2E"):
             from .hcurl import build_hcurl
 
             build_hcurl(self)

@@ -75,8 +75,10 @@ def entity_transformations(el):
     out = {}
     if el.dim < 2:
         return out
-    if el.family == "N1E":  # one tangential moment per edge: reversing the edge flips its sign; no face dofs at degree 1
-        out["interval"] = [-np.ones((1, 1))]
+    if el.family in ("N1E", "N2E"):
+        # N1E_1: one tangential moment per edge, reversing the edge flips its sign; N2E_1: moments against the Legendre
+        # functions 1 and sqrt(3)(2s - 1) -- the even one flips with the tangent, the odd one does not; no face dofs
+        out["interval"] = [-np.ones((1, 1))] if el.family == "N1E" else [np.diag([-1.0, 1.0])]
         if el.dim == 3:
             out["triangle"] = [np.zeros((0, 0)), np.zeros((0, 0))]
         return out

@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 from .. import _lib, coefficients
-from ..basis.orientation import case_matrices, edge_signs
+from ..basis.orientation import case_matrices, edge_dof_signs
 from ..device import space_device
 from ..weak_forms.laplace_dual_weak_form import _all_cases
 
@@ -44,7 +44,7 @@ def _field_errors(dim, fe_space, functions, alpha, skip_fields, divergence):
         if name in skip_fields:
             continue
         vector_family = s.family in ("RT", "BDM")
-        if s.family == "N1E" and not divergence and s.dimension == dim:
+        if s.family in ("N1E", "N2E") and not divergence and s.dimension == dim:
             # H(curl) field: covariant map + edge signs (csrc/nfa_hcurl.cu)
             ref = s.ref_element
             cell_nodes = dev.cell_nodes(name)
@@ -54,7 +54,7 @@ def _field_errors(dim, fe_space, functions, alpha, skip_fields, divergence):
             val = np.asarray(functions[name](flat[:, 0], flat[:, 1], flat[:, 2]), dtype=np.float64)
             exact = np.ascontiguousarray(val.reshape(-1, 3, flat.shape[0])[0].T).reshape(n, len(weights), 3)
             per_cell = torch.empty(n, dtype=torch.float64, device=dev.device)
-            tab, sg, ex = up(ref.tabulate(0, points)[0]), up(edge_signs(s.mesh, dim, s.mesh_topology.selected_local), np.int8), up(exact)
+            tab, sg, ex = up(ref.tabulate(0, points)[0]), up(edge_dof_signs(s.mesh, dim, s.mesh_topology.selected_local, ref), np.int8), up(exact)
             _lib.call(
                 "nfa_hcurl_field_error", dim, ref.n_phi, len(weights), _lib.ptr(tab), _lib.ptr(w), _lib.ptr(sg),
                 _lib.ptr(dev.coords), _lib.ptr(cell_nodes), n, _lib.ptr(alpha_dev), _lib.ptr(dest), int(dest.shape[1]),

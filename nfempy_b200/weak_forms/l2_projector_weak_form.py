@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from .. import _lib, coefficients
-from ..basis.orientation import case_matrices, edge_signs
+from ..basis.orientation import case_matrices, edge_dof_signs
 from .laplace_dual_weak_form import _all_cases
 from .weak_form import BatchedWeakForm, FormData, take_rows
 
@@ -57,18 +57,18 @@ class L2ProjectorWeakForm(BatchedWeakForm):
                     kind="hdiv", dim=dim, n_u=ref.n_phi, n_q=nq, nfd=nfd, n_loc=ref.n_phi, u_val=up(tab[0]),
                     u_div=up(sum(tab[1 + d][:, :, d] for d in range(dim))), p_val=up(np.zeros((nq, 1))), w=up(weights),
                     tcases=up(case_matrices(ref)), cases=cases, cell_nodes=cell_nodes, one=up(np.ones(1)), f_u=up(f_u)))
-            elif s.family == "N1E":
+            elif s.family in ("N1E", "N2E"):
                 # H(curl): covariant Piola map + edge-orientation signs (csrc/nfa_hcurl.cu); the exact function returns
                 # [n_comp, 3, n_points] like the H(div) ones
                 if s.n_comp != 1 or s.k_order != 1:
-                    raise NotImplementedError("L2ProjectorWeakForm: N1E fields are implemented for degree 1, one component")
+                    raise NotImplementedError("L2ProjectorWeakForm: N1E / N2E fields are implemented for degree 1, one component")
                 flat = x.reshape(-1, 3)
                 val = np.asarray(fn(flat[:, 0], flat[:, 1], flat[:, 2]), dtype=np.float64)
                 f_u = np.ascontiguousarray(val.reshape(-1, 3, n * nq)[0].T).reshape(n, nq, 3)
                 sel = s.mesh_topology.selected_local if items is None else s.mesh_topology.selected_local[np.asarray(items)]
                 parts.append(dict(
                     kind="hcurl", dim=dim, n_u=ref.n_phi, n_q=nq, n_loc=ref.n_phi, u_val=up(ref.tabulate(0, points)[0]),
-                    w=up(weights), signs=up(edge_signs(s.mesh, dim, sel), np.int8), cell_nodes=cell_nodes, f_u=up(f_u)))
+                    w=up(weights), signs=up(edge_dof_signs(s.mesh, dim, sel, ref), np.int8), cell_nodes=cell_nodes, f_u=up(f_u)))
             else:
                 raise NotImplementedError("L2ProjectorWeakForm: family %r" % s.family)
         return FormData(n_items=int(parts[0]["cell_nodes"].shape[0]), items=items, parts=parts)

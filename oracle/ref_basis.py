@@ -77,6 +77,10 @@ def num_entity_dofs(family, dim, k, discontinuous):
         if k != 1:
             raise NotImplementedError("oracle N1E degree >= 2")
         per = [0, 1, 0, 0][: dim + 1]  # one tangential moment per edge
+    elif family == "N2E":
+        if k != 1:
+            raise NotImplementedError("oracle N2E degree >= 2")
+        per = [0, 2, 0, 0][: dim + 1]  # two tangential moments per edge, nothing else at degree 1
     else:
         raise NotImplementedError(family)
     out = [[per[d]] * len(SUB[dim][d]) for d in range(dim + 1)]

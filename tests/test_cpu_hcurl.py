@@ -95,3 +95,62 @@ def test_mapped_oriented_basis_equals_the_physical_whitney_functions(dim):
         phi = covariant_piola(tab, (X[1:] - X[0]).T) * sg[i][None, :, None]
         _, _, ref = ref_hcurl.whitney(rs.discrete_spaces["e"], rs.discrete_spaces["e"].element_ids[i], pts)
         assert np.abs(phi - ref[:, :, : phi.shape[2]]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_n2e_reference_element_is_dual_to_the_legendre_edge_moments(dim):
+    """N2E of degree 1: the full [P_1]^d, two dofs per edge, dual to the tangential moments against 1 and sqrt(3)(2s - 1);
+    the edge transformation is diag(-1, +1)."""
+    from nfempy_b200.basis.reference_element import REF_VERTICES, SUB_ENTITIES
+
+    el = create_element("N2E", dim, 1)
+    n_edges = len(SUB_ENTITIES[dim][1])
+    assert el.n_phi == 2 * n_edges == dim * (dim + 1) and el.value_size == dim
+    assert el.entity_dofs[1] == [[2 * e, 2 * e + 1] for e in range(n_edges)]
+    assert all(len(d) == 0 for k in (0, 2, 3)[: dim] for d in el.entity_dofs[k] if k != 1)
+    s, w = np.polynomial.legendre.leggauss(4)
+    s, w = 0.5 * (s + 1.0), 0.5 * w
+    D = np.zeros((el.n_phi, el.n_phi))
+    for e, (a, b) in enumerate(SUB_ENTITIES[dim][1]):
+        va, vb = REF_VERTICES[dim][a], REF_VERTICES[dim][b]
+        tab = el.tabulate(0, va[None, :] + s[:, None] * (vb - va)[None, :])[0]
+        for k, q in enumerate((np.ones_like(s), np.sqrt(3.0) * (2.0 * s - 1.0))):
+            D[2 * e + k] = np.einsum("q,qjc,c->j", w * q, tab, vb - va)
+    assert np.abs(D - np.eye(el.n_phi)).max() <= 1e-14
+    assert np.array_equal(el.entity_transformations()["interval"][0], np.diag([-1.0, 1.0]))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_n2e_mapped_oriented_basis_equals_the_physical_functions(dim):
+    """Reference tables + covariant map + per-dof edge signs (what csrc/nfa_hcurl.cu evaluates) against the oracle's
+    second-kind functions written in physical coordinates, on every cell of a jittered, locally shuffled mesh; the
+    destination tables of product and oracle (two dofs per edge, first-appearance edge order)."""
+    from nfempy_b200.basis.hcurl import covariant_piola
+    from nfempy_b200.basis.orientation import edge_dof_signs
+    from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
+    from nfempy_b200.spaces import ProductSpace
+    from oracle import ref_hcurl
+    from oracle.ref_mesh import RefMesh
+    from oracle.ref_spaces import RefProductSpace
+
+    mesh = box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(3, jitter=0.2)
+    space = ProductSpace({"e": (dim, 1, "N2E", 1, mesh)})
+    space.build_structures({"e": [1]}, {})
+    s = space.discrete_spaces["e"]
+    r = RefMesh(dim, mesh.points, mesh._blocks)
+    r.build_conformal_mesh()
+    rs = RefProductSpace({"e": (dim, 1, "N2E", 1, r)})
+    rs.build_structures({"e": [1]}, {})
+    dest = np.asarray(space.destination_table())
+    assert dest.shape[1] == dim * (dim + 1)
+    assert np.array_equal(dest, np.array([rs.destination_indexes(i) for i in range(len(dest))]))
+    pts, _ = space.quadrature[dim]
+    sg = edge_dof_signs(mesh, dim, s.mesh_topology.selected_local, s.ref_element)
+    assert (sg[:, 0::2] == -1).any() and (sg[:, 1::2] == 1).all()
+    tab = s.ref_element.tabulate(0, pts)[0]
+    cn = s.cell_nodes()
+    for i in range(len(cn)):
+        X = mesh.points[cn[i]]
+        phi = covariant_piola(tab, (X[1:] - X[0]).T) * sg[i][None, :, None]
+        _, _, ref = ref_hcurl.nedelec2(rs.discrete_spaces["e"], rs.discrete_spaces["e"].element_ids[i], pts)
+        assert np.abs(phi - ref[:, :, : phi.shape[2]]).max() <= 1e-12

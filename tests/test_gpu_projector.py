@@ -133,3 +133,59 @@ def test_hcurl_projection_of_a_field_in_the_space_is_exact(dim):
     moment = float(np.sum(ws * np.einsum("dq,d->q", f["e"](xs[:, 0], xs[:, 1], xs[:, 2])[0], xb - xa)))
     dof = int(s.dof_map.entity_block(1, np.array([edge]))[0, 0])
     assert abs(abs(alpha[dof]) - abs(moment)) <= 1e-12 * max(1.0, abs(moment))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_n2e_projector_matches_oracle(dim):
+    """N2E of degree 1 (two tangential moments per edge, edge transformation diag(-1, +1)) through DiscreteSpace +
+    L2ProjectorWeakForm + csrc/nfa_hcurl.cu against the oracle's physical-space functions."""
+    from nfempy_b200.weak_forms import L2ProjectorWeakForm
+    from oracle import ref_hcurl
+
+    mesh = box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(3, jitter=0.2)
+    functions = {"e": lambda x, y, z: np.array([[np.sin(x) + y, x * y - z, 1.0 + z * x]])}
+
+    def gpu_forms(space, a):
+        wf = L2ProjectorWeakForm(space)
+        wf.functions = functions
+        return {"proj": ["form", range(len(space.discrete_spaces["e"].elements)), wf, a]}
+
+    def ref_forms_fn(space):
+        return [("form", ref_hcurl.l2_projector_n2e, functions, len(space.discrete_spaces["e"].element_ids))]
+
+    case = Case(mesh, lambda g: {"e": (dim, 1, "N2E", 1, g)}, {"e": [1]}, {}, gpu_forms, ref_forms_fn)
+    compare_csr(case.run_gpu(), case.run_oracle(), 1e-12)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_n2e_projection_of_a_linear_field_is_exact(dim):
+    """The reference's projector property test for the N2E family at its first order
+    (R/tests/test_projectors/test_projectors.py:187-216, ``v_functions[0] = (y, -x, -z)``), and a general affine field:
+    ``l2_projector`` then ``l2_error <= 1e-12`` through the CUDA path; the even dof of an edge is the tangential moment of
+    the field along the globally oriented edge."""
+    from nfempy_b200.postprocess import l2_error, l2_projector
+    from nfempy_b200.spaces import ProductSpace
+
+    mesh = box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(3, jitter=0.2)
+    space = ProductSpace({"e": (dim, 1, "N2E", 1, mesh)})
+    space.build_structures({"e": [1]}, {})
+    planar = 0.0 if dim == 2 else 1.0  # a 2-D space only represents the in-plane components
+    fields = [
+        lambda x, y, z: np.array([[y, -x, -z * planar]]),
+        lambda x, y, z: np.array([[1.0 + 2.0 * x - y + 0.5 * z * planar, 0.3 - x + 4.0 * y, planar * (2.0 - 3.0 * z + x)]]),
+    ]
+    for fn in fields:
+        f = {"e": fn}
+        alpha = l2_projector(space, f)
+        err = l2_error(dim, space, f, alpha)
+        assert len(err) == 1 and err[0] <= 1e-12, err
+        s = space.discrete_spaces["e"]
+        edge = s.mesh_topology.entity_ids[1][3]
+        a, b = mesh.edge_nodes[edge - mesh.offset[1]]
+        xa, xb = mesh.points[a], mesh.points[b]
+        ts, ws = np.polynomial.legendre.leggauss(4)
+        ts, ws = (ts + 1.0) / 2.0, ws / 2.0
+        xs = xa[None, :] + ts[:, None] * (xb - xa)[None, :]
+        moment = float(np.sum(ws * np.einsum("dq,d->q", fn(xs[:, 0], xs[:, 1], xs[:, 2])[0], xb - xa)))
+        dof = int(s.dof_map.entity_block(1, np.array([edge]))[0, 0])
+        assert abs(abs(alpha[dof]) - abs(moment)) <= 1e-12 * max(1.0, abs(moment))
