@@ -213,6 +213,11 @@ int nfa_rows_copy_i32(int64_t n_rows, const int64_t *d_indptr, const int64_t *d_
  *   scalar rows read: form 0: r_p, C[0..n_u); form 1: K_pp, K_cc, r_p, r_c, C[0..n_u).  Arguments as nfa_local_hdiv_l2 /
  *   nfa_local_sundus (d_f_f is the load `rhs` of form 0; delta, eta, delta_t, f_r, alpha, alpha_prev, dest are read by
  *   form 1 only).
+ *   form = 2: the generalised mixed elliptic forms (DegenerateEllipticWeakForm, UnscaledEllipticWeakForm,
+ *   R/src/weak_forms/degenerate_elliptic_weak_form.py:41-144, unscaled_elliptic_weak_form.py:41-153) on RT_1 x P_0, local
+ *   order [u | p]: d_kappa = c_uu (multiplies the flux mass), d_delta = c_d (scales div psi; NULL = 1), d_eta = c_pp (weight
+ *   of the (p, p) mass; NULL = no such block), d_f_f = load_p, d_f_r = g [n_cells][n_q][dim] (adds g . psi to the coupling),
+ *   r = J alpha - [0; int load_p w]; record: flux rows as above, then K_pp, r_p, C[0..n_u).
  * Runs: local row a of an item reads the record doubles [d_roff[a], d_roff[a] + 8) (d_roff even); d_codes int8 [n_loc][8]
  *   says what entry k of the run is for that row: 0 = nothing, +-(b + 1) = local column b with that sign (each column at
  *   most once; columns without a code are structural zeros, stored as 0.0), 127 = the row's residual.

@@ -104,6 +104,26 @@ def laplace_dual_maps(n_u):
     return emap, ridx, stride
 
 
+def general_maps(n_u):
+    """The same for the generalised mixed elliptic forms (form 2, ``HdivL2GeneralForm``), local order [u | p]: like the
+    mixed Poisson layout plus the (p, p) mass; scalar block ``K_pp, r_p, C[.]``."""
+    roww, n_loc = (n_u + 3) // 2 * 2, n_u + 1
+    soff = n_u * roww
+    emap = np.zeros((n_loc, n_loc), dtype=np.int16)
+    ridx = np.zeros(n_loc, dtype=np.int16)
+    for a in range(n_u):
+        base = a * roww
+        for b in range(n_u):
+            emap[a, b] = base + b + 1
+        emap[a, n_u] = -(base + n_u + 1)
+        emap[n_u, a] = soff + 2 + a + 1
+        ridx[a] = base + n_u + 1
+    emap[n_u, n_u] = soff + 1
+    ridx[n_u] = soff + 1
+    stride = (soff + 2 + n_u + 3) // 4 * 4
+    return emap, ridx, stride
+
+
 RUN = 8  # record doubles a local row may read (csrc/nfa_hdivrows.cu)
 CODE_RHS = 127
 

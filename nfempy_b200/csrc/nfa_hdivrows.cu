@@ -35,7 +35,9 @@ struct CoefR {
 constexpr int REC_CELLS = 128;  // cells per CTA pass of the records kernel
 constexpr int ROWS_PER_CTA = 256;
 
-// FORM 0: mixed Poisson [u | p]; FORM 1: Sundus [mp | mc | p | c]
+// FORM 0: mixed Poisson [u | p]; FORM 1: Sundus [mp | mc | p | c]; FORM 2: generalised mixed elliptic form [u | p]
+// (HdivL2GeneralForm: kappa = c_uu multiplies the flux mass, delta = c_d scales the divergence, eta = c_pp is the weight of
+// the (p, p) mass, f_f = load_p, f_r = g [cell][q][DIM] adds g . psi to the coupling; absent arrays: 1, 0, 0, 0)
 template <int DIM, int FORM>
 __global__ void __launch_bounds__(REC_CELLS, 3)
     rt1_records_kernel(int n_q, const double *__restrict__ u_val, const double *__restrict__ u_div,
@@ -49,8 +51,8 @@ __global__ void __launch_bounds__(REC_CELLS, 3)
     constexpr int NU = DIM + 1, NS = NU * (NU + 1) / 2, NFLUX = FORM == 1 ? 2 : 1;
     constexpr int NLOC = NFLUX * NU + NFLUX;
     constexpr int ROWW = (NU + 3) & ~1;      // M[a][0..NU), C[a], r[a] (+ one pad in 2-D: rows start 16-byte aligned)
-    constexpr int SOFF = NFLUX * NU * ROWW;  // scalar rows' block: FORM 0: r_p, C[.]; FORM 1: K_pp, K_cc, r_p, r_c, C[.]
-    constexpr int NSC = FORM == 1 ? 4 : 1;
+    constexpr int SOFF = NFLUX * NU * ROWW;  // scalar rows' block: FORM 0: r_p, C[.]; 1: K_pp, K_cc, r_p, r_c, C[.]; 2: K_pp, r_p, C[.]
+    constexpr int NSC = FORM == 1 ? 4 : (FORM == 2 ? 2 : 1);
     constexpr int USED = SOFF + NSC + NU;
     extern __shared__ double sm[];
     double *s_val = sm;                       // [n_q][NU][DIM]
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(REC_CELLS, 3)
             double a_s[NFLUX], an_s[NFLUX];
 #pragma unroll
             for (int F = 0; F < NFLUX; ++F) a_s[F] = an_s[F] = 0.0;
-            if (FORM == 1) {
+            if (FORM >= 1 && (alpha || alpha_prev)) {
                 const int32_t *d = dest + cell * NLOC;
 #pragma unroll
                 for (int F = 0; F < NFLUX; ++F) {
@@ -106,6 +108,9 @@ __global__ void __launch_bounds__(REC_CELLS, 3)
                 dq = delta.p[cell * delta.sc];
                 eq = eta.p[cell * eta.sc];
                 frq = f_r ? f_r[cell * n_q] : 0.0;
+            } else if (FORM == 2) {
+                dq = delta.p ? delta.p[cell * delta.sc] : 1.0;
+                eq = eta.p ? eta.p[cell * eta.sc] : 0.0;
             }
             ffq = f_f ? f_f[cell * n_q] : 0.0;
             for (int q = 0; q < n_q; ++q) {
@@ -117,11 +122,14 @@ __global__ void __launch_bounds__(REC_CELLS, 3)
                         dq = delta.p[cell * delta.sc + (q + 1) * delta.sq];
                         eq = eta.p[cell * eta.sc + (q + 1) * eta.sq];
                         if (f_r) frq = f_r[cell * n_q + q + 1];
+                    } else if (FORM == 2) {
+                        if (delta.p) dq = delta.p[cell * delta.sc + (q + 1) * delta.sq];
+                        if (eta.p) eq = eta.p[cell * eta.sc + (q + 1) * eta.sq];
                     }
                     if (f_f) ffq = f_f[cell * n_q + q + 1];
                 }
                 double wt[NFLUX];
-                wt[0] = wd * (1.0 / k_now);
+                wt[0] = FORM == 2 ? wd * k_now : wd * (1.0 / k_now);
                 if (FORM == 1) wt[NFLUX - 1] = wd * (1.0 / d_now);
                 double psi[NU][DIM];
 #pragma unroll
@@ -147,8 +155,18 @@ __global__ void __launch_bounds__(REC_CELLS, 3)
                     }
                 const double pw = s_pw[q], wp = wd * pw;
 #pragma unroll
-                for (int a = 0; a < NU; ++a) C[a] = fma(wp, (s_div[q * NU + a] * idet) * sgn[a], C[a]);
-                W2 = fma(wp, pw, W2);
+                for (int a = 0; a < NU; ++a) {
+                    double D = (s_div[q * NU + a] * idet) * sgn[a];
+                    if (FORM == 2) {
+                        D *= d_now;
+                        if (f_r) {
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) D = fma(f_r[(cell * n_q + q) * DIM + c], psi[a][c], D);
+                        }
+                    }
+                    C[a] = fma(wp, D, C[a]);
+                }
+                W2 = fma(wp, FORM == 2 ? pw * e_now : pw, W2);
                 if (FORM == 1) {
                     const double et = e_now, ch = a_s[NFLUX - 1] * pw;
                     Wc = fma(wp * pw, et * ch, Wc);
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(REC_CELLS, 3)
 #pragma unroll
             for (int F = 0; F < NFLUX; ++F)
 #pragma unroll
-                for (int a = 0; a < NU; ++a) a_f[F][a] = (FORM == 1 && alpha) ? __ldg(alpha + dest[cell * NLOC + F * NU + a]) : 0.0;
+                for (int a = 0; a < NU; ++a) a_f[F][a] = (FORM >= 1 && alpha) ? __ldg(alpha + dest[cell * NLOC + F * NU + a]) : 0.0;
             // record rows of the flux dofs: M[a][.], C[a], r[a]
 #pragma unroll
             for (int F = 0; F < NFLUX; ++F)
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(REC_CELLS, 3)
                         r = fma(m, a_f[F][b], r);
                     }
                     R[(F * NU + a) * ROWW + NU] = C[a];
-                    R[(F * NU + a) * ROWW + NU + 1] = FORM == 1 ? r - a_s[F] * C[a] : 0.0;
+                    R[(F * NU + a) * ROWW + NU + 1] = FORM >= 1 ? r - a_s[F] * C[a] : 0.0;
                     if (ROWW > NU + 2) R[(F * NU + a) * ROWW + NU + 2] = 0.0;
                 }
             if (FORM == 1) {
@@ -192,6 +210,12 @@ __global__ void __launch_bounds__(REC_CELLS, 3)
                 R[SOFF + 1] = app + 2.0 * Wc;
                 R[SOFF + 2] = (a_s[0] - an_s[0]) * app + dmp - Ff;
                 R[SOFF + 3] = (a_s[NFLUX - 1] - an_s[NFLUX - 1]) * app + dmc + Rc;
+            } else if (FORM == 2) {
+                double da = 0.0;
+#pragma unroll
+                for (int a = 0; a < NU; ++a) da = fma(a_f[0][a], C[a], da);
+                R[SOFF + 0] = W2;  // int c_pp w w
+                R[SOFF + 1] = da + W2 * a_s[0] - Ff;
             } else {
                 R[SOFF] = -Ff;
             }
@@ -361,12 +385,12 @@ extern "C" int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *u_
                                     int stride, double *rec, nfa_stream stream) {
     if (n_cells == 0) return 0;
     if (dim != 2 && dim != 3) return fail("nfa_hdiv_rt1_records: dim must be 2 or 3");
-    if (form != 0 && form != 1) return fail("nfa_hdiv_rt1_records: form must be 0 (mixed Poisson) or 1 (Sundus)");
+    if (form < 0 || form > 2) return fail("nfa_hdiv_rt1_records: form must be 0 (mixed Poisson), 1 (Sundus) or 2 (general)");
     if (n_q < 1 || n_q > 64) return fail("nfa_hdiv_rt1_records: 1 to 64 quadrature points");
     if (!u_val || !u_div || !p_val || !weights || !Tcases || !cases || !coords || !cell_nodes || !kappa || !rec)
         return fail("nfa_hdiv_rt1_records: NULL argument");
     const int nu = dim + 1, nflux = form == 1 ? 2 : 1;
-    const int used = nflux * nu * ((nu + 3) & ~1) + (form == 1 ? 4 : 1) + nu;
+    const int used = nflux * nu * ((nu + 3) & ~1) + (form == 1 ? 4 : (form == 2 ? 2 : 1)) + nu;
     if (stride < used || (stride & 3)) return fail("nfa_hdiv_rt1_records: record stride too small or not a multiple of 4");
     if (form == 1) {
         if (!delta || !eta || !dest) return fail("nfa_hdiv_rt1_records: the Sundus form needs delta, eta and dest");
@@ -381,6 +405,8 @@ extern "C" int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *u_
     const int64_t want = (n_cells + REC_CELLS - 1) / REC_CELLS;
     const int grid = (int)std::min<int64_t>(want, (int64_t)n_sm * 8);
     const double inv_dt = form == 1 ? 1.0 / delta_t : 0.0;
+    // form 2 (HdivL2GeneralForm): kappa = c_uu, delta = c_d, eta = c_pp (NULL allowed for the last two), f_f = load_p,
+    // f_r = g [n_cells][n_q][dim]
 #define NFA_REC_LAUNCH(D, F)                                                                                          \
     {                                                                                                                 \
         auto kern = rt1_records_kernel<D, F>;                                                                         \
@@ -388,10 +414,11 @@ extern "C" int nfa_hdiv_rt1_records(int dim, int form, int n_q, const double *u_
         kern<<<grid, REC_CELLS, smem, s>>>(n_q, u_val, u_div, p_val, weights, Tcases, cases, coords, cell_nodes, n_cells, \
                                            kp, dl, et, inv_dt, f_f, f_r, alpha, alpha_prev, dest, stride, rec);       \
     }
+    if (form == 2 && alpha && !dest) return fail("nfa_hdiv_rt1_records: alpha given without dest");
     if (dim == 3) {
-        if (form == 1) NFA_REC_LAUNCH(3, 1) else NFA_REC_LAUNCH(3, 0)
+        if (form == 1) NFA_REC_LAUNCH(3, 1) else if (form == 2) NFA_REC_LAUNCH(3, 2) else NFA_REC_LAUNCH(3, 0)
     } else {
-        if (form == 1) NFA_REC_LAUNCH(2, 1) else NFA_REC_LAUNCH(2, 0)
+        if (form == 1) NFA_REC_LAUNCH(2, 1) else if (form == 2) NFA_REC_LAUNCH(2, 2) else NFA_REC_LAUNCH(2, 0)
     }
 #undef NFA_REC_LAUNCH
     NFA_LAUNCH_CHECK();

@@ -58,6 +58,32 @@ class HdivL2GeneralForm(BatchedWeakForm):
             cases=cases, cell_nodes=cell_nodes, co=dev_co,
         )
 
+    def row_spec(self, data):
+        """Row-owner path (``assembly/hdiv_rows.py``, ``csrc/nfa_hdivrows.cu`` form 2) for RT_1 x P_0 -- config 3's other
+        form classes at k = 1; ``None`` for every other element and for forms with a second state vector."""
+        from ..assembly import hdiv_rows
+
+        u = self.space.discrete_spaces[self.flux_name]
+        c = data.co
+        if u.family != "RT" or data.nfd != 1 or data.n_u != data.dim + 1 or data.n_p != 1 or data.n_q > 64 \
+                or c["s_u"] is not None or c["s_p"] is not None or getattr(self, "alpha_scaled", None) is not None \
+                or list(self.space.discrete_spaces.keys()) != [self.flux_name, self.scalar_name]:
+            return None
+        emap, ridx, stride = hdiv_rows.general_maps(data.n_u)
+        return {"emap": emap, "ridx": ridx, "stride": stride}
+
+    def launch_records(self, dev, data, alpha_dev, alpha_prev_dev, dest_dev, rec, stride):
+        c, nq = data.co, data.n_q
+        arr = lambda t: (_lib.ptr(t), nq if t is not None else 0, 1 if t is not None else 0)
+        if alpha_dev is not None and not self.uses_alpha:
+            alpha_dev = None
+        _lib.call(
+            "nfa_hdiv_rt1_records", data.dim, 2, nq, _lib.ptr(data.u_val), _lib.ptr(data.u_div), _lib.ptr(data.p_val),
+            _lib.ptr(data.w), _lib.ptr(data.tcases), _lib.ptr(data.cases), _lib.ptr(dev.coords), _lib.ptr(data.cell_nodes),
+            data.n_items, *arr(c["c_uu"]), *arr(c["c_d"]), *arr(c["c_pp"]), 0.0, _lib.ptr(c["load_p"]), _lib.ptr(c["g"]),
+            _lib.ptr(alpha_dev), None, _lib.ptr(dest_dev), stride, _lib.ptr(rec), _lib.stream_ptr(),
+        )
+
     def launch_local(self, dev, data, alpha_dev, dest_dev, Ke, re, beta_dev=None):
         c = data.co
         need_dest = alpha_dev is not None or beta_dev is not None

@@ -154,3 +154,20 @@ def test_row_blocks_cut_runs_of_consecutive_rows():
     rows = torch.tensor(list(range(5, 8)) + list(range(20, 20 + 600)) + [1000], dtype=torch.int32)
     blocks = hdiv_rows.row_blocks(rows).tolist()
     assert blocks == [[5, 3, 0, 0], [20, 256, 3, 0], [276, 256, 259, 0], [532, 88, 515, 0], [1000, 1, 603, 0]]
+
+
+@pytest.mark.parametrize("kind,dim", [("degenerate", 3), ("unscaled", 2)])
+def test_general_elliptic_records_expand_to_the_oracle_matrix(kind, dim):
+    """Record layout / entry maps of form 2 (DegenerateEllipticWeakForm, UnscaledEllipticWeakForm on RT_1 x P_0) against
+    the oracle's local matrices and assembled system, non-zero state vector."""
+    from tests.parity_helpers import degenerate_case
+
+    case = degenerate_case(kind=kind, dim=dim, k=1, n=2, with_bc=False)
+    space, ref = case.space(), case.ref_space()
+    alpha = case.alpha_fn(ref.n_dof)
+    (_, form_fn, functions, n_cells), = case.ref_forms_fn(ref)
+    want = ref_assembly.assemble(ref, [("form", form_fn, functions, n_cells)], alpha)
+    dest = np.asarray(space.destination_table(), dtype=np.int64)
+    blocks = [form_fn(ref, functions, i, alpha[dest[i]]) for i in range(n_cells)]
+    emap, ridx, stride = hdiv_rows.general_maps(dim + 1)
+    _check(dest, ref.n_dof, emap, ridx, stride, blocks, want)

@@ -191,3 +191,27 @@ def test_new_time_reuses_geometry_and_matches_a_fresh_assembler():
     want = fresh.assemble()
     assert np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
     compare_csr(got, case2.run_oracle(), RTOL)
+
+
+@pytest.mark.parametrize("kind", ["degenerate", "unscaled"])
+@pytest.mark.parametrize("dim,alpha", [(3, True), (2, True), (3, False)])
+def test_general_elliptic_rt1_by_row_owner(kind, dim, alpha):
+    """Config 3's other form classes at k = 1 (DegenerateEllipticWeakForm / UnscaledEllipticWeakForm + their natural
+    boundary forms; porosity vanishing on part of the domain) through the records kernel's form 2 and the rows kernel."""
+    from tests.parity_helpers import degenerate_case
+
+    case = degenerate_case(kind=kind, dim=dim, k=1, n=3, alpha=alpha)
+    space, asm = _assembler(case, case.alpha_fn)
+    got = asm.assemble()
+    assert _took_rows(asm)
+    compare_csr(got, case.run_oracle(), RTOL)
+
+
+def test_projection_form_with_a_second_state_vector_keeps_the_two_stage_path():
+    from tests.parity_helpers import degenerate_case
+
+    case = degenerate_case(kind="projection", dim=3, k=1, n=2)
+    space, asm = _assembler(case, case.alpha_fn)
+    got = asm.assemble()
+    assert not _took_rows(asm)
+    compare_csr(got, case.run_oracle(), RTOL)

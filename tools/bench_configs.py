@@ -317,6 +317,8 @@ def main():
         run_case("config3: 3D mixed Poisson RT%d x P%d disc + natural BC" % (k, k - 1),
                  mixed_poisson_case(dim=3, k=k, mesh=mesh3), mixed_poisson_case(dim=3, k=k, n=2), args.steps,
                  args.warmup)
+    run_case("config3: DegenerateEllipticWeakForm RT1 x P0 disc + BC", degenerate_case("degenerate", 3, 1, mesh=mesh3),
+             degenerate_case("degenerate", 3, 1, n=2), args.steps, args.warmup, oracle_cells=20)
     # config 5: reassembly of the two-flux transport system, plan built once, 100 "time steps" of kernels
     run_sundus(mesh3, 20 if q else 100)
     del mesh3
