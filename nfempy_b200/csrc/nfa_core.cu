@@ -697,16 +697,17 @@ extern "C" int nfa_bplan_load_rhs(const nfa_bplan *bp, int dim, int n_q, const d
     if (!bp || !tab0 || !weights || !coords || !cell_nodes || !f || !rhs) return fail("nfa_bplan_load_rhs: NULL argument");
     if (n_q < 1 || n_q > 64) return fail("nfa_bplan_load_rhs: 1 to 64 quadrature points");
     cudaStream_t s = (cudaStream_t)stream;
-    static_assert(nfa_bplan::LOAD_TILE == 64, "the streaming load kernel runs tiles of 64 cells");
+    constexpr int LT = nfa_bplan::LOAD_TILE;  // cells per tile of the plan's pair lists (64; NFA_LOAD_TILE for experiments)
+    static_assert(LT == 32 || LT == 64 || LT == 128, "the streaming load kernel runs tiles of 32, 64 or 128 cells");
     const LoadMerge mg = {(const int32_t *)bp->tile_ptr.p, (const uint32_t *)bp->pair_ptr.p, (const uint16_t *)bp->tile_ent.p,
                           (double *)bp->pair_sum.p};
     int rc;
     if (dim == 3 && bp->n_phi == 10 && bp->n_comp == 3)
-        rc = launch_h1_load_stream<3, 10, 3, 64, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 3, mg);
+        rc = launch_h1_load_stream<3, 10, 3, LT, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 3, mg);
     else if (dim == 3 && bp->n_phi == 4 && bp->n_comp == 3)
-        rc = launch_h1_load_stream<3, 4, 3, 64, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 3, mg);
+        rc = launch_h1_load_stream<3, 4, 3, LT, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 3, mg);
     else if (dim == 2 && bp->n_phi == 6 && bp->n_comp == 2)
-        rc = launch_h1_load_stream<2, 6, 2, 64, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 2, mg);
+        rc = launch_h1_load_stream<2, 6, 2, LT, true>(n_q, tab0, weights, coords, cell_nodes, bp->n_cells, f, sign, nullptr, s, 2, mg);
     else
         return fail("nfa_bplan_load_rhs: vector P2 / P1 on tetrahedra and vector P2 on triangles only");
     if (rc) return rc;

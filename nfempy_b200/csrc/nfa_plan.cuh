@@ -78,7 +78,10 @@ struct nfa_bplan {
     // node) with at least one (cell, local node) of the tile on that node.  Pairs are ordered by (tile, node); the entries
     // of a pair (ascending cell) are tile_ent[pair_ptr[p] .. pair_ptr[p+1]) as uint16 local ids (cell - tile * LOAD_TILE) *
     // n_phi + a.  A node's pairs (ascending tile) are node_pair[node_pair_ptr[N] .. node_pair_ptr[N+1]).
-    static constexpr int LOAD_TILE = 64;
+#ifndef NFA_LOAD_TILE
+#define NFA_LOAD_TILE 64
+#endif
+    static constexpr int LOAD_TILE = NFA_LOAD_TILE;
     int64_t n_pairs = 0;
     nfa::DevBuf tile_ptr;         // int32 [n_tiles + 1]  first pair of each tile
     nfa::DevBuf pair_ptr;         // uint32 [n_pairs + 1]
