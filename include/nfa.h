@@ -165,6 +165,11 @@ int nfa_plan_create(int64_t n_dof, int n_segments, const int32_t *const *d_dest,
 int nfa_plan_create_filtered(int64_t n_dof, int n_segments, const int32_t *const *d_dest, const int64_t *n_items,
                              const int32_t *n_loc, const int32_t *seg_flags, const uint8_t *const *d_masks,
                              nfa_plan **out, nfa_stream stream);
+/* masks of nfa_plan_create_filtered from the local matrices, in one pass: kept = |v - 1e-16| > tol (~np.isclose(v, 1e-16));
+ * d_mask = kept, and dest[a] <= dest[b] when `upper`, and 1 on the local diagonal when `force_diag`; entries that fail the
+ * value test are zeroed in d_Ke (a forced diagonal entry then adds 0.0). */
+int nfa_filter_local_entries(int64_t n_items, int n_loc, const int32_t *d_dest, double tol, int upper, int force_diag,
+                             double *d_Ke, uint8_t *d_mask, nfa_stream stream);
 int nfa_plan_from_bplan(const nfa_bplan *bp, nfa_plan **out, nfa_stream stream);
 void nfa_plan_destroy(nfa_plan *plan);
 int64_t nfa_plan_nnz(const nfa_plan *plan);

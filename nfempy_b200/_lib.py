@@ -46,6 +46,7 @@ SIGNATURES = {
     ),
     "nfa_plan_create": (_i, [_i64, _i, ctypes.POINTER(_vp), _c_i64p, _c_i32p, _c_i32p, _vp, ctypes.POINTER(_vp), _vp]),
     "nfa_plan_create_filtered": (_i, [_i64, _i, ctypes.POINTER(_vp), _c_i64p, _c_i32p, _c_i32p, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp]),
+    "nfa_filter_local_entries": (_i, [_i64, _i, _vp, _d, _i, _i, _vp, _vp, _vp]),
     "nfa_plan_from_bplan": (_i, [_vp, ctypes.POINTER(_vp), _vp]),
     "nfa_plan_destroy": (None, [_vp]),
     "nfa_plan_nnz": (_i64, [_vp]),

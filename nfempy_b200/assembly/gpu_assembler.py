@@ -837,17 +837,16 @@ class GPUAssembler:
                 raise NotImplementedError("GPUAssembler: filtered patterns are implemented for form / bc_form lists")
             alpha_dev = None if data.alpha_zero else data.alpha_dev
             Ke, re = form.local_blocks(data.dev, data, alpha_dev, dest if alpha_dev is not None else None)
-            value_kept = (Ke - 1.0e-16).abs() > tol
-            mask = value_kept.clone()
-            if self.pattern_policy == "filtered_upper":
-                mask &= dest[:, :, None] <= dest[:, None, :]
-            if self.explicit_diagonal and kind == "form":
-                idx = torch.arange(Ke.shape[1], device=dev.device)
-                mask[:, idx, idx] = True
-            Ke = torch.where(value_kept, Ke, torch.zeros_like(Ke))  # a forced diagonal entry that failed the test adds 0.0
+            # one pass over the local matrices (nfa_filter_local_entries): value test, row <= col, forced diagonal; entries
+            # that fail the value test are zeroed in place (a forced diagonal entry then adds 0.0)
+            mask = torch.empty(Ke.shape, dtype=torch.uint8, device=dev.device)
+            _lib.check(lib.nfa_filter_local_entries(int(Ke.shape[0]), int(Ke.shape[1]), _lib.ptr(dest), tol,
+                                                    1 if self.pattern_policy == "filtered_upper" else 0,
+                                                    1 if (self.explicit_diagonal and kind == "form") else 0, _lib.ptr(Ke),
+                                                    _lib.ptr(mask), stream), "nfa_filter_local_entries")
             Ke_list.append(Ke)
             re_list.append(re)
-            masks.append(mask.to(torch.uint8).contiguous())
+            masks.append(mask)
             keep += [alpha_dev]
         t0 = time.perf_counter()
         p = _Plan()

@@ -309,6 +309,41 @@ static int plan_create_impl(int64_t n_dof, int n_segments, const int32_t *const 
     return 0;
 }
 
+// Value-dependent pattern policies of the example drivers' inline scatter closures (R/examples/cauchy_elasticity/
+// cg_elasticity_example_1.py:92-145): one pass over the local matrices instead of half a dozen elementwise tensor
+// operations.  kept = ~isclose(v, 1e-16) (|v - 1e-16| > tol); mask = kept, and row <= col for the "sbaij" storage, and
+// always set on the diagonal when the closure inserts explicit (i, i, 0.0) entries; entries that fail the value test are
+// zeroed in place (a forced diagonal entry then adds 0.0).
+__global__ void filter_local_entries_kernel(int64_t n_entries, int n_loc, const int32_t *__restrict__ dest, double tol,
+                                            int upper, int force_diag, double *__restrict__ Ke,
+                                            uint8_t *__restrict__ mask) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const int64_t ia = e / n_loc;  // item * n_loc + a
+    const int b = (int)(e - ia * n_loc);
+    const int64_t item = ia / n_loc;
+    const int a = (int)(ia - item * n_loc);
+    const double v = Ke[e];
+    const bool kept = fabs(v - 1.0e-16) > tol;
+    bool m = kept;
+    if (upper) m = m && dest[ia] <= dest[item * n_loc + b];
+    if (force_diag && a == b) m = true;
+    if (!kept) Ke[e] = 0.0;
+    mask[e] = m ? 1 : 0;
+}
+
+extern "C" int nfa_filter_local_entries(int64_t n_items, int n_loc, const int32_t *d_dest, double tol, int upper,
+                                        int force_diag, double *d_Ke, uint8_t *d_mask, nfa_stream stream) {
+    if (n_items <= 0) return 0;
+    if (!d_dest || !d_Ke || !d_mask) return fail("nfa_filter_local_entries: NULL argument");
+    if (n_loc < 1) return fail("nfa_filter_local_entries: n_loc must be positive");
+    const int64_t n = n_items * (int64_t)n_loc * n_loc;
+    filter_local_entries_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, n_loc, d_dest, tol, upper, force_diag,
+                                                                                     d_Ke, d_mask);
+    NFA_LAUNCH_CHECK();
+    return 0;
+}
+
 // Pattern-only plan over a CSR the caller owns (and keeps alive): the base that nfa_plan_create merges boundary / coupling
 // segments into when the volume forms are assembled by row owner (csrc/nfa_hdivrows.cu).
 extern "C" int nfa_plan_from_csr(int64_t n_dof, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
