@@ -164,6 +164,7 @@ class GPUAssembler:
         self._state_event = []
         self._capturing = False
         self._rows_refused = None
+        self._filtered_plan = None  # plan of the last value-dependent pattern (reused while the masks do not change)
         # row-owner path only: bool mask [n_dof] of the rows the caller wants (a rank's owned rows); the other rows the listed
         # cells feed are neither computed nor written
         self.rows_wanted = None
@@ -849,25 +850,37 @@ class GPUAssembler:
             masks.append(mask)
             keep += [alpha_dev]
         t0 = time.perf_counter()
-        p = _Plan()
-        p.n_dof = n_dof
-        dest_ptrs = (ctypes.c_void_p * nseg)(*[d.data_ptr() for d in dests])
-        n_items = (ctypes.c_int64 * nseg)(*[int(d.shape[0]) for d in dests])
-        n_loc = (ctypes.c_int32 * nseg)(*[int(d.shape[1]) for d in dests])
-        mask_ptrs = (ctypes.c_void_p * nseg)(*[m.data_ptr() for m in masks])
-        handle = ctypes.c_void_p()
-        _lib.check(
-            lib.nfa_plan_create_filtered(n_dof, nseg, dest_ptrs, n_items, n_loc, None, mask_ptrs, ctypes.byref(handle), stream),
-            "nfa_plan_create_filtered",
-        )
-        p.plan = handle
-        p.nnz = int(lib.nfa_plan_nnz(p.plan))
-        p.indptr = torch.empty(n_dof + 1, dtype=torch.int32, device=dev.device)
-        p.indices = torch.empty(p.nnz, dtype=torch.int32, device=dev.device)
-        _lib.check(lib.nfa_plan_csr(p.plan, _lib.ptr(p.indptr), _lib.ptr(p.indices), stream), "nfa_plan_csr")
-        p.build_seconds = time.perf_counter() - t0
-        self._filtered_plan = p
-        jac.bind_pattern(("filtered", id(p)), n_dof, p.indptr, p.indices)
+        # the pattern depends on the values, but in a Newton / time loop it rarely changes: when the masks (and the
+        # destination tables) are the ones of the previous assembly, its plan -- a sort of every kept local entry -- is reused
+        prev = self._filtered_plan
+        same = prev is not None and prev.n_dof == n_dof and len(prev.masks) == nseg and \
+            all(pd is d and pm.shape == m.shape and bool(torch.equal(pm, m)) for pd, pm, d, m in zip(prev.dests, prev.masks, dests, masks))
+        if same:
+            p = prev
+            p.masks = masks  # the previous arrays may be released
+            p.reused += 1
+        else:
+            p = _Plan()
+            p.n_dof = n_dof
+            dest_ptrs = (ctypes.c_void_p * nseg)(*[d.data_ptr() for d in dests])
+            n_items = (ctypes.c_int64 * nseg)(*[int(d.shape[0]) for d in dests])
+            n_loc = (ctypes.c_int32 * nseg)(*[int(d.shape[1]) for d in dests])
+            mask_ptrs = (ctypes.c_void_p * nseg)(*[m.data_ptr() for m in masks])
+            handle = ctypes.c_void_p()
+            _lib.check(
+                lib.nfa_plan_create_filtered(n_dof, nseg, dest_ptrs, n_items, n_loc, None, mask_ptrs, ctypes.byref(handle), stream),
+                "nfa_plan_create_filtered",
+            )
+            p.plan = handle
+            p.nnz = int(lib.nfa_plan_nnz(p.plan))
+            p.indptr = torch.empty(n_dof + 1, dtype=torch.int32, device=dev.device)
+            p.indices = torch.empty(p.nnz, dtype=torch.int32, device=dev.device)
+            _lib.check(lib.nfa_plan_csr(p.plan, _lib.ptr(p.indptr), _lib.ptr(p.indices), stream), "nfa_plan_csr")
+            p.build_seconds = time.perf_counter() - t0
+            p.dests, p.masks, p.reused = list(dests), masks, 0
+            self._filtered_plan = p
+        if jac.plan_key != ("filtered", id(p)):
+            jac.bind_pattern(("filtered", id(p)), n_dof, p.indptr, p.indices)
         ke_ptrs = (ctypes.c_void_p * nseg)(*[k.data_ptr() for k in Ke_list])
         re_ptrs = (ctypes.c_void_p * nseg)(*[r.data_ptr() for r in re_list])
         _lib.check(

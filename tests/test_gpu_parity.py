@@ -156,6 +156,40 @@ def test_example_driver_scatter_policy_primal_elasticity():
     compare_csr(got, ref, RTOL)
 
 
+def test_filtered_pattern_plan_is_reused_while_the_masks_do_not_change():
+    """A Newton loop on the example drivers' value-dependent pattern: the second assembly finds the same masks and reuses
+    the plan (no second sort of the kept entries); another load changes nothing in the pattern either; a coefficient that
+    zeroes entries does, and the plan is rebuilt."""
+    from nfempy_b200.assembly import GPUAssembler
+
+    case = elasticity_case(n=2, with_bc=True, k=2)
+    space = case.space()
+    asm = GPUAssembler(space, None, np.zeros(space.n_dof), pattern_policy="filtered_upper", explicit_diagonal=True)
+    asm.form_to_input_list = case.gpu_forms(space, None)
+    first = [np.array(v, copy=True) for v in asm.assemble()]
+    plan = asm._filtered_plan
+    assert plan.reused == 0
+    again = asm.assemble()
+    assert asm._filtered_plan is plan and plan.reused == 1
+    assert all(np.array_equal(a, b) for a, b in zip(first, again))
+    compare_csr(again, case.run_oracle(upper=True, explicit_diagonal=True), RTOL)
+    # other coefficients: whatever happens to the masks, the system is the one a fresh assembler builds
+    wf = asm.form_to_input_list["volume"][2]
+    fns = dict(wf.functions)
+    fns["lambda"] = lambda x, y, z: 0.0 * x
+    wf.functions = fns
+    third = [np.array(v, copy=True) for v in asm.assemble()]
+    fresh = GPUAssembler(space, None, np.zeros(space.n_dof), pattern_policy="filtered_upper", explicit_diagonal=True)
+    fresh.form_to_input_list = asm.form_to_input_list
+    want = fresh.assemble()
+    assert all(np.array_equal(a, b) for a, b in zip(third, want))
+    # another sequence: other destination tables -> the plan is rebuilt
+    before = asm._filtered_plan
+    asm.form_to_input_list["volume"][1] = list(range(3, 40))
+    asm.assemble()
+    assert asm._filtered_plan is not before and asm._filtered_plan.reused == 0
+
+
 def test_scatter_forms_reuses_cached_coefficients_and_tracks_the_state_vector():
     """Second and later ``scatter_forms()`` calls (a Newton loop written the reference's way,
     R/examples/geothermal_flow/three_fields_advection_diffusion.py:397-431) reuse the evaluated coefficient arrays and the
