@@ -185,10 +185,20 @@ class SundusDualWeakFormBCDirichlet(BatchedWeakForm):
         if Ke is not None:
             Ke.zero_()
         nfd = data.nfd
-        for k, part in enumerate(data.parts):
-            tmp = torch.empty((data.n_items, nfd), dtype=torch.float64, device=dev.device)
-            data.inner.launch_local(dev, part, None, None, None, tmp)
-            re[:, k * nfd : (k + 1) * nfd] = tmp
+        d = data.parts[0]
+        common = (_lib.ptr(d.trace_tab), _lib.ptr(d.tidx), _lib.ptr(d.w), _lib.ptr(d.tcases), _lib.ptr(d.cases),
+                  _lib.ptr(dev.coords), _lib.ptr(d.facet_nodes), _lib.ptr(d.neigh_nodes), _lib.ptr(d.normals))
+        if nfd == 1:
+            # lowest order: local order [mp_f, mc_f] = one facet function with the two boundary data as components -> one
+            # launch on the interleaved data instead of two launches + two strided copies
+            if data.get("pd2") is None:
+                data.pd2 = torch.stack([p.pd for p in data.parts], dim=2).contiguous()
+            _lib.call("nfa_local_hdiv_facet_vec", d.dim, 1, d.n_q, 2, *common, _lib.ptr(data.pd2), data.n_items, 1.0, 0, 2,
+                      _lib.ptr(re), _lib.stream_ptr())
+            return
+        for k, part in enumerate(data.parts):  # the field's block of the local vector written in place
+            _lib.call("nfa_local_hdiv_facet_vec", d.dim, nfd, d.n_q, 1, *common, _lib.ptr(part.pd), data.n_items, 1.0, k * nfd,
+                      2 * nfd, _lib.ptr(re), _lib.stream_ptr())
 
 
 class _FluxView:
