@@ -154,3 +154,47 @@ def test_n2e_mapped_oriented_basis_equals_the_physical_functions(dim):
         phi = covariant_piola(tab, (X[1:] - X[0]).T) * sg[i][None, :, None]
         _, _, ref = ref_hcurl.nedelec2(rs.discrete_spaces["e"], rs.discrete_spaces["e"].element_ids[i], pts)
         assert np.abs(phi - ref[:, :, : phi.shape[2]]).max() <= 1e-12
+
+
+def test_n2e_tangential_traces_are_single_valued_on_shared_edges():
+    """Conformity of the second-kind element on a tetrahedral mesh: after the covariant map and the diag(-1, +1) edge
+    transformation, the two functions of an edge have the same tangential trace -- as a function of the position along
+    the GLOBALLY oriented edge -- in every cell that shares the edge, their moments against 1 and sqrt(3)(2s - 1) are the
+    identity, and the functions of all other edges have no tangential trace there."""
+    dim = 3
+    mesh = box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True)
+    el = create_element("N2E", dim, 1)
+    flip = np.diag(el.entity_transformations()["interval"][0])
+    edges = SUB_ENTITIES[dim][1]
+    verts = REF_VERTICES[dim]
+    s, w = np.polynomial.legendre.leggauss(3)
+    s, w = 0.5 * (s + 1.0), 0.5 * w
+    q = np.stack([np.ones_like(s), np.sqrt(3.0) * (2.0 * s - 1.0)])
+    seen, checked = {}, 0
+    for nodes in mesh.vol_nodes:
+        X = mesh.points[nodes]
+        J = (X[1:] - X[0]).T
+        for i, (a, b) in enumerate(edges):
+            ga, gb = int(nodes[a]), int(nodes[b])
+            oriented = ga < gb
+            lo, hi = (a, b) if oriented else (b, a)  # local vertices in the global direction of the edge
+            xi = verts[lo][None, :] + s[:, None] * (verts[hi] - verts[lo])[None, :]
+            phi = covariant_piola(el.tabulate(0, xi)[0], J)  # [nq, n_phi, 3]
+            sign = np.ones(el.n_phi)
+            for e, (ea, eb) in enumerate(edges):
+                if not int(nodes[ea]) < int(nodes[eb]):
+                    sign[2 * e : 2 * e + 2] = flip
+            tangent = mesh.points[max(ga, gb)] - mesh.points[min(ga, gb)]
+            trace = np.einsum("qjc,c->qj", phi, tangent) * sign[None, :]  # [nq, n_phi] along the global direction
+            moments = np.einsum("kq,q,qj->kj", q, w, trace)  # [2, n_phi]
+            want = np.zeros((2, el.n_phi))
+            want[0, 2 * i], want[1, 2 * i + 1] = 1.0, 1.0
+            assert np.abs(moments - want).max() < 1e-12
+            own = trace[:, 2 * i : 2 * i + 2]
+            key = (min(ga, gb), max(ga, gb))
+            if key in seen:
+                assert np.abs(own - seen[key]).max() < 1e-12
+                checked += 1
+            else:
+                seen[key] = own
+    assert checked > 50
