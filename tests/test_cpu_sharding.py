@@ -221,3 +221,24 @@ def test_halo_replicated_rows_are_final_without_exchange_over_gloo(world):
         p.join(timeout=180)
         assert p.exitcode == 0
     assert out.get(timeout=10) == (1, 1, 1)
+
+
+def test_halo_replicated_assembler_refuses_what_it_cannot_shard():
+    from nfempy_b200.assembly.sharding import HaloReplicatedAssembler
+
+    case, space = _sundus_space(2)
+    forms = case.gpu_forms(space, case.alphas(space.n_dof))
+    h = HaloReplicatedAssembler(space, 2, 0)
+    part = dict(forms)
+    part["volume"] = list(forms["volume"])
+    part["volume"][1] = range(5)  # a volume form over part of the cells: the caller already partitioned, refuse
+    with pytest.raises(NotImplementedError):
+        h.set_forms(part)
+    odd = dict(forms)
+    odd["coupling"] = ["interface_form", [], forms["volume"][2], None]
+    with pytest.raises(NotImplementedError):
+        h.set_forms(odd)
+    # world 1: everything is the rank's own
+    h1 = HaloReplicatedAssembler(space, 1, 0).set_forms(forms)
+    assert len(h1.cells) == len(space.destination_table()) and len(h1.owned_rows) == space.n_dof
+    assert len(h1.asm.form_to_input_list["bc"][1]) == len(space.discrete_spaces["mp"].bc_elements)
