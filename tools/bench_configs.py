@@ -3,8 +3,14 @@
 
   config 1  2-D Poisson, H1 p=1, 64 x 64 x 2 triangles            (launch/latency bound; time only)
   config 2' 3-D elasticity p=2 through the TWO-STAGE path           (for comparison with the fused path)
-  config 3  3-D mixed Poisson, RT_k x P_{k-1}^disc, k = 1, 2, 3     (two-stage path; k = 3 on a smaller box because
-            the generic plan indexes local entries with 31 bits)
+  config 2" 3-D elasticity p=2 with the example driver's scatter policy (filtered_upper + explicit diagonal)
+  config 3  3-D mixed Poisson, RT_k x P_{k-1}^disc, k = 1, 2, 3     (k = 1 by row owner, csrc/nfa_hdivrows.cu; k = 2, 3
+            two-stage; k = 3 on a smaller box because the generic plan indexes local entries with 31 bits); the
+            degenerate-elliptic form at k = 1 (row owner) and k = 2 (two-stage)
+  config 4  mixed Cosserat elasticity at the reference example's orders (two-stage; tools/bench_config4.py runs the
+            BASELINE order through the streamed assembler)
+  config 5  two-flux transport, 100 reassemblies on one plan: one box, and the mixed-dimensional fractured box (row owner;
+            tools/bench_config5_sharded.py runs it on N GPUs)
 
 One JSON line per case: elements/s with inputs resident in HBM (CUDA events, K steps after W warm-ups), nnz, local
 sizes, plan-build seconds, and the oracle's rate on a few cells of the same mesh (1 core) for scale.
