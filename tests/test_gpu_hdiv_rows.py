@@ -167,6 +167,7 @@ def test_chunked_state_upload_and_residual_add(monkeypatch):
     from nfempy_b200.assembly import gpu_assembler
 
     monkeypatch.setattr(gpu_assembler, "_CHUNK", 37)
+    monkeypatch.setenv("NFA_HOST_THREADS", "4")  # the pool is sized from the core count; force it on small boxes too
     case = SundusCase(dim=3, k=1, n=2)
     _, asm = _assembler(case, SundusCase.alphas)
     got = [np.array(v, copy=True) for v in asm.assemble()]
