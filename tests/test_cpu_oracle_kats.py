@@ -140,3 +140,38 @@ def test_oracle_reproduces_golden_multi_form_fixture():
         assert np.array_equal(indptr, z[name + "_indptr"]) and np.array_equal(indices, z[name + "_indices"]), name
         assert np.abs(data - z[name + "_data"]).max() <= 1e-13 * np.abs(data).max(), name
         assert np.abs(rhs - z[name + "_rhs"]).max() <= 1e-13 * max(np.abs(rhs).max(), 1e-300), name
+
+
+def test_sundus_oracle_tangent_is_the_derivative_of_its_residual():
+    """The nonlinear two-flux form (reaction 1 + eta c^2): the oracle's complex-step Jacobian against central differences
+    of its own residual, its structure (no (mp, mc) / (p, c) couplings, the reaction tangent only on (c, c)) and the
+    linearity in everything but c -- what the CUDA kernels' hand-derived tangent is compared with."""
+    from oracle import ref_forms
+    from tests.parity_helpers import SundusCase
+
+    case = SundusCase(dim=3, k=1, n=1)
+    space = case.ref_space()
+    n_loc = len(space.destination_indexes(0))
+    rng = np.random.default_rng(11)
+    a, a_n = rng.standard_normal(n_loc), rng.standard_normal(n_loc)
+    r0, J = ref_forms.sundus_dual(space, case.functions, 2, a, a_n, case.t)
+    h = 1e-6
+    for j in range(n_loc):
+        e = np.zeros(n_loc)
+        e[j] = h
+        rp, _ = ref_forms.sundus_dual(space, case.functions, 2, a + e, a_n, case.t)
+        rm, _ = ref_forms.sundus_dual(space, case.functions, 2, a - e, a_n, case.t)
+        assert np.abs((rp - rm) / (2 * h) - J[:, j]).max() <= 1e-7 * max(1.0, np.abs(J).max())
+    n_u = (n_loc - 2) // 2
+    mp, mc, p, c = slice(0, n_u), slice(n_u, 2 * n_u), 2 * n_u, 2 * n_u + 1
+    assert not J[mp, mc].any() and not J[mc, mp].any() and J[p, c] == 0.0 and J[c, p] == 0.0
+    assert not J[mp, c].any() and not J[mc, p].any() and not J[p, mc].any() and not J[c, mp].any()
+    assert np.allclose(J[mp, p], -J[p, mp]) and np.allclose(J[mc, c], -J[c, mc]) and np.allclose(J[mp, mp], J[mp, mp].T)
+    # only the (c, c) entry depends on the iterate: J(a) - J(a') is zero elsewhere
+    a2 = a.copy()
+    a2[c] += 0.7
+    _, J2 = ref_forms.sundus_dual(space, case.functions, 2, a2, a_n, case.t)
+    D = J2 - J
+    assert abs(D[c, c]) > 1e-6
+    D[c, c] = 0.0
+    assert np.abs(D).max() <= 1e-13 * np.abs(J).max()
