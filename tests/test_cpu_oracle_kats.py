@@ -1,6 +1,7 @@
 """CPU tests pinning the oracle: known-answer and invariant tests of the restated weak forms (the reference's own
 tests hold no golden vectors for this path), plus the committed golden fixtures."""
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 from oracle import ref_assembly, ref_forms
@@ -175,3 +176,47 @@ def test_sundus_oracle_tangent_is_the_derivative_of_its_residual():
     assert abs(D[c, c]) > 1e-6
     D[c, c] = 0.0
     assert np.abs(D).max() <= 1e-13 * np.abs(J).max()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_oracle_lowest_order_mixed_poisson_reproduces_a_constant_flux(dim):
+    """Known answer for RT_1 x P_0 (element scaling, Piola map, facet orientation and the sign of the natural boundary
+    term all enter): with f = 0, constant kappa and linear boundary data p_D the discrete solution is the exact constant
+    flux u = -kappa grad p_D, and the pressure dofs are the cell averages of p_D, i.e. its centroid values."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from oracle import ref_assembly, ref_forms
+    from tests.parity_helpers import mixed_poisson_case
+
+    case = mixed_poisson_case(dim=dim, k=1, n=2)
+    space = case.ref_space()
+    grad = np.array([1.0, 2.0, -1.0 if dim == 3 else 0.0])
+    p_d = lambda x, y, z: np.array([grad[0] * x + grad[1] * y + grad[2] * z + 0.25])
+    u_sp = space.discrete_spaces["u"]
+    forms = [
+        ("form", ref_forms.laplace_dual, {"rhs": lambda x, y, z: np.array([0.0 * x]), "kappa": lambda x, y, z: 2.0}, len(u_sp.element_ids)),
+        ("bc_form", ref_forms.laplace_dual_bc_dirichlet, {"p": p_d}, len(u_sp.bc_element_ids)),
+    ]
+    indptr, indices, data, rhs = ref_assembly.assemble(space, forms)
+    A = sp.csr_matrix((data, indices, indptr)).tocsc()
+    sol = spl.spsolve(A, -rhs)
+    assert np.abs(A @ sol + rhs).max() < 1e-11
+    n_u = u_sp.n_dof
+    mesh = space.discrete_spaces["p"].mesh
+    for i, cid in enumerate(space.discrete_spaces["p"].element_ids):
+        centroid = mesh.points[mesh.cells[cid].node_tags].mean(axis=0)
+        dof = space.destination_indexes(i)[-1]
+        assert dof >= n_u and abs(sol[dof] - float(p_d(*centroid)[0])) < 1e-10
+    # the discrete flux is the exact one: evaluate u_h at the centroid of a few cells through the oracle's basis
+    from oracle.ref_forms import RefElement
+
+    exact = -2.0 * grad[:dim]
+    for i in range(0, len(u_sp.element_ids), 5):
+        el = RefElement(u_sp, u_sp.element_ids[i])
+        pts = np.full((1, dim), 1.0 / (dim + 1))
+        x, jac, det_jac, inv_jac = el.evaluate_mapping(pts)
+        tab = el.evaluate_basis(pts, jac, det_jac, inv_jac)
+        dest = space.destination_indexes(i)[: tab.shape[2]]
+        u_h = sol[dest] @ tab[0, 0, :, :dim]
+        assert np.abs(u_h - exact).max() < 1e-10
