@@ -220,3 +220,49 @@ def test_oracle_lowest_order_mixed_poisson_reproduces_a_constant_flux(dim):
         dest = space.destination_indexes(i)[: tab.shape[2]]
         u_h = sol[dest] @ tab[0, 0, :, :dim]
         assert np.abs(u_h - exact).max() < 1e-10
+
+
+@pytest.mark.parametrize("family,k,dim,n", [
+    ("RT", 2, 2, 3), ("RT", 3, 2, 2), ("BDM", 1, 2, 3), ("BDM", 2, 2, 3), ("BDM", 3, 2, 2),
+    ("RT", 2, 3, 2), ("RT", 3, 3, 1), ("BDM", 1, 3, 2), ("BDM", 2, 3, 1), ("BDM", 3, 3, 1),
+])
+def test_oracle_mixed_poisson_is_exact_for_polynomial_fluxes(family, k, dim, n):
+    """Known answer for every H(div) element of the oracle (facet and interior moments, their scaling, the Piola map and
+    the orientation transformations of all facets of a mesh with shuffled local vertices): for p = s^k / k with
+    s = a . x, constant kappa and f = div u the flux u = -kappa grad p has degree k - 1, lies in RT_k and BDM_k, and
+    div u lies in the pressure space -- so (u, P_h p) solves the discrete equations and the computed flux is the exact one
+    at every point."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from oracle import ref_assembly, ref_forms
+    from oracle.ref_forms import RefElement
+    from tests.parity_helpers import mixed_poisson_case
+
+    kappa = 2.0
+    a = np.array([1.0, 2.0, -1.0 if dim == 3 else 0.0])
+    s = lambda x, y, z: a[0] * x + a[1] * y + a[2] * z + 0.3
+    p_d = lambda x, y, z: np.array([s(x, y, z) ** k / k])
+    flux = lambda x, y, z: -kappa * s(x, y, z) ** (k - 1) * a[:dim]
+    rhs = lambda x, y, z: np.array([-kappa * (k - 1) * s(x, y, z) ** max(k - 2, 0) * float(a @ a) + 0.0 * x])
+    case = mixed_poisson_case(dim=dim, k=k, n=n, family=family)
+    space = case.ref_space()
+    u_sp = space.discrete_spaces["u"]
+    forms = [
+        ("form", ref_forms.laplace_dual, {"rhs": rhs, "kappa": lambda x, y, z: kappa}, len(u_sp.element_ids)),
+        ("bc_form", ref_forms.laplace_dual_bc_dirichlet, {"p": p_d}, len(u_sp.bc_element_ids)),
+    ]
+    indptr, indices, data, res = ref_assembly.assemble(space, forms)
+    A = sp.csr_matrix((data, indices, indptr)).tocsc()
+    sol = spl.spsolve(A, -res)
+    assert np.abs(A @ sol + res).max() < 1e-9 * max(1.0, np.abs(res).max())
+    pts = np.array([[0.2, 0.3, 0.1][:dim], [0.6, 0.1, 0.25][:dim]])
+    scale = max(1.0, np.abs(flux(1.0, 1.0, 0.0)).max())
+    for i in range(len(u_sp.element_ids)):
+        el = RefElement(u_sp, u_sp.element_ids[i])
+        x, jac, det_jac, inv_jac = el.evaluate_mapping(pts)
+        tab = el.evaluate_basis(pts, jac, det_jac, inv_jac)
+        dest = space.destination_indexes(i)[: tab.shape[2]]
+        for q in range(len(pts)):
+            u_h = sol[dest] @ tab[0, q, :, :dim]
+            assert np.abs(u_h - flux(*x[q])).max() < 1e-8 * scale, (i, q, u_h, flux(*x[q]))
