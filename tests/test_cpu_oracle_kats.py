@@ -266,3 +266,103 @@ def test_oracle_mixed_poisson_is_exact_for_polynomial_fluxes(family, k, dim, n):
         for q in range(len(pts)):
             u_h = sol[dest] @ tab[0, q, :, :dim]
             assert np.abs(u_h - flux(*x[q])).max() < 1e-8 * scale, (i, q, u_h, flux(*x[q]))
+
+
+@pytest.mark.parametrize("dim,k", [(2, 1), (3, 1), (2, 2)])
+def test_oracle_mixed_elasticity_reproduces_a_constant_stress(dim, k):
+    """Known answer for the weakly symmetric mixed elasticity oracle (config 4's form family: row-wise BDM stresses,
+    discontinuous displacement and rotation multipliers, natural displacement condition): for a linear displacement
+    u = G x + b with constant Lame parameters the stress sigma = 2 mu sym(G) + lambda tr(G) I is constant, lies in the
+    stress space with div sigma = 0, and the rotation is constant -- so the discrete solution carries the exact stress
+    at every point, whatever the orientation of the facets."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from oracle import ref_assembly
+    from oracle import ref_tensor_forms as rt
+    from oracle.ref_forms import RefElement
+    from tests.parity_helpers import tensor_mixed_case
+
+    lam, mu = 1.5, 0.75
+    G = np.array([[0.3, -0.2, 0.5], [0.7, 0.1, -0.4], [-0.6, 0.25, 0.2]])[:dim, :dim]
+    b = np.array([0.1, -0.3, 0.2])[:dim]
+    sigma = mu * (G + G.T) + lam * np.trace(G) * np.eye(dim)
+    tc = 3 if dim == 3 else 1
+    u_d = lambda x, y, z: np.array([sum(G[r, c] * (x, y, z)[c] for c in range(dim)) + b[r] for r in range(dim)])
+    functions = {"rhs": lambda x, y, z: np.zeros((dim + tc,) + np.shape(x)), "lambda": lambda x, y, z: lam, "mu": lambda x, y, z: mu}
+    case = tensor_mixed_case(kind="le", dim=dim, s_family="BDM", k=k, n=2 if dim == 2 or k == 1 else 1)
+    space = case.ref_space()
+    s_sp = space.discrete_spaces["s"]
+    forms = [("form", rt.le_dual, functions, len(s_sp.element_ids)),
+             ("bc_form", rt.le_dual_bc_dirichlet, {"u": u_d}, len(s_sp.bc_element_ids))]
+    indptr, indices, data, res = ref_assembly.assemble(space, forms)
+    A = sp.csr_matrix((data, indices, indptr)).tocsc()
+    sol = spl.spsolve(A, -res)
+    assert np.abs(A @ sol + res).max() < 1e-10 * max(1.0, np.abs(res).max())
+    pts = np.array([[0.2, 0.3, 0.1][:dim], [0.55, 0.15, 0.2][:dim]])
+    for i in range(len(s_sp.element_ids)):
+        el = RefElement(s_sp, s_sp.element_ids[i])
+        x, jac, det_jac, inv_jac = el.evaluate_mapping(pts)
+        tab = el.evaluate_basis(pts, jac, det_jac, inv_jac)
+        n_phi = tab.shape[2]
+        coef = sol[space.destination_indexes(i)[: n_phi * dim]].reshape(n_phi, dim)  # [basis, row]: component-minor dofs
+        for q in range(len(pts)):
+            s_h = coef.T @ tab[0, q, :, :dim]  # row r = sum_j coef[j, r] psi_j
+            assert np.abs(s_h - sigma).max() < 1e-9 * np.abs(sigma).max(), (i, q, s_h, sigma)
+
+
+@pytest.mark.parametrize("kind", ["lce", "lce_scaled"])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_oracle_mixed_cosserat_reproduces_a_symmetric_constant_stress(kind, dim):
+    """Known answer for the mixed Cosserat oracles (BASELINE config 4's forms): a linear displacement with SYMMETRIC
+    gradient and zero micro-rotation gives the constant symmetric stress 2 mu_s G + lambda_s tr(G) I (the coupling modulus
+    kappa_s only acts on the skew part) and zero couple stress; both lie in the discrete spaces with zero divergence,
+    the angular balance holds because the stress is symmetric, so the discrete solution is exact -- for the plain and for
+    the length-scaled formulation (variable length scale l(x))."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from oracle import ref_assembly
+    from oracle import ref_tensor_forms as rt
+    from oracle.ref_forms import RefElement
+    from tests.parity_helpers import tensor_mixed_case
+
+    lam, mu = 1.5, 0.75
+    G = np.array([[0.3, -0.2, 0.5], [-0.2, 0.1, -0.4], [0.5, -0.4, 0.2]])[:dim, :dim]
+    b = np.array([0.1, -0.3, 0.2])[:dim]
+    sigma = 2.0 * mu * G + lam * np.trace(G) * np.eye(dim)
+    tc = 3 if dim == 3 else 1
+    one = lambda x: np.ones_like(x)
+    functions = {
+        "rhs": lambda x, y, z: np.zeros((dim + tc,) + np.shape(x)),
+        "lambda_s": lambda x, y, z: lam * one(x), "mu_s": lambda x, y, z: mu * one(x), "kappa_s": lambda x, y, z: 0.35 * one(x),
+        "lambda_o": lambda x, y, z: 0.7 * one(x), "mu_o": lambda x, y, z: 1.3 * one(x), "kappa_o": lambda x, y, z: 0.4 * one(x),
+        "l": lambda x, y, z: 0.5 + 0.25 * x + 0.1 * y * y, "grad_l": lambda x, y, z: np.array([0.25 * one(x), 0.2 * y, 0.0 * x]),
+    }
+    bc_functions = {
+        "u": lambda x, y, z: np.array([sum(G[r, c] * (x, y, z)[c] for c in range(dim)) + b[r] for r in range(dim)]),
+        "t": lambda x, y, z: np.zeros((tc,) + np.shape(x)), "l": functions["l"], "grad_l": functions["grad_l"],
+    }
+    case = tensor_mixed_case(kind=kind, dim=dim, s_family="BDM", m_family="RT", k=1, n=2)
+    space = case.ref_space()
+    s_sp, m_sp = space.discrete_spaces["s"], space.discrete_spaces["m"]
+    vol, bc = (rt.lce_dual, rt.lce_dual_bc_dirichlet) if kind == "lce" else (rt.lce_scaled_dual, rt.lce_scaled_dual_bc_dirichlet)
+    forms = [("form", vol, functions, len(s_sp.element_ids)), ("bc_form", bc, bc_functions, len(s_sp.bc_element_ids))]
+    indptr, indices, data, res = ref_assembly.assemble(space, forms)
+    A = sp.csr_matrix((data, indices, indptr)).tocsc()
+    sol = spl.spsolve(A, -res)
+    assert np.abs(A @ sol + res).max() < 1e-10 * max(1.0, np.abs(res).max())
+    pts = np.array([[0.2, 0.3, 0.1][:dim], [0.55, 0.15, 0.2][:dim]])
+    mc = m_sp.n_comp
+    for i in range(len(s_sp.element_ids)):
+        el_s, el_m = RefElement(s_sp, s_sp.element_ids[i]), RefElement(m_sp, m_sp.element_ids[i])
+        x, jac, det_jac, inv_jac = el_s.evaluate_mapping(pts)
+        tab_s = el_s.evaluate_basis(pts, jac, det_jac, inv_jac)
+        tab_m = el_m.evaluate_basis(pts, jac, det_jac, inv_jac)
+        dest = space.destination_indexes(i)
+        ns, nm = tab_s.shape[2], tab_m.shape[2]
+        cs = sol[dest[: ns * dim]].reshape(ns, dim)
+        cm = sol[dest[ns * dim : ns * dim + nm * mc]].reshape(nm, mc)
+        for q in range(len(pts)):
+            assert np.abs(cs.T @ tab_s[0, q, :, :dim] - sigma).max() < 1e-9 * np.abs(sigma).max()
+            assert np.abs(cm.T @ tab_m[0, q, :, :dim]).max() < 1e-9 * np.abs(sigma).max()
