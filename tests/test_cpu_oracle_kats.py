@@ -366,3 +366,43 @@ def test_oracle_mixed_cosserat_reproduces_a_symmetric_constant_stress(kind, dim)
         for q in range(len(pts)):
             assert np.abs(cs.T @ tab_s[0, q, :, :dim] - sigma).max() < 1e-9 * np.abs(sigma).max()
             assert np.abs(cm.T @ tab_m[0, q, :, :dim]).max() < 1e-9 * np.abs(sigma).max()
+
+
+@pytest.mark.parametrize("kind", ["degenerate", "unscaled"])
+@pytest.mark.parametrize("dim,k", [(2, 1), (3, 1), (2, 2), (3, 2)])
+def test_oracle_degenerate_elliptic_forms_reproduce_a_constant_flux(kind, dim, k):
+    """Known answer for the Arbogast-Taicher forms of config 3 (flux mass, generalised divergence coupling AND the (q, q)
+    mass block): with porosity = d_phi = 1 both forms read (v, psi) - (q, div psi) = -<q_D, psi . n>,
+    (div v, w) + (q, w) = (f, w); for linear q and f = q the flux v = -grad q is constant and (v, P_h q) solves the
+    discrete equations, so the computed flux is exact at every point."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from oracle import ref_assembly, ref_forms
+    from oracle.ref_forms import RefElement
+    from tests.parity_helpers import degenerate_case
+
+    a = np.array([1.0, 2.0, -1.0 if dim == 3 else 0.0])
+    q_ex = lambda x, y, z: np.array([a[0] * x + a[1] * y + a[2] * z + 0.25])
+    one = lambda x: np.ones_like(x)
+    flux_name, scalar = ("u", "p") if kind == "unscaled" else ("v", "q")
+    functions = {"rhs": q_ex, "porosity": lambda x, y, z: one(x), "d_phi": lambda x, y, z: one(x),
+                 "grad_d_phi": lambda x, y, z: np.array([0.0 * x, 0.0 * y, 0.0 * z])}
+    bc_functions = {scalar: q_ex, "porosity": functions["porosity"], "d_phi": functions["d_phi"]}
+    space = degenerate_case(kind=kind, dim=dim, k=k, n=2).ref_space()
+    v_sp = space.discrete_spaces[flux_name]
+    vol, bc = (ref_forms.unscaled_elliptic, ref_forms.unscaled_elliptic_bc_dirichlet) if kind == "unscaled" else \
+        (ref_forms.degenerate_elliptic, ref_forms.degenerate_elliptic_bc_dirichlet)
+    forms = [("form", vol, functions, len(v_sp.element_ids)), ("bc_form", bc, bc_functions, len(v_sp.bc_element_ids))]
+    indptr, indices, data, res = ref_assembly.assemble(space, forms)
+    A = sp.csr_matrix((data, indices, indptr)).tocsc()
+    sol = spl.spsolve(A, -res)
+    assert np.abs(A @ sol + res).max() < 1e-10 * max(1.0, np.abs(res).max())
+    pts = np.array([[0.2, 0.3, 0.1][:dim], [0.55, 0.15, 0.2][:dim]])
+    for i in range(len(v_sp.element_ids)):
+        el = RefElement(v_sp, v_sp.element_ids[i])
+        x, jac, det_jac, inv_jac = el.evaluate_mapping(pts)
+        tab = el.evaluate_basis(pts, jac, det_jac, inv_jac)
+        dest = space.destination_indexes(i)[: tab.shape[2]]
+        for q in range(len(pts)):
+            assert np.abs(sol[dest] @ tab[0, q, :, :dim] + a[:dim]).max() < 1e-9
