@@ -406,3 +406,53 @@ def test_oracle_degenerate_elliptic_forms_reproduce_a_constant_flux(kind, dim, k
         dest = space.destination_indexes(i)[: tab.shape[2]]
         for q in range(len(pts)):
             assert np.abs(sol[dest] @ tab[0, q, :, :dim] + a[:dim]).max() < 1e-9
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_sundus_oracle_steady_linear_state_is_a_fixed_point(dim):
+    """Known answer for the two-flux transport oracle (config 5) without the nonlinearity (eta = 0): linear p and c that
+    do not change in time (previous level = cell averages of the same fields), constant kappa and delta, f_f = 0 and
+    f_r = 1 (the reaction's constant part): one Newton step from zero lands on the exact constant fluxes
+    mp = -kappa grad p, mc = -delta grad c and on the cell averages of p and c -- time-derivative terms, both
+    divergence couplings, the boundary terms and their signs all enter."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from oracle import ref_assembly, ref_forms
+    from oracle.ref_forms import RefElement
+    from tests.parity_helpers import SundusCase
+
+    kappa, delta = 2.0, 1.5
+    gp = np.array([1.0, 2.0, -1.0 if dim == 3 else 0.0])
+    gc = np.array([-0.5, 0.75, 0.4 if dim == 3 else 0.0])
+    p_ex = lambda x, y, z, t=0.0: np.array([gp[0] * x + gp[1] * y + gp[2] * z + 0.2])
+    c_ex = lambda x, y, z, t=0.0: np.array([gc[0] * x + gc[1] * y + gc[2] * z - 0.1])
+    one = lambda x: np.ones_like(x)
+    functions = {"rhs_f": lambda x, y, z, t: np.array([0.0 * x]), "rhs_r": lambda x, y, z, t: np.array([one(x)]),
+                 "kappa": lambda x, y, z: kappa, "delta": lambda x, y, z: delta, "eta": lambda x, y, z: 0.0, "delta_t": 0.1}
+    case = SundusCase(dim=dim, k=1, n=2)
+    space = case.ref_space()
+    mp = space.discrete_spaces["mp"]
+    n_cells = len(mp.element_ids)
+    mesh = mp.mesh
+    previous = np.zeros(space.n_dof)
+    for i in range(n_cells):
+        centroid = mesh.points[mesh.cells[mp.element_ids[i]].node_tags].mean(axis=0)
+        dest = space.destination_indexes(i)
+        previous[dest[-2]], previous[dest[-1]] = p_ex(*centroid)[0], c_ex(*centroid)[0]
+    forms = [("time_dependent_form", ref_forms.sundus_dual, functions, n_cells),
+             ("time_dependent_bc_form", ref_forms.sundus_dual_bc_dirichlet, {"p": p_ex, "c": c_ex}, len(mp.bc_element_ids))]
+    indptr, indices, data, res = ref_assembly.assemble_time_dependent(space, forms, (np.zeros(space.n_dof), previous), 0.3)
+    A = sp.csr_matrix((data, indices, indptr)).tocsc()
+    sol = spl.spsolve(A, -res)
+    pts = np.array([[0.2, 0.3, 0.1][:dim], [0.55, 0.15, 0.2][:dim]])
+    for i in range(n_cells):
+        el = RefElement(mp, mp.element_ids[i])
+        x, jac, det_jac, inv_jac = el.evaluate_mapping(pts)
+        tab = el.evaluate_basis(pts, jac, det_jac, inv_jac)
+        n_u = tab.shape[2]
+        dest = space.destination_indexes(i)
+        for q in range(len(pts)):
+            assert np.abs(sol[dest[:n_u]] @ tab[0, q, :, :dim] + kappa * gp[:dim]).max() < 1e-9
+            assert np.abs(sol[dest[n_u : 2 * n_u]] @ tab[0, q, :, :dim] + delta * gc[:dim]).max() < 1e-9
+        assert abs(sol[dest[-2]] - previous[dest[-2]]) < 1e-9 and abs(sol[dest[-1]] - previous[dest[-1]]) < 1e-9
