@@ -143,6 +143,12 @@ def fractured_box_tet_mesh(n, jitter=0.0, seed=1234, shuffle_local_nodes=False):
     # fracture triangles: faces of the tets above that lie in the plane, in that tet's local face order
     faces = tets[above][:, TET_FACES].reshape(-1, 3)
     c1 = faces[np.all(on_plane[faces], axis=1)]
+    # consistently oriented fracture triangles (normal +z), as a mesher leaves the cells of a plane surface: the 2-D
+    # orientation rule of the H(div) edge functions (R/src/basis/permute_and_transform.py:8-19) only gives a continuous
+    # normal flux across an edge when both triangles turn the same way
+    P = points[c1]
+    flip = np.cross(P[:, 1] - P[:, 0], P[:, 2] - P[:, 0])[:, 2] < 0.0
+    c1[flip] = c1[flip][:, [0, 2, 1]]
     new_tets = tets.copy()
     new_tets[above] = pos_of[tets[above]]
     new_tets[~above] = neg_of[tets[~above]]

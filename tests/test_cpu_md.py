@@ -53,3 +53,49 @@ def test_oracle_coupling_block_structure():
     assert j[0, 1] == 0.0 and j[2, 2] == 0.0
     assert np.allclose(np.abs(j[0:2, 2]), 1.0, atol=1e-13)  # int psi.n over the facet of a lowest-order RT function
     assert j[0, 0] > 0 and np.isclose(j[0, 0], j[1, 1])
+
+
+def test_md_oracle_reproduces_uniform_flow_across_the_fracture():
+    """Known answer for the mixed-dimensional oracle (bulk mixed Poisson on both sides + fracture + Robin coupling,
+    R/examples/md_elliptic_scalar/CouplingWeakForm.py:11-151): a uniform flux q through the fracture plane z = 1/2.  The
+    bulk pressure is linear in z on each side with the jump the Robin law u . n = alpha (p|_Gamma - p_f) asks for
+    (alpha = kappa_n / (delta / 2)), the fracture carries no tangential flux and a constant pressure, what leaves one side
+    enters the other -- everything lies in RT_1 x P_0, so the discrete solution is exact: bulk flux (0, 0, -q) at every
+    point, fracture pressure p_f, zero fracture flux."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from oracle import ref_forms
+    from oracle.ref_forms import RefElement
+
+    mesh, spaces, ref_spaces, triples, outer = md_problem(2)
+    q, kappa, kappa_n, delta, p_f = 0.8, 2.0, 3.0, 0.2, 0.4
+    alpha = kappa_n / (delta / 2.0)
+    side = lambda z: np.where(np.asarray(z) > 0.5, 1.0, -1.0)
+    p_bulk = lambda x, y, z: np.array([p_f + side(z) * q / alpha + (q / kappa) * (np.asarray(z) - 0.5) + 0.0 * x])
+    zero = lambda x, y, z: np.array([0.0 * x])
+    f0 = {"rhs": zero, "kappa": lambda x, y, z: kappa}
+    f1 = {"rhs": zero, "kappa": lambda x, y, z: 0.7}
+    coupling = {"kappa_normal": lambda x, y, z: kappa_n, "delta": lambda x, y, z: delta}
+    u0, u1 = ref_spaces[0].discrete_spaces["u"], ref_spaces[1].discrete_spaces["u"]
+    indptr, indices, data, res = ref_md.assemble_md(
+        ref_spaces,
+        [[("form", ref_forms.laplace_dual, f0, len(u0.element_ids)), ("bc_form", ref_forms.laplace_dual_bc_dirichlet, {"p": p_bulk}, outer)],
+         [("form", ref_forms.laplace_dual, f1, len(u1.element_ids)),
+          ("bc_form", ref_forms.laplace_dual_bc_dirichlet, {"p": lambda x, y, z: np.array([p_f + 0.0 * x])}, len(u1.bc_element_ids))]],
+        triples, coupling)
+    A = sp.csr_matrix((data, indices, indptr)).tocsc()
+    sol = spl.spsolve(A, -res)
+    assert np.abs(A @ sol + res).max() < 1e-11
+    pts = np.array([[0.2, 0.3, 0.1], [0.55, 0.15, 0.2]])
+    s0, s1 = ref_spaces
+    for i in range(len(u0.element_ids)):
+        el = RefElement(u0, u0.element_ids[i])
+        x, jac, det_jac, inv_jac = el.evaluate_mapping(pts)
+        tab = el.evaluate_basis(pts, jac, det_jac, inv_jac)
+        dest = s0.destination_indexes(i)
+        for k in range(len(pts)):
+            assert np.abs(sol[dest[: tab.shape[2]]] @ tab[0, k, :, :3] - np.array([0.0, 0.0, -q])).max() < 1e-9
+    for i in range(len(u1.element_ids)):
+        dest = s1.destination_indexes(i)
+        assert abs(sol[dest[-1]] - p_f) < 1e-9 and np.abs(sol[dest[:-1]]).max() < 1e-9
