@@ -171,3 +171,30 @@ def test_general_elliptic_records_expand_to_the_oracle_matrix(kind, dim):
     blocks = [form_fn(ref, functions, i, alpha[dest[i]]) for i in range(n_cells)]
     emap, ridx, stride = hdiv_rows.general_maps(dim + 1)
     _check(dest, ref.n_dof, emap, ridx, stride, blocks, want)
+
+
+def test_row_runs_describe_every_map_and_refuse_what_does_not_fit():
+    """``row_runs``: every local row's record entries fit one 16-byte aligned run of eight doubles for the three record
+    layouts (both dimensions); a row whose entries span more, or a record entry that feeds two columns of one row, is
+    refused (the form list then takes the two-stage path)."""
+    for maps in (hdiv_rows.sundus_maps, hdiv_rows.laplace_dual_maps, hdiv_rows.general_maps):
+        for n_u in (3, 4):
+            emap, ridx, stride = maps(n_u)
+            roff, codes = hdiv_rows.row_runs(emap, ridx)
+            assert roff.dtype == np.int32 and codes.dtype == np.int8 and codes.shape == (emap.shape[0], hdiv_rows.RUN)
+            for a in range(emap.shape[0]):
+                assert roff[a] % 2 == 0 and roff[a] + hdiv_rows.RUN <= stride + 6
+                seen_cols = sorted(abs(int(c)) - 1 for c in codes[a] if c not in (0, hdiv_rows.CODE_RHS))
+                assert seen_cols == sorted(np.flatnonzero(emap[a]).tolist())
+                assert (codes[a] == hdiv_rows.CODE_RHS).sum() == 1
+                k = int(np.flatnonzero(codes[a] == hdiv_rows.CODE_RHS)[0])
+                assert roff[a] + k == ridx[a]
+                for kk, c in enumerate(codes[a]):
+                    if c not in (0, hdiv_rows.CODE_RHS):
+                        b = abs(int(c)) - 1
+                        assert abs(int(emap[a, b])) - 1 == roff[a] + kk and np.sign(emap[a, b]) == np.sign(c)
+    wide = np.zeros((2, 2), dtype=np.int16)
+    wide[0, 0], wide[0, 1] = 1, 12  # entries 0 and 11 of the record: more than one run
+    assert hdiv_rows.row_runs(wide, np.array([0, 1], dtype=np.int16)) is None
+    twice = np.array([[1, 1], [0, 2]], dtype=np.int16)  # record entry 0 feeds two columns of row 0
+    assert hdiv_rows.row_runs(twice, np.array([3, 3], dtype=np.int16)) is None
