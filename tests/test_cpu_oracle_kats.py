@@ -456,3 +456,48 @@ def test_sundus_oracle_steady_linear_state_is_a_fixed_point(dim):
             assert np.abs(sol[dest[:n_u]] @ tab[0, q, :, :dim] + kappa * gp[:dim]).max() < 1e-9
             assert np.abs(sol[dest[n_u : 2 * n_u]] @ tab[0, q, :, :dim] + delta * gc[:dim]).max() < 1e-9
         assert abs(sol[dest[-2]] - previous[dest[-2]]) < 1e-9 and abs(sol[dest[-1]] - previous[dest[-1]]) < 1e-9
+
+
+def test_taylor_hood_oracle_reproduces_a_linear_displacement():
+    """Known answer for the displacement-pressure (Taylor-Hood P2-P1) elasticity oracle: a linear displacement has a
+    constant stress, so with f = 0 its nodal interpolant together with the constant pressure (lambda + mu) div u makes
+    the residual of every row vanish -- the rows of the boundary nodes too, once the penalty term (which is zero for the
+    exact boundary values) is left out.  (Solving the penalised system instead would lose six digits to the 1e12
+    penalty in the factorisation.)"""
+    from oracle import ref_assembly, ref_h1_multi
+    from oracle.ref_basis import SUB
+    from tests.parity_helpers import taylor_hood_case
+
+    lam, mu = 3.0, 0.75
+    G = np.array([[0.3, -0.2], [0.7, 0.1]])
+    b = np.array([0.1, -0.3])
+    u_ex = lambda x, y, z: np.array([G[0, 0] * x + G[0, 1] * y + b[0], G[1, 0] * x + G[1, 1] * y + b[1]])
+    functions = {"lambda": lambda x, y, z: lam + 0.0 * x, "mu": lambda x, y, z: mu + 0.0 * x,
+                 "rhs": lambda x, y, z: np.array([0.0 * x, 0.0 * x])}
+    space = taylor_hood_case(n=3).ref_space()
+    u_sp = space.discrete_spaces["u"]
+    mesh = u_sp.mesh
+    exact = np.zeros(space.n_dof)
+    for i in range(len(u_sp.element_ids)):
+        cell = mesh.cells[u_sp.element_ids[i]]
+        X = mesh.points[cell.node_tags]
+        dest = space.destination_indexes(i)
+        for v in range(3):
+            exact[dest[2 * v : 2 * v + 2]] = u_ex(*X[v])
+        for e, (a, c) in enumerate(SUB[2][1]):
+            exact[dest[6 + 2 * e : 8 + 2 * e]] = u_ex(*(0.5 * (X[a] + X[c])))
+        exact[dest[12:15]] = (lam + mu) * np.trace(G)
+    # interior equilibrium: volume form alone, all rows whose node is not on the boundary
+    indptr, indices, data, res = ref_assembly.assemble(
+        space, [("form", ref_h1_multi.le_taylor_hood, functions, len(u_sp.element_ids))], exact)
+    boundary = np.zeros(space.n_dof, dtype=bool)
+    for i in range(len(u_sp.bc_element_ids)):
+        boundary[space.bc_destination_indexes(i)] = True
+    scale = np.abs(data).max() * np.abs(exact).max()
+    assert np.abs(res[~boundary]).max() < 1e-12 * scale and (~boundary).sum() > 50
+    # and the penalty equations hold at the exact boundary values (the boundary form ignores the state vector: its
+    # residual is -beta int u_D phi, its matrix beta int phi phi)
+    ip, ix, dat, res_bc = ref_assembly.assemble(
+        space, [("bc_form", ref_h1_multi.le_taylor_hood_bc_dirichlet, {"u": u_ex}, len(u_sp.bc_element_ids))])
+    A_bc = sp.csr_matrix((dat, ix, ip), shape=(space.n_dof, space.n_dof))
+    assert np.abs(A_bc @ exact + res_bc).max() < 1e-12 * np.abs(res_bc).max()
