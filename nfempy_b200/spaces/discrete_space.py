@@ -243,7 +243,27 @@ class DiscreteSpace:
         return self.mesh.node_tags_of(self.dimension - 1)[self.bc_element_ids - self.mesh.offset[self.dimension - 1]]
 
     def destination_table(self):
-        return self.dof_map._dest_cache()
+        """``int64[n_elements, n_loc_field]``.  Continuous cubic Lagrange fields: the two interior dofs of an edge the
+        reference finds mis-oriented are listed in exchanged order.  The reference exchanges the two basis functions instead
+        (``permute_and_transform`` with ``transformations["interval"][0] = [[0, 1], [1, 0]]``,
+        R/src/basis/permute_and_transform.py:22-35, 110-140: P_3 is the first Lagrange degree whose dof transformations
+        are not the identity); scattering the untransformed local matrix through the exchanged destinations gives the same
+        global system, and the kernels keep one reference table for every cell."""
+        if not hasattr(self, "_dest_oriented"):
+            dest = self.dof_map._dest_cache()
+            if self.family == "Lagrange" and self.k_order == 3 and not self.discontinuous and self.dimension >= 2:
+                from ..basis.orientation import edge_signs
+
+                signs = edge_signs(self.mesh, self.dimension, self.mesh_topology.selected_local)  # [n, n_edges]
+                nc, first = int(self.n_comp), (self.dimension + 1) * int(self.n_comp)
+                dest = dest.copy()
+                for e in range(signs.shape[1]):
+                    rows = np.flatnonzero(signs[:, e] < 0)
+                    a = first + 2 * nc * e
+                    block = dest[rows, a : a + 2 * nc].copy()
+                    dest[rows, a : a + nc], dest[rows, a + nc : a + 2 * nc] = block[:, nc:], block[:, :nc]
+            self._dest_oriented = dest
+        return self._dest_oriented
 
     def bc_destination_table(self):
         if not hasattr(self, "_bc_dest"):

@@ -253,6 +253,9 @@ def entity_dofs(family, dim, k):
     return _element(family, dim, k)[2]
 
 
+SUB_EDGES = {2: ((1, 2), (0, 2), (0, 1)), 3: ((2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1))}
+
+
 def _perm_matrix(image):
     """``P[image[j], j] = 1``: node j goes to node image[j]."""
     P = np.zeros((len(image), len(image)))
@@ -282,7 +285,22 @@ def permute_and_transform(tab, element):
     """``element``: oracle RefElement (``.cell``, ``.mesh``, ``.family``, ``.k``, ``.disc``)."""
     cell, mesh = element.cell, element.mesh
     dim = cell.dimension
-    if element.disc or element.family == "Lagrange" or dim < 2:
+    if element.disc or dim < 2:
+        return tab
+    if element.family == "Lagrange":
+        # P_3 is the first Lagrange degree whose dof transformations are not the identity: the two interior nodes of a
+        # mis-oriented edge are exchanged (transformations["interval"][0] = [[0, 1], [1, 0]]); the single face node needs
+        # nothing.  Edge rule: R/src/basis/permute_and_transform.py:8-19 (2-D), :38-54 (3-D)
+        if element.k != 3:
+            return tab
+        for i, (a, b) in enumerate(SUB_EDGES[dim]):
+            edge = cell.node_tags[[a, b]]
+            v_edge = mesh.cells[cell.sub_cells_ids[1][i]].node_tags
+            oriented = np.all(edge == v_edge) if dim == 2 else np.all(edge == np.sort(v_edge))
+            if oriented:
+                continue
+            d0 = dim + 1 + 2 * i
+            tab[:, :, [d0, d0 + 1], :] = tab[:, :, [d0 + 1, d0], :]
         return tab
     T = entity_transformations(element.family, dim, element.k)
     edofs = entity_dofs(element.family, dim, element.k)

@@ -118,3 +118,56 @@ def test_empty_physical_tag_selects_no_cells():
     ps.build_structures({"u": []}, {})
     assert ps.n_dof == 0 and len(ps.discrete_spaces["u"].elements) == 0
     assert ps.destination_table().shape[0] == 0
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_continuous_cubic_lagrange_is_conforming_and_matches_the_oracle(dim):
+    """P_3 is the first Lagrange degree with non-identity dof transformations (two interior nodes per edge).  The product
+    lists the two dofs of a mis-oriented edge in exchanged order and keeps one reference table; the oracle, like the
+    reference, exchanges the two basis functions.  (a) With the product's tables the global functions are single-valued
+    along every shared edge; (b) cell by cell, the function the product attaches to a global dof is the function the
+    oracle attaches to it."""
+    from nfempy_b200.basis.reference_element import REF_VERTICES, SUB_ENTITIES
+    from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
+    from oracle.ref_forms import RefElement
+    from oracle.ref_mesh import RefMesh
+    from oracle.ref_spaces import RefProductSpace
+
+    mesh = square_tri_mesh(3, jitter=0.2) if dim == 2 else box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True)
+    space = ProductSpace({"f": (dim, 1, "Lagrange", 3, mesh)})
+    space.build_structures({"f": [1]}, {})
+    fs = space.discrete_spaces["f"]
+    dest = np.asarray(space.destination_table())
+    raw = np.asarray(fs.dof_map._dest_cache())
+    assert (dest != raw).any() and np.array_equal(np.sort(dest, axis=1), np.sort(raw, axis=1))
+    cn, ref, verts = fs.cell_nodes(), fs.ref_element, REF_VERTICES[dim]
+    seen, shared = {}, 0
+    for i in range(len(cn)):
+        for a, b in SUB_ENTITIES[dim][1]:
+            ga, gb = int(cn[i][a]), int(cn[i][b])
+            lo, hi = (a, b) if ga < gb else (b, a)
+            for t in (0.3, 0.6):
+                vals = ref.tabulate(0, (verts[lo] + t * (verts[hi] - verts[lo]))[None, :])[0, 0, :, 0]
+                for j, d in enumerate(dest[i]):
+                    key = (int(d), min(ga, gb), max(ga, gb), t)
+                    if key in seen:
+                        shared += 1
+                        assert abs(seen[key] - vals[j]) < 1e-12
+                    else:
+                        seen[key] = vals[j]
+    assert shared > 50
+    r = RefMesh(dim, mesh.points, mesh._blocks)
+    r.build_conformal_mesh()
+    rs = RefProductSpace({"f": (dim, 1, "Lagrange", 3, r)})
+    rs.build_structures({"f": [1]}, {})
+    rf = rs.discrete_spaces["f"]
+    pts, _ = space.quadrature[dim]
+    tab_p = ref.tabulate(0, pts)[0, :, :, 0]
+    for i in range(len(cn)):
+        el = RefElement(rf, rf.element_ids[i])
+        x, jac, det_jac, inv_jac = el.evaluate_mapping(pts)
+        tab_o = el.evaluate_basis(pts, jac, det_jac, inv_jac)[0, :, :, 0]
+        d_o = list(rs.destination_indexes(i))
+        assert sorted(d_o) == sorted(dest[i].tolist())
+        for j, d in enumerate(dest[i]):
+            assert np.abs(tab_p[:, j] - tab_o[:, d_o.index(int(d))]).max() < 1e-12
