@@ -266,8 +266,24 @@ class DiscreteSpace:
         return self._dest_oriented
 
     def bc_destination_table(self):
+        """``int64[n_bc_elements, n_loc_facet]``.  Continuous cubic Lagrange fields on tetrahedra: the boundary triangle's
+        own nodal table lists the two interior nodes of its local edge (a, b) from a to b, the volume side orders the
+        edge's two dofs along ascending vertex tags (``destination_table``), so the pair is exchanged where
+        ``tag[a] > tag[b]``.  (On triangles the facet IS the edge and both sides follow the edge cell's own vertex order.)"""
         if not hasattr(self, "_bc_dest"):
-            self._bc_dest = self.dof_map.bc_destination_table(self.bc_element_ids)
+            dest = self.dof_map.bc_destination_table(self.bc_element_ids)
+            if self.family == "Lagrange" and self.k_order == 3 and not self.discontinuous and self.dimension == 3 and len(dest):
+                from ..basis.reference_element import SUB_ENTITIES
+
+                tags = self.bc_cell_nodes()
+                nc = int(self.n_comp)
+                dest = dest.copy()
+                for e, (a, b) in enumerate(SUB_ENTITIES[2][1]):
+                    rows = np.flatnonzero(tags[:, a] > tags[:, b])
+                    c0 = (3 + 2 * e) * nc
+                    block = dest[rows, c0 : c0 + 2 * nc].copy()
+                    dest[rows, c0 : c0 + nc], dest[rows, c0 + nc : c0 + 2 * nc] = block[:, nc:], block[:, :nc]
+            self._bc_dest = dest
         return self._bc_dest
 
 

@@ -171,3 +171,31 @@ def test_continuous_cubic_lagrange_is_conforming_and_matches_the_oracle(dim):
         assert sorted(d_o) == sorted(dest[i].tolist())
         for j, d in enumerate(dest[i]):
             assert np.abs(tab_p[:, j] - tab_o[:, d_o.index(int(d))]).max() < 1e-12
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_cubic_lagrange_boundary_elements_see_the_dofs_where_the_cells_do(dim):
+    """Every global dof of a continuous P_3 field sits at one physical node, whether it is reached through a cell's
+    destination row and the cell's reference nodes or through a boundary element's destination row and the facet's
+    reference nodes (Dirichlet penalty forms integrate the facet's own nodal basis against those dofs)."""
+    from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
+
+    mesh = square_tri_mesh(3, jitter=0.2) if dim == 2 else box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True)
+    space = ProductSpace({"f": (dim, 2, "Lagrange", 3, mesh)})
+    space.build_structures({"f": [1]}, {"f": [2, 3, 4, 5] if dim == 2 else [2, 3, 4, 5, 6, 7]})
+    fs = space.discrete_spaces["f"]
+
+    def positions(ref_nodes, cell_nodes):
+        lam = np.concatenate([1.0 - ref_nodes.sum(axis=1, keepdims=True), ref_nodes], axis=1)
+        return np.repeat(np.einsum("jv,nvc->njc", lam, mesh.points[cell_nodes]), 2, axis=1)  # two components per node
+
+    where = {}
+    dest = np.asarray(space.destination_table())
+    for row, X in zip(dest, positions(fs.ref_element.nodes, fs.cell_nodes())):
+        for d, x in zip(row, X):
+            assert np.abs(where.setdefault(int(d), x) - x).max() < 1e-12
+    bdest = np.asarray(space.bc_destination_table())
+    assert len(bdest) > 10
+    for row, X in zip(bdest, positions(fs.bc_ref_element.nodes, fs.bc_cell_nodes())):
+        for d, x in zip(row, X):
+            assert np.abs(where[int(d)] - x).max() < 1e-12
