@@ -501,3 +501,56 @@ def test_taylor_hood_oracle_reproduces_a_linear_displacement():
         space, [("bc_form", ref_h1_multi.le_taylor_hood_bc_dirichlet, {"u": u_ex}, len(u_sp.bc_element_ids))])
     A_bc = sp.csr_matrix((dat, ix, ip), shape=(space.n_dof, space.n_dof))
     assert np.abs(A_bc @ exact + res_bc).max() < 1e-12 * np.abs(res_bc).max()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_primal_cosserat_oracle_balances_a_linear_displacement_with_its_rotation(dim):
+    """Known answer for the primal Cosserat oracle (fields u, t): for a linear displacement with ANY gradient G and the
+    constant micro-rotation that cancels its skew part (Theta(t) = -skew G in the oracle's convention
+    e = grad u + Theta(t)) the strain is symmetric, the stress 2 mu sym(G) + lambda tr(G) I is constant and symmetric,
+    the couple stress vanishes -- so with zero loads every interior equation holds for the nodal interpolant.  A sign
+    error between the rotation's entry into the strain and the stress' skew part entering the rotation equation would
+    leave a residual proportional to kappa."""
+    from oracle import ref_assembly, ref_h1_multi
+    from oracle.ref_basis import SUB
+    from tests.parity_helpers import lce_primal_case
+
+    G = np.array([[0.3, -0.2, 0.5], [0.7, 0.1, -0.4], [-0.6, 0.25, 0.2]])[:dim, :dim]
+    b = np.array([0.1, -0.3, 0.2])[:dim]
+    if dim == 2:
+        t_ex = np.array([0.5 * (G[0, 1] - G[1, 0])])
+    else:
+        t_ex = np.array([0.5 * (G[1, 2] - G[2, 1]), 0.5 * (G[2, 0] - G[0, 2]), 0.5 * (G[0, 1] - G[1, 0])])
+    nt = len(t_ex)
+    u_ex = lambda X: G @ X[:dim] + b
+    functions = {"lambda": lambda x, y, z: 3.0, "mu": lambda x, y, z: 0.5, "kappa": lambda x, y, z: 0.35, "gamma": lambda x, y, z: 2.0,
+                 "rhs": lambda x, y, z: np.zeros((dim + nt,) + np.shape(x))}
+    case = lce_primal_case(dim=dim, k=2, kt=1, n=3 if dim == 2 else 2)
+    space = case.ref_space()
+    u_sp = space.discrete_spaces["u"]
+    mesh = u_sp.mesh
+    n_v, edges = dim + 1, SUB[dim][1]
+    exact = np.zeros(space.n_dof)
+    for i in range(len(u_sp.element_ids)):
+        X = mesh.points[mesh.cells[u_sp.element_ids[i]].node_tags]
+        dest = space.destination_indexes(i)
+        nodes = [X[v] for v in range(n_v)] + [0.5 * (X[a] + X[c]) for a, c in edges]
+        for j, xn in enumerate(nodes):
+            exact[dest[dim * j : dim * j + dim]] = u_ex(xn)
+        off = dim * len(nodes)
+        for v in range(n_v):
+            exact[dest[off + nt * v : off + nt * v + nt]] = t_ex
+    _, _, data, res = ref_assembly.assemble(space, [("form", ref_h1_multi.lce_primal, functions, len(u_sp.element_ids))], exact)
+    boundary = np.zeros(space.n_dof, dtype=bool)
+    for i in range(len(u_sp.bc_element_ids)):
+        boundary[space.bc_destination_indexes(i)] = True
+    scale = np.abs(data).max() * max(1.0, np.abs(exact).max())
+    assert (~boundary).sum() > 20 and np.abs(res[~boundary]).max() < 1e-12 * scale
+    # the test has teeth: with the opposite rotation the rotation equations are violated at order kappa
+    wrong = exact.copy()
+    for i in range(len(u_sp.element_ids)):
+        dest = space.destination_indexes(i)
+        off = dim * (n_v + len(edges))
+        wrong[dest[off:]] = -np.tile(t_ex, n_v)
+    _, _, _, res_w = ref_assembly.assemble(space, [("form", ref_h1_multi.lce_primal, functions, len(u_sp.element_ids))], wrong)
+    assert np.abs(res_w[~boundary]).max() > 1e-4 * scale
