@@ -313,12 +313,13 @@ def test_oracle_mixed_elasticity_reproduces_a_constant_stress(dim, k):
 
 @pytest.mark.parametrize("kind", ["lce", "lce_scaled"])
 @pytest.mark.parametrize("dim", [2, 3])
-def test_oracle_mixed_cosserat_reproduces_a_symmetric_constant_stress(kind, dim):
-    """Known answer for the mixed Cosserat oracles (BASELINE config 4's forms): a linear displacement with SYMMETRIC
-    gradient and zero micro-rotation gives the constant symmetric stress 2 mu_s G + lambda_s tr(G) I (the coupling modulus
-    kappa_s only acts on the skew part) and zero couple stress; both lie in the discrete spaces with zero divergence,
-    the angular balance holds because the stress is symmetric, so the discrete solution is exact -- for the plain and for
-    the length-scaled formulation (variable length scale l(x))."""
+def test_oracle_mixed_cosserat_reproduces_a_constant_stress(kind, dim):
+    """Known answer for the mixed Cosserat oracles (BASELINE config 4's forms): a linear displacement with ANY gradient G
+    and the constant micro-rotation that cancels its skew part (the convention of the primal oracle, Theta(t) = -skew G)
+    give the constant symmetric stress 2 mu_s sym(G) + lambda_s tr(G) I and zero couple stress; both lie in the discrete
+    spaces with zero divergence and the angular balance holds, so the discrete solution is exact -- for the plain and the
+    length-scaled formulation (variable length scale l(x)).  With the opposite rotation the stress is off by O(1): the
+    asymmetry coupling, the boundary term of the rotation and the primal oracle's convention are tied together."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spl
 
@@ -328,10 +329,12 @@ def test_oracle_mixed_cosserat_reproduces_a_symmetric_constant_stress(kind, dim)
     from tests.parity_helpers import tensor_mixed_case
 
     lam, mu = 1.5, 0.75
-    G = np.array([[0.3, -0.2, 0.5], [-0.2, 0.1, -0.4], [0.5, -0.4, 0.2]])[:dim, :dim]
+    G = np.array([[0.3, -0.2, 0.5], [0.7, 0.1, -0.4], [-0.6, 0.25, 0.2]])[:dim, :dim]
     b = np.array([0.1, -0.3, 0.2])[:dim]
-    sigma = 2.0 * mu * G + lam * np.trace(G) * np.eye(dim)
-    tc = 3 if dim == 3 else 1
+    sigma = mu * (G + G.T) + lam * np.trace(G) * np.eye(dim)
+    t_ex = np.array([0.5 * (G[0, 1] - G[1, 0])]) if dim == 2 else \
+        np.array([0.5 * (G[1, 2] - G[2, 1]), 0.5 * (G[2, 0] - G[0, 2]), 0.5 * (G[0, 1] - G[1, 0])])
+    tc = len(t_ex)
     one = lambda x: np.ones_like(x)
     functions = {
         "rhs": lambda x, y, z: np.zeros((dim + tc,) + np.shape(x)),
@@ -339,33 +342,41 @@ def test_oracle_mixed_cosserat_reproduces_a_symmetric_constant_stress(kind, dim)
         "lambda_o": lambda x, y, z: 0.7 * one(x), "mu_o": lambda x, y, z: 1.3 * one(x), "kappa_o": lambda x, y, z: 0.4 * one(x),
         "l": lambda x, y, z: 0.5 + 0.25 * x + 0.1 * y * y, "grad_l": lambda x, y, z: np.array([0.25 * one(x), 0.2 * y, 0.0 * x]),
     }
-    bc_functions = {
-        "u": lambda x, y, z: np.array([sum(G[r, c] * (x, y, z)[c] for c in range(dim)) + b[r] for r in range(dim)]),
-        "t": lambda x, y, z: np.zeros((tc,) + np.shape(x)), "l": functions["l"], "grad_l": functions["grad_l"],
-    }
     case = tensor_mixed_case(kind=kind, dim=dim, s_family="BDM", m_family="RT", k=1, n=2)
     space = case.ref_space()
     s_sp, m_sp = space.discrete_spaces["s"], space.discrete_spaces["m"]
     vol, bc = (rt.lce_dual, rt.lce_dual_bc_dirichlet) if kind == "lce" else (rt.lce_scaled_dual, rt.lce_scaled_dual_bc_dirichlet)
-    forms = [("form", vol, functions, len(s_sp.element_ids)), ("bc_form", bc, bc_functions, len(s_sp.bc_element_ids))]
-    indptr, indices, data, res = ref_assembly.assemble(space, forms)
-    A = sp.csr_matrix((data, indices, indptr)).tocsc()
-    sol = spl.spsolve(A, -res)
-    assert np.abs(A @ sol + res).max() < 1e-10 * max(1.0, np.abs(res).max())
     pts = np.array([[0.2, 0.3, 0.1][:dim], [0.55, 0.15, 0.2][:dim]])
     mc = m_sp.n_comp
-    for i in range(len(s_sp.element_ids)):
-        el_s, el_m = RefElement(s_sp, s_sp.element_ids[i]), RefElement(m_sp, m_sp.element_ids[i])
-        x, jac, det_jac, inv_jac = el_s.evaluate_mapping(pts)
-        tab_s = el_s.evaluate_basis(pts, jac, det_jac, inv_jac)
-        tab_m = el_m.evaluate_basis(pts, jac, det_jac, inv_jac)
-        dest = space.destination_indexes(i)
-        ns, nm = tab_s.shape[2], tab_m.shape[2]
-        cs = sol[dest[: ns * dim]].reshape(ns, dim)
-        cm = sol[dest[ns * dim : ns * dim + nm * mc]].reshape(nm, mc)
-        for q in range(len(pts)):
-            assert np.abs(cs.T @ tab_s[0, q, :, :dim] - sigma).max() < 1e-9 * np.abs(sigma).max()
-            assert np.abs(cm.T @ tab_m[0, q, :, :dim]).max() < 1e-9 * np.abs(sigma).max()
+
+    def worst(sign):
+        bc_functions = {
+            "u": lambda x, y, z: np.array([sum(G[r, c] * (x, y, z)[c] for c in range(dim)) + b[r] for r in range(dim)]),
+            "t": lambda x, y, z: np.array([sign * t_ex[c] * one(x) for c in range(tc)]), "l": functions["l"], "grad_l": functions["grad_l"],
+        }
+        forms = [("form", vol, functions, len(s_sp.element_ids)), ("bc_form", bc, bc_functions, len(s_sp.bc_element_ids))]
+        indptr, indices, data, res = ref_assembly.assemble(space, forms)
+        A = sp.csr_matrix((data, indices, indptr)).tocsc()
+        sol = spl.spsolve(A, -res)
+        assert np.abs(A @ sol + res).max() < 1e-10 * max(1.0, np.abs(res).max())
+        err_s = err_m = 0.0
+        for i in range(len(s_sp.element_ids)):
+            el_s, el_m = RefElement(s_sp, s_sp.element_ids[i]), RefElement(m_sp, m_sp.element_ids[i])
+            x, jac, det_jac, inv_jac = el_s.evaluate_mapping(pts)
+            tab_s = el_s.evaluate_basis(pts, jac, det_jac, inv_jac)
+            tab_m = el_m.evaluate_basis(pts, jac, det_jac, inv_jac)
+            dest = space.destination_indexes(i)
+            ns, nm = tab_s.shape[2], tab_m.shape[2]
+            cs = sol[dest[: ns * dim]].reshape(ns, dim)
+            cm = sol[dest[ns * dim : ns * dim + nm * mc]].reshape(nm, mc)
+            for q in range(len(pts)):
+                err_s = max(err_s, np.abs(cs.T @ tab_s[0, q, :, :dim] - sigma).max())
+                err_m = max(err_m, np.abs(cm.T @ tab_m[0, q, :, :dim]).max())
+        return err_s, err_m
+
+    err_s, err_m = worst(1.0)
+    assert err_s < 1e-9 * np.abs(sigma).max() and err_m < 1e-9 * np.abs(sigma).max()
+    assert worst(-1.0)[0] > 1e-2 * np.abs(sigma).max()
 
 
 @pytest.mark.parametrize("kind", ["degenerate", "unscaled"])
