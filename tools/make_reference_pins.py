@@ -1,0 +1,205 @@
+#!/usr/bin/env python
+"""Runs the REFERENCE'S OWN SOURCE (/root/reference/src) on the parity cases of tests/parity_helpers.py and commits what it
+produced as fixtures ``tests/golden/refcode_<case>.npz``.  Works only in the build container (/root/reference is not on the
+GPU box); the fixtures travel.
+
+    python tools/make_reference_pins.py            # all cases
+    python tools/make_reference_pins.py le_p2_3d   # some
+
+What runs is the reference's ``Mesh.build_conformal_mesh`` (mesh.py:239-339), ``MeshTopology``, ``DoFMap``,
+``DiscreteSpace`` / ``ProductSpace.build_structures`` and ``destination_indexes``, ``FiniteElement.evaluate_mapping /
+evaluate_basis`` with ``permute_and_transform`` and ``transform_lower_to_higher``, each weak form's ``evaluate_form`` and
+``SequentialAssembler.scatter_forms`` (ScatterFormData.py:5-56) -- line for line, unmodified, imported from where it lies.
+What does NOT run is the third-party code underneath, absent in this image: meshio, basix, auto_diff (and PETSc's Mat,
+replaced by a dict of keys with ADD_VALUES).  tools/ref_shims/ holds the stand-ins and says what each answers with; the
+basix stand-in answers with the oracle's element tables, so these fixtures pin every restated line ABOVE the basix boundary
+(numbering, dof maps, geometry map, orientation handling, trace maps, the forms, the scatter) and leave basix's own
+conventions unpinned.
+
+Each fixture: ``indptr, indices, data, rhs`` of the assembled system, ``dest`` / ``bc_dest`` (every cell's and boundary
+cell's destination indexes, ragged rows padded with -1), and the mesh numbering (``cell_dim, cell_material, node_tags,
+sub_cells`` per cell id) the reference's ``Mesh`` built."""
+import importlib
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference/src"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools", "ref_shims"))
+sys.path.insert(0, REFERENCE)
+
+import meshio  # noqa: E402  (the stand-in)
+
+from tests import parity_helpers as ph  # noqa: E402
+
+# oracle restatement -> the reference class it restates
+REF_CLASS = {
+    "le_primal": ("le_primal_weak_form", "LEPrimalWeakForm"),
+    "le_primal_bc_dirichlet": ("le_primal_weak_form", "LEPrimalWeakFormBCDirichlet"),
+    "le_primal_bc_neumann": ("le_primal_weak_form", "LEPrimalWeakFormBCNeumann"),
+    "le_primal_bc_normal_dirichlet": ("le_primal_weak_form", "LEPrimalWeakFormBCNormalDirichlet"),
+    "laplace_dual": ("laplace_dual_weak_form", "LaplaceDualWeakForm"),
+    "laplace_dual_bc_dirichlet": ("laplace_dual_weak_form", "LaplaceDualWeakFormBCDirichlet"),
+    "l2_projector": ("l2_projector_weak_form", "L2ProjectorWeakForm"),
+    "degenerate_elliptic": ("degenerate_elliptic_weak_form", "DegenerateEllipticWeakForm"),
+    "degenerate_elliptic_bc_dirichlet": ("degenerate_elliptic_weak_form", "DegenerateEllipticWeakFormBCDirichlet"),
+    "unscaled_elliptic": ("unscaled_elliptic_weak_form", "UnscaledEllipticWeakForm"),
+    "unscaled_elliptic_bc_dirichlet": ("unscaled_elliptic_weak_form", "UnscaledEllipticWeakFormBCDirichlet"),
+    "le_dual": ("le_dual_weak_form", "LEDualWeakForm"),
+    "le_dual_bc_dirichlet": ("le_dual_weak_form", "LEDualWeakFormBCDirichlet"),
+    "lce_dual": ("lce_dual_weak_form", "LCEDualWeakForm"),
+    "lce_dual_bc_dirichlet": ("lce_dual_weak_form", "LCEDualWeakFormBCDirichlet"),
+    "lce_scaled_dual": ("lce_scaled_dual_weak_form", "LCEScaledDualWeakForm"),
+    "lce_scaled_dual_bc_dirichlet": ("lce_scaled_dual_weak_form", "LCEScaledDualWeakFormBCDirichlet"),
+    "le_riesz_map": ("le_riesz_map_weak_form", "LERieszMapWeakForm"),
+    "lce_riesz_map": ("lce_riesz_map_weak_form", "LCERieszMapWeakForm"),
+    "lce_scaled_riesz_map": ("lce_scaled_riesz_map_weak_form", "LCEScaledRieszMapWeakForm"),
+    "lce_primal": ("lce_primal_weak_form", "LCEPrimalWeakForm"),
+    "lce_primal_bc_dirichlet": ("lce_primal_weak_form", "LCEPrimalWeakFormBCDirichlet"),
+    "le_taylor_hood": ("le_taylor_hood_weak_form", "LETaylorHoodWeakForm"),
+    "le_taylor_hood_bc_dirichlet": ("le_taylor_hood_weak_form", "LETaylorHoodWeakFormBCDirichlet"),
+    "le_stress_constraint": ("le_primal_stress_constraint_weak_form", "LEPrimalStressConstraintWeakForm"),
+}
+
+
+class DictMat:
+    """PETSc ``Mat`` stand-in for ``jac_g.setValue(row=, col=, value=, addv=True)`` (ScatterFormData.py:11)."""
+
+    def __init__(self, n):
+        self.n, self.entries = n, {}
+
+    def setValue(self, row, col, value, addv=True):
+        key = (int(row), int(col))
+        self.entries[key] = (self.entries.get(key, 0.0) + float(value)) if addv else float(value)
+
+    def csr(self):
+        keys = sorted(self.entries)
+        rows = np.array([k[0] for k in keys], dtype=np.int64)
+        indices = np.array([k[1] for k in keys], dtype=np.int64)
+        data = np.array([self.entries[k] for k in keys])
+        indptr = np.zeros(self.n + 1, dtype=np.int64)
+        np.add.at(indptr, rows + 1, 1)
+        return np.cumsum(indptr), indices, data
+
+
+def fixture_mesh_case(maker, dim, level=0):
+    return lambda: maker(mesh=ph.fixture_mesh(dim, level)) if hasattr(ph, "fixture_mesh") else None
+
+
+def cases():
+    """name -> zero-argument function returning a tests.parity_helpers.Case (the same constructors the GPU parity tests
+    use, so product, oracle and reference code see the same mesh, spaces, coefficient functions and form lists)."""
+    out = {
+        "le_p2_3d": lambda: ph.elasticity_case(n=2, with_bc=True, k=2),
+        "le_p2_3d_varying_alpha": lambda: ph.elasticity_case(n=1, with_bc=True, varying=True, alpha=True, k=2),
+        "le_p1_2d_neumann": lambda: ph.elasticity_case(n=3, with_bc=True, k=1, dim=2, neumann=True),
+        "le_p2_3d_normal": lambda: ph.elasticity_case(n=1, with_bc=True, k=2, normal_bc=True),
+        "poisson_rt1_3d": lambda: ph.mixed_poisson_case(dim=3, k=1, n=2),
+        "poisson_rt2_3d": lambda: ph.mixed_poisson_case(dim=3, k=2, n=1, varying=True),
+        "poisson_rt3_2d": lambda: ph.mixed_poisson_case(dim=2, k=3, n=2),
+        "poisson_bdm2_3d": lambda: ph.mixed_poisson_case(dim=3, k=2, n=1, family="BDM"),
+        "poisson_bdm3_3d": lambda: ph.mixed_poisson_case(dim=3, k=3, n=1, family="BDM"),
+    }
+    return out
+
+
+def reference_system(case, verbose=True):
+    from assembly.SequentialAssembler import SequentialAssembler
+    from mesh.mesh import Mesh
+    from spaces.product_space import ProductSpace
+
+    name = "memory://%d" % id(case)
+    meshio.register(name, case.mesh.points, case.mesh._blocks)
+    gmesh = Mesh(dimension=case.mesh.dimension, file_name=name)
+    gmesh.build_conformal_mesh()
+    data = case.data_fn(gmesh)
+    space = ProductSpace(data)
+    space.make_subspaces_discontinuous({k: bool(case.disc.get(k, False)) for k in data})
+    space.build_structures(case.tags, case.btags)
+    n = space.n_dof
+    alpha = np.zeros(n) if case.alpha_fn is None else case.alpha_fn(n)
+    oracle_space = case.ref_space()  # only for the form list (functions, counts) of the case
+    assert oracle_space.n_dof == n, (oracle_space.n_dof, n)
+    jac, res = DictMat(n), np.zeros(n)
+    assembler = SequentialAssembler(space, jac, res)
+    form_list = {}
+    for j, (kind, oracle_fn, functions, n_items) in enumerate(case.ref_forms_fn(oracle_space)):
+        module, cls = REF_CLASS[oracle_fn.__name__]
+        form = getattr(importlib.import_module("weak_forms." + module), cls)(space)
+        form.functions = functions
+        sequence = range(n_items) if isinstance(n_items, int) else list(n_items)
+        form_list["f%d" % j] = [kind, sequence, form, alpha]
+    assembler.form_to_input_list = form_list
+    assembler.scatter_forms(measure_time_q=False)
+    indptr, indices, values = jac.csr()
+    # destination tables of every cell / boundary cell (all fields concatenated, as the scatter sees them)
+    first = next(iter(space.discrete_spaces.values()))
+    dest = [np.asarray(space.destination_indexes(i)) for i in range(len(first.elements))]
+    bc_dest = [np.asarray(space.bc_destination_indexes(i)) for i in range(len(first.bc_elements))] if case.btags and any(case.btags.values()) else []
+    return dict(indptr=indptr, indices=indices, data=values, rhs=res, dest=_ragged(dest), bc_dest=_ragged(bc_dest),
+                **mesh_numbering(gmesh))
+
+
+def _ragged(rows):
+    if not rows:
+        return np.zeros((0, 0), dtype=np.int64)
+    width = max(len(r) for r in rows)
+    out = np.full((len(rows), width), -1, dtype=np.int64)
+    for i, r in enumerate(rows):
+        out[i, : len(r)] = r
+    return out
+
+
+def mesh_numbering(gmesh):
+    """The reference Mesh's cells as arrays: dimension, material id (-1 = None), node tags and sub-cell ids of every
+    dimension (padded with -1), indexed by cell id."""
+    cells = gmesh.cells
+    n = len(cells)
+    cell_dim = np.array([c.dimension for c in cells], dtype=np.int64)
+    material = np.array([-1 if c.material_id is None else int(c.material_id) for c in cells], dtype=np.int64)
+    node_tags = _ragged([np.asarray(c.node_tags) for c in cells])
+    sub = np.full((n, 4, 6), -1, dtype=np.int64)
+    for i, c in enumerate(cells):
+        assert c.id == i
+        for d in range(c.dimension + 1):
+            ids = np.asarray(c.sub_cells_ids[d])
+            sub[i, d, : len(ids)] = ids
+    return dict(cell_dim=cell_dim, cell_material=material, node_tags=node_tags, sub_cells=sub)
+
+
+def compare_with_oracle(case, got):
+    want = case.run_oracle()
+    same_pattern = np.array_equal(want[0], got["indptr"]) and np.array_equal(want[1], got["indices"])
+    if not same_pattern:
+        return {"pattern_equal": False}
+    scale = max(np.abs(want[2]).max(), 1e-300)
+    rscale = max(np.abs(want[3]).max(), 1e-300)
+    return {"pattern_equal": True, "max_rel_values": float(np.abs(want[2] - got["data"]).max() / scale),
+            "max_rel_rhs": float(np.abs(want[3] - got["rhs"]).max() / rscale)}
+
+
+def main():
+    wanted = sys.argv[1:]
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for name, make in cases().items():
+        if wanted and name not in wanted:
+            continue
+        t0 = time.perf_counter()
+        import contextlib
+        import io
+
+        case = make()
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints timing lines while it builds spaces
+            got = reference_system(case)
+        report = compare_with_oracle(case, got)
+        np.savez_compressed(os.path.join(out_dir, "refcode_%s.npz" % name), **got)
+        print("%-28s n_dof %6d nnz %8d  vs oracle: %s  (%.1f s)" % (name, len(got["rhs"]), len(got["data"]), report,
+                                                                   time.perf_counter() - t0), flush=True)
+
+
+if __name__ == "__main__":
+    main()
