@@ -1,0 +1,89 @@
+"""The oracle (and the product's host layer) against fixtures produced by the REFERENCE'S OWN SOURCE.
+
+``tests/golden/refcode_<case>.npz`` were written by ``tools/make_reference_pins.py``, which imports /root/reference/src
+unmodified -- ``Mesh.build_conformal_mesh``, ``DoFMap``, ``DiscreteSpace`` / ``ProductSpace``, ``FiniteElement``,
+``permute_and_transform``, ``transform_lower_to_higher``, the weak forms' ``evaluate_form`` (quadrature loop + forward AD) or
+``evaluate_form_vectorized``, ``SequentialAssembler.scatter_forms`` -- over stand-ins for the third-party packages this
+image lacks (``tools/ref_shims``: meshio, basix, auto_diff).  They pin every restated line ABOVE the basix boundary; basix's
+own element conventions stay unpinned (the stand-in answers with the oracle's tables).  Lagrange P1 / P2 bases are unique,
+so for configs 1-2 nothing is left unpinned but summation order."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.parity_helpers import compare_csr
+from tests.refcode_cases import cases
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = cases()
+SKIP_ORACLE = set()
+
+
+def _fixture(name):
+    path = os.path.join(GOLDEN, "refcode_%s.npz" % name)
+    if not os.path.exists(path):
+        pytest.fail("fixture missing: run tools/make_reference_pins.py %s in the build container" % name)
+    return np.load(path)
+
+
+def test_every_case_has_its_fixture_and_nothing_else():
+    have = {f[len("refcode_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("refcode_")}
+    assert have == set(CASES)
+
+
+@pytest.mark.parametrize("name", sorted(set(CASES) - SKIP_ORACLE))
+def test_oracle_assembles_what_the_reference_code_assembled(name):
+    fx = _fixture(name)
+    case = CASES[name]()
+    got = case.run_oracle()
+    compare_csr(got, (fx["indptr"], fx["indices"], fx["data"], fx["rhs"]), 1e-12)
+
+
+def _rows(table):
+    return [row[row >= 0] for row in table]
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_numbering_and_destination_tables_equal_the_reference_codes(name):
+    """Mesh numbering (cell ids by dimension, node tags, sub-cell ids, material ids) and the destination indexes of every
+    cell and boundary cell: product (vectorised tables) and oracle (dict-based) against the reference's ``Mesh`` /
+    ``DoFMap`` / ``ProductSpace``."""
+    fx = _fixture(name)
+    case = CASES[name]()
+    # --- product mesh
+    space = case.space()
+    mesh = case.mesh
+    n = len(fx["cell_dim"])
+    assert mesh.max_cell_id() == n
+    assert np.array_equal(mesh.cell_dimension(np.arange(n)), fx["cell_dim"])
+    for d in range(mesh.dimension + 1):
+        ids = np.flatnonzero(fx["cell_dim"] == d)
+        assert np.array_equal(mesh.ids_of_dimension(d), ids)
+        assert np.array_equal(mesh.node_tags_of(d), fx["node_tags"][ids, : d + 1])
+        for e in range(d + 1):
+            width = len(mesh.sub_cells_of(d, e)[0])
+            assert np.array_equal(mesh.sub_cells_of(d, e), fx["sub_cells"][ids, e, :width])
+            assert np.all(fx["sub_cells"][ids, e, width:] == -1)
+    for cid in range(0, n, max(1, n // 97)):  # material ids through the cell objects (None <-> -1)
+        material = mesh.cells[cid].material_id
+        assert (-1 if material is None else int(material)) == int(fx["cell_material"][cid])
+    # --- oracle mesh
+    rspace = case.ref_space()
+    rmesh = next(iter(rspace.discrete_spaces.values())).mesh
+    for cid in range(n):
+        cell = rmesh.cells[cid]
+        assert cell.dimension == fx["cell_dim"][cid]
+        assert np.array_equal(cell.node_tags, fx["node_tags"][cid, : cell.dimension + 1])
+        for e in range(cell.dimension + 1):
+            want = fx["sub_cells"][cid, e]
+            assert np.array_equal(cell.sub_cells_ids[e], want[want >= 0])
+    # --- destination tables
+    assert space.n_dof == rspace.n_dof == len(fx["rhs"])
+    dest = _rows(fx["dest"])
+    for i, want in enumerate(dest):
+        assert np.array_equal(space.destination_indexes(i), want)
+        assert np.array_equal(rspace.destination_indexes(i), want)
+    for i, want in enumerate(_rows(fx["bc_dest"])):
+        assert np.array_equal(space.bc_destination_indexes(i), want)
+        assert np.array_equal(rspace.bc_destination_indexes(i), want)

@@ -1,0 +1,34 @@
+"""The CUDA path against fixtures produced by the REFERENCE'S OWN SOURCE (``tests/golden/refcode_*.npz``, written by
+``tools/make_reference_pins.py``: /root/reference/src imported unmodified over stand-ins for meshio / basix / auto_diff;
+see ``tests/test_cpu_reference_pins.py`` for what that pins and what it leaves open).
+
+The cases are form lists the oracle-parity tests of this suite already run (same constructors, same arguments); here the
+expected CSR and right-hand side come from the reference code instead of the oracle.  (The file sorts last on purpose.)"""
+import os
+
+import numpy as np
+import pytest
+
+from tests.parity_helpers import compare_csr
+from tests.refcode_cases import cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+# name -> the oracle-parity test that runs the same case
+SAME_AS = {
+    "le_p2_3d": "test_gpu_parity.py::test_elasticity_p2_3d (BASELINE config 2's form list)",
+    "poisson_rt1_3d": "test_gpu_hdiv.py::test_mixed_poisson_rt_3d[1] (config 3, k = 1; row-owner path)",
+    "poisson_bdm3_3d_varying": "test_gpu_hdiv.py::test_mixed_poisson_bdm[3-3]",
+    "degenerate_rt1_3d": "test_gpu_hdiv.py::test_degenerate_elliptic_family[3-1-degenerate]",
+    "unscaled_rt1_3d": "test_gpu_hdiv.py::test_degenerate_elliptic_family[3-1-unscaled]",
+    "lce_scaled_config4_order_ad": "test_gpu_tensor_forms.py::test_config_4_order_bdm3[lce_scaled-RT] (config 4's order)",
+    "taylor_hood_3d_n3": "test_gpu_h1_multifield.py::test_taylor_hood_2d[True-True]",
+}
+
+
+@pytest.mark.parametrize("name", sorted(SAME_AS))
+def test_cuda_path_assembles_what_the_reference_code_assembled(name):
+    fx = np.load(os.path.join(GOLDEN, "refcode_%s.npz" % name))
+    case = cases()[name]()
+    compare_csr(case.run_gpu(), (fx["indptr"], fx["indices"], fx["data"], fx["rhs"]), 1e-12)

@@ -34,7 +34,8 @@ sys.path.insert(0, REFERENCE)
 
 import meshio  # noqa: E402  (the stand-in)
 
-from tests import parity_helpers as ph  # noqa: E402
+from tests import parity_helpers as ph  # noqa: E402,F401
+from tests.refcode_cases import cases  # noqa: E402
 
 # oracle restatement -> the reference class it restates
 REF_CLASS = {
@@ -63,7 +64,15 @@ REF_CLASS = {
     "le_taylor_hood": ("le_taylor_hood_weak_form", "LETaylorHoodWeakForm"),
     "le_taylor_hood_bc_dirichlet": ("le_taylor_hood_weak_form", "LETaylorHoodWeakFormBCDirichlet"),
     "le_stress_constraint": ("le_primal_stress_constraint_weak_form", "LEPrimalStressConstraintWeakForm"),
+    # (le_dual_weak_form.py's own LCEDualWeakFormBCNeumann, :580-, is stale: it reads a stored mapping its elements no
+    # longer keep -- AttributeError 'MappingData' object has no attribute 'x' -- so the oracle's le_dual_bc_neumann has no
+    # runnable counterpart)
+    "lce_dual_bc_neumann": ("lce_dual_weak_form", "LCEDualWeakFormBCNeumann"),
 }
+
+# forms whose example drivers call ``evaluate_form_vectorized`` from their own scatter closure
+# (R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py:150-243); the oracle restates those bodies
+VECTORIZED = {"le_dual", "lce_dual", "lce_scaled_dual", "le_riesz_map", "lce_riesz_map", "lce_scaled_riesz_map"}
 
 
 class DictMat:
@@ -86,28 +95,7 @@ class DictMat:
         return np.cumsum(indptr), indices, data
 
 
-def fixture_mesh_case(maker, dim, level=0):
-    return lambda: maker(mesh=ph.fixture_mesh(dim, level)) if hasattr(ph, "fixture_mesh") else None
-
-
-def cases():
-    """name -> zero-argument function returning a tests.parity_helpers.Case (the same constructors the GPU parity tests
-    use, so product, oracle and reference code see the same mesh, spaces, coefficient functions and form lists)."""
-    out = {
-        "le_p2_3d": lambda: ph.elasticity_case(n=2, with_bc=True, k=2),
-        "le_p2_3d_varying_alpha": lambda: ph.elasticity_case(n=1, with_bc=True, varying=True, alpha=True, k=2),
-        "le_p1_2d_neumann": lambda: ph.elasticity_case(n=3, with_bc=True, k=1, dim=2, neumann=True),
-        "le_p2_3d_normal": lambda: ph.elasticity_case(n=1, with_bc=True, k=2, normal_bc=True),
-        "poisson_rt1_3d": lambda: ph.mixed_poisson_case(dim=3, k=1, n=2),
-        "poisson_rt2_3d": lambda: ph.mixed_poisson_case(dim=3, k=2, n=1, varying=True),
-        "poisson_rt3_2d": lambda: ph.mixed_poisson_case(dim=2, k=3, n=2),
-        "poisson_bdm2_3d": lambda: ph.mixed_poisson_case(dim=3, k=2, n=1, family="BDM"),
-        "poisson_bdm3_3d": lambda: ph.mixed_poisson_case(dim=3, k=3, n=1, family="BDM"),
-    }
-    return out
-
-
-def reference_system(case, verbose=True):
+def reference_system(case, vectorized=True):
     from assembly.SequentialAssembler import SequentialAssembler
     from mesh.mesh import Mesh
     from spaces.product_space import ProductSpace
@@ -131,6 +119,8 @@ def reference_system(case, verbose=True):
         module, cls = REF_CLASS[oracle_fn.__name__]
         form = getattr(importlib.import_module("weak_forms." + module), cls)(space)
         form.functions = functions
+        if vectorized and oracle_fn.__name__ in VECTORIZED:
+            form.evaluate_form = form.evaluate_form_vectorized
         sequence = range(n_items) if isinstance(n_items, int) else list(n_items)
         form_list["f%d" % j] = [kind, sequence, form, alpha]
     assembler.form_to_input_list = form_list
@@ -193,8 +183,12 @@ def main():
         import io
 
         case = make()
-        with contextlib.redirect_stdout(io.StringIO()):  # the reference prints timing lines while it builds spaces
-            got = reference_system(case)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):  # the reference prints timing lines while it builds spaces
+                got = reference_system(case, vectorized=not name.endswith("_ad"))
+        except Exception as exc:  # keep going: one stale reference class must not hide the others
+            print("%-28s FAILED in the reference code: %s: %s" % (name, type(exc).__name__, exc), flush=True)
+            continue
         report = compare_with_oracle(case, got)
         np.savez_compressed(os.path.join(out_dir, "refcode_%s.npz" % name), **got)
         print("%-28s n_dof %6d nnz %8d  vs oracle: %s  (%.1f s)" % (name, len(got["rhs"]), len(got["data"]), report,

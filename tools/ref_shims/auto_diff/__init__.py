@@ -30,9 +30,35 @@ class AutoDiff:
             val = self._true_zeros(shape, *args, **kwargs)
             return VecValDer(val, self._true_zeros(val.shape + (total,)))
 
-        np.zeros = zeros
+        self._true_array = np.array
+
+        def array(obj, *args, **kwargs):
+            """``np.array([[0.0 * t, -t2, +t1], ...])`` of differentiated scalars / arrays gives a ``VecValDer``."""
+            if not _contains(obj):
+                return self._true_array(obj, *args, **kwargs)
+            return _assemble(obj, total, self._true_zeros)
+
+        np.zeros, np.array = zeros, array
         return out[0] if len(out) == 1 else tuple(out)
 
     def __exit__(self, *exc):
-        np.zeros = self._true_zeros
+        np.zeros, np.array = self._true_zeros, self._true_array
         return False
+
+
+def _contains(obj):
+    if isinstance(obj, VecValDer):
+        return True
+    if isinstance(obj, (list, tuple)):
+        return any(_contains(o) for o in obj)
+    return False
+
+
+def _assemble(obj, total, zeros):
+    if isinstance(obj, VecValDer):
+        return obj
+    if isinstance(obj, (list, tuple)):
+        parts = [_assemble(o, total, zeros) for o in obj]
+        return VecValDer(np.stack([p.val for p in parts]), np.stack([p.der for p in parts]))
+    val = np.asarray(obj, dtype=float)
+    return VecValDer(val, zeros(val.shape + (total,)))

@@ -70,6 +70,9 @@ class VecValDer:
         return VecValDer(self.val.trace(), self.der.trace())
 
     # ---- linear arithmetic -------------------------------------------------------------------------------
+    def __pos__(self):
+        return self
+
     def __neg__(self):
         return VecValDer(-self.val, -self.der)
 
