@@ -38,6 +38,11 @@ def cases():
         "lce_scaled_bdm1_rt1_2d_ad": lambda: ph.tensor_mixed_case(kind="lce_scaled", dim=2, k=1, n=2),
         "lce_scaled_bdm1_rt1_3d_ad": lambda: ph.tensor_mixed_case(kind="lce_scaled", dim=3, k=1, n=1),
         "lce_scaled_config4_order_ad": lambda: ph.tensor_mixed_case(kind="lce_scaled", dim=3, s_family="BDM", m_family="RT", k=3, n=1),
+        # config 5's element and form (two-flux transport, implicit Euler, nonlinear reaction; residual and tangent at a
+        # non-zero iterate through the time-dependent scatter); the k = 2 case takes the two-stage CUDA path
+        "sundus_rt1_3d": lambda: ph.SundusCase(dim=3, k=1, n=2),
+        "sundus_rt1_2d": lambda: ph.SundusCase(dim=2, k=1, n=3),
+        "sundus_rt2_3d": lambda: ph.SundusCase(dim=3, k=2, n=1),
         "lce_primal_3d": lambda: ph.lce_primal_case(dim=3, k=2, n=1, varying=True, alpha=True),
         "lce_primal_2d": lambda: ph.lce_primal_case(dim=2, k=2, n=2),
         "taylor_hood_3d": lambda: ph.taylor_hood_case(n=1, varying=True, alpha=True),

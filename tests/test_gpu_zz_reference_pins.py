@@ -23,6 +23,8 @@ SAME_AS = {
     "degenerate_rt1_3d": "test_gpu_hdiv.py::test_degenerate_elliptic_family[3-1-degenerate]",
     "unscaled_rt1_3d": "test_gpu_hdiv.py::test_degenerate_elliptic_family[3-1-unscaled]",
     "lce_scaled_config4_order_ad": "test_gpu_tensor_forms.py::test_config_4_order_bdm3[lce_scaled-RT] (config 4's order)",
+    "sundus_rt1_3d": "__graft_entry__.smoke() / test_gpu_hdiv.py::test_sundus_time_dependent_forms[3-1] (config 5's element; row-owner path)",
+    "sundus_rt1_2d": "test_gpu_hdiv.py::test_sundus_time_dependent_forms[2-1]",
     "taylor_hood_3d_n3": "test_gpu_h1_multifield.py::test_taylor_hood_2d[True-True]",
 }
 

@@ -134,6 +134,39 @@ def reference_system(case, vectorized=True):
                 **mesh_numbering(gmesh))
 
 
+def reference_system_sundus(case):
+    """Config 5's form classes (example-local: R/examples/parabolic_diffusive_problem/SundusWeakForm.py) through the
+    reference's time-dependent scatter (ScatterFormData.py:28-33, 43-49): residual AND tangent at a non-zero iterate."""
+    sys.path.insert(0, "/root/reference/examples/parabolic_diffusive_problem")
+    from assembly.SequentialAssembler import SequentialAssembler
+    from mesh.mesh import Mesh
+    from spaces.product_space import ProductSpace
+    from SundusWeakForm import SundusDualWeakForm, SundusDualWeakFormBCDirichlet
+
+    name = "memory://%d" % id(case)
+    meshio.register(name, case.mesh.points, case.mesh._blocks)
+    gmesh = Mesh(dimension=case.mesh.dimension, file_name=name)
+    gmesh.build_conformal_mesh()
+    space = case._build(ProductSpace(case._data(gmesh)))  # the case's own calls, on the reference's ProductSpace
+    n = space.n_dof
+    alphas = case.alphas(n)
+    jac, res = DictMat(n), np.zeros(n)
+    wf, bf = SundusDualWeakForm(space), SundusDualWeakFormBCDirichlet(space)
+    wf.functions, bf.functions = case.functions, case.bc_functions
+    mp = space.discrete_spaces["mp"]
+    assembler = SequentialAssembler(space, jac, res)
+    assembler.form_to_input_list = {
+        "volume": ["time_dependent_form", range(len(mp.elements)), wf, alphas, case.t],
+        "bc": ["time_dependent_bc_form", range(len(mp.bc_elements)), bf, alphas, case.t],
+    }
+    assembler.scatter_forms(measure_time_q=False)
+    indptr, indices, values = jac.csr()
+    dest = [np.asarray(space.destination_indexes(i)) for i in range(len(mp.elements))]
+    bc_dest = [np.asarray(space.bc_destination_indexes(i)) for i in range(len(mp.bc_elements))]
+    return dict(indptr=indptr, indices=indices, data=values, rhs=res, dest=_ragged(dest), bc_dest=_ragged(bc_dest),
+                **mesh_numbering(gmesh))
+
+
 def _ragged(rows):
     if not rows:
         return np.zeros((0, 0), dtype=np.int64)
@@ -185,7 +218,10 @@ def main():
         case = make()
         try:
             with contextlib.redirect_stdout(io.StringIO()):  # the reference prints timing lines while it builds spaces
-                got = reference_system(case, vectorized=not name.endswith("_ad"))
+                if isinstance(case, ph.SundusCase):
+                    got = reference_system_sundus(case)
+                else:
+                    got = reference_system(case, vectorized=not name.endswith("_ad"))
         except Exception as exc:  # keep going: one stale reference class must not hide the others
             print("%-28s FAILED in the reference code: %s: %s" % (name, type(exc).__name__, exc), flush=True)
             continue
