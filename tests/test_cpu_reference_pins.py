@@ -18,6 +18,7 @@ from tests.refcode_cases import cases
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 CASES = cases()
 SKIP_ORACLE = set()
+MD_CASES = {"md_elliptic_k1": (1, 5), "md_elliptic_k2": (2, None)}  # name -> (k, alpha seed); tools/make_reference_pins.py
 
 
 def _fixture(name):
@@ -29,7 +30,7 @@ def _fixture(name):
 
 def test_every_case_has_its_fixture_and_nothing_else():
     have = {f[len("refcode_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("refcode_")}
-    assert have == set(CASES)
+    assert have == set(CASES) | set(MD_CASES)
 
 
 @pytest.mark.parametrize("name", sorted(set(CASES) - SKIP_ORACLE))
@@ -87,3 +88,37 @@ def test_numbering_and_destination_tables_equal_the_reference_codes(name):
     for i, want in enumerate(_rows(fx["bc_dest"])):
         assert np.array_equal(space.bc_destination_indexes(i), want)
         assert np.array_equal(rspace.bc_destination_indexes(i), want)
+
+
+@pytest.mark.parametrize("name", sorted(MD_CASES))
+def test_oracle_md_system_equals_the_reference_codes(name):
+    """Mixed-dimensional system (R/examples/md_elliptic_scalar/md_elliptic_scalar.py:205-342): the reference's mixed Poisson
+    forms on the fractured box and on the fracture plane (stacked with ``dof_shift``) and its ``CouplingWeakForm`` over the
+    interface triples, against the oracle's ``ref_md.assemble_md``; the product's triples and stacked destination indexes
+    against the ones the reference's spaces gave."""
+    from oracle import ref_forms, ref_md
+    from tests import md_helpers as mh
+
+    k, seed = MD_CASES[name]
+    fx = _fixture(name)
+    mesh, spaces, ref_spaces, triples, outer = mh.md_problem(2, k)
+    assert np.array_equal(np.asarray(triples, dtype=np.int64), fx["triples"])
+    n = len(fx["rhs"])
+    assert n == spaces[1].dof_shift + spaces[1].n_dof
+    alpha = np.zeros(n) if seed is None else np.random.default_rng(seed).standard_normal(n)
+    u0, u1 = ref_spaces[0].discrete_spaces["u"], ref_spaces[1].discrete_spaces["u"]
+    bc = {"p": mh.P_EXACT}
+    got = ref_md.assemble_md(
+        ref_spaces,
+        [[("form", ref_forms.laplace_dual, {"rhs": mh.RHS, "kappa": mh.KAPPA_C0}, len(u0.element_ids)),
+          ("bc_form", ref_forms.laplace_dual_bc_dirichlet, bc, outer)],
+         [("form", ref_forms.laplace_dual, {"rhs": mh.RHS, "kappa": mh.KAPPA_C1}, len(u1.element_ids)),
+          ("bc_form", ref_forms.laplace_dual_bc_dirichlet, bc, len(u1.bc_element_ids))]],
+        triples, mh.COUPLING, alpha)
+    compare_csr(got, (fx["indptr"], fx["indices"], fx["data"], fx["rhs"]), 1e-12)
+    # the synthetic post-cut mesh as the reference's Mesh numbers it
+    nc = len(fx["cell_dim"])
+    assert mesh.max_cell_id() == nc and np.array_equal(mesh.cell_dimension(np.arange(nc)), fx["cell_dim"])
+    for d in range(4):
+        ids = np.flatnonzero(fx["cell_dim"] == d)
+        assert np.array_equal(mesh.node_tags_of(d), fx["node_tags"][ids, : d + 1])

@@ -34,3 +34,14 @@ def test_cuda_path_assembles_what_the_reference_code_assembled(name):
     fx = np.load(os.path.join(GOLDEN, "refcode_%s.npz" % name))
     case = cases()[name]()
     compare_csr(case.run_gpu(), (fx["indptr"], fx["indices"], fx["data"], fx["rhs"]), 1e-12)
+
+
+@pytest.mark.parametrize("name,k,seed", [("md_elliptic_k1", 1, 5), ("md_elliptic_k2", 2, None)])
+def test_cuda_md_system_equals_the_reference_codes(name, k, seed):
+    """The stacked mixed-dimensional system (bulk + fracture + Robin coupling, ``GPUAssembler([space_c0, space_c1])``) of
+    test_gpu_md_coupling.py, expected values from the reference's forms and its example-local ``CouplingWeakForm``."""
+    from tests.test_gpu_md_coupling import _systems
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_%s.npz" % name))
+    got = _systems(k, alpha_seed=seed)[0]
+    compare_csr(got, (fx["indptr"], fx["indices"], fx["data"], fx["rhs"]), 1e-12)

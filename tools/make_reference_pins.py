@@ -167,6 +167,60 @@ def reference_system_sundus(case):
                 **mesh_numbering(gmesh))
 
 
+def reference_system_md(k, alpha_seed):
+    """The mixed-dimensional system of R/examples/md_elliptic_scalar/md_elliptic_scalar.py:205-342 on the synthetic
+    fractured box: the library's mixed Poisson forms on each dimension (through SequentialAssembler) and the example's
+    ``CouplingWeakForm`` over the interface triples, scattered the way the driver's closure does (:284-302)."""
+    sys.path.insert(0, "/root/reference/examples/md_elliptic_scalar")
+    from assembly.SequentialAssembler import SequentialAssembler
+    from CouplingWeakForm import CouplingWeakForm
+    from mesh.mesh import Mesh
+    from spaces.product_space import ProductSpace
+    from weak_forms.laplace_dual_weak_form import LaplaceDualWeakForm, LaplaceDualWeakFormBCDirichlet
+
+    from tests import md_helpers as mh
+
+    mesh, spaces, _, triples, outer = mh.md_problem(2, k)
+    name = "memory://md%d" % k
+    meshio.register(name, mesh.points, mesh._blocks)
+    gmesh = Mesh(dimension=3, file_name=name)
+    gmesh.build_conformal_mesh()
+    md_space = mh.md_spaces(gmesh, ProductSpace, k)
+    n = md_space[1].dof_shift + md_space[1].n_dof
+    assert n == spaces[1].dof_shift + spaces[1].n_dof
+    alpha = np.zeros(n) if alpha_seed is None else np.random.default_rng(alpha_seed).standard_normal(n)
+    jac, res = DictMat(n), np.zeros(n)
+    bc = {"p": mh.P_EXACT}
+    for space, fun, bc_items in ((md_space[0], {"rhs": mh.RHS, "kappa": mh.KAPPA_C0}, outer),
+                                 (md_space[1], {"rhs": mh.RHS, "kappa": mh.KAPPA_C1}, None)):
+        vol, bnd = LaplaceDualWeakForm(space), LaplaceDualWeakFormBCDirichlet(space)
+        vol.functions, bnd.functions = fun, bc
+        u = space.discrete_spaces["u"]
+        assembler = SequentialAssembler(space, jac, res)
+        assembler.form_to_input_list = {
+            "vol": ["form", range(len(u.elements)), vol, alpha],
+            "bc": ["bc_form", list(bc_items) if bc_items is not None else range(len(u.bc_elements)), bnd, alpha],
+        }
+        assembler.scatter_forms(measure_time_q=False)
+    coupling = CouplingWeakForm(md_space)
+    coupling.functions = mh.COUPLING
+    for c1_idx, c0_p_idx, c0_n_idx in np.asarray(triples).tolist():
+        dest = np.concatenate([md_space[0].bc_destination_indexes(c0_p_idx, "u"),
+                               md_space[0].bc_destination_indexes(c0_n_idx, "u"),
+                               md_space[1].destination_indexes(c1_idx, "p")])
+        r_el, j_el = coupling.evaluate_form(c1_idx, c0_p_idx, c0_n_idx, alpha[dest])
+        res[dest] += r_el
+        data, row, col = j_el.ravel(), np.repeat(dest, len(dest)), np.tile(dest, len(dest))
+        for v, r, c in zip(data, row, col):
+            jac.setValue(row=r, col=c, value=v, addv=True)
+    indptr, indices, values = jac.csr()
+    return dict(indptr=indptr, indices=indices, data=values, rhs=res, triples=np.asarray(triples, dtype=np.int64),
+                **mesh_numbering(gmesh))
+
+
+MD_CASES = {"md_elliptic_k1": (1, 5), "md_elliptic_k2": (2, None)}  # name -> (k, alpha seed), as tests/test_gpu_md_coupling.py
+
+
 def _ragged(rows):
     if not rows:
         return np.zeros((0, 0), dtype=np.int64)
@@ -208,6 +262,38 @@ def compare_with_oracle(case, got):
 def main():
     wanted = sys.argv[1:]
     out_dir = os.path.join(ROOT, "tests", "golden")
+    for name, (k, seed) in MD_CASES.items():
+        if wanted and name not in wanted:
+            continue
+        import contextlib
+        import io
+
+        from oracle import ref_forms, ref_md
+        from tests import md_helpers as mh
+
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = reference_system_md(k, seed)
+        _, _, ref_spaces, triples, outer = mh.md_problem(2, k)
+        n = len(got["rhs"])
+        alpha = np.zeros(n) if seed is None else np.random.default_rng(seed).standard_normal(n)
+        u0, u1 = ref_spaces[0].discrete_spaces["u"], ref_spaces[1].discrete_spaces["u"]
+        bc = {"p": mh.P_EXACT}
+        want = ref_md.assemble_md(
+            ref_spaces,
+            [[("form", ref_forms.laplace_dual, {"rhs": mh.RHS, "kappa": mh.KAPPA_C0}, len(u0.element_ids)),
+              ("bc_form", ref_forms.laplace_dual_bc_dirichlet, bc, outer)],
+             [("form", ref_forms.laplace_dual, {"rhs": mh.RHS, "kappa": mh.KAPPA_C1}, len(u1.element_ids)),
+              ("bc_form", ref_forms.laplace_dual_bc_dirichlet, bc, len(u1.bc_element_ids))]],
+            triples, mh.COUPLING, alpha)
+        same = np.array_equal(want[0], got["indptr"]) and np.array_equal(want[1], got["indices"])
+        report = {"pattern_equal": same}
+        if same:
+            report["max_rel_values"] = float(np.abs(want[2] - got["data"]).max() / np.abs(want[2]).max())
+            report["max_rel_rhs"] = float(np.abs(want[3] - got["rhs"]).max() / np.abs(want[3]).max())
+        np.savez_compressed(os.path.join(out_dir, "refcode_%s.npz" % name), **got)
+        print("%-28s n_dof %6d nnz %8d  vs oracle: %s  (%.1f s)" % (name, n, len(got["data"]), report,
+                                                                   time.perf_counter() - t0), flush=True)
     for name, make in cases().items():
         if wanted and name not in wanted:
             continue
