@@ -259,7 +259,76 @@ def compare_with_oracle(case, got):
             "max_rel_rhs": float(np.abs(want[3] - got["rhs"]).max() / rscale)}
 
 
+def verify_golden():
+    """The committed golden fixtures of tools/make_golden.py are ORACLE output.  This runs the reference's own source on the
+    reference's own gmsh files (through its ``Mesh(dimension, file_name)`` constructor) and on the same form lists, compares
+    with the committed arrays and records the outcome -- with the sha256 of each array it was compared with -- in
+    ``tests/golden/refcode_verified.json`` (tests/test_cpu_reference_pins.py checks the hashes against the files)."""
+    import contextlib
+    import hashlib
+    import io
+    import json
+
+    from assembly.SequentialAssembler import SequentialAssembler
+    from mesh.mesh import Mesh
+    from spaces.product_space import ProductSpace
+    from weak_forms.le_primal_weak_form import LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet
+
+    from tests import golden_cases as gc
+
+    msh_dir = "/root/reference/examples/cosserat_elasticity/gmsh_files/ex_3"
+    out = {}
+
+    def digest(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    def record(key, got, want):
+        same = np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        entry = {"pattern_equal": bool(same), "sha256_data": digest(want[2]), "sha256_rhs": digest(want[3])}
+        if same:
+            entry["values_bit_identical"] = bool(np.array_equal(got[2], want[2]))
+            entry["rhs_bit_identical"] = bool(np.array_equal(got[3], want[3]))
+            entry["max_rel_values"] = float(np.abs(got[2] - want[2]).max() / np.abs(want[2]).max())
+            entry["max_rel_rhs"] = float(np.abs(got[3] - want[3]).max() / np.abs(want[3]).max())
+        out[key] = entry
+        print(key, entry, flush=True)
+
+    # vector-P2 elasticity + Dirichlet penalty on the reference's 3-D fixture, levels 0 and 1 (config 2's form list)
+    for level in (0, 1):
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            gmesh = Mesh(dimension=3, file_name=os.path.join(msh_dir, "example_3_3d_l_%d.msh" % level))
+            gmesh.build_conformal_mesh()
+            space = ProductSpace({"u": (3, 3, "Lagrange", 2, gmesh)})
+            space.make_subspaces_discontinuous({"u": False})
+            space.build_structures({"u": [1]}, {"u": [2, 3, 4, 5, 6, 7]})
+            n = space.n_dof
+            jac, res = DictMat(n), np.zeros(n)
+            wf, bf = LEPrimalWeakForm(space), LEPrimalWeakFormBCDirichlet(space)
+            wf.functions, bf.functions = gc.LE_FUNCTIONS, gc.LE_BC_FUNCTIONS
+            us = space.discrete_spaces["u"]
+            assembler = SequentialAssembler(space, jac, res)
+            alpha = np.zeros(n)
+            assembler.form_to_input_list = {"volume": ["form", range(len(us.elements)), wf, alpha],
+                                            "bc": ["bc_form", range(len(us.bc_elements)), bf, alpha]}
+            assembler.scatter_forms(measure_time_q=False)
+        z = np.load(os.path.join(gc.GOLDEN, "le_p2_ex3_3d_l%d.npz" % level))
+        record("le_p2_ex3_3d_l%d.npz" % level, jac.csr() + (res,), (z["indptr"], z["indices"], z["data"], z["rhs"]))
+        print("  (%d tets, %.0f s)" % (len(us.elements), time.perf_counter() - t0), flush=True)
+    # the four systems of multi_ex3_2d_l0.npz on the reference's 2-D fixture
+    z = np.load(os.path.join(gc.GOLDEN, "multi_ex3_2d_l0.npz"))
+    for key, (case, _) in gc.multi_cases().items():
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = reference_system(case, vectorized=False)
+        record("multi_ex3_2d_l0.npz:" + key, (got["indptr"], got["indices"], got["data"], got["rhs"]),
+               tuple(z["%s_%s" % (key, part)] for part in ("indptr", "indices", "data", "rhs")))
+    with open(os.path.join(gc.GOLDEN, "refcode_verified.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def main():
+    if sys.argv[1:] == ["--verify-golden"]:
+        return verify_golden()
     wanted = sys.argv[1:]
     out_dir = os.path.join(ROOT, "tests", "golden")
     for name, (k, seed) in MD_CASES.items():
