@@ -29,7 +29,7 @@ def _fixture(name):
 
 
 def test_every_case_has_its_fixture_and_nothing_else():
-    have = {f[len("refcode_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("refcode_")}
+    have = {f[len("refcode_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("refcode_") and f.endswith(".npz")}
     assert have == set(CASES) | set(MD_CASES)
 
 
