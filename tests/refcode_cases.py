@@ -4,6 +4,12 @@ tests/parity_helpers.py, so product, oracle and reference code see the same mesh
 from tests import parity_helpers as ph
 
 
+def projector_case(dim, fields):
+    from tests.test_gpu_projector import _case
+
+    return _case(dim, fields)
+
+
 def cases():
     """name -> zero-argument function returning a tests.parity_helpers.Case (the same constructors the GPU parity tests
     use, so product, oracle and reference code see the same mesh, spaces, coefficient functions and form lists)."""
@@ -43,6 +49,13 @@ def cases():
         "sundus_rt1_3d": lambda: ph.SundusCase(dim=3, k=1, n=2),
         "sundus_rt1_2d": lambda: ph.SundusCase(dim=2, k=1, n=3),
         "sundus_rt2_3d": lambda: ph.SundusCase(dim=3, k=2, n=1),
+        # L2ProjectorWeakForm (the only path the reference's own tests exercise); the continuous cubic Lagrange cases go
+        # through the reference's edge exchange (permute_and_transform with transformations["interval"][0])
+        "projector_mixed_2d": lambda: projector_case(2, {"u": ("RT", 2, False), "p": ("Lagrange", 1, True), "q": ("Lagrange", 2, False)}),
+        "projector_mixed_3d": lambda: projector_case(3, {"u": ("RT", 2, False), "p": ("Lagrange", 1, True), "q": ("Lagrange", 2, False)}),
+        "projector_bdm1_rt3_3d": lambda: projector_case(3, {"u": ("BDM", 1, False), "v": ("RT", 3, False)}),
+        "projector_p3_2d": lambda: projector_case(2, {"u": ("Lagrange", 3, False)}),
+        "projector_p3_3d": lambda: projector_case(3, {"u": ("Lagrange", 3, False)}),
         "lce_primal_3d": lambda: ph.lce_primal_case(dim=3, k=2, n=1, varying=True, alpha=True),
         "lce_primal_2d": lambda: ph.lce_primal_case(dim=2, k=2, n=2),
         "taylor_hood_3d": lambda: ph.taylor_hood_case(n=1, varying=True, alpha=True),

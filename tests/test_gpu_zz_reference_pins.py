@@ -25,6 +25,12 @@ SAME_AS = {
     "lce_scaled_config4_order_ad": "test_gpu_tensor_forms.py::test_config_4_order_bdm3[lce_scaled-RT] (config 4's order)",
     "sundus_rt1_3d": "__graft_entry__.smoke() / test_gpu_hdiv.py::test_sundus_time_dependent_forms[3-1] (config 5's element; row-owner path)",
     "sundus_rt1_2d": "test_gpu_hdiv.py::test_sundus_time_dependent_forms[2-1]",
+    "projector_mixed_2d": "test_gpu_projector.py::test_projector_matches_oracle_mixed_fields[2]",
+    "projector_mixed_3d": "test_gpu_projector.py::test_projector_matches_oracle_mixed_fields[3]",
+    # continuous cubic Lagrange: the product scatters through exchanged destinations where the reference exchanges basis
+    # functions -- the assembled systems must coincide (same space as test_gpu_cubic.py's projector test)
+    "projector_p3_2d": "test_gpu_cubic.py::test_projection_of_a_cubic_onto_continuous_cubic_lagrange_is_exact[2]",
+    "projector_p3_3d": "test_gpu_cubic.py::test_projection_of_a_cubic_onto_continuous_cubic_lagrange_is_exact[3]",
     "taylor_hood_3d_n3": "test_gpu_h1_multifield.py::test_taylor_hood_2d[True-True]",
 }
 
