@@ -12,6 +12,9 @@ independent of ``nfempy_b200.basis`` (closed forms / scipy instead of the produc
 PARITY UNPINNED against real basix: basix is an un-vendored, unpinned dependency (R/requirements.txt:2) that cannot
 be installed here, and the reference's tests hold no golden vectors for this path.  Lagrange
 P1/P2 nodal bases are unique, so those tables are determined; H(div) tables follow basix's documented construction.
+Everything the reference does ABOVE these calls is pinned: tools/make_reference_pins.py runs the reference's own source with
+this module standing in for basix (tools/ref_shims/basix) and tests/test_cpu_reference_pins.py compares the oracle with what it
+produced (tests/golden/refcode_*.npz); what stays unpinned is exactly this module's and ref_hdiv.py's element tables.
 """
 import numpy as np
 from scipy.special import roots_jacobi

@@ -12,6 +12,14 @@ Forms restated:
 * ``le_primal_bc_neumann``    -- R/src/weak_forms/le_primal_weak_form.py:179-221
 * ``laplace_primal``          -- R/src/weak_forms/laplace_primal_weak_form.py:10-74 (with ``quadrature[dim]``)
 * ``laplace_primal_bc_dirichlet`` -- R/src/weak_forms/laplace_primal_weak_form.py:77-157
+
+PARITY: pinned against the reference's own source above the basix boundary.  tools/make_reference_pins.py imports
+/root/reference/src unmodified over stand-ins for meshio / basix / auto_diff (tools/ref_shims) and runs the classes restated
+here through ``SequentialAssembler.scatter_forms``; tests/test_cpu_reference_pins.py compares this module with the result
+(tests/golden/refcode_*.npz): bit-identical for every form of this file except the Sundus tangent (complex step here, AD
+there: 5e-16).  ``laplace_primal*`` alone has no counterpart run: the reference's class is stale (it unpacks
+``space.quadrature`` as a pair, R/src/weak_forms/laplace_primal_weak_form.py:26, where ProductSpace now keeps a list per
+dimension) -- it is checked by known answers only.  basix's own element conventions stay unpinned (oracle/ref_basis.py).
 """
 import numpy as np
 

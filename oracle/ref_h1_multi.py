@@ -10,9 +10,10 @@ forms on several Lagrange fields:
 * ``le_stress_constraint``     -- R/src/weak_forms/le_primal_stress_constraint_weak_form.py:10-126
 
 The reference differentiates its residual with ``auto_diff``; the forms are linear in ``alpha``, so the Jacobian is the
-homogeneous residual of the unit vectors (``ref_forms._linearise``, see that module's header).  PARITY UNPINNED against
-the real reference (basix / auto_diff cannot be imported here); P1 / P2 Lagrange bases are unique, so only round-off
-can differ.
+homogeneous residual of the unit vectors (``ref_forms._linearise``, see that module's header).  PARITY: the reference's own classes, run over
+stand-ins for basix / auto_diff (tools/make_reference_pins.py), give these matrices bit for bit
+(tests/golden/refcode_lce_primal_*, refcode_taylor_hood_*, refcode_stress_constraint_*); P1 / P2 Lagrange bases are unique,
+so nothing of basix's conventions enters.
 """
 import numpy as np
 

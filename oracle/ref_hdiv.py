@@ -9,7 +9,8 @@ snapped to their exact rationals and a 60-digit solve here; exact rational arith
   edge cell's own ``node_tags``, face table of six permutation cases, forced reflection of tagged faces with
   local index 1 or 3, faces before edges).
 
-PARITY UNPINNED against real basix (see oracle/ref_basis.py).
+PARITY UNPINNED against real basix (see oracle/ref_basis.py); ``permute_and_transform`` below is pinned against the
+reference's own (tests/test_cpu_reference_pins.py: the reference's source run over these tables).
 """
 from itertools import permutations
 

@@ -9,7 +9,9 @@ Mixed-dimensional coupling, cell by cell:
 * ``assemble_md`` -- the driver's scatter loops, R/examples/md_elliptic_scalar/md_elliptic_scalar.py:250-342: volume and
   boundary forms of every space with its ``dof_shift``, then ``scatter_coupling_form_data`` over the interface triples.
 
-PARITY UNPINNED against the real reference (basix / auto_diff / petsc4py absent; see oracle/ref_basis.py).
+PARITY: pinned against the reference's own source above the basix boundary (tools/make_reference_pins.py runs
+CouplingWeakForm + the stacked spaces over stand-ins for basix / auto_diff; tests/golden/refcode_md_elliptic_k*.npz: bit-identical);
+basix's element conventions stay unpinned (oracle/ref_basis.py).
 """
 import numpy as np
 

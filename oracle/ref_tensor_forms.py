@@ -13,7 +13,9 @@ Restatement of the reference's closed-form (``evaluate_form_vectorized``) mixed 
 The block operators are built the way the reference builds them (``outer_fun`` / ``inner_fun`` with ``np.tensordot`` and
 ``np.block`` per quadrature point, then a weighted sum over the points); the Jacobian is the closed form and the
 residual is ``J alpha + load`` (what the reference's AD variant ``evaluate_form`` returns for these linear forms; the
-vectorised variant returns the load only -- ``alpha=None`` reproduces that).  PARITY UNPINNED (see ref_basis.py).
+vectorised variant returns the load only -- ``alpha=None`` reproduces that).  PARITY: pinned against the reference's own source above the basix boundary, through BOTH of its
+entry points (``evaluate_form_vectorized`` at alpha = 0, the AD quadrature loop ``evaluate_form`` at a non-zero state, config 4's order
+included: tests/golden/refcode_l*.npz, tools/make_reference_pins.py); basix's element conventions stay unpinned (ref_basis.py).
 """
 import numpy as np
 

@@ -16,7 +16,8 @@
 
 The reference itself cannot run here (basix / auto_diff / petsc4py / meshio absent), so these are ORACLE outputs:
 they pin the oracle against regressions and give the GPU tests a fixed target; they do not pin the oracle to the
-real reference ("parity unpinned").
+real reference ("parity unpinned").  Later: tools/make_reference_pins.py --verify-golden runs the reference's own
+source on the same gmsh files and form lists and reproduces these arrays bit for bit (tests/golden/refcode_verified.json).
 """
 import os
 import sys
