@@ -149,3 +149,40 @@ def test_committed_golden_fixtures_are_the_ones_the_reference_code_reproduced():
         assert hashlib.sha256(np.ascontiguousarray(rhs).tobytes()).hexdigest() == entry["sha256_rhs"], key
         assert entry["pattern_equal"] and entry["max_rel_values"] <= 1e-13 and entry["max_rel_rhs"] <= 1e-13, key
     assert verified["le_p2_ex3_3d_l0.npz"]["values_bit_identical"] and verified["le_p2_ex3_3d_l1.npz"]["values_bit_identical"]
+
+
+@pytest.mark.parametrize("dim,k,fam", [(3, 1, "BDM"), (2, 2, "RT"), (3, 2, "RT")])
+def test_oracle_error_norms_equal_the_reference_codes(dim, k, fam):
+    """``l2_error``, ``div_error``, ``l2_error_projected`` (+ ``dof_shift``), ``l2_norm``, ``div_norm``, ``div_scaled_error``
+    of R/src/postprocess, run by tools/make_reference_pins.py --postprocess on the spaces / fields of
+    tests/test_gpu_postprocess.py (which compares the CUDA reductions with the same oracle functions)."""
+    import json
+
+    from oracle import ref_postprocess as rp
+    from tests.parity_helpers import tensor_mixed_case
+    from tests.test_gpu_postprocess import _fields
+
+    with open(os.path.join(GOLDEN, "refcode_postprocess.json")) as f:
+        want = json.load(f)["%dd_k%d_%s" % (dim, k, fam)]
+    case = tensor_mixed_case(kind="lce", dim=dim, s_family=fam, m_family="RT", k=k, n=2 if dim == 2 else 1)
+    rspace = case.ref_space()
+    assert rspace.n_dof == want["n_dof"]
+    alpha = np.cos(np.arange(rspace.n_dof) * 0.31) + 0.2
+    fn = _fields(dim)
+    fn_l = dict(fn, l=lambda x, y, z: 0.5 + 0.25 * x + 0.1 * y * y,
+                grad_l=lambda x, y, z: np.array([0.25 * np.ones_like(x), 0.2 * y, 0.0 * x]))
+    shifted = np.concatenate([np.full(5, 7.0), alpha])
+    got = {
+        "l2_error": rp.l2_error(dim, rspace, fn, alpha),
+        "l2_error_skip_m_t": rp.l2_error(dim, rspace, fn, alpha, skip_fields=["m", "t"]),
+        "div_error": rp.div_error(dim, rspace, fn, alpha),
+        "l2_error_projected": rp.l2_error_projected(dim, rspace, alpha),
+        "l2_error_projected_shift5": rp.l2_error_projected(dim, rspace, shifted, dof_shift=5),
+        "l2_norm": rp.l2_norm(dim, rspace, fn),
+        "div_norm": rp.div_norm(dim, rspace, fn),
+        "div_scaled_error_without_scale": rp.div_scaled_error(dim, rspace, fn, alpha),
+        "div_scaled_error": rp.div_scaled_error(dim, rspace, fn_l, alpha),
+    }
+    for key, values in got.items():
+        assert len(values) == len(want[key]), key
+        assert np.allclose(values, want[key], rtol=1e-13, atol=0.0), (key, values, want[key])

@@ -326,9 +326,64 @@ def verify_golden():
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+POSTPROCESS_CASES = [(3, 1, "BDM"), (2, 2, "RT"), (3, 2, "RT")]  # as tests/test_gpu_postprocess.py
+
+
+def postprocess_pins():
+    """The reference's error / solution norms (R/src/postprocess/l2_error_post_processor.py:7-117, 185-305,
+    solution_norms_post_processor.py:7-78) on the mixed Cosserat spaces and fields of tests/test_gpu_postprocess.py, for a
+    seeded coefficient vector -> tests/golden/refcode_postprocess.json."""
+    import contextlib
+    import io
+    import json
+
+    from mesh.mesh import Mesh
+    from postprocess.l2_error_post_processor import div_error, div_scaled_error, l2_error, l2_error_projected
+    from postprocess.solution_norms_post_processor import div_norm, l2_norm
+    from spaces.product_space import ProductSpace
+
+    from tests.test_gpu_postprocess import _fields
+
+    out = {}
+    for dim, k, fam in POSTPROCESS_CASES:
+        case = ph.tensor_mixed_case(kind="lce", dim=dim, s_family=fam, m_family="RT", k=k, n=2 if dim == 2 else 1)
+        with contextlib.redirect_stdout(io.StringIO()):
+            name = "memory://pp%d%d%s" % (dim, k, fam)
+            meshio.register(name, case.mesh.points, case.mesh._blocks)
+            gmesh = Mesh(dimension=dim, file_name=name)
+            gmesh.build_conformal_mesh()
+            data = case.data_fn(gmesh)
+            space = ProductSpace(data)
+            space.make_subspaces_discontinuous({f: bool(case.disc.get(f, False)) for f in data})
+            space.build_structures(case.tags, case.btags)
+        alpha = np.cos(np.arange(space.n_dof) * 0.31) + 0.2
+        fn = _fields(dim)
+        fn_l = dict(fn, l=lambda x, y, z: 0.5 + 0.25 * x + 0.1 * y * y,
+                    grad_l=lambda x, y, z: np.array([0.25 * np.ones_like(x), 0.2 * y, 0.0 * x]))
+        shifted = np.concatenate([np.full(5, 7.0), alpha])
+        entry = {
+            "n_dof": int(space.n_dof),
+            "l2_error": [float(v) for v in l2_error(dim, space, fn, alpha)],
+            "l2_error_skip_m_t": [float(v) for v in l2_error(dim, space, fn, alpha, skip_fields=["m", "t"])],
+            "div_error": [float(v) for v in div_error(dim, space, fn, alpha)],
+            "l2_error_projected": [float(v) for v in l2_error_projected(dim, space, alpha)],
+            "l2_error_projected_shift5": [float(v) for v in l2_error_projected(dim, space, shifted, dof_shift=5)],
+            "l2_norm": [float(v) for v in l2_norm(dim, space, fn)],
+            "div_norm": [float(v) for v in div_norm(dim, space, fn)],
+            "div_scaled_error_without_scale": [float(v) for v in div_scaled_error(dim, space, fn, alpha)],
+            "div_scaled_error": [float(v) for v in div_scaled_error(dim, space, fn_l, alpha)],
+        }
+        out["%dd_k%d_%s" % (dim, k, fam)] = entry
+        print(dim, k, fam, {key: len(v) if isinstance(v, list) else v for key, v in entry.items()}, flush=True)
+    with open(os.path.join(ROOT, "tests", "golden", "refcode_postprocess.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
 def main():
     if sys.argv[1:] == ["--verify-golden"]:
         return verify_golden()
+    if sys.argv[1:] == ["--postprocess"]:
+        return postprocess_pins()
     wanted = sys.argv[1:]
     out_dir = os.path.join(ROOT, "tests", "golden")
     for name, (k, seed) in MD_CASES.items():
