@@ -4,6 +4,29 @@ tests/parity_helpers.py, so product, oracle and reference code see the same mesh
 from tests import parity_helpers as ph
 
 
+def hcurl_projector_case(dim):
+    """N1E of degree 1 through L2ProjectorWeakForm, as tests/test_gpu_projector.py::test_hcurl_projector_matches_oracle."""
+    import numpy as np
+
+    from nfempy_b200.mesh import box_tet_mesh, square_tri_mesh
+    from oracle import ref_hcurl
+
+    mesh = box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True) if dim == 3 else square_tri_mesh(3, jitter=0.2)
+    functions = {"e": lambda x, y, z: np.array([[np.sin(x) + y, x * y - z, 1.0 + z * x]])}
+
+    def gpu_forms(space, a):
+        from nfempy_b200.weak_forms import L2ProjectorWeakForm
+
+        wf = L2ProjectorWeakForm(space)
+        wf.functions = functions
+        return {"proj": ["form", range(len(space.discrete_spaces["e"].elements)), wf, a]}
+
+    def ref_forms_fn(space):
+        return [("form", ref_hcurl.l2_projector, functions, len(space.discrete_spaces["e"].element_ids))]
+
+    return ph.Case(mesh, lambda g: {"e": (dim, 1, "N1E", 1, g)}, {"e": [1]}, {}, gpu_forms, ref_forms_fn)
+
+
 def projector_case(dim, fields):
     from tests.test_gpu_projector import _case
 
@@ -54,6 +77,11 @@ def cases():
         "projector_mixed_2d": lambda: projector_case(2, {"u": ("RT", 2, False), "p": ("Lagrange", 1, True), "q": ("Lagrange", 2, False)}),
         "projector_mixed_3d": lambda: projector_case(3, {"u": ("RT", 2, False), "p": ("Lagrange", 1, True), "q": ("Lagrange", 2, False)}),
         "projector_bdm1_rt3_3d": lambda: projector_case(3, {"u": ("BDM", 1, False), "v": ("RT", 3, False)}),
+        # H(curl): N1E of degree 1; the stand-in tabulates the textbook Whitney functions on the reference simplex, the
+        # reference's FiniteElement maps them (covariant) and its permute_and_transform applies the edge signs; the oracle
+        # builds the same functions in physical coordinates
+        "projector_n1e_2d": lambda: hcurl_projector_case(2),
+        "projector_n1e_3d": lambda: hcurl_projector_case(3),
         "projector_p3_2d": lambda: projector_case(2, {"u": ("Lagrange", 3, False)}),
         "projector_p3_3d": lambda: projector_case(3, {"u": ("Lagrange", 3, False)}),
         "lce_primal_3d": lambda: ph.lce_primal_case(dim=3, k=2, n=1, varying=True, alpha=True),

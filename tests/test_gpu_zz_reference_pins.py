@@ -25,6 +25,8 @@ SAME_AS = {
     "lce_scaled_config4_order_ad": "test_gpu_tensor_forms.py::test_config_4_order_bdm3[lce_scaled-RT] (config 4's order)",
     "sundus_rt1_3d": "__graft_entry__.smoke() / test_gpu_hdiv.py::test_sundus_time_dependent_forms[3-1] (config 5's element; row-owner path)",
     "sundus_rt1_2d": "test_gpu_hdiv.py::test_sundus_time_dependent_forms[2-1]",
+    "projector_n1e_2d": "test_gpu_projector.py::test_hcurl_projector_matches_oracle[2]",
+    "projector_n1e_3d": "test_gpu_projector.py::test_hcurl_projector_matches_oracle[3]",
     "projector_mixed_2d": "test_gpu_projector.py::test_projector_matches_oracle_mixed_fields[2]",
     "projector_mixed_3d": "test_gpu_projector.py::test_projector_matches_oracle_mixed_fields[3]",
     # continuous cubic Lagrange: the product scatters through exchanged destinations where the reference exchanges basis
