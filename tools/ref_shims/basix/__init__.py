@@ -1,5 +1,5 @@
 """Stand-in for fenics-basix (absent here) behind the call surface the reference uses (SURVEY.md section 8c lists the call
-sites).  Every answer comes from ``oracle/ref_basis.py`` / ``oracle/ref_hdiv.py``: the pins made with this stand-in cover the
+sites).  Every answer but the N1E table (``_whitney``, textbook) comes from ``oracle/ref_basis.py`` / ``oracle/ref_hdiv.py``: the pins made with this stand-in cover the
 reference's code ABOVE the basix boundary, not basix's own conventions (see tools/ref_shims/README.md)."""
 import enum
 
