@@ -144,7 +144,8 @@ def parity_check(torch, space, asm, plan, step, n_sample):
     rel = np.abs(got_val - want) / np.where(scale > 0, scale, 1.0)
     return {"rows_checked": int(len(rows)), "values_checked": int(len(want)), "sample_cells": int(m),
             "pattern_equal": bool(np.array_equal(got_idx, ref_idx[rpos])), "max_rel": float(rel.max(initial=0.0)),
-            "against": "oracle/strong_cpu.py (vectorised numpy restatement, pinned to the cell-by-cell oracle)",
+            "against": "oracle/strong_cpu.py (vectorised numpy restatement, pinned to the cell-by-cell oracle, which the "
+                       "reference's own source reproduces bit for bit: tests/test_cpu_reference_pins.py)",
             "tolerance": 1e-12}
 
 

@@ -27,6 +27,56 @@ def hcurl_projector_case(dim):
     return ph.Case(mesh, lambda g: {"e": (dim, 1, "N1E", 1, g)}, {"e": [1]}, {}, gpu_forms, ref_forms_fn)
 
 
+DRIVER_MATERIAL = {"lambda": 2.5, "mu": 0.75}
+
+
+def driver_displacement(m_lambda, m_mu, dim=2):
+    """Takes the place of strong_solution_elasticity_example_1.displacement while the reference's driver runs."""
+    import numpy as np
+
+    return lambda x, y, z: np.array([x * (1 - x) * y, np.sin(np.pi * x) * z + m_mu * y, 0.5 * z * z + y / (1.0 + m_lambda)])[:dim]
+
+
+def driver_rhs(m_lambda, m_mu, dim=2):
+    import numpy as np
+
+    return lambda x, y, z: np.array([np.sin(np.pi * x) * np.cos(np.pi * y), m_lambda * np.cos(np.pi * y) * np.sin(np.pi * z),
+                                     x * y + m_mu * z])[:dim]
+
+
+def driver_case():
+    """What R/examples/cauchy_elasticity/cg_elasticity_example_1.py ``primal_approximation`` assembles on the jittered
+    2 x 2 x 2 Kuhn box: vector-P2 elasticity, volume tags [1, 2, 3, 4], Dirichlet penalty on the boundary tags [5, 6, 7, 8]
+    (three of the box's six sides carry them), through the driver's own scatter closure -- entries with
+    ``~isclose(v, 1e-16)`` and ``row <= col`` only ("sbaij"), explicit zeros on the diagonal (:92-145)."""
+    import numpy as np
+
+    from nfempy_b200.mesh import box_tet_mesh
+    from oracle import ref_forms
+
+    lam, mu = DRIVER_MATERIAL["lambda"], DRIVER_MATERIAL["mu"]
+    functions = {"rhs": driver_rhs(lam, mu, 3), "lambda": lambda x, y, z: lam * np.ones_like(x),
+                 "mu": lambda x, y, z: mu * np.ones_like(x)}
+    bc_functions = {"u": driver_displacement(lam, mu, 3)}
+
+    def gpu_forms(space, a):
+        from nfempy_b200.weak_forms import LEPrimalWeakForm, LEPrimalWeakFormBCDirichlet
+
+        wf, bf = LEPrimalWeakForm(space), LEPrimalWeakFormBCDirichlet(space)
+        wf.functions, bf.functions = functions, bc_functions
+        u = space.discrete_spaces["u"]
+        return {"volume": ["form", range(len(u.elements)), wf, a], "bc": ["bc_form", range(len(u.bc_elements)), bf, a]}
+
+    def ref_forms_fn(space):
+        u = space.discrete_spaces["u"]
+        return [("form", ref_forms.le_primal, functions, len(u.element_ids)),
+                ("bc_form", ref_forms.le_primal_bc_dirichlet, bc_functions, len(u.bc_element_ids))]
+
+    mesh = box_tet_mesh(2, jitter=0.2, shuffle_local_nodes=True)
+    return ph.Case(mesh, lambda g: {"u": (3, 3, "Lagrange", 2, g)}, {"u": [1, 2, 3, 4]}, {"u": [5, 6, 7, 8]}, gpu_forms,
+                   ref_forms_fn)
+
+
 def projector_case(dim, fields):
     from tests.test_gpu_projector import _case
 

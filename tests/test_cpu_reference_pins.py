@@ -186,3 +186,37 @@ def test_oracle_error_norms_equal_the_reference_codes(dim, k, fam):
     for key, values in got.items():
         assert len(values) == len(want[key]), key
         assert np.allclose(values, want[key], rtol=1e-13, atol=0.0), (key, values, want[key])
+
+
+def test_oracle_filtered_scatter_equals_what_the_reference_driver_inserted():
+    """``tools/make_reference_pins.py --driver`` ran the reference's example driver itself
+    (R/examples/cauchy_elasticity/cg_elasticity_example_1.py ``primal_approximation`` + ``primal_postprocessing``, over the
+    stand-ins incl. a petsc4py one) and kept what its OWN scatter closure put into the "sbaij" matrix: entries with
+    ``~isclose(v, 1e-16)`` and ``row <= col``, explicit diagonal zeros (:92-145) -- the ``filtered_upper`` policy of
+    ``GPUAssembler``.  The oracle's ``assemble_filtered`` must give the same CSR, the driver's solution must solve the oracle's
+    system, and the oracle's ``l2_error`` of that solution must be the number the driver printed."""
+    import scipy.sparse as sp
+
+    from oracle import ref_postprocess
+    from tests.refcode_cases import DRIVER_MATERIAL, driver_case, driver_displacement
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_driver_cg_elasticity.npz"))
+    case = driver_case()
+    indptr, indices, data, rhs = case.run_oracle(upper=True, explicit_diagonal=True)
+    assert np.array_equal(indptr, fx["indptr"]) and np.array_equal(indices, fx["indices"])
+    assert np.abs(data - fx["data"]).max() <= 1e-13 * np.abs(fx["data"]).max()
+    n = len(rhs)
+    upper = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    assert (sp.tril(upper, -1)).nnz == 0
+    full = upper + sp.triu(upper, 1).T
+    assert np.abs(full @ fx["alpha"] + rhs).max() <= 1e-9 * np.abs(rhs).max()  # the driver solved K alpha = -rg
+    rspace = case.ref_space()
+    exact = {"u": driver_displacement(DRIVER_MATERIAL["lambda"], DRIVER_MATERIAL["mu"], 3)}
+    assert np.allclose(ref_postprocess.l2_error(3, rspace, exact, fx["alpha"]), fx["l2_error"], rtol=1e-12, atol=0.0)
+    # the product's host layer on the driver's tag lists (volume [1, 2, 3, 4], boundary [5, 6, 7, 8])
+    space = case.space()
+    assert space.n_dof == n
+    u, ru = space.discrete_spaces["u"], rspace.discrete_spaces["u"]
+    assert len(u.elements) == len(ru.element_ids) == 48 and len(u.bc_elements) == len(ru.bc_element_ids) > 0
+    for i in range(len(u.bc_elements)):
+        assert np.array_equal(space.bc_destination_indexes(i), rspace.bc_destination_indexes(i))

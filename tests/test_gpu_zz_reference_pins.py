@@ -53,3 +53,15 @@ def test_cuda_md_system_equals_the_reference_codes(name, k, seed):
     fx = np.load(os.path.join(GOLDEN, "refcode_%s.npz" % name))
     got = _systems(k, alpha_seed=seed)[0]
     compare_csr(got, (fx["indptr"], fx["indices"], fx["data"], fx["rhs"]), 1e-12)
+
+
+def test_cuda_filtered_upper_policy_equals_what_the_reference_driver_inserted():
+    """The example drivers' scatter semantic (``GPUAssembler(pattern_policy="filtered_upper", explicit_diagonal=True)``, as
+    test_gpu_parity.py::test_example_driver_scatter_policy_primal_elasticity) against the "sbaij" matrix the reference's own
+    driver closure filled (R/examples/cauchy_elasticity/cg_elasticity_example_1.py:92-145, run by
+    tools/make_reference_pins.py --driver): pattern bit-exact, values to 1e-12."""
+    from tests.refcode_cases import driver_case
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_driver_cg_elasticity.npz"))
+    got = driver_case().run_gpu(pattern_policy="filtered_upper", explicit_diagonal=True)
+    compare_csr(got, (fx["indptr"], fx["indices"], fx["data"], got[3]), 1e-12)

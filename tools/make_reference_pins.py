@@ -379,7 +379,46 @@ def postprocess_pins():
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def driver_pin():
+    """Runs the reference's EXAMPLE DRIVER itself -- ``primal_approximation`` and ``primal_postprocessing`` of
+    R/examples/cauchy_elasticity/cg_elasticity_example_1.py, unmodified -- over the stand-ins (plus tools/ref_shims/petsc4py)
+    and keeps what its own scatter closure inserted into the "sbaij" matrix: the filtered, upper-triangular CSR with explicit
+    diagonal zeros, the solution vector and the L2 error it reports -> tests/golden/refcode_driver_cg_elasticity.npz.  The
+    example's strong-solution module is replaced by tests/refcode_cases.py's functions so that the tests need no reference."""
+    import contextlib
+    import io
+    import types
+
+    from petsc4py import PETSc
+
+    from tests import refcode_cases as rc
+
+    stub = types.ModuleType("strong_solution_elasticity_example_1")
+    stub.displacement, stub.rhs = rc.driver_displacement, rc.driver_rhs
+    sys.modules["strong_solution_elasticity_example_1"] = stub
+    sys.path.insert(0, "/root/reference/examples/cauchy_elasticity")
+    import cg_elasticity_example_1 as driver
+
+    case = rc.driver_case()
+    meshio.register("memory://driver", case.mesh.points, case.mesh._blocks)
+    method = ("FEM", {"u": ("Lagrange", 2)})
+    with contextlib.redirect_stdout(io.StringIO()):
+        gmesh = driver.create_mesh_from_file("memory://driver", 3)
+        PETSc.ASSEMBLED.clear()
+        alpha, _ = driver.primal_approximation(rc.DRIVER_MATERIAL, method, gmesh)
+        n_dof, errors = driver.primal_postprocessing(rc.DRIVER_MATERIAL, method, gmesh, alpha)
+    indptr, indices, data = PETSc.ASSEMBLED[-1].getValuesCSR()
+    want = case.run_oracle(upper=True, explicit_diagonal=True)
+    same = np.array_equal(want[0], indptr) and np.array_equal(want[1], indices)
+    print("driver cg_elasticity_example_1: n_dof %d nnz %d pattern_equal %s max_rel_values %s l2_error %.6e" % (
+        n_dof, len(data), same, float(np.abs(want[2] - data).max() / np.abs(want[2]).max()) if same else None, errors[0]))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refcode_driver_cg_elasticity.npz"), indptr=indptr,
+                        indices=indices, data=data, alpha=np.asarray(alpha), l2_error=np.asarray(errors), **mesh_numbering(gmesh))
+
+
 def main():
+    if sys.argv[1:] == ["--driver"]:
+        return driver_pin()
     if sys.argv[1:] == ["--verify-golden"]:
         return verify_golden()
     if sys.argv[1:] == ["--postprocess"]:
