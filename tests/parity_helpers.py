@@ -319,10 +319,12 @@ def degenerate_case(kind="degenerate", dim=3, k=1, n=2, with_bc=True, alpha=True
         return out
 
     alpha_fn = (lambda nd: np.cos(np.arange(nd) * 0.37) + 0.1) if alpha else None
-    return Case(
+    case = Case(
         mesh, lambda g: {flux: (dim, 1, "RT", k, g), scalar: (dim, 1, "Lagrange", k - 1, g)}, {flux: [1], scalar: [1]},
         {flux: btag_list if with_bc else []}, gpu_forms, ref_forms_fn, disc={scalar: True}, alpha_fn=alpha_fn,
     )
+    case.scaled_fn = scaled_fn  # the second state vector of the "projection" kind (tools/make_reference_pins.py)
+    return case
 
 
 def tensor_mixed_case(kind="lce", dim=3, s_family="BDM", m_family="RT", k=1, n=2, with_bc=True, alpha=True, mesh=None,

@@ -106,6 +106,8 @@ def cases():
         # point returns the load vector only); names ending in "_ad": the SAME classes through ``evaluate_form`` (quadrature
         # loop + AD) at a non-zero state -- the oracle restates the vectorized blocks and adds J.alpha, so these agree to
         # round-off, not bit for bit
+        "scaled_to_physical_projection_3d": lambda: ph.degenerate_case(kind="projection", dim=3, k=1, n=2),
+        "scaled_to_physical_projection_2d": lambda: ph.degenerate_case(kind="projection", dim=2, k=2, n=3),
         "le_dual_bdm1_3d": lambda: ph.tensor_mixed_case(kind="le", dim=3, k=1, n=1, alpha=False),
         "lce_dual_bdm1_rt1_3d": lambda: ph.tensor_mixed_case(kind="lce", dim=3, k=1, n=1, alpha=False),
         "lce_dual_bdm2_2d_neumann": lambda: ph.tensor_mixed_case(kind="lce", dim=2, s_family="BDM", m_family="BDM", k=2, n=2, neumann=True, alpha=False),

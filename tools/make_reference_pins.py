@@ -116,6 +116,22 @@ def reference_system(case, vectorized=True):
     assembler = SequentialAssembler(space, jac, res)
     form_list = {}
     for j, (kind, oracle_fn, functions, n_items) in enumerate(case.ref_forms_fn(oracle_space)):
+        if oracle_fn.__name__ == "proj":
+            # ScaledToPhysicalL2Projection takes two local vectors and is scattered by its driver's own closure
+            # (R/examples/degenerate_elliptic_scalar/degenerate_mixed_flow_model.py:172-189): restated here
+            from weak_forms.scaled_to_physical_l2_projection import ScaledToPhysicalL2Projection
+
+            form = ScaledToPhysicalL2Projection(space)
+            form.functions = functions
+            scaled = case.scaled_fn(n)
+            for i in range(n_items):
+                dest = space.destination_indexes(i)
+                r_el, j_el = form.evaluate_form(i, alpha[dest], scaled[dest])
+                res[dest] += r_el
+                data, row, col = j_el.ravel(), np.repeat(dest, len(dest)), np.tile(dest, len(dest))
+                for v, r, c in zip(data, row, col):
+                    jac.setValue(row=r, col=c, value=v, addv=True)
+            continue
         module, cls = REF_CLASS[oracle_fn.__name__]
         form = getattr(importlib.import_module("weak_forms." + module), cls)(space)
         form.functions = functions
