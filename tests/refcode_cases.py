@@ -77,6 +77,19 @@ def driver_case():
                    ref_forms_fn)
 
 
+def cosserat_driver_cases():
+    """(saddle-point case, Riesz-map case) of what R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py
+    ``four_field_scaled_approximation`` assembles with its method "wc_rt" at k_order = 0 (BDM_1 x RT_1 x P_0 x P_0) on the
+    jittered Kuhn box of six tetrahedra: ``A`` from LCEScaledDualWeakForm through the driver's closure (filtered, upper,
+    explicit diagonal zeros; the natural boundary form only feeds the right-hand side) and the preconditioner ``P`` from
+    LCEScaledRieszMapWeakForm (filtered, upper).  Coefficients: tests/parity_helpers.tensor_mixed_case's."""
+    from nfempy_b200.mesh import box_tet_mesh
+
+    mesh = box_tet_mesh(1, jitter=0.2, shuffle_local_nodes=True)
+    return (ph.tensor_mixed_case(kind="lce_scaled", dim=3, n=1, alpha=False, mesh=mesh),
+            ph.tensor_mixed_case(kind="lce_scaled_riesz", dim=3, n=1, alpha=False, mesh=mesh))
+
+
 def projector_case(dim, fields):
     from tests.test_gpu_projector import _case
 

@@ -30,7 +30,7 @@ def _fixture(name):
 
 def test_every_case_has_its_fixture_and_nothing_else():
     have = {f[len("refcode_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("refcode_") and f.endswith(".npz")}
-    assert have == set(CASES) | set(MD_CASES) | {"driver_cg_elasticity"}
+    assert have == set(CASES) | set(MD_CASES) | {"driver_cg_elasticity", "driver_mfe_cosserat"}
 
 
 @pytest.mark.parametrize("name", sorted(set(CASES) - SKIP_ORACLE))
@@ -220,3 +220,27 @@ def test_oracle_filtered_scatter_equals_what_the_reference_driver_inserted():
     assert len(u.elements) == len(ru.element_ids) == 48 and len(u.bc_elements) == len(ru.bc_element_ids) > 0
     for i in range(len(u.bc_elements)):
         assert np.array_equal(space.bc_destination_indexes(i), rspace.bc_destination_indexes(i))
+
+
+def test_oracle_equals_what_the_reference_cosserat_driver_assembled():
+    """BASELINE config 4's driver (R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py
+    ``four_field_scaled_approximation``, run unmodified by tools/make_reference_pins.py --cosserat-driver, method "wc_rt" at
+    k_order = 0): the saddle-point matrix its closure fills from ``LCEScaledDualWeakForm.evaluate_form_vectorized`` (filtered,
+    upper, explicit diagonal zeros; the natural boundary form feeds the right-hand side only) and the preconditioner from
+    ``LCEScaledRieszMapWeakForm`` (filtered, upper), against the oracle's ``assemble_filtered``; the driver's solution solves
+    the oracle's system."""
+    import scipy.sparse as sp
+
+    from tests.refcode_cases import cosserat_driver_cases
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_driver_mfe_cosserat.npz"))
+    case, riesz = cosserat_driver_cases()
+    a = case.run_oracle(upper=True, explicit_diagonal=True)
+    p = riesz.run_oracle(upper=True, explicit_diagonal=False)
+    for got, key in ((a, "a"), (p, "p")):
+        assert np.array_equal(got[0], fx[key + "_indptr"]) and np.array_equal(got[1], fx[key + "_indices"])
+        assert np.abs(got[2] - fx[key + "_data"]).max() <= 1e-13 * np.abs(fx[key + "_data"]).max()
+    n = len(a[3])
+    upper = sp.csr_matrix((a[2], a[1], a[0]), shape=(n, n))
+    full = upper + sp.triu(upper, 1).T
+    assert np.abs(full @ fx["alpha"] + a[3]).max() <= 1e-9 * max(np.abs(a[3]).max(), 1.0)

@@ -65,3 +65,16 @@ def test_cuda_filtered_upper_policy_equals_what_the_reference_driver_inserted():
     fx = np.load(os.path.join(GOLDEN, "refcode_driver_cg_elasticity.npz"))
     got = driver_case().run_gpu(pattern_policy="filtered_upper", explicit_diagonal=True)
     compare_csr(got, (fx["indptr"], fx["indices"], fx["data"], got[3]), 1e-12)
+
+
+def test_cuda_filtered_upper_policy_equals_what_the_reference_cosserat_driver_inserted():
+    """BASELINE config 4's driver (mfe_cosserat_elasticity_example_3.py ``four_field_scaled_approximation``, "wc_rt" at
+    k_order = 0, run by tools/make_reference_pins.py --cosserat-driver): its saddle-point matrix against
+    ``GPUAssembler(pattern_policy="filtered_upper", explicit_diagonal=True)`` on the same form list -- the case of
+    test_gpu_tensor_forms.py::test_example_driver_scatter_policies_cosserat[filtered_upper-True]."""
+    from tests.refcode_cases import cosserat_driver_cases
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_driver_mfe_cosserat.npz"))
+    case, _ = cosserat_driver_cases()
+    got = case.run_gpu(pattern_policy="filtered_upper", explicit_diagonal=True)
+    compare_csr(got, (fx["a_indptr"], fx["a_indices"], fx["a_data"], got[3]), 1e-12)

@@ -432,7 +432,55 @@ def driver_pin():
                         indices=indices, data=data, alpha=np.asarray(alpha), l2_error=np.asarray(errors), **mesh_numbering(gmesh))
 
 
+def cosserat_driver_pin():
+    """BASELINE config 4's driver itself: ``four_field_scaled_approximation`` of
+    R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py (:93-316, unmodified, "wc_rt" method at k_order = 0,
+    symmetric storage) over the stand-ins: the saddle-point matrix ``A`` and the Riesz-map preconditioner ``P`` exactly as its
+    scatter closures insert them, and the solution of its (here: direct) solve -> refcode_driver_mfe_cosserat.npz.  The
+    example's strong-solution module is replaced by the coefficient / boundary functions of tests/parity_helpers.py."""
+    import contextlib
+    import io
+    import types
+
+    from petsc4py import PETSc
+
+    from tests import refcode_cases as rc
+
+    case, riesz = rc.cosserat_driver_cases()
+    space0 = case.ref_space()
+    (_, _, functions, _), (_, _, bc_functions, _) = case.ref_forms_fn(space0)
+    stub = types.ModuleType("strong_solution_cosserat_elasticity_example_3")
+    stub.displacement = lambda material, dim: bc_functions["u"]
+    stub.rotation = lambda material, dim: bc_functions["t"]
+    unused = lambda material, dim: (lambda x, y, z: np.zeros((dim, dim)))  # noqa: E731  (post-processing only)
+    stub.stress = stub.couple_stress_scaled = stub.stress_divergence = stub.couple_stress_divergence_scaled = unused
+    stub.rhs_scaled = lambda material, dim: functions["rhs"]
+    stub.get_material_functions = lambda material, dim: {k: v for k, v in functions.items() if k != "rhs"}
+    sys.modules["strong_solution_cosserat_elasticity_example_3"] = stub
+    sys.path.insert(0, "/root/reference/examples/cosserat_elasticity")
+    import mfe_cosserat_elasticity_example_3 as driver
+
+    meshio.register("memory://cosserat", case.mesh.points, case.mesh._blocks)
+    method = next(iter(driver.method_definition(0)))
+    assert method[0] == "wc_rt"
+    with contextlib.redirect_stdout(io.StringIO()):
+        gmesh = driver.create_mesh_from_file("memory://cosserat", 3)
+        PETSc.ASSEMBLED.clear()
+        alpha, _ = driver.four_field_scaled_approximation(method, gmesh, symmetric_solver_q=True)
+    (a_ptr, a_idx, a_val), (p_ptr, p_idx, p_val) = [m.getValuesCSR() for m in PETSc.ASSEMBLED[-2:]]
+    want_a = case.run_oracle(upper=True, explicit_diagonal=True)
+    want_p = riesz.run_oracle(upper=True, explicit_diagonal=False)
+    for label, want, got in (("A", want_a, (a_ptr, a_idx, a_val)), ("P", want_p, (p_ptr, p_idx, p_val))):
+        same = np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1])
+        print("driver mfe_cosserat %s: nnz %d pattern_equal %s max_rel_values %s" % (
+            label, len(got[2]), same, float(np.abs(want[2] - got[2]).max() / np.abs(want[2]).max()) if same else None))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refcode_driver_mfe_cosserat.npz"), a_indptr=a_ptr,
+                        a_indices=a_idx, a_data=a_val, p_indptr=p_ptr, p_indices=p_idx, p_data=p_val, alpha=np.asarray(alpha))
+
+
 def main():
+    if sys.argv[1:] == ["--cosserat-driver"]:
+        return cosserat_driver_pin()
     if sys.argv[1:] == ["--driver"]:
         return driver_pin()
     if sys.argv[1:] == ["--verify-golden"]:

@@ -55,16 +55,34 @@ class Mat:
         return None
 
 
-class _PC:
-    def setType(self, name):
-        return None
+class _Permissive:
+    """Solver-configuration calls (types, tolerances, field splits, factor packages ...) are accepted and ignored: the
+    stand-in always solves directly."""
+
+    def __getattr__(self, name):
+        return lambda *args, **kwargs: None
 
 
-class KSP:
+class IS(_Permissive):
+    pass
+
+
+class PC(_Permissive):
+    class CompositeType:
+        ADDITIVE = "additive"
+
+    def getFieldSplitSubKSP(self):
+        return KSP(), KSP()
+
+
+_PC = PC
+
+
+class KSP(_Permissive):
     def create(self, comm=None):
         return self
 
-    def setOperators(self, A):
+    def setOperators(self, A, P=None):
         self.A = A
 
     def setType(self, name):
