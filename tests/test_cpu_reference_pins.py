@@ -131,7 +131,7 @@ def test_oracle_md_system_equals_the_reference_codes(name):
 
 def test_committed_golden_fixtures_are_the_ones_the_reference_code_reproduced():
     """``tools/make_reference_pins.py --verify-golden`` ran the reference's source on the reference's own gmsh files
-    (vector-P2 elasticity on example_3_3d_l_0 / l_1.msh: 298 and 1 325 tets of config 2's form list; four more systems on
+    (vector-P2 elasticity on example_3_3d_l_0 / l_1 / l_2.msh: 298, 1 325 and 4 261 tets of config 2's form list; four more systems on
     example_3_2d_l_0.msh) and compared with the ORACLE-made fixtures of tools/make_golden.py: same pattern, values and
     right-hand sides bit for bit (to round-off where the reference was run through its AD entry point and the oracle
     restates the vectorized one).  The recorded hashes tie that outcome to the files committed here."""
@@ -140,7 +140,13 @@ def test_committed_golden_fixtures_are_the_ones_the_reference_code_reproduced():
 
     with open(os.path.join(GOLDEN, "refcode_verified.json")) as f:
         verified = json.load(f)
-    assert len(verified) == 6
+    assert len(verified) == 7
+    probe = verified.pop("le_p2_ex3_3d_l2_probe.npz")  # 4 261 tets: fingerprint of the oracle's result
+    z = np.load(os.path.join(GOLDEN, "le_p2_ex3_3d_l2_probe.npz"))
+    assert hashlib.sha256(np.ascontiguousarray(z["rhs"]).tobytes()).hexdigest() == probe["sha256_rhs"]
+    assert hashlib.sha256(np.ascontiguousarray(z["KV"]).tobytes()).hexdigest() == probe["sha256_KV"]
+    assert probe["pattern_equal"] and probe["rhs_bit_identical"]
+    assert max(probe["max_rel_KV"], probe["max_rel_diag"], probe["max_rel_abs_row_sum"]) <= 1e-13
     for key, entry in verified.items():
         file_name, _, prefix = key.partition(":")
         z = np.load(os.path.join(GOLDEN, file_name))
