@@ -13,7 +13,10 @@ node_tags; :38-54 in 3-D: they do not ascend), since ``transformations["interval
 
 ``nedelec2`` does the same for the second-kind element of degree 1 ("N2E").
 
-PARITY UNPINNED against real basix (see oracle/ref_basis.py).
+PARITY: N1E of degree 1 is pinned against the reference's own pipeline (its ``FiniteElement`` covariant map and
+``permute_and_transform`` edge signs over a textbook Whitney table: tests/golden/refcode_projector_n1e_*.npz, agreement 5e-16);
+N2E has no counterpart run -- the reference's ``family_by_name("N2E")`` returns the N1E family (element_family.py:10).
+basix's own N1E scaling stays unpinned (see oracle/ref_basis.py).
 """
 import numpy as np
 
