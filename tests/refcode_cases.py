@@ -90,6 +90,35 @@ def cosserat_driver_cases():
             ph.tensor_mixed_case(kind="lce_scaled_riesz", dim=3, n=1, alpha=False, mesh=mesh))
 
 
+def transport_driver_problem():
+    """Mesh, coefficient / source functions and boundary data of what
+    R/examples/parabolic_diffusive_problem/mixed_transport_model.py ``four_fields_formulation`` solves in 3-D (:104-216):
+    manufactured p = c = t b(x) b(y) b(z), b(s) = s (1 - s), fluxes -grad p, unit kappa / delta / eta, delta_t = 0.1 up to
+    t = 1, on the jittered Kuhn box of six tetrahedra.  Returns ``(mesh, functions, bc_functions, delta_t, t_end)``."""
+    import numpy as np
+
+    from nfempy_b200.mesh import box_tet_mesh
+
+    b, db = (lambda s: s * (1.0 - s)), (lambda s: 1.0 - 2.0 * s)
+    scalar = lambda x, y, z, t: np.array([t * b(x) * b(y) * b(z)])  # noqa: E731
+    flux = lambda x, y, z, t: np.array([[-t * db(x) * b(y) * b(z), -t * b(x) * db(y) * b(z), -t * b(x) * b(y) * db(z)]])  # noqa: E731
+    source = lambda x, y, z, t: np.array([2.0 * t * (b(x) * b(y) + b(x) * b(z) + b(y) * b(z)) + b(x) * b(y) * b(z)])  # noqa: E731
+    delta_t, t_end, eta = 0.1, 1.0, 1.0
+    functions = {"rhs_f": source, "rhs_r": lambda x, y, z, t: source(x, y, z, t) + (1.0 + eta * scalar(x, y, z, t) ** 2),
+                 "kappa": lambda x, y, z: 1.0, "delta": lambda x, y, z: 1.0, "eta": lambda x, y, z: eta, "delta_t": delta_t}
+    bc_functions = {"mp": flux, "p": scalar, "mc": flux, "c": scalar}
+    return box_tet_mesh(1, jitter=0.2, shuffle_local_nodes=True), functions, bc_functions, delta_t, t_end
+
+
+def transport_space(space_class, mesh):
+    space = space_class({"mp": (3, 1, "RT", 1, mesh), "mc": (3, 1, "RT", 1, mesh), "p": (3, 1, "Lagrange", 0, mesh),
+                         "c": (3, 1, "Lagrange", 0, mesh)})
+    space.make_subspaces_discontinuous({"p": True, "c": True})
+    sides = [2, 3, 4, 5, 6, 7]
+    space.build_structures({f: [1] for f in ("mp", "mc", "p", "c")}, {"mp": sides, "mc": sides})
+    return space
+
+
 def projector_case(dim, fields):
     from tests.test_gpu_projector import _case
 

@@ -30,7 +30,7 @@ def _fixture(name):
 
 def test_every_case_has_its_fixture_and_nothing_else():
     have = {f[len("refcode_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("refcode_") and f.endswith(".npz")}
-    assert have == set(CASES) | set(MD_CASES) | {"driver_cg_elasticity", "driver_mfe_cosserat"}
+    assert have == set(CASES) | set(MD_CASES) | {"driver_cg_elasticity", "driver_mfe_cosserat", "driver_transport"}
 
 
 @pytest.mark.parametrize("name", sorted(set(CASES) - SKIP_ORACLE))
@@ -250,3 +250,49 @@ def test_oracle_equals_what_the_reference_cosserat_driver_assembled():
     upper = sp.csr_matrix((a[2], a[1], a[0]), shape=(n, n))
     full = upper + sp.triu(upper, 1).T
     assert np.abs(full @ fx["alpha"] + a[3]).max() <= 1e-9 * max(np.abs(a[3]).max(), 1.0)
+
+
+def test_oracle_time_loop_reproduces_the_reference_transport_driver():
+    """BASELINE config 5's driver (R/examples/parabolic_diffusive_problem/mixed_transport_model.py ``four_fields_formulation``,
+    run unmodified by tools/make_reference_pins.py --transport-driver; RT_1 x RT_1 x P_0 x P_0 on six tetrahedra): ten
+    implicit-Euler steps of Newton iterations on the Sundus forms, then the L2 errors at t = 1.  The same loop written with
+    the oracle's forms, scatter and error norms must arrive at the driver's final coefficients and at the numbers it reports.
+    Manufactured solution of the driver's 3-D branch (:177-216): p = c = t b(x) b(y) b(z), b(s) = s (1 - s), fluxes
+    -grad p, unit coefficients."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from oracle import ref_assembly, ref_forms, ref_postprocess
+    from oracle.ref_mesh import RefMesh
+    from oracle.ref_spaces import RefProductSpace
+
+    from tests.refcode_cases import transport_driver_problem, transport_space
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_driver_transport.npz"))
+    mesh, functions, bc_functions, delta_t, t_end = transport_driver_problem()
+    rmesh = RefMesh(3, mesh.points, mesh._blocks)
+    rmesh.build_conformal_mesh()
+    space = transport_space(RefProductSpace, rmesh)
+    n = space.n_dof
+    assert n == len(fx["alpha"])
+    mp = space.discrete_spaces["mp"]
+    forms = [("time_dependent_form", ref_forms.sundus_dual, functions, len(mp.element_ids)),
+             ("time_dependent_bc_form", ref_forms.sundus_dual_bc_dirichlet, bc_functions, len(mp.bc_element_ids))]
+    previous, newton_total = np.zeros(n), 0
+    for t in np.arange(delta_t, t_end + delta_t, delta_t):
+        iterate = previous.copy()
+        for _ in range(20):
+            indptr, indices, data, res = ref_assembly.assemble_time_dependent(space, forms, (iterate, previous), t)
+            if np.linalg.norm(res) < 1.0e-10:
+                break
+            iterate += spl.spsolve(sp.csr_matrix((data, indices, indptr), shape=(n, n)).tocsc(), -res)
+            newton_total += 1
+        else:
+            raise AssertionError("Newton did not converge at t = %g" % t)
+        previous = iterate
+    assert 10 <= newton_total <= 60
+    assert np.abs(previous - fx["alpha"]).max() <= 1e-9 * np.abs(fx["alpha"]).max()
+    at_end = {k: (lambda x, y, z, f=f: f(x, y, z, t_end)) for k, f in bc_functions.items()}
+    errors = ref_postprocess.l2_error(3, space, at_end, previous)
+    assert np.allclose(errors, fx["l2_errors"], rtol=1e-8, atol=0.0)
+    assert abs(errors[2] + errors[3] - float(fx["returned"])) <= 1e-8 * float(fx["returned"])

@@ -78,3 +78,42 @@ def test_cuda_filtered_upper_policy_equals_what_the_reference_cosserat_driver_in
     case, _ = cosserat_driver_cases()
     got = case.run_gpu(pattern_policy="filtered_upper", explicit_diagonal=True)
     compare_csr(got, (fx["a_indptr"], fx["a_indices"], fx["a_data"], got[3]), 1e-12)
+
+
+def test_cuda_time_loop_reproduces_the_reference_transport_driver():
+    """BASELINE config 5's driver (mixed_transport_model.py ``four_fields_formulation``, run by
+    tools/make_reference_pins.py --transport-driver): ten implicit-Euler steps of Newton iterations, every Jacobian and
+    residual assembled by the CUDA path through the drop-in call (time-dependent form types, row-owner kernels), linear solves
+    on the host -- the final coefficients must be the driver's."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    from nfempy_b200.assembly import GPUAssembler
+    from nfempy_b200.spaces import ProductSpace
+    from nfempy_b200.weak_forms import SundusDualWeakForm, SundusDualWeakFormBCDirichlet
+    from tests.refcode_cases import transport_driver_problem, transport_space
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_driver_transport.npz"))
+    mesh, functions, bc_functions, delta_t, t_end = transport_driver_problem()
+    space = transport_space(ProductSpace, mesh)
+    n = space.n_dof
+    wf, bf = SundusDualWeakForm(space), SundusDualWeakFormBCDirichlet(space)
+    wf.functions, bf.functions = functions, bc_functions
+    mp = space.discrete_spaces["mp"]
+    previous = np.zeros(n)
+    for t in np.arange(delta_t, t_end + delta_t, delta_t):
+        iterate = previous.copy()
+        for _ in range(20):
+            asm = GPUAssembler(space, None, np.zeros(n))
+            asm.form_to_input_list = {
+                "volume": ["time_dependent_form", range(len(mp.elements)), wf, (iterate, previous), t],
+                "bc": ["time_dependent_bc_form", range(len(mp.bc_elements)), bf, (iterate, previous), t],
+            }
+            indptr, indices, data, res = asm.assemble()
+            if np.linalg.norm(res) < 1.0e-10:
+                break
+            iterate = iterate + spl.spsolve(sp.csr_matrix((data, indices, indptr), shape=(n, n)).tocsc(), -res)
+        else:
+            raise AssertionError("Newton did not converge at t = %g" % t)
+        previous = iterate
+    assert np.abs(previous - fx["alpha"]).max() <= 1e-9 * np.abs(fx["alpha"]).max()

@@ -497,7 +497,48 @@ def cosserat_driver_pin():
                         a_indices=a_idx, a_data=a_val, p_indptr=p_ptr, p_indices=p_idx, p_data=p_val, alpha=np.asarray(alpha))
 
 
+def transport_driver_pin():
+    """BASELINE config 5's driver itself: ``four_fields_formulation`` of
+    R/examples/parabolic_diffusive_problem/mixed_transport_model.py (:104-387, unmodified; method "mixed_rt" at k_order = 0 =
+    RT_1 x RT_1 x P_0 x P_0): ten implicit-Euler steps, each a Newton loop that re-assembles the Sundus forms into the SAME
+    matrix (``scale(0.0)`` + ADD_VALUES) until the residual norm drops below 1e-10, then the L2 errors at t = 1 -- on the
+    jittered Kuhn box of six tetrahedra.  Kept: the final coefficient vector, the four L2 errors, the returned number ->
+    tests/golden/refcode_driver_transport.npz.  (``gmsh`` is an empty stand-in: the driver's mesher is not used.)"""
+    import contextlib
+    import io
+    import types
+
+    from nfempy_b200.mesh import box_tet_mesh
+
+    sys.modules.setdefault("gmsh", types.ModuleType("gmsh"))
+    sys.path.insert(0, "/root/reference/examples/parabolic_diffusive_problem")
+    import mixed_transport_model as driver
+
+    mesh = box_tet_mesh(1, jitter=0.2, shuffle_local_nodes=True)
+    meshio.register("memory://transport", mesh.points, mesh._blocks)
+    kept = {}
+    true_l2_error = driver.l2_error
+
+    def l2_error(dim, fe_space, functions, alpha):
+        kept["alpha"], kept["errors"] = np.array(alpha), np.array(true_l2_error(dim, fe_space, functions, alpha))
+        return kept["errors"]
+
+    driver.l2_error = l2_error
+    method = next(iter(driver.method_definition(0)))
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        gmesh = driver.Mesh(dimension=3, file_name="memory://transport")
+        gmesh.build_conformal_mesh()
+        returned = driver.four_fields_formulation(method, gmesh)
+    print("driver mixed_transport_model: n_dof %d, L2 errors %s, returned %.12e (%.0f s)" % (
+        len(kept["alpha"]), kept["errors"], returned, time.perf_counter() - t0))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refcode_driver_transport.npz"), alpha=kept["alpha"],
+                        l2_errors=kept["errors"], returned=np.array(returned))
+
+
 def main():
+    if sys.argv[1:] == ["--transport-driver"]:
+        return transport_driver_pin()
     if sys.argv[1:] == ["--cosserat-driver"]:
         return cosserat_driver_pin()
     if sys.argv[1:] == ["--driver"]:

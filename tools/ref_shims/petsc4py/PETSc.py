@@ -32,6 +32,10 @@ class Mat:
     def assemble(self):
         ASSEMBLED.append(self)
 
+    def scale(self, factor):
+        for key in self.entries:
+            self.entries[key] *= float(factor)
+
     def getInfo(self):
         nz = float(len(self.entries))
         return {"nz_allocated": nz, "nz_used": nz, "nz_unneeded": 0.0}
