@@ -77,6 +77,47 @@ def driver_case():
                    ref_forms_fn)
 
 
+def driver_pressure(m_lambda, m_mu, dim=2):
+    """Takes the place of strong_solution_elasticity_example_1.pressure while the reference's driver runs."""
+    import numpy as np
+
+    return lambda x, y, z: np.array([m_lambda * (x - y) + m_mu * np.cos(z)])
+
+
+def taylor_hood_driver_case(dim=2):
+    """What R/examples/cauchy_elasticity/th_elasticity_example_1.py ``mixed_approximation`` assembles with its method at
+    k_order = 2 (u in P_2, p in discontinuous P_0; volume tags [1, 2, 3, 4], Dirichlet penalty on [5, 6, 7, 8]) through its
+    own closures: entries with ``~isclose(v, 1e-16)`` (full storage, "filtered"), explicit diagonal zeros (:99-145).  2-D:
+    the reference's Taylor-Hood form refuses tetrahedra (``assert False``, le_taylor_hood_weak_form.py:133-135); one side of
+    the jittered square carries a boundary tag of the driver's list."""
+    import numpy as np
+
+    from nfempy_b200.mesh import square_tri_mesh
+    from oracle import ref_h1_multi
+
+    lam, mu = DRIVER_MATERIAL["lambda"], DRIVER_MATERIAL["mu"]
+    functions = {"rhs": driver_rhs(lam, mu, dim), "lambda": lambda x, y, z: lam * np.ones_like(x),
+                 "mu": lambda x, y, z: mu * np.ones_like(x)}
+    bc_functions = {"u": driver_displacement(lam, mu, dim), "p": driver_pressure(lam, mu, dim)}
+
+    def gpu_forms(space, a):
+        from nfempy_b200.weak_forms import LETaylorHoodWeakForm, LETaylorHoodWeakFormBCDirichlet
+
+        wf, bf = LETaylorHoodWeakForm(space), LETaylorHoodWeakFormBCDirichlet(space)
+        wf.functions, bf.functions = functions, bc_functions
+        u = space.discrete_spaces["u"]
+        return {"volume": ["form", range(len(u.elements)), wf, a], "bc": ["bc_form", range(len(u.bc_elements)), bf, a]}
+
+    def ref_forms_fn(space):
+        u = space.discrete_spaces["u"]
+        return [("form", ref_h1_multi.le_taylor_hood, functions, len(u.element_ids)),
+                ("bc_form", ref_h1_multi.le_taylor_hood_bc_dirichlet, bc_functions, len(u.bc_element_ids))]
+
+    mesh = square_tri_mesh(3, jitter=0.2)
+    return ph.Case(mesh, lambda g: {"u": (dim, dim, "Lagrange", 2, g), "p": (dim, 1, "Lagrange", 0, g)},
+                   {"u": [1, 2, 3, 4], "p": [1, 2, 3, 4]}, {"u": [5, 6, 7, 8]}, gpu_forms, ref_forms_fn, disc={"p": True})
+
+
 def cosserat_driver_cases():
     """(saddle-point case, Riesz-map case) of what R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py
     ``four_field_scaled_approximation`` assembles with its method "wc_rt" at k_order = 0 (BDM_1 x RT_1 x P_0 x P_0) on the

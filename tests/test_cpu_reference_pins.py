@@ -30,7 +30,8 @@ def _fixture(name):
 
 def test_every_case_has_its_fixture_and_nothing_else():
     have = {f[len("refcode_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("refcode_") and f.endswith(".npz")}
-    assert have == set(CASES) | set(MD_CASES) | {"driver_cg_elasticity", "driver_mfe_cosserat", "driver_transport"}
+    assert have == set(CASES) | set(MD_CASES) | {"driver_cg_elasticity", "driver_mfe_cosserat", "driver_transport",
+                                                       "driver_th_elasticity"}
 
 
 @pytest.mark.parametrize("name", sorted(set(CASES) - SKIP_ORACLE))
@@ -296,3 +297,29 @@ def test_oracle_time_loop_reproduces_the_reference_transport_driver():
     errors = ref_postprocess.l2_error(3, space, at_end, previous)
     assert np.allclose(errors, fx["l2_errors"], rtol=1e-8, atol=0.0)
     assert abs(errors[2] + errors[3] - float(fx["returned"])) <= 1e-8 * float(fx["returned"])
+
+
+def test_oracle_filtered_scatter_equals_what_the_reference_taylor_hood_driver_inserted():
+    """R/examples/cauchy_elasticity/th_elasticity_example_1.py ``mixed_approximation`` (run unmodified by
+    tools/make_reference_pins.py --th-driver, u in P_2, p in discontinuous P_0, 2-D): the "filtered" policy with explicit
+    diagonal zeros in full storage, as its closures fill the matrix (:99-145), against the oracle's ``assemble_filtered``;
+    the driver's solution solves the oracle's system."""
+    import scipy.sparse as sp
+
+    from tests.refcode_cases import taylor_hood_driver_case
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_driver_th_elasticity.npz"))
+    case = taylor_hood_driver_case()
+    indptr, indices, data, rhs = case.run_oracle(upper=False, explicit_diagonal=True)
+    assert np.array_equal(indptr, fx["indptr"]) and np.array_equal(indices, fx["indices"])
+    assert np.abs(data - fx["data"]).max() <= 1e-13 * np.abs(fx["data"]).max()
+    n = len(rhs)
+    K = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    assert np.abs(K @ fx["alpha"] + rhs).max() <= 1e-9 * np.abs(rhs).max()
+    # the product's host layer on the driver's spaces and tag lists
+    space, rspace = case.space(), case.ref_space()
+    assert space.n_dof == n
+    for i in range(len(space.discrete_spaces["u"].elements)):
+        assert np.array_equal(space.destination_indexes(i), rspace.destination_indexes(i))
+    for i in range(len(space.discrete_spaces["u"].bc_elements)):
+        assert np.array_equal(space.bc_destination_indexes(i), rspace.bc_destination_indexes(i))

@@ -451,6 +451,41 @@ def driver_pin():
                         indices=indices, data=data, alpha=np.asarray(alpha), l2_error=np.asarray(errors), **mesh_numbering(gmesh))
 
 
+def taylor_hood_driver_pin():
+    """``mixed_approximation`` of R/examples/cauchy_elasticity/th_elasticity_example_1.py, unmodified, method at k_order = 2:
+    the matrix its closures fill ("filtered" policy with explicit diagonal zeros, full storage) and its solution ->
+    tests/golden/refcode_driver_th_elasticity.npz."""
+    import contextlib
+    import io
+    import types
+
+    from petsc4py import PETSc
+
+    from tests import refcode_cases as rc
+
+    stub = types.ModuleType("strong_solution_elasticity_example_1")
+    stub.displacement, stub.rhs, stub.pressure = rc.driver_displacement, rc.driver_rhs, rc.driver_pressure
+    sys.modules["strong_solution_elasticity_example_1"] = stub
+    sys.path.insert(0, "/root/reference/examples/cauchy_elasticity")
+    import th_elasticity_example_1 as driver
+
+    case = rc.taylor_hood_driver_case()
+    meshio.register("memory://th", case.mesh.points, case.mesh._blocks)
+    method = next(iter(driver.method_definition(2)))
+    with contextlib.redirect_stdout(io.StringIO()):
+        gmesh = driver.create_mesh_from_file("memory://th", 2)
+        PETSc.ASSEMBLED.clear()
+        alpha = driver.mixed_approximation(rc.DRIVER_MATERIAL, method, gmesh)
+    alpha = alpha[0] if isinstance(alpha, tuple) else alpha
+    indptr, indices, data = PETSc.ASSEMBLED[-1].getValuesCSR()
+    want = case.run_oracle(upper=False, explicit_diagonal=True)
+    same = np.array_equal(want[0], indptr) and np.array_equal(want[1], indices)
+    print("driver th_elasticity_example_1: n_dof %d nnz %d pattern_equal %s max_rel_values %s" % (
+        len(want[3]), len(data), same, float(np.abs(want[2] - data).max() / np.abs(want[2]).max()) if same else None))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refcode_driver_th_elasticity.npz"), indptr=indptr,
+                        indices=indices, data=data, alpha=np.asarray(alpha))
+
+
 def cosserat_driver_pin():
     """BASELINE config 4's driver itself: ``four_field_scaled_approximation`` of
     R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py (:93-316, unmodified, "wc_rt" method at k_order = 0,
@@ -537,6 +572,8 @@ def transport_driver_pin():
 
 
 def main():
+    if sys.argv[1:] == ["--th-driver"]:
+        return taylor_hood_driver_pin()
     if sys.argv[1:] == ["--transport-driver"]:
         return transport_driver_pin()
     if sys.argv[1:] == ["--cosserat-driver"]:
