@@ -118,6 +118,29 @@ def taylor_hood_driver_case(dim=2):
                    {"u": [1, 2, 3, 4], "p": [1, 2, 3, 4]}, {"u": [5, 6, 7, 8]}, gpu_forms, ref_forms_fn, disc={"p": True})
 
 
+def mixed_elasticity_driver_cases():
+    """(saddle-point case, Riesz-map case) of what R/examples/cauchy_elasticity/mfe_elasticity_example_1.py
+    ``three_field_approximation`` assembles with its method at k_order = 0 (s in BDM_1 rows, u, t in discontinuous P_0) on the
+    jittered Kuhn box of six tetrahedra: constant Lame parameters from its material table, volume tags [1, 2, 3, 4], natural
+    boundary form on the tags [5, 6, 7, 8]; ``A`` from LEDualWeakForm through the driver's closure (filtered, upper, explicit
+    diagonal zeros), ``P`` from LERieszMapWeakForm (filtered, upper)."""
+    import numpy as np
+
+    from nfempy_b200.mesh import box_tet_mesh
+
+    mesh = box_tet_mesh(1, jitter=0.2, shuffle_local_nodes=True)
+    out = []
+    for kind in ("le", "le_riesz"):
+        case = ph.tensor_mixed_case(kind=kind, dim=3, n=1, alpha=False, mesh=mesh)
+        case.tags = {name: [1, 2, 3, 4] for name in ("s", "u", "t")}
+        case.btags = {"s": [5, 6, 7, 8]}
+        functions = case.ref_forms_fn(case.ref_space())[0][2]  # the dict both form lists of the case share
+        functions["lambda"] = lambda x, y, z: DRIVER_MATERIAL["lambda"] * np.ones_like(x)
+        functions["mu"] = lambda x, y, z: DRIVER_MATERIAL["mu"] * np.ones_like(x)
+        out.append(case)
+    return tuple(out)
+
+
 def cosserat_driver_cases():
     """(saddle-point case, Riesz-map case) of what R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py
     ``four_field_scaled_approximation`` assembles with its method "wc_rt" at k_order = 0 (BDM_1 x RT_1 x P_0 x P_0) on the

@@ -31,7 +31,7 @@ def _fixture(name):
 def test_every_case_has_its_fixture_and_nothing_else():
     have = {f[len("refcode_"):-len(".npz")] for f in os.listdir(GOLDEN) if f.startswith("refcode_") and f.endswith(".npz")}
     assert have == set(CASES) | set(MD_CASES) | {"driver_cg_elasticity", "driver_mfe_cosserat", "driver_transport",
-                                                       "driver_th_elasticity"}
+                                                       "driver_th_elasticity", "driver_mfe_elasticity"}
 
 
 @pytest.mark.parametrize("name", sorted(set(CASES) - SKIP_ORACLE))
@@ -322,4 +322,30 @@ def test_oracle_filtered_scatter_equals_what_the_reference_taylor_hood_driver_in
     for i in range(len(space.discrete_spaces["u"].elements)):
         assert np.array_equal(space.destination_indexes(i), rspace.destination_indexes(i))
     for i in range(len(space.discrete_spaces["u"].bc_elements)):
+        assert np.array_equal(space.bc_destination_indexes(i), rspace.bc_destination_indexes(i))
+
+
+def test_oracle_equals_what_the_reference_mixed_elasticity_driver_assembled():
+    """R/examples/cauchy_elasticity/mfe_elasticity_example_1.py ``three_field_approximation`` (run unmodified by
+    tools/make_reference_pins.py --mfe-driver; BDM_1 rows x P_0 x P_0, symmetric storage): ``A`` from
+    ``LEDualWeakForm.evaluate_form_vectorized`` (filtered, upper, explicit diagonal zeros; natural boundary form on the tags
+    [5, 6, 7, 8]) and ``P`` from ``LERieszMapWeakForm`` (filtered, upper), against the oracle's ``assemble_filtered``; the
+    driver's solution solves the oracle's system."""
+    import scipy.sparse as sp
+
+    from tests.refcode_cases import mixed_elasticity_driver_cases
+
+    fx = np.load(os.path.join(GOLDEN, "refcode_driver_mfe_elasticity.npz"))
+    case, riesz = mixed_elasticity_driver_cases()
+    a = case.run_oracle(upper=True, explicit_diagonal=True)
+    p = riesz.run_oracle(upper=True, explicit_diagonal=False)
+    for got, key in ((a, "a"), (p, "p")):
+        assert np.array_equal(got[0], fx[key + "_indptr"]) and np.array_equal(got[1], fx[key + "_indices"])
+        assert np.abs(got[2] - fx[key + "_data"]).max() <= 1e-13 * np.abs(fx[key + "_data"]).max()
+    n = len(a[3])
+    upper = sp.csr_matrix((a[2], a[1], a[0]), shape=(n, n))
+    full = upper + sp.triu(upper, 1).T
+    assert np.abs(full @ fx["alpha"] + a[3]).max() <= 1e-9 * max(np.abs(a[3]).max(), 1.0)
+    space, rspace = case.space(), case.ref_space()
+    for i in range(len(space.discrete_spaces["s"].bc_elements)):
         assert np.array_equal(space.bc_destination_indexes(i), rspace.bc_destination_indexes(i))

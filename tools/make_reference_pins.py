@@ -486,6 +486,49 @@ def taylor_hood_driver_pin():
                         indices=indices, data=data, alpha=np.asarray(alpha))
 
 
+def mixed_elasticity_driver_pin():
+    """``three_field_approximation`` of R/examples/cauchy_elasticity/mfe_elasticity_example_1.py (:68-294, unmodified, method
+    at k_order = 0, symmetric storage): ``A`` (LEDualWeakForm + the natural boundary form) and ``P`` (LERieszMapWeakForm) as
+    its closures fill them, and its solution -> tests/golden/refcode_driver_mfe_elasticity.npz."""
+    import contextlib
+    import io
+    import types
+
+    from petsc4py import PETSc
+
+    from tests import refcode_cases as rc
+
+    case, riesz = rc.mixed_elasticity_driver_cases()
+    forms = case.ref_forms_fn(case.ref_space())
+    functions, bc_functions = forms[0][2], forms[1][2]
+    stub = types.ModuleType("strong_solution_elasticity_example_1")
+    stub.displacement = lambda m_lambda, m_mu, dim: bc_functions["u"]
+    stub.rotation = lambda m_lambda, m_mu, dim: bc_functions["t"]
+    stub.stress = lambda m_lambda, m_mu, dim: (lambda x, y, z: np.zeros((dim, dim)))
+    stub.stress_divergence = stub.stress
+    stub.rhs = lambda m_lambda, m_mu, dim: functions["rhs"]
+    sys.modules["strong_solution_elasticity_example_1"] = stub
+    sys.path.insert(0, "/root/reference/examples/cauchy_elasticity")
+    import mfe_elasticity_example_1 as driver
+
+    meshio.register("memory://mfe", case.mesh.points, case.mesh._blocks)
+    method = next(iter(driver.method_definition(0)))
+    with contextlib.redirect_stdout(io.StringIO()):
+        gmesh = driver.create_mesh_from_file("memory://mfe", 3)
+        PETSc.ASSEMBLED.clear()
+        result = driver.three_field_approximation(rc.DRIVER_MATERIAL, method, gmesh, symmetric_solver_q=True)
+    alpha = result[0] if isinstance(result, tuple) else result
+    (a_ptr, a_idx, a_val), (p_ptr, p_idx, p_val) = [m.getValuesCSR() for m in PETSc.ASSEMBLED[-2:]]
+    want_a = case.run_oracle(upper=True, explicit_diagonal=True)
+    want_p = riesz.run_oracle(upper=True, explicit_diagonal=False)
+    for label, want, got in (("A", want_a, (a_ptr, a_idx, a_val)), ("P", want_p, (p_ptr, p_idx, p_val))):
+        same = np.array_equal(want[0], got[0]) and np.array_equal(want[1], got[1])
+        print("driver mfe_elasticity %s: nnz %d pattern_equal %s max_rel_values %s" % (
+            label, len(got[2]), same, float(np.abs(want[2] - got[2]).max() / np.abs(want[2]).max()) if same else None))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "refcode_driver_mfe_elasticity.npz"), a_indptr=a_ptr,
+                        a_indices=a_idx, a_data=a_val, p_indptr=p_ptr, p_indices=p_idx, p_data=p_val, alpha=np.asarray(alpha))
+
+
 def cosserat_driver_pin():
     """BASELINE config 4's driver itself: ``four_field_scaled_approximation`` of
     R/examples/cosserat_elasticity/mfe_cosserat_elasticity_example_3.py (:93-316, unmodified, "wc_rt" method at k_order = 0,
@@ -572,6 +615,8 @@ def transport_driver_pin():
 
 
 def main():
+    if sys.argv[1:] == ["--mfe-driver"]:
+        return mixed_elasticity_driver_pin()
     if sys.argv[1:] == ["--th-driver"]:
         return taylor_hood_driver_pin()
     if sys.argv[1:] == ["--transport-driver"]:
