@@ -179,7 +179,11 @@ def run_reference(args):
     n_full = 6 * args.n**3
     sample = ("ORACLE PORT, not nfempy itself (basix / auto_diff / petsc4py are absent here): %d tets per step = the first "
               "tets of a %d^3-cube jittered Kuhn box (same generator and seed as the %d^3 bench box, smaller so that the "
-              "dict-based oracle mesh builds in seconds), split over %d worker processes, throughput extrapolated per tet"
+              "dict-based oracle mesh builds in seconds), split over %d worker processes, throughput extrapolated per tet.  "
+              "The port's results equal the reference's own source bit for bit (tests/test_cpu_reference_pins.py), its "
+              "speed does not: that source, run in the build container over stand-ins for basix / auto_diff / PETSc, did "
+              "114 tets/s on one core where this port did 25 (the port differentiates by 30 residual sweeps per cell, "
+              "the reference by one sweep on dual numbers) -- divide any ratio against this arm by about 4.5"
               % (per_step, n_box, args.n, cores))
     line = {
         "impl": "reference", "metric": "elements/s assembled (3D elasticity p=2)", "value": value, "unit": "elements/s",
@@ -495,7 +499,8 @@ def run_graft(args):
         v, cells, wall = cpu_baseline(min(args.n, 12), args.cpu_cells, 1)
         cpu = {"value": v, "unit": "elements/s", "cores": 1, "kind": "port",
                "sample": "%d tets of the same jittered Kuhn box, oracle port (cell-by-cell numpy restatement of the "
-                         "reference, dict-of-keys scatter), %.1f s" % (cells, wall)}
+                         "reference, dict-of-keys scatter), %.1f s; the reference's own source over stand-ins is about "
+                         "4.5 x faster per core than this port (DESIGN.md section 6)" % (cells, wall)}
     cpu_strong = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cells, wall = cpu_strong_baseline(space, 40000)
