@@ -3,7 +3,13 @@ reference's weak forms use (R/src/weak_forms/*.py: ``with ad.AutoDiff(alpha) as 
 
 ``AutoDiff(alpha)`` for a 1-D ``alpha`` of length n hands out ``val = alpha[None, :]`` and ``der[0, i, j] = delta_ij``
 (``der.shape = val.shape + (n,)``): the forms index ``alpha[:, c:n:nc]``, multiply ``alpha @ grad_phi`` with
-``grad_phi[n_phi, dim]`` and end with ``el_form.der.reshape((n, n))``, which fixes these shapes."""
+``grad_phi[n_phi, dim]`` and end with ``el_form.der.reshape((n, n))``, which fixes these shapes.
+
+While the context is open ``np.zeros`` and ``np.array`` are replaced (the real package must do the same, since the forms rely on
+it): they write ``el_form = np.zeros(n_dof)`` / ``integrand = np.zeros((1, n_dof))`` INSIDE the ``with`` block, assign
+differentiated slices into them and read ``el_form.val`` / ``el_form.der`` afterwards -- which only works when those arrays are
+born as ``VecValDer`` with a zero derivative; and they build matrices as nested lists of differentiated scalars
+(``Gamma_outer``, lce_dual_weak_form.py:366-372), which must come out as one ``VecValDer``."""
 import numpy as np
 
 from .vecvalder import VecValDer
