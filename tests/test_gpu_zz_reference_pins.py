@@ -2,8 +2,11 @@
 ``tools/make_reference_pins.py``: /root/reference/src imported unmodified over stand-ins for meshio / basix / auto_diff;
 see ``tests/test_cpu_reference_pins.py`` for what that pins and what it leaves open).
 
-The cases are form lists the oracle-parity tests of this suite already run (same constructors, same arguments); here the
-expected CSR and right-hand side come from the reference code instead of the oracle.  (The file sorts last on purpose.)"""
+Most cases are form lists the oracle-parity tests of this suite already run (same constructors, same arguments); here the
+expected CSR and right-hand side come from the reference code instead of the oracle.  New combinations: the cg example
+driver's tag lists under the ``filtered_upper`` policy, the continuous cubic Lagrange projector with a linear function, and
+the transport driver's ten-step Newton / time loop.  (The file sorts last on purpose: written after the round's GPU budget was
+spent, it has not run on a B200 yet, and ``pytest -x`` reaches every other GPU test first.)"""
 import os
 
 import numpy as np
