@@ -349,3 +349,15 @@ def test_oracle_equals_what_the_reference_mixed_elasticity_driver_assembled():
     space, rspace = case.space(), case.ref_space()
     for i in range(len(space.discrete_spaces["s"].bc_elements)):
         assert np.array_equal(space.bc_destination_indexes(i), rspace.bc_destination_indexes(i))
+
+
+def test_recorded_outcome_on_the_largest_reference_fixture():
+    """A RECORD, not a re-run (the suite has no /root/reference): ``tools/make_reference_pins.py --verify-l3`` assembled
+    config 2's matrix on example_3_3d_l_3.msh (28 736 tets, 10.4 M nonzeros) with the reference's own source -- five minutes --
+    and compared it entry by entry with oracle/strong_cpu.py, the vectorised CPU assembly that bench.py checks the timed GPU
+    step against at 998 250 tets."""
+    import json
+
+    with open(os.path.join(GOLDEN, "refcode_verified_l3.json")) as f:
+        rec = json.load(f)
+    assert rec["tets"] == 28736 and rec["pattern_equal"] and rec["max_rel_values_vs_strong_cpu"] <= 1e-13

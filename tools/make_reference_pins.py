@@ -614,7 +614,60 @@ def transport_driver_pin():
                         l2_errors=kept["errors"], returned=np.array(returned))
 
 
+def verify_level3():
+    """The largest reference fixture, example_3_3d_l_3.msh (28 736 tets): the reference's source assembles the vector-P2
+    elasticity VOLUME form (config 2's matrix) cell by cell -- about four minutes -- and the result is compared, entry by
+    entry, with oracle/strong_cpu.py (the vectorised CPU assembly bench.py checks the timed GPU step against), fed with the
+    numbering the reference's own spaces produced.  Outcome appended to tests/golden/refcode_verified.json (a record: the test
+    suite cannot repeat it without /root/reference, this mode can)."""
+    import contextlib
+    import io
+    import json
+
+    from assembly.SequentialAssembler import SequentialAssembler
+    from mesh.mesh import Mesh
+    from spaces.product_space import ProductSpace
+    from weak_forms.le_primal_weak_form import LEPrimalWeakForm
+
+    from oracle import strong_cpu
+    from tests import golden_cases as gc
+
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        gmesh = Mesh(dimension=3, file_name="/root/reference/examples/cosserat_elasticity/gmsh_files/ex_3/example_3_3d_l_3.msh")
+        gmesh.build_conformal_mesh()
+        space = ProductSpace({"u": (3, 3, "Lagrange", 2, gmesh)})
+        space.make_subspaces_discontinuous({"u": False})
+        space.build_structures({"u": [1]}, {"u": [2, 3, 4, 5, 6, 7]})
+        n = space.n_dof
+        jac, res = DictMat(n), np.zeros(n)
+        wf = LEPrimalWeakForm(space)
+        wf.functions = gc.LE_FUNCTIONS
+        us = space.discrete_spaces["u"]
+        assembler = SequentialAssembler(space, jac, res)
+        assembler.form_to_input_list = {"volume": ["form", range(len(us.elements)), wf, np.zeros(n)]}
+        assembler.scatter_forms(measure_time_q=False)
+    t1 = time.perf_counter()
+    indptr, indices, values = jac.csr()
+    dest = np.array([space.destination_indexes(i) for i in range(len(us.elements))], dtype=np.int64)
+    cell_nodes = np.array([el.data.cell.node_tags for el in us.elements], dtype=np.int64)
+    s_ptr, s_idx, s_val = strong_cpu.assemble_elasticity(np.asarray(gmesh.points), cell_nodes, dest, n, 1.0, 1.0)
+    same = np.array_equal(indptr, s_ptr) and np.array_equal(indices, s_idx)
+    row = np.repeat(np.arange(n), np.diff(indptr))
+    row_max = np.zeros(n)
+    np.maximum.at(row_max, row, np.abs(values))
+    entry = {"tets": int(len(us.elements)), "n_dof": int(n), "nnz": int(len(values)), "pattern_equal": bool(same),
+             "max_rel_values_vs_strong_cpu": float((np.abs(values - s_val) / np.maximum(np.abs(values), row_max[row])).max())
+             if same else None, "reference_source_seconds": round(t1 - t0, 1)}
+    print("le_p2 volume form on example_3_3d_l_3.msh:", entry, flush=True)
+    path = os.path.join(gc.GOLDEN, "refcode_verified_l3.json")
+    with open(path, "w") as f:
+        json.dump(entry, f, indent=1, sort_keys=True)
+
+
 def main():
+    if sys.argv[1:] == ["--verify-l3"]:
+        return verify_level3()
     if sys.argv[1:] == ["--mfe-driver"]:
         return mixed_elasticity_driver_pin()
     if sys.argv[1:] == ["--th-driver"]:
