@@ -4,6 +4,12 @@ tests/parity_helpers.py, so product, oracle and reference code see the same mesh
 from tests import parity_helpers as ph
 
 
+def _gmsh_fixture(dim, level=0):
+    from tests.golden_cases import fixture_mesh
+
+    return fixture_mesh(dim, level)
+
+
 def hcurl_projector_case(dim):
     """N1E of degree 1 through L2ProjectorWeakForm, as tests/test_gpu_projector.py::test_hcurl_projector_matches_oracle."""
     import numpy as np
@@ -203,6 +209,9 @@ def cases():
         "poisson_bdm2_3d": lambda: ph.mixed_poisson_case(dim=3, k=2, n=1, family="BDM"),
         "poisson_bdm3_3d": lambda: ph.mixed_poisson_case(dim=3, k=3, n=1, family="BDM"),
         "poisson_bdm3_3d_varying": lambda: ph.mixed_poisson_case(dim=3, k=3, n=1, family="BDM", varying=True),
+        # on the reference's own unstructured gmsh fixture (example_3_3d_l_0.msh, 298 tets: arbitrary face orientations)
+        "poisson_rt2_gmsh3d": lambda: ph.mixed_poisson_case(dim=3, k=2, varying=True, mesh=_gmsh_fixture(3)),
+        "sundus_rt1_gmsh3d": lambda: ph.SundusCase(dim=3, k=1, mesh=_gmsh_fixture(3)),
         "poisson_bdm1_2d": lambda: ph.mixed_poisson_case(dim=2, k=1, n=3, family="BDM"),
         "degenerate_rt1_3d": lambda: ph.degenerate_case(kind="degenerate", dim=3, k=1, n=2),
         "degenerate_rt2_2d": lambda: ph.degenerate_case(kind="degenerate", dim=2, k=2, n=3),
